@@ -1,0 +1,112 @@
+"""ctypes binding of libafmg.so (C ABI: include/afmg.h).
+
+The library is the product; this module only loads it.  There is no CPU fallback: if the
+shared library is missing the import of the solver fails loudly, and without a CUDA device
+``afmg_create`` returns AFMG_ERR_CUDA.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libafmg.so")
+
+AFMG_OK = 0
+ERR_NAMES = {-1: "AFMG_ERR_ARG", -2: "AFMG_ERR_CUDA", -3: "AFMG_ERR_UNSUPPORTED", -4: "AFMG_ERR_STATE",
+             -5: "AFMG_ERR_SINGULAR", -6: "AFMG_ERR_NCCL"}
+
+
+class AfmgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Opts(C.Structure):
+    _fields_ = [
+        ("ndim", C.c_int32), ("n_cell", C.c_int32), ("coord_t", C.c_int32), ("n_cycle_down", C.c_int32),
+        ("n_cycle_up", C.c_int32), ("use_corners", C.c_int32), ("subtract_mean", C.c_int32),
+        ("prolongation_type", C.c_int32), ("operator_mask", C.c_int32), ("has_eps", C.c_int32),
+        ("device", C.c_int32), ("reserved", C.c_int32), ("helmholtz_lambda", C.c_double),
+        ("lsf_boundary_value", C.c_double), ("coarse_grid_size", C.c_int32 * 3), ("periodic", C.c_int32 * 3),
+        ("dr_base", C.c_double * 3), ("r_base", C.c_double * 3),
+    ]
+
+
+class TreeDesc(C.Structure):
+    _fields_ = [
+        ("highest_lvl", C.c_int32), ("highest_id", C.c_int32), ("lvl_counts", C.POINTER(C.c_int32)),
+        ("lvl_ids", C.POINTER(C.c_int32)), ("lvl", C.POINTER(C.c_int32)), ("ix", C.POINTER(C.c_int32)),
+        ("parent", C.POINTER(C.c_int32)), ("children", C.POINTER(C.c_int32)),
+        ("neighbors", C.POINTER(C.c_int32)), ("neighbor_mat", C.POINTER(C.c_int32)),
+        ("r_min", C.POINTER(C.c_double)),
+    ]
+
+
+# every symbol include/afmg.h declares: name -> (restype, argtypes)
+_H = C.c_void_p
+_I = C.c_int32
+_IP = C.POINTER(C.c_int32)
+_DP = C.POINTER(C.c_double)
+SYMBOLS = {
+    "afmg_create": (C.c_int, [C.POINTER(_H), C.POINTER(Opts)]),
+    "afmg_destroy": (C.c_int, [_H]),
+    "afmg_last_error": (C.c_char_p, [_H]),
+    "afmg_set_tree": (C.c_int, [_H, C.POINTER(TreeDesc)]),
+    "afmg_set_bc": (C.c_int, [_H, _I, _IP, _IP, _IP, _DP]),
+    "afmg_set_helmholtz_lambda": (C.c_int, [_H, C.c_double]),
+    "afmg_set_lsf_boundary_value": (C.c_int, [_H, C.c_double]),
+    "afmg_set_lsf_distances": (C.c_int, [_H, _I, _IP, _DP]),
+    "afmg_update_operator_stencil": (C.c_int, [_H]),
+    "afmg_upload": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
+    "afmg_download": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
+    "afmg_upload_device": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
+    "afmg_download_device": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
+    "afmg_clear": (C.c_int, [_H, _I]),
+    "afmg_fas_fmg": (C.c_int, [_H, _I, _I]),
+    "afmg_fas_vcycle": (C.c_int, [_H, _I, _I, _I]),
+    "afmg_fas_fmg_async": (C.c_int, [_H, _I, _I, _I]),
+    "afmg_fas_vcycle_async": (C.c_int, [_H, _I, _I, _I]),
+    "afmg_sync": (C.c_int, [_H]),
+    "afmg_gsrb_boxes": (C.c_int, [_H, _I, _I]),
+    "afmg_gsrb_halfsweep": (C.c_int, [_H, _I, _I]),
+    "afmg_gc_lvl": (C.c_int, [_H, _I, _I, _I]),
+    "afmg_update_coarse": (C.c_int, [_H, _I, _I]),
+    "afmg_correct_children": (C.c_int, [_H, _I]),
+    "afmg_residual_lvl": (C.c_int, [_H, _I]),
+    "afmg_solve_coarse_grid": (C.c_int, [_H]),
+    "afmg_init_phi_rhs": (C.c_int, [_H]),
+    "afmg_max_abs": (C.c_int, [_H, _I, _DP]),
+    "afmg_tree_sum": (C.c_int, [_H, _I, _DP]),
+    "afmg_kernel_launches": (C.c_int64, [_H]),
+    "afmg_last_cycle_ms": (C.c_int, [_H, _DP]),
+    "afmg_set_profiling": (C.c_int, [_H, _I]),
+    "afmg_profile": (C.c_int, [_H, _I, C.c_void_p, _DP, C.POINTER(C.c_int64), _IP]),
+    "afmg_cell_updates": (C.c_int, [_H, _I, _I, _DP]),
+    "afmg_layout_offset": (C.c_int32, [_I, _I, _I, _I, _I]),
+    "afmg_layout_box_len": (C.c_int32, [_I, _I]),
+    "afmg_slot_of_box": (C.c_int32, [_H, _I]),
+    "afmg_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "afmg_comm_init": (C.c_int, [_H, _I, _I, C.c_char_p]),
+    "afmg_owner_of_box": (C.c_int32, [_H, _I]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libafmg.so; raises if it has not been built (python __graft_entry__.py / make -C csrc)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build the CUDA library first (make -C afivo_streamer_b200/csrc). "
+                "There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib

@@ -1,0 +1,1339 @@
+// libafmg: host side of the B200-native FAS multigrid solver (C ABI in include/afmg.h).
+//
+// Mirrors the control flow of afivo/src/m_af_multigrid.f90 (mg_fas_fmg :137-180, mg_fas_vcycle
+// :185-264, gsrb_boxes :648-687, update_coarse :691-738, set_coarse_phi_rhs :742-776, init_phi_rhs
+// :779-799, correct_children :624-646) as sequences of kernel launches on one stream, replayed as
+// CUDA graphs.  There is no CPU compute path: every cell-data operation is a kernel in
+// kernels3d.cuh.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/afmg.h"
+#include "kernels3d.cuh"
+
+using namespace afmg;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Graph {
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;
+};
+
+struct ProfEntry {
+  double ms = 0;
+  int64_t calls = 0;
+};
+
+}  // namespace
+
+struct afmg_handle {
+  afmg_opts o{};
+  std::string err;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+
+  // ---- host copy of the tree, slot maps
+  bool have_tree = false;
+  int L = 0, nslots = 0, highest_id = 0;
+  std::vector<int> lvl_off;  // [L+2]: slots of level l are [lvl_off[l], lvl_off[l+1])
+  std::vector<int> id2slot, slot2id;
+  std::vector<int> h_nbr, h_aux, h_nmat, h_parent, h_child0, h_coff, h_lvl;
+  std::vector<int> h_ix;  // [nslots*3]
+  std::vector<int> npar;  // [L+2] number of boxes with children per level
+  int nbc = 0, nrb = 0;
+  std::vector<int> rb_lvl_off;  // [L+2] refinement-boundary faces per level (prefix)
+  std::vector<int> h_rb_slot, h_rb_face;
+  std::vector<char> bc_set;
+  std::vector<int> h_bc_type;      // [nbc]
+  std::vector<int> bc_slot, bc_face;  // [nbc]
+  int box_len = 0, nc2 = 0;
+
+  // ---- device data
+  double* d_cc[4] = {nullptr, nullptr, nullptr, nullptr};
+  int *d_nbr = nullptr, *d_aux = nullptr, *d_nmat = nullptr, *d_parent = nullptr, *d_child0 = nullptr,
+      *d_coff = nullptr, *d_lvl = nullptr, *d_rb_slot = nullptr, *d_rb_face = nullptr;
+  double *d_coef = nullptr, *d_rule_c = nullptr, *d_rule_B = nullptr, *d_pcoef = nullptr;
+  unsigned long long* d_scal = nullptr;  // [0] fused residual max, [1] generic max, [2] mean (double bits)
+  double* d_boxsum = nullptr;
+  double* d_stage = nullptr;
+  size_t stage_bytes = 0;
+  int* d_stage_slots = nullptr;
+  size_t stage_slots_n = 0;
+  DevCtx cx{};
+
+  // ---- coarse solver
+  bool cs_ready = false;
+  CoarseCtx cs{};
+  double *d_b2r = nullptr, *d_Q[3] = {nullptr, nullptr, nullptr}, *d_inveig = nullptr, *d_v0 = nullptr, *d_v1 = nullptr;
+  int* d_cs_bix = nullptr;
+
+  // ---- state
+  bool resid_fresh = false;
+  std::map<std::tuple<int, int, int>, Graph> graphs;
+  bool capturing = false;
+  int64_t launches = 0;
+  bool profiling = false;
+  std::map<std::string, ProfEntry> prof;
+  std::vector<std::tuple<std::string, cudaEvent_t, cudaEvent_t>> prof_pending;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return h->fail(AFMG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+namespace {
+
+template <class T>
+int dev_upload(afmg_handle* h, T** dptr, const std::vector<T>& v) {
+  if (*dptr) cudaFree(*dptr);
+  *dptr = nullptr;
+  size_t n = std::max<size_t>(v.size(), 1);
+  CK(cudaMalloc((void**)dptr, n * sizeof(T)));
+  if (!v.empty()) CK(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return AFMG_OK;
+}
+
+inline uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) {
+  auto spread = [](uint64_t v) {
+    v &= 0x1fffff;
+    v = (v | v << 32) & 0x1f00000000ffffULL;
+    v = (v | v << 16) & 0x1f0000ff0000ffULL;
+    v = (v | v << 8) & 0x100f00f00f00f00fULL;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+    v = (v | v << 2) & 0x1249249249249249ULL;
+    return v;
+  };
+  return spread(x) | (spread(y) << 1) | (spread(z) << 2);
+}
+
+// cyclic Jacobi eigenvalue iteration for a symmetric n x n matrix (row-major); on return A's
+// diagonal holds the eigenvalues and V (row-major, V[r*n+c]) the eigenvectors as columns
+void jacobi_eig(int n, std::vector<long double>& A, std::vector<long double>& V) {
+  V.assign((size_t)n * n, 0.0L);
+  for (int i = 0; i < n; ++i) V[(size_t)i * n + i] = 1.0L;
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    long double off = 0, diag = 0;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) (i == j ? diag : off) += A[(size_t)i * n + j] * A[(size_t)i * n + j];
+    if (off <= 1e-40L * diag) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        long double apq = A[(size_t)p * n + q];
+        if (apq == 0.0L) continue;
+        long double app = A[(size_t)p * n + p], aqq = A[(size_t)q * n + q];
+        long double theta = (aqq - app) / (2 * apq);
+        long double t = (theta >= 0 ? 1.0L : -1.0L) / (fabsl(theta) + sqrtl(theta * theta + 1));
+        long double c = 1 / sqrtl(t * t + 1), s = t * c;
+        for (int k = 0; k < n; ++k) {
+          long double akp = A[(size_t)k * n + p], akq = A[(size_t)k * n + q];
+          A[(size_t)k * n + p] = c * akp - s * akq;
+          A[(size_t)k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {
+          long double apk = A[(size_t)p * n + k], aqk = A[(size_t)q * n + k];
+          A[(size_t)p * n + k] = c * apk - s * aqk;
+          A[(size_t)q * n + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          long double vkp = V[(size_t)k * n + p], vkq = V[(size_t)k * n + q];
+          V[(size_t)k * n + p] = c * vkp - s * vkq;
+          V[(size_t)k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+}
+
+// ---- kernel launch plumbing -------------------------------------------------------------------
+struct Launch {
+  afmg_handle* h;
+  const char* name;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  Launch(afmg_handle* h_, const char* name_) : h(h_), name(name_) {
+    h->launches++;
+    if (h->profiling && !h->capturing) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, h->stream);
+    }
+  }
+  ~Launch() {
+    if (e0) {
+      cudaEventRecord(e1, h->stream);
+      h->prof_pending.emplace_back(name, e0, e1);
+    }
+  }
+};
+
+void prof_resolve(afmg_handle* h) {
+  for (auto& t : h->prof_pending) {
+    float ms = 0;
+    cudaEventSynchronize(std::get<2>(t));
+    cudaEventElapsedTime(&ms, std::get<1>(t), std::get<2>(t));
+    auto& e = h->prof[std::get<0>(t)];
+    e.ms += ms;
+    e.calls++;
+    cudaEventDestroy(std::get<1>(t));
+    cudaEventDestroy(std::get<2>(t));
+  }
+  h->prof_pending.clear();
+}
+
+#define DISPATCH_NC(h, NCVAR, ...)                                      \
+  switch ((h)->o.n_cell) {                                              \
+    case 4: { constexpr int NCVAR = 4; __VA_ARGS__; } break;            \
+    case 8: { constexpr int NCVAR = 8; __VA_ARGS__; } break;            \
+    case 16: { constexpr int NCVAR = 16; __VA_ARGS__; } break;          \
+    default: break;                                                     \
+  }
+
+template <int NC>
+struct GsrbCfg {
+  static constexpr int BPC = (NC == 16) ? 2 : (NC == 8 ? 8 : 16);
+};
+
+inline int nlev(const afmg_handle* h, int l) { return h->lvl_off[l + 1] - h->lvl_off[l]; }
+
+// one half-sweep + side ghost fill on level l
+void enq_gsrb(afmg_handle* h, int l, int redblack) {
+  const int n = nlev(h, l);
+  if (n == 0) return;
+  Launch L_(h, "gsrb");
+  DISPATCH_NC(h, NC, {
+    constexpr int BPC = GsrbCfg<NC>::BPC;
+    const int threads = BPC * NC * NC / 2;
+    const size_t smem = (size_t)BPC * Lay3<NC>::COL * sizeof(double);
+    k_gsrb<NC, BPC><<<(n + BPC - 1) / BPC, threads, smem, h->stream>>>(h->cx, h->lvl_off[l], n, redblack & 1, l);
+  });
+}
+
+void enq_rb_prepare(afmg_handle* h, int l) {
+  const int n = h->rb_lvl_off[l + 1] - h->rb_lvl_off[l];
+  if (n == 0) return;
+  Launch L_(h, "rb_prepare");
+  DISPATCH_NC(h, NC, { k_rb_prepare<NC><<<n, 128, 0, h->stream>>>(h->cx, h->rb_lvl_off[l], n, V_PHI); });
+}
+
+// af_gc_lvl (+ parent update when mode != 0)
+void enq_gc(afmg_handle* h, int l, int var, int corners, int mode) {
+  const int n = nlev(h, l);
+  if (n == 0) return;
+  Launch L_(h, mode ? "gc_parent" : "gc");
+  DISPATCH_NC(h, NC, { k_gc<NC><<<n, 256, 0, h->stream>>>(h->cx, h->lvl_off[l], n, var, corners, mode); });
+}
+
+void enq_edges_corners(afmg_handle* h, int l) {
+  const int n = nlev(h, l);
+  if (n == 0) return;
+  Launch L_(h, "edges_corners");
+  DISPATCH_NC(h, NC, { k_edges_corners<NC><<<n, 64, 0, h->stream>>>(h->cx, h->lvl_off[l], n, V_PHI); });
+}
+
+void enq_restrict(afmg_handle* h, int l, int keep_res) {
+  const int n = nlev(h, l);
+  if (n == 0) return;
+  Launch L_(h, "restrict");
+  DISPATCH_NC(h, NC, {
+    constexpr int T = (NC == 16) ? 256 : (NC == 8 ? 64 : 32);
+    k_restrict<NC><<<n, T, 0, h->stream>>>(h->cx, h->lvl_off[l], n, keep_res);
+  });
+}
+
+void enq_correct(afmg_handle* h, int lp) {
+  const int n = nlev(h, lp);
+  if (n == 0 || h->npar[lp] == 0) return;
+  Launch L_(h, "correct");
+  DISPATCH_NC(h, NC, {
+    const size_t smem = (size_t)(NC + 2) * (NC + 2) * (NC + 2) * sizeof(double);
+    k_correct<NC><<<n, 256, smem, h->stream>>>(h->cx, h->lvl_off[lp], n);
+  });
+}
+
+void enq_residual(afmg_handle* h, int l_lo, int l_hi, bool with_max) {
+  const int s0 = h->lvl_off[l_lo], n = h->lvl_off[l_hi + 1] - s0;
+  if (n == 0) return;
+  Launch L_(h, "residual");
+  DISPATCH_NC(h, NC, { k_residual<NC><<<n, 256, 0, h->stream>>>(h->cx, s0, n, with_max ? h->d_scal : nullptr); });
+}
+
+void enq_copy_lvl(afmg_handle* h, int l, int dst, int src) {
+  const size_t n = (size_t)nlev(h, l) * h->box_len;
+  if (n == 0) return;
+  Launch L_(h, "copy");
+  const size_t off = (size_t)h->lvl_off[l] * h->box_len;
+  const int blocks = (int)std::min<size_t>((n + 1023) / 1024, 148 * 8);
+  k_copy<<<blocks, 256, 0, h->stream>>>(h->d_cc[dst] + off, h->d_cc[src] + off, n);
+}
+
+// solve_coarse_grid (m_af_multigrid.f90:266-291)
+void enq_coarse(afmg_handle* h) {
+  const int nbox1 = nlev(h, 1);
+  const int ntot = h->cs.nx[0] * h->cs.nx[1] * h->cs.nx[2];
+  const int blocks = (ntot + 127) / 128;
+  {
+    Launch L_(h, "coarse");
+    DISPATCH_NC(h, NC, { k_cs_gather<NC><<<blocks, 128, 0, h->stream>>>(h->cx, h->cs, nbox1); });
+  }
+  double *a = h->d_v0, *b = h->d_v1;
+  for (int d = 0; d < 3; ++d) {
+    Launch L_(h, "coarse");
+    k_cs_apply<<<blocks, 128, 0, h->stream>>>(h->cs, a, b, d, 1, d == 2);
+    std::swap(a, b);
+  }
+  for (int d = 0; d < 3; ++d) {
+    Launch L_(h, "coarse");
+    k_cs_apply<<<blocks, 128, 0, h->stream>>>(h->cs, a, b, d, 0, 0);
+    std::swap(a, b);
+  }
+  {
+    Launch L_(h, "coarse");
+    DISPATCH_NC(h, NC, { k_cs_scatter<NC><<<blocks, 128, 0, h->stream>>>(h->cx, h->cs, nbox1, a); });
+  }
+  enq_gc(h, 1, V_PHI, 1, 0);
+}
+
+// gsrb_boxes (m_af_multigrid.f90:648-687)
+void enq_gsrb_boxes(afmg_handle* h, int l, bool up) {
+  const int ncyc = up ? h->o.n_cycle_up : h->o.n_cycle_down;
+  for (int n = 1; n <= 2 * ncyc; ++n) {
+    enq_gsrb(h, l, n);
+    const bool corners = h->o.use_corners || (up && n == 2 * ncyc);
+    if (corners) enq_edges_corners(h, l);
+  }
+}
+
+// update_coarse (:691-738) with_tmp = true, set_coarse_phi_rhs (:742-776) with_tmp = false
+void enq_update_coarse(afmg_handle* h, int l, bool with_tmp) {
+  if (!with_tmp && l == h->L) {
+    enq_rb_prepare(h, l);
+    enq_gc(h, l, V_PHI, 1, 0);
+  }
+  enq_restrict(h, l, with_tmp ? 0 : 1);
+  enq_rb_prepare(h, l - 1);
+  enq_gc(h, l - 1, V_PHI, 1, with_tmp ? 1 : 2);
+}
+
+void enq_subtract_mean(afmg_handle* h, int max_lvl);
+
+// mg_fas_vcycle (m_af_multigrid.f90:185-264)
+void enq_vcycle(afmg_handle* h, bool set_residual, int max_lvl) {
+  for (int l = max_lvl; l >= 2; --l) {
+    enq_rb_prepare(h, l);
+    enq_gsrb_boxes(h, l, false);
+    enq_update_coarse(h, l, true);
+  }
+  enq_coarse(h);
+  for (int l = 2; l <= max_lvl; ++l) {
+    enq_correct(h, l - 1);
+    enq_rb_prepare(h, l);
+    enq_gc(h, l, V_PHI, 1, 0);
+    enq_gsrb_boxes(h, l, true);
+  }
+  if (set_residual) {
+    const bool all = (max_lvl == h->L);
+    if (all) cudaMemsetAsync(h->d_scal, 0, sizeof(unsigned long long), h->stream);
+    enq_residual(h, 1, max_lvl, all);
+  }
+  if (h->o.subtract_mean) enq_subtract_mean(h, max_lvl);
+}
+
+__global__ void k_weighted_sum(const double* boxsum, const int* child0, const int* lvl, const double* lvl_fac, int n,
+                               double inv_volume, double* out) {
+  // deterministic single-CTA reduction: thread t sums slots t, t+T, ...; then a fixed tree
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (child0[i] < 0) s = s + lvl_fac[lvl[i]] * boxsum[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] = sh[threadIdx.x] + sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0] * inv_volume;
+}
+
+void enq_subtract_mean(afmg_handle* h, int max_lvl) {
+  // af_tree_sum_cc over all leaves / af_total_volume, then phi -= mean on levels 1..max_lvl (full boxes)
+  {
+    Launch L_(h, "sum");
+    DISPATCH_NC(h, NC, { k_box_sums<NC><<<h->nslots, 128, 0, h->stream>>>(h->cx, 0, h->nslots, V_PHI, h->d_boxsum); });
+  }
+  double vol = (double)nlev(h, 1);
+  for (int d = 0; d < 3; ++d) vol *= h->o.n_cell * h->o.dr_base[d];
+  {
+    Launch L_(h, "sum");
+    k_weighted_sum<<<1, 256, 0, h->stream>>>(h->d_boxsum, h->d_child0, h->d_lvl, h->d_coef + 8 * (h->L + 1), h->nslots,
+                                            1.0 / vol, (double*)(h->d_scal + 2));
+  }
+  {
+    Launch L_(h, "sub_mean");
+    const size_t n = (size_t)h->lvl_off[max_lvl + 1] * h->box_len;
+    const int blocks = (int)std::min<size_t>((n + 1023) / 1024, 148 * 8);
+    k_sub_scalar<<<blocks, 256, 0, h->stream>>>(h->d_cc[V_PHI], (const double*)(h->d_scal + 2), n);
+  }
+}
+
+// init_phi_rhs (m_af_multigrid.f90:779-799)
+void enq_init_phi_rhs(afmg_handle* h) {
+  for (int l = h->L; l >= 2; --l) {
+    const int n = nlev(h, l);
+    if (n == 0) continue;
+    Launch L_(h, "init_phi_rhs");
+    DISPATCH_NC(h, NC, {
+      constexpr int T = (NC == 16) ? 256 : (NC == 8 ? 64 : 32);
+      k_restrict_var<NC><<<n, T, 0, h->stream>>>(h->cx, h->lvl_off[l], n, V_RHS, 1);
+    });
+  }
+}
+
+// mg_fas_fmg (m_af_multigrid.f90:137-180)
+void enq_fmg(afmg_handle* h, bool set_residual, bool have_guess) {
+  if (have_guess) {
+    for (int l = h->L; l >= 2; --l) enq_update_coarse(h, l, false);
+  } else {
+    enq_init_phi_rhs(h);
+  }
+  enq_copy_lvl(h, 1, V_TMP, V_PHI);
+  enq_vcycle(h, set_residual && h->L == 1, 1);
+  for (int l = 2; l <= h->L; ++l) {
+    enq_copy_lvl(h, l, V_TMP, V_PHI);
+    enq_correct(h, l - 1);
+    enq_rb_prepare(h, l);
+    enq_gc(h, l, V_PHI, 1, 0);
+    enq_vcycle(h, set_residual && l == h->L, l);
+  }
+}
+
+// ---- set-up ---------------------------------------------------------------------------------------
+int build_constant_stencils(afmg_handle* h) {
+  // mg_box_lpl_stencil (m_af_multigrid.f90:1246-1264) per level; plus (after the L+1 rows) the volume
+  // factors product(dr_base) * 0.5^(3(l-1)) used by af_tree_sum_cc (m_af_utils.f90:966-1027)
+  std::vector<double> coef((size_t)(h->L + 1) * 8 + (h->L + 2), 0.0);
+  for (int l = 1; l <= h->L; ++l) {
+    double* c = &coef[(size_t)8 * l];
+    for (int d = 0; d < 3; ++d) {
+      const double dr = h->o.dr_base[d] * std::pow(0.5, l - 1);
+      const double inv_dr2 = 1 / (dr * dr);
+      c[1 + 2 * d] = inv_dr2;
+      c[2 + 2 * d] = inv_dr2;
+    }
+    double s = 0.0;
+    for (int m = 1; m < 7; ++m) s = s + c[m];
+    c[0] = -s - h->o.helmholtz_lambda;
+    c[7] = 1 / c[0];
+    double fac = 1.0;
+    for (int d = 0; d < 3; ++d) fac *= h->o.dr_base[d] * std::pow(0.5, l - 1);
+    coef[(size_t)8 * (h->L + 1) + l] = fac;
+  }
+  int rc = dev_upload(h, &h->d_coef, coef);
+  if (rc) return rc;
+  // mg_box_prolong_linear_stencil / _sparse_stencil (m_af_multigrid.f90:1267-1304)
+  std::vector<double> pc(8, 0.0);
+  int pshape = 8;
+  if (h->o.prolongation_type == AFMG_PROLONG_SPARSE) {
+    pshape = 4;
+    pc = {0.25, 0.25, 0.25, 0.25, 0, 0, 0, 0};
+  } else {
+    pc = {27 / 64.0, 9 / 64.0, 9 / 64.0, 3 / 64.0, 9 / 64.0, 3 / 64.0, 3 / 64.0, 1 / 64.0};
+  }
+  rc = dev_upload(h, &h->d_pcoef, pc);
+  if (rc) return rc;
+  h->cx.coef = h->d_coef;
+  h->cx.pcoef = h->d_pcoef;
+  h->cx.pshape = pshape;
+  return AFMG_OK;
+}
+
+void drop_graphs(afmg_handle* h) {
+  for (auto& kv : h->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  h->graphs.clear();
+}
+
+// coarse_solver_initialize (m_coarse_solver.f90:71-194) + stencil_handle_boundaries (:442-491), with the
+// Hypre solve replaced by the eigen-decomposition of the separable BC-folded operator
+int coarse_setup(afmg_handle* h) {
+  const int nc = h->o.n_cell, nc2 = h->nc2;
+  const int nbox1 = nlev(h, 1);
+  int nb[3], nx[3];
+  for (int d = 0; d < 3; ++d) {
+    nx[d] = h->o.coarse_grid_size[d];
+    nb[d] = nx[d] / nc;
+  }
+  if (nb[0] * nb[1] * nb[2] != nbox1) return h->fail(AFMG_ERR_ARG, "coarse grid size does not match the level-1 boxes");
+  // BC type per domain face must be uniform for the separable solve
+  int face_type[6] = {0, 0, 0, 0, 0, 0};
+  for (int r = 0; r < h->nbc; ++r) {
+    if (h->h_lvl[h->bc_slot[r]] != 1) continue;
+    if (!h->bc_set[r]) return h->fail(AFMG_ERR_STATE, "boundary condition not set for level-1 box %d face %d",
+                                      h->slot2id[h->bc_slot[r]], h->bc_face[r] + 1);
+    const int f = h->bc_face[r], ty = h->h_bc_type[r];
+    if (ty != AFMG_BC_DIRICHLET && ty != AFMG_BC_NEUMANN)
+      return h->fail(AFMG_ERR_UNSUPPORTED, "coarse grid: unsupported boundary condition %d (reference: error stop, "
+                                           "m_coarse_solver.f90:486)", ty);
+    if (face_type[f] != 0 && face_type[f] != ty)
+      return h->fail(AFMG_ERR_UNSUPPORTED, "coarse grid: mixed boundary condition types on domain face %d", f + 1);
+    face_type[f] = ty;
+  }
+  const double* c1 = nullptr;
+  std::vector<double> coef1(8);
+  {
+    for (int d = 0; d < 3; ++d) {
+      const double dr = h->o.dr_base[d];
+      coef1[1 + 2 * d] = coef1[2 + 2 * d] = 1 / (dr * dr);
+    }
+    c1 = coef1.data();
+  }
+  // bc_to_rhs per (box, face, cell)
+  std::vector<double> b2r((size_t)nbox1 * 6 * nc2, 0.0);
+  for (int r = 0; r < h->nbc; ++r) {
+    const int s = h->bc_slot[r], f = h->bc_face[r];
+    if (h->h_lvl[s] != 1) continue;
+    const double cnb = c1[f + 1];
+    double v;
+    if (h->h_bc_type[r] == AFMG_BC_DIRICHLET) v = -2 * cnb;
+    else v = -(cnb * h->o.dr_base[f >> 1]) * ((f & 1) ? 1 : -1);
+    for (int q = 0; q < nc2; ++q) b2r[((size_t)s * 6 + f) * nc2 + q] = v;
+  }
+  // 1D operators and their eigen-decompositions
+  std::vector<std::vector<double>> Qd(3), lam(3);
+  for (int d = 0; d < 3; ++d) {
+    const int n = nx[d];
+    const long double c = c1[1 + 2 * d];
+    std::vector<long double> A((size_t)n * n, 0.0L), V;
+    for (int i = 0; i < n; ++i) {
+      A[(size_t)i * n + i] = -2 * c;
+      if (i > 0) A[(size_t)i * n + i - 1] = c;
+      if (i < n - 1) A[(size_t)i * n + i + 1] = c;
+    }
+    const int flo = 2 * d, fhi = 2 * d + 1;
+    if (h->o.periodic[d]) {
+      if (n > 2) {
+        A[(size_t)0 * n + n - 1] += c;
+        A[(size_t)(n - 1) * n + 0] += c;
+      }
+    } else {
+      if (face_type[flo] == 0 || face_type[fhi] == 0)
+        return h->fail(AFMG_ERR_STATE, "boundary conditions missing on domain faces of dimension %d", d + 1);
+      A[0] += (face_type[flo] == AFMG_BC_DIRICHLET) ? -c : c;
+      A[(size_t)(n - 1) * n + n - 1] += (face_type[fhi] == AFMG_BC_DIRICHLET) ? -c : c;
+    }
+    jacobi_eig(n, A, V);
+    Qd[d].resize((size_t)n * n);
+    lam[d].resize(n);
+    for (int i = 0; i < n; ++i) lam[d][i] = (double)A[(size_t)i * n + i];
+    for (size_t i = 0; i < (size_t)n * n; ++i) Qd[d][i] = (double)V[i];
+  }
+  const int ntot = nx[0] * nx[1] * nx[2];
+  std::vector<double> inveig(ntot);
+  double mu_max = 0, mu_min = 1e300;
+  for (int k = 0; k < nx[2]; ++k)
+    for (int j = 0; j < nx[1]; ++j)
+      for (int i = 0; i < nx[0]; ++i) {
+        const double mu = lam[0][i] + lam[1][j] + lam[2][k] - h->o.helmholtz_lambda;
+        mu_max = std::max(mu_max, std::fabs(mu));
+        mu_min = std::min(mu_min, std::fabs(mu));
+        inveig[i + nx[0] * (j + nx[1] * k)] = 1 / mu;
+      }
+  if (mu_min < 1e-10 * mu_max)
+    return h->fail(AFMG_ERR_SINGULAR, "coarse-grid operator is singular (all-Neumann/periodic without Helmholtz term)");
+  std::vector<int> bix((size_t)nbox1 * 3);
+  for (int s = 0; s < nbox1; ++s)
+    for (int d = 0; d < 3; ++d) bix[(size_t)s * 3 + d] = h->h_ix[(size_t)s * 3 + d] - 1;
+  int rc;
+  if ((rc = dev_upload(h, &h->d_b2r, b2r))) return rc;
+  for (int d = 0; d < 3; ++d)
+    if ((rc = dev_upload(h, &h->d_Q[d], Qd[d]))) return rc;
+  if ((rc = dev_upload(h, &h->d_inveig, inveig))) return rc;
+  if ((rc = dev_upload(h, &h->d_cs_bix, bix))) return rc;
+  std::vector<double> zeros(ntot, 0.0);
+  if ((rc = dev_upload(h, &h->d_v0, zeros))) return rc;
+  if ((rc = dev_upload(h, &h->d_v1, zeros))) return rc;
+  for (int d = 0; d < 3; ++d) {
+    h->cs.nx[d] = nx[d];
+    h->cs.nb[d] = nb[d];
+    h->cs.Q[d] = h->d_Q[d];
+  }
+  h->cs.b2r = h->d_b2r;
+  h->cs.inv_eig = h->d_inveig;
+  h->cs.v0 = h->d_v0;
+  h->cs.v1 = h->d_v1;
+  h->cs.bix = h->d_cs_bix;
+  h->cs_ready = true;
+  return AFMG_OK;
+}
+
+int ensure_ready(afmg_handle* h) {
+  if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
+  for (int r = 0; r < h->nbc; ++r)
+    if (!h->bc_set[r])
+      return h->fail(AFMG_ERR_STATE, "boundary condition not set for box %d face %d (call afmg_set_bc)",
+                     h->slot2id[h->bc_slot[r]], h->bc_face[r] + 1);
+  if (!h->cs_ready) {
+    int rc = coarse_setup(h);
+    if (rc) return rc;
+  }
+  return AFMG_OK;
+}
+
+int ensure_stage(afmg_handle* h, size_t bytes, size_t nslots) {
+  if (bytes > h->stage_bytes) {
+    if (h->d_stage) cudaFree(h->d_stage);
+    h->d_stage = nullptr;
+    CK(cudaMalloc((void**)&h->d_stage, bytes));
+    h->stage_bytes = bytes;
+  }
+  if (nslots > h->stage_slots_n) {
+    if (h->d_stage_slots) cudaFree(h->d_stage_slots);
+    h->d_stage_slots = nullptr;
+    CK(cudaMalloc((void**)&h->d_stage_slots, nslots * sizeof(int)));
+    h->stage_slots_n = nslots;
+  }
+  return AFMG_OK;
+}
+
+// run `body` through a cached CUDA graph (or directly when profiling)
+template <class F>
+int run_graph(afmg_handle* h, std::tuple<int, int, int> key, int n_rep, F body) {
+  if (h->profiling) {
+    for (int i = 0; i < n_rep; ++i) body();
+    CK(cudaGetLastError());
+    return AFMG_OK;
+  }
+  auto it = h->graphs.find(key);
+  if (it == h->graphs.end()) {
+    cudaGraph_t g = nullptr;
+    const int64_t before = h->launches;
+    h->capturing = true;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    body();
+    cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    h->capturing = false;
+    if (e != cudaSuccess) return h->fail(AFMG_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    Graph gr;
+    gr.launches = h->launches - before;
+    h->launches = before;
+    e = cudaGraphInstantiate(&gr.exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return h->fail(AFMG_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    it = h->graphs.emplace(key, gr).first;
+  }
+  for (int i = 0; i < n_rep; ++i) {
+    CK(cudaGraphLaunch(it->second.exec, h->stream));
+    h->launches += it->second.launches;
+  }
+  return AFMG_OK;
+}
+
+int check_lvl(afmg_handle* h, int lvl) {
+  if (lvl < 1 || lvl > h->L) return h->fail(AFMG_ERR_ARG, "level %d out of range 1..%d", lvl, h->L);
+  return AFMG_OK;
+}
+
+int finish_op(afmg_handle* h) {
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->profiling) prof_resolve(h);
+  return AFMG_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* afmg_last_error(const afmg_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int afmg_create(afmg_handle** out, const afmg_opts* opts) {
+  if (!out || !opts) {
+    g_create_error = "null argument";
+    return AFMG_ERR_ARG;
+  }
+  *out = nullptr;
+  if (opts->ndim != 3) {
+    g_create_error = "only ndim = 3 is supported by this build";
+    return AFMG_ERR_UNSUPPORTED;
+  }
+  if (opts->n_cell != 4 && opts->n_cell != 8 && opts->n_cell != 16) {
+    g_create_error = "n_cell must be 4, 8 or 16";
+    return AFMG_ERR_UNSUPPORTED;
+  }
+  if (opts->coord_t != AFMG_XYZ) {
+    g_create_error = "3D trees must be Cartesian";
+    return AFMG_ERR_ARG;
+  }
+  if (opts->has_eps) {
+    g_create_error = "variable-coefficient (eps) operators are not supported by this build";
+    return AFMG_ERR_UNSUPPORTED;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)";
+    return AFMG_ERR_CUDA;
+  }
+  afmg_handle* h = new afmg_handle();
+  h->o = *opts;
+  if (opts->device >= 0) {
+    h->device = opts->device;
+    e = cudaSetDevice(h->device);
+  } else {
+    e = cudaGetDevice(&h->device);
+  }
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_scal, 8 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->d_scal, 0, 8 * sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e);
+    delete h;
+    return AFMG_ERR_CUDA;
+  }
+  h->nc2 = opts->n_cell * opts->n_cell;
+  h->box_len = (opts->n_cell + 2) * (opts->n_cell + 2) * (opts->n_cell + 2);
+  *out = h;
+  return AFMG_OK;
+}
+
+int afmg_destroy(afmg_handle* h) {
+  if (!h) return AFMG_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  drop_graphs(h);
+  for (auto& p : h->d_cc) cudaFree(p);
+  int* ip[] = {h->d_nbr, h->d_aux, h->d_nmat, h->d_parent, h->d_child0, h->d_coff, h->d_lvl, h->d_rb_slot,
+               h->d_rb_face, h->d_stage_slots, h->d_cs_bix};
+  for (auto p : ip) cudaFree(p);
+  double* dp[] = {h->d_coef, h->d_rule_c, h->d_rule_B, h->d_pcoef, h->d_boxsum, h->d_stage, h->d_b2r, h->d_Q[0],
+                  h->d_Q[1], h->d_Q[2], h->d_inveig, h->d_v0, h->d_v1};
+  for (auto p : dp) cudaFree(p);
+  cudaFree(h->d_scal);
+  cudaEventDestroy(h->ev0);
+  cudaEventDestroy(h->ev1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return AFMG_OK;
+}
+
+int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
+  if (!h || !t) return AFMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  drop_graphs(h);
+  h->have_tree = false;
+  h->cs_ready = false;
+  h->resid_fresh = false;
+  const int L = t->highest_lvl, N = t->highest_id;
+  if (L < 1 || N < 1) return h->fail(AFMG_ERR_ARG, "empty tree");
+  int total = 0;
+  for (int l = 0; l < L; ++l) total += t->lvl_counts[l];
+  h->L = L;
+  h->highest_id = N;
+  h->nslots = total;
+  h->lvl_off.assign(L + 2, 0);
+  for (int l = 1; l <= L; ++l) h->lvl_off[l + 1] = h->lvl_off[l] + t->lvl_counts[l - 1];
+  h->lvl_off[1] = 0;
+  h->id2slot.assign(N + 1, -1);
+  h->slot2id.assign(total, 0);
+  // slots: level 1 in list order, finer levels in Morton order of ix-1
+  {
+    int p = 0;
+    for (int l = 1; l <= L; ++l) {
+      const int n = t->lvl_counts[l - 1];
+      std::vector<std::pair<uint64_t, int>> keyed(n);
+      for (int q = 0; q < n; ++q) {
+        const int id = t->lvl_ids[p + q];
+        if (id < 1 || id > N) return h->fail(AFMG_ERR_ARG, "box id %d out of range", id);
+        if (t->lvl[id] != l) return h->fail(AFMG_ERR_ARG, "box %d listed on level %d but has lvl %d", id, l, t->lvl[id]);
+        const int* ix = t->ix + (size_t)id * 3;
+        keyed[q] = {l == 1 ? (uint64_t)q : morton3(ix[0] - 1, ix[1] - 1, ix[2] - 1), id};
+      }
+      std::sort(keyed.begin(), keyed.end());
+      for (int q = 0; q < n; ++q) {
+        const int id = keyed[q].second;
+        if (h->id2slot[id] != -1) return h->fail(AFMG_ERR_ARG, "box %d listed twice", id);
+        h->id2slot[id] = h->lvl_off[l] + q;
+        h->slot2id[h->lvl_off[l] + q] = id;
+      }
+      p += n;
+    }
+  }
+  auto slot_of = [&](int id) { return id > 0 ? h->id2slot[id] : (id == 0 ? -2 : -1); };
+  h->h_nbr.assign((size_t)total * 6, 0);
+  h->h_aux.assign((size_t)total * 6, -1);
+  h->h_nmat.assign((size_t)total * 27, 0);
+  h->h_parent.assign(total, -1);
+  h->h_child0.assign(total, -1);
+  h->h_coff.assign(total, 0);
+  h->h_lvl.assign(total, 0);
+  h->h_ix.assign((size_t)total * 3, 0);
+  h->npar.assign(L + 2, 0);
+  h->bc_slot.clear();
+  h->bc_face.clear();
+  h->h_rb_slot.clear();
+  h->h_rb_face.clear();
+  h->rb_lvl_off.assign(L + 2, 0);
+  for (int s = 0; s < total; ++s) {
+    const int id = h->slot2id[s];
+    const int l = t->lvl[id];
+    h->h_lvl[s] = l;
+    for (int d = 0; d < 3; ++d) h->h_ix[(size_t)s * 3 + d] = t->ix[(size_t)id * 3 + d];
+    if (l > 1) {
+      const int p = t->parent[id];
+      if (p < 1 || p > N || h->id2slot[p] < 0) return h->fail(AFMG_ERR_ARG, "box %d has invalid parent %d", id, p);
+      h->h_parent[s] = h->id2slot[p];
+    }
+    const int* ix = t->ix + (size_t)id * 3;
+    h->h_coff[s] = ((ix[0] - 1) & 1) | (((ix[1] - 1) & 1) << 1) | (((ix[2] - 1) & 1) << 2);
+    const int* ch = t->children + (size_t)id * 8;
+    if (ch[0] != 0) {
+      for (int c = 0; c < 8; ++c)
+        if (ch[c] < 1 || ch[c] > N || h->id2slot[ch[c]] < 0)
+          return h->fail(AFMG_ERR_ARG, "box %d has invalid child %d", id, ch[c]);
+      h->h_child0[s] = h->id2slot[ch[0]];
+      for (int c = 0; c < 8; ++c)
+        if (h->id2slot[ch[c]] != h->h_child0[s] + c)
+          return h->fail(AFMG_ERR_ARG, "children of box %d are not a complete sibling group", id);
+      h->npar[l]++;
+    }
+    for (int m = 0; m < 27; ++m) {
+      const int v = t->neighbor_mat[(size_t)id * 27 + m];
+      if (v > N) return h->fail(AFMG_ERR_ARG, "neighbor_mat of box %d out of range", id);
+      h->h_nmat[(size_t)s * 27 + m] = slot_of(v);
+    }
+  }
+  // faces: neighbour slot, or rule row (physical faces first, then refinement boundaries by level)
+  for (int s = 0; s < total; ++s) {
+    const int id = h->slot2id[s];
+    for (int f = 0; f < 6; ++f) {
+      const int v = t->neighbors[(size_t)id * 6 + f];
+      if (v > 0) {
+        if (v > N || h->id2slot[v] < 0) return h->fail(AFMG_ERR_ARG, "box %d has invalid neighbour %d", id, v);
+        h->h_nbr[(size_t)s * 6 + f] = h->id2slot[v];
+      } else if (v < 0) {
+        h->h_nbr[(size_t)s * 6 + f] = -1;
+        h->h_aux[(size_t)s * 6 + f] = (int)h->bc_slot.size();
+        h->bc_slot.push_back(s);
+        h->bc_face.push_back(f);
+      } else {
+        if (h->h_lvl[s] == 1) return h->fail(AFMG_ERR_ARG, "level-1 box %d has a refinement boundary", id);
+        h->h_nbr[(size_t)s * 6 + f] = -1;
+      }
+    }
+  }
+  h->nbc = (int)h->bc_slot.size();
+  for (int s = 0; s < total; ++s)
+    for (int f = 0; f < 6; ++f)
+      if (h->h_nbr[(size_t)s * 6 + f] == -1 && h->h_aux[(size_t)s * 6 + f] == -1) {
+        const int p = h->h_parent[s];
+        if (h->h_nbr[(size_t)p * 6 + f] < 0)
+          return h->fail(AFMG_ERR_ARG, "tree is not 2:1 balanced at box %d face %d", h->slot2id[s], f + 1);
+        h->h_aux[(size_t)s * 6 + f] = h->nbc + (int)h->h_rb_slot.size();
+        h->h_rb_slot.push_back(s);
+        h->h_rb_face.push_back(f);
+        h->rb_lvl_off[h->h_lvl[s] + 1]++;
+      }
+  for (int l = 1; l <= L; ++l) h->rb_lvl_off[l + 1] += h->rb_lvl_off[l];
+  h->nrb = (int)h->h_rb_slot.size();
+  h->bc_set.assign(h->nbc, 0);
+  h->h_bc_type.assign(h->nbc, 0);
+
+  int rc;
+  if ((rc = dev_upload(h, &h->d_nbr, h->h_nbr))) return rc;
+  if ((rc = dev_upload(h, &h->d_aux, h->h_aux))) return rc;
+  if ((rc = dev_upload(h, &h->d_nmat, h->h_nmat))) return rc;
+  if ((rc = dev_upload(h, &h->d_parent, h->h_parent))) return rc;
+  if ((rc = dev_upload(h, &h->d_child0, h->h_child0))) return rc;
+  if ((rc = dev_upload(h, &h->d_coff, h->h_coff))) return rc;
+  if ((rc = dev_upload(h, &h->d_lvl, h->h_lvl))) return rc;
+  if ((rc = dev_upload(h, &h->d_rb_slot, h->h_rb_slot))) return rc;
+  if ((rc = dev_upload(h, &h->d_rb_face, h->h_rb_face))) return rc;
+  const int nrules = h->nbc + h->nrb;
+  std::vector<double> rule_c((size_t)std::max(nrules, 1) * 3, 0.0);
+  for (int r = h->nbc; r < nrules; ++r) {  // mg_sides_rb: 0.5*gc + 0.75*x1 - 0.25*x2
+    rule_c[(size_t)r * 3 + 0] = 0.5;
+    rule_c[(size_t)r * 3 + 1] = 0.75;
+    rule_c[(size_t)r * 3 + 2] = -0.25;
+  }
+  if ((rc = dev_upload(h, &h->d_rule_c, rule_c))) return rc;
+  std::vector<double> rule_B((size_t)std::max(nrules, 1) * h->nc2, 0.0);
+  if ((rc = dev_upload(h, &h->d_rule_B, rule_B))) return rc;
+  for (int v = 0; v < 3; ++v) {
+    if (h->d_cc[v]) cudaFree(h->d_cc[v]);
+    h->d_cc[v] = nullptr;
+    const size_t bytes = (size_t)total * h->box_len * sizeof(double);
+    CK(cudaMalloc((void**)&h->d_cc[v], bytes));
+    CK(cudaMemset(h->d_cc[v], 0, bytes));
+  }
+  if (h->d_boxsum) cudaFree(h->d_boxsum);
+  h->d_boxsum = nullptr;
+  CK(cudaMalloc((void**)&h->d_boxsum, (size_t)total * sizeof(double)));
+
+  for (int v = 0; v < 4; ++v) h->cx.cc[v] = h->d_cc[v];
+  h->cx.nbr = h->d_nbr;
+  h->cx.aux = h->d_aux;
+  h->cx.nmat = h->d_nmat;
+  h->cx.parent = h->d_parent;
+  h->cx.child0 = h->d_child0;
+  h->cx.coff = h->d_coff;
+  h->cx.lvl = h->d_lvl;
+  h->cx.rule_c = h->d_rule_c;
+  h->cx.rule_B = h->d_rule_B;
+  h->cx.rb_slot = h->d_rb_slot;
+  h->cx.rb_face = h->d_rb_face;
+  h->cx.rb_row0 = h->nbc;
+  if ((rc = build_constant_stencils(h))) return rc;
+  h->have_tree = true;
+  return AFMG_OK;
+}
+
+int afmg_set_bc(afmg_handle* h, int32_t n_faces, const int32_t* box_id, const int32_t* nb, const int32_t* bc_type,
+                const double* bc_val) {
+  if (!h) return AFMG_ERR_ARG;
+  if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  const int nc2 = h->nc2;
+  std::vector<double> rc3((size_t)3);
+  bool types_changed = false;
+  // stage into host mirrors then upload row by row (rows are few: physical faces only)
+  std::vector<double> rows((size_t)n_faces * nc2), coefs((size_t)n_faces * 3);
+  std::vector<int> rowidx(n_faces);
+  for (int q = 0; q < n_faces; ++q) {
+    const int id = box_id[q], f = nb[q] - 1;
+    if (id < 1 || id > h->highest_id || h->id2slot[id] < 0) return h->fail(AFMG_ERR_ARG, "afmg_set_bc: unknown box %d", id);
+    if (f < 0 || f > 5) return h->fail(AFMG_ERR_ARG, "afmg_set_bc: invalid neighbour direction %d", nb[q]);
+    const int s = h->id2slot[id];
+    if (h->h_nbr[(size_t)s * 6 + f] != -1 || h->h_aux[(size_t)s * 6 + f] >= h->nbc)
+      return h->fail(AFMG_ERR_ARG, "afmg_set_bc: box %d face %d is not a physical boundary", id, nb[q]);
+    const int r = h->h_aux[(size_t)s * 6 + f];
+    double c0, c1, c2;
+    switch (bc_type[q]) {  // bc_to_gc (m_af_ghostcell.f90:192-214)
+      case AFMG_BC_DIRICHLET: c0 = 2; c1 = -1; c2 = 0; break;
+      case AFMG_BC_NEUMANN:
+        c0 = h->o.dr_base[f >> 1] * std::pow(0.5, h->h_lvl[s] - 1) * ((f & 1) ? 1 : -1);
+        c1 = 1;
+        c2 = 0;
+        break;
+      case AFMG_BC_CONTINUOUS: c0 = 0; c1 = 2; c2 = -1; break;
+      case AFMG_BC_DIRICHLET_COPY: c0 = 1; c1 = 0; c2 = 0; break;
+      default: return h->fail(AFMG_ERR_ARG, "afmg_set_bc: unknown boundary condition %d", bc_type[q]);
+    }
+    if (!h->bc_set[r] || h->h_bc_type[r] != bc_type[q]) types_changed = true;
+    h->bc_set[r] = 1;
+    h->h_bc_type[r] = bc_type[q];
+    rowidx[q] = r;
+    coefs[(size_t)q * 3 + 0] = c0;
+    coefs[(size_t)q * 3 + 1] = c1;
+    coefs[(size_t)q * 3 + 2] = c2;
+    std::memcpy(&rows[(size_t)q * nc2], bc_val + (size_t)q * nc2, nc2 * sizeof(double));
+  }
+  // coalesce contiguous runs of rows into few memcpys
+  int q = 0;
+  while (q < n_faces) {
+    int e = q + 1;
+    while (e < n_faces && rowidx[e] == rowidx[e - 1] + 1) ++e;
+    CK(cudaMemcpy(h->d_rule_B + (size_t)rowidx[q] * nc2, &rows[(size_t)q * nc2], (size_t)(e - q) * nc2 * sizeof(double),
+                  cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_rule_c + (size_t)rowidx[q] * 3, &coefs[(size_t)q * 3], (size_t)(e - q) * 3 * sizeof(double),
+                  cudaMemcpyHostToDevice));
+    q = e;
+  }
+  if (types_changed) h->cs_ready = false;
+  return AFMG_OK;
+}
+
+int afmg_set_helmholtz_lambda(afmg_handle* h, double lambda) {
+  if (!h) return AFMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  h->o.helmholtz_lambda = lambda;
+  h->cs_ready = false;
+  if (h->have_tree) return build_constant_stencils(h);
+  return AFMG_OK;
+}
+
+int afmg_set_lsf_boundary_value(afmg_handle* h, double value) {
+  if (!h) return AFMG_ERR_ARG;
+  h->o.lsf_boundary_value = value;
+  return AFMG_OK;
+}
+
+int afmg_set_lsf_distances(afmg_handle* h, int32_t n, const int32_t*, const double*) {
+  if (!h) return AFMG_ERR_ARG;
+  if (n == 0) return AFMG_OK;
+  return h->fail(AFMG_ERR_UNSUPPORTED, "level-set (electrode) stencils are not supported by this build");
+}
+
+int afmg_update_operator_stencil(afmg_handle* h) {
+  if (!h) return AFMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  h->cs_ready = false;
+  if (h->have_tree) return build_constant_stencils(h);
+  return AFMG_OK;
+}
+
+static int transfer(afmg_handle* h, int var, int n, const int32_t* box_id, double* packed, bool up, bool device_ptr) {
+  if (!h) return AFMG_ERR_ARG;
+  if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
+  if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
+  if (n == 0) return AFMG_OK;
+  CK(cudaSetDevice(h->device));
+  std::vector<int> slots(n);
+  for (int q = 0; q < n; ++q) {
+    const int id = box_id[q];
+    if (id < 1 || id > h->highest_id || h->id2slot[id] < 0) return h->fail(AFMG_ERR_ARG, "unknown box id %d", id);
+    slots[q] = h->id2slot[id];
+  }
+  const size_t box_bytes = (size_t)h->box_len * sizeof(double);
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)256 << 20) / box_bytes));
+  int rc = ensure_stage(h, device_ptr ? 16 : (size_t)chunk * box_bytes, (size_t)n);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->d_stage_slots, slots.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  for (int q0 = 0; q0 < n; q0 += chunk) {
+    const int m = std::min(chunk, n - q0);
+    double* hp = packed + (size_t)q0 * h->box_len;
+    double* dp = device_ptr ? hp : h->d_stage;
+    if (up) {
+      if (!device_ptr) CK(cudaMemcpyAsync(dp, hp, (size_t)m * box_bytes, cudaMemcpyHostToDevice, h->stream));
+      Launch L_(h, "unpack");
+      DISPATCH_NC(h, NC, { k_unpack<NC><<<m, 256, 0, h->stream>>>(h->d_cc[var], h->d_stage_slots + q0, m, dp); });
+    } else {
+      {
+        Launch L_(h, "pack");
+        DISPATCH_NC(h, NC, { k_pack<NC><<<m, 256, 0, h->stream>>>(h->d_cc[var], h->d_stage_slots + q0, m, dp); });
+      }
+      if (!device_ptr) CK(cudaMemcpyAsync(hp, dp, (size_t)m * box_bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+  }
+  if (up && var == AFMG_TMP) h->resid_fresh = false;
+  if (up) h->resid_fresh = false;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));  // slots vector and (pageable) host buffers must outlive the copies
+  return AFMG_OK;
+}
+
+int afmg_upload(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, const double* packed) {
+  return transfer(h, var, n, box_id, const_cast<double*>(packed), true, false);
+}
+int afmg_download(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, double* packed) {
+  return transfer(h, var, n, box_id, packed, false, false);
+}
+int afmg_upload_device(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, const double* packed) {
+  return transfer(h, var, n, box_id, const_cast<double*>(packed), true, true);
+}
+int afmg_download_device(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, double* packed) {
+  return transfer(h, var, n, box_id, packed, false, true);
+}
+
+int afmg_clear(afmg_handle* h, int32_t var) {
+  if (!h) return AFMG_ERR_ARG;
+  if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
+  if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemsetAsync(h->d_cc[var], 0, (size_t)h->nslots * h->box_len * sizeof(double), h->stream));
+  h->resid_fresh = false;
+  return finish_op(h);
+}
+
+int afmg_fas_vcycle_async(afmg_handle* h, int32_t set_residual, int32_t highest_lvl, int32_t n_cycles) {
+  if (!h) return AFMG_ERR_ARG;
+  int rc = ensure_ready(h);
+  if (rc) return rc;
+  CK(cudaSetDevice(h->device));
+  const int max_lvl = highest_lvl > 0 ? highest_lvl : h->L;
+  if ((rc = check_lvl(h, max_lvl))) return rc;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  rc = run_graph(h, {0, set_residual ? 1 : 0, max_lvl}, n_cycles, [&] { enq_vcycle(h, set_residual != 0, max_lvl); });
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->ev_valid = true;
+  h->resid_fresh = set_residual && max_lvl == h->L;
+  return AFMG_OK;
+}
+
+int afmg_fas_fmg_async(afmg_handle* h, int32_t set_residual, int32_t have_guess, int32_t n_cycles) {
+  if (!h) return AFMG_ERR_ARG;
+  int rc = ensure_ready(h);
+  if (rc) return rc;
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  rc = run_graph(h, {1, set_residual ? 1 : 0, have_guess ? 1 : 0}, n_cycles,
+                 [&] { enq_fmg(h, set_residual != 0, have_guess != 0); });
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->ev_valid = true;
+  h->resid_fresh = set_residual != 0;
+  return AFMG_OK;
+}
+
+int afmg_sync(afmg_handle* h) {
+  if (!h) return AFMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  return finish_op(h);
+}
+
+int afmg_fas_vcycle(afmg_handle* h, int32_t set_residual, int32_t highest_lvl, int32_t standalone) {
+  (void)standalone;  // mg_use / done_with_mg bookkeeping lives in the Fortran shim
+  int rc = afmg_fas_vcycle_async(h, set_residual, highest_lvl, 1);
+  if (rc) return rc;
+  return afmg_sync(h);
+}
+
+int afmg_fas_fmg(afmg_handle* h, int32_t set_residual, int32_t have_guess) {
+  int rc = afmg_fas_fmg_async(h, set_residual, have_guess, 1);
+  if (rc) return rc;
+  return afmg_sync(h);
+}
+
+// ---- single operations ------------------------------------------------------------------------------
+#define SINGLE_OP_PROLOGUE()          \
+  if (!h) return AFMG_ERR_ARG;        \
+  {                                   \
+    int rc_ = ensure_ready(h);        \
+    if (rc_) return rc_;              \
+  }                                   \
+  CK(cudaSetDevice(h->device));       \
+  h->resid_fresh = false;
+
+int afmg_gsrb_boxes(afmg_handle* h, int32_t lvl, int32_t type_cycle) {
+  SINGLE_OP_PROLOGUE();
+  int rc = check_lvl(h, lvl);
+  if (rc) return rc;
+  if (type_cycle != 1 && type_cycle != 3) return h->fail(AFMG_ERR_ARG, "gsrb_boxes: invalid cycle type");
+  enq_rb_prepare(h, lvl);
+  enq_gsrb_boxes(h, lvl, type_cycle == 3);
+  return finish_op(h);
+}
+
+int afmg_gsrb_halfsweep(afmg_handle* h, int32_t lvl, int32_t redblack) {
+  SINGLE_OP_PROLOGUE();
+  int rc = check_lvl(h, lvl);
+  if (rc) return rc;
+  enq_rb_prepare(h, lvl);
+  enq_gsrb(h, lvl, redblack);
+  return finish_op(h);
+}
+
+int afmg_gc_lvl(afmg_handle* h, int32_t lvl, int32_t var, int32_t corners) {
+  SINGLE_OP_PROLOGUE();
+  int rc = check_lvl(h, lvl);
+  if (rc) return rc;
+  if (var != AFMG_PHI) return h->fail(AFMG_ERR_UNSUPPORTED, "ghost cells are only defined for phi on this path");
+  enq_rb_prepare(h, lvl);
+  enq_gc(h, lvl, var, corners, 0);
+  return finish_op(h);
+}
+
+int afmg_update_coarse(afmg_handle* h, int32_t lvl, int32_t with_tmp) {
+  SINGLE_OP_PROLOGUE();
+  int rc = check_lvl(h, lvl);
+  if (rc) return rc;
+  if (lvl < 2) return h->fail(AFMG_ERR_ARG, "update_coarse needs lvl >= 2");
+  enq_update_coarse(h, lvl, with_tmp != 0);
+  return finish_op(h);
+}
+
+int afmg_correct_children(afmg_handle* h, int32_t lvl_parents) {
+  SINGLE_OP_PROLOGUE();
+  int rc = check_lvl(h, lvl_parents);
+  if (rc) return rc;
+  enq_correct(h, lvl_parents);
+  return finish_op(h);
+}
+
+int afmg_residual_lvl(afmg_handle* h, int32_t lvl) {
+  SINGLE_OP_PROLOGUE();
+  int rc = check_lvl(h, lvl);
+  if (rc) return rc;
+  enq_residual(h, lvl, lvl, false);
+  return finish_op(h);
+}
+
+int afmg_solve_coarse_grid(afmg_handle* h) {
+  SINGLE_OP_PROLOGUE();
+  enq_coarse(h);
+  return finish_op(h);
+}
+
+int afmg_init_phi_rhs(afmg_handle* h) {
+  SINGLE_OP_PROLOGUE();
+  enq_init_phi_rhs(h);
+  return finish_op(h);
+}
+
+int afmg_max_abs(afmg_handle* h, int32_t var, double* out) {
+  if (!h || !out) return AFMG_ERR_ARG;
+  if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
+  if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
+  CK(cudaSetDevice(h->device));
+  unsigned long long bits = 0;
+  if (var == AFMG_TMP && h->resid_fresh) {
+    CK(cudaMemcpyAsync(&bits, h->d_scal, sizeof bits, cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    CK(cudaMemsetAsync(h->d_scal + 1, 0, sizeof(unsigned long long), h->stream));
+    {
+      Launch L_(h, "maxabs");
+      DISPATCH_NC(h, NC,
+                  { k_maxabs<NC><<<h->nslots, 256, 0, h->stream>>>(h->cx, 0, h->nslots, var, h->d_scal + 1); });
+    }
+    CK(cudaMemcpyAsync(&bits, h->d_scal + 1, sizeof bits, cudaMemcpyDeviceToHost, h->stream));
+  }
+  int rc = finish_op(h);
+  if (rc) return rc;
+  std::memcpy(out, &bits, sizeof bits);
+  return AFMG_OK;
+}
+
+int afmg_tree_sum(afmg_handle* h, int32_t var, double* out) {
+  if (!h || !out) return AFMG_ERR_ARG;
+  if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
+  if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
+  CK(cudaSetDevice(h->device));
+  {
+    Launch L_(h, "sum");
+    DISPATCH_NC(h, NC, { k_box_sums<NC><<<h->nslots, 128, 0, h->stream>>>(h->cx, 0, h->nslots, var, h->d_boxsum); });
+  }
+  std::vector<double> sums(h->nslots);
+  CK(cudaMemcpyAsync(sums.data(), h->d_boxsum, (size_t)h->nslots * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  int rc = finish_op(h);
+  if (rc) return rc;
+  // af_tree_sum_cc: my_sum += fac(lvl) * box_sum over leaves, in level / list order
+  double s = 0.0;
+  for (int l = 1; l <= h->L; ++l) {
+    double fac = 1.0;
+    for (int d = 0; d < 3; ++d) fac *= h->o.dr_base[d] * std::pow(0.5, l - 1);
+    for (int q = h->lvl_off[l]; q < h->lvl_off[l + 1]; ++q)
+      if (h->h_child0[q] < 0) s = s + fac * sums[q];
+  }
+  *out = s;
+  return AFMG_OK;
+}
+
+int64_t afmg_kernel_launches(const afmg_handle* h) { return h ? h->launches : 0; }
+
+int afmg_last_cycle_ms(afmg_handle* h, double* ms) {
+  if (!h || !ms) return AFMG_ERR_ARG;
+  if (!h->ev_valid) return h->fail(AFMG_ERR_STATE, "no cycle has been run");
+  CK(cudaEventSynchronize(h->ev1));
+  float f = 0;
+  CK(cudaEventElapsedTime(&f, h->ev0, h->ev1));
+  *ms = f;
+  return AFMG_OK;
+}
+
+int afmg_set_profiling(afmg_handle* h, int32_t on) {
+  if (!h) return AFMG_ERR_ARG;
+  CK(cudaStreamSynchronize(h->stream));
+  prof_resolve(h);
+  h->profiling = on != 0;
+  if (on) h->prof.clear();
+  return AFMG_OK;
+}
+
+int afmg_profile(afmg_handle* h, int32_t cap, char (*names)[32], double* ms, int64_t* calls, int32_t* n) {
+  if (!h || !n) return AFMG_ERR_ARG;
+  prof_resolve(h);
+  int k = 0;
+  for (auto& kv : h->prof) {
+    if (k >= cap) break;
+    std::snprintf(names[k], 32, "%s", kv.first.c_str());
+    ms[k] = kv.second.ms;
+    calls[k] = kv.second.calls;
+    ++k;
+  }
+  *n = k;
+  return AFMG_OK;
+}
+
+int afmg_cell_updates(afmg_handle* h, int32_t highest_lvl, int32_t fmg, double* out) {
+  if (!h || !out) return AFMG_ERR_ARG;
+  if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
+  const int maxl = highest_lvl > 0 ? highest_lvl : h->L;
+  const double ncell = (double)h->o.n_cell * h->o.n_cell * h->o.n_cell;
+  auto vc = [&](int m) {
+    double s = 0;
+    for (int l = 2; l <= m; ++l) s += (double)(h->o.n_cycle_down + h->o.n_cycle_up) * nlev(h, l) * ncell;
+    return s;
+  };
+  double s = 0;
+  if (fmg) for (int m = 2; m <= h->L; ++m) s += vc(m);
+  else s = vc(maxl);
+  *out = s;
+  return AFMG_OK;
+}
+
+int32_t afmg_layout_offset(int32_t ndim, int32_t nc, int32_t i, int32_t j, int32_t k) {
+  if (ndim == 3) {
+    switch (nc) {
+      case 4: return Lay3<4>::cell(i, j, k);
+      case 8: return Lay3<8>::cell(i, j, k);
+      case 16: return Lay3<16>::cell(i, j, k);
+      case 32: return Lay3<32>::cell(i, j, k);
+    }
+  } else if (ndim == 2) {
+    switch (nc) {
+      case 4: return Lay2<4>::cell(i, j);
+      case 8: return Lay2<8>::cell(i, j);
+      case 16: return Lay2<16>::cell(i, j);
+      case 32: return Lay2<32>::cell(i, j);
+    }
+  }
+  return -1;
+}
+
+int32_t afmg_layout_box_len(int32_t ndim, int32_t nc) {
+  return ndim == 3 ? (nc + 2) * (nc + 2) * (nc + 2) : (nc + 2) * (nc + 2);
+}
+
+int32_t afmg_slot_of_box(const afmg_handle* h, int32_t box_id) {
+  if (!h || !h->have_tree || box_id < 1 || box_id > h->highest_id) return -1;
+  return h->id2slot[box_id];
+}
+
+int afmg_comm_unique_id(char id[128]) {
+  std::memset(id, 0, 128);
+  return AFMG_ERR_UNSUPPORTED;
+}
+int afmg_comm_init(afmg_handle* h, int32_t n_ranks, int32_t, const char*) {
+  if (!h) return AFMG_ERR_ARG;
+  if (n_ranks == 1) return AFMG_OK;
+  return h->fail(AFMG_ERR_UNSUPPORTED, "multi-GPU partitioning is not part of this build yet");
+}
+int32_t afmg_owner_of_box(const afmg_handle* h, int32_t box_id) {
+  if (!h || !h->have_tree || box_id < 1 || box_id > h->highest_id || h->id2slot[box_id] < 0) return -1;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,746 @@
+// sm_100a kernels of the 3D FAS multigrid path.  Everything is fp64 and bandwidth bound; no
+// tensor cores.  Compiled with -fmad=false so that every expression rounds exactly like the
+// reference's gfortran -O2 build (no FMA contraction on x86-64): results are bit-identical to the
+// CPU oracle except downstream of the coarse-grid solve.
+//
+// Conventions: "slot" = position of a box in the device arrays (level-major, Morton order inside a
+// level), box record layout = layout.cuh.  Face ghost cells of a box whose neighbour exists are
+// written by the NEIGHBOUR's half-sweep kernel ("push"); ghost cells on physical / refinement
+// boundaries are computed by the box's own CTA from a rule row  ghost = (c0*B + c1*x1) + c2*x2,
+// where B is the boundary value (bc_val) or the interpolated coarse value (k_rb_prepare).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "layout.cuh"
+
+namespace afmg {
+
+enum { V_PHI = 0, V_RHS = 1, V_TMP = 2, V_EPS = 3 };
+
+struct DevCtx {
+  double* cc[4];         // per variable: nslots * BOX doubles
+  const int* nbr;        // [nslots*6]  >= 0: neighbour slot; -1: own-ghost rule row in aux
+  const int* aux;        // [nslots*6]  rule row
+  const int* nmat;       // [nslots*27] >= 0 slot, -1 physical boundary, -2 no box (coarser there)
+  const int* parent;     // [nslots]    parent slot (-1 on level 1)
+  const int* child0;     // [nslots]    slot of first child, -1 for leaves
+  const int* coff;       // [nslots]    child index 0..7 inside the parent (bit d: upper half in dim d)
+  const int* lvl;        // [nslots]
+  const double* coef;    // [(L+1)*8]   per level: c1..c7 of the constant 7-point stencil, 1/c1
+  const double* rule_c;  // [nrules*3]  c0, c1, c2
+  double* rule_B;        // [nrules*NC2] boundary values / interpolated coarse values, index (a-1)+(b-1)*nc
+  const int* rb_slot;    // [nrb] fine slot of refinement-boundary face r (rule row = rb_row0 + r)
+  const int* rb_face;    // [nrb] face 0..5
+  int rb_row0;           // first rule row that is a refinement-boundary face
+  const double* pcoef;   // [8] constant prolongation coefficients
+  int pshape;            // 8 = stencil_prolong_248 (linear), 4 = stencil_prolong_234 (sparse)
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1D TMA bulk copy (cp.async.bulk -> SASS UBLKCP)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// neighbour offset tables
+__device__ __forceinline__ int nmat_index(int dx, int dy, int dz) { return (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1); }
+
+// ---------------------------------------------------------------------------------------------
+// k_gsrb: one red-black half-sweep (stencil_gsrb_357, afivo/src/m_af_stencil.f90:956-973) over the
+// boxes [slot0, slot0+nbox) of one level, fused with the side ghost-cell fill that follows it in
+// gsrb_boxes (afivo/src/m_af_multigrid.f90:648-687; af_gc_box m_af_ghostcell.f90:64-120 without
+// corners).  C = colour updated = redblack & 1.
+//   - the opposite colour block (interior + 6 face segments) arrives by one TMA bulk copy
+//   - thread (m, j) owns the column of nc cells of colour C over k; rhs comes straight from global
+//     into registers, new values go straight back to global (256 B per warp, coalesced)
+//   - boundary-layer values are pushed into the neighbours' ghost face segments (copy_from_nb,
+//     m_af_ghostcell.f90:654-669); physical / refinement faces apply their rule (bc_to_gc :173-279,
+//     mg_sides_rb m_af_multigrid.f90:383-459)
+// ---------------------------------------------------------------------------------------------
+template <int NC, int BPC>
+__global__ void __launch_bounds__(BPC* NC* NC / 2) k_gsrb(DevCtx cx, int slot0, int nbox, int C, int lvl) {
+  using L = Lay3<NC>;
+  constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX, TPB = H * NC;
+  extern __shared__ __align__(128) double smem[];
+  __shared__ uint64_t bar;
+  const int tid = threadIdx.x;
+  const int box0 = blockIdx.x * BPC;
+  const int nhere = min(BPC, nbox - box0);
+  double* const phi = cx.cc[V_PHI];
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, (uint32_t)(nhere * COL * 8));
+    for (int b = 0; b < nhere; ++b)
+      bulk_g2s(smem + b * COL, phi + (size_t)(slot0 + box0 + b) * BOX + (1 - C) * COL, COL * 8, &bar);
+  }
+  const int b = tid / TPB, t = tid % TPB;
+  if (b >= nhere) return;
+  const int m = t % H, j = t / H + 1;
+  const int slot = slot0 + box0 + b;
+  const double* const S = smem + b * COL;
+  const double* const grhs = cx.cc[V_RHS] + (size_t)slot * BOX + C * COL;
+  double* const gC = phi + (size_t)slot * BOX + C * COL;
+  double* const gN = phi + (size_t)slot * BOX + (1 - C) * COL;
+
+  double r[NC];
+#pragma unroll
+  for (int k = 1; k <= NC; ++k) r[k - 1] = __ldg(grhs + L::iidx(m, j, k));
+
+  int nbf[6], ax[6];
+#pragma unroll
+  for (int f = 0; f < 6; ++f) {
+    nbf[f] = __ldg(cx.nbr + slot * 6 + f);
+    ax[f] = __ldg(cx.aux + slot * 6 + f);
+  }
+  const double* cf = cx.coef + 8 * lvl;
+  const double c2 = cf[1], c3 = cf[2], c4 = cf[3], c5 = cf[4], c6 = cf[5], c7 = cf[6], inv = cf[7];
+
+  mbar_wait(&bar, 0);
+
+  // push value v (colour C, boundary layer) through face f at face index fi
+  auto push = [&](int f, int fi, double v) { phi[(size_t)nbf[f] * BOX + C * COL + NI + (f ^ 1) * NF + fi] = v; };
+  // rule for face f: layer-1 cell changed -> ghost of the other colour; x2 = unchanged layer-2 value
+  auto rule1 = [&](int f, int fi, int bidx, double x1new, double x2) {
+    const double* rc = cx.rule_c + 3 * ax[f];
+    const double B = cx.rule_B[(size_t)ax[f] * L::NC2 + bidx];
+    gN[NI + f * NF + fi] = (rc[0] * B + rc[1] * x1new) + rc[2] * x2;
+  };
+  // layer-2 cell changed -> ghost of colour C; x1 = unchanged layer-1 value
+  auto rule2 = [&](int f, int fi, int bidx, double x1, double x2new) {
+    const double* rc = cx.rule_c + 3 * ax[f];
+    const double B = cx.rule_B[(size_t)ax[f] * L::NC2 + bidx];
+    gC[NI + f * NF + fi] = (rc[0] * B + rc[1] * x1) + rc[2] * x2new;
+  };
+
+  double s_km1 = S[NI + 4 * NF + (j - 1) * H + m];
+  double s_k = S[L::iidx(m, j, 1)];
+#pragma unroll
+  for (int k = 1; k <= NC; ++k) {
+    const int idx = L::iidx(m, j, k);
+    const int pi = (C + j + k) & 1;  // 1: i = 2m+1, 0: i = 2m+2
+    const int i = 2 * m + 2 - pi;
+    const double s_kp1 = (k < NC) ? S[idx + NC * H] : S[NI + 5 * NF + (j - 1) * H + m];
+    const double ym = (j > 1) ? S[idx - H] : S[NI + 2 * NF + (k - 1) * H + m];
+    const double yp = (j < NC) ? S[idx + H] : S[NI + 3 * NF + (k - 1) * H + m];
+    const int fx = (k - 1) * H + ((j - 1) >> 1);
+    double xm, xp;
+    if (pi) {
+      xm = (m > 0) ? S[idx - 1] : S[NI + 0 * NF + fx];
+      xp = s_k;
+    } else {
+      xm = s_k;
+      xp = (m < H - 1) ? S[idx + 1] : S[NI + 1 * NF + fx];
+    }
+    double acc = r[k - 1];
+    acc = acc - c2 * xm;
+    acc = acc - c3 * xp;
+    acc = acc - c4 * ym;
+    acc = acc - c5 * yp;
+    acc = acc - c6 * s_km1;
+    acc = acc - c7 * s_kp1;
+    const double v = acc * inv;
+    gC[idx] = v;
+
+    // ---- z faces
+    const int fz = (j - 1) * H + m, bz = (i - 1) + (j - 1) * NC;
+    if (k == 1) {
+      if (nbf[4] >= 0) push(4, fz, v);
+      else rule1(4, fz, bz, v, s_kp1);
+    }
+    if (k == 2 && nbf[4] < 0) rule2(4, fz, bz, s_km1, v);
+    if (k == NC) {
+      if (nbf[5] >= 0) push(5, fz, v);
+      else rule1(5, fz, bz, v, s_km1);
+    }
+    if (k == NC - 1 && nbf[5] < 0) rule2(5, fz, bz, s_kp1, v);
+    // ---- y faces
+    const int fy = (k - 1) * H + m, by = (i - 1) + (k - 1) * NC;
+    if (j == 1) {
+      if (nbf[2] >= 0) push(2, fy, v);
+      else rule1(2, fy, by, v, yp);
+    }
+    if (j == 2 && nbf[2] < 0) rule2(2, fy, by, ym, v);
+    if (j == NC) {
+      if (nbf[3] >= 0) push(3, fy, v);
+      else rule1(3, fy, by, v, ym);
+    }
+    if (j == NC - 1 && nbf[3] < 0) rule2(3, fy, by, yp, v);
+    // ---- x faces
+    const int bx = (j - 1) + (k - 1) * NC;
+    if (m == 0) {
+      if (pi) {  // i == 1
+        if (nbf[0] >= 0) push(0, fx, v);
+        else rule1(0, fx, bx, v, xp);
+      } else if (nbf[0] < 0) {  // i == 2
+        rule2(0, fx, bx, xm, v);
+      }
+    }
+    if (m == H - 1) {
+      if (!pi) {  // i == NC
+        if (nbf[1] >= 0) push(1, fx, v);
+        else rule1(1, fx, bx, v, xm);
+      } else if (nbf[1] < 0) {  // i == NC-1
+        rule2(1, fx, bx, xp, v);
+      }
+    }
+    s_km1 = s_k;
+    s_k = s_kp1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic cell access on a box record in global memory (non-hot kernels)
+// ---------------------------------------------------------------------------------------------
+template <int NC>
+__device__ __forceinline__ double ldcell(const double* box, int i, int j, int k) {
+  return box[Lay3<NC>::cell(i, j, k)];
+}
+
+// L phi at interior cell (i,j,k): stencil_apply_357 (m_af_stencil.f90:462-487), left to right
+template <int NC>
+__device__ __forceinline__ double apply357(const double* box, const double* cf, double c1, int i, int j, int k) {
+  double acc = c1 * ldcell<NC>(box, i, j, k);
+  acc = acc + cf[1] * ldcell<NC>(box, i - 1, j, k);
+  acc = acc + cf[2] * ldcell<NC>(box, i + 1, j, k);
+  acc = acc + cf[3] * ldcell<NC>(box, i, j - 1, k);
+  acc = acc + cf[4] * ldcell<NC>(box, i, j + 1, k);
+  acc = acc + cf[5] * ldcell<NC>(box, i, j, k - 1);
+  acc = acc + cf[6] * ldcell<NC>(box, i, j, k + 1);
+  return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_rb_prepare: for every refinement-boundary face of a level, interpolate the coarse neighbour's
+// boundary layer to the fine face (first half of mg_sides_rb, m_af_multigrid.f90:294-380).  The
+// coarse level is frozen while the fine level is smoothed, so this runs once per gsrb_boxes /
+// af_gc_lvl group.  One CTA per face, one thread per fine face cell.
+// ---------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void k_rb_prepare(DevCtx cx, int r0, int nr, int var) {
+  using L = Lay3<NC>;
+  constexpr int H = L::H;
+  const int r = r0 + blockIdx.x;
+  if (blockIdx.x >= nr) return;
+  const int s = cx.rb_slot[r], f = cx.rb_face[r];
+  const int p = cx.parent[s];
+  const int pn = cx.nbr[p * 6 + f];  // coarse neighbour (exists by 2:1 balance)
+  const int d = f >> 1;
+  const int layer = (f & 1) ? 1 : NC;
+  const int cof = cx.coff[s];
+  const int ta = (d == 0) ? 1 : 0, tb = (d == 2) ? 1 : 2;
+  const int coa = ((cof >> ta) & 1) * H, cob = ((cof >> tb) & 1) * H;
+  const double* cb = cx.cc[var] + (size_t)pn * L::BOX;
+  auto T = [&](int x, int y) {
+    int q[3];
+    q[d] = layer;
+    q[ta] = coa + x;
+    q[tb] = cob + y;
+    return ldcell<NC>(cb, q[0], q[1], q[2]);
+  };
+  double* out = cx.rule_B + (size_t)(cx.rb_row0 + r) * L::NC2;
+  for (int n = threadIdx.x; n < L::NC2; n += blockDim.x) {
+    const int a = n % NC + 1, b = n / NC + 1;
+    const int ia = (a + 1) >> 1, ib = (b + 1) >> 1;
+    const double t0 = T(ia, ib);
+    const double g1 = 0.125 * (T(ia + 1, ib) - T(ia - 1, ib));
+    const double g2 = 0.125 * (T(ia, ib + 1) - T(ia, ib - 1));
+    double v = (a & 1) ? (t0 - g1) : (t0 + g1);
+    v = (b & 1) ? (v - g2) : (v + g2);
+    out[n] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ghost cells by gathering (af_gc_box, m_af_ghostcell.f90:64-170): sides, then edges and corners.
+// ---------------------------------------------------------------------------------------------
+template <int NC>
+__device__ void gc_sides(const DevCtx& cx, int slot, double* var_base) {
+  using L = Lay3<NC>;
+  double* box = var_base + (size_t)slot * L::BOX;
+  for (int n = threadIdx.x; n < 6 * L::NC2; n += blockDim.x) {
+    const int f = n / L::NC2, rr = n % L::NC2;
+    const int a = rr % NC + 1, b = rr / NC + 1;
+    const int d = f >> 1, hi = f & 1;
+    const int ta = (d == 0) ? 1 : 0, tb = (d == 2) ? 1 : 2;
+    int q[3];
+    q[ta] = a;
+    q[tb] = b;
+    const int nb = cx.nbr[slot * 6 + f];
+    double v;
+    if (nb >= 0) {  // copy_from_nb: ghost (g) <- neighbour cell g - dnb*nc
+      q[d] = hi ? 1 : NC;
+      v = ldcell<NC>(var_base + (size_t)nb * L::BOX, q[0], q[1], q[2]);
+    } else {
+      const int row = cx.aux[slot * 6 + f];
+      const double* rc = cx.rule_c + 3 * row;
+      const double B = cx.rule_B[(size_t)row * L::NC2 + rr];
+      q[d] = hi ? NC : 1;
+      const double x1 = ldcell<NC>(box, q[0], q[1], q[2]);
+      q[d] = hi ? NC - 1 : 2;
+      const double x2 = ldcell<NC>(box, q[0], q[1], q[2]);
+      v = (rc[0] * B + rc[1] * x1) + rc[2] * x2;
+    }
+    box[L::face(f, a, b)] = v;
+  }
+}
+
+// af_gc_box_corner (m_af_ghostcell.f90:125-170): needs the box's own face ghosts (call after a
+// __syncthreads following gc_sides, or in a later kernel)
+template <int NC>
+__device__ void gc_edges_corners(const DevCtx& cx, int slot, double* var_base) {
+  using L = Lay3<NC>;
+  double* box = var_base + (size_t)slot * L::BOX;
+  for (int n = threadIdx.x; n < 12 * NC + 8; n += blockDim.x) {
+    if (n < 12 * NC) {
+      const int e = n / NC, pos = n % NC + 1, dim = e >> 2;
+      const int o1 = (dim == 0) ? 1 : 0, o2 = (dim == 2) ? 1 : 2;
+      int dir[3] = {0, 0, 0}, q[3];
+      dir[o1] = (e & 1) ? 1 : -1;
+      dir[o2] = (e & 2) ? 1 : -1;
+      q[dim] = pos;
+      q[o1] = (e & 1) ? NC + 1 : 0;
+      q[o2] = (e & 2) ? NC + 1 : 0;
+      const int nb = cx.nmat[slot * 27 + nmat_index(dir[0], dir[1], dir[2])];
+      double v;
+      if (nb >= 0) {
+        v = ldcell<NC>(var_base + (size_t)nb * L::BOX, q[0] - dir[0] * NC, q[1] - dir[1] * NC, q[2] - dir[2] * NC);
+      } else {  // af_edge_gc_extrap (:885-924): a + b - c
+        int qa[3] = {q[0], q[1], q[2]}, qb[3] = {q[0], q[1], q[2]}, qc[3] = {q[0], q[1], q[2]};
+        qa[o1] -= dir[o1];
+        qb[o2] -= dir[o2];
+        qc[o1] -= dir[o1];
+        qc[o2] -= dir[o2];
+        // the reference orders the two face-ghost terms by (dim+1, dim+2) cyclically
+        const int c1 = (dim + 1) % 3;
+        const double va = ldcell<NC>(box, qa[0], qa[1], qa[2]);
+        const double vb = ldcell<NC>(box, qb[0], qb[1], qb[2]);
+        const double vc = ldcell<NC>(box, qc[0], qc[1], qc[2]);
+        v = (c1 == o1) ? (va + vb - vc) : (vb + va - vc);
+      }
+      box[L::edge(e, pos)] = v;
+    } else {
+      const int c = n - 12 * NC;
+      const int dx = (c & 1) ? 1 : -1, dy = (c & 2) ? 1 : -1, dz = (c & 4) ? 1 : -1;
+      const int qi = (c & 1) ? NC + 1 : 0, qj = (c & 2) ? NC + 1 : 0, qk = (c & 4) ? NC + 1 : 0;
+      const int nb = cx.nmat[slot * 27 + nmat_index(dx, dy, dz)];
+      double v;
+      if (nb >= 0) {
+        v = ldcell<NC>(var_base + (size_t)nb * L::BOX, qi - dx * NC, qj - dy * NC, qk - dz * NC);
+      } else {  // af_corner_gc_extrap (:860-879)
+        v = ldcell<NC>(box, qi, qj - dy, qk - dz) + ldcell<NC>(box, qi - dx, qj, qk - dz) +
+            ldcell<NC>(box, qi - dx, qj - dy, qk) - 2 * ldcell<NC>(box, qi - dx, qj - dy, qk - dz);
+      }
+      box[L::corner(c)] = v;
+    }
+  }
+}
+
+// k_gc: af_gc_lvl (m_af_ghostcell.f90:49-61) for boxes [slot0, slot0+nbox), optionally followed, for
+// boxes that have children, by the parent part of update_coarse (m_af_multigrid.f90:724-737):
+//   rhs = L(phi) + tmp (interior), tmp = phi (full box) when mode == 1
+//   rhs = L(phi) + tmp only (set_coarse_phi_rhs :769-774) when mode == 2
+// One CTA per box.
+template <int NC>
+__global__ void k_gc(DevCtx cx, int slot0, int nbox, int var, int corners, int mode) {
+  using L = Lay3<NC>;
+  const int slot = slot0 + blockIdx.x;
+  if ((int)blockIdx.x >= nbox) return;
+  double* vb = cx.cc[var];
+  gc_sides<NC>(cx, slot, vb);
+  if (corners) {
+    __syncthreads();
+    gc_edges_corners<NC>(cx, slot, vb);
+  }
+  if (mode == 0 || cx.child0[slot] < 0) return;
+  __syncthreads();
+  const double* phi = cx.cc[V_PHI] + (size_t)slot * L::BOX;
+  double* rhs = cx.cc[V_RHS] + (size_t)slot * L::BOX;
+  double* tmp = cx.cc[V_TMP] + (size_t)slot * L::BOX;
+  const double* cf = cx.coef + 8 * cx.lvl[slot];
+  const double c1 = cf[0];
+  for (int q = threadIdx.x; q < L::BOX; q += blockDim.x) {
+    const bool is_interior = (q < L::OFF_E) && ((q % L::COL) < L::NI);
+    if (is_interior) {
+      int i, j, k;
+      L::uncell(q, i, j, k);
+      const double lp = apply357<NC>(phi, cf, c1, i, j, k);
+      rhs[q] = lp + tmp[q];
+    }
+    if (mode == 1) tmp[q] = phi[q];
+  }
+}
+
+// edges + corners only (after the last half-sweep of an upward gsrb_boxes, or every half-sweep when
+// mg%use_corners, m_af_multigrid.f90:676-684)
+template <int NC>
+__global__ void k_edges_corners(DevCtx cx, int slot0, int nbox, int var) {
+  const int slot = slot0 + blockIdx.x;
+  if ((int)blockIdx.x >= nbox) return;
+  gc_edges_corners<NC>(cx, slot, cx.cc[var]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_restrict: child part of update_coarse / set_coarse_phi_rhs (m_af_multigrid.f90:704-716, 754-761):
+// residual r = rhs - L(phi) (residual_box :801-810), restrict r into the parent's tmp and phi into
+// the parent's phi (af_restrict_box, m_af_restrict.f90:120-133: 0.125 * sum in array element order).
+// The child's tmp is left untouched (the reference saves and restores it) unless keep_res != 0
+// (set_coarse_phi_rhs leaves the residual there).  One CTA per child box, one thread per coarse cell.
+// ---------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void k_restrict(DevCtx cx, int slot0, int nbox, int keep_res) {
+  using L = Lay3<NC>;
+  constexpr int H = L::H;
+  const int slot = slot0 + blockIdx.x;
+  if ((int)blockIdx.x >= nbox) return;
+  const double* phi = cx.cc[V_PHI] + (size_t)slot * L::BOX;
+  const double* rhs = cx.cc[V_RHS] + (size_t)slot * L::BOX;
+  double* tmp = cx.cc[V_TMP] + (size_t)slot * L::BOX;
+  const int p = cx.parent[slot], cof = cx.coff[slot];
+  double* pphi = cx.cc[V_PHI] + (size_t)p * L::BOX;
+  double* ptmp = cx.cc[V_TMP] + (size_t)p * L::BOX;
+  const int ox = (cof & 1) * H, oy = ((cof >> 1) & 1) * H, oz = ((cof >> 2) & 1) * H;
+  const double* cf = cx.coef + 8 * cx.lvl[slot];
+  const double c1 = cf[0];
+  for (int n = threadIdx.x; n < H * H * H; n += blockDim.x) {
+    const int ic = n % H + 1, jc = (n / H) % H + 1, kc = n / (H * H) + 1;
+    double sr = 0.0, sp = 0.0;
+#pragma unroll
+    for (int dk = 0; dk < 2; ++dk)
+#pragma unroll
+      for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+        for (int di = 0; di < 2; ++di) {
+          const int i = 2 * ic - 1 + di, j = 2 * jc - 1 + dj, k = 2 * kc - 1 + dk;
+          const int q = L::interior(i, j, k);
+          const double lp = apply357<NC>(phi, cf, c1, i, j, k);
+          const double res = rhs[q] - lp;
+          if (keep_res) tmp[q] = res;
+          sr = sr + res;
+          sp = sp + phi[q];
+        }
+    const int qp = L::interior(ox + ic, oy + jc, oz + kc);
+    ptmp[qp] = 0.125 * sr;
+    pphi[qp] = 0.125 * sp;
+  }
+}
+
+// restriction of one variable only (init_phi_rhs, m_af_multigrid.f90:779-799: phi = 0, restrict rhs)
+template <int NC>
+__global__ void k_restrict_var(DevCtx cx, int slot0, int nbox, int var, int clear_phi) {
+  using L = Lay3<NC>;
+  constexpr int H = L::H;
+  const int slot = slot0 + blockIdx.x;
+  if ((int)blockIdx.x >= nbox) return;
+  const double* src = cx.cc[var] + (size_t)slot * L::BOX;
+  const int p = cx.parent[slot], cof = cx.coff[slot];
+  double* dst = cx.cc[var] + (size_t)p * L::BOX;
+  const int ox = (cof & 1) * H, oy = ((cof >> 1) & 1) * H, oz = ((cof >> 2) & 1) * H;
+  if (clear_phi) {
+    double* phi = cx.cc[V_PHI] + (size_t)slot * L::BOX;
+    for (int q = threadIdx.x; q < L::BOX; q += blockDim.x) phi[q] = 0.0;
+  }
+  for (int n = threadIdx.x; n < H * H * H; n += blockDim.x) {
+    const int ic = n % H + 1, jc = (n / H) % H + 1, kc = n / (H * H) + 1;
+    double s = 0.0;
+#pragma unroll
+    for (int dk = 0; dk < 2; ++dk)
+#pragma unroll
+      for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+        for (int di = 0; di < 2; ++di) s = s + src[L::interior(2 * ic - 1 + di, 2 * jc - 1 + dj, 2 * kc - 1 + dk)];
+    dst[L::interior(ox + ic, oy + jc, oz + kc)] = 0.125 * s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_correct: correct_children (m_af_multigrid.f90:624-646) for parents [slot0, slot0+nbox) that
+// have children: tmp_p = phi_p - tmp_p on the full box, then phi_c += P(tmp_p) for the 8 children
+// (stencil_prolong_248 / _234, m_af_stencil.f90:582-815).  One CTA per parent; the correction is
+// staged in shared memory in plain (nc+2)^3 order.
+// ---------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void k_correct(DevCtx cx, int slot0, int nbox) {
+  using L = Lay3<NC>;
+  constexpr int H = L::H, N2 = NC + 2;
+  extern __shared__ __align__(16) double tile[];  // N2^3
+  const int slot = slot0 + blockIdx.x;
+  if ((int)blockIdx.x >= nbox) return;
+  const int c0 = cx.child0[slot];
+  if (c0 < 0) return;
+  const double* phi = cx.cc[V_PHI] + (size_t)slot * L::BOX;
+  double* tmp = cx.cc[V_TMP] + (size_t)slot * L::BOX;
+  for (int q = threadIdx.x; q < L::BOX; q += blockDim.x) {
+    const double t = phi[q] - tmp[q];
+    tmp[q] = t;
+    int i, j, k;
+    L::uncell(q, i, j, k);
+    tile[(k * N2 + j) * N2 + i] = t;
+  }
+  __syncthreads();
+  const double* pc = cx.pcoef;
+  const int pshape = cx.pshape;
+  for (int ch = 0; ch < 8; ++ch) {
+    double* cphi = cx.cc[V_PHI] + (size_t)(c0 + ch) * L::BOX;
+    const int ox = (ch & 1) * H, oy = ((ch >> 1) & 1) * H, oz = ((ch >> 2) & 1) * H;
+    for (int n = threadIdx.x; n < 2 * L::NI; n += blockDim.x) {
+      const int q = (n < L::NI) ? n : (L::COL + n - L::NI);
+      int i, j, k;
+      L::uncell(q, i, j, k);
+      const int i1 = ox + ((i + 1) >> 1), i2 = i1 + 1 - 2 * (i & 1);
+      const int j1 = oy + ((j + 1) >> 1), j2 = j1 + 1 - 2 * (j & 1);
+      const int k1 = oz + ((k + 1) >> 1), k2 = k1 + 1 - 2 * (k & 1);
+      auto P = [&](int a, int b, int c) { return tile[(c * N2 + b) * N2 + a]; };
+      double acc = cphi[q];
+      if (pshape == 8) {
+        acc = acc + pc[0] * P(i1, j1, k1);
+        acc = acc + pc[1] * P(i2, j1, k1);
+        acc = acc + pc[2] * P(i1, j2, k1);
+        acc = acc + pc[3] * P(i2, j2, k1);
+        acc = acc + pc[4] * P(i1, j1, k2);
+        acc = acc + pc[5] * P(i2, j1, k2);
+        acc = acc + pc[6] * P(i1, j2, k2);
+        acc = acc + pc[7] * P(i2, j2, k2);
+      } else {
+        acc = acc + pc[0] * P(i1, j1, k1);
+        acc = acc + pc[1] * P(i2, j1, k1);
+        acc = acc + pc[2] * P(i1, j2, k1);
+        acc = acc + pc[3] * P(i1, j1, k2);
+      }
+      cphi[q] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_residual: tmp = rhs - L(phi) on the interior of boxes [slot0, slot0+nbox) (any levels)
+// (residual_box, m_af_multigrid.f90:801-810), plus max |tmp| over leaves (af_tree_maxabs_cc,
+// m_af_utils.f90:773-785) accumulated into *maxabs_bits (non-negative doubles order like uint64).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_nonneg(unsigned long long* addr, double v) {
+  atomicMax(addr, (unsigned long long)__double_as_longlong(v));
+}
+
+template <int NC>
+__global__ void k_residual(DevCtx cx, int slot0, int nbox, unsigned long long* maxabs_bits) {
+  using L = Lay3<NC>;
+  const int slot = slot0 + blockIdx.x;
+  if ((int)blockIdx.x >= nbox) return;
+  const double* phi = cx.cc[V_PHI] + (size_t)slot * L::BOX;
+  const double* rhs = cx.cc[V_RHS] + (size_t)slot * L::BOX;
+  double* tmp = cx.cc[V_TMP] + (size_t)slot * L::BOX;
+  const double* cf = cx.coef + 8 * cx.lvl[slot];
+  const double c1 = cf[0];
+  double mx = 0.0;
+  for (int n = threadIdx.x; n < 2 * L::NI; n += blockDim.x) {
+    const int q = (n < L::NI) ? n : (L::COL + n - L::NI);
+    int i, j, k;
+    L::uncell(q, i, j, k);
+    const double lp = apply357<NC>(phi, cf, c1, i, j, k);
+    const double res = rhs[q] - lp;
+    tmp[q] = res;
+    mx = fmax(mx, fabs(res));
+  }
+  if (maxabs_bits && cx.child0[slot] < 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.0) atomic_max_nonneg(maxabs_bits, mx);
+  }
+}
+
+// max |var| over the interior of leaves
+template <int NC>
+__global__ void k_maxabs(DevCtx cx, int slot0, int nbox, int var, unsigned long long* maxabs_bits) {
+  using L = Lay3<NC>;
+  const int slot = slot0 + blockIdx.x;
+  if ((int)blockIdx.x >= nbox || cx.child0[slot] >= 0) return;
+  const double* v = cx.cc[var] + (size_t)slot * L::BOX;
+  double mx = 0.0;
+  for (int n = threadIdx.x; n < 2 * L::NI; n += blockDim.x) {
+    const int q = (n < L::NI) ? n : (L::COL + n - L::NI);
+    mx = fmax(mx, fabs(v[q]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.0) atomic_max_nonneg(maxabs_bits, mx);
+}
+
+// per-leaf-box sums of the interior in (k,j,i) order (af_tree_sum_cc, m_af_utils.f90:966-1027); the
+// host adds fac(lvl) * sum in box order.  One warp per box is plenty (only used by subtract_mean).
+template <int NC>
+__global__ void k_box_sums(DevCtx cx, int slot0, int nbox, int var, double* out) {
+  using L = Lay3<NC>;
+  const int slot = slot0 + blockIdx.x;
+  if ((int)blockIdx.x >= nbox) return;
+  const double* v = cx.cc[var] + (size_t)slot * L::BOX;
+  __shared__ double part[NC * NC];
+  for (int n = threadIdx.x; n < NC * NC; n += blockDim.x) {  // row sums in i order
+    const int j = n % NC + 1, k = n / NC + 1;
+    double s = 0.0;
+    for (int i = 1; i <= NC; ++i) s = s + v[L::interior(i, j, k)];
+    part[n] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int n = 0; n < NC * NC; ++n) s = s + part[n];
+    out[slot] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// streaming helpers on whole box records: copy (af_boxes_copy_cc, m_af_utils.f90:553-563), clear
+// (af_box_clear_cc :385), add constant (subtract_mean, m_af_multigrid.f90:247-257)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_copy(double* __restrict__ dst, const double* __restrict__ src, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = src[i];
+}
+__global__ void k_fill(double* dst, double v, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = v;
+}
+__global__ void k_sub_scalar(double* dst, const double* scalar, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const double s = *scalar;
+  for (; i < n; i += stride) dst[i] = dst[i] - s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack / unpack between the reference's cc(0:nc+1,0:nc+1,0:nc+1) order and the device layout
+// ---------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void k_unpack(double* var_base, const int* slots, int n, const double* packed) {
+  using L = Lay3<NC>;
+  constexpr int N2 = NC + 2;
+  if ((int)blockIdx.x >= n) return;
+  double* box = var_base + (size_t)slots[blockIdx.x] * L::BOX;
+  const double* src = packed + (size_t)blockIdx.x * L::BOX;
+  for (int q = threadIdx.x; q < L::BOX; q += blockDim.x) {
+    int i, j, k;
+    L::uncell(q, i, j, k);
+    box[q] = src[(k * N2 + j) * N2 + i];
+  }
+}
+template <int NC>
+__global__ void k_pack(const double* var_base, const int* slots, int n, double* packed) {
+  using L = Lay3<NC>;
+  constexpr int N2 = NC + 2;
+  if ((int)blockIdx.x >= n) return;
+  const double* box = var_base + (size_t)slots[blockIdx.x] * L::BOX;
+  double* dst = packed + (size_t)blockIdx.x * L::BOX;
+  for (int q = threadIdx.x; q < L::BOX; q += blockDim.x) {
+    int i, j, k;
+    L::uncell(q, i, j, k);
+    dst[(k * N2 + j) * N2 + i] = box[q];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Coarse grid (replaces Hypre, m_coarse_solver.f90): the BC-folded level-1 operator of a constant
+// coefficient Laplace/Helmholtz problem is separable, A = Tx (x) I (x) I + I (x) Ty (x) I + I (x) I (x) Tz
+// (- lambda), so  x = Q diag(1/(lx+ly+lz-lambda)) Q^T b  with the 1D eigenvectors Q = Qx (x) Qy (x) Qz:
+// an exact direct solve ("fast diagonalisation").
+// ---------------------------------------------------------------------------------------------
+struct CoarseCtx {
+  int nx[3];            // coarse grid size in cells
+  int nb[3];            // level-1 boxes per dim
+  const int* bix;       // [nbox1*3] 0-based position of each level-1 box in the coarse grid (box%ix - 1)
+  const double* b2r;    // [nbox1][6][NC2] bc_to_rhs (stencil_handle_boundaries, m_coarse_solver.f90:442-491)
+  const double* Q[3];   // eigenvectors, Q[d][row*n + col], column = eigenvector
+  const double* inv_eig;  // [n] 1 / (lx(i)+ly(j)+lz(k) - lambda)
+  double* v0;           // [n] work vectors
+  double* v1;
+};
+
+// coarse_solver_set_rhs_phi (m_coarse_solver.f90:286-338): b = rhs + bc_to_rhs * bc_val per face
+template <int NC>
+__global__ void k_cs_gather(DevCtx cx, CoarseCtx cs, int nbox1) {
+  using L = Lay3<NC>;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ncell = NC * NC * NC;
+  if (n >= nbox1 * ncell) return;
+  const int bx = n / ncell, r = n % ncell;
+  const int i = r % NC + 1, j = (r / NC) % NC + 1, k = r / (NC * NC) + 1;
+  const double* rhs = cx.cc[V_RHS] + (size_t)bx * L::BOX;  // level-1 boxes occupy slots 0..nbox1-1
+  double t = rhs[L::interior(i, j, k)];
+  const int q[3] = {i, j, k};
+#pragma unroll
+  for (int f = 0; f < 6; ++f) {
+    const int d = f >> 1;
+    if (cx.nbr[bx * 6 + f] >= 0) continue;
+    if (q[d] != ((f & 1) ? NC : 1)) continue;
+    const int ta = (d == 0) ? 1 : 0, tb = (d == 2) ? 1 : 2;
+    const int fi = (q[ta] - 1) + (q[tb] - 1) * NC;
+    const int row = cx.aux[bx * 6 + f];
+    t = t + cs.b2r[((size_t)bx * 6 + f) * L::NC2 + fi] * cx.rule_B[(size_t)row * L::NC2 + fi];
+  }
+  const int gi = cs.bix[bx * 3] * NC + i - 1, gj = cs.bix[bx * 3 + 1] * NC + j - 1, gk = cs.bix[bx * 3 + 2] * NC + k - 1;
+  cs.v0[gi + cs.nx[0] * (gj + cs.nx[1] * gk)] = t;
+}
+
+// out = (M applied along dimension d) in, M = Q^T (trans = 1) or Q (trans = 0); optional scaling of
+// the result by inv_eig (fused into the last forward transform)
+__global__ void k_cs_apply(CoarseCtx cs, const double* in, double* out, int d, int trans, int scale) {
+  const int ntot = cs.nx[0] * cs.nx[1] * cs.nx[2];
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= ntot) return;
+  int q[3] = {n % cs.nx[0], (n / cs.nx[0]) % cs.nx[1], n / (cs.nx[0] * cs.nx[1])};
+  const int stride = (d == 0) ? 1 : (d == 1 ? cs.nx[0] : cs.nx[0] * cs.nx[1]);
+  const int nd = cs.nx[d], o = q[d];
+  const double* Q = cs.Q[d];
+  const int base = n - o * stride;
+  double s = 0.0;
+  for (int p = 0; p < nd; ++p) {
+    const double mval = trans ? Q[p * nd + o] : Q[o * nd + p];
+    s = s + mval * in[base + p * stride];
+  }
+  if (scale) s = s * cs.inv_eig[n];
+  out[n] = s;
+}
+
+// coarse_solver_get_phi (m_coarse_solver.f90:341-358)
+template <int NC>
+__global__ void k_cs_scatter(DevCtx cx, CoarseCtx cs, int nbox1, const double* x) {
+  using L = Lay3<NC>;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ncell = NC * NC * NC;
+  if (n >= nbox1 * ncell) return;
+  const int bx = n / ncell, r = n % ncell;
+  const int i = r % NC + 1, j = (r / NC) % NC + 1, k = r / (NC * NC) + 1;
+  const int gi = cs.bix[bx * 3] * NC + i - 1, gj = cs.bix[bx * 3 + 1] * NC + j - 1, gk = cs.bix[bx * 3 + 2] * NC + k - 1;
+  double* phi = cx.cc[V_PHI] + (size_t)bx * L::BOX;
+  phi[L::interior(i, j, k)] = x[gi + cs.nx[0] * (gj + cs.nx[1] * gk)];
+}
+
+}  // namespace afmg

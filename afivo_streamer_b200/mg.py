@@ -1,0 +1,265 @@
+"""Host-side mirror of the reference's multigrid interface (afivo/src/m_af_multigrid.f90:14-38)
+on top of the C ABI: same names, argument meaning and error behaviour (``error stop`` becomes
+``AfmgError``).
+
+    mg = mg_t(sides_bc=af_bc_dirichlet_zero)          ! type(mg_t) :: mg ; mg%sides_bc => ...
+    mg_init(tree, mg)                                 ! call mg_init(tree, mg)
+    mg.set_cc(I_RHS, ids, rhs)                        ! box%cc(:, :, :, i_rhs) = ...
+    mg_fas_fmg(tree, mg, set_residual=True, have_guess=False)
+    mg_fas_vcycle(tree, mg, set_residual=True)
+    res = af_tree_maxabs_cc(tree, mg, I_TMP)
+
+The tree (``tree.Tree``) is the flat copy of ``af_t``; cell data lives on the GPU and is
+moved with ``set_cc`` / ``get_cc`` in the reference's own box layout cc(0:nc+1, ...).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import AfmgError, Opts, TreeDesc
+from .tree import Tree
+from .workloads import (AF_BC_DIRICHLET, AF_BC_NEUMANN, BCTable, bc_table)
+
+I_PHI, I_RHS, I_TMP, I_EPS = 0, 1, 2, 3
+MG_CYCLE_DOWN, MG_CYCLE_UP = 1, 3
+MG_PROLONG_LINEAR, MG_PROLONG_SPARSE, MG_PROLONG_AUTO = 17, 18, 19
+
+
+# built-in boundary conditions (afivo/src/m_af_ghostcell.f90:615-652), as callbacks (nb, coords)
+def af_bc_dirichlet_zero(nb, coords):
+    return AF_BC_DIRICHLET, 0.0
+
+
+def af_bc_neumann_zero(nb, coords):
+    return AF_BC_NEUMANN, 0.0
+
+
+@dataclasses.dataclass
+class mg_t:
+    """mg_t (afivo/src/m_af_types.f90:572-665): the options a caller may set before mg_init."""
+    n_cycle_down: int = 2
+    n_cycle_up: int = 2
+    use_corners: bool = False
+    subtract_mean: bool = False
+    helmholtz_lambda: float = 0.0
+    lsf_boundary_value: float = 0.0
+    operator_mask: int = -1
+    prolongation_type: int = MG_PROLONG_AUTO
+    sides_bc: Optional[Callable] = None  # (nb, coords[n, nface, D]) -> (bc_type, values)
+    device: int = -1
+    initialized: bool = False
+    _h: Optional[C.c_void_p] = None
+    _tree: Optional[Tree] = None
+
+    # ---- helpers -------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            msg = _lib.lib().afmg_last_error(self._h)
+            raise AfmgError(rc, msg.decode() if msg else "")
+
+    def _need_init(self):
+        if not self.initialized:
+            raise AfmgError(-4, "mg_t not initialized (reference: error stop in mg_use)")
+
+    def set_bc(self, bc: BCTable):
+        """Ship the evaluated mg%sides_bc callback (one row per physical face)."""
+        self._need_init()
+        ids = np.ascontiguousarray(bc.ids, np.int32)
+        nbs = np.ascontiguousarray(bc.nbs, np.int32)
+        ty = np.ascontiguousarray(bc.types, np.int32)
+        vals = np.ascontiguousarray(bc.vals, np.float64)
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        self._check(_lib.lib().afmg_set_bc(self._h, len(ids), ip(ids), ip(nbs), ip(ty),
+                                           vals.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def set_cc(self, var, ids, data):
+        self._need_init()
+        ids = np.ascontiguousarray(ids, np.int32)
+        data = np.ascontiguousarray(data, np.float64)
+        assert data.size == len(ids) * self._tree.box_len
+        self._check(_lib.lib().afmg_upload(self._h, var, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                           data.ctypes.data))
+
+    def get_cc(self, var, ids):
+        self._need_init()
+        ids = np.ascontiguousarray(ids, np.int32)
+        out = np.empty((len(ids),) + (self._tree.nc + 2,) * self._tree.ndim)
+        self._check(_lib.lib().afmg_download(self._h, var, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                             out.ctypes.data))
+        return out
+
+    def upload_ptr(self, var, ids, host_ptr):
+        """Upload from a raw host pointer (e.g. a pinned torch tensor's data_ptr())."""
+        ids = np.ascontiguousarray(ids, np.int32)
+        self._check(_lib.lib().afmg_upload(self._h, var, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)), host_ptr))
+
+    def download_ptr(self, var, ids, host_ptr):
+        ids = np.ascontiguousarray(ids, np.int32)
+        self._check(_lib.lib().afmg_download(self._h, var, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)), host_ptr))
+
+    def clear(self, var):
+        self._need_init()
+        self._check(_lib.lib().afmg_clear(self._h, var))
+
+    # ---- per-level building blocks (exported for parity tests) -----------------------
+    def gsrb_boxes(self, lvl, type_cycle):
+        self._check(_lib.lib().afmg_gsrb_boxes(self._h, lvl, type_cycle))
+
+    def gsrb_halfsweep(self, lvl, redblack):
+        self._check(_lib.lib().afmg_gsrb_halfsweep(self._h, lvl, redblack))
+
+    def gc_lvl(self, lvl, var=I_PHI, corners=True):
+        self._check(_lib.lib().afmg_gc_lvl(self._h, lvl, var, int(corners)))
+
+    def update_coarse(self, lvl, with_tmp=True):
+        self._check(_lib.lib().afmg_update_coarse(self._h, lvl, int(with_tmp)))
+
+    def correct_children(self, lvl_parents):
+        self._check(_lib.lib().afmg_correct_children(self._h, lvl_parents))
+
+    def residual_lvl(self, lvl):
+        self._check(_lib.lib().afmg_residual_lvl(self._h, lvl))
+
+    def solve_coarse_grid(self):
+        self._check(_lib.lib().afmg_solve_coarse_grid(self._h))
+
+    def init_phi_rhs(self):
+        self._check(_lib.lib().afmg_init_phi_rhs(self._h))
+
+    # ---- asynchronous cycles + instrumentation (bench) ------------------------------
+    def fas_vcycle_async(self, set_residual=True, highest_lvl=0, n_cycles=1):
+        self._check(_lib.lib().afmg_fas_vcycle_async(self._h, int(set_residual), int(highest_lvl), n_cycles))
+
+    def fas_fmg_async(self, set_residual=True, have_guess=True, n_cycles=1):
+        self._check(_lib.lib().afmg_fas_fmg_async(self._h, int(set_residual), int(have_guess), n_cycles))
+
+    def sync(self):
+        self._check(_lib.lib().afmg_sync(self._h))
+
+    def last_cycle_ms(self):
+        v = C.c_double()
+        self._check(_lib.lib().afmg_last_cycle_ms(self._h, C.byref(v)))
+        return v.value
+
+    def kernel_launches(self):
+        return int(_lib.lib().afmg_kernel_launches(self._h))
+
+    def cell_updates(self, highest_lvl=0, fmg=False):
+        v = C.c_double()
+        self._check(_lib.lib().afmg_cell_updates(self._h, highest_lvl, int(fmg), C.byref(v)))
+        return v.value
+
+    def set_profiling(self, on):
+        self._check(_lib.lib().afmg_set_profiling(self._h, int(on)))
+
+    def profile(self):
+        cap = 64
+        names = ((C.c_char * 32) * cap)()
+        ms = (C.c_double * cap)()
+        calls = (C.c_int64 * cap)()
+        n = C.c_int32()
+        self._check(_lib.lib().afmg_profile(self._h, cap, names, ms, calls, C.byref(n)))
+        return {names[i].value.decode(): (ms[i], calls[i]) for i in range(n.value)}
+
+    def slot_of_box(self, box_id):
+        return int(_lib.lib().afmg_slot_of_box(self._h, int(box_id)))
+
+
+def _opts_from(tree: Tree, mg: mg_t) -> Opts:
+    o = Opts()
+    o.ndim, o.n_cell, o.coord_t = tree.ndim, tree.nc, tree.coord_t
+    o.n_cycle_down, o.n_cycle_up = mg.n_cycle_down, mg.n_cycle_up
+    o.use_corners, o.subtract_mean = int(mg.use_corners), int(mg.subtract_mean)
+    o.prolongation_type, o.operator_mask = mg.prolongation_type, mg.operator_mask
+    o.has_eps, o.device = 0, mg.device
+    o.helmholtz_lambda, o.lsf_boundary_value = mg.helmholtz_lambda, mg.lsf_boundary_value
+    for d in range(3):
+        o.coarse_grid_size[d] = int(tree.coarse_grid_size[d]) if d < tree.ndim else 1
+        o.periodic[d] = int(tree.periodic[d]) if d < tree.ndim else 0
+        o.dr_base[d] = float(tree.dr_base[d]) if d < tree.ndim else 0.0
+        o.r_base[d] = float(tree.r_base[d]) if d < tree.ndim else 0.0
+    return o
+
+
+def _tree_desc(tree: Tree):
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    keep = dict(
+        counts=i32([len(a) for a in tree.lvl_ids]), ids=i32(np.concatenate(tree.lvl_ids)), lvl=i32(tree.lvl),
+        ix=i32(tree.ix), parent=i32(tree.parent), children=i32(tree.children), neighbors=i32(tree.neighbors),
+        nmat=i32(tree.neighbor_mat), r_min=np.ascontiguousarray(tree.r_min, np.float64))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    td = TreeDesc(tree.highest_lvl, tree.highest_id, ip(keep["counts"]), ip(keep["ids"]), ip(keep["lvl"]),
+                  ip(keep["ix"]), ip(keep["parent"]), ip(keep["children"]), ip(keep["neighbors"]), ip(keep["nmat"]),
+                  keep["r_min"].ctypes.data_as(C.POINTER(C.c_double)))
+    return td, keep
+
+
+def mg_init(tree: Tree, mg: mg_t):
+    """mg_init (afivo/src/m_af_multigrid.f90:43-109)."""
+    if mg.sides_bc is None:
+        raise AfmgError(-1, "mg_init: sides_bc not set")  # :50-51 error stop
+    L = _lib.lib()
+    h = C.c_void_p()
+    o = _opts_from(tree, mg)
+    rc = L.afmg_create(C.byref(h), C.byref(o))
+    if rc != 0:
+        raise AfmgError(rc, (L.afmg_last_error(None) or b"").decode())
+    mg._h, mg._tree = h, tree
+    mg.initialized = True
+    mg_set_tree(tree, mg)
+
+
+def mg_set_tree(tree: Tree, mg: mg_t):
+    """Forward a (new) topology, e.g. after af_adjust_refinement, and re-evaluate sides_bc."""
+    mg._need_init()
+    td, keep = _tree_desc(tree)
+    mg._check(_lib.lib().afmg_set_tree(mg._h, C.byref(td)))
+    mg._tree = tree
+    bc = mg.sides_bc if isinstance(mg.sides_bc, BCTable) else bc_table(tree, mg.sides_bc)
+    mg.set_bc(bc)
+
+
+def mg_destroy(mg: mg_t):
+    """mg_destroy (afivo/src/m_af_multigrid.f90:111-115)."""
+    if mg._h is not None:
+        _lib.lib().afmg_destroy(mg._h)
+    mg._h, mg.initialized = None, False
+
+
+def mg_fas_fmg(tree: Tree, mg: mg_t, set_residual: bool, have_guess: bool):
+    """mg_fas_fmg (afivo/src/m_af_multigrid.f90:137-180)."""
+    mg._need_init()
+    mg._check(_lib.lib().afmg_fas_fmg(mg._h, int(set_residual), int(have_guess)))
+
+
+def mg_fas_vcycle(tree: Tree, mg: mg_t, set_residual: bool, highest_lvl: Optional[int] = None,
+                  standalone: bool = True):
+    """mg_fas_vcycle (afivo/src/m_af_multigrid.f90:185-264)."""
+    mg._need_init()
+    mg._check(_lib.lib().afmg_fas_vcycle(mg._h, int(set_residual), int(highest_lvl or 0), int(standalone)))
+
+
+def mg_update_operator_stencil(tree: Tree, mg: mg_t):
+    """mg_update_operator_stencil (afivo/src/m_af_multigrid.f90:1188-1214)."""
+    mg._need_init()
+    mg._check(_lib.lib().afmg_set_helmholtz_lambda(mg._h, float(mg.helmholtz_lambda)))
+    mg._check(_lib.lib().afmg_update_operator_stencil(mg._h))
+
+
+def af_tree_maxabs_cc(tree: Tree, mg: mg_t, iv: int) -> float:
+    """af_tree_maxabs_cc (afivo/src/m_af_utils.f90:773-785): max |cc| over leaves, interior cells."""
+    v = C.c_double()
+    mg._check(_lib.lib().afmg_max_abs(mg._h, iv, C.byref(v)))
+    return v.value
+
+
+def af_tree_sum_cc(tree: Tree, mg: mg_t, iv: int) -> float:
+    """af_tree_sum_cc (afivo/src/m_af_utils.f90:966-1027)."""
+    v = C.c_double()
+    mg._check(_lib.lib().afmg_tree_sum(mg._h, iv, C.byref(v)))
+    return v.value

@@ -1,0 +1,207 @@
+/* afmg.h -- C ABI of the B200-native FAS multigrid solver that replaces afivo's m_af_multigrid.
+ *
+ * The reference exposes no C ABI on this path; its replaceable unit is the set of module-level
+ * Fortran entry points of afivo/src/m_af_multigrid.f90 (mg_init :43, mg_destroy :111, mg_use :118,
+ * mg_fas_fmg :137, mg_fas_vcycle :185, mg_update_operator_stencil :1188) acting on af_t / box_t
+ * (afivo/src/m_af_types.f90:286-393) and mg_t (:572-665).  A Fortran shim module with those same
+ * signatures (fortran/m_af_multigrid_gpu.f90) binds the functions below through
+ * ISO_C_BINDING.  Every entry point says which reference interface it stands in for.
+ *
+ * Conventions: all integers are int32, reals are fp64, logicals are int (0/1).  Box ids, level
+ * numbers and neighbour directions are the reference's (1-based ids, af_no_box = 0,
+ * af_phys_boundary = -1; nb = 1..2*ndim = lowx, highx, lowy, highy, lowz, highz;
+ * m_af_types.f90:38-41, 186-214).  Cell data crosses the boundary in the reference's own box layout:
+ * cc(0:nc+1, 0:nc+1 [, 0:nc+1]) per box, first index fastest (m_af_core.f90:551).
+ * All pointers are HOST pointers unless the function name ends in _device.
+ * Every function returns AFMG_OK (0) or a negative error code; nothing aborts the process
+ * (the reference uses `error stop`; the shim turns non-zero codes into that).
+ * A handle is not re-entrant; use one handle per mg_t.  There is no CPU fallback: without a CUDA
+ * device afmg_create fails with AFMG_ERR_CUDA.
+ */
+#ifndef AFMG_H
+#define AFMG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct afmg_handle afmg_handle;
+
+enum {
+  AFMG_OK = 0,
+  AFMG_ERR_ARG = -1,          /* invalid argument / inconsistent tree                      */
+  AFMG_ERR_CUDA = -2,         /* CUDA runtime error or no device (see afmg_last_error)     */
+  AFMG_ERR_UNSUPPORTED = -3,  /* valid in the reference, not (yet) supported here          */
+  AFMG_ERR_STATE = -4,        /* call order violated (e.g. solve before afmg_set_tree)     */
+  AFMG_ERR_SINGULAR = -5,     /* coarse-grid operator is singular (all-Neumann, lambda=0)   */
+  AFMG_ERR_NCCL = -6
+};
+
+/* cell-centred variables of the solver: mg%i_phi, mg%i_rhs, mg%i_tmp, tree%mg_i_eps
+ * (m_af_types.f90:574-584) */
+enum { AFMG_PHI = 0, AFMG_RHS = 1, AFMG_TMP = 2, AFMG_EPS = 3 };
+
+/* boundary condition types (m_af_types.f90:58-69) */
+enum {
+  AFMG_BC_DIRICHLET = -10,
+  AFMG_BC_NEUMANN = -11,
+  AFMG_BC_CONTINUOUS = -12,
+  AFMG_BC_DIRICHLET_COPY = -13
+};
+
+/* mg%prolongation_type (m_af_types.f90:523-544) */
+enum { AFMG_PROLONG_LINEAR = 17, AFMG_PROLONG_SPARSE = 18, AFMG_PROLONG_AUTO = 19 };
+
+/* coordinate systems (m_af_types.f90:45-48) */
+enum { AFMG_XYZ = 1, AFMG_CYL = 2 };
+
+/* POD copy of the scalar members of mg_t (m_af_types.f90:572-665) and of the af_t members the
+ * solver needs (m_af_types.f90:326-393).  Filled by mg_init in the shim. */
+typedef struct afmg_opts {
+  int32_t ndim;                 /* NDIM (2 or 3)                                              */
+  int32_t n_cell;               /* tree%n_cell: cells per box side (even)                     */
+  int32_t coord_t;              /* tree%coord_t: AFMG_XYZ / AFMG_CYL                          */
+  int32_t n_cycle_down;         /* mg%n_cycle_down (default 2)                                */
+  int32_t n_cycle_up;           /* mg%n_cycle_up (default 2)                                  */
+  int32_t use_corners;          /* mg%use_corners                                             */
+  int32_t subtract_mean;        /* mg%subtract_mean                                           */
+  int32_t prolongation_type;    /* mg%prolongation_type                                       */
+  int32_t operator_mask;        /* mg%operator_mask (-1 = all bits)                           */
+  int32_t has_eps;              /* tree%mg_i_eps > 0                                          */
+  int32_t device;               /* CUDA device ordinal, -1 = current device                   */
+  int32_t reserved;
+  double helmholtz_lambda;      /* mg%helmholtz_lambda (lambda^2 of L phi - lambda phi = f)   */
+  double lsf_boundary_value;    /* mg%lsf_boundary_value                                      */
+  int32_t coarse_grid_size[3];  /* tree%coarse_grid_size (cells)                              */
+  int32_t periodic[3];          /* tree%periodic                                              */
+  double dr_base[3];            /* tree%dr_base                                               */
+  double r_base[3];             /* tree%r_base                                                */
+} afmg_opts;
+
+/* Borrowed, read-only flat copy of the tree topology (box_t members lvl, ix, parent, children,
+ * neighbors, neighbor_mat, m_af_types.f90:286-300; level lists lvls(l)%ids, :76-80).
+ * Per-box arrays have (highest_id + 1) rows; row 0 is unused, so reference ids index directly.
+ * lvl_ids concatenates lvls(1)%ids ... lvls(highest_lvl)%ids, lvl_counts gives their sizes. */
+typedef struct afmg_tree {
+  int32_t highest_lvl;
+  int32_t highest_id;
+  const int32_t* lvl_counts;   /* (highest_lvl)                                               */
+  const int32_t* lvl_ids;      /* (sum lvl_counts)                                            */
+  const int32_t* lvl;          /* (n+1)                                                       */
+  const int32_t* ix;           /* (n+1, ndim)  1-based spatial index on the level grid        */
+  const int32_t* parent;       /* (n+1)                                                       */
+  const int32_t* children;     /* (n+1, 2^ndim)                                               */
+  const int32_t* neighbors;    /* (n+1, 2*ndim)                                               */
+  const int32_t* neighbor_mat; /* (n+1, 3^ndim), first offset fastest                         */
+  const double* r_min;         /* (n+1, ndim)  box%r_min (used by cylindrical stencils)       */
+} afmg_tree;
+
+/* ---- lifecycle: mg_init (m_af_multigrid.f90:43-109), mg_destroy (:111-115) -------------------- */
+int afmg_create(afmg_handle** out, const afmg_opts* opts);
+int afmg_destroy(afmg_handle* h);
+/* text of the last error raised on this handle (or by afmg_create when h == NULL) */
+const char* afmg_last_error(const afmg_handle* h);
+
+/* ---- topology: called after mg_init and whenever af_adjust_refinement (m_af_core.f90:697) changed
+ * the tree.  Copies the arrays; rebuilds slot maps, ghost-cell plans, constant stencils
+ * (mg_set_operators_tree, m_af_multigrid.f90:1216-1224) and the coarse-grid factorisation
+ * (coarse_solver_initialize, m_coarse_solver.f90:71-194).  Cell data of boxes that exist in both the
+ * old and the new tree (same id, lvl and ix) is kept on the device. */
+int afmg_set_tree(afmg_handle* h, const afmg_tree* tree);
+
+/* ---- boundary conditions as data: one row per physical face.  Replaces the mg%sides_bc callback
+ * (m_af_types.f90:401-420; af_bc_dirichlet_zero etc. m_af_ghostcell.f90:615-652;
+ * field_bc_homogeneous src/m_field.f90:590-610): the shim evaluates the callback on the host for
+ * every face with neighbors(nb) == af_phys_boundary.  bc_val has n_faces rows of nc^(ndim-1) values,
+ * indexed like bc_val in bc_to_gc (m_af_ghostcell.f90:173-279).  May be called before every solve
+ * (e.g. when the applied voltage changed). */
+int afmg_set_bc(afmg_handle* h, int32_t n_faces, const int32_t* box_id, const int32_t* nb,
+                const int32_t* bc_type, const double* bc_val);
+
+/* ---- operator updates: mg_update_operator_stencil (m_af_multigrid.f90:1188-1214) and the scalar
+ * members that enter the stencils */
+int afmg_set_helmholtz_lambda(afmg_handle* h, double lambda);
+int afmg_set_lsf_boundary_value(afmg_handle* h, double value);
+/* Level-set distances all_distances(2*ndim, nc^ndim) (store_lsf_distance_matrix,
+ * m_af_multigrid.f90:977-1097) for the n boxes that contain an electrode boundary; the host
+ * evaluates mg%lsf.  Boxes not listed have no boundary.  n = 0 clears. */
+int afmg_set_lsf_distances(afmg_handle* h, int32_t n, const int32_t* box_id, const double* dd);
+/* (Re)build the operator and prolongation stencils after eps (AFMG_EPS data), lsf distances or
+ * lambda changed: mg_update_operator_stencil(tree, mg, new_lsf, new_eps). */
+int afmg_update_operator_stencil(afmg_handle* h);
+
+/* ---- cell data: box%cc(:, :, :, iv) of n boxes, (nc+2)^ndim doubles each, packed in the order of
+ * `box_id` (m_af_types.f90:302).  upload/download take host memory; the _device variants take
+ * device memory (for callers that keep rhs / phi resident). */
+int afmg_upload(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, const double* packed);
+int afmg_download(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, double* packed);
+int afmg_upload_device(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id_host,
+                       const double* packed_device);
+int afmg_download_device(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id_host,
+                         double* packed_device);
+/* af_tree_clear_cc / af_box_clear_cc (m_af_utils.f90:385): set a variable to zero on all boxes */
+int afmg_clear(afmg_handle* h, int32_t var);
+
+/* ---- the two solver entry points -------------------------------------------------------------
+ * mg_fas_fmg(tree, mg, set_residual, have_guess)               m_af_multigrid.f90:137-180
+ * mg_fas_vcycle(tree, mg, set_residual, highest_lvl, standalone) m_af_multigrid.f90:185-264
+ * highest_lvl <= 0 means tree%highest_lvl.  Blocking: return after the device finished. */
+int afmg_fas_fmg(afmg_handle* h, int32_t set_residual, int32_t have_guess);
+int afmg_fas_vcycle(afmg_handle* h, int32_t set_residual, int32_t highest_lvl, int32_t standalone);
+/* Asynchronous variants: enqueue n_cycles back-to-back cycles on the handle's stream and return;
+ * afmg_sync waits.  Used by callers that keep data resident and test convergence every few cycles
+ * (field_compute, src/m_field.f90:491-524). */
+int afmg_fas_fmg_async(afmg_handle* h, int32_t set_residual, int32_t have_guess, int32_t n_cycles);
+int afmg_fas_vcycle_async(afmg_handle* h, int32_t set_residual, int32_t highest_lvl, int32_t n_cycles);
+int afmg_sync(afmg_handle* h);
+
+/* ---- single operations (the mg_t per-level building blocks; exported for parity tests) -------- */
+int afmg_gsrb_boxes(afmg_handle* h, int32_t lvl, int32_t type_cycle /*1 = down, 3 = up*/); /* :648-687 */
+int afmg_gsrb_halfsweep(afmg_handle* h, int32_t lvl, int32_t redblack);   /* mg%box_gsrb on a level + side ghost fill */
+int afmg_gc_lvl(afmg_handle* h, int32_t lvl, int32_t var, int32_t corners); /* af_gc_lvl, m_af_ghostcell.f90:49-61 */
+int afmg_update_coarse(afmg_handle* h, int32_t lvl, int32_t with_tmp);    /* :691-738 / :742-776 */
+int afmg_correct_children(afmg_handle* h, int32_t lvl_parents);           /* :624-646 */
+int afmg_residual_lvl(afmg_handle* h, int32_t lvl);                       /* residual_box :801-810 */
+int afmg_solve_coarse_grid(afmg_handle* h);                               /* :266-291 */
+int afmg_init_phi_rhs(afmg_handle* h);                                    /* :779-799 */
+
+/* ---- reductions: af_tree_maxabs_cc (m_af_utils.f90:773-785, leaves, interior cells) and
+ * af_tree_sum_cc (m_af_utils.f90:966-1027, volume-weighted leaf sum) */
+int afmg_max_abs(afmg_handle* h, int32_t var, double* out);
+int afmg_tree_sum(afmg_handle* h, int32_t var, double* out);
+
+/* ---- instrumentation ------------------------------------------------------------------------- */
+/* number of kernel launches the handle issued since creation (graph nodes counted per replay) */
+int64_t afmg_kernel_launches(const afmg_handle* h);
+/* device time in ms of the most recent (group of) cycle(s), measured with CUDA events on the
+ * handle's stream */
+int afmg_last_cycle_ms(afmg_handle* h, double* ms);
+/* per-kernel-family accumulated device time; fills up to cap entries, returns count via *n.
+ * Only collected while profiling is enabled (it serialises launches). */
+int afmg_set_profiling(afmg_handle* h, int32_t on);
+int afmg_profile(afmg_handle* h, int32_t cap, char (*names)[32], double* ms, int64_t* calls, int32_t* n);
+/* cell-updates performed by one V-cycle to highest_lvl (<=0: all) and by one FMG */
+int afmg_cell_updates(afmg_handle* h, int32_t highest_lvl, int32_t fmg, double* out);
+
+/* ---- device layout (exported so host-side tests can check the index maps without a GPU) -------
+ * Offset (in doubles) of cell (i, j, k), 0 <= i,j,k <= nc+1 (k ignored in 2D), inside the device
+ * box record; a bijection onto 0 .. (nc+2)^ndim - 1.  See DESIGN.md "data layout". */
+int32_t afmg_layout_offset(int32_t ndim, int32_t nc, int32_t i, int32_t j, int32_t k);
+int32_t afmg_layout_box_len(int32_t ndim, int32_t nc);
+/* slot (position in the device arrays) of a box id, -1 if unknown */
+int32_t afmg_slot_of_box(const afmg_handle* h, int32_t box_id);
+
+/* ---- multi-GPU: one process per GPU.  The caller distributes a 128-byte NCCL unique id (e.g. with
+ * MPI or torch.distributed) and every rank calls afmg_comm_init before afmg_set_tree.  Boxes are
+ * partitioned by contiguous Morton ranges per level; every rank passes the same full tree. */
+int afmg_comm_unique_id(char id[128]);
+int afmg_comm_init(afmg_handle* h, int32_t n_ranks, int32_t rank, const char id[128]);
+/* which rank owns a box (-1 if unknown); upload/download only touch boxes owned by this rank */
+int32_t afmg_owner_of_box(const afmg_handle* h, int32_t box_id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFMG_H */

@@ -1,0 +1,103 @@
+"""-m gpu: whole FMG / V-cycles against the oracle.  Tolerance from BASELINE.json north_star: fp64
+potential <= 1e-10 relative max-norm after the same number of cycles, same per-cycle residual
+history."""
+import numpy as np
+import pytest
+
+from afivo_streamer_b200 import mg as M
+from afivo_streamer_b200 import tree as T
+from afivo_streamer_b200 import workloads as W
+from oracle.oracle import Oracle
+
+from util import TREES, all_ids, bc_mixed
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def run_both(tree, bc_fn, n_v=4, have_guess=False, **opts):
+    bc = W.bc_table(tree, bc_fn)
+    orc = Oracle(tree, **opts)
+    orc.set_bc(bc)
+    orc.mg_init()
+    mg = M.mg_t(sides_bc=bc, **opts)
+    M.mg_init(tree, mg)
+    ids, rhs = W.random_rhs_on_leaves(tree)
+    orc.set_cc(M.I_RHS, ids, rhs)
+    mg.set_cc(M.I_RHS, ids, rhs)
+    hist_o, hist_g = [], []
+    orc.fas_fmg(True, have_guess)
+    M.mg_fas_fmg(tree, mg, True, have_guess)
+    hist_o.append(orc.maxabs(M.I_TMP))
+    hist_g.append(M.af_tree_maxabs_cc(tree, mg, M.I_TMP))
+    for _ in range(n_v):
+        orc.fas_vcycle(True)
+        M.mg_fas_vcycle(tree, mg, True)
+        hist_o.append(orc.maxabs(M.I_TMP))
+        hist_g.append(M.af_tree_maxabs_cc(tree, mg, M.I_TMP))
+    a = orc.get_cc(M.I_PHI, all_ids(tree)).reshape(-1)
+    b = mg.get_cc(M.I_PHI, all_ids(tree)).reshape(-1)
+    M.mg_destroy(mg)
+    return np.array(hist_o), np.array(hist_g), a, b
+
+
+@pytest.mark.parametrize("name", sorted(TREES))
+def test_fmg_then_vcycles(name):
+    tree = TREES[name]()
+    ho, hg, a, b = run_both(tree, bc_mixed)
+    assert ho[-1] < 0.1 * ho[0]  # it converges
+    # per-cycle residual history: the residual is rhs - L(phi) with |L| ~ 1/dr^2, so compare with
+    # the rounding level of that expression
+    assert np.all(np.abs(ho - hg) <= 1e-9 * ho[0] + 1e-6 * ho), (ho, hg)
+    assert np.max(np.abs(a - b)) <= RTOL * np.max(np.abs(a))
+
+
+def test_fmg_with_guess_and_helmholtz():
+    tree = T.corner_refined_tree(3, 8, 8, 4)
+    ho, hg, a, b = run_both(tree, lambda nb, c: W.bc_table.__defaults__ and (W.AF_BC_DIRICHLET, 0.0) if False else
+                            ((W.AF_BC_DIRICHLET, 0.0) if (nb - 1) // 2 == 2 else (W.AF_BC_NEUMANN, 0.0)),
+                            have_guess=True, helmholtz_lambda=1.0e3)
+    assert np.max(np.abs(a - b)) <= RTOL * np.max(np.abs(a))
+    assert np.all(np.abs(ho - hg) <= 1e-9 * ho[0] + 1e-6 * ho)
+
+
+def test_sparse_prolongation_and_cycles():
+    tree = T.corner_refined_tree(3, 8, 8, 3)
+    ho, hg, a, b = run_both(tree, bc_mixed, prolongation_type=M.MG_PROLONG_SPARSE, n_cycle_down=1, n_cycle_up=3)
+    assert np.max(np.abs(a - b)) <= RTOL * np.max(np.abs(a))
+
+
+def test_highest_lvl_argument():
+    tree = T.uniform_tree(3, 8, 8, 3)
+    bc = W.bc_table(tree, bc_mixed)
+    orc = Oracle(tree)
+    orc.set_bc(bc)
+    orc.mg_init()
+    mg = M.mg_t(sides_bc=bc)
+    M.mg_init(tree, mg)
+    ids, rhs = W.random_rhs_on_leaves(tree)
+    orc.set_cc(M.I_RHS, ids, rhs)
+    mg.set_cc(M.I_RHS, ids, rhs)
+    orc.init_phi_rhs()
+    mg.init_phi_rhs()
+    orc.fas_vcycle(True, 2, False)
+    M.mg_fas_vcycle(tree, mg, True, 2, False)
+    a = orc.get_cc(M.I_PHI, all_ids(tree))
+    b = mg.get_cc(M.I_PHI, all_ids(tree)).reshape(a.shape)
+    assert np.max(np.abs(a - b)) <= RTOL * np.max(np.abs(a))
+    M.mg_destroy(mg)
+
+
+def test_errors_are_codes_not_aborts():
+    tree = T.uniform_tree(3, 8, 8, 2)
+    mg = M.mg_t(sides_bc=M.af_bc_neumann_zero)  # all-Neumann Poisson: singular coarse operator
+    M.mg_init(tree, mg)
+    with pytest.raises(M.AfmgError) as e:
+        M.mg_fas_fmg(tree, mg, True, False)
+    assert e.value.code == -5
+    with pytest.raises(M.AfmgError):
+        mg.gc_lvl(7)
+    M.mg_destroy(mg)
+    with pytest.raises(M.AfmgError):
+        M.mg_fas_vcycle(tree, mg, True)
