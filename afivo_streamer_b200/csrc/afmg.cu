@@ -173,9 +173,10 @@ void jacobi_eig(int n, std::vector<long double>& A, std::vector<long double>& V)
 // ---- kernel launch plumbing -------------------------------------------------------------------
 struct Launch {
   afmg_handle* h;
-  const char* name;
+  std::string name;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  Launch(afmg_handle* h_, const char* name_) : h(h_), name(name_) {
+  Launch(afmg_handle* h_, const char* name_, int lvl = 0) : h(h_) {
+    if (h->profiling && !h->capturing) name = lvl > 0 ? std::string(name_) + "_L" + std::to_string(lvl) : std::string(name_);
     h->launches++;
     if (h->profiling && !h->capturing) {
       cudaEventCreate(&e0);
@@ -221,22 +222,54 @@ struct GsrbCfg {
 inline int nlev(const afmg_handle* h, int l) { return h->lvl_off[l + 1] - h->lvl_off[l]; }
 
 // one half-sweep + side ghost fill on level l
+template <int NC>
+struct Gsrb2Cfg {  // boxes per CTA, k-splits, min CTAs per SM
+  static constexpr int BPC = (NC == 16) ? 1 : (NC == 8 ? 4 : 16);
+  static constexpr int KS = (NC == 16) ? 2 : (NC == 8 ? 2 : 1);
+  static constexpr int MINB = (NC == 16) ? 5 : 6;
+};
+
+template <class K>
+void set_max_smem(K kernel, size_t smem) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 void enq_gsrb(afmg_handle* h, int l, int redblack) {
   const int n = nlev(h, l);
   if (n == 0) return;
-  Launch L_(h, "gsrb");
+  Launch L_(h, "gsrb", l);
+  static const int variant = getenv("AFMG_GSRB_V1") ? 1 : 2;
   DISPATCH_NC(h, NC, {
-    constexpr int BPC = GsrbCfg<NC>::BPC;
-    const int threads = BPC * NC * NC / 2;
-    const size_t smem = (size_t)BPC * Lay3<NC>::COL * sizeof(double);
-    k_gsrb<NC, BPC><<<(n + BPC - 1) / BPC, threads, smem, h->stream>>>(h->cx, h->lvl_off[l], n, redblack & 1, l);
+    if (variant == 1) {
+      constexpr int BPC = GsrbCfg<NC>::BPC;
+      const int threads = BPC * NC * NC / 2;
+      const size_t smem = (size_t)BPC * Lay3<NC>::COL * sizeof(double);
+      k_gsrb<NC, BPC><<<(n + BPC - 1) / BPC, threads, smem, h->stream>>>(h->cx, h->lvl_off[l], n, redblack & 1, l);
+    } else {
+      using G = Gsrb2Cfg<NC>;
+      constexpr int threads = G::BPC * G::KS * NC * NC / 2;
+      const size_t smem = (size_t)G::BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double);
+      auto kern = k_gsrb2<NC, G::BPC, G::KS, G::MINB>;
+      kern<<<(n + G::BPC - 1) / G::BPC, threads, smem, h->stream>>>(h->cx, h->lvl_off[l], n, redblack & 1, l);
+    }
+  });
+}
+
+// opt in to large dynamic shared memory / max carveout once per process (not a stream operation, but
+// kept out of graph capture)
+void configure_kernels(afmg_handle* h) {
+  DISPATCH_NC(h, NC, {
+    using G = Gsrb2Cfg<NC>;
+    set_max_smem(k_gsrb2<NC, G::BPC, G::KS, G::MINB>, (size_t)G::BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double));
+    set_max_smem(k_gsrb<NC, GsrbCfg<NC>::BPC>, (size_t)GsrbCfg<NC>::BPC * Lay3<NC>::COL * sizeof(double));
   });
 }
 
 void enq_rb_prepare(afmg_handle* h, int l) {
   const int n = h->rb_lvl_off[l + 1] - h->rb_lvl_off[l];
   if (n == 0) return;
-  Launch L_(h, "rb_prepare");
+  Launch L_(h, "rb_prepare", l);
   DISPATCH_NC(h, NC, { k_rb_prepare<NC><<<n, 128, 0, h->stream>>>(h->cx, h->rb_lvl_off[l], n, V_PHI); });
 }
 
@@ -244,21 +277,21 @@ void enq_rb_prepare(afmg_handle* h, int l) {
 void enq_gc(afmg_handle* h, int l, int var, int corners, int mode) {
   const int n = nlev(h, l);
   if (n == 0) return;
-  Launch L_(h, mode ? "gc_parent" : "gc");
+  Launch L_(h, mode ? "gc_parent" : "gc", l);
   DISPATCH_NC(h, NC, { k_gc<NC><<<n, 256, 0, h->stream>>>(h->cx, h->lvl_off[l], n, var, corners, mode); });
 }
 
 void enq_edges_corners(afmg_handle* h, int l) {
   const int n = nlev(h, l);
   if (n == 0) return;
-  Launch L_(h, "edges_corners");
+  Launch L_(h, "edges_corners", l);
   DISPATCH_NC(h, NC, { k_edges_corners<NC><<<n, 64, 0, h->stream>>>(h->cx, h->lvl_off[l], n, V_PHI); });
 }
 
 void enq_restrict(afmg_handle* h, int l, int keep_res) {
   const int n = nlev(h, l);
   if (n == 0) return;
-  Launch L_(h, "restrict");
+  Launch L_(h, "restrict", l);
   DISPATCH_NC(h, NC, {
     constexpr int T = (NC == 16) ? 256 : (NC == 8 ? 64 : 32);
     k_restrict<NC><<<n, T, 0, h->stream>>>(h->cx, h->lvl_off[l], n, keep_res);
@@ -268,7 +301,7 @@ void enq_restrict(afmg_handle* h, int l, int keep_res) {
 void enq_correct(afmg_handle* h, int lp) {
   const int n = nlev(h, lp);
   if (n == 0 || h->npar[lp] == 0) return;
-  Launch L_(h, "correct");
+  Launch L_(h, "correct", lp);
   DISPATCH_NC(h, NC, {
     const size_t smem = (size_t)(NC + 2) * (NC + 2) * (NC + 2) * sizeof(double);
     k_correct<NC><<<n, 256, smem, h->stream>>>(h->cx, h->lvl_off[lp], n);
@@ -285,7 +318,7 @@ void enq_residual(afmg_handle* h, int l_lo, int l_hi, bool with_max) {
 void enq_copy_lvl(afmg_handle* h, int l, int dst, int src) {
   const size_t n = (size_t)nlev(h, l) * h->box_len;
   if (n == 0) return;
-  Launch L_(h, "copy");
+  Launch L_(h, "copy", l);
   const size_t off = (size_t)h->lvl_off[l] * h->box_len;
   const int blocks = (int)std::min<size_t>((n + 1023) / 1024, 148 * 8);
   k_copy<<<blocks, 256, 0, h->stream>>>(h->d_cc[dst] + off, h->d_cc[src] + off, n);
@@ -405,7 +438,7 @@ void enq_init_phi_rhs(afmg_handle* h) {
   for (int l = h->L; l >= 2; --l) {
     const int n = nlev(h, l);
     if (n == 0) continue;
-    Launch L_(h, "init_phi_rhs");
+    Launch L_(h, "init_phi_rhs", l);
     DISPATCH_NC(h, NC, {
       constexpr int T = (NC == 16) ? 256 : (NC == 8 ? 64 : 32);
       k_restrict_var<NC><<<n, T, 0, h->stream>>>(h->cx, h->lvl_off[l], n, V_RHS, 1);
@@ -719,6 +752,7 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
     delete h;
     return AFMG_ERR_CUDA;
   }
+  configure_kernels(h);
   h->nc2 = opts->n_cell * opts->n_cell;
   h->box_len = (opts->n_cell + 2) * (opts->n_cell + 2) * (opts->n_cell + 2);
   *out = h;

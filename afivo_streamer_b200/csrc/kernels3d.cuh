@@ -217,6 +217,151 @@ __global__ void __launch_bounds__(BPC* NC* NC / 2) k_gsrb(DevCtx cx, int slot0, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_gsrb2: same operation as k_gsrb, restructured for issue rate and bytes in flight:
+//   - TMA bulk copies bring in the opposite colour block of phi (interior + faces) AND the rhs of
+//     colour C; the rhs buffer is overwritten in place with the new phi values and leaves by one TMA
+//     bulk store (smem -> global), so the inner loop is LDS / DADD / DMUL / STS only
+//   - KS threads share one (m, j) column (k split in KS ranges) for more warps per box
+//   - ghost pushes / boundary rules run after the sweep as cooperative, coalesced copies out of smem;
+//     the two z faces are contiguous in smem and leave as bulk copies too
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int NC, int BPC, int KS, int MINB>
+__global__ void __launch_bounds__(BPC* KS* NC* NC / 2, MINB) k_gsrb2(DevCtx cx, int slot0, int nbox, int C, int lvl) {
+  using L = Lay3<NC>;
+  constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX;
+  constexpr int TPB = H * NC * KS;  // threads per box
+  constexpr int KL = NC / KS;       // k-steps per thread
+  constexpr int SBOX = COL + NI;    // smem doubles per box: phi block of the other colour, rhs/out
+  extern __shared__ __align__(128) double smem[];
+  __shared__ uint64_t bar;
+  const int tid = threadIdx.x;
+  const int box0 = blockIdx.x * BPC;
+  const int nhere = min(BPC, nbox - box0);
+  double* const phi = cx.cc[V_PHI];
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, (uint32_t)(nhere * SBOX * 8));
+    for (int b = 0; b < nhere; ++b) {
+      const size_t base = (size_t)(slot0 + box0 + b) * BOX;
+      bulk_g2s(smem + b * SBOX, phi + base + (1 - C) * COL, COL * 8, &bar);
+      bulk_g2s(smem + b * SBOX + COL, cx.cc[V_RHS] + base + C * COL, NI * 8, &bar);
+    }
+  }
+  const int b = tid / TPB, t = tid % TPB;
+  const bool active = b < nhere;
+  const int slot = slot0 + box0 + (active ? b : 0);
+  const double* const S = smem + b * SBOX;
+  double* const R = smem + b * SBOX + COL;
+  const double* cf = cx.coef + 8 * lvl;
+  const double c2 = cf[1], c3 = cf[2], c4 = cf[3], c5 = cf[4], c6 = cf[5], c7 = cf[6], inv = cf[7];
+  mbar_wait(&bar, 0);
+
+  if (active) {
+    const int m = t % H, j = (t / H) % NC + 1, ks = t / (H * NC);
+    const int k0 = ks * KL + 1;
+    double s_km1 = (k0 == 1) ? S[NI + 4 * NF + (j - 1) * H + m] : S[L::iidx(m, j, k0 - 1)];
+    double s_k = S[L::iidx(m, j, k0)];
+#pragma unroll
+    for (int kk = 0; kk < KL; ++kk) {
+      const int k = k0 + kk;
+      const int idx = L::iidx(m, j, k);
+      const int pi = (C + j + k) & 1;  // 1: i = 2m+1, 0: i = 2m+2
+      const double s_kp1 = (k < NC) ? S[idx + NC * H] : S[NI + 5 * NF + (j - 1) * H + m];
+      const double ym = (j > 1) ? S[idx - H] : S[NI + 2 * NF + (k - 1) * H + m];
+      const double yp = (j < NC) ? S[idx + H] : S[NI + 3 * NF + (k - 1) * H + m];
+      const int fx = (k - 1) * H + ((j - 1) >> 1);
+      double xm, xp;
+      if (pi) {
+        xm = (m > 0) ? S[idx - 1] : S[NI + 0 * NF + fx];
+        xp = s_k;
+      } else {
+        xm = s_k;
+        xp = (m < H - 1) ? S[idx + 1] : S[NI + 1 * NF + fx];
+      }
+      double acc = R[idx];
+      acc = acc - c2 * xm;
+      acc = acc - c3 * xp;
+      acc = acc - c4 * ym;
+      acc = acc - c5 * yp;
+      acc = acc - c6 * s_km1;
+      acc = acc - c7 * s_kp1;
+      R[idx] = acc * inv;
+      s_km1 = s_k;
+      s_k = s_kp1;
+    }
+  }
+  fence_async_smem();
+  __syncthreads();
+  if (!active) return;
+
+  // ---- epilogue: new colour-C values are in R (layout of an interior colour block)
+  double* const gbox = phi + (size_t)slot * BOX;
+  const int* nbp = cx.nbr + slot * 6;
+  if (t == 0) {
+    bulk_s2g(gbox + C * COL, R, NI * 8);
+    // z faces: layer k = 1 / k = NC of R is contiguous (NF doubles)
+    const int n4 = nbp[4], n5 = nbp[5];
+    if (n4 >= 0) bulk_s2g(phi + (size_t)n4 * BOX + C * COL + NI + 5 * NF, R, NF * 8);
+    if (n5 >= 0) bulk_s2g(phi + (size_t)n5 * BOX + C * COL + NI + 4 * NF, R + (NC - 1) * NC * H, NF * 8);
+    bulk_commit();
+  }
+  // y and x faces: push the colour-C boundary layer into the neighbour's opposite ghost face
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    const int nb = nbp[f];
+    if (nb < 0) continue;
+    double* dst = phi + (size_t)nb * BOX + C * COL + NI + (f ^ 1) * NF;
+    for (int fi = t; fi < NF; fi += TPB) {
+      const int k = fi / H + 1, ah = fi % H;
+      int src;
+      if (f >= 2) {
+        src = L::iidx(ah, (f & 1) ? NC : 1, k);
+      } else {
+        // cells i = 1 (f = 0) or i = NC (f = 1) of colour C: j has parity (C + i + k) & 1
+        const int i = (f & 1) ? NC : 1;
+        const int j = 2 * ah + 2 - ((C + i + k) & 1);
+        src = L::iidx((i - 1) >> 1, j, k);
+      }
+      dst[fi] = R[src];
+    }
+  }
+  // physical / refinement faces: recompute all nc^2 ghost cells of the face from the rule
+#pragma unroll
+  for (int f = 0; f < 6; ++f) {
+    if (nbp[f] >= 0) continue;
+    const int row = cx.aux[slot * 6 + f];
+    const double* rc = cx.rule_c + 3 * row;
+    const double r0 = rc[0], r1 = rc[1], r2 = rc[2];
+    const double* B = cx.rule_B + (size_t)row * L::NC2;
+    const int d = f >> 1, hi = f & 1;
+    const int ta = (d == 0) ? 1 : 0, tb = (d == 2) ? 1 : 2;
+    for (int n = t; n < L::NC2; n += TPB) {
+      const int a = n % NC + 1, bb = n / NC + 1;
+      int q1[3], q2[3];
+      q1[ta] = q2[ta] = a;
+      q1[tb] = q2[tb] = bb;
+      q1[d] = hi ? NC : 1;
+      q2[d] = hi ? NC - 1 : 2;
+      const int col1 = (q1[0] + q1[1] + q1[2]) & 1;  // colour of the layer-1 cell; ghost has colour 1 - col1
+      const int i1 = L::iidx((q1[0] - 1) >> 1, q1[1], q1[2]), i2 = L::iidx((q2[0] - 1) >> 1, q2[1], q2[2]);
+      const double x1 = (col1 == C) ? R[i1] : S[i1];
+      const double x2 = (col1 == C) ? S[i2] : R[i2];
+      gbox[(1 - col1) * COL + L::fidx(f, a, bb)] = (r0 * B[n] + r1 * x1) + r2 * x2;
+    }
+  }
+  if (t == 0) bulk_wait_read0();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Generic cell access on a box record in global memory (non-hot kernels)
 // ---------------------------------------------------------------------------------------------
 template <int NC>
