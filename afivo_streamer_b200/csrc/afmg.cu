@@ -256,16 +256,6 @@ void enq_gsrb(afmg_handle* h, int l, int redblack) {
   });
 }
 
-// opt in to large dynamic shared memory / max carveout once per process (not a stream operation, but
-// kept out of graph capture)
-void configure_kernels(afmg_handle* h) {
-  DISPATCH_NC(h, NC, {
-    using G = Gsrb2Cfg<NC>;
-    set_max_smem(k_gsrb2<NC, G::BPC, G::KS, G::MINB>, (size_t)G::BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double));
-    set_max_smem(k_gsrb<NC, GsrbCfg<NC>::BPC>, (size_t)GsrbCfg<NC>::BPC * Lay3<NC>::COL * sizeof(double));
-  });
-}
-
 void enq_rb_prepare(afmg_handle* h, int l) {
   const int n = h->rb_lvl_off[l + 1] - h->rb_lvl_off[l];
   if (n == 0) return;
@@ -288,31 +278,57 @@ void enq_edges_corners(afmg_handle* h, int l) {
   DISPATCH_NC(h, NC, { k_edges_corners<NC><<<n, 64, 0, h->stream>>>(h->cx, h->lvl_off[l], n, V_PHI); });
 }
 
+template <int NC>
+struct OpCfg {
+  static constexpr int KS = (NC == 16) ? 2 : 2;          // k-splits of k_residual2
+  static constexpr int RES_MINB = (NC == 16) ? 4 : 8;
+  static constexpr int RSTR_T = (NC == 16) ? 256 : (NC == 8 ? 64 : 8);
+  static constexpr size_t TILE = (size_t)2 * Lay3<NC>::COL * sizeof(double);
+};
+
 void enq_restrict(afmg_handle* h, int l, int keep_res) {
   const int n = nlev(h, l);
   if (n == 0) return;
   Launch L_(h, "restrict", l);
   DISPATCH_NC(h, NC, {
-    constexpr int T = (NC == 16) ? 256 : (NC == 8 ? 64 : 32);
-    k_restrict<NC><<<n, T, 0, h->stream>>>(h->cx, h->lvl_off[l], n, keep_res);
+    k_restrict2<NC, 4><<<n, OpCfg<NC>::RSTR_T, OpCfg<NC>::TILE, h->stream>>>(h->cx, h->lvl_off[l], n, keep_res);
   });
 }
 
-void enq_correct(afmg_handle* h, int lp) {
+void enq_correct(afmg_handle* h, int lp, bool store_corr) {
   const int n = nlev(h, lp);
   if (n == 0 || h->npar[lp] == 0) return;
-  Launch L_(h, "correct", lp);
-  DISPATCH_NC(h, NC, {
-    const size_t smem = (size_t)(NC + 2) * (NC + 2) * (NC + 2) * sizeof(double);
-    k_correct<NC><<<n, 256, smem, h->stream>>>(h->cx, h->lvl_off[lp], n);
-  });
+  {
+    Launch L_(h, "correct", lp);
+    DISPATCH_NC(h, NC, { k_correct2<NC><<<n * 8, 256, 0, h->stream>>>(h->cx, h->lvl_off[lp], n); });
+  }
+  if (store_corr) {
+    Launch L_(h, "store_corr", lp);
+    DISPATCH_NC(h, NC, { k_store_corr<NC><<<n, 256, 0, h->stream>>>(h->cx, h->lvl_off[lp], n); });
+  }
 }
 
 void enq_residual(afmg_handle* h, int l_lo, int l_hi, bool with_max) {
   const int s0 = h->lvl_off[l_lo], n = h->lvl_off[l_hi + 1] - s0;
   if (n == 0) return;
   Launch L_(h, "residual");
-  DISPATCH_NC(h, NC, { k_residual<NC><<<n, 256, 0, h->stream>>>(h->cx, s0, n, with_max ? h->d_scal : nullptr); });
+  DISPATCH_NC(h, NC, {
+    constexpr int KS = OpCfg<NC>::KS;
+    k_residual2<NC, KS, OpCfg<NC>::RES_MINB><<<n, KS * NC * NC / 2, OpCfg<NC>::TILE, h->stream>>>(
+        h->cx, s0, n, with_max ? h->d_scal : nullptr);
+  });
+}
+
+// opt in to large dynamic shared memory / max carveout once per process (not a stream operation, but
+// kept out of graph capture)
+void configure_kernels(afmg_handle* h) {
+  DISPATCH_NC(h, NC, {
+    using G = Gsrb2Cfg<NC>;
+    set_max_smem(k_gsrb2<NC, G::BPC, G::KS, G::MINB>, (size_t)G::BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double));
+    set_max_smem(k_gsrb<NC, GsrbCfg<NC>::BPC>, (size_t)GsrbCfg<NC>::BPC * Lay3<NC>::COL * sizeof(double));
+    set_max_smem(k_residual2<NC, OpCfg<NC>::KS, OpCfg<NC>::RES_MINB>, OpCfg<NC>::TILE);
+    set_max_smem(k_restrict2<NC, 4>, OpCfg<NC>::TILE);
+  });
 }
 
 void enq_copy_lvl(afmg_handle* h, int l, int dst, int src) {
@@ -375,7 +391,7 @@ void enq_update_coarse(afmg_handle* h, int l, bool with_tmp) {
 void enq_subtract_mean(afmg_handle* h, int max_lvl);
 
 // mg_fas_vcycle (m_af_multigrid.f90:185-264)
-void enq_vcycle(afmg_handle* h, bool set_residual, int max_lvl) {
+void enq_vcycle(afmg_handle* h, bool set_residual, int max_lvl, bool final_state = true) {
   for (int l = max_lvl; l >= 2; --l) {
     enq_rb_prepare(h, l);
     enq_gsrb_boxes(h, l, false);
@@ -383,7 +399,7 @@ void enq_vcycle(afmg_handle* h, bool set_residual, int max_lvl) {
   }
   enq_coarse(h);
   for (int l = 2; l <= max_lvl; ++l) {
-    enq_correct(h, l - 1);
+    enq_correct(h, l - 1, final_state && !set_residual);
     enq_rb_prepare(h, l);
     enq_gc(h, l, V_PHI, 1, 0);
     enq_gsrb_boxes(h, l, true);
@@ -454,13 +470,14 @@ void enq_fmg(afmg_handle* h, bool set_residual, bool have_guess) {
     enq_init_phi_rhs(h);
   }
   enq_copy_lvl(h, 1, V_TMP, V_PHI);
-  enq_vcycle(h, set_residual && h->L == 1, 1);
+  enq_vcycle(h, set_residual && h->L == 1, 1, h->L == 1);
   for (int l = 2; l <= h->L; ++l) {
     enq_copy_lvl(h, l, V_TMP, V_PHI);
-    enq_correct(h, l - 1);
+    // the correction stored in tmp of the parents is overwritten on the way down of the next cycle
+    enq_correct(h, l - 1, l == h->L && !set_residual);
     enq_rb_prepare(h, l);
     enq_gc(h, l, V_PHI, 1, 0);
-    enq_vcycle(h, set_residual && l == h->L, l);
+    enq_vcycle(h, set_residual && l == h->L, l, l == h->L);
   }
 }
 
@@ -1203,7 +1220,7 @@ int afmg_correct_children(afmg_handle* h, int32_t lvl_parents) {
   SINGLE_OP_PROLOGUE();
   int rc = check_lvl(h, lvl_parents);
   if (rc) return rc;
-  enq_correct(h, lvl_parents);
+  enq_correct(h, lvl_parents, true);
   return finish_op(h);
 }
 

@@ -69,6 +69,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+__device__ __forceinline__ void atomic_max_nonneg(unsigned long long* addr, double v) {
+  atomicMax(addr, (unsigned long long)__double_as_longlong(v));
+}
+
 // neighbour offset tables
 __device__ __forceinline__ int nmat_index(int dx, int dy, int dz) { return (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1); }
 
@@ -383,6 +387,229 @@ __device__ __forceinline__ double apply357(const double* box, const double* cf, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Shared-memory versions of the operator kernels.  S points at both colour blocks of one box
+// (2*COL doubles, as laid out in global memory) staged by one TMA bulk copy.
+// ---------------------------------------------------------------------------------------------
+// L phi at interior cell (i,j,k) from the staged box: stencil_apply_357 (m_af_stencil.f90:462-487)
+template <int NC>
+__device__ __forceinline__ double apply357_smem(const double* S, const double* cf, double c1, int i, int j, int k) {
+  using L = Lay3<NC>;
+  constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL;
+  const int c = (i + j + k) & 1, m = (i - 1) >> 1;
+  const double* Sn = S + (1 - c) * COL;
+  const int idx = L::iidx(m, j, k);
+  const int fx = (k - 1) * H + ((j - 1) >> 1);
+  double xm, xp;
+  if (i & 1) {
+    xm = (m > 0) ? Sn[idx - 1] : Sn[NI + 0 * NF + fx];
+    xp = Sn[idx];
+  } else {
+    xm = Sn[idx];
+    xp = (m < H - 1) ? Sn[idx + 1] : Sn[NI + 1 * NF + fx];
+  }
+  const double ym = (j > 1) ? Sn[idx - H] : Sn[NI + 2 * NF + (k - 1) * H + m];
+  const double yp = (j < NC) ? Sn[idx + H] : Sn[NI + 3 * NF + (k - 1) * H + m];
+  const double zm = (k > 1) ? Sn[idx - NC * H] : Sn[NI + 4 * NF + (j - 1) * H + m];
+  const double zp = (k < NC) ? Sn[idx + NC * H] : Sn[NI + 5 * NF + (j - 1) * H + m];
+  double acc = c1 * S[c * COL + idx];
+  acc = acc + cf[1] * xm;
+  acc = acc + cf[2] * xp;
+  acc = acc + cf[3] * ym;
+  acc = acc + cf[4] * yp;
+  acc = acc + cf[5] * zm;
+  acc = acc + cf[6] * zp;
+  return acc;
+}
+
+// k_residual2: as k_residual; thread (m, j, ks) walks its k-range for both colours, rhs / tmp move
+// directly between global memory and registers (coalesced 256 B per warp).
+template <int NC, int KS, int MINB>
+__global__ void __launch_bounds__(KS* NC* NC / 2, MINB)
+    k_residual2(DevCtx cx, int slot0, int nbox, unsigned long long* maxabs_bits) {
+  using L = Lay3<NC>;
+  constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX, KL = NC / KS;
+  extern __shared__ __align__(128) double smem[];
+  __shared__ uint64_t bar;
+  const int slot = slot0 + blockIdx.x;
+  const int t = threadIdx.x;
+  if (t == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (t == 0) {
+    mbar_expect_tx(&bar, 2 * COL * 8);
+    bulk_g2s(smem, cx.cc[V_PHI] + (size_t)slot * BOX, 2 * COL * 8, &bar);
+  }
+  const double* grhs = cx.cc[V_RHS] + (size_t)slot * BOX;
+  double* gtmp = cx.cc[V_TMP] + (size_t)slot * BOX;
+  const int m = t % H, j = (t / H) % NC + 1, ks = t / (H * NC);
+  const int k0 = ks * KL + 1;
+  double r[KL];
+#pragma unroll
+  for (int kk = 0; kk < KL; ++kk) r[kk] = __ldg(grhs + L::iidx(m, j, k0 + kk));
+  const double* cf = cx.coef + 8 * cx.lvl[slot];
+  const double c1 = cf[0], c2 = cf[1], c3 = cf[2], c4 = cf[3], c5 = cf[4], c6 = cf[5], c7 = cf[6];
+  mbar_wait(&bar, 0);
+  double mx = 0.0;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const double* Sc = smem + c * COL;
+    const double* Sn = smem + (1 - c) * COL;
+    if (c == 1) {
+#pragma unroll
+      for (int kk = 0; kk < KL; ++kk) r[kk] = __ldg(grhs + COL + L::iidx(m, j, k0 + kk));
+    }
+    double s_km1 = (k0 == 1) ? Sn[NI + 4 * NF + (j - 1) * H + m] : Sn[L::iidx(m, j, k0 - 1)];
+    double s_k = Sn[L::iidx(m, j, k0)];
+#pragma unroll
+    for (int kk = 0; kk < KL; ++kk) {
+      const int k = k0 + kk;
+      const int idx = L::iidx(m, j, k);
+      const int pi = (c + j + k) & 1;
+      const double s_kp1 = (k < NC) ? Sn[idx + NC * H] : Sn[NI + 5 * NF + (j - 1) * H + m];
+      const double ym = (j > 1) ? Sn[idx - H] : Sn[NI + 2 * NF + (k - 1) * H + m];
+      const double yp = (j < NC) ? Sn[idx + H] : Sn[NI + 3 * NF + (k - 1) * H + m];
+      const int fx = (k - 1) * H + ((j - 1) >> 1);
+      double xm, xp;
+      if (pi) {
+        xm = (m > 0) ? Sn[idx - 1] : Sn[NI + 0 * NF + fx];
+        xp = s_k;
+      } else {
+        xm = s_k;
+        xp = (m < H - 1) ? Sn[idx + 1] : Sn[NI + 1 * NF + fx];
+      }
+      double acc = c1 * Sc[idx];
+      acc = acc + c2 * xm;
+      acc = acc + c3 * xp;
+      acc = acc + c4 * ym;
+      acc = acc + c5 * yp;
+      acc = acc + c6 * s_km1;
+      acc = acc + c7 * s_kp1;
+      const double res = r[kk] - acc;
+      gtmp[c * COL + idx] = res;
+      mx = fmax(mx, fabs(res));
+      s_km1 = s_k;
+      s_k = s_kp1;
+    }
+  }
+  if (maxabs_bits && cx.child0[slot] < 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((t & 31) == 0 && mx > 0.0) atomic_max_nonneg(maxabs_bits, mx);
+  }
+}
+
+// k_restrict2: as k_restrict with the child's phi staged in shared memory; one thread per coarse
+// cell computes the 8 fine residuals and both 2x2x2 averages.
+template <int NC, int MINB>
+__global__ void __launch_bounds__((NC / 2) * (NC / 2) * (NC / 2) >= 256 ? 256 : (NC / 2) * (NC / 2) * (NC / 2), MINB)
+    k_restrict2(DevCtx cx, int slot0, int nbox, int keep_res) {
+  using L = Lay3<NC>;
+  constexpr int H = L::H, COL = L::COL, BOX = L::BOX;
+  extern __shared__ __align__(128) double smem[];
+  __shared__ uint64_t bar;
+  const int slot = slot0 + blockIdx.x;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, 2 * COL * 8);
+    bulk_g2s(smem, cx.cc[V_PHI] + (size_t)slot * BOX, 2 * COL * 8, &bar);
+  }
+  const double* rhs = cx.cc[V_RHS] + (size_t)slot * BOX;
+  double* tmp = cx.cc[V_TMP] + (size_t)slot * BOX;
+  const int p = cx.parent[slot], cof = cx.coff[slot];
+  double* pphi = cx.cc[V_PHI] + (size_t)p * BOX;
+  double* ptmp = cx.cc[V_TMP] + (size_t)p * BOX;
+  const int ox = (cof & 1) * H, oy = ((cof >> 1) & 1) * H, oz = ((cof >> 2) & 1) * H;
+  const double* cf = cx.coef + 8 * cx.lvl[slot];
+  const double c1 = cf[0];
+  mbar_wait(&bar, 0);
+  for (int n = threadIdx.x; n < H * H * H; n += blockDim.x) {
+    const int ic = n % H + 1, jc = (n / H) % H + 1, kc = n / (H * H) + 1;
+    double rr[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = 2 * ic - 1 + (q & 1), j = 2 * jc - 1 + ((q >> 1) & 1), k = 2 * kc - 1 + (q >> 2);
+      rr[q] = __ldg(rhs + L::interior(i, j, k));
+    }
+    double sr = 0.0, sp = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = 2 * ic - 1 + (q & 1), j = 2 * jc - 1 + ((q >> 1) & 1), k = 2 * kc - 1 + (q >> 2);
+      const double lp = apply357_smem<NC>(smem, cf, c1, i, j, k);
+      const double res = rr[q] - lp;
+      if (keep_res) tmp[L::interior(i, j, k)] = res;
+      sr = sr + res;
+      sp = sp + smem[L::interior(i, j, k)];
+    }
+    const int qp = L::interior(ox + ic, oy + jc, oz + kc);
+    ptmp[qp] = 0.125 * sr;
+    pphi[qp] = 0.125 * sp;
+  }
+}
+
+// k_correct2: child part of correct_children, one CTA per (parent, child): the (nc/2+2)^3 window of
+// the correction t = phi_p - tmp_p the child's prolongation needs is formed in shared memory; the
+// parent's tmp is NOT modified here (k_store_corr does that when the state is observable).
+template <int NC>
+__global__ void __launch_bounds__(256) k_correct2(DevCtx cx, int slot0, int nbox) {
+  using L = Lay3<NC>;
+  constexpr int H = L::H, W = H + 2;
+  __shared__ double sub[W * W * W];
+  const int slot = slot0 + blockIdx.x / 8, ch = blockIdx.x % 8;
+  const int c0 = cx.child0[slot];
+  if (c0 < 0) return;
+  const double* phi = cx.cc[V_PHI] + (size_t)slot * L::BOX;
+  const double* tmp = cx.cc[V_TMP] + (size_t)slot * L::BOX;
+  const int ox = (ch & 1) * H, oy = ((ch >> 1) & 1) * H, oz = ((ch >> 2) & 1) * H;
+  for (int n = threadIdx.x; n < W * W * W; n += blockDim.x) {
+    const int a = n % W, b = (n / W) % W, c = n / (W * W);
+    const int q = L::cell(ox + a, oy + b, oz + c);
+    sub[n] = phi[q] - tmp[q];
+  }
+  __syncthreads();
+  const double* pc = cx.pcoef;
+  const int pshape = cx.pshape;
+  double* cphi = cx.cc[V_PHI] + (size_t)(c0 + ch) * L::BOX;
+  for (int n = threadIdx.x; n < 2 * L::NI; n += blockDim.x) {
+    const int q = (n < L::NI) ? n : (L::COL + n - L::NI);
+    int i, j, k;
+    L::uncell(q, i, j, k);
+    const int i1 = (i + 1) >> 1, i2 = i1 + 1 - 2 * (i & 1);
+    const int j1 = (j + 1) >> 1, j2 = j1 + 1 - 2 * (j & 1);
+    const int k1 = (k + 1) >> 1, k2 = k1 + 1 - 2 * (k & 1);
+    auto P = [&](int a, int b, int c) { return sub[(c * W + b) * W + a]; };
+    double acc = cphi[q];
+    if (pshape == 8) {
+      acc = acc + pc[0] * P(i1, j1, k1);
+      acc = acc + pc[1] * P(i2, j1, k1);
+      acc = acc + pc[2] * P(i1, j2, k1);
+      acc = acc + pc[3] * P(i2, j2, k1);
+      acc = acc + pc[4] * P(i1, j1, k2);
+      acc = acc + pc[5] * P(i2, j1, k2);
+      acc = acc + pc[6] * P(i1, j2, k2);
+      acc = acc + pc[7] * P(i2, j2, k2);
+    } else {
+      acc = acc + pc[0] * P(i1, j1, k1);
+      acc = acc + pc[1] * P(i2, j1, k1);
+      acc = acc + pc[2] * P(i1, j2, k1);
+      acc = acc + pc[3] * P(i1, j1, k2);
+    }
+    cphi[q] = acc;
+  }
+}
+
+// tmp_p = phi_p - tmp_p on the full record of every box of [slot0, slot0+nbox) that has children
+// (first statement of correct_children, m_af_multigrid.f90:636-637)
+template <int NC>
+__global__ void k_store_corr(DevCtx cx, int slot0, int nbox) {
+  using L = Lay3<NC>;
+  const int slot = slot0 + blockIdx.x;
+  if (cx.child0[slot] < 0) return;
+  const double* phi = cx.cc[V_PHI] + (size_t)slot * L::BOX;
+  double* tmp = cx.cc[V_TMP] + (size_t)slot * L::BOX;
+  for (int q = threadIdx.x; q < L::BOX; q += blockDim.x) tmp[q] = phi[q] - tmp[q];
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_rb_prepare: for every refinement-boundary face of a level, interpolate the coarse neighbour's
 // boundary layer to the fine face (first half of mg_sides_rb, m_af_multigrid.f90:294-380).  The
 // coarse level is frozen while the fine level is smoothed, so this runs once per gsrb_boxes /
@@ -689,9 +916,6 @@ __global__ void k_correct(DevCtx cx, int slot0, int nbox) {
 // (residual_box, m_af_multigrid.f90:801-810), plus max |tmp| over leaves (af_tree_maxabs_cc,
 // m_af_utils.f90:773-785) accumulated into *maxabs_bits (non-negative doubles order like uint64).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void atomic_max_nonneg(unsigned long long* addr, double v) {
-  atomicMax(addr, (unsigned long long)__double_as_longlong(v));
-}
 
 template <int NC>
 __global__ void k_residual(DevCtx cx, int slot0, int nbox, unsigned long long* maxabs_bits) {
