@@ -74,6 +74,7 @@ SYMBOLS = {
     "afmg_gc_lvl": (C.c_int, [_H, _I, _I, _I]),
     "afmg_update_coarse": (C.c_int, [_H, _I, _I]),
     "afmg_correct_children": (C.c_int, [_H, _I]),
+    "afmg_correct_children_gc": (C.c_int, [_H, _I]),
     "afmg_residual_lvl": (C.c_int, [_H, _I]),
     "afmg_solve_coarse_grid": (C.c_int, [_H]),
     "afmg_init_phi_rhs": (C.c_int, [_H]),

@@ -268,7 +268,12 @@ void enq_gc(afmg_handle* h, int l, int var, int corners, int mode) {
   const int n = nlev(h, l);
   if (n == 0) return;
   Launch L_(h, mode ? "gc_parent" : "gc", l);
-  DISPATCH_NC(h, NC, { k_gc<NC><<<n, 256, 0, h->stream>>>(h->cx, h->lvl_off[l], n, var, corners, mode); });
+  DISPATCH_NC(h, NC, {
+    if (var == V_PHI && mode != 0)
+      k_gc2<NC><<<n, 256, (size_t)2 * Lay3<NC>::COL * sizeof(double), h->stream>>>(h->cx, h->lvl_off[l], n, corners, mode);
+    else
+      k_gc<NC><<<n, 256, 0, h->stream>>>(h->cx, h->lvl_off[l], n, var, corners, mode);
+  });
 }
 
 void enq_edges_corners(afmg_handle* h, int l) {
@@ -280,9 +285,8 @@ void enq_edges_corners(afmg_handle* h, int l) {
 
 template <int NC>
 struct OpCfg {
-  static constexpr int KS = (NC == 16) ? 2 : 2;          // k-splits of k_residual2
-  static constexpr int RES_MINB = (NC == 16) ? 4 : 8;
-  static constexpr int RSTR_T = (NC == 16) ? 256 : (NC == 8 ? 64 : 8);
+  static constexpr int KS = (NC == 4) ? 1 : 2;           // k-splits of k_resid3 (k-range must stay even)
+  static constexpr int RES_MINB = (NC == 16) ? 3 : 6;
   static constexpr size_t TILE = (size_t)2 * Lay3<NC>::COL * sizeof(double);
 };
 
@@ -291,21 +295,36 @@ void enq_restrict(afmg_handle* h, int l, int keep_res) {
   if (n == 0) return;
   Launch L_(h, "restrict", l);
   DISPATCH_NC(h, NC, {
-    k_restrict2<NC, 4><<<n, OpCfg<NC>::RSTR_T, OpCfg<NC>::TILE, h->stream>>>(h->cx, h->lvl_off[l], n, keep_res);
+    constexpr int KS = OpCfg<NC>::KS;
+    k_resid3<NC, KS, 1, OpCfg<NC>::RES_MINB><<<n, KS * NC * NC / 2, OpCfg<NC>::TILE, h->stream>>>(
+        h->cx, h->lvl_off[l], n, nullptr, keep_res);
   });
 }
 
-void enq_correct(afmg_handle* h, int lp, bool store_corr) {
+// correct_children; with push the side ghost cells of the children are filled as well (the caller
+// must have run enq_rb_prepare(lp + 1) before and runs enq_edges_corners(lp + 1) after)
+void enq_correct(afmg_handle* h, int lp, bool store_corr, bool push) {
   const int n = nlev(h, lp);
   if (n == 0 || h->npar[lp] == 0) return;
   {
     Launch L_(h, "correct", lp);
-    DISPATCH_NC(h, NC, { k_correct2<NC><<<n * 8, 256, 0, h->stream>>>(h->cx, h->lvl_off[lp], n); });
+    DISPATCH_NC(h, NC, {
+      constexpr int W = NC / 2 + 2;
+      const size_t smem = (size_t)(2 * Lay3<NC>::NI + W * W * W) * sizeof(double);
+      k_correct3<NC><<<n * 8, 256, smem, h->stream>>>(h->cx, h->lvl_off[lp], n, push ? 1 : 0);
+    });
   }
   if (store_corr) {
     Launch L_(h, "store_corr", lp);
     DISPATCH_NC(h, NC, { k_store_corr<NC><<<n, 256, 0, h->stream>>>(h->cx, h->lvl_off[lp], n); });
   }
+}
+
+// correct_children(lp) followed by af_gc_lvl(lp + 1) (m_af_multigrid.f90:219-222)
+void enq_correct_gc(afmg_handle* h, int lp, bool store_corr) {
+  enq_rb_prepare(h, lp + 1);
+  enq_correct(h, lp, store_corr, true);
+  enq_edges_corners(h, lp + 1);
 }
 
 void enq_residual(afmg_handle* h, int l_lo, int l_hi, bool with_max) {
@@ -314,8 +333,8 @@ void enq_residual(afmg_handle* h, int l_lo, int l_hi, bool with_max) {
   Launch L_(h, "residual");
   DISPATCH_NC(h, NC, {
     constexpr int KS = OpCfg<NC>::KS;
-    k_residual2<NC, KS, OpCfg<NC>::RES_MINB><<<n, KS * NC * NC / 2, OpCfg<NC>::TILE, h->stream>>>(
-        h->cx, s0, n, with_max ? h->d_scal : nullptr);
+    k_resid3<NC, KS, 0, OpCfg<NC>::RES_MINB><<<n, KS * NC * NC / 2, OpCfg<NC>::TILE, h->stream>>>(
+        h->cx, s0, n, with_max ? h->d_scal : nullptr, 0);
   });
 }
 
@@ -326,8 +345,10 @@ void configure_kernels(afmg_handle* h) {
     using G = Gsrb2Cfg<NC>;
     set_max_smem(k_gsrb2<NC, G::BPC, G::KS, G::MINB>, (size_t)G::BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double));
     set_max_smem(k_gsrb<NC, GsrbCfg<NC>::BPC>, (size_t)GsrbCfg<NC>::BPC * Lay3<NC>::COL * sizeof(double));
-    set_max_smem(k_residual2<NC, OpCfg<NC>::KS, OpCfg<NC>::RES_MINB>, OpCfg<NC>::TILE);
-    set_max_smem(k_restrict2<NC, 4>, OpCfg<NC>::TILE);
+    set_max_smem(k_resid3<NC, OpCfg<NC>::KS, 0, OpCfg<NC>::RES_MINB>, OpCfg<NC>::TILE);
+    set_max_smem(k_resid3<NC, OpCfg<NC>::KS, 1, OpCfg<NC>::RES_MINB>, OpCfg<NC>::TILE);
+    set_max_smem(k_gc2<NC>, OpCfg<NC>::TILE);
+    set_max_smem(k_correct3<NC>, (size_t)(2 * Lay3<NC>::NI + (NC / 2 + 2) * (NC / 2 + 2) * (NC / 2 + 2)) * sizeof(double));
   });
 }
 
@@ -399,9 +420,7 @@ void enq_vcycle(afmg_handle* h, bool set_residual, int max_lvl, bool final_state
   }
   enq_coarse(h);
   for (int l = 2; l <= max_lvl; ++l) {
-    enq_correct(h, l - 1, final_state && !set_residual);
-    enq_rb_prepare(h, l);
-    enq_gc(h, l, V_PHI, 1, 0);
+    enq_correct_gc(h, l - 1, final_state && !set_residual);
     enq_gsrb_boxes(h, l, true);
   }
   if (set_residual) {
@@ -474,9 +493,7 @@ void enq_fmg(afmg_handle* h, bool set_residual, bool have_guess) {
   for (int l = 2; l <= h->L; ++l) {
     enq_copy_lvl(h, l, V_TMP, V_PHI);
     // the correction stored in tmp of the parents is overwritten on the way down of the next cycle
-    enq_correct(h, l - 1, l == h->L && !set_residual);
-    enq_rb_prepare(h, l);
-    enq_gc(h, l, V_PHI, 1, 0);
+    enq_correct_gc(h, l - 1, l == h->L && !set_residual);
     enq_vcycle(h, set_residual && l == h->L, l, l == h->L);
   }
 }
@@ -1220,7 +1237,16 @@ int afmg_correct_children(afmg_handle* h, int32_t lvl_parents) {
   SINGLE_OP_PROLOGUE();
   int rc = check_lvl(h, lvl_parents);
   if (rc) return rc;
-  enq_correct(h, lvl_parents, true);
+  enq_correct(h, lvl_parents, true, false);
+  return finish_op(h);
+}
+
+int afmg_correct_children_gc(afmg_handle* h, int32_t lvl_parents) {
+  SINGLE_OP_PROLOGUE();
+  int rc = check_lvl(h, lvl_parents);
+  if (rc) return rc;
+  if (lvl_parents >= h->L) return h->fail(AFMG_ERR_ARG, "no level above %d", lvl_parents);
+  enq_correct_gc(h, lvl_parents, true);
   return finish_op(h);
 }
 

@@ -237,6 +237,73 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Ghost-cell epilogue shared by the kernels that hold freshly computed interior values of a box in
+// shared memory (I0 / I1 = interior colour blocks 0 / 1, NI doubles each).  For the colours in `mask`
+// the boundary layers are pushed into the opposite ghost faces of the same-level neighbours
+// (copy_from_nb, m_af_ghostcell.f90:654-669); on physical / refinement faces all nc^2 ghost cells of
+// the box are recomputed from their rule (bc_to_gc :173-279; mg_sides_rb m_af_multigrid.f90:383-459).
+// t = index among the TPB threads working on this box.  The z faces are contiguous in shared memory
+// and leave as TMA bulk copies issued by t == 0; the CALLER commits and waits for the bulk group.
+template <int NC, int TPB>
+__device__ __forceinline__ void epilogue_faces(const DevCtx& cx, int slot, const double* I0, const double* I1, int mask,
+                                               int t) {
+  using L = Lay3<NC>;
+  constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX;
+  double* const phi = cx.cc[V_PHI];
+  double* const gbox = phi + (size_t)slot * BOX;
+  const int* nbp = cx.nbr + slot * 6;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    if (!((mask >> c) & 1)) continue;
+    const double* Ic = c ? I1 : I0;
+    if (t == 0) {
+      const int n4 = nbp[4], n5 = nbp[5];
+      if (n4 >= 0) bulk_s2g(phi + (size_t)n4 * BOX + c * COL + NI + 5 * NF, Ic, NF * 8);
+      if (n5 >= 0) bulk_s2g(phi + (size_t)n5 * BOX + c * COL + NI + 4 * NF, Ic + (NC - 1) * NC * H, NF * 8);
+    }
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const int nb = nbp[f];
+      if (nb < 0) continue;
+      double* dst = phi + (size_t)nb * BOX + c * COL + NI + (f ^ 1) * NF;
+      for (int fi = t; fi < NF; fi += TPB) {
+        const int k = fi / H + 1, ah = fi % H;
+        int src;
+        if (f >= 2) {
+          src = L::iidx(ah, (f & 1) ? NC : 1, k);
+        } else {
+          // cells i = 1 (f = 0) or i = NC (f = 1) of colour c: j has parity (c + i + k) & 1
+          const int i = (f & 1) ? NC : 1;
+          const int j = 2 * ah + 2 - ((c + i + k) & 1);
+          src = L::iidx((i - 1) >> 1, j, k);
+        }
+        dst[fi] = Ic[src];
+      }
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < 6; ++f) {
+    if (nbp[f] >= 0) continue;
+    const int row = cx.aux[slot * 6 + f];
+    const double* rc = cx.rule_c + 3 * row;
+    const double r0 = rc[0], r1 = rc[1], r2 = rc[2];
+    const double* B = cx.rule_B + (size_t)row * L::NC2;
+    const int d = f >> 1, hi = f & 1;
+    for (int n = t; n < L::NC2; n += TPB) {
+      const int a = n % NC + 1, bb = n / NC + 1;
+      const int l1 = hi ? NC : 1, l2 = hi ? NC - 1 : 2;
+      // (x, y, z) of the layer-1 / layer-2 cells: dim d takes the layer, the others (a, bb) in order
+      const int px1 = (d == 0) ? l1 : a, py1 = (d == 0) ? a : (d == 1 ? l1 : bb), pz1 = (d == 2) ? l1 : bb;
+      const int px2 = (d == 0) ? l2 : a, py2 = (d == 0) ? a : (d == 1 ? l2 : bb), pz2 = (d == 2) ? l2 : bb;
+      const int col1 = (px1 + py1 + pz1) & 1;  // colour of the layer-1 cell; ghost has colour 1 - col1
+      const int i1 = L::iidx((px1 - 1) >> 1, py1, pz1), i2 = L::iidx((px2 - 1) >> 1, py2, pz2);
+      const double x1 = (col1 ? I1 : I0)[i1];
+      const double x2 = (col1 ? I0 : I1)[i2];
+      gbox[(1 - col1) * COL + L::fidx(f, a, bb)] = (r0 * B[n] + r1 * x1) + r2 * x2;
+    }
+  }
+}
+
 template <int NC, int BPC, int KS, int MINB>
 __global__ void __launch_bounds__(BPC* KS* NC* NC / 2, MINB) k_gsrb2(DevCtx cx, int slot0, int nbox, int C, int lvl) {
   using L = Lay3<NC>;
@@ -308,60 +375,9 @@ __global__ void __launch_bounds__(BPC* KS* NC* NC / 2, MINB) k_gsrb2(DevCtx cx, 
   if (!active) return;
 
   // ---- epilogue: new colour-C values are in R (layout of an interior colour block)
-  double* const gbox = phi + (size_t)slot * BOX;
-  const int* nbp = cx.nbr + slot * 6;
-  if (t == 0) {
-    bulk_s2g(gbox + C * COL, R, NI * 8);
-    // z faces: layer k = 1 / k = NC of R is contiguous (NF doubles)
-    const int n4 = nbp[4], n5 = nbp[5];
-    if (n4 >= 0) bulk_s2g(phi + (size_t)n4 * BOX + C * COL + NI + 5 * NF, R, NF * 8);
-    if (n5 >= 0) bulk_s2g(phi + (size_t)n5 * BOX + C * COL + NI + 4 * NF, R + (NC - 1) * NC * H, NF * 8);
-    bulk_commit();
-  }
-  // y and x faces: push the colour-C boundary layer into the neighbour's opposite ghost face
-#pragma unroll
-  for (int f = 0; f < 4; ++f) {
-    const int nb = nbp[f];
-    if (nb < 0) continue;
-    double* dst = phi + (size_t)nb * BOX + C * COL + NI + (f ^ 1) * NF;
-    for (int fi = t; fi < NF; fi += TPB) {
-      const int k = fi / H + 1, ah = fi % H;
-      int src;
-      if (f >= 2) {
-        src = L::iidx(ah, (f & 1) ? NC : 1, k);
-      } else {
-        // cells i = 1 (f = 0) or i = NC (f = 1) of colour C: j has parity (C + i + k) & 1
-        const int i = (f & 1) ? NC : 1;
-        const int j = 2 * ah + 2 - ((C + i + k) & 1);
-        src = L::iidx((i - 1) >> 1, j, k);
-      }
-      dst[fi] = R[src];
-    }
-  }
-  // physical / refinement faces: recompute all nc^2 ghost cells of the face from the rule
-#pragma unroll
-  for (int f = 0; f < 6; ++f) {
-    if (nbp[f] >= 0) continue;
-    const int row = cx.aux[slot * 6 + f];
-    const double* rc = cx.rule_c + 3 * row;
-    const double r0 = rc[0], r1 = rc[1], r2 = rc[2];
-    const double* B = cx.rule_B + (size_t)row * L::NC2;
-    const int d = f >> 1, hi = f & 1;
-    const int ta = (d == 0) ? 1 : 0, tb = (d == 2) ? 1 : 2;
-    for (int n = t; n < L::NC2; n += TPB) {
-      const int a = n % NC + 1, bb = n / NC + 1;
-      int q1[3], q2[3];
-      q1[ta] = q2[ta] = a;
-      q1[tb] = q2[tb] = bb;
-      q1[d] = hi ? NC : 1;
-      q2[d] = hi ? NC - 1 : 2;
-      const int col1 = (q1[0] + q1[1] + q1[2]) & 1;  // colour of the layer-1 cell; ghost has colour 1 - col1
-      const int i1 = L::iidx((q1[0] - 1) >> 1, q1[1], q1[2]), i2 = L::iidx((q2[0] - 1) >> 1, q2[1], q2[2]);
-      const double x1 = (col1 == C) ? R[i1] : S[i1];
-      const double x2 = (col1 == C) ? S[i2] : R[i2];
-      gbox[(1 - col1) * COL + L::fidx(f, a, bb)] = (r0 * B[n] + r1 * x1) + r2 * x2;
-    }
-  }
+  if (t == 0) bulk_s2g(phi + (size_t)slot * BOX + C * COL, R, NI * 8);
+  epilogue_faces<NC, TPB>(cx, slot, C ? S : R, C ? R : S, 1 << C, t);
+  if (t == 0) bulk_commit();
   if (t == 0) bulk_wait_read0();
 }
 
@@ -497,6 +513,135 @@ __global__ void __launch_bounds__(KS* NC* NC / 2, MINB)
   }
 }
 
+// k_resid3: residual of one box per CTA with the x-pair formulation: thread (m, j, ks) owns the two
+// cells i = 2m+1 (A) and i = 2m+2 (B) of row (j, k) -- one of each colour, same index in their colour
+// blocks -- and walks its k-range, so that z neighbours chain through registers (8 LDS per 2 cells).
+//   MODE 0: tmp = rhs - L(phi)  (+ max |tmp| over leaves)          residual_box / af_tree_maxabs_cc
+//   MODE 1: child part of update_coarse / set_coarse_phi_rhs: the residual and phi are averaged over
+//           2x2x2 cells in the reference's summation order (m_af_restrict.f90:120-133) and written into
+//           the parent's tmp / phi; odd-j lanes accumulate, the even-j row arrives by warp shuffle.
+template <int NC, int KS, int MODE, int MINB>
+__global__ void __launch_bounds__(KS* NC* NC / 2, MINB)
+    k_resid3(DevCtx cx, int slot0, int nbox, unsigned long long* maxabs_bits, int keep_res) {
+  using L = Lay3<NC>;
+  constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX, KL = NC / KS;
+  static_assert(KL % 2 == 0, "z pairs must stay inside one thread");
+  extern __shared__ __align__(128) double smem[];
+  __shared__ uint64_t bar;
+  const int slot = slot0 + blockIdx.x;
+  const int t = threadIdx.x;
+  if (t == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (t == 0) {
+    mbar_expect_tx(&bar, 2 * COL * 8);
+    bulk_g2s(smem, cx.cc[V_PHI] + (size_t)slot * BOX, 2 * COL * 8, &bar);
+  }
+  const double* grhs = cx.cc[V_RHS] + (size_t)slot * BOX;
+  double* gtmp = cx.cc[V_TMP] + (size_t)slot * BOX;
+  const int m = t % H, j = (t / H) % NC + 1, ks = t / (H * NC);
+  const int k0 = ks * KL + 1;
+  // colour of cell A at (j, k0); it alternates with k
+  const int cA0 = (1 + j + k0) & 1;
+  double rA[KL], rB[KL];
+#pragma unroll
+  for (int kk = 0; kk < KL; ++kk) {
+    const int cA = (cA0 + kk) & 1;
+    const int idx = L::iidx(m, j, k0 + kk);
+    rA[kk] = __ldg(grhs + cA * COL + idx);
+    rB[kk] = __ldg(grhs + (1 - cA) * COL + idx);
+  }
+  const double* cf = cx.coef + 8 * cx.lvl[slot];
+  const double c1 = cf[0], c2 = cf[1], c3 = cf[2], c4 = cf[3], c5 = cf[4], c6 = cf[5], c7 = cf[6];
+  int p = 0, ox = 0, oy = 0, oz = 0;
+  if (MODE == 1) {
+    p = cx.parent[slot];
+    const int cof = cx.coff[slot];
+    ox = (cof & 1) * H;
+    oy = ((cof >> 1) & 1) * H;
+    oz = ((cof >> 2) & 1) * H;
+  }
+  const unsigned lanes = __activemask();  // a box of 4^3 cells has fewer than 32 threads
+  mbar_wait(&bar, 0);
+  double mx = 0.0, sr = 0.0, sp = 0.0;
+  // chain registers: a0/b0 = centre values at k, azm/bzm = values below
+  const double* SA = smem + cA0 * COL;        // block holding cell A at k0
+  const double* SB = smem + (1 - cA0) * COL;  // block holding cell B at k0
+  double a0 = SA[L::iidx(m, j, k0)], b0 = SB[L::iidx(m, j, k0)];
+  double azm = (k0 == 1) ? SB[NI + 4 * NF + (j - 1) * H + m] : SB[L::iidx(m, j, k0 - 1)];
+  double bzm = (k0 == 1) ? SA[NI + 4 * NF + (j - 1) * H + m] : SA[L::iidx(m, j, k0 - 1)];
+#pragma unroll
+  for (int kk = 0; kk < KL; ++kk) {
+    const int k = k0 + kk;
+    const int idx = L::iidx(m, j, k);
+    const int fx = (k - 1) * H + ((j - 1) >> 1);
+    const int fy = NI + (k - 1) * H + m, fz = NI + (j - 1) * H + m;
+    const double azp = (k < NC) ? SB[idx + NC * H] : SB[fz + 5 * NF];
+    const double bzp = (k < NC) ? SA[idx + NC * H] : SA[fz + 5 * NF];
+    const double axm = (m > 0) ? SB[idx - 1] : SB[NI + 0 * NF + fx];
+    const double bxp = (m < H - 1) ? SA[idx + 1] : SA[NI + 1 * NF + fx];
+    const double aym = (j > 1) ? SB[idx - H] : SB[fy + 2 * NF];
+    const double ayp = (j < NC) ? SB[idx + H] : SB[fy + 3 * NF];
+    const double bym = (j > 1) ? SA[idx - H] : SA[fy + 2 * NF];
+    const double byp = (j < NC) ? SA[idx + H] : SA[fy + 3 * NF];
+    double la = c1 * a0;
+    la = la + c2 * axm;
+    la = la + c3 * b0;
+    la = la + c4 * aym;
+    la = la + c5 * ayp;
+    la = la + c6 * azm;
+    la = la + c7 * azp;
+    double lb = c1 * b0;
+    lb = lb + c2 * a0;
+    lb = lb + c3 * bxp;
+    lb = lb + c4 * bym;
+    lb = lb + c5 * byp;
+    lb = lb + c6 * bzm;
+    lb = lb + c7 * bzp;
+    const double resA = rA[kk] - la, resB = rB[kk] - lb;
+    const int cA = (cA0 + kk) & 1;
+    if (MODE == 0 || keep_res) {
+      gtmp[cA * COL + idx] = resA;
+      gtmp[(1 - cA) * COL + idx] = resB;
+    }
+    if (MODE == 0) {
+      mx = fmax(mx, fmax(fabs(resA), fabs(resB)));
+    } else {
+      // rows j (own) and j+1 (lane + H); only odd j accumulates
+      const double nA = __shfl_down_sync(lanes, resA, H), nB = __shfl_down_sync(lanes, resB, H);
+      if ((kk & 1) == 0) {
+        sr = 0.0;
+        sp = 0.0;
+      }
+      sr = sr + resA;
+      sr = sr + resB;
+      sr = sr + nA;
+      sr = sr + nB;
+      sp = sp + a0;
+      sp = sp + b0;
+      sp = sp + ayp;  // phi(2m+1, j+1, k)
+      sp = sp + byp;  // phi(2m+2, j+1, k)
+      if ((kk & 1) == 1 && (j & 1)) {
+        const int qp = L::interior(ox + m + 1, oy + ((j + 1) >> 1), oz + (k >> 1));
+        cx.cc[V_TMP][(size_t)p * BOX + qp] = 0.125 * sr;
+        cx.cc[V_PHI][(size_t)p * BOX + qp] = 0.125 * sp;
+      }
+    }
+    // next step: colours swap, so A/B blocks swap roles
+    azm = a0;
+    bzm = b0;
+    a0 = azp;
+    b0 = bzp;
+    const double* tsw = SA;
+    SA = SB;
+    SB = tsw;
+  }
+  if (MODE == 0 && maxabs_bits && cx.child0[slot] < 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(lanes, mx, o, 32));
+    if ((t & 31) == 0 && mx > 0.0) atomic_max_nonneg(maxabs_bits, mx);
+  }
+}
+
 // k_restrict2: as k_restrict with the child's phi staged in shared memory; one thread per coarse
 // cell computes the 8 fine residuals and both 2x2x2 averages.
 template <int NC, int MINB>
@@ -594,6 +739,152 @@ __global__ void __launch_bounds__(256) k_correct2(DevCtx cx, int slot0, int nbox
       acc = acc + pc[3] * P(i1, j1, k2);
     }
     cphi[q] = acc;
+  }
+}
+
+// k_correct3: k_correct2 with the child's interior staged in shared memory by TMA (bulk load, update
+// in place, bulk store).  With push != 0 it also performs the side ghost fill of the af_gc_lvl that
+// follows correct_children in the cycle (m_af_multigrid.f90:222, :171): boundary layers of both
+// colours are pushed to the neighbours, rule faces are recomputed (epilogue_faces); edges / corners
+// are done by k_edges_corners afterwards.
+template <int NC>
+__global__ void __launch_bounds__(256) k_correct3(DevCtx cx, int slot0, int nbox, int push) {
+  using L = Lay3<NC>;
+  constexpr int H = L::H, W = H + 2, NI = L::NI, COL = L::COL, BOX = L::BOX;
+  extern __shared__ __align__(128) double smem[];  // I0[NI], I1[NI], sub[W^3]
+  __shared__ uint64_t bar;
+  double* I0 = smem;
+  double* I1 = smem + NI;
+  double* sub = smem + 2 * NI;
+  const int slot = slot0 + blockIdx.x / 8, ch = blockIdx.x % 8;
+  const int c0 = cx.child0[slot];
+  if (c0 < 0) return;
+  const int t = threadIdx.x;
+  const int cslot = c0 + ch;
+  double* cphi = cx.cc[V_PHI] + (size_t)cslot * BOX;
+  if (t == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (t == 0) {
+    mbar_expect_tx(&bar, 2 * NI * 8);
+    bulk_g2s(I0, cphi, NI * 8, &bar);
+    bulk_g2s(I1, cphi + COL, NI * 8, &bar);
+  }
+  const double* phi = cx.cc[V_PHI] + (size_t)slot * BOX;
+  const double* tmp = cx.cc[V_TMP] + (size_t)slot * BOX;
+  const int ox = (ch & 1) * H, oy = ((ch >> 1) & 1) * H, oz = ((ch >> 2) & 1) * H;
+  for (int n = t; n < W * W * W; n += 256) {
+    const int a = n % W, b = (n / W) % W, c = n / (W * W);
+    const int q = L::cell(ox + a, oy + b, oz + c);
+    sub[n] = phi[q] - tmp[q];
+  }
+  mbar_wait(&bar, 0);
+  __syncthreads();
+  double pc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) pc[q] = cx.pcoef[q];
+  const int pshape = cx.pshape;
+  constexpr int TPBX = H * NC;  // threads per k-range
+  constexpr int KSX = (256 / TPBX < NC) ? 256 / TPBX : NC;
+  constexpr int KLX = NC / KSX;
+  if (t < TPBX * KSX) {
+    const int m = t % H, j = (t / H) % NC + 1, ks = t / TPBX;
+    const int j1 = (j + 1) >> 1, j2 = j1 + 1 - 2 * (j & 1);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      double* Ic = c ? I1 : I0;
+#pragma unroll
+      for (int kk = 0; kk < KLX; ++kk) {
+        const int k = ks * KLX + kk + 1;
+        const int i = 2 * m + 2 - ((c + j + k) & 1);
+        const int i1 = (i + 1) >> 1, i2 = i1 + 1 - 2 * (i & 1);
+        const int k1 = (k + 1) >> 1, k2 = k1 + 1 - 2 * (k & 1);
+        const double* r11 = sub + (k1 * W + j1) * W;
+        const double* r21 = sub + (k1 * W + j2) * W;
+        const double* r12 = sub + (k2 * W + j1) * W;
+        const double* r22 = sub + (k2 * W + j2) * W;
+        const int idx = L::iidx(m, j, k);
+        double acc = Ic[idx];
+        if (pshape == 8) {
+          acc = acc + pc[0] * r11[i1];
+          acc = acc + pc[1] * r11[i2];
+          acc = acc + pc[2] * r21[i1];
+          acc = acc + pc[3] * r21[i2];
+          acc = acc + pc[4] * r12[i1];
+          acc = acc + pc[5] * r12[i2];
+          acc = acc + pc[6] * r22[i1];
+          acc = acc + pc[7] * r22[i2];
+        } else {
+          acc = acc + pc[0] * r11[i1];
+          acc = acc + pc[1] * r11[i2];
+          acc = acc + pc[2] * r21[i1];
+          acc = acc + pc[3] * r12[i1];
+        }
+        Ic[idx] = acc;
+      }
+    }
+  }
+  fence_async_smem();
+  __syncthreads();
+  if (t == 0) {
+    bulk_s2g(cphi, I0, NI * 8);
+    bulk_s2g(cphi + COL, I1, NI * 8);
+  }
+  if (push) epilogue_faces<NC, 256>(cx, cslot, I0, I1, 3, t);
+  if (t == 0) {
+    bulk_commit();
+    bulk_wait_read0();
+  }
+}
+
+template <int NC>
+__device__ void gc_sides(const DevCtx& cx, int slot, double* var_base);
+template <int NC>
+__device__ void gc_edges_corners(const DevCtx& cx, int slot, double* var_base);
+
+// k_gc2: af_gc_lvl for one level, and for boxes with children the parent part of update_coarse
+// (see k_gc) computed from a shared-memory copy of the box (TMA bulk load) instead of global loads.
+template <int NC>
+__global__ void __launch_bounds__(256) k_gc2(DevCtx cx, int slot0, int nbox, int corners, int mode) {
+  using L = Lay3<NC>;
+  constexpr int NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX;
+  extern __shared__ __align__(128) double smem[];  // 2*COL
+  __shared__ uint64_t bar;
+  const int slot = slot0 + blockIdx.x;
+  const int t = threadIdx.x;
+  double* gphi = cx.cc[V_PHI] + (size_t)slot * BOX;
+  const bool upd = mode != 0 && cx.child0[slot] >= 0;
+  if (upd) {
+    if (t == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (t == 0) {
+      mbar_expect_tx(&bar, 2 * COL * 8);
+      bulk_g2s(smem, gphi, 2 * COL * 8, &bar);
+    }
+  }
+  gc_sides<NC>(cx, slot, cx.cc[V_PHI]);
+  __syncthreads();
+  if (corners) gc_edges_corners<NC>(cx, slot, cx.cc[V_PHI]);
+  if (!upd) return;
+  mbar_wait(&bar, 0);
+  // the staged copy may hold stale ghost faces: refresh them from what this CTA just wrote
+  for (int n = t; n < 2 * 6 * NF; n += 256) {
+    const int c = n / (6 * NF), r = n % (6 * NF);
+    smem[c * COL + NI + r] = gphi[c * COL + NI + r];
+  }
+  __syncthreads();
+  double* rhs = cx.cc[V_RHS] + (size_t)slot * BOX;
+  double* tmp = cx.cc[V_TMP] + (size_t)slot * BOX;
+  const double* cf = cx.coef + 8 * cx.lvl[slot];
+  const double c1 = cf[0];
+  for (int q = t; q < BOX; q += 256) {
+    const bool is_interior = (q < L::OFF_E) && ((q % COL) < NI);
+    if (is_interior) {
+      int i, j, k;
+      L::uncell(q, i, j, k);
+      const double lp = apply357_smem<NC>(smem, cf, c1, i, j, k);
+      rhs[q] = lp + tmp[q];
+    }
+    if (mode == 1) tmp[q] = (q < 2 * COL) ? smem[q] : gphi[q];
   }
 }
 

@@ -122,6 +122,9 @@ class mg_t:
     def correct_children(self, lvl_parents):
         self._check(_lib.lib().afmg_correct_children(self._h, lvl_parents))
 
+    def correct_children_gc(self, lvl_parents):
+        self._check(_lib.lib().afmg_correct_children_gc(self._h, lvl_parents))
+
     def residual_lvl(self, lvl):
         self._check(_lib.lib().afmg_residual_lvl(self._h, lvl))
 

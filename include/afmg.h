@@ -163,6 +163,8 @@ int afmg_gsrb_halfsweep(afmg_handle* h, int32_t lvl, int32_t redblack);   /* mg%
 int afmg_gc_lvl(afmg_handle* h, int32_t lvl, int32_t var, int32_t corners); /* af_gc_lvl, m_af_ghostcell.f90:49-61 */
 int afmg_update_coarse(afmg_handle* h, int32_t lvl, int32_t with_tmp);    /* :691-738 / :742-776 */
 int afmg_correct_children(afmg_handle* h, int32_t lvl_parents);           /* :624-646 */
+/* correct_children(lvl_parents) followed by af_gc_lvl(lvl_parents + 1), as in the cycles (:219-222) */
+int afmg_correct_children_gc(afmg_handle* h, int32_t lvl_parents);
 int afmg_residual_lvl(afmg_handle* h, int32_t lvl);                       /* residual_box :801-810 */
 int afmg_solve_coarse_grid(afmg_handle* h);                               /* :266-291 */
 int afmg_init_phi_rhs(afmg_handle* h);                                    /* :779-799 */

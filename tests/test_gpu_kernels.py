@@ -78,6 +78,17 @@ def test_correct_children_bit_exact(pair):
     assert_same_state(tree, orc, mg)
 
 
+def test_correct_children_then_gc_bit_exact(pair):
+    """correct_children + af_gc_lvl as fused in the cycles (push from the prolongation kernel)."""
+    tree, orc, mg = pair
+    fill_all_ghosts(tree, orc, mg)
+    for lvl in range(1, tree.highest_lvl):
+        orc.correct_children(lvl)
+        orc.gc_lvl(lvl + 1, M.I_PHI, True)
+        mg.correct_children_gc(lvl)
+    assert_same_state(tree, orc, mg)
+
+
 def test_residual_and_maxabs(pair):
     tree, orc, mg = pair
     fill_all_ghosts(tree, orc, mg)

@@ -22,14 +22,23 @@ print(f"{name}: V-cycle {mg.last_cycle_ms() / 20:.4f} ms  ({mg.cell_updates() * 
 mg.fas_fmg_async(False, True, 5)
 mg.sync()
 print(f"{name}: FMG {mg.last_cycle_ms() / 5:.4f} ms")
-mg.set_profiling(True)
 L = tree.highest_lvl
+prev = 0.0
+for lv in range(1, L + 1):
+    mg.fas_vcycle_async(False, lv, 3)
+    mg.sync()
+    mg.fas_vcycle_async(False, lv, 20)
+    mg.sync()
+    cur = mg.last_cycle_ms() / 20
+    print(f"  V-cycle(highest_lvl={lv}) {1e3 * cur:9.1f} us   (+{1e3 * (cur - prev):.1f} us for this level)")
+    prev = cur
+mg.set_profiling(True)
 for _ in range(reps):
     for lv in range(L, 1, -1):
         mg.gsrb_halfsweep(lv, 1)
         mg.gsrb_halfsweep(lv, 2)
     mg.update_coarse(L, True)
-    mg.correct_children(L - 1)
+    mg.correct_children_gc(L - 1)
     mg.gc_lvl(L, M.I_PHI, True)
     mg.residual_lvl(L)
     mg.solve_coarse_grid()
