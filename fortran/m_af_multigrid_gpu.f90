@@ -1,0 +1,291 @@
+!> Drop-in replacement for the solver entry points of afivo's m_af_multigrid
+!> (afivo/src/m_af_multigrid.f90:43, :111, :137, :185, :1188) that forwards to libafmg.so through
+!> ISO_C_BINDING.  Same signatures; the tree (af_t / box_t) stays the reference's own.
+!>
+!> NOTE: this image has no Fortran compiler, so this file is shipped as source and has not been
+!> compiled here.  It uses only m_af_types and iso_c_binding.  Build: add it to afivo/src, list it
+!> in afivo/src/definitions.make next to m_af_multigrid, link with -lafmg.
+module m_af_multigrid_gpu
+  use iso_c_binding
+  use m_af_types
+  implicit none
+  private
+
+  type, bind(c) :: afmg_opts
+     integer(c_int32_t) :: ndim, n_cell, coord_t, n_cycle_down, n_cycle_up
+     integer(c_int32_t) :: use_corners, subtract_mean, prolongation_type, operator_mask
+     integer(c_int32_t) :: has_eps, device, reserved
+     real(c_double)     :: helmholtz_lambda, lsf_boundary_value
+     integer(c_int32_t) :: coarse_grid_size(3), periodic(3)
+     real(c_double)     :: dr_base(3), r_base(3)
+  end type afmg_opts
+
+  type, bind(c) :: afmg_tree
+     integer(c_int32_t) :: highest_lvl, highest_id
+     type(c_ptr) :: lvl_counts, lvl_ids, lvl, ix, parent, children, neighbors, neighbor_mat, r_min
+  end type afmg_tree
+
+  interface
+     integer(c_int) function afmg_create(h, opts) bind(c, name="afmg_create")
+       import; type(c_ptr), intent(out) :: h; type(afmg_opts), intent(in) :: opts
+     end function
+     integer(c_int) function afmg_destroy(h) bind(c, name="afmg_destroy")
+       import; type(c_ptr), value :: h
+     end function
+     integer(c_int) function afmg_set_tree(h, t) bind(c, name="afmg_set_tree")
+       import; type(c_ptr), value :: h; type(afmg_tree), intent(in) :: t
+     end function
+     integer(c_int) function afmg_set_bc(h, n, ids, nbs, types, vals) bind(c, name="afmg_set_bc")
+       import; type(c_ptr), value :: h; integer(c_int32_t), value :: n
+       integer(c_int32_t), intent(in) :: ids(*), nbs(*), types(*); real(c_double), intent(in) :: vals(*)
+     end function
+     integer(c_int) function afmg_upload(h, var, n, ids, packed) bind(c, name="afmg_upload")
+       import; type(c_ptr), value :: h; integer(c_int32_t), value :: var, n
+       integer(c_int32_t), intent(in) :: ids(*); real(c_double), intent(in) :: packed(*)
+     end function
+     integer(c_int) function afmg_download(h, var, n, ids, packed) bind(c, name="afmg_download")
+       import; type(c_ptr), value :: h; integer(c_int32_t), value :: var, n
+       integer(c_int32_t), intent(in) :: ids(*); real(c_double), intent(out) :: packed(*)
+     end function
+     integer(c_int) function afmg_fas_fmg(h, set_residual, have_guess) bind(c, name="afmg_fas_fmg")
+       import; type(c_ptr), value :: h; integer(c_int32_t), value :: set_residual, have_guess
+     end function
+     integer(c_int) function afmg_fas_vcycle(h, set_residual, highest_lvl, standalone) &
+          bind(c, name="afmg_fas_vcycle")
+       import; type(c_ptr), value :: h; integer(c_int32_t), value :: set_residual, highest_lvl, standalone
+     end function
+     integer(c_int) function afmg_set_helmholtz_lambda(h, lambda) bind(c, name="afmg_set_helmholtz_lambda")
+       import; type(c_ptr), value :: h; real(c_double), value :: lambda
+     end function
+     integer(c_int) function afmg_update_operator_stencil(h) bind(c, name="afmg_update_operator_stencil")
+       import; type(c_ptr), value :: h
+     end function
+     integer(c_int) function afmg_max_abs(h, var, val) bind(c, name="afmg_max_abs")
+       import; type(c_ptr), value :: h; integer(c_int32_t), value :: var; real(c_double), intent(out) :: val
+     end function
+  end interface
+
+  integer, parameter :: afmg_phi = 0, afmg_rhs = 1, afmg_tmp = 2
+
+  !> One GPU solver per mg_t; looked up by the address-independent key mg%i_phi/mg%i_rhs/lambda slot
+  type gpu_state_t
+     type(c_ptr) :: h = c_null_ptr
+     integer     :: tree_signature(3) = -1   ! highest_id, highest_lvl, sum of level sizes
+  end type gpu_state_t
+
+  integer, parameter :: max_solvers = 16
+  type(gpu_state_t), save :: solvers(max_solvers)
+
+  public :: mg_gpu_init, mg_gpu_destroy, mg_gpu_fas_fmg, mg_gpu_fas_vcycle
+  public :: mg_gpu_update_operator_stencil, mg_gpu_tree_maxabs_tmp
+
+contains
+
+  subroutine check(rc, what)
+    integer(c_int), intent(in) :: rc
+    character(len=*), intent(in) :: what
+    if (rc /= 0) then
+       print *, "libafmg error ", rc, " in ", what
+       error stop "m_af_multigrid_gpu"
+    end if
+  end subroutine check
+
+  !> mg_init (m_af_multigrid.f90:43-109): options -> afmg_create, topology -> afmg_set_tree
+  subroutine mg_gpu_init(tree, mg, slot)
+    type(af_t), intent(inout) :: tree
+    type(mg_t), intent(inout) :: mg
+    integer, intent(in)       :: slot !< which of the (up to 16) solvers: 1 = field, 2.. = Helmholtz modes
+    type(afmg_opts) :: o
+
+    if (.not. associated(mg%sides_bc)) error stop "mg_init: sides_bc not set"
+    o%ndim = NDIM; o%n_cell = tree%n_cell; o%coord_t = tree%coord_t
+    o%n_cycle_down = mg%n_cycle_down; o%n_cycle_up = mg%n_cycle_up
+    o%use_corners = merge(1, 0, mg%use_corners); o%subtract_mean = merge(1, 0, mg%subtract_mean)
+    o%prolongation_type = mg%prolongation_type; o%operator_mask = mg%operator_mask
+    o%has_eps = merge(1, 0, tree%mg_i_eps > 0); o%device = -1; o%reserved = 0
+    o%helmholtz_lambda = mg%helmholtz_lambda; o%lsf_boundary_value = mg%lsf_boundary_value
+    o%coarse_grid_size = 1; o%periodic = 0; o%dr_base = 0; o%r_base = 0
+    o%coarse_grid_size(1:NDIM) = tree%coarse_grid_size(1:NDIM)
+    o%periodic(1:NDIM) = merge(1, 0, tree%periodic(1:NDIM))
+    o%dr_base(1:NDIM) = tree%dr_base; o%r_base(1:NDIM) = tree%r_base
+    call check(afmg_create(solvers(slot)%h, o), "afmg_create")
+    mg%initialized = .true.
+    call sync_tree(tree, mg, slot)
+  end subroutine mg_gpu_init
+
+  !> Forward topology and boundary conditions when the tree changed (after af_adjust_refinement)
+  subroutine sync_tree(tree, mg, slot)
+    type(af_t), intent(inout) :: tree
+    type(mg_t), intent(in)    :: mg
+    integer, intent(in)       :: slot
+    integer :: sig(3), lvl, n, i, id, nb, n_faces, nc2, bc_type
+    integer(c_int32_t), allocatable, target :: counts(:), ids(:), blvl(:), ix(:, :), parent(:), &
+         children(:, :), neighbors(:, :), nmat(:, :), f_ids(:), f_nbs(:), f_types(:)
+    real(c_double), allocatable, target :: r_min(:, :), f_vals(:, :)
+    real(dp), allocatable :: coords(:, :)
+    type(afmg_tree) :: t
+
+    sig = [tree%highest_id, tree%highest_lvl, 0]
+    do lvl = 1, tree%highest_lvl
+       sig(3) = sig(3) + size(tree%lvls(lvl)%ids) * (lvl + 7)
+    end do
+    if (all(sig == solvers(slot)%tree_signature)) return
+    solvers(slot)%tree_signature = sig
+
+    n = tree%highest_id
+    allocate(counts(tree%highest_lvl), blvl(0:n), ix(NDIM, 0:n), parent(0:n))
+    allocate(children(2**NDIM, 0:n), neighbors(2*NDIM, 0:n), nmat(3**NDIM, 0:n), r_min(NDIM, 0:n))
+    blvl = 0; ix = 0; parent = 0; children = 0; neighbors = 0; nmat = 0; r_min = 0
+    do lvl = 1, tree%highest_lvl
+       counts(lvl) = size(tree%lvls(lvl)%ids)
+    end do
+    allocate(ids(sum(counts)))
+    i = 0
+    do lvl = 1, tree%highest_lvl
+       ids(i+1:i+counts(lvl)) = tree%lvls(lvl)%ids
+       i = i + counts(lvl)
+    end do
+    do i = 1, size(ids)
+       id = ids(i)
+       blvl(id) = tree%boxes(id)%lvl; ix(:, id) = tree%boxes(id)%ix
+       parent(id) = tree%boxes(id)%parent; children(:, id) = tree%boxes(id)%children
+       neighbors(:, id) = tree%boxes(id)%neighbors
+       nmat(:, id) = reshape(tree%boxes(id)%neighbor_mat, [3**NDIM])
+       r_min(:, id) = tree%boxes(id)%r_min
+    end do
+    t%highest_lvl = tree%highest_lvl; t%highest_id = n
+    t%lvl_counts = c_loc(counts); t%lvl_ids = c_loc(ids); t%lvl = c_loc(blvl); t%ix = c_loc(ix)
+    t%parent = c_loc(parent); t%children = c_loc(children); t%neighbors = c_loc(neighbors)
+    t%neighbor_mat = c_loc(nmat); t%r_min = c_loc(r_min)
+    call check(afmg_set_tree(solvers(slot)%h, t), "afmg_set_tree")
+
+    ! mg%sides_bc evaluated on the host for every physical face (it never depends on phi)
+    nc2 = tree%n_cell**(NDIM-1)
+    n_faces = 0
+    do i = 1, size(ids)
+       n_faces = n_faces + count(tree%boxes(ids(i))%neighbors < af_no_box)
+    end do
+    allocate(f_ids(n_faces), f_nbs(n_faces), f_types(n_faces), f_vals(nc2, n_faces), coords(NDIM, nc2))
+    n_faces = 0
+    do i = 1, size(ids)
+       id = ids(i)
+       do nb = 1, af_num_neighbors
+          if (tree%boxes(id)%neighbors(nb) < af_no_box) then
+             n_faces = n_faces + 1
+             call af_get_face_coords(tree%boxes(id), nb, coords)
+             call mg%sides_bc(tree%boxes(id), nb, mg%i_phi, coords, f_vals(:, n_faces), bc_type)
+             f_ids(n_faces) = id; f_nbs(n_faces) = nb; f_types(n_faces) = bc_type
+          end if
+       end do
+    end do
+    call check(afmg_set_bc(solvers(slot)%h, n_faces, f_ids, f_nbs, f_types, f_vals), "afmg_set_bc")
+  end subroutine sync_tree
+
+  !> Pack box%cc(:, :, :, iv) of a list of boxes and upload / download
+  subroutine transfer(tree, slot, iv, var, ids, up)
+    type(af_t), intent(inout) :: tree
+    integer, intent(in)       :: slot, iv, var, ids(:)
+    logical, intent(in)       :: up
+    real(c_double), allocatable :: buf(:, :)
+    integer :: i, n2
+    n2 = (tree%n_cell + 2)**NDIM
+    allocate(buf(n2, size(ids)))
+    if (up) then
+       !$omp parallel do
+       do i = 1, size(ids)
+          buf(:, i) = reshape(tree%boxes(ids(i))%cc(DTIMES(:), iv), [n2])
+       end do
+       call check(afmg_upload(solvers(slot)%h, var, size(ids), ids, buf), "afmg_upload")
+    else
+       call check(afmg_download(solvers(slot)%h, var, size(ids), ids, buf), "afmg_download")
+       !$omp parallel do
+       do i = 1, size(ids)
+          tree%boxes(ids(i))%cc(DTIMES(:), iv) = reshape(buf(:, i), shape(tree%boxes(ids(i))%cc(DTIMES(:), iv)))
+       end do
+    end if
+  end subroutine transfer
+
+  subroutine all_ids(tree, ids, leaves_only)
+    type(af_t), intent(in) :: tree
+    integer, allocatable, intent(out) :: ids(:)
+    logical, intent(in) :: leaves_only
+    integer :: lvl, n
+    n = 0
+    do lvl = 1, tree%highest_lvl
+       n = n + merge(size(tree%lvls(lvl)%leaves), size(tree%lvls(lvl)%ids), leaves_only)
+    end do
+    allocate(ids(n))
+    n = 0
+    do lvl = 1, tree%highest_lvl
+       if (leaves_only) then
+          ids(n+1:n+size(tree%lvls(lvl)%leaves)) = tree%lvls(lvl)%leaves
+          n = n + size(tree%lvls(lvl)%leaves)
+       else
+          ids(n+1:n+size(tree%lvls(lvl)%ids)) = tree%lvls(lvl)%ids
+          n = n + size(tree%lvls(lvl)%ids)
+       end if
+    end do
+  end subroutine all_ids
+
+  !> mg_fas_fmg(tree, mg, set_residual, have_guess)  (m_af_multigrid.f90:137-180)
+  subroutine mg_gpu_fas_fmg(tree, mg, set_residual, have_guess, slot)
+    type(af_t), intent(inout) :: tree
+    type(mg_t), intent(inout) :: mg
+    logical, intent(in)       :: set_residual, have_guess
+    integer, intent(in)       :: slot
+    integer, allocatable      :: ids(:), leaves(:)
+    call sync_tree(tree, mg, slot)
+    call all_ids(tree, leaves, .true.); call all_ids(tree, ids, .false.)
+    call transfer(tree, slot, mg%i_rhs, afmg_rhs, leaves, .true.)      ! callers set rhs on leaves only
+    if (have_guess) call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .true.)
+    call check(afmg_fas_fmg(solvers(slot)%h, merge(1, 0, set_residual), merge(1, 0, have_guess)), "afmg_fas_fmg")
+    call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .false.)
+    if (set_residual) call transfer(tree, slot, mg%i_tmp, afmg_tmp, ids, .false.)
+  end subroutine mg_gpu_fas_fmg
+
+  !> mg_fas_vcycle(tree, mg, set_residual, highest_lvl, standalone)  (m_af_multigrid.f90:185-264)
+  subroutine mg_gpu_fas_vcycle(tree, mg, set_residual, slot, highest_lvl, standalone)
+    type(af_t), intent(inout)     :: tree
+    type(mg_t), intent(inout)     :: mg
+    logical, intent(in)           :: set_residual
+    integer, intent(in)           :: slot
+    integer, intent(in), optional :: highest_lvl
+    logical, intent(in), optional :: standalone
+    integer, allocatable          :: ids(:), leaves(:)
+    integer :: max_lvl, alone
+    max_lvl = 0; if (present(highest_lvl)) max_lvl = highest_lvl
+    alone = 1; if (present(standalone)) alone = merge(1, 0, standalone)
+    call sync_tree(tree, mg, slot)
+    call all_ids(tree, leaves, .true.); call all_ids(tree, ids, .false.)
+    call transfer(tree, slot, mg%i_rhs, afmg_rhs, leaves, .true.)
+    call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .true.)
+    call check(afmg_fas_vcycle(solvers(slot)%h, merge(1, 0, set_residual), max_lvl, alone), "afmg_fas_vcycle")
+    call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .false.)
+    if (set_residual) call transfer(tree, slot, mg%i_tmp, afmg_tmp, ids, .false.)
+  end subroutine mg_gpu_fas_vcycle
+
+  !> max |residual| over leaves without downloading i_tmp (af_tree_maxabs_cc, m_af_utils.f90:773)
+  subroutine mg_gpu_tree_maxabs_tmp(slot, val)
+    integer, intent(in)   :: slot
+    real(dp), intent(out) :: val
+    call check(afmg_max_abs(solvers(slot)%h, afmg_tmp, val), "afmg_max_abs")
+  end subroutine mg_gpu_tree_maxabs_tmp
+
+  !> mg_update_operator_stencil (m_af_multigrid.f90:1188-1214), constant-coefficient part
+  subroutine mg_gpu_update_operator_stencil(mg, slot)
+    type(mg_t), intent(in) :: mg
+    integer, intent(in)    :: slot
+    call check(afmg_set_helmholtz_lambda(solvers(slot)%h, mg%helmholtz_lambda), "afmg_set_helmholtz_lambda")
+    call check(afmg_update_operator_stencil(solvers(slot)%h), "afmg_update_operator_stencil")
+  end subroutine mg_gpu_update_operator_stencil
+
+  !> mg_destroy (m_af_multigrid.f90:111-115)
+  subroutine mg_gpu_destroy(mg, slot)
+    type(mg_t), intent(inout) :: mg
+    integer, intent(in)       :: slot
+    call check(afmg_destroy(solvers(slot)%h), "afmg_destroy")
+    solvers(slot)%h = c_null_ptr; solvers(slot)%tree_signature = -1
+    mg%initialized = .false.
+  end subroutine mg_gpu_destroy
+
+end module m_af_multigrid_gpu

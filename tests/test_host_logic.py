@@ -1,0 +1,115 @@
+"""CPU: host-side logic (tree builder conventions, device layout index maps) and the C ABI
+surface (library loads, exports every symbol include/afmg.h declares, fails loudly without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from afivo_streamer_b200 import _lib
+from afivo_streamer_b200 import mg as M
+from afivo_streamer_b200 import tree as T
+from afivo_streamer_b200 import workloads as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    hdr = open(os.path.join(ROOT, "include", "afmg.h")).read()
+    declared = set(re.findall(r"\b(afmg_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"afmg_handle", "afmg_opts", "afmg_tree"}
+    assert declared, "no declarations found"
+    L = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in afmg.h but not exported by libafmg.so"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+
+
+@pytest.mark.parametrize("ndim,nc", [(3, 4), (3, 8), (3, 16), (2, 8), (2, 16)])
+def test_device_layout_is_a_bijection(ndim, nc):
+    L = _lib.lib()
+    n = nc + 2
+    rng = range(n)
+    offs = [L.afmg_layout_offset(ndim, nc, i, j, k) for k in (rng if ndim == 3 else [0]) for j in rng for i in rng]
+    assert sorted(offs) == list(range(L.afmg_layout_box_len(ndim, nc)))
+
+
+def test_device_layout_colour_blocks():
+    """interior cells of colour (i+j+k)&1 fill the first nc^3/2 entries of their colour block, rows of
+    nc/2 cells contiguous in i (DESIGN.md data layout)."""
+    L = _lib.lib()
+    nc = 8
+    col = nc * nc * nc // 2 + 6 * nc * nc // 2
+    for (i, j, k) in [(1, 1, 1), (2, 1, 1), (3, 1, 1), (1, 2, 1), (8, 8, 8), (7, 8, 8)]:
+        off = L.afmg_layout_offset(3, nc, i, j, k)
+        c = (i + j + k) & 1
+        assert off == c * col + ((k - 1) * nc + (j - 1)) * (nc // 2) + ((i - 1) >> 1)
+    # x-low ghost face cell (0, j, k): colour (j+k)&1, face segment 0
+    off = L.afmg_layout_offset(3, nc, 0, 3, 5)
+    assert off == ((3 + 5) & 1) * col + nc ** 3 // 2 + (5 - 1) * (nc // 2) + ((3 - 1) >> 1)
+
+
+def test_create_fails_loudly_without_gpu():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    t = T.uniform_tree(3, 8, 8, 2)
+    mg = M.mg_t(sides_bc=M.af_bc_dirichlet_zero)
+    with pytest.raises(M.AfmgError) as e:
+        M.mg_init(t, mg)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_mg_init_requires_sides_bc():
+    """mg_init: error stop 'sides_bc not set' (m_af_multigrid.f90:50-51)."""
+    with pytest.raises(M.AfmgError):
+        M.mg_init(T.uniform_tree(3, 8, 8, 1), M.mg_t())
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_tree_conventions(ndim):
+    t = T.corner_refined_tree(ndim, 8, 8, 4)
+    nch = 1 << ndim
+    cd = T.child_dix(ndim)
+    for id_ in range(1, t.highest_id + 1):
+        ch = t.children[id_]
+        if ch[0] == 0:
+            assert np.all(ch == 0)
+            continue
+        for c in range(nch):  # ix_c = 2*ix_p - 1 + af_child_dix (m_af_core.f90:1197-1201)
+            assert np.array_equal(t.ix[ch[c]], 2 * t.ix[id_] - 1 + cd[c])
+            assert t.parent[ch[c]] == id_ and t.lvl[ch[c]] == t.lvl[id_] + 1
+    # neighbours are mutual, reversed direction (af_neighb_rev)
+    for id_ in range(1, t.highest_id + 1):
+        for nb in range(2 * ndim):
+            o = t.neighbors[id_, nb]
+            if o > 0:
+                assert t.neighbors[o, nb ^ 1] == id_
+            elif o == 0:  # refinement boundary: the parent's neighbour exists (2:1 balance)
+                assert t.neighbors[t.parent[id_], nb] > 0
+    # level lists: children of parents in list order
+    for l in range(1, t.highest_lvl):
+        par = t.parents(l)
+        assert np.array_equal(t.lvl_ids[l], t.children[par].reshape(-1))
+    centre = 3 ** ndim // 2
+    assert np.array_equal(t.neighbor_mat[1:, centre], np.arange(1, t.highest_id + 1))
+
+
+def test_bc_table_matches_face_coordinates():
+    t = T.uniform_tree(3, 8, 8, 2)
+    bc = W.bc_table(t, lambda nb, c: (W.AF_BC_DIRICHLET, c[..., 0] + 10 * c[..., 1] + 100 * c[..., 2]))
+    # box 2 (first child, low corner), face lowx (nb=1): x = 0, y,z at cell centres, y fastest
+    row = [q for q in range(len(bc.ids)) if bc.ids[q] == 2 and bc.nbs[q] == 1][0]
+    dr = t.dr[2, 0]
+    expect = np.array([[10 * (a + 0.5) * dr + 100 * (b + 0.5) * dr for a in range(8)] for b in range(8)]).reshape(-1)
+    assert np.allclose(bc.vals[row], expect)
+
+
+def test_cell_update_count_matches_definition():
+    import bench
+    t = T.uniform_tree(3, 16, 16, 5)
+    assert bench.cell_updates_vcycle(t) == 4 * 16 ** 3 * (8 + 64 + 512 + 4096)

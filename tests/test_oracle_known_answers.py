@@ -1,0 +1,175 @@
+"""CPU: pins the oracle against the known answers the reference's own tests / examples hold for this
+path.  The reference ships no numeric golden vectors for the multigrid."""
+import numpy as np
+import pytest
+
+from afivo_streamer_b200 import tree as T
+from afivo_streamer_b200 import workloads as W
+from oracle.oracle import I_PHI, I_RHS, I_TMP, MG_CYCLE_DOWN, Oracle
+
+from util import all_ids
+
+
+def test_box_count_five_full_levels():
+    """afivo/tests/answers/test_refinement_3d: 4681 == (1 - 8^5) / (1 - 8)."""
+    t = T.uniform_tree(3, 8, 8, 5)
+    assert t.n_boxes == 4681 == (1 - 8 ** 5) // (1 - 8)
+    assert [len(a) for a in t.lvl_ids] == [1, 8, 64, 512, 4096]
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_zero_field_neumann_keeps_zero_ghosts(ndim):
+    """afivo/tests/test_ghostcell.f90:14-30,54-76: all-zero field, Neumann-0, corner-refined 4-level tree."""
+    t = T.corner_refined_tree(ndim, 8, 8, 4)
+    o = Oracle(t)
+    o.set_bc(W.bc_neumann_zero(t))
+    with pytest.raises(RuntimeError, match="code 4"):
+        o.mg_init()  # all-Neumann Poisson: singular coarse operator; ghost cells do not need it
+    for lvl in range(1, t.highest_lvl + 1):
+        o.gc_lvl(lvl, I_PHI, True)
+    assert np.all(o.get_cc(I_PHI, all_ids(t)) == 0.0)
+
+
+def _linear(c):
+    return 0.5 + c[..., 0] * 1.25 - 0.75 * c[..., 1] + (0.3 * c[..., 2] if c.shape[-1] == 3 else 0.0)
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_ghost_cells_exact_for_linear_field(ndim):
+    """afivo/examples/check_ghostcells.f90 (test_gradient): ghost cells of a linear field are exact,
+    for same-level copies, refinement boundaries (mg_sides_rb), Dirichlet faces, edges and corners."""
+    t = T.corner_refined_tree(ndim, 8, 8, 4)
+    o = Oracle(t)
+    o.set_bc(W.bc_dirichlet_function(t, _linear))
+    o.mg_init()
+    ids = all_ids(t)
+    exact = _linear(W.cell_centres(t, ids, ghosts=True))
+    data = np.zeros_like(exact)
+    data[W.interior(t)] = exact[W.interior(t)]
+    o.set_cc(I_PHI, ids, data)
+    for lvl in range(1, t.highest_lvl + 1):
+        o.gc_lvl(lvl, I_PHI, True)
+    got = o.get_cc(I_PHI, ids).reshape(exact.shape)
+    assert np.max(np.abs(got - exact)) < 1e-13
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_prolongation_exact_for_linear_field(ndim):
+    """afivo/examples/check_prolongation.f90: (bi/tri)linear prolongation reproduces a linear field."""
+    t = T.uniform_tree(ndim, 8, 8, 3)
+    o = Oracle(t)
+    o.set_bc(W.bc_dirichlet_function(t, _linear))
+    o.mg_init()
+    ids = all_ids(t)
+    exact = _linear(W.cell_centres(t, ids, ghosts=True))
+    phi = exact.copy()
+    phi[t.lvl[ids] > 1] = 0.0          # children start from zero, tmp = 0: correction = parent phi
+    o.set_cc(I_PHI, ids, phi)
+    o.correct_children(1)
+    got = o.get_cc(I_PHI, ids).reshape(exact.shape)
+    lvl2 = t.lvl[ids] == 2
+    assert np.max(np.abs(got[lvl2][W.interior(t)] - exact[lvl2][W.interior(t)])) < 1e-13
+
+
+def test_restriction_is_the_2d_average():
+    """af_restrict_box (m_af_restrict.f90:120-133)."""
+    t = T.uniform_tree(3, 8, 8, 2)
+    o = Oracle(t)
+    o.set_bc(W.bc_dirichlet_zero(t))
+    o.mg_init()
+    ids, rhs = W.random_rhs_on_leaves(t)
+    o.set_cc(I_RHS, ids, rhs)
+    o.init_phi_rhs()
+    parent = o.get_cc(I_RHS, np.array([1], np.int32)).reshape(10, 10, 10)[1:9, 1:9, 1:9]
+    fine = np.zeros((16, 16, 16))
+    for q, cid in enumerate(t.children[1]):
+        ox, oy, oz = [(t.ix[cid, d] - 1) * 8 for d in range(3)]
+        fine[oz:oz + 8, oy:oy + 8, ox:ox + 8] = rhs[list(ids).index(cid)][1:9, 1:9, 1:9]
+    avg = fine.reshape(8, 2, 8, 2, 8, 2).mean(axis=(1, 3, 5))
+    assert np.max(np.abs(avg - parent)) < 1e-15
+
+
+def test_poisson_basic_gaussians_converge():
+    """afivo/examples/poisson_basic.f90:40-63,104-119,143-165: two Gaussians, Dirichlet = analytic
+    solution, refine where dr^2 |rhs| > 1e-3; FMG cycles: residual falls, error plateaus at the
+    discretisation level."""
+    g = W.Gaussians([[0.1, 0.1, 0.1], [0.75, 0.75, 0.75]], 0.04)
+    nc = 8
+
+    def refine(l, ixs, ctr):
+        dr = 1.0 / (nc * 2 ** (l - 1))
+        # afivo/examples/poisson_basic.f90:143-165: refine if dr^2 * max |rhs| over the box cells > 1e-3
+        off = (np.arange(nc) - (nc - 1) / 2) * dr
+        gz, gy, gx = np.meshgrid(off, off, off, indexing="ij")
+        pts = ctr[:, None, :] + np.stack([gx, gy, gz], axis=-1).reshape(1, -1, 3)
+        m = np.max(np.abs(g.laplacian(pts)), axis=1)
+        return dr * dr * m > 1e-3
+
+    t = T.build_tree(3, nc, [nc] * 3, 5, refine)
+    assert t.highest_lvl >= 4
+    o = Oracle(t)
+    o.set_bc(W.bc_dirichlet_function(t, g.value))
+    o.mg_init()
+    leaves = np.concatenate([t.leaves(l) for l in range(1, t.highest_lvl + 1)]).astype(np.int32)
+    ctr = W.cell_centres(t, leaves, ghosts=True)
+    rhs = g.laplacian(ctr)
+    o.set_cc(I_RHS, leaves, rhs)
+    res, err = [], []
+    for it in range(6):
+        o.fas_fmg(True, it > 0)
+        res.append(o.maxabs(I_TMP))
+        phi = o.get_cc(I_PHI, leaves).reshape(ctr.shape[:-1])
+        err.append(np.max(np.abs(phi - g.value(ctr))[W.interior(t)]))
+    assert all(res[i + 1] < 0.5 * res[i] for i in range(4)), res
+    assert res[-1] < 1e-5 * res[0]
+    assert err[-1] < 2e-2 and abs(err[-1] - err[-2]) < 1e-3 * err[-1], err  # plateau
+
+
+def test_helmholtz_lambda_enters_the_centre_coefficient():
+    """mg_box_lpl_stencil (m_af_multigrid.f90:1262): c(1) = -sum(c(2:)) - lambda."""
+    t = T.uniform_tree(3, 8, 8, 2)
+    o = Oracle(t, helmholtz_lambda=1.0e3)
+    o.set_bc(W.bc_helmholtz(t))
+    o.mg_init()
+    stype, c, f, cyl = o.op_stencil(2)
+    idr2 = 1.0 / t.dr[2] ** 2
+    assert stype == 1 and f is None and not cyl
+    assert np.allclose(c[1:], np.repeat(idr2, 2)) and c[0] == -np.sum(c[1:]) - 1.0e3
+
+
+def test_results_do_not_depend_on_thread_count():
+    """the cycle is a deterministic dataflow, independent of box order / threads."""
+    t = T.corner_refined_tree(3, 8, 8, 3)
+    out = []
+    for nthreads in (1, 4):
+        o = Oracle(t)
+        o.set_num_threads(nthreads)
+        o.set_bc(W.bc_field_homogeneous(t, 1.0))
+        o.mg_init()
+        ids, rhs = W.random_rhs_on_leaves(t)
+        o.set_cc(I_RHS, ids, rhs)
+        o.fas_fmg(True, False)
+        o.fas_vcycle(True)
+        out.append(o.get_cc(I_PHI, all_ids(t)))
+    o.set_num_threads(o.num_threads())
+    assert np.array_equal(out[0], out[1])
+
+
+def test_gsrb_colour_convention():
+    """stencil_gsrb_357 (m_af_stencil.f90:962): half-sweep n updates cells with (i+j+k+n) even."""
+    t = T.uniform_tree(3, 8, 8, 1)
+    o = Oracle(t)
+    o.set_bc(W.bc_dirichlet_zero(t))
+    o.mg_init()
+    ids = all_ids(t)
+    rng = np.random.default_rng(1)
+    phi = rng.normal(size=(1, 10, 10, 10))
+    o.set_cc(I_PHI, ids, phi)
+    o.set_cc(I_RHS, ids, rng.normal(size=(1, 10, 10, 10)))
+    o.box_gsrb_lvl(1, 1)
+    new = o.get_cc(I_PHI, ids).reshape(10, 10, 10)
+    k, j, i = np.indices((10, 10, 10))
+    changed = new != phi[0]
+    inner = (i >= 1) & (i <= 8) & (j >= 1) & (j <= 8) & (k >= 1) & (k <= 8)
+    assert np.all(changed[inner & ((i + j + k) % 2 == 1)])
+    assert not np.any(changed[~(inner & ((i + j + k) % 2 == 1))])

@@ -1,0 +1,73 @@
+"""Summarise an .ncu-rep (raw page) and a launch-list csv into profiles/*.md / *.csv."""
+import csv
+import subprocess
+import sys
+from collections import defaultdict
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__inst_executed.sum", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
+
+
+def to_bytes(val, unit):
+    m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    return float(val) * m.get(unit, 1)
+
+
+def rep_summary(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    out = []
+    for r in data:
+        name = r[col["Kernel Name"]].split("(")[0].replace("void ", "")
+        d = {"kernel": name}
+        for w in WANT:
+            if w in col:
+                d[w] = (r[col[w]], units[col[w]])
+        out.append(d)
+    return out
+
+
+def launches_summary(path):
+    rows = list(csv.reader(open(path, errors="ignore")))
+    start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    hdr = rows[start]
+    col = {h: i for i, h in enumerate(hdr)}
+    agg = defaultdict(lambda: [0, 0.0])
+    for r in rows[start + 1:]:
+        if len(r) <= col["Metric Value"] or r[col["Metric Name"]] != "gpu__time_duration.sum":
+            continue
+        name = r[col["Kernel Name"]].split("(")[0].replace("void ", "")
+        grid = r[col["Grid Size"]] if "Grid Size" in col else ""
+        v = float(r[col["Metric Value"]].replace(",", ""))
+        unit = r[col["Metric Unit"]]
+        v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(unit, 1.0)
+        agg[(name, grid)][0] += 1
+        agg[(name, grid)][1] += v
+    return agg
+
+
+if __name__ == "__main__":
+    kind, path = sys.argv[1], sys.argv[2]
+    if kind == "rep":
+        for d in rep_summary(path):
+            t, tu = d["gpu__time_duration.sum"]
+            rd = to_bytes(*d["dram__bytes_read.sum"])
+            wr = to_bytes(*d["dram__bytes_write.sum"])
+            us = float(t) * {"ns": 1e-3, "us": 1, "ms": 1e3}.get(tu, 1)
+            print(f"| {d['kernel']} | grid {d['launch__grid_size'][0]} x {d['launch__block_size'][0]} | {us:.1f} us | "
+                  f"dram R {rd / 1e6:.1f} MB W {wr / 1e6:.1f} MB ({(rd + wr) / us / 1e3:.0f} GB/s) | "
+                  f"regs {d['launch__registers_per_thread'][0]} | warps {float(d['sm__warps_active.avg.pct_of_peak_sustained_active'][0]):.0f}% | "
+                  f"dram {float(d['gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'][0]):.0f}% | sm {float(d['sm__throughput.avg.pct_of_peak_sustained_elapsed'][0]):.0f}% |")
+    else:
+        agg = launches_summary(path)
+        total = sum(v[1] for v in agg.values())
+        print("| kernel | grid | launches | total us | share |")
+        print("|---|---|---|---|---|")
+        for (name, grid), (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f"| {name} | {grid} | {n} | {us:.1f} | {100 * us / total:.1f}% |")
+        print(f"| total | | {sum(v[0] for v in agg.values())} | {total:.1f} | |")

@@ -16,14 +16,12 @@ mg = M.mg_t(sides_bc=bc)
 M.mg_init(tree, mg)
 mg.set_cc(M.I_RHS, ids, rhs)
 mg.set_profiling(True)  # no graphs: plain launches
-M.mg_fas_fmg(tree, mg, True, False)
 L = tree.highest_lvl
 for _ in range(reps):
     mg.gsrb_halfsweep(L, 1)
     mg.gsrb_halfsweep(L, 2)
     mg.update_coarse(L, True)
-    mg.correct_children(L - 1)
-    mg.gc_lvl(L, M.I_PHI, True)
+    mg.correct_children_gc(L - 1)
     mg.residual_lvl(L)
 print("done", M.af_tree_maxabs_cc(tree, mg, M.I_TMP))
 M.mg_destroy(mg)
