@@ -13,8 +13,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libafmg.so")
 
 AFMG_OK = 0
+AFMG_MAX_RANKS = 8
+AFMG_COMM_BLOB_BYTES = 192
 ERR_NAMES = {-1: "AFMG_ERR_ARG", -2: "AFMG_ERR_CUDA", -3: "AFMG_ERR_UNSUPPORTED", -4: "AFMG_ERR_STATE",
-             -5: "AFMG_ERR_SINGULAR", -6: "AFMG_ERR_NCCL"}
+             -5: "AFMG_ERR_SINGULAR", -6: "AFMG_ERR_COMM"}
 
 
 class AfmgError(RuntimeError):
@@ -88,9 +90,11 @@ SYMBOLS = {
     "afmg_layout_offset": (C.c_int32, [_I, _I, _I, _I, _I]),
     "afmg_layout_box_len": (C.c_int32, [_I, _I]),
     "afmg_slot_of_box": (C.c_int32, [_H, _I]),
-    "afmg_comm_unique_id": (C.c_int, [C.c_char_p]),
-    "afmg_comm_init": (C.c_int, [_H, _I, _I, C.c_char_p]),
+    "afmg_comm_init": (C.c_int, [_H, _I, _I]),
+    "afmg_comm_export": (C.c_int, [_H, C.c_void_p]),
+    "afmg_comm_connect": (C.c_int, [_H, C.c_void_p]),
     "afmg_owner_of_box": (C.c_int32, [_H, _I]),
+    "afmg_partition": (C.c_int, [_I, _I, _IP, _IP]),
 }
 
 _lib = None

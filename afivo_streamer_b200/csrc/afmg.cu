@@ -81,6 +81,20 @@ struct afmg_handle {
   double *d_b2r = nullptr, *d_Q[3] = {nullptr, nullptr, nullptr}, *d_inveig = nullptr, *d_v0 = nullptr, *d_v1 = nullptr;
   int* d_cs_bix = nullptr;
 
+  // ---- multi-GPU (one process per GPU; peers' arrays mapped through CUDA IPC)
+  int nranks = 1, me = 0;
+  bool connected = false;
+  std::vector<int> cut;  // [(L+2) * (nranks+1)]: slots [cut[l][r], cut[l][r+1]) of level l belong to rank r
+  std::vector<int> rb_cut;  // same for the refinement-boundary face list (rb rows of level l)
+  std::vector<unsigned char> h_owner;
+  unsigned char* d_owner = nullptr;
+  CommBlock* d_comm = nullptr;
+  CommPeers peers{};
+  char* d_slab = nullptr;  // phi | rhs | tmp | box sums, one allocation so that one IPC handle covers it
+  size_t slab_bytes = 0, slab_var_stride = 0;
+  char* peer_slab[AFMG_MAX_RANKS] = {};
+  unsigned long long barrier_timeout_ns = 30ull * 1000000000ull;
+
   // ---- state
   bool resid_fresh = false;
   std::map<std::tuple<int, int, int>, Graph> graphs;
@@ -214,12 +228,23 @@ void prof_resolve(afmg_handle* h) {
     default: break;                                                     \
   }
 
-template <int NC>
-struct GsrbCfg {
-  static constexpr int BPC = (NC == 16) ? 2 : (NC == 8 ? 8 : 16);
-};
-
 inline int nlev(const afmg_handle* h, int l) { return h->lvl_off[l + 1] - h->lvl_off[l]; }
+
+// slots of level l this rank computes (all of them on a single GPU)
+struct Range {
+  int s0, n;
+};
+inline Range own(const afmg_handle* h, int l) {
+  const int* c = &h->cut[(size_t)l * (h->nranks + 1)];
+  return {c[h->me], c[h->me + 1] - c[h->me]};
+}
+
+// Cross-GPU barrier between dependent kernels (no-op on one GPU, where stream order suffices)
+void enq_barrier(afmg_handle* h) {
+  if (h->nranks == 1) return;
+  Launch L_(h, "barrier");
+  k_barrier<<<1, 32, 0, h->stream>>>(h->d_comm, h->peers, h->nranks, h->me, h->barrier_timeout_ns);
+}
 
 // one half-sweep + side ghost fill on level l
 template <int NC>
@@ -235,52 +260,54 @@ void set_max_smem(K kernel, size_t smem) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
+// Every enq_* below works on the slots of a level this rank owns and ends with a cross-GPU barrier
+// when its results are read, or its inputs overwritten, by kernels of other ranks.
 void enq_gsrb(afmg_handle* h, int l, int redblack) {
-  const int n = nlev(h, l);
-  if (n == 0) return;
-  Launch L_(h, "gsrb", l);
-  static const int variant = getenv("AFMG_GSRB_V1") ? 1 : 2;
-  DISPATCH_NC(h, NC, {
-    if (variant == 1) {
-      constexpr int BPC = GsrbCfg<NC>::BPC;
-      const int threads = BPC * NC * NC / 2;
-      const size_t smem = (size_t)BPC * Lay3<NC>::COL * sizeof(double);
-      k_gsrb<NC, BPC><<<(n + BPC - 1) / BPC, threads, smem, h->stream>>>(h->cx, h->lvl_off[l], n, redblack & 1, l);
-    } else {
+  const Range r = own(h, l);
+  if (r.n > 0) {
+    Launch L_(h, "gsrb", l);
+    DISPATCH_NC(h, NC, {
       using G = Gsrb2Cfg<NC>;
       constexpr int threads = G::BPC * G::KS * NC * NC / 2;
       const size_t smem = (size_t)G::BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double);
       auto kern = k_gsrb2<NC, G::BPC, G::KS, G::MINB>;
-      kern<<<(n + G::BPC - 1) / G::BPC, threads, smem, h->stream>>>(h->cx, h->lvl_off[l], n, redblack & 1, l);
-    }
-  });
+      kern<<<(r.n + G::BPC - 1) / G::BPC, threads, smem, h->stream>>>(h->cx, r.s0, r.n, redblack & 1, l);
+    });
+  }
+  enq_barrier(h);
 }
 
+// reads the (frozen) coarse level, writes this rank's rule rows: no barrier needed afterwards
 void enq_rb_prepare(afmg_handle* h, int l) {
-  const int n = h->rb_lvl_off[l + 1] - h->rb_lvl_off[l];
+  const int* c = &h->rb_cut[(size_t)l * (h->nranks + 1)];
+  const int r0 = c[h->me], n = c[h->me + 1] - c[h->me];
   if (n == 0) return;
   Launch L_(h, "rb_prepare", l);
-  DISPATCH_NC(h, NC, { k_rb_prepare<NC><<<n, 128, 0, h->stream>>>(h->cx, h->rb_lvl_off[l], n, V_PHI); });
+  DISPATCH_NC(h, NC, { k_rb_prepare<NC><<<n, 128, 0, h->stream>>>(h->cx, r0, n, V_PHI); });
 }
 
 // af_gc_lvl (+ parent update when mode != 0)
 void enq_gc(afmg_handle* h, int l, int var, int corners, int mode) {
-  const int n = nlev(h, l);
-  if (n == 0) return;
-  Launch L_(h, mode ? "gc_parent" : "gc", l);
-  DISPATCH_NC(h, NC, {
-    if (var == V_PHI && mode != 0)
-      k_gc2<NC><<<n, 256, (size_t)2 * Lay3<NC>::COL * sizeof(double), h->stream>>>(h->cx, h->lvl_off[l], n, corners, mode);
-    else
-      k_gc<NC><<<n, 256, 0, h->stream>>>(h->cx, h->lvl_off[l], n, var, corners, mode);
-  });
+  const Range r = own(h, l);
+  if (r.n > 0) {
+    Launch L_(h, mode ? "gc_parent" : "gc", l);
+    DISPATCH_NC(h, NC, {
+      if (var == V_PHI && mode != 0)
+        k_gc2<NC><<<r.n, 256, (size_t)2 * Lay3<NC>::COL * sizeof(double), h->stream>>>(h->cx, r.s0, r.n, corners, mode);
+      else
+        k_gc<NC><<<r.n, 256, 0, h->stream>>>(h->cx, r.s0, r.n, var, corners, mode);
+    });
+  }
+  enq_barrier(h);
 }
 
 void enq_edges_corners(afmg_handle* h, int l) {
-  const int n = nlev(h, l);
-  if (n == 0) return;
-  Launch L_(h, "edges_corners", l);
-  DISPATCH_NC(h, NC, { k_edges_corners<NC><<<n, 64, 0, h->stream>>>(h->cx, h->lvl_off[l], n, V_PHI); });
+  const Range r = own(h, l);
+  if (r.n > 0) {
+    Launch L_(h, "edges_corners", l);
+    DISPATCH_NC(h, NC, { k_edges_corners<NC><<<r.n, 64, 0, h->stream>>>(h->cx, r.s0, r.n, V_PHI); });
+  }
+  enq_barrier(h);
 }
 
 template <int NC>
@@ -291,32 +318,39 @@ struct OpCfg {
 };
 
 void enq_restrict(afmg_handle* h, int l, int keep_res) {
-  const int n = nlev(h, l);
-  if (n == 0) return;
-  Launch L_(h, "restrict", l);
-  DISPATCH_NC(h, NC, {
-    constexpr int KS = OpCfg<NC>::KS;
-    k_resid3<NC, KS, 1, OpCfg<NC>::RES_MINB><<<n, KS * NC * NC / 2, OpCfg<NC>::TILE, h->stream>>>(
-        h->cx, h->lvl_off[l], n, nullptr, keep_res);
-  });
+  const Range r = own(h, l);
+  if (r.n > 0) {
+    Launch L_(h, "restrict", l);
+    DISPATCH_NC(h, NC, {
+      constexpr int KS = OpCfg<NC>::KS;
+      k_resid3<NC, KS, 1, OpCfg<NC>::RES_MINB><<<r.n, KS * NC * NC / 2, OpCfg<NC>::TILE, h->stream>>>(
+          h->cx, r.s0, r.n, nullptr, keep_res);
+    });
+  }
+  enq_barrier(h);
 }
 
 // correct_children; with push the side ghost cells of the children are filled as well (the caller
-// must have run enq_rb_prepare(lp + 1) before and runs enq_edges_corners(lp + 1) after)
+// must have run enq_rb_prepare(lp + 1) before and runs enq_edges_corners(lp + 1) after).  One CTA per
+// child box (all boxes of level lp + 1 have a parent on level lp).
 void enq_correct(afmg_handle* h, int lp, bool store_corr, bool push) {
-  const int n = nlev(h, lp);
-  if (n == 0 || h->npar[lp] == 0) return;
-  {
+  if (lp >= h->L || h->npar[lp] == 0) return;
+  const Range rc = own(h, lp + 1);
+  if (rc.n > 0) {
     Launch L_(h, "correct", lp);
     DISPATCH_NC(h, NC, {
       constexpr int W = NC / 2 + 2;
       const size_t smem = (size_t)(2 * Lay3<NC>::NI + W * W * W) * sizeof(double);
-      k_correct3<NC><<<n * 8, 256, smem, h->stream>>>(h->cx, h->lvl_off[lp], n, push ? 1 : 0);
+      k_correct3<NC><<<rc.n, 256, smem, h->stream>>>(h->cx, rc.s0, rc.n, push ? 1 : 0);
     });
   }
+  enq_barrier(h);  // all children have read the old tmp of their parents
   if (store_corr) {
-    Launch L_(h, "store_corr", lp);
-    DISPATCH_NC(h, NC, { k_store_corr<NC><<<n, 256, 0, h->stream>>>(h->cx, h->lvl_off[lp], n); });
+    const Range rp = own(h, lp);
+    if (rp.n > 0) {
+      Launch L_(h, "store_corr", lp);
+      DISPATCH_NC(h, NC, { k_store_corr<NC><<<rp.n, 256, 0, h->stream>>>(h->cx, rp.s0, rp.n); });
+    }
   }
 }
 
@@ -327,15 +361,37 @@ void enq_correct_gc(afmg_handle* h, int lp, bool store_corr) {
   enq_edges_corners(h, lp + 1);
 }
 
+// max over ranks of scal[idx] -> scal[4 + idx] on every rank
+void enq_allmax(afmg_handle* h, int idx) {
+  if (h->nranks == 1) return;
+  enq_barrier(h);
+  {
+    Launch L_(h, "allmax");
+    k_allmax<<<1, 1, 0, h->stream>>>(h->d_comm, h->peers, h->nranks, idx);
+  }
+  enq_barrier(h);  // nobody resets scal[idx] while a peer still reads it
+}
+
+// residual on levels l_lo..l_hi: purely local (reads own phi/rhs, writes own tmp)
 void enq_residual(afmg_handle* h, int l_lo, int l_hi, bool with_max) {
-  const int s0 = h->lvl_off[l_lo], n = h->lvl_off[l_hi + 1] - s0;
-  if (n == 0) return;
-  Launch L_(h, "residual");
-  DISPATCH_NC(h, NC, {
-    constexpr int KS = OpCfg<NC>::KS;
-    k_resid3<NC, KS, 0, OpCfg<NC>::RES_MINB><<<n, KS * NC * NC / 2, OpCfg<NC>::TILE, h->stream>>>(
-        h->cx, s0, n, with_max ? h->d_scal : nullptr, 0);
-  });
+  auto launch = [&](int s0, int n) {
+    if (n == 0) return;
+    Launch L_(h, "residual");
+    DISPATCH_NC(h, NC, {
+      constexpr int KS = OpCfg<NC>::KS;
+      k_resid3<NC, KS, 0, OpCfg<NC>::RES_MINB><<<n, KS * NC * NC / 2, OpCfg<NC>::TILE, h->stream>>>(
+          h->cx, s0, n, with_max ? h->d_scal : nullptr, 0);
+    });
+  };
+  if (h->nranks == 1) {
+    launch(h->lvl_off[l_lo], h->lvl_off[l_hi + 1] - h->lvl_off[l_lo]);
+  } else {
+    for (int l = l_lo; l <= l_hi; ++l) {
+      const Range r = own(h, l);
+      launch(r.s0, r.n);
+    }
+    if (with_max) enq_allmax(h, 0);
+  }
 }
 
 // opt in to large dynamic shared memory / max carveout once per process (not a stream operation, but
@@ -344,7 +400,6 @@ void configure_kernels(afmg_handle* h) {
   DISPATCH_NC(h, NC, {
     using G = Gsrb2Cfg<NC>;
     set_max_smem(k_gsrb2<NC, G::BPC, G::KS, G::MINB>, (size_t)G::BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double));
-    set_max_smem(k_gsrb<NC, GsrbCfg<NC>::BPC>, (size_t)GsrbCfg<NC>::BPC * Lay3<NC>::COL * sizeof(double));
     set_max_smem(k_resid3<NC, OpCfg<NC>::KS, 0, OpCfg<NC>::RES_MINB>, OpCfg<NC>::TILE);
     set_max_smem(k_resid3<NC, OpCfg<NC>::KS, 1, OpCfg<NC>::RES_MINB>, OpCfg<NC>::TILE);
     set_max_smem(k_gc2<NC>, OpCfg<NC>::TILE);
@@ -353,16 +408,21 @@ void configure_kernels(afmg_handle* h) {
 }
 
 void enq_copy_lvl(afmg_handle* h, int l, int dst, int src) {
-  const size_t n = (size_t)nlev(h, l) * h->box_len;
+  const Range r = own(h, l);
+  const size_t n = (size_t)r.n * h->box_len;
   if (n == 0) return;
   Launch L_(h, "copy", l);
-  const size_t off = (size_t)h->lvl_off[l] * h->box_len;
+  const size_t off = (size_t)r.s0 * h->box_len;
   const int blocks = (int)std::min<size_t>((n + 1023) / 1024, 148 * 8);
   k_copy<<<blocks, 256, 0, h->stream>>>(h->d_cc[dst] + off, h->d_cc[src] + off, n);
 }
 
 // solve_coarse_grid (m_af_multigrid.f90:266-291)
 void enq_coarse(afmg_handle* h) {
+  if (h->me != 0) {  // level 1 lives on rank 0; the others only keep the barrier count in step
+    enq_barrier(h);
+    return;
+  }
   const int nbox1 = nlev(h, 1);
   const int ntot = h->cs.nx[0] * h->cs.nx[1] * h->cs.nx[2];
   const int blocks = (ntot + 127) / 128;
@@ -447,12 +507,22 @@ __global__ void k_weighted_sum(const double* boxsum, const int* child0, const in
   if (threadIdx.x == 0) *out = sh[0] * inv_volume;
 }
 
+// per-box interior sums of this rank's boxes, written into the tables of all ranks
+void enq_box_sums(afmg_handle* h, int var) {
+  for (int l = 1; l <= h->L; ++l) {
+    const Range r = (h->nranks == 1) ? Range{0, h->nslots} : own(h, l);
+    if (r.n > 0) {
+      Launch L_(h, "sum");
+      DISPATCH_NC(h, NC, { k_box_sums<NC><<<r.n, 128, 0, h->stream>>>(h->cx, r.s0, r.n, var, h->d_boxsum); });
+    }
+    if (h->nranks == 1) break;
+  }
+  enq_barrier(h);
+}
+
 void enq_subtract_mean(afmg_handle* h, int max_lvl) {
   // af_tree_sum_cc over all leaves / af_total_volume, then phi -= mean on levels 1..max_lvl (full boxes)
-  {
-    Launch L_(h, "sum");
-    DISPATCH_NC(h, NC, { k_box_sums<NC><<<h->nslots, 128, 0, h->stream>>>(h->cx, 0, h->nslots, V_PHI, h->d_boxsum); });
-  }
+  enq_box_sums(h, V_PHI);
   double vol = (double)nlev(h, 1);
   for (int d = 0; d < 3; ++d) vol *= h->o.n_cell * h->o.dr_base[d];
   {
@@ -460,24 +530,32 @@ void enq_subtract_mean(afmg_handle* h, int max_lvl) {
     k_weighted_sum<<<1, 256, 0, h->stream>>>(h->d_boxsum, h->d_child0, h->d_lvl, h->d_coef + 8 * (h->L + 1), h->nslots,
                                             1.0 / vol, (double*)(h->d_scal + 2));
   }
-  {
-    Launch L_(h, "sub_mean");
-    const size_t n = (size_t)h->lvl_off[max_lvl + 1] * h->box_len;
-    const int blocks = (int)std::min<size_t>((n + 1023) / 1024, 148 * 8);
-    k_sub_scalar<<<blocks, 256, 0, h->stream>>>(h->d_cc[V_PHI], (const double*)(h->d_scal + 2), n);
+  for (int l = 1; l <= max_lvl; ++l) {
+    const Range r = (h->nranks == 1) ? Range{0, h->lvl_off[max_lvl + 1]} : own(h, l);
+    const size_t n = (size_t)r.n * h->box_len;
+    if (n > 0) {
+      Launch L_(h, "sub_mean");
+      const int blocks = (int)std::min<size_t>((n + 1023) / 1024, 148 * 8);
+      k_sub_scalar<<<blocks, 256, 0, h->stream>>>(h->d_cc[V_PHI] + (size_t)r.s0 * h->box_len,
+                                                  (const double*)(h->d_scal + 2), n);
+    }
+    if (h->nranks == 1) break;
   }
+  enq_barrier(h);
 }
 
 // init_phi_rhs (m_af_multigrid.f90:779-799)
 void enq_init_phi_rhs(afmg_handle* h) {
   for (int l = h->L; l >= 2; --l) {
-    const int n = nlev(h, l);
-    if (n == 0) continue;
-    Launch L_(h, "init_phi_rhs", l);
-    DISPATCH_NC(h, NC, {
-      constexpr int T = (NC == 16) ? 256 : (NC == 8 ? 64 : 32);
-      k_restrict_var<NC><<<n, T, 0, h->stream>>>(h->cx, h->lvl_off[l], n, V_RHS, 1);
-    });
+    const Range r = own(h, l);
+    if (r.n > 0) {
+      Launch L_(h, "init_phi_rhs", l);
+      DISPATCH_NC(h, NC, {
+        constexpr int T = (NC == 16) ? 256 : (NC == 8 ? 64 : 32);
+        k_restrict_var<NC><<<r.n, T, 0, h->stream>>>(h->cx, r.s0, r.n, V_RHS, 1);
+      });
+    }
+    enq_barrier(h);
   }
 }
 
@@ -536,6 +614,15 @@ int build_constant_stencils(afmg_handle* h) {
   h->cx.pcoef = h->d_pcoef;
   h->cx.pshape = pshape;
   return AFMG_OK;
+}
+
+// unmap the peers' slabs (CUDA IPC)
+void close_peers(afmg_handle* h) {
+  for (int r = 0; r < AFMG_MAX_RANKS; ++r) {
+    if (r != h->me && h->peer_slab[r]) cudaIpcCloseMemHandle(h->peer_slab[r]);
+    h->peer_slab[r] = nullptr;
+  }
+  h->connected = (h->nranks == 1);
 }
 
 void drop_graphs(afmg_handle* h) {
@@ -663,6 +750,8 @@ int ensure_ready(afmg_handle* h) {
     if (!h->bc_set[r])
       return h->fail(AFMG_ERR_STATE, "boundary condition not set for box %d face %d (call afmg_set_bc)",
                      h->slot2id[h->bc_slot[r]], h->bc_face[r] + 1);
+  if (!h->connected)
+    return h->fail(AFMG_ERR_STATE, "multi-GPU handle: call afmg_comm_export / afmg_comm_connect after afmg_set_tree");
   if (!h->cs_ready) {
     int rc = coarse_setup(h);
     if (rc) return rc;
@@ -728,6 +817,11 @@ int finish_op(afmg_handle* h) {
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   if (h->profiling) prof_resolve(h);
+  if (h->nranks > 1) {
+    unsigned long long err = 0;
+    CK(cudaMemcpy(&err, &h->d_comm->err, sizeof err, cudaMemcpyDeviceToHost));
+    if (err) return h->fail(AFMG_ERR_COMM, "a cross-GPU barrier timed out (a peer rank is missing or out of step)");
+  }
   return AFMG_OK;
 }
 
@@ -779,8 +873,14 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_scal, 8 * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMemset(h->d_scal, 0, 8 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_comm, sizeof(CommBlock));
+  if (e == cudaSuccess) e = cudaMemset(h->d_comm, 0, sizeof(CommBlock));
+  if (e == cudaSuccess) h->d_scal = h->d_comm->scal;  // address arithmetic only
+  h->peers.p[0] = h->d_comm;
+  if (const char* env = getenv("AFMG_BARRIER_TIMEOUT_S")) {
+    const double sec = atof(env);
+    if (sec > 0) h->barrier_timeout_ns = (unsigned long long)(sec * 1e9);
+  }
   if (e != cudaSuccess) {
     g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e);
     delete h;
@@ -798,14 +898,16 @@ int afmg_destroy(afmg_handle* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   drop_graphs(h);
-  for (auto& p : h->d_cc) cudaFree(p);
+  close_peers(h);
+  cudaFree(h->d_slab);
+  cudaFree(h->d_owner);
   int* ip[] = {h->d_nbr, h->d_aux, h->d_nmat, h->d_parent, h->d_child0, h->d_coff, h->d_lvl, h->d_rb_slot,
                h->d_rb_face, h->d_stage_slots, h->d_cs_bix};
   for (auto p : ip) cudaFree(p);
-  double* dp[] = {h->d_coef, h->d_rule_c, h->d_rule_B, h->d_pcoef, h->d_boxsum, h->d_stage, h->d_b2r, h->d_Q[0],
+  double* dp[] = {h->d_coef, h->d_rule_c, h->d_rule_B, h->d_pcoef, h->d_stage, h->d_b2r, h->d_Q[0],
                   h->d_Q[1], h->d_Q[2], h->d_inveig, h->d_v0, h->d_v1};
   for (auto p : dp) cudaFree(p);
-  cudaFree(h->d_scal);
+  cudaFree(h->d_comm);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);
@@ -956,18 +1058,57 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
   if ((rc = dev_upload(h, &h->d_rule_c, rule_c))) return rc;
   std::vector<double> rule_B((size_t)std::max(nrules, 1) * h->nc2, 0.0);
   if ((rc = dev_upload(h, &h->d_rule_B, rule_B))) return rc;
-  for (int v = 0; v < 3; ++v) {
-    if (h->d_cc[v]) cudaFree(h->d_cc[v]);
-    h->d_cc[v] = nullptr;
-    const size_t bytes = (size_t)total * h->box_len * sizeof(double);
-    CK(cudaMalloc((void**)&h->d_cc[v], bytes));
-    CK(cudaMemset(h->d_cc[v], 0, bytes));
+  // one slab per rank: phi | rhs | tmp | box sums (a single CUDA IPC handle covers all of it)
+  close_peers(h);
+  if (h->d_slab) cudaFree(h->d_slab);
+  h->d_slab = nullptr;
+  h->slab_var_stride = (((size_t)total * h->box_len * sizeof(double)) + 255) / 256 * 256;
+  h->slab_bytes = 3 * h->slab_var_stride + (size_t)total * sizeof(double);
+  CK(cudaMalloc((void**)&h->d_slab, h->slab_bytes));
+  CK(cudaMemset(h->d_slab, 0, h->slab_bytes));
+  for (int v = 0; v < 3; ++v) h->d_cc[v] = (double*)(h->d_slab + v * h->slab_var_stride);
+  h->d_cc[3] = nullptr;
+  h->d_boxsum = (double*)(h->d_slab + 3 * h->slab_var_stride);
+  h->peer_slab[h->me] = h->d_slab;
+
+  // ownership: contiguous Morton ranges per level, cut at sibling groups (afmg_partition)
+  {
+    std::vector<int> rel((size_t)L * (h->nranks + 1));
+    afmg_partition(h->nranks, L, t->lvl_counts, rel.data());
+    h->cut.assign((size_t)(L + 2) * (h->nranks + 1), 0);
+    h->rb_cut.assign((size_t)(L + 2) * (h->nranks + 1), 0);
+    h->h_owner.assign(total, 0);
+    for (int l = 1; l <= L; ++l)
+      for (int r = 0; r <= h->nranks; ++r) h->cut[(size_t)l * (h->nranks + 1) + r] = h->lvl_off[l] + rel[(size_t)(l - 1) * (h->nranks + 1) + r];
+    for (int l = 1; l <= L; ++l)
+      for (int r = 0; r < h->nranks; ++r)
+        for (int q = h->cut[(size_t)l * (h->nranks + 1) + r]; q < h->cut[(size_t)l * (h->nranks + 1) + r + 1]; ++q)
+          h->h_owner[q] = (unsigned char)r;
+    // refinement-boundary faces are listed by level, then by slot: the faces of a rank are contiguous
+    for (int l = 1; l <= L; ++l) {
+      int* c = &h->rb_cut[(size_t)l * (h->nranks + 1)];
+      int q = h->rb_lvl_off[l];
+      for (int r = 0; r < h->nranks; ++r) {
+        c[r] = q;
+        while (q < h->rb_lvl_off[l + 1] && h->h_owner[h->h_rb_slot[q]] == r) ++q;
+      }
+      c[h->nranks] = q;
+      if (q != h->rb_lvl_off[l + 1]) return h->fail(AFMG_ERR_ARG, "internal: refinement-boundary faces not sorted by owner");
+    }
+    if ((rc = dev_upload(h, &h->d_owner, h->h_owner))) return rc;
   }
-  if (h->d_boxsum) cudaFree(h->d_boxsum);
-  h->d_boxsum = nullptr;
-  CK(cudaMalloc((void**)&h->d_boxsum, (size_t)total * sizeof(double)));
+  h->connected = (h->nranks == 1);
 
   for (int v = 0; v < 4; ++v) h->cx.cc[v] = h->d_cc[v];
+  h->cx.nranks = h->nranks;
+  h->cx.me = h->me;
+  h->cx.owner = h->d_owner;
+  for (int r = 0; r < AFMG_MAX_RANKS; ++r) {
+    for (int v = 0; v < 3; ++v) h->cx.ccr[r][v] = nullptr;
+    h->cx.bsum[r] = nullptr;
+  }
+  for (int v = 0; v < 3; ++v) h->cx.ccr[h->me][v] = h->d_cc[v];
+  h->cx.bsum[h->me] = h->d_boxsum;
   h->cx.nbr = h->d_nbr;
   h->cx.aux = h->d_aux;
   h->cx.nmat = h->d_nmat;
@@ -1078,11 +1219,13 @@ static int transfer(afmg_handle* h, int var, int n, const int32_t* box_id, doubl
   if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
   if (n == 0) return AFMG_OK;
   CK(cudaSetDevice(h->device));
+  // slot < 0 marks a box owned by another rank: its packed record is skipped (k_pack / k_unpack)
   std::vector<int> slots(n);
   for (int q = 0; q < n; ++q) {
     const int id = box_id[q];
     if (id < 1 || id > h->highest_id || h->id2slot[id] < 0) return h->fail(AFMG_ERR_ARG, "unknown box id %d", id);
     slots[q] = h->id2slot[id];
+    if (h->nranks > 1 && h->h_owner[slots[q]] != h->me) slots[q] = -1;
   }
   const size_t box_bytes = (size_t)h->box_len * sizeof(double);
   const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)256 << 20) / box_bytes));
@@ -1276,16 +1419,22 @@ int afmg_max_abs(afmg_handle* h, int32_t var, double* out) {
   if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
   CK(cudaSetDevice(h->device));
   unsigned long long bits = 0;
+  const int comb = (h->nranks > 1) ? 4 : 0;  // multi-GPU: the value combined over all ranks
   if (var == AFMG_TMP && h->resid_fresh) {
-    CK(cudaMemcpyAsync(&bits, h->d_scal, sizeof bits, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&bits, h->d_scal + comb, sizeof bits, cudaMemcpyDeviceToHost, h->stream));
   } else {
+    if (h->nranks > 1 && !h->connected) return h->fail(AFMG_ERR_STATE, "multi-GPU handle is not connected");
     CK(cudaMemsetAsync(h->d_scal + 1, 0, sizeof(unsigned long long), h->stream));
-    {
-      Launch L_(h, "maxabs");
-      DISPATCH_NC(h, NC,
-                  { k_maxabs<NC><<<h->nslots, 256, 0, h->stream>>>(h->cx, 0, h->nslots, var, h->d_scal + 1); });
+    for (int l = 1; l <= h->L; ++l) {
+      const Range r = (h->nranks == 1) ? Range{0, h->nslots} : own(h, l);
+      if (r.n > 0) {
+        Launch L_(h, "maxabs");
+        DISPATCH_NC(h, NC, { k_maxabs<NC><<<r.n, 256, 0, h->stream>>>(h->cx, r.s0, r.n, var, h->d_scal + 1); });
+      }
+      if (h->nranks == 1) break;
     }
-    CK(cudaMemcpyAsync(&bits, h->d_scal + 1, sizeof bits, cudaMemcpyDeviceToHost, h->stream));
+    enq_allmax(h, 1);
+    CK(cudaMemcpyAsync(&bits, h->d_scal + 1 + comb, sizeof bits, cudaMemcpyDeviceToHost, h->stream));
   }
   int rc = finish_op(h);
   if (rc) return rc;
@@ -1298,10 +1447,8 @@ int afmg_tree_sum(afmg_handle* h, int32_t var, double* out) {
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
   if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
   CK(cudaSetDevice(h->device));
-  {
-    Launch L_(h, "sum");
-    DISPATCH_NC(h, NC, { k_box_sums<NC><<<h->nslots, 128, 0, h->stream>>>(h->cx, 0, h->nslots, var, h->d_boxsum); });
-  }
+  if (h->nranks > 1 && !h->connected) return h->fail(AFMG_ERR_STATE, "multi-GPU handle is not connected");
+  enq_box_sums(h, var);
   std::vector<double> sums(h->nslots);
   CK(cudaMemcpyAsync(sums.data(), h->d_boxsum, (size_t)h->nslots * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   int rc = finish_op(h);
@@ -1399,18 +1546,98 @@ int32_t afmg_slot_of_box(const afmg_handle* h, int32_t box_id) {
   return h->id2slot[box_id];
 }
 
-int afmg_comm_unique_id(char id[128]) {
-  std::memset(id, 0, 128);
-  return AFMG_ERR_UNSUPPORTED;
+// Contiguous Morton ranges per level, cut at sibling groups of 2^ndim boxes so that the children of a
+// box never straddle two ranks; level 1 (the coarse grid) stays on rank 0.  cuts[(l-1)*(n_ranks+1)+r] =
+// first box (position in the level's Morton order) of rank r on level l; the last entry is the count.
+int afmg_partition(int32_t n_ranks, int32_t highest_lvl, const int32_t* lvl_counts, int32_t* cuts) {
+  if (n_ranks < 1 || n_ranks > AFMG_MAX_RANKS || highest_lvl < 1 || !lvl_counts || !cuts) return AFMG_ERR_ARG;
+  for (int l = 1; l <= highest_lvl; ++l) {
+    int32_t* c = cuts + (size_t)(l - 1) * (n_ranks + 1);
+    const int n = lvl_counts[l - 1];
+    if (l == 1 || n % 8 != 0) {
+      c[0] = 0;
+      for (int r = 1; r <= n_ranks; ++r) c[r] = n;
+      continue;
+    }
+    const long long groups = n / 8;
+    for (int r = 0; r <= n_ranks; ++r) c[r] = (int32_t)(8 * ((groups * r) / n_ranks));
+  }
+  return AFMG_OK;
 }
-int afmg_comm_init(afmg_handle* h, int32_t n_ranks, int32_t, const char*) {
+
+int afmg_comm_init(afmg_handle* h, int32_t n_ranks, int32_t rank) {
   if (!h) return AFMG_ERR_ARG;
-  if (n_ranks == 1) return AFMG_OK;
-  return h->fail(AFMG_ERR_UNSUPPORTED, "multi-GPU partitioning is not part of this build yet");
+  if (n_ranks < 1 || n_ranks > AFMG_MAX_RANKS || rank < 0 || rank >= n_ranks)
+    return h->fail(AFMG_ERR_ARG, "afmg_comm_init: need 1 <= n_ranks <= %d and 0 <= rank < n_ranks", AFMG_MAX_RANKS);
+  if (h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_comm_init must be called before afmg_set_tree");
+  h->nranks = n_ranks;
+  h->me = rank;
+  for (auto& p : h->peers.p) p = nullptr;
+  h->peers.p[rank] = h->d_comm;
+  h->connected = (n_ranks == 1);
+  return AFMG_OK;
 }
+
+namespace {
+struct CommBlob {  // what one rank tells the others (AFMG_COMM_BLOB_BYTES)
+  cudaIpcMemHandle_t slab, comm;
+  uint64_t slab_bytes;
+  int32_t rank, nslots, box_len, pad;
+};
+static_assert(sizeof(CommBlob) <= AFMG_COMM_BLOB_BYTES, "blob size");
+}  // namespace
+
+int afmg_comm_export(afmg_handle* h, void* blob) {
+  if (!h || !blob) return AFMG_ERR_ARG;
+  if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_comm_export: call afmg_set_tree first");
+  CK(cudaSetDevice(h->device));
+  CommBlob b{};
+  CK(cudaIpcGetMemHandle(&b.slab, h->d_slab));
+  CK(cudaIpcGetMemHandle(&b.comm, h->d_comm));
+  b.slab_bytes = h->slab_bytes;
+  b.rank = h->me;
+  b.nslots = h->nslots;
+  b.box_len = h->box_len;
+  std::memset(blob, 0, AFMG_COMM_BLOB_BYTES);
+  std::memcpy(blob, &b, sizeof b);
+  return AFMG_OK;
+}
+
+int afmg_comm_connect(afmg_handle* h, const void* blobs) {
+  if (!h || !blobs) return AFMG_ERR_ARG;
+  if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_comm_connect: call afmg_set_tree first");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  drop_graphs(h);
+  for (int r = 0; r < h->nranks; ++r) {
+    CommBlob b;
+    std::memcpy(&b, (const char*)blobs + (size_t)r * AFMG_COMM_BLOB_BYTES, sizeof b);
+    if (b.rank != r || b.nslots != h->nslots || b.box_len != h->box_len || b.slab_bytes != h->slab_bytes)
+      return h->fail(AFMG_ERR_ARG, "afmg_comm_connect: blob %d does not describe the same tree (rank %d, %d slots)", r,
+                     b.rank, b.nslots);
+    if (r == h->me) continue;
+    if (!h->peer_slab[r]) {
+      void* p = nullptr;
+      CK(cudaIpcOpenMemHandle(&p, b.slab, cudaIpcMemLazyEnablePeerAccess));
+      h->peer_slab[r] = (char*)p;
+    }
+    if (!h->peers.p[r]) {
+      void* p = nullptr;
+      CK(cudaIpcOpenMemHandle(&p, b.comm, cudaIpcMemLazyEnablePeerAccess));
+      h->peers.p[r] = (CommBlock*)p;
+    }
+  }
+  for (int r = 0; r < h->nranks; ++r) {
+    for (int v = 0; v < 3; ++v) h->cx.ccr[r][v] = (double*)(h->peer_slab[r] + v * h->slab_var_stride);
+    h->cx.bsum[r] = (double*)(h->peer_slab[r] + 3 * h->slab_var_stride);
+  }
+  h->connected = true;
+  return AFMG_OK;
+}
+
 int32_t afmg_owner_of_box(const afmg_handle* h, int32_t box_id) {
   if (!h || !h->have_tree || box_id < 1 || box_id > h->highest_id || h->id2slot[box_id] < 0) return -1;
-  return 0;
+  return h->h_owner[h->id2slot[box_id]];
 }
 
 }  // extern "C"

@@ -17,6 +17,7 @@
 namespace afmg {
 
 enum { V_PHI = 0, V_RHS = 1, V_TMP = 2, V_EPS = 3 };
+#define AFMG_MAX_RANKS 8
 
 struct DevCtx {
   double* cc[4];         // per variable: nslots * BOX doubles
@@ -35,6 +36,21 @@ struct DevCtx {
   int rb_row0;           // first rule row that is a refinement-boundary face
   const double* pcoef;   // [8] constant prolongation coefficients
   int pshape;            // 8 = stencil_prolong_248 (linear), 4 = stencil_prolong_234 (sparse)
+  // ---- multi-GPU (one process per GPU): every rank allocates the same slot-indexed arrays and
+  // maps its peers' arrays through CUDA IPC, so a box is addressed as (owner rank, slot) on every
+  // GPU.  nranks == 1: ccr is unused.
+  int nranks, me;
+  const unsigned char* owner;  // [nslots] rank that owns (computes) the box
+  double* ccr[AFMG_MAX_RANKS][3];  // phi / rhs / tmp base pointers of every rank (own entry == cc)
+  double* bsum[AFMG_MAX_RANKS];    // per-box sums (k_box_sums) of every rank
+
+  // base of the record of box `slot` for variable `var` in the memory of the rank that owns it
+  template <int BOX>
+  __device__ __forceinline__ double* at(int var, int slot) const {
+    if (nranks == 1) return cc[var] + (size_t)slot * BOX;
+    return ccr[owner[slot]][var] + (size_t)slot * BOX;
+  }
+  __device__ __forceinline__ bool remote(int slot) const { return nranks > 1 && owner[slot] != me; }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -73,152 +89,77 @@ __device__ __forceinline__ void atomic_max_nonneg(unsigned long long* addr, doub
   atomicMax(addr, (unsigned long long)__double_as_longlong(v));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU synchronisation over peer memory (NVLink).  Every rank owns one CommBlock and maps the
+// blocks of its peers (CUDA IPC).  k_barrier is enqueued between dependent kernels in place of the
+// stream order a single GPU gives for free: it publishes this rank's barrier count into every peer's
+// block (system-scope release after a system fence, so the previous kernels' peer stores are visible
+// first) and waits until every peer has published the same count.  A wait that exceeds the time-out
+// sets `err` (reported by the host as AFMG_ERR_COMM) and later barriers fall through, so a lost peer
+// can never hang the GPU.
+// ---------------------------------------------------------------------------------------------
+struct CommBlock {
+  unsigned long long flags[AFMG_MAX_RANKS];  // flags[r] = number of barriers rank r has entered
+  unsigned long long epoch;                  // number of barriers this rank has entered
+  unsigned long long err;                    // != 0 after a barrier time-out
+  unsigned long long scal[8];                // reduction scratch: [0] residual max, [1] generic max,
+                                             // [2] mean, [4],[5] = [0],[1] combined over all ranks
+};
+struct CommPeers {
+  CommBlock* p[AFMG_MAX_RANKS];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void k_barrier(CommBlock* mine, CommPeers peers, int nranks, int me, unsigned long long timeout_ns) {
+  __shared__ unsigned long long ep;
+  const int t = threadIdx.x;
+  if (t == 0) {
+    ep = mine->epoch + 1;
+    mine->epoch = ep;
+  }
+  __syncthreads();
+  const unsigned long long e = ep;
+  if (t < nranks && t != me) {
+    __threadfence_system();
+    st_release_sys(&peers.p[t]->flags[me], e);
+    if (ld_acquire_sys(&mine->err) == 0) {
+      const unsigned long long t0 = globaltimer_ns();
+      while (ld_acquire_sys(&mine->flags[t]) < e) {
+        if (globaltimer_ns() - t0 > timeout_ns) {
+          mine->err = 1;
+          break;
+        }
+      }
+    }
+  }
+  __threadfence_system();
+}
+
+// scal[4 + idx] = max over ranks of scal[idx] (after a barrier); non-negative doubles order like uint64
+__global__ void k_allmax(CommBlock* mine, CommPeers peers, int nranks, int idx) {
+  unsigned long long m = 0;
+  for (int r = 0; r < nranks; ++r) {
+    const unsigned long long v = ld_acquire_sys(&peers.p[r]->scal[idx]);
+    m = v > m ? v : m;
+  }
+  mine->scal[4 + idx] = m;
+}
+
 // neighbour offset tables
 __device__ __forceinline__ int nmat_index(int dx, int dy, int dz) { return (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1); }
-
-// ---------------------------------------------------------------------------------------------
-// k_gsrb: one red-black half-sweep (stencil_gsrb_357, afivo/src/m_af_stencil.f90:956-973) over the
-// boxes [slot0, slot0+nbox) of one level, fused with the side ghost-cell fill that follows it in
-// gsrb_boxes (afivo/src/m_af_multigrid.f90:648-687; af_gc_box m_af_ghostcell.f90:64-120 without
-// corners).  C = colour updated = redblack & 1.
-//   - the opposite colour block (interior + 6 face segments) arrives by one TMA bulk copy
-//   - thread (m, j) owns the column of nc cells of colour C over k; rhs comes straight from global
-//     into registers, new values go straight back to global (256 B per warp, coalesced)
-//   - boundary-layer values are pushed into the neighbours' ghost face segments (copy_from_nb,
-//     m_af_ghostcell.f90:654-669); physical / refinement faces apply their rule (bc_to_gc :173-279,
-//     mg_sides_rb m_af_multigrid.f90:383-459)
-// ---------------------------------------------------------------------------------------------
-template <int NC, int BPC>
-__global__ void __launch_bounds__(BPC* NC* NC / 2) k_gsrb(DevCtx cx, int slot0, int nbox, int C, int lvl) {
-  using L = Lay3<NC>;
-  constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX, TPB = H * NC;
-  extern __shared__ __align__(128) double smem[];
-  __shared__ uint64_t bar;
-  const int tid = threadIdx.x;
-  const int box0 = blockIdx.x * BPC;
-  const int nhere = min(BPC, nbox - box0);
-  double* const phi = cx.cc[V_PHI];
-  if (tid == 0) mbar_init(&bar, 1);
-  __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(&bar, (uint32_t)(nhere * COL * 8));
-    for (int b = 0; b < nhere; ++b)
-      bulk_g2s(smem + b * COL, phi + (size_t)(slot0 + box0 + b) * BOX + (1 - C) * COL, COL * 8, &bar);
-  }
-  const int b = tid / TPB, t = tid % TPB;
-  if (b >= nhere) return;
-  const int m = t % H, j = t / H + 1;
-  const int slot = slot0 + box0 + b;
-  const double* const S = smem + b * COL;
-  const double* const grhs = cx.cc[V_RHS] + (size_t)slot * BOX + C * COL;
-  double* const gC = phi + (size_t)slot * BOX + C * COL;
-  double* const gN = phi + (size_t)slot * BOX + (1 - C) * COL;
-
-  double r[NC];
-#pragma unroll
-  for (int k = 1; k <= NC; ++k) r[k - 1] = __ldg(grhs + L::iidx(m, j, k));
-
-  int nbf[6], ax[6];
-#pragma unroll
-  for (int f = 0; f < 6; ++f) {
-    nbf[f] = __ldg(cx.nbr + slot * 6 + f);
-    ax[f] = __ldg(cx.aux + slot * 6 + f);
-  }
-  const double* cf = cx.coef + 8 * lvl;
-  const double c2 = cf[1], c3 = cf[2], c4 = cf[3], c5 = cf[4], c6 = cf[5], c7 = cf[6], inv = cf[7];
-
-  mbar_wait(&bar, 0);
-
-  // push value v (colour C, boundary layer) through face f at face index fi
-  auto push = [&](int f, int fi, double v) { phi[(size_t)nbf[f] * BOX + C * COL + NI + (f ^ 1) * NF + fi] = v; };
-  // rule for face f: layer-1 cell changed -> ghost of the other colour; x2 = unchanged layer-2 value
-  auto rule1 = [&](int f, int fi, int bidx, double x1new, double x2) {
-    const double* rc = cx.rule_c + 3 * ax[f];
-    const double B = cx.rule_B[(size_t)ax[f] * L::NC2 + bidx];
-    gN[NI + f * NF + fi] = (rc[0] * B + rc[1] * x1new) + rc[2] * x2;
-  };
-  // layer-2 cell changed -> ghost of colour C; x1 = unchanged layer-1 value
-  auto rule2 = [&](int f, int fi, int bidx, double x1, double x2new) {
-    const double* rc = cx.rule_c + 3 * ax[f];
-    const double B = cx.rule_B[(size_t)ax[f] * L::NC2 + bidx];
-    gC[NI + f * NF + fi] = (rc[0] * B + rc[1] * x1) + rc[2] * x2new;
-  };
-
-  double s_km1 = S[NI + 4 * NF + (j - 1) * H + m];
-  double s_k = S[L::iidx(m, j, 1)];
-#pragma unroll
-  for (int k = 1; k <= NC; ++k) {
-    const int idx = L::iidx(m, j, k);
-    const int pi = (C + j + k) & 1;  // 1: i = 2m+1, 0: i = 2m+2
-    const int i = 2 * m + 2 - pi;
-    const double s_kp1 = (k < NC) ? S[idx + NC * H] : S[NI + 5 * NF + (j - 1) * H + m];
-    const double ym = (j > 1) ? S[idx - H] : S[NI + 2 * NF + (k - 1) * H + m];
-    const double yp = (j < NC) ? S[idx + H] : S[NI + 3 * NF + (k - 1) * H + m];
-    const int fx = (k - 1) * H + ((j - 1) >> 1);
-    double xm, xp;
-    if (pi) {
-      xm = (m > 0) ? S[idx - 1] : S[NI + 0 * NF + fx];
-      xp = s_k;
-    } else {
-      xm = s_k;
-      xp = (m < H - 1) ? S[idx + 1] : S[NI + 1 * NF + fx];
-    }
-    double acc = r[k - 1];
-    acc = acc - c2 * xm;
-    acc = acc - c3 * xp;
-    acc = acc - c4 * ym;
-    acc = acc - c5 * yp;
-    acc = acc - c6 * s_km1;
-    acc = acc - c7 * s_kp1;
-    const double v = acc * inv;
-    gC[idx] = v;
-
-    // ---- z faces
-    const int fz = (j - 1) * H + m, bz = (i - 1) + (j - 1) * NC;
-    if (k == 1) {
-      if (nbf[4] >= 0) push(4, fz, v);
-      else rule1(4, fz, bz, v, s_kp1);
-    }
-    if (k == 2 && nbf[4] < 0) rule2(4, fz, bz, s_km1, v);
-    if (k == NC) {
-      if (nbf[5] >= 0) push(5, fz, v);
-      else rule1(5, fz, bz, v, s_km1);
-    }
-    if (k == NC - 1 && nbf[5] < 0) rule2(5, fz, bz, s_kp1, v);
-    // ---- y faces
-    const int fy = (k - 1) * H + m, by = (i - 1) + (k - 1) * NC;
-    if (j == 1) {
-      if (nbf[2] >= 0) push(2, fy, v);
-      else rule1(2, fy, by, v, yp);
-    }
-    if (j == 2 && nbf[2] < 0) rule2(2, fy, by, ym, v);
-    if (j == NC) {
-      if (nbf[3] >= 0) push(3, fy, v);
-      else rule1(3, fy, by, v, ym);
-    }
-    if (j == NC - 1 && nbf[3] < 0) rule2(3, fy, by, yp, v);
-    // ---- x faces
-    const int bx = (j - 1) + (k - 1) * NC;
-    if (m == 0) {
-      if (pi) {  // i == 1
-        if (nbf[0] >= 0) push(0, fx, v);
-        else rule1(0, fx, bx, v, xp);
-      } else if (nbf[0] < 0) {  // i == 2
-        rule2(0, fx, bx, xm, v);
-      }
-    }
-    if (m == H - 1) {
-      if (!pi) {  // i == NC
-        if (nbf[1] >= 0) push(1, fx, v);
-        else rule1(1, fx, bx, v, xm);
-      } else if (nbf[1] < 0) {  // i == NC-1
-        rule2(1, fx, bx, xp, v);
-      }
-    }
-    s_km1 = s_k;
-    s_k = s_kp1;
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // k_gsrb2: same operation as k_gsrb, restructured for issue rate and bytes in flight:
@@ -249,23 +190,29 @@ __device__ __forceinline__ void epilogue_faces(const DevCtx& cx, int slot, const
                                                int t) {
   using L = Lay3<NC>;
   constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX;
-  double* const phi = cx.cc[V_PHI];
-  double* const gbox = phi + (size_t)slot * BOX;
+  double* const gbox = cx.cc[V_PHI] + (size_t)slot * BOX;
   const int* nbp = cx.nbr + slot * 6;
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     if (!((mask >> c) & 1)) continue;
     const double* Ic = c ? I1 : I0;
-    if (t == 0) {
-      const int n4 = nbp[4], n5 = nbp[5];
-      if (n4 >= 0) bulk_s2g(phi + (size_t)n4 * BOX + c * COL + NI + 5 * NF, Ic, NF * 8);
-      if (n5 >= 0) bulk_s2g(phi + (size_t)n5 * BOX + c * COL + NI + 4 * NF, Ic + (NC - 1) * NC * H, NF * 8);
+#pragma unroll
+    for (int f = 4; f < 6; ++f) {
+      const int nb = nbp[f];
+      if (nb < 0) continue;
+      double* dst = cx.at<BOX>(V_PHI, nb) + c * COL + NI + (f ^ 1) * NF;
+      const double* srcz = (f == 4) ? Ic : Ic + (NC - 1) * NC * H;
+      if (!cx.remote(nb)) {
+        if (t == 0) bulk_s2g(dst, srcz, NF * 8);
+      } else {  // peer GPU: plain coalesced stores over NVLink
+        for (int fi = t; fi < NF; fi += TPB) dst[fi] = srcz[fi];
+      }
     }
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
       const int nb = nbp[f];
       if (nb < 0) continue;
-      double* dst = phi + (size_t)nb * BOX + c * COL + NI + (f ^ 1) * NF;
+      double* dst = cx.at<BOX>(V_PHI, nb) + c * COL + NI + (f ^ 1) * NF;
       for (int fi = t; fi < NF; fi += TPB) {
         const int k = fi / H + 1, ah = fi % H;
         int src;
@@ -437,82 +384,6 @@ __device__ __forceinline__ double apply357_smem(const double* S, const double* c
   return acc;
 }
 
-// k_residual2: as k_residual; thread (m, j, ks) walks its k-range for both colours, rhs / tmp move
-// directly between global memory and registers (coalesced 256 B per warp).
-template <int NC, int KS, int MINB>
-__global__ void __launch_bounds__(KS* NC* NC / 2, MINB)
-    k_residual2(DevCtx cx, int slot0, int nbox, unsigned long long* maxabs_bits) {
-  using L = Lay3<NC>;
-  constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX, KL = NC / KS;
-  extern __shared__ __align__(128) double smem[];
-  __shared__ uint64_t bar;
-  const int slot = slot0 + blockIdx.x;
-  const int t = threadIdx.x;
-  if (t == 0) mbar_init(&bar, 1);
-  __syncthreads();
-  if (t == 0) {
-    mbar_expect_tx(&bar, 2 * COL * 8);
-    bulk_g2s(smem, cx.cc[V_PHI] + (size_t)slot * BOX, 2 * COL * 8, &bar);
-  }
-  const double* grhs = cx.cc[V_RHS] + (size_t)slot * BOX;
-  double* gtmp = cx.cc[V_TMP] + (size_t)slot * BOX;
-  const int m = t % H, j = (t / H) % NC + 1, ks = t / (H * NC);
-  const int k0 = ks * KL + 1;
-  double r[KL];
-#pragma unroll
-  for (int kk = 0; kk < KL; ++kk) r[kk] = __ldg(grhs + L::iidx(m, j, k0 + kk));
-  const double* cf = cx.coef + 8 * cx.lvl[slot];
-  const double c1 = cf[0], c2 = cf[1], c3 = cf[2], c4 = cf[3], c5 = cf[4], c6 = cf[5], c7 = cf[6];
-  mbar_wait(&bar, 0);
-  double mx = 0.0;
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    const double* Sc = smem + c * COL;
-    const double* Sn = smem + (1 - c) * COL;
-    if (c == 1) {
-#pragma unroll
-      for (int kk = 0; kk < KL; ++kk) r[kk] = __ldg(grhs + COL + L::iidx(m, j, k0 + kk));
-    }
-    double s_km1 = (k0 == 1) ? Sn[NI + 4 * NF + (j - 1) * H + m] : Sn[L::iidx(m, j, k0 - 1)];
-    double s_k = Sn[L::iidx(m, j, k0)];
-#pragma unroll
-    for (int kk = 0; kk < KL; ++kk) {
-      const int k = k0 + kk;
-      const int idx = L::iidx(m, j, k);
-      const int pi = (c + j + k) & 1;
-      const double s_kp1 = (k < NC) ? Sn[idx + NC * H] : Sn[NI + 5 * NF + (j - 1) * H + m];
-      const double ym = (j > 1) ? Sn[idx - H] : Sn[NI + 2 * NF + (k - 1) * H + m];
-      const double yp = (j < NC) ? Sn[idx + H] : Sn[NI + 3 * NF + (k - 1) * H + m];
-      const int fx = (k - 1) * H + ((j - 1) >> 1);
-      double xm, xp;
-      if (pi) {
-        xm = (m > 0) ? Sn[idx - 1] : Sn[NI + 0 * NF + fx];
-        xp = s_k;
-      } else {
-        xm = s_k;
-        xp = (m < H - 1) ? Sn[idx + 1] : Sn[NI + 1 * NF + fx];
-      }
-      double acc = c1 * Sc[idx];
-      acc = acc + c2 * xm;
-      acc = acc + c3 * xp;
-      acc = acc + c4 * ym;
-      acc = acc + c5 * yp;
-      acc = acc + c6 * s_km1;
-      acc = acc + c7 * s_kp1;
-      const double res = r[kk] - acc;
-      gtmp[c * COL + idx] = res;
-      mx = fmax(mx, fabs(res));
-      s_km1 = s_k;
-      s_k = s_kp1;
-    }
-  }
-  if (maxabs_bits && cx.child0[slot] < 0) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((t & 31) == 0 && mx > 0.0) atomic_max_nonneg(maxabs_bits, mx);
-  }
-}
-
 // k_resid3: residual of one box per CTA with the x-pair formulation: thread (m, j, ks) owns the two
 // cells i = 2m+1 (A) and i = 2m+2 (B) of row (j, k) -- one of each colour, same index in their colour
 // blocks -- and walks its k-range, so that z neighbours chain through registers (8 LDS per 2 cells).
@@ -552,9 +423,12 @@ __global__ void __launch_bounds__(KS* NC* NC / 2, MINB)
   }
   const double* cf = cx.coef + 8 * cx.lvl[slot];
   const double c1 = cf[0], c2 = cf[1], c3 = cf[2], c4 = cf[3], c5 = cf[4], c6 = cf[5], c7 = cf[6];
-  int p = 0, ox = 0, oy = 0, oz = 0;
+  int ox = 0, oy = 0, oz = 0;
+  double *ptmp = nullptr, *pphi = nullptr;  // parent records (possibly on a peer GPU)
   if (MODE == 1) {
-    p = cx.parent[slot];
+    const int p = cx.parent[slot];
+    ptmp = cx.at<BOX>(V_TMP, p);
+    pphi = cx.at<BOX>(V_PHI, p);
     const int cof = cx.coff[slot];
     ox = (cof & 1) * H;
     oy = ((cof >> 1) & 1) * H;
@@ -622,8 +496,8 @@ __global__ void __launch_bounds__(KS* NC* NC / 2, MINB)
       sp = sp + byp;  // phi(2m+2, j+1, k)
       if ((kk & 1) == 1 && (j & 1)) {
         const int qp = L::interior(ox + m + 1, oy + ((j + 1) >> 1), oz + (k >> 1));
-        cx.cc[V_TMP][(size_t)p * BOX + qp] = 0.125 * sr;
-        cx.cc[V_PHI][(size_t)p * BOX + qp] = 0.125 * sp;
+        ptmp[qp] = 0.125 * sr;
+        pphi[qp] = 0.125 * sp;
       }
     }
     // next step: colours swap, so A/B blocks swap roles
@@ -642,106 +516,6 @@ __global__ void __launch_bounds__(KS* NC* NC / 2, MINB)
   }
 }
 
-// k_restrict2: as k_restrict with the child's phi staged in shared memory; one thread per coarse
-// cell computes the 8 fine residuals and both 2x2x2 averages.
-template <int NC, int MINB>
-__global__ void __launch_bounds__((NC / 2) * (NC / 2) * (NC / 2) >= 256 ? 256 : (NC / 2) * (NC / 2) * (NC / 2), MINB)
-    k_restrict2(DevCtx cx, int slot0, int nbox, int keep_res) {
-  using L = Lay3<NC>;
-  constexpr int H = L::H, COL = L::COL, BOX = L::BOX;
-  extern __shared__ __align__(128) double smem[];
-  __shared__ uint64_t bar;
-  const int slot = slot0 + blockIdx.x;
-  if (threadIdx.x == 0) mbar_init(&bar, 1);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(&bar, 2 * COL * 8);
-    bulk_g2s(smem, cx.cc[V_PHI] + (size_t)slot * BOX, 2 * COL * 8, &bar);
-  }
-  const double* rhs = cx.cc[V_RHS] + (size_t)slot * BOX;
-  double* tmp = cx.cc[V_TMP] + (size_t)slot * BOX;
-  const int p = cx.parent[slot], cof = cx.coff[slot];
-  double* pphi = cx.cc[V_PHI] + (size_t)p * BOX;
-  double* ptmp = cx.cc[V_TMP] + (size_t)p * BOX;
-  const int ox = (cof & 1) * H, oy = ((cof >> 1) & 1) * H, oz = ((cof >> 2) & 1) * H;
-  const double* cf = cx.coef + 8 * cx.lvl[slot];
-  const double c1 = cf[0];
-  mbar_wait(&bar, 0);
-  for (int n = threadIdx.x; n < H * H * H; n += blockDim.x) {
-    const int ic = n % H + 1, jc = (n / H) % H + 1, kc = n / (H * H) + 1;
-    double rr[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int i = 2 * ic - 1 + (q & 1), j = 2 * jc - 1 + ((q >> 1) & 1), k = 2 * kc - 1 + (q >> 2);
-      rr[q] = __ldg(rhs + L::interior(i, j, k));
-    }
-    double sr = 0.0, sp = 0.0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int i = 2 * ic - 1 + (q & 1), j = 2 * jc - 1 + ((q >> 1) & 1), k = 2 * kc - 1 + (q >> 2);
-      const double lp = apply357_smem<NC>(smem, cf, c1, i, j, k);
-      const double res = rr[q] - lp;
-      if (keep_res) tmp[L::interior(i, j, k)] = res;
-      sr = sr + res;
-      sp = sp + smem[L::interior(i, j, k)];
-    }
-    const int qp = L::interior(ox + ic, oy + jc, oz + kc);
-    ptmp[qp] = 0.125 * sr;
-    pphi[qp] = 0.125 * sp;
-  }
-}
-
-// k_correct2: child part of correct_children, one CTA per (parent, child): the (nc/2+2)^3 window of
-// the correction t = phi_p - tmp_p the child's prolongation needs is formed in shared memory; the
-// parent's tmp is NOT modified here (k_store_corr does that when the state is observable).
-template <int NC>
-__global__ void __launch_bounds__(256) k_correct2(DevCtx cx, int slot0, int nbox) {
-  using L = Lay3<NC>;
-  constexpr int H = L::H, W = H + 2;
-  __shared__ double sub[W * W * W];
-  const int slot = slot0 + blockIdx.x / 8, ch = blockIdx.x % 8;
-  const int c0 = cx.child0[slot];
-  if (c0 < 0) return;
-  const double* phi = cx.cc[V_PHI] + (size_t)slot * L::BOX;
-  const double* tmp = cx.cc[V_TMP] + (size_t)slot * L::BOX;
-  const int ox = (ch & 1) * H, oy = ((ch >> 1) & 1) * H, oz = ((ch >> 2) & 1) * H;
-  for (int n = threadIdx.x; n < W * W * W; n += blockDim.x) {
-    const int a = n % W, b = (n / W) % W, c = n / (W * W);
-    const int q = L::cell(ox + a, oy + b, oz + c);
-    sub[n] = phi[q] - tmp[q];
-  }
-  __syncthreads();
-  const double* pc = cx.pcoef;
-  const int pshape = cx.pshape;
-  double* cphi = cx.cc[V_PHI] + (size_t)(c0 + ch) * L::BOX;
-  for (int n = threadIdx.x; n < 2 * L::NI; n += blockDim.x) {
-    const int q = (n < L::NI) ? n : (L::COL + n - L::NI);
-    int i, j, k;
-    L::uncell(q, i, j, k);
-    const int i1 = (i + 1) >> 1, i2 = i1 + 1 - 2 * (i & 1);
-    const int j1 = (j + 1) >> 1, j2 = j1 + 1 - 2 * (j & 1);
-    const int k1 = (k + 1) >> 1, k2 = k1 + 1 - 2 * (k & 1);
-    auto P = [&](int a, int b, int c) { return sub[(c * W + b) * W + a]; };
-    double acc = cphi[q];
-    if (pshape == 8) {
-      acc = acc + pc[0] * P(i1, j1, k1);
-      acc = acc + pc[1] * P(i2, j1, k1);
-      acc = acc + pc[2] * P(i1, j2, k1);
-      acc = acc + pc[3] * P(i2, j2, k1);
-      acc = acc + pc[4] * P(i1, j1, k2);
-      acc = acc + pc[5] * P(i2, j1, k2);
-      acc = acc + pc[6] * P(i1, j2, k2);
-      acc = acc + pc[7] * P(i2, j2, k2);
-    } else {
-      acc = acc + pc[0] * P(i1, j1, k1);
-      acc = acc + pc[1] * P(i2, j1, k1);
-      acc = acc + pc[2] * P(i1, j2, k1);
-      acc = acc + pc[3] * P(i1, j1, k2);
-    }
-    cphi[q] = acc;
-  }
-}
-
 // k_correct3: k_correct2 with the child's interior staged in shared memory by TMA (bulk load, update
 // in place, bulk store).  With push != 0 it also performs the side ghost fill of the af_gc_lvl that
 // follows correct_children in the cycle (m_af_multigrid.f90:222, :171): boundary layers of both
@@ -756,11 +530,9 @@ __global__ void __launch_bounds__(256) k_correct3(DevCtx cx, int slot0, int nbox
   double* I0 = smem;
   double* I1 = smem + NI;
   double* sub = smem + 2 * NI;
-  const int slot = slot0 + blockIdx.x / 8, ch = blockIdx.x % 8;
-  const int c0 = cx.child0[slot];
-  if (c0 < 0) return;
+  const int cslot = slot0 + blockIdx.x;  // child box (this rank's); its parent may live on a peer GPU
+  const int slot = cx.parent[cslot], ch = cx.coff[cslot];
   const int t = threadIdx.x;
-  const int cslot = c0 + ch;
   double* cphi = cx.cc[V_PHI] + (size_t)cslot * BOX;
   if (t == 0) mbar_init(&bar, 1);
   __syncthreads();
@@ -769,8 +541,8 @@ __global__ void __launch_bounds__(256) k_correct3(DevCtx cx, int slot0, int nbox
     bulk_g2s(I0, cphi, NI * 8, &bar);
     bulk_g2s(I1, cphi + COL, NI * 8, &bar);
   }
-  const double* phi = cx.cc[V_PHI] + (size_t)slot * BOX;
-  const double* tmp = cx.cc[V_TMP] + (size_t)slot * BOX;
+  const double* phi = cx.at<BOX>(V_PHI, slot);
+  const double* tmp = cx.at<BOX>(V_TMP, slot);
   const int ox = (ch & 1) * H, oy = ((ch >> 1) & 1) * H, oz = ((ch >> 2) & 1) * H;
   for (int n = t; n < W * W * W; n += 256) {
     const int a = n % W, b = (n / W) % W, c = n / (W * W);
@@ -837,9 +609,9 @@ __global__ void __launch_bounds__(256) k_correct3(DevCtx cx, int slot0, int nbox
 }
 
 template <int NC>
-__device__ void gc_sides(const DevCtx& cx, int slot, double* var_base);
+__device__ void gc_sides(const DevCtx& cx, int slot, int var);
 template <int NC>
-__device__ void gc_edges_corners(const DevCtx& cx, int slot, double* var_base);
+__device__ void gc_edges_corners(const DevCtx& cx, int slot, int var);
 
 // k_gc2: af_gc_lvl for one level, and for boxes with children the parent part of update_coarse
 // (see k_gc) computed from a shared-memory copy of the box (TMA bulk load) instead of global loads.
@@ -861,9 +633,9 @@ __global__ void __launch_bounds__(256) k_gc2(DevCtx cx, int slot0, int nbox, int
       bulk_g2s(smem, gphi, 2 * COL * 8, &bar);
     }
   }
-  gc_sides<NC>(cx, slot, cx.cc[V_PHI]);
+  gc_sides<NC>(cx, slot, V_PHI);
   __syncthreads();
-  if (corners) gc_edges_corners<NC>(cx, slot, cx.cc[V_PHI]);
+  if (corners) gc_edges_corners<NC>(cx, slot, V_PHI);
   if (!upd) return;
   mbar_wait(&bar, 0);
   // the staged copy may hold stale ghost faces: refresh them from what this CTA just wrote
@@ -920,7 +692,7 @@ __global__ void k_rb_prepare(DevCtx cx, int r0, int nr, int var) {
   const int cof = cx.coff[s];
   const int ta = (d == 0) ? 1 : 0, tb = (d == 2) ? 1 : 2;
   const int coa = ((cof >> ta) & 1) * H, cob = ((cof >> tb) & 1) * H;
-  const double* cb = cx.cc[var] + (size_t)pn * L::BOX;
+  const double* cb = cx.at<L::BOX>(var, pn);
   auto T = [&](int x, int y) {
     int q[3];
     q[d] = layer;
@@ -945,9 +717,9 @@ __global__ void k_rb_prepare(DevCtx cx, int r0, int nr, int var) {
 // Ghost cells by gathering (af_gc_box, m_af_ghostcell.f90:64-170): sides, then edges and corners.
 // ---------------------------------------------------------------------------------------------
 template <int NC>
-__device__ void gc_sides(const DevCtx& cx, int slot, double* var_base) {
+__device__ void gc_sides(const DevCtx& cx, int slot, int var) {
   using L = Lay3<NC>;
-  double* box = var_base + (size_t)slot * L::BOX;
+  double* box = cx.cc[var] + (size_t)slot * L::BOX;
   for (int n = threadIdx.x; n < 6 * L::NC2; n += blockDim.x) {
     const int f = n / L::NC2, rr = n % L::NC2;
     const int a = rr % NC + 1, b = rr / NC + 1;
@@ -960,7 +732,7 @@ __device__ void gc_sides(const DevCtx& cx, int slot, double* var_base) {
     double v;
     if (nb >= 0) {  // copy_from_nb: ghost (g) <- neighbour cell g - dnb*nc
       q[d] = hi ? 1 : NC;
-      v = ldcell<NC>(var_base + (size_t)nb * L::BOX, q[0], q[1], q[2]);
+      v = ldcell<NC>(cx.at<L::BOX>(var, nb), q[0], q[1], q[2]);
     } else {
       const int row = cx.aux[slot * 6 + f];
       const double* rc = cx.rule_c + 3 * row;
@@ -978,9 +750,9 @@ __device__ void gc_sides(const DevCtx& cx, int slot, double* var_base) {
 // af_gc_box_corner (m_af_ghostcell.f90:125-170): needs the box's own face ghosts (call after a
 // __syncthreads following gc_sides, or in a later kernel)
 template <int NC>
-__device__ void gc_edges_corners(const DevCtx& cx, int slot, double* var_base) {
+__device__ void gc_edges_corners(const DevCtx& cx, int slot, int var) {
   using L = Lay3<NC>;
-  double* box = var_base + (size_t)slot * L::BOX;
+  double* box = cx.cc[var] + (size_t)slot * L::BOX;
   for (int n = threadIdx.x; n < 12 * NC + 8; n += blockDim.x) {
     if (n < 12 * NC) {
       const int e = n / NC, pos = n % NC + 1, dim = e >> 2;
@@ -994,7 +766,7 @@ __device__ void gc_edges_corners(const DevCtx& cx, int slot, double* var_base) {
       const int nb = cx.nmat[slot * 27 + nmat_index(dir[0], dir[1], dir[2])];
       double v;
       if (nb >= 0) {
-        v = ldcell<NC>(var_base + (size_t)nb * L::BOX, q[0] - dir[0] * NC, q[1] - dir[1] * NC, q[2] - dir[2] * NC);
+        v = ldcell<NC>(cx.at<L::BOX>(var, nb), q[0] - dir[0] * NC, q[1] - dir[1] * NC, q[2] - dir[2] * NC);
       } else {  // af_edge_gc_extrap (:885-924): a + b - c
         int qa[3] = {q[0], q[1], q[2]}, qb[3] = {q[0], q[1], q[2]}, qc[3] = {q[0], q[1], q[2]};
         qa[o1] -= dir[o1];
@@ -1016,7 +788,7 @@ __device__ void gc_edges_corners(const DevCtx& cx, int slot, double* var_base) {
       const int nb = cx.nmat[slot * 27 + nmat_index(dx, dy, dz)];
       double v;
       if (nb >= 0) {
-        v = ldcell<NC>(var_base + (size_t)nb * L::BOX, qi - dx * NC, qj - dy * NC, qk - dz * NC);
+        v = ldcell<NC>(cx.at<L::BOX>(var, nb), qi - dx * NC, qj - dy * NC, qk - dz * NC);
       } else {  // af_corner_gc_extrap (:860-879)
         v = ldcell<NC>(box, qi, qj - dy, qk - dz) + ldcell<NC>(box, qi - dx, qj, qk - dz) +
             ldcell<NC>(box, qi - dx, qj - dy, qk) - 2 * ldcell<NC>(box, qi - dx, qj - dy, qk - dz);
@@ -1036,11 +808,10 @@ __global__ void k_gc(DevCtx cx, int slot0, int nbox, int var, int corners, int m
   using L = Lay3<NC>;
   const int slot = slot0 + blockIdx.x;
   if ((int)blockIdx.x >= nbox) return;
-  double* vb = cx.cc[var];
-  gc_sides<NC>(cx, slot, vb);
+  gc_sides<NC>(cx, slot, var);
   if (corners) {
     __syncthreads();
-    gc_edges_corners<NC>(cx, slot, vb);
+    gc_edges_corners<NC>(cx, slot, var);
   }
   if (mode == 0 || cx.child0[slot] < 0) return;
   __syncthreads();
@@ -1067,52 +838,7 @@ template <int NC>
 __global__ void k_edges_corners(DevCtx cx, int slot0, int nbox, int var) {
   const int slot = slot0 + blockIdx.x;
   if ((int)blockIdx.x >= nbox) return;
-  gc_edges_corners<NC>(cx, slot, cx.cc[var]);
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_restrict: child part of update_coarse / set_coarse_phi_rhs (m_af_multigrid.f90:704-716, 754-761):
-// residual r = rhs - L(phi) (residual_box :801-810), restrict r into the parent's tmp and phi into
-// the parent's phi (af_restrict_box, m_af_restrict.f90:120-133: 0.125 * sum in array element order).
-// The child's tmp is left untouched (the reference saves and restores it) unless keep_res != 0
-// (set_coarse_phi_rhs leaves the residual there).  One CTA per child box, one thread per coarse cell.
-// ---------------------------------------------------------------------------------------------
-template <int NC>
-__global__ void k_restrict(DevCtx cx, int slot0, int nbox, int keep_res) {
-  using L = Lay3<NC>;
-  constexpr int H = L::H;
-  const int slot = slot0 + blockIdx.x;
-  if ((int)blockIdx.x >= nbox) return;
-  const double* phi = cx.cc[V_PHI] + (size_t)slot * L::BOX;
-  const double* rhs = cx.cc[V_RHS] + (size_t)slot * L::BOX;
-  double* tmp = cx.cc[V_TMP] + (size_t)slot * L::BOX;
-  const int p = cx.parent[slot], cof = cx.coff[slot];
-  double* pphi = cx.cc[V_PHI] + (size_t)p * L::BOX;
-  double* ptmp = cx.cc[V_TMP] + (size_t)p * L::BOX;
-  const int ox = (cof & 1) * H, oy = ((cof >> 1) & 1) * H, oz = ((cof >> 2) & 1) * H;
-  const double* cf = cx.coef + 8 * cx.lvl[slot];
-  const double c1 = cf[0];
-  for (int n = threadIdx.x; n < H * H * H; n += blockDim.x) {
-    const int ic = n % H + 1, jc = (n / H) % H + 1, kc = n / (H * H) + 1;
-    double sr = 0.0, sp = 0.0;
-#pragma unroll
-    for (int dk = 0; dk < 2; ++dk)
-#pragma unroll
-      for (int dj = 0; dj < 2; ++dj)
-#pragma unroll
-        for (int di = 0; di < 2; ++di) {
-          const int i = 2 * ic - 1 + di, j = 2 * jc - 1 + dj, k = 2 * kc - 1 + dk;
-          const int q = L::interior(i, j, k);
-          const double lp = apply357<NC>(phi, cf, c1, i, j, k);
-          const double res = rhs[q] - lp;
-          if (keep_res) tmp[q] = res;
-          sr = sr + res;
-          sp = sp + phi[q];
-        }
-    const int qp = L::interior(ox + ic, oy + jc, oz + kc);
-    ptmp[qp] = 0.125 * sr;
-    pphi[qp] = 0.125 * sp;
-  }
+  gc_edges_corners<NC>(cx, slot, var);
 }
 
 // restriction of one variable only (init_phi_rhs, m_af_multigrid.f90:779-799: phi = 0, restrict rhs)
@@ -1124,7 +850,7 @@ __global__ void k_restrict_var(DevCtx cx, int slot0, int nbox, int var, int clea
   if ((int)blockIdx.x >= nbox) return;
   const double* src = cx.cc[var] + (size_t)slot * L::BOX;
   const int p = cx.parent[slot], cof = cx.coff[slot];
-  double* dst = cx.cc[var] + (size_t)p * L::BOX;
+  double* dst = cx.at<L::BOX>(var, p);
   const int ox = (cof & 1) * H, oy = ((cof >> 1) & 1) * H, oz = ((cof >> 2) & 1) * H;
   if (clear_phi) {
     double* phi = cx.cc[V_PHI] + (size_t)slot * L::BOX;
@@ -1140,98 +866,6 @@ __global__ void k_restrict_var(DevCtx cx, int slot0, int nbox, int var, int clea
 #pragma unroll
         for (int di = 0; di < 2; ++di) s = s + src[L::interior(2 * ic - 1 + di, 2 * jc - 1 + dj, 2 * kc - 1 + dk)];
     dst[L::interior(ox + ic, oy + jc, oz + kc)] = 0.125 * s;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_correct: correct_children (m_af_multigrid.f90:624-646) for parents [slot0, slot0+nbox) that
-// have children: tmp_p = phi_p - tmp_p on the full box, then phi_c += P(tmp_p) for the 8 children
-// (stencil_prolong_248 / _234, m_af_stencil.f90:582-815).  One CTA per parent; the correction is
-// staged in shared memory in plain (nc+2)^3 order.
-// ---------------------------------------------------------------------------------------------
-template <int NC>
-__global__ void k_correct(DevCtx cx, int slot0, int nbox) {
-  using L = Lay3<NC>;
-  constexpr int H = L::H, N2 = NC + 2;
-  extern __shared__ __align__(16) double tile[];  // N2^3
-  const int slot = slot0 + blockIdx.x;
-  if ((int)blockIdx.x >= nbox) return;
-  const int c0 = cx.child0[slot];
-  if (c0 < 0) return;
-  const double* phi = cx.cc[V_PHI] + (size_t)slot * L::BOX;
-  double* tmp = cx.cc[V_TMP] + (size_t)slot * L::BOX;
-  for (int q = threadIdx.x; q < L::BOX; q += blockDim.x) {
-    const double t = phi[q] - tmp[q];
-    tmp[q] = t;
-    int i, j, k;
-    L::uncell(q, i, j, k);
-    tile[(k * N2 + j) * N2 + i] = t;
-  }
-  __syncthreads();
-  const double* pc = cx.pcoef;
-  const int pshape = cx.pshape;
-  for (int ch = 0; ch < 8; ++ch) {
-    double* cphi = cx.cc[V_PHI] + (size_t)(c0 + ch) * L::BOX;
-    const int ox = (ch & 1) * H, oy = ((ch >> 1) & 1) * H, oz = ((ch >> 2) & 1) * H;
-    for (int n = threadIdx.x; n < 2 * L::NI; n += blockDim.x) {
-      const int q = (n < L::NI) ? n : (L::COL + n - L::NI);
-      int i, j, k;
-      L::uncell(q, i, j, k);
-      const int i1 = ox + ((i + 1) >> 1), i2 = i1 + 1 - 2 * (i & 1);
-      const int j1 = oy + ((j + 1) >> 1), j2 = j1 + 1 - 2 * (j & 1);
-      const int k1 = oz + ((k + 1) >> 1), k2 = k1 + 1 - 2 * (k & 1);
-      auto P = [&](int a, int b, int c) { return tile[(c * N2 + b) * N2 + a]; };
-      double acc = cphi[q];
-      if (pshape == 8) {
-        acc = acc + pc[0] * P(i1, j1, k1);
-        acc = acc + pc[1] * P(i2, j1, k1);
-        acc = acc + pc[2] * P(i1, j2, k1);
-        acc = acc + pc[3] * P(i2, j2, k1);
-        acc = acc + pc[4] * P(i1, j1, k2);
-        acc = acc + pc[5] * P(i2, j1, k2);
-        acc = acc + pc[6] * P(i1, j2, k2);
-        acc = acc + pc[7] * P(i2, j2, k2);
-      } else {
-        acc = acc + pc[0] * P(i1, j1, k1);
-        acc = acc + pc[1] * P(i2, j1, k1);
-        acc = acc + pc[2] * P(i1, j2, k1);
-        acc = acc + pc[3] * P(i1, j1, k2);
-      }
-      cphi[q] = acc;
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_residual: tmp = rhs - L(phi) on the interior of boxes [slot0, slot0+nbox) (any levels)
-// (residual_box, m_af_multigrid.f90:801-810), plus max |tmp| over leaves (af_tree_maxabs_cc,
-// m_af_utils.f90:773-785) accumulated into *maxabs_bits (non-negative doubles order like uint64).
-// ---------------------------------------------------------------------------------------------
-
-template <int NC>
-__global__ void k_residual(DevCtx cx, int slot0, int nbox, unsigned long long* maxabs_bits) {
-  using L = Lay3<NC>;
-  const int slot = slot0 + blockIdx.x;
-  if ((int)blockIdx.x >= nbox) return;
-  const double* phi = cx.cc[V_PHI] + (size_t)slot * L::BOX;
-  const double* rhs = cx.cc[V_RHS] + (size_t)slot * L::BOX;
-  double* tmp = cx.cc[V_TMP] + (size_t)slot * L::BOX;
-  const double* cf = cx.coef + 8 * cx.lvl[slot];
-  const double c1 = cf[0];
-  double mx = 0.0;
-  for (int n = threadIdx.x; n < 2 * L::NI; n += blockDim.x) {
-    const int q = (n < L::NI) ? n : (L::COL + n - L::NI);
-    int i, j, k;
-    L::uncell(q, i, j, k);
-    const double lp = apply357<NC>(phi, cf, c1, i, j, k);
-    const double res = rhs[q] - lp;
-    tmp[q] = res;
-    mx = fmax(mx, fabs(res));
-  }
-  if (maxabs_bits && cx.child0[slot] < 0) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0 && mx > 0.0) atomic_max_nonneg(maxabs_bits, mx);
   }
 }
 
@@ -1272,6 +906,8 @@ __global__ void k_box_sums(DevCtx cx, int slot0, int nbox, int var, double* out)
     double s = 0.0;
     for (int n = 0; n < NC * NC; ++n) s = s + part[n];
     out[slot] = s;
+    for (int r = 0; r < cx.nranks; ++r)  // multi-GPU: every rank keeps the complete table
+      if (r != cx.me && cx.nranks > 1) cx.bsum[r][slot] = s;
   }
 }
 
@@ -1303,7 +939,7 @@ template <int NC>
 __global__ void k_unpack(double* var_base, const int* slots, int n, const double* packed) {
   using L = Lay3<NC>;
   constexpr int N2 = NC + 2;
-  if ((int)blockIdx.x >= n) return;
+  if ((int)blockIdx.x >= n || slots[blockIdx.x] < 0) return;
   double* box = var_base + (size_t)slots[blockIdx.x] * L::BOX;
   const double* src = packed + (size_t)blockIdx.x * L::BOX;
   for (int q = threadIdx.x; q < L::BOX; q += blockDim.x) {
@@ -1316,7 +952,7 @@ template <int NC>
 __global__ void k_pack(const double* var_base, const int* slots, int n, double* packed) {
   using L = Lay3<NC>;
   constexpr int N2 = NC + 2;
-  if ((int)blockIdx.x >= n) return;
+  if ((int)blockIdx.x >= n || slots[blockIdx.x] < 0) return;
   const double* box = var_base + (size_t)slots[blockIdx.x] * L::BOX;
   double* dst = packed + (size_t)blockIdx.x * L::BOX;
   for (int q = threadIdx.x; q < L::BOX; q += blockDim.x) {

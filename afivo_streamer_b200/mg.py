@@ -52,6 +52,9 @@ class mg_t:
     prolongation_type: int = MG_PROLONG_AUTO
     sides_bc: Optional[Callable] = None  # (nb, coords[n, nface, D]) -> (bc_type, values)
     device: int = -1
+    # multi-GPU: (rank, world_size, allgather) with allgather(bytes) -> list of every rank's bytes, e.g.
+    # built on torch.distributed (see comm_from_torch); None = single GPU
+    comm: Optional[tuple] = None
     initialized: bool = False
     _h: Optional[C.c_void_p] = None
     _tree: Optional[Tree] = None
@@ -172,6 +175,36 @@ class mg_t:
     def slot_of_box(self, box_id):
         return int(_lib.lib().afmg_slot_of_box(self._h, int(box_id)))
 
+    def owner_of_box(self, box_id):
+        return int(_lib.lib().afmg_owner_of_box(self._h, int(box_id)))
+
+
+def comm_from_torch(group=None):
+    """(rank, world, allgather) on top of an initialised torch.distributed process group (nccl or gloo)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+
+    def allgather(raw: bytes):
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        mine = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        out = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(out, mine, group=group)
+        return [bytes(t.cpu().numpy().tobytes()) for t in out]
+
+    return rank, world, allgather
+
+
+def partition(n_ranks: int, lvl_counts):
+    """afmg_partition: per level, the first position (Morton order) of every rank; shape (L, n_ranks + 1)."""
+    counts = np.ascontiguousarray(lvl_counts, np.int32)
+    cuts = np.zeros((len(counts), n_ranks + 1), np.int32)
+    rc = _lib.lib().afmg_partition(n_ranks, len(counts), counts.ctypes.data_as(C.POINTER(C.c_int32)),
+                                   cuts.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != 0:
+        raise AfmgError(rc, "afmg_partition: invalid arguments")
+    return cuts
+
 
 def _opts_from(tree: Tree, mg: mg_t) -> Opts:
     o = Opts()
@@ -214,6 +247,8 @@ def mg_init(tree: Tree, mg: mg_t):
         raise AfmgError(rc, (L.afmg_last_error(None) or b"").decode())
     mg._h, mg._tree = h, tree
     mg.initialized = True
+    if mg.comm is not None:
+        mg._check(L.afmg_comm_init(h, int(mg.comm[1]), int(mg.comm[0])))
     mg_set_tree(tree, mg)
 
 
@@ -223,6 +258,14 @@ def mg_set_tree(tree: Tree, mg: mg_t):
     td, keep = _tree_desc(tree)
     mg._check(_lib.lib().afmg_set_tree(mg._h, C.byref(td)))
     mg._tree = tree
+    if mg.comm is not None and mg.comm[1] > 1:
+        # exchange the CUDA IPC handles of the ranks' device arrays (plumbing; the data path itself is
+        # peer-memory loads / stores inside the kernels)
+        blob = C.create_string_buffer(_lib.AFMG_COMM_BLOB_BYTES)
+        mg._check(_lib.lib().afmg_comm_export(mg._h, blob))
+        blobs = mg.comm[2](blob.raw)
+        allb = C.create_string_buffer(b"".join(blobs), _lib.AFMG_COMM_BLOB_BYTES * len(blobs))
+        mg._check(_lib.lib().afmg_comm_connect(mg._h, allb))
     bc = mg.sides_bc if isinstance(mg.sides_bc, BCTable) else bc_table(tree, mg.sides_bc)
     mg.set_bc(bc)
 

@@ -332,9 +332,10 @@ def corner_refined_tree(ndim: int, nc: int, coarse: int, max_lvl: int) -> Tree:
     return build_tree(ndim, nc, [coarse] * ndim, max_lvl, fn)
 
 
-def channel_tree(nc: int = 8, coarse: int = 8, max_lvl: int = 9, uniform_lvls: int = 3) -> Tree:
+def channel_tree(nc: int = 8, coarse: int = 8, max_lvl: int = 9, uniform_lvls: int = 3, width: float = 2.0) -> Tree:
     """S2 stand-in for ``programs/standard_3d``: levels 1..uniform_lvls uniform, then refine
-    boxes whose centre lies within 0.6*0.5^(l-1) of the segment (0.5,0.5,0.35)-(0.5,0.5,0.65)."""
+    boxes whose centre lies within ``width`` box lengths (width * 0.5^(l-1)) of the segment
+    (0.5,0.5,0.35)-(0.5,0.5,0.65): a streamer-channel-like refinement down to max_lvl."""
     a = np.array([0.5, 0.5, 0.35])
     b = np.array([0.5, 0.5, 0.65])
 
@@ -344,7 +345,7 @@ def channel_tree(nc: int = 8, coarse: int = 8, max_lvl: int = 9, uniform_lvls: i
         ab = b - a
         t = np.clip(((ctr - a) @ ab) / (ab @ ab), 0.0, 1.0)
         d = np.linalg.norm(ctr - (a + t[:, None] * ab), axis=1)
-        return d < 0.6 * 0.5 ** (l - 1)
+        return d < width * 0.5 ** (l - 1)
 
     return build_tree(3, nc, [coarse] * 3, max_lvl, fn)
 

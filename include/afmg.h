@@ -36,7 +36,7 @@ enum {
   AFMG_ERR_UNSUPPORTED = -3,  /* valid in the reference, not (yet) supported here          */
   AFMG_ERR_STATE = -4,        /* call order violated (e.g. solve before afmg_set_tree)     */
   AFMG_ERR_SINGULAR = -5,     /* coarse-grid operator is singular (all-Neumann, lambda=0)   */
-  AFMG_ERR_NCCL = -6
+  AFMG_ERR_COMM = -6           /* a peer GPU did not reach a barrier in time               */
 };
 
 /* cell-centred variables of the solver: mg%i_phi, mg%i_rhs, mg%i_tmp, tree%mg_i_eps
@@ -195,13 +195,30 @@ int32_t afmg_layout_box_len(int32_t ndim, int32_t nc);
 /* slot (position in the device arrays) of a box id, -1 if unknown */
 int32_t afmg_slot_of_box(const afmg_handle* h, int32_t box_id);
 
-/* ---- multi-GPU: one process per GPU.  The caller distributes a 128-byte NCCL unique id (e.g. with
- * MPI or torch.distributed) and every rank calls afmg_comm_init before afmg_set_tree.  Boxes are
- * partitioned by contiguous Morton ranges per level; every rank passes the same full tree. */
-int afmg_comm_unique_id(char id[128]);
-int afmg_comm_init(afmg_handle* h, int32_t n_ranks, int32_t rank, const char id[128]);
-/* which rank owns a box (-1 if unknown); upload/download only touch boxes owned by this rank */
+/* ---- multi-GPU: one process per GPU of one NVLink / NVSwitch domain.  Boxes are
+ * partitioned by contiguous Morton ranges per level (afmg_partition); every rank passes the same full
+ * tree and boundary conditions, computes only the boxes it owns, and reads / writes the halo boxes of
+ * its peers directly through NVLink peer memory (CUDA IPC): ghost-cell pushes, restriction into and
+ * prolongation from remote parents and the max-norm reduction are fused into the kernels, with
+ * device-side barriers in place of collectives.  Call order on every rank:
+ *     afmg_create; afmg_comm_init(h, n, rank); afmg_set_tree; afmg_comm_export(h, blob);
+ *     <all-gather the n blobs with MPI / torch.distributed / ...>; afmg_comm_connect(h, blobs); ...
+ * and again export / all-gather / connect after every later afmg_set_tree.  All ranks must then make
+ * the same sequence of solver calls.  upload / download only touch boxes owned by the calling rank
+ * (other boxes' records in `packed` are ignored / left untouched); afmg_max_abs and afmg_tree_sum
+ * return the global value on every rank.  A peer that stops responding makes the calls of the others
+ * fail with AFMG_ERR_COMM after AFMG_BARRIER_TIMEOUT_S (default 30) seconds instead of hanging. */
+#define AFMG_MAX_RANKS 8
+#define AFMG_COMM_BLOB_BYTES 192
+int afmg_comm_init(afmg_handle* h, int32_t n_ranks, int32_t rank);
+int afmg_comm_export(afmg_handle* h, void* blob /* AFMG_COMM_BLOB_BYTES */);
+int afmg_comm_connect(afmg_handle* h, const void* blobs /* n_ranks * AFMG_COMM_BLOB_BYTES, rank order */);
+/* which rank owns a box (-1 if unknown) */
 int32_t afmg_owner_of_box(const afmg_handle* h, int32_t box_id);
+/* The partition rule itself (pure host function, no handle or GPU needed): cuts has
+ * highest_lvl * (n_ranks + 1) entries; rank r owns positions [cuts[(l-1)*(n_ranks+1)+r],
+ * cuts[(l-1)*(n_ranks+1)+r+1]) of level l's boxes in Morton order of box%ix. */
+int afmg_partition(int32_t n_ranks, int32_t highest_lvl, const int32_t* lvl_counts, int32_t* cuts);
 
 #ifdef __cplusplus
 }

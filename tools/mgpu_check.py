@@ -1,0 +1,101 @@
+"""Multi-GPU parity check, run under torchrun (one process per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/mgpu_check.py
+
+Every rank solves the same problems twice -- with the partitioned multi-GPU handle (boxes split by
+Morton ranges, halos through NVLink peer memory) and with a private single-GPU handle on its own
+device -- and compares its own boxes BIT FOR BIT, plus the residual histories.  Prints one line per
+case and exits non-zero on any mismatch.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from afivo_streamer_b200 import mg as M  # noqa: E402
+from afivo_streamer_b200 import tree as T  # noqa: E402
+from afivo_streamer_b200 import workloads as W  # noqa: E402
+
+
+def bc_mixed(nb, coords):
+    d = (nb - 1) // 2
+    vals = 0.3 * np.sin(3.0 * coords.sum(axis=-1)) + 0.1 * nb
+    if d == coords.shape[-1] - 1:
+        return W.AF_BC_DIRICHLET, vals
+    return W.AF_BC_NEUMANN, vals
+
+
+CASES = {
+    "uniform_nc8_l4": (lambda: T.uniform_tree(3, 8, 8, 4), {}),
+    "corner_nc8_l4": (lambda: T.corner_refined_tree(3, 8, 8, 4), {}),
+    "shell_nc8_l5": (lambda: T.shell_tree(8, 8, 4, 0.35), {}),
+    "uniform_nc16_l3": (lambda: T.uniform_tree(3, 16, 16, 3), {}),
+    "multibox_coarse_nc8": (lambda: T.build_tree(3, 8, [16, 8, 24], 3,
+                                                  lambda l, ix, c: np.linalg.norm(c - 0.4, axis=1) < 0.45), {}),
+    "corner_nc8_l4_corners_mean": (lambda: T.corner_refined_tree(3, 8, 8, 4),
+                                   dict(use_corners=True, helmholtz_lambda=50.0)),
+    "channel_nc8": (lambda: T.channel_tree(8, 8, 6, 3), {}),
+}
+
+
+def solve(tree, bc, ids, rhs, comm, local, opts, n_v=3):
+    mg = M.mg_t(sides_bc=bc, device=local, comm=comm, **opts)
+    M.mg_init(tree, mg)
+    mg.set_cc(M.I_RHS, ids, rhs)
+    hist = []
+    M.mg_fas_fmg(tree, mg, True, False)
+    hist.append(M.af_tree_maxabs_cc(tree, mg, M.I_TMP))
+    for _ in range(n_v):
+        M.mg_fas_vcycle(tree, mg, True)
+        hist.append(M.af_tree_maxabs_cc(tree, mg, M.I_TMP))
+    M.mg_fas_fmg(tree, mg, False, True)
+    all_ids = np.concatenate(tree.lvl_ids).astype(np.int32)
+    owner = np.array([mg.owner_of_box(i) for i in all_ids])
+    out = {v: mg.get_cc(v, all_ids) for v in (M.I_PHI, M.I_TMP)}
+    s = M.af_tree_sum_cc(tree, mg, M.I_PHI)
+    mx = M.af_tree_maxabs_cc(tree, mg, M.I_PHI)
+    M.mg_destroy(mg)
+    return np.array(hist), out, owner, s, mx
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = M.comm_from_torch()
+    bad = 0
+    names = sys.argv[1:] or sorted(CASES)
+    for name in names:
+        mk, opts = CASES[name]
+        tree = mk()
+        bc = W.bc_table(tree, bc_mixed)
+        ids, rhs = W.random_rhs_on_leaves(tree)
+        h1, o1, _, s1, m1 = solve(tree, bc, ids, rhs, None, local, opts)
+        dist.barrier()
+        hN, oN, owner, sN, mN = solve(tree, bc, ids, rhs, comm, local, opts)
+        mine = owner == rank
+        ok = np.array_equal(h1, hN) and s1 == sN and m1 == mN
+        ndiff = 0
+        for v in o1:
+            ndiff += int(np.count_nonzero(o1[v][mine] != oN[v][mine]))
+        ok = ok and ndiff == 0
+        print(f"[rank {rank}] {name}: boxes {tree.n_boxes} own {int(mine.sum())} residuals {hN[0]:.3e}->{hN[-1]:.3e} "
+              f"hist_equal={np.array_equal(h1, hN)} sum_equal={s1 == sN} cells_differing={ndiff} "
+              f"{'OK' if ok else 'MISMATCH'}", flush=True)
+        bad += 0 if ok else 1
+        dist.barrier()
+    t = torch.tensor([bad], device="cuda")
+    dist.all_reduce(t)
+    dist.destroy_process_group()
+    if int(t.item()) != 0:
+        raise SystemExit(f"{int(t.item())} mismatching case(s)")
+    if rank == 0:
+        print("mgpu_check: all cases bit-identical to the single-GPU solve")
+
+
+if __name__ == "__main__":
+    main()
