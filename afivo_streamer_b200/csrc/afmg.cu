@@ -1560,7 +1560,8 @@ int afmg_partition(int32_t n_ranks, int32_t highest_lvl, const int32_t* lvl_coun
       continue;
     }
     const long long groups = n / 8;
-    for (int r = 0; r <= n_ranks; ++r) c[r] = (int32_t)(8 * ((groups * r) / n_ranks));
+    // ceil: levels with fewer sibling groups than ranks fill the low ranks (next to the coarse grid)
+    for (int r = 0; r <= n_ranks; ++r) c[r] = (int32_t)(8 * ((groups * r + n_ranks - 1) / n_ranks));
   }
   return AFMG_OK;
 }

@@ -178,6 +178,17 @@ class mg_t:
     def owner_of_box(self, box_id):
         return int(_lib.lib().afmg_owner_of_box(self._h, int(box_id)))
 
+    def owners(self, ids):
+        f = _lib.lib().afmg_owner_of_box
+        return np.fromiter((f(self._h, int(i)) for i in ids), dtype=np.int32, count=len(ids))
+
+    def own_boxes(self, lvl):
+        """number of boxes of level lvl this rank computes"""
+        ids = self._tree.lvl_ids[lvl - 1]
+        if self.comm is None or self.comm[1] == 1:
+            return len(ids)
+        return int(np.count_nonzero(self.owners(ids) == self.comm[0]))
+
 
 def comm_from_torch(group=None):
     """(rank, world, allgather) on top of an initialised torch.distributed process group (nccl or gloo)."""

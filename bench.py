@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the afivo FAS multigrid hot path on B200 (contract: see the task prompt / DESIGN.md).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload S1|S1r|S3s]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload S3|S1|S1r|S3s|S2]
 
 One step = one standalone ``mg_fas_vcycle(set_residual=.true.)`` (afivo/src/m_af_multigrid.f90:185)
 on the 3D Poisson benchmark tree of BASELINE.json configs[1]: uniform 256^3 grid of 16^3 boxes
@@ -44,6 +44,35 @@ def algo_bytes_gsrb(nc):
     return ALGO_BYTES_PER_CELL_HALFSWEEP + 96.0 / nc
 
 
+def algo_bytes_vcycle(tree):
+    """SURVEY 8(d) byte model of one V-cycle (set_residual=T): leaf-level cells 305 B (nc=16) + 62 B more on
+    cells of boxes that have children; the face-ghost term scales with 1/nc."""
+    nc = tree.nc
+    ghost = 9 * 96.0 / nc
+    leaf_cell = 192 + ghost + 18 + 17 + 24
+    parent_extra = 32 + 24 + 96.0 / nc
+    total = 0.0
+    for l in range(2, tree.highest_lvl + 1):
+        ids = tree.lvl_ids[l - 1]
+        npar = int(np.count_nonzero(tree.has_children(ids)))
+        total += len(ids) * nc ** 3 * leaf_cell + npar * nc ** 3 * parent_extra
+    return total
+
+
+def cpu_baseline(workload):
+    name = CPU_SAMPLE.get(workload, workload)
+    tree, bc, ids, rhs, desc = build_workload(name)
+    n_cpu = 3
+    dt, cores, _ = time_oracle(tree, bc, ids, rhs, n_cpu, 1)
+    cu = cell_updates_vcycle(tree)
+    what = f"{n_cpu} full V-cycles (set_residual + max-norm) with the OpenMP oracle after 1 FMG + 1 warm-up on {name}"
+    if name != workload:
+        what += f" = the same shell-refined octree one level coarser ({tree.n_boxes * tree.nc ** 3 / 1e6:.0f} M cells), " \
+                f"a bounded sample of {workload} (cell-updates/s is size-independent at this scale)"
+    return {"value": cu * n_cpu / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": what,
+            "vcycles_per_s_on_sample": n_cpu / dt}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -57,9 +86,20 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def build_workload(name):
+CPU_SAMPLE = {"S3": "S3s"}  # bounded CPU sample of a workload too large to time on the host in seconds
+
+
+def build_workload(name, want_rhs=True):
     from afivo_streamer_b200 import tree as T
     from afivo_streamer_b200 import workloads as W
+    if not want_rhs:  # only the tree and the boundary conditions (rhs is made on the device)
+        saved = (W.random_rhs_on_leaves, W.constant_rhs_on_leaves)
+        W.random_rhs_on_leaves = lambda tree, seed=12345: (None, None)
+        W.constant_rhs_on_leaves = lambda tree, value=1.0: (None, None)
+        try:
+            return build_workload(name, True)
+        finally:
+            W.random_rhs_on_leaves, W.constant_rhs_on_leaves = saved
     if name == "S1":
         tree = T.uniform_tree(3, 16, 16, 5)
         bc = W.bc_dirichlet_zero(tree)
@@ -75,11 +115,18 @@ def build_workload(name):
         bc = W.bc_field_homogeneous(tree, 1.0)
         ids, rhs = W.random_rhs_on_leaves(tree)
         desc = "S3s: 256^3 uniform + one refined level inside (512^3-equivalent shell-refined octree)"
-    elif name == "S2":
-        tree = T.channel_tree(8, 8, 8, 3)
+    elif name == "S3":
+        tree = T.shell_tree(16, 16, 6)
         bc = W.bc_field_homogeneous(tree, 1.0)
         ids, rhs = W.random_rhs_on_leaves(tree)
-        desc = "S2: standard_3d-like channel-refined tree, nc=8, 8 levels"
+        desc = ("S3: 1024^3-equivalent refined octree (BASELINE.json configs[4]): 512^3 uniform (levels 1-6) + level 7 "
+                "on all but the outermost box layer, 16^3 boxes, 1.04e9 cells, field_bc_homogeneous; it fits one B200 "
+                "and is the >=1e8-cell tree the north-star target is quoted on")
+    elif name == "S2":
+        tree = T.channel_tree(8, 8, 9, 3)
+        bc = W.bc_field_homogeneous(tree, 1.0)
+        ids, rhs = W.random_rhs_on_leaves(tree)
+        desc = "S2: standard_3d-like channel-refined tree, nc=8, 9 levels"
     else:
         raise SystemExit(f"unknown workload {name}")
     return tree, bc, ids, rhs, desc
@@ -164,15 +211,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    tree, bc, ids, rhs, desc = build_workload(args.workload)
+    sample_name = CPU_SAMPLE.get(args.workload, args.workload)
+    tree, bc, ids, rhs, desc = build_workload(sample_name)
+    if sample_name != args.workload:
+        desc = build_workload(args.workload, want_rhs=False)[4] + f" [CPU steps run on the bounded sample {sample_name}: {desc}]"
     steps = max(1, min(args.steps, 10))
     dt, cores, _ = time_oracle(tree, bc, ids, rhs, steps, min(args.warmup, 1))
     cu = cell_updates_vcycle(tree)
     val = cu * steps / dt
-    sample = f"{steps} full V-cycles (set_residual + max-norm) of {args.workload} after 1 FMG"
+    sample = f"{steps} full V-cycles (set_residual + max-norm) of {sample_name} after 1 FMG"
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "n_boxes": tree.n_boxes, "n_cell": tree.nc, "levels": tree.highest_lvl},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -180,6 +230,15 @@ def run_reference(args):
         "note": "CPU oracle (C++/OpenMP port of the reference path); the Fortran reference cannot be built here",
     }
     print(json.dumps(out))
+
+
+def synthetic_rhs_device(torch, leaf_index, box_len):
+    """Deterministic pseudo-random rhs in (-1, 1), a function of the global (leaf index, cell) only, so
+    every GPU count solves the same problem; generated on the device in packed box order."""
+    base = torch.as_tensor(np.asarray(leaf_index, dtype=np.float64) * box_len, device="cuda")
+    idx = base[:, None] + torch.arange(box_len, dtype=torch.float64, device="cuda")[None, :]
+    v = torch.sin(idx * 12.9898) * 43758.5453
+    return ((v - torch.floor(v)) * 2.0 - 1.0).reshape(-1)
 
 
 def run_gpu(args):
@@ -194,28 +253,63 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
+    comm = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    tree, bc, ids, rhs, desc = build_workload(args.workload)
-    mg = M.mg_t(sides_bc=bc, device=local)
-    M.mg_init(tree, mg)
-    nbytes = rhs.size * 8
-    # pinned host buffers for the e2e leg
-    h_rhs = torch.empty(rhs.size, dtype=torch.float64).pin_memory()
-    h_rhs.numpy()[:] = rhs.reshape(-1)
-    h_phi = torch.empty(rhs.size, dtype=torch.float64).pin_memory()
-
-    mg.upload_ptr(M.I_RHS, ids, h_rhs.data_ptr())
-    M.mg_fas_fmg(tree, mg, True, False)  # start-up solve as in field_compute (src/m_field.f90:491-517)
-    res0 = M.af_tree_maxabs_cc(tree, mg, M.I_TMP)
+        comm = M.comm_from_torch()  # plumbing only: exchanges the CUDA IPC handles of the ranks' arrays
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    tree, bc, _, _, desc = build_workload(args.workload, want_rhs=False)
+    mg = M.mg_t(sides_bc=bc, device=local, comm=comm)
+    M.mg_init(tree, mg)
+    # this rank's leaves, in the tree's (level, list) order
+    leaves = np.concatenate([tree.leaves(l) for l in range(1, tree.highest_lvl + 1)]).astype(np.int32)
+    if world > 1:
+        owner = mg.owners(leaves)
+        sel = np.nonzero(owner == rank)[0]
+    else:
+        sel = np.arange(len(leaves))
+    ids = np.ascontiguousarray(leaves[sel])
+    box_len = tree.box_len
+    # rhs: constant 1 for S1 (poisson_benchmark), deterministic pseudo-random otherwise; made on the device
+    chunk = 4096
+    h_rhs = torch.empty(len(ids) * box_len, dtype=torch.float64).pin_memory()
+    h_phi = torch.empty(len(ids) * box_len, dtype=torch.float64).pin_memory()
+    for q0 in range(0, len(ids), chunk):
+        q1 = min(len(ids), q0 + chunk)
+        if args.workload == "S1":
+            d = torch.ones((q1 - q0) * box_len, dtype=torch.float64, device="cuda")
+        else:
+            d = synthetic_rhs_device(torch, sel[q0:q1], box_len)
+        h_rhs[q0 * box_len:q1 * box_len].copy_(d)
+        del d
+    torch.cuda.synchronize()
+    nbytes = h_rhs.numel() * 8
+
+    barrier()
+    mg.upload_ptr(M.I_RHS, ids, h_rhs.data_ptr())
+    barrier()
+    M.mg_fas_fmg(tree, mg, True, False)  # start-up solve as in field_compute (src/m_field.f90:491-517)
+    res0 = M.af_tree_maxabs_cc(tree, mg, M.I_TMP)
+
     # ---- device-resident V-cycles -----------------------------------------------------------
+    barrier()
     mg.fas_vcycle_async(True, 0, args.warmup)
     mg.sync()
     sampler = ClockSampler(local)
@@ -228,20 +322,21 @@ def run_gpu(args):
     ms = mg.last_cycle_ms()
     l1 = mg.kernel_launches()
     barrier()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = allmax(ms)
+    launches = int(allsum(l1 - l0))
     res1 = M.af_tree_maxabs_cc(tree, mg, M.I_TMP)
-    cu = mg.cell_updates(0, False)
-    value = world * cu * args.steps / (ms_max * 1e-3)
+    cu = mg.cell_updates(0, False)  # whole tree, all ranks together
+    value = cu * args.steps / (ms_max * 1e-3)
 
     # ---- FMG timing (secondary figure) ------------------------------------------------------
+    n_fmg = max(2, args.steps // 4)
+    barrier()
     mg.fas_fmg_async(False, True, 1)
     mg.sync()
-    mg.fas_fmg_async(False, True, max(2, args.steps // 4))
+    barrier()
+    mg.fas_fmg_async(False, True, n_fmg)
     mg.sync()
-    fmg_ms = mg.last_cycle_ms() / max(2, args.steps // 4)
+    fmg_ms = allmax(mg.last_cycle_ms()) / n_fmg
     cu_fmg = mg.cell_updates(0, True)
 
     # ---- e2e: host buffers through the C ABI -----------------------------------------------
@@ -252,25 +347,24 @@ def run_gpu(args):
         mg.download_ptr(M.I_PHI, ids, h_phi.data_ptr())
         return r
 
-    for _ in range(min(args.warmup, 3)):
+    big = nbytes > (2 << 30)
+    for _ in range(1 if big else 3):
+        barrier()
         e2e_step()
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = 3 if big else max(3, min(args.steps, 10))
     barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    ev0.record()
     for _ in range(e2e_steps):
         e2e_step()
-    ev1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0  # the C ABI calls are blocking: host wall time == end-to-end time
-    t = torch.tensor([wall], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * cu * e2e_steps / float(t.item())
+    wall_max = allmax(wall)
+    e2e_val = cu * e2e_steps / wall_max
+    h2d_total, d2h_total = allsum(nbytes), allsum(nbytes + 8)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel timing with CUDA events (library profiling mode, no graph) -----------------
+    barrier()
     mg.set_profiling(True)
     nprof = 3
     mg.fas_vcycle_async(True, 0, nprof)
@@ -283,7 +377,7 @@ def run_gpu(args):
     peak, peak_src = peaks()
     roof = None
     if g_calls:
-        cells = tree.n_cells_level(tree.highest_lvl)
+        cells = mg.own_boxes(tree.highest_lvl) * tree.nc ** 3  # finest-level cells this rank sweeps per launch
         per_launch_bytes = algo_bytes_gsrb(tree.nc) * cells
         dur = g_ms / g_calls * 1e-3
         achieved = per_launch_bytes / dur / 1e9
@@ -294,39 +388,40 @@ def run_gpu(args):
                 traffic = json.load(open(tpath)).get(args.workload)
             except Exception:
                 traffic = None
-        roof = {"bound": "hbm", "kernel": "k_gsrb (finest level)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        cyc_bytes = algo_bytes_vcycle(tree)
+        roof = {"bound": "hbm", "kernel": "k_gsrb2 (finest level, rank 0)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": per_launch_bytes, "launch_us": dur * 1e6,
                 "share_of_step": g_ms / total_prof if total_prof else None,
-                "whole_cycle": {"algorithmic_bytes_per_cell_update": 78.0,
-                                "achieved_GBs": value / world * 78.0 / 1e9, "frac": value / world * 78.0 / 1e9 / peak}}
+                "whole_cycle": {"algorithmic_bytes_per_vcycle": cyc_bytes,
+                                "achieved_GBs_per_gpu": cyc_bytes / (ms_max / args.steps * 1e-3) / 1e9 / world,
+                                "frac_per_gpu": cyc_bytes / (ms_max / args.steps * 1e-3) / 1e9 / world / peak}}
 
-    # ---- CPU baseline on the host cores (rank 0, N=1 only) ---------------------------------
+    # ---- CPU baseline on the host cores (rank 0, N=1 only): bounded sample ---------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        n_cpu = 5
-        dt, cores, _ = time_oracle(tree, bc, ids, rhs, n_cpu, 1)
-        cpu = {"value": cu * n_cpu / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n_cpu} full V-cycles of {args.workload} with the OpenMP oracle after 1 FMG + 1 warm-up",
-               "vcycles_per_s": n_cpu / dt}
+        cpu = cpu_baseline(args.workload)
 
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "n_boxes": tree.n_boxes, "n_cell": tree.nc, "levels": tree.highest_lvl,
+                       "cells_all_levels": tree.n_boxes * tree.nc ** 3,
                        "cells_finest": tree.n_cells_level(tree.highest_lvl), "step": "mg_fas_vcycle(set_residual=T)",
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (weak)",
-                       "l2_policy": "working set 655 MB (3 variables) exceeds the 126 MB L2; no flush needed"},
-            "vcycles_per_s": world * args.steps / (ms_max * 1e-3),
+                       "parallelism": "single GPU" if world == 1 else
+                       f"boxes partitioned over {world} GPUs by Morton ranges per level; halos via NVLink peer memory",
+                       "l2_policy": f"working set {3 * tree.n_boxes * box_len * 8 / world / 1e6:.0f} MB per GPU "
+                                    "(3 variables) exceeds the 126 MB L2; no flush needed"},
+            "vcycles_per_s": args.steps / (ms_max * 1e-3),
             "fmg": {"ms": fmg_ms, "cell_updates_per_s": cu_fmg / (fmg_ms * 1e-3)},
             "residual": {"after_fmg": res0, "after_timed_cycles": res1},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 8,
-                    "steps": e2e_steps, "ms_per_step": 1e3 * float(t.item()) / e2e_steps},
-            "gpu_launches": l1 - l0,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
+                    "steps": e2e_steps, "ms_per_step": 1e3 * wall_max / e2e_steps},
+            "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
-            "kernel_profile_ms_per_cycle": {k: v[0] / nprof for k, v in sorted(prof.items())},
+            "kernel_profile_ms_per_cycle_rank0": {k: v[0] / nprof for k, v in sorted(prof.items())},
         }
         print(json.dumps(out))
     M.mg_destroy(mg)
@@ -340,7 +435,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="S1")
+    ap.add_argument("--workload", default="S3")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

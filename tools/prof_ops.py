@@ -11,10 +11,9 @@ from afivo_streamer_b200 import mg as M  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "S1"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-tree, bc, ids, rhs, desc = bench.build_workload(name)
+tree, bc, ids, rhs, desc = bench.build_workload(name, want_rhs=False)  # data values do not change the traffic
 mg = M.mg_t(sides_bc=bc)
 M.mg_init(tree, mg)
-mg.set_cc(M.I_RHS, ids, rhs)
 mg.set_profiling(True)  # no graphs: plain launches
 L = tree.highest_lvl
 for _ in range(reps):
