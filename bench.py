@@ -255,6 +255,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     comm = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of the one-JSON-line stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         comm = M.comm_from_torch()  # plumbing only: exchanges the CUDA IPC handles of the ranks' arrays
 
