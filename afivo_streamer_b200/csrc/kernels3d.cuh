@@ -544,10 +544,25 @@ __global__ void __launch_bounds__(256) k_correct3(DevCtx cx, int slot0, int nbox
   const double* phi = cx.at<BOX>(V_PHI, slot);
   const double* tmp = cx.at<BOX>(V_TMP, slot);
   const int ox = (ch & 1) * H, oy = ((ch >> 1) & 1) * H, oz = ((ch >> 2) & 1) * H;
-  for (int n = t; n < W * W * W; n += 256) {
-    const int a = n % W, b = (n / W) % W, c = n / (W * W);
-    const int q = L::cell(ox + a, oy + b, oz + c);
-    sub[n] = phi[q] - tmp[q];
+  {
+    // all loads of the window are issued before the first use (one round trip instead of NW)
+    constexpr int NW = (W * W * W + 255) / 256;
+    double pv[NW], tv[NW];
+#pragma unroll
+    for (int u = 0; u < NW; ++u) {
+      const int n = t + u * 256;
+      if (n < W * W * W) {
+        const int a = n % W, b = (n / W) % W, c = n / (W * W);
+        const int q = L::cell(ox + a, oy + b, oz + c);
+        pv[u] = __ldg(phi + q);
+        tv[u] = __ldg(tmp + q);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NW; ++u) {
+      const int n = t + u * 256;
+      if (n < W * W * W) sub[n] = pv[u] - tv[u];
+    }
   }
   mbar_wait(&bar, 0);
   __syncthreads();

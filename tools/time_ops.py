@@ -9,10 +9,11 @@ from afivo_streamer_b200 import mg as M  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "S1"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-tree, bc, ids, rhs, desc = bench.build_workload(name)
+tree, bc, ids, rhs, desc = bench.build_workload(name, want_rhs=(name != "S3"))
 mg = M.mg_t(sides_bc=bc)
 M.mg_init(tree, mg)
-mg.set_cc(M.I_RHS, ids, rhs)
+if ids is not None:
+    mg.set_cc(M.I_RHS, ids, rhs)
 M.mg_fas_fmg(tree, mg, True, False)
 mg.fas_vcycle_async(True, 0, 3)
 mg.sync()
