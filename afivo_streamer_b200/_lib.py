@@ -36,6 +36,14 @@ class Opts(C.Structure):
     ]
 
 
+class StencilDesc(C.Structure):
+    _fields_ = [
+        ("box_id", C.c_int32), ("op_stype", C.c_int32), ("prolong_shape", C.c_int32), ("prolong_stype", C.c_int32),
+        ("tag", C.c_int32), ("reserved", C.c_int32), ("op_offset", C.c_int64), ("f_offset", C.c_int64),
+        ("prolong_offset", C.c_int64),
+    ]
+
+
 class TreeDesc(C.Structure):
     _fields_ = [
         ("highest_lvl", C.c_int32), ("highest_id", C.c_int32), ("lvl_counts", C.POINTER(C.c_int32)),
@@ -59,7 +67,7 @@ SYMBOLS = {
     "afmg_set_bc": (C.c_int, [_H, _I, _IP, _IP, _IP, _DP]),
     "afmg_set_helmholtz_lambda": (C.c_int, [_H, C.c_double]),
     "afmg_set_lsf_boundary_value": (C.c_int, [_H, C.c_double]),
-    "afmg_set_lsf_distances": (C.c_int, [_H, _I, _IP, _DP]),
+    "afmg_set_stencils": (C.c_int, [_H, _I, C.c_void_p, _DP, C.c_int64]),
     "afmg_update_operator_stencil": (C.c_int, [_H]),
     "afmg_upload": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
     "afmg_download": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),

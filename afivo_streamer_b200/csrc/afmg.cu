@@ -14,6 +14,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -80,6 +81,21 @@ struct afmg_handle {
   CoarseCtx cs{};
   double *d_b2r = nullptr, *d_Q[3] = {nullptr, nullptr, nullptr}, *d_inveig = nullptr, *d_v0 = nullptr, *d_v1 = nullptr;
   int* d_cs_bix = nullptr;
+
+  // ---- explicit stencils (afmg_set_stencils)
+  bool have_stencils = false;
+  std::vector<unsigned char> h_opk, h_pk, h_rule_flag;
+  std::vector<long long> h_opoff, h_foff, h_poff;
+  std::vector<int> h_tag;
+  unsigned char *d_opk = nullptr, *d_pk = nullptr, *d_rule_flag = nullptr;
+  long long *d_opoff = nullptr, *d_foff = nullptr, *d_poff = nullptr;
+  double* d_stv = nullptr;
+  std::map<int, std::pair<std::vector<double>, std::vector<double>>> l1_st;  // level-1 slot -> (7 per cell, f)
+  std::vector<int> spec_off;  // [L+2] prefix over levels of this rank's boxes with an explicit operator
+  int* d_spec = nullptr;
+  // general coarse solve (explicit stencils on level 1): dense inverse of the BC-folded matrix
+  bool cs_dense = false;
+  double *d_Ainv = nullptr, *d_lsf_fac = nullptr;
 
   // ---- multi-GPU (one process per GPU; peers' arrays mapped through CUDA IPC)
   int nranks = 1, me = 0;
@@ -260,6 +276,8 @@ void set_max_smem(K kernel, size_t smem) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
+inline int nspec(const afmg_handle* h, int l) { return h->have_stencils ? h->spec_off[l + 1] - h->spec_off[l] : 0; }
+
 // Every enq_* below works on the slots of a level this rank owns and ends with a cross-GPU barrier
 // when its results are read, or its inputs overwritten, by kernels of other ranks.
 void enq_gsrb(afmg_handle* h, int l, int redblack) {
@@ -273,6 +291,10 @@ void enq_gsrb(afmg_handle* h, int l, int redblack) {
       auto kern = k_gsrb2<NC, G::BPC, G::KS, G::MINB>;
       kern<<<(r.n + G::BPC - 1) / G::BPC, threads, smem, h->stream>>>(h->cx, r.s0, r.n, redblack & 1, l);
     });
+  }
+  if (const int ns = nspec(h, l)) {  // boxes with an explicit stencil (skipped by the kernel above)
+    Launch L_(h, "gsrb_gen", l);
+    DISPATCH_NC(h, NC, { k_gsrb_gen<NC><<<ns, 256, 0, h->stream>>>(h->cx, h->d_spec + h->spec_off[l], ns, redblack & 1); });
   }
   enq_barrier(h);
 }
@@ -325,6 +347,13 @@ void enq_restrict(afmg_handle* h, int l, int keep_res) {
       constexpr int KS = OpCfg<NC>::KS;
       k_resid3<NC, KS, 1, OpCfg<NC>::RES_MINB><<<r.n, KS * NC * NC / 2, OpCfg<NC>::TILE, h->stream>>>(
           h->cx, r.s0, r.n, nullptr, keep_res);
+    });
+  }
+  if (const int ns = nspec(h, l)) {
+    Launch L_(h, "restrict_gen", l);
+    DISPATCH_NC(h, NC, {
+      k_resid_gen<NC, 1><<<ns, 256, (size_t)2 * Lay3<NC>::NI * sizeof(double), h->stream>>>(
+          h->cx, h->d_spec + h->spec_off[l], ns, nullptr, keep_res);
     });
   }
   enq_barrier(h);
@@ -383,6 +412,15 @@ void enq_residual(afmg_handle* h, int l_lo, int l_hi, bool with_max) {
           h->cx, s0, n, with_max ? h->d_scal : nullptr, 0);
     });
   };
+  if (h->have_stencils) {
+    const int s0 = h->spec_off[l_lo], ns = h->spec_off[l_hi + 1] - s0;
+    if (ns > 0) {
+      Launch L_(h, "residual_gen");
+      DISPATCH_NC(h, NC, {
+        k_resid_gen<NC, 0><<<ns, 256, 0, h->stream>>>(h->cx, h->d_spec + s0, ns, with_max ? h->d_scal : nullptr, 0);
+      });
+    }
+  }
   if (h->nranks == 1) {
     launch(h->lvl_off[l_lo], h->lvl_off[l_hi + 1] - h->lvl_off[l_lo]);
   } else {
@@ -431,15 +469,21 @@ void enq_coarse(afmg_handle* h) {
     DISPATCH_NC(h, NC, { k_cs_gather<NC><<<blocks, 128, 0, h->stream>>>(h->cx, h->cs, nbox1); });
   }
   double *a = h->d_v0, *b = h->d_v1;
-  for (int d = 0; d < 3; ++d) {
+  if (h->cs_dense) {
     Launch L_(h, "coarse");
-    k_cs_apply<<<blocks, 128, 0, h->stream>>>(h->cs, a, b, d, 1, d == 2);
+    k_cs_dense<<<(ntot * 32 + 255) / 256, 256, 0, h->stream>>>(h->cs, a, b);
     std::swap(a, b);
-  }
-  for (int d = 0; d < 3; ++d) {
-    Launch L_(h, "coarse");
-    k_cs_apply<<<blocks, 128, 0, h->stream>>>(h->cs, a, b, d, 0, 0);
-    std::swap(a, b);
+  } else {
+    for (int d = 0; d < 3; ++d) {
+      Launch L_(h, "coarse");
+      k_cs_apply<<<blocks, 128, 0, h->stream>>>(h->cs, a, b, d, 1, d == 2);
+      std::swap(a, b);
+    }
+    for (int d = 0; d < 3; ++d) {
+      Launch L_(h, "coarse");
+      k_cs_apply<<<blocks, 128, 0, h->stream>>>(h->cs, a, b, d, 0, 0);
+      std::swap(a, b);
+    }
   }
   {
     Launch L_(h, "coarse");
@@ -633,9 +677,30 @@ void drop_graphs(afmg_handle* h) {
 
 // coarse_solver_initialize (m_coarse_solver.f90:71-194) + stencil_handle_boundaries (:442-491), with the
 // Hypre solve replaced by the eigen-decomposition of the separable BC-folded operator
+// reference layout v(ncf, i, j, k) -> device planes [m][colour][iidx]
+template <int NC>
+void planes_from_ref(const double* v, int ncf, std::vector<double>& out) {
+  using L = Lay3<NC>;
+  const size_t base = out.size();
+  out.resize(base + (size_t)ncf * 2 * L::NI);
+  for (int k = 1; k <= NC; ++k)
+    for (int j = 1; j <= NC; ++j)
+      for (int i = 1; i <= NC; ++i) {
+        const int col = (i + j + k) & 1, idx = L::iidx((i - 1) >> 1, j, k);
+        const double* src = v + (size_t)ncf * ((i - 1) + NC * ((j - 1) + NC * (k - 1)));
+        for (int m = 0; m < ncf; ++m) out[base + (size_t)(m * 2 + col) * L::NI + idx] = src[m];
+      }
+}
+
+int coarse_setup_dense(afmg_handle* h);
+
 int coarse_setup(afmg_handle* h) {
   const int nc = h->o.n_cell, nc2 = h->nc2;
   const int nbox1 = nlev(h, 1);
+  h->cs_dense = false;
+  h->cs.lsf_fac = nullptr;
+  h->cs.Ainv = nullptr;
+  if (!h->l1_st.empty()) return coarse_setup_dense(h);
   int nb[3], nx[3];
   for (int d = 0; d < 3; ++d) {
     nx[d] = h->o.coarse_grid_size[d];
@@ -740,6 +805,167 @@ int coarse_setup(afmg_handle* h) {
   h->cs.v0 = h->d_v0;
   h->cs.v1 = h->d_v1;
   h->cs.bix = h->d_cs_bix;
+  h->cs_ready = true;
+  return AFMG_OK;
+}
+
+// General coarse solve: level-1 boxes carry explicit stencils (variable eps / level set), so the operator is
+// not separable.  Same matrix as coarse_solver_initialize + stencil_handle_boundaries
+// (m_coarse_solver.f90:71-194, :442-491); its inverse is formed on the host (banded LU, one solve per unit
+// vector, threaded) and applied on the device as a dense mat-vec (k_cs_dense).
+int coarse_setup_dense(afmg_handle* h) {
+  const int nc = h->o.n_cell, nc2 = h->nc2, ncell = nc * nc * nc;
+  const int nbox1 = nlev(h, 1);
+  int nx[3], nbx[3];
+  for (int d = 0; d < 3; ++d) {
+    nx[d] = h->o.coarse_grid_size[d];
+    nbx[d] = nx[d] / nc;
+  }
+  if (nbx[0] * nbx[1] * nbx[2] != nbox1) return h->fail(AFMG_ERR_ARG, "coarse grid size does not match the level-1 boxes");
+  const int n = nx[0] * nx[1] * nx[2];
+  if (n > 8192)
+    return h->fail(AFMG_ERR_UNSUPPORTED, "explicit stencils on a coarse grid of %d cells (dense inverse limited to 8192)", n);
+  for (int d = 0; d < 3; ++d)
+    if (h->o.periodic[d]) return h->fail(AFMG_ERR_UNSUPPORTED, "explicit coarse-grid stencils with periodic boundaries");
+  const int bw = nx[0] * nx[1], ldab = 2 * bw + 1;
+  std::vector<double> ab((size_t)ldab * n, 0.0);  // ab[(bw + r - c) + ldab * c] = A(r, c)
+  std::vector<double> b2r((size_t)nbox1 * 6 * nc2, 0.0), lsf_fac((size_t)nbox1 * ncell, 0.0);
+  bool any_f = false;
+  const int gstride[3] = {1, nx[0], nx[0] * nx[1]};
+  std::vector<double> lvl_c(7);
+  for (int d = 0; d < 3; ++d) lvl_c[1 + 2 * d] = lvl_c[2 + 2 * d] = 1 / (h->o.dr_base[d] * h->o.dr_base[d]);
+  {
+    double sum = 0.0;
+    for (int m = 1; m < 7; ++m) sum = sum + lvl_c[m];
+    lvl_c[0] = -sum - h->o.helmholtz_lambda;
+  }
+  for (int sb = 0; sb < nbox1; ++sb) {
+    std::vector<double> full((size_t)7 * ncell);
+    auto it = h->l1_st.find(sb);
+    if (it != h->l1_st.end()) {
+      full = it->second.first;
+      if (!it->second.second.empty()) {
+        any_f = true;
+        std::copy(it->second.second.begin(), it->second.second.end(), lsf_fac.begin() + (size_t)sb * ncell);
+      }
+    } else {
+      for (int q = 0; q < ncell; ++q)
+        for (int m = 0; m < 7; ++m) full[(size_t)7 * q + m] = lvl_c[m];
+    }
+    auto lin = [&](int i, int j, int k) { return (i - 1) + nc * ((j - 1) + nc * (k - 1)); };
+    for (int f = 0; f < 6; ++f) {  // stencil_handle_boundaries
+      if (h->h_nbr[(size_t)sb * 6 + f] >= 0) continue;
+      const int r = h->h_aux[(size_t)sb * 6 + f];
+      if (!h->bc_set[r]) return h->fail(AFMG_ERR_STATE, "boundary condition not set for level-1 box %d face %d",
+                                        h->slot2id[sb], f + 1);
+      const int ty = h->h_bc_type[r], d = f >> 1, layer = (f & 1) ? nc : 1;
+      const int ta = (d == 0) ? 1 : 0, tb = (d == 2) ? 1 : 2;
+      for (int b = 1; b <= nc; ++b)
+        for (int a = 1; a <= nc; ++a) {
+          int q[3];
+          q[d] = layer;
+          q[ta] = a;
+          q[tb] = b;
+          double* st = &full[(size_t)7 * lin(q[0], q[1], q[2])];
+          double& out = b2r[((size_t)sb * 6 + f) * nc2 + (a - 1) + (b - 1) * nc];
+          if (ty == AFMG_BC_DIRICHLET) {
+            st[0] = st[0] - st[f + 1];
+            out = -2 * st[f + 1];
+          } else if (ty == AFMG_BC_NEUMANN) {
+            st[0] = st[0] + st[f + 1];
+            out = -(st[f + 1] * h->o.dr_base[d]) * ((f & 1) ? 1 : -1);
+          } else {
+            return h->fail(AFMG_ERR_UNSUPPORTED, "coarse grid: unsupported boundary condition %d (reference: error "
+                                                 "stop, m_coarse_solver.f90:486)", ty);
+          }
+          st[f + 1] = 0.0;
+        }
+    }
+    const int* bix = &h->h_ix[(size_t)sb * 3];
+    for (int k = 1; k <= nc; ++k)
+      for (int j = 1; j <= nc; ++j)
+        for (int i = 1; i <= nc; ++i) {
+          const int gi[3] = {(bix[0] - 1) * nc + i - 1, (bix[1] - 1) * nc + j - 1, (bix[2] - 1) * nc + k - 1};
+          const int r = gi[0] + nx[0] * (gi[1] + nx[1] * gi[2]);
+          const double* st = &full[(size_t)7 * lin(i, j, k)];
+          ab[(size_t)bw + (size_t)ldab * r] += st[0];
+          for (int m = 0; m < 6; ++m) {
+            if (st[m + 1] == 0.0) continue;
+            const int d = m >> 1, sgn = (m & 1) ? 1 : -1;
+            const int qd = gi[d] + sgn;
+            if (qd < 0 || qd >= nx[d]) return h->fail(AFMG_ERR_ARG, "coarse matrix: coupling outside the grid");
+            const int c = r + sgn * gstride[d];
+            ab[(size_t)(bw + r - c) + (size_t)ldab * c] += st[m + 1];
+          }
+        }
+  }
+  // banded LU without pivoting (diagonally dominant M-matrix up to sign)
+  for (int c = 0; c < n; ++c) {
+    const double piv = ab[(size_t)bw + (size_t)ldab * c];
+    if (piv == 0.0 || !std::isfinite(piv)) return h->fail(AFMG_ERR_SINGULAR, "coarse-grid operator: zero pivot");
+    const int rmax = std::min(n - 1, c + bw);
+    for (int r = c + 1; r <= rmax; ++r) ab[(size_t)(bw + r - c) + (size_t)ldab * c] /= piv;
+    for (int c2 = c + 1; c2 <= rmax; ++c2) {
+      const double u = ab[(size_t)(bw + c - c2) + (size_t)ldab * c2];
+      if (u == 0.0) continue;
+      for (int r = c + 1; r <= rmax; ++r)
+        ab[(size_t)(bw + r - c2) + (size_t)ldab * c2] -= ab[(size_t)(bw + r - c) + (size_t)ldab * c] * u;
+    }
+  }
+  if (std::fabs(ab[(size_t)bw + (size_t)ldab * (n - 1)]) < 1e-10 * std::fabs(ab[(size_t)bw]))
+    return h->fail(AFMG_ERR_SINGULAR, "coarse-grid operator is singular (all-Neumann without Helmholtz term)");
+  // inverse, column by column (A^-1 e_c), stored row-major
+  std::vector<double> Ainv((size_t)n * n);
+  {
+    const int nthr = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (int tid = 0; tid < nthr; ++tid)
+      pool.emplace_back([&, tid] {
+        std::vector<double> x(n);
+        for (int col = tid; col < n; col += nthr) {
+          std::fill(x.begin(), x.end(), 0.0);
+          x[col] = 1.0;
+          for (int c = col; c < n; ++c) {  // L y = e (unit lower)
+            const double xc = x[c];
+            if (xc == 0.0) continue;
+            const int rmax = std::min(n - 1, c + bw);
+            for (int r = c + 1; r <= rmax; ++r) x[r] -= ab[(size_t)(bw + r - c) + (size_t)ldab * c] * xc;
+          }
+          for (int c = n - 1; c >= 0; --c) {  // U x = y
+            x[c] /= ab[(size_t)bw + (size_t)ldab * c];
+            const double xc = x[c];
+            const int rmin = std::max(0, c - bw);
+            for (int r = rmin; r < c; ++r) x[r] -= ab[(size_t)(bw + r - c) + (size_t)ldab * c] * xc;
+          }
+          for (int r = 0; r < n; ++r) Ainv[(size_t)r * n + col] = x[r];
+        }
+      });
+    for (auto& th : pool) th.join();
+  }
+  std::vector<int> bix((size_t)nbox1 * 3);
+  for (int sb = 0; sb < nbox1; ++sb)
+    for (int d = 0; d < 3; ++d) bix[(size_t)sb * 3 + d] = h->h_ix[(size_t)sb * 3 + d] - 1;
+  int rc;
+  if ((rc = dev_upload(h, &h->d_b2r, b2r))) return rc;
+  if ((rc = dev_upload(h, &h->d_Ainv, Ainv))) return rc;
+  if ((rc = dev_upload(h, &h->d_lsf_fac, lsf_fac))) return rc;
+  if ((rc = dev_upload(h, &h->d_cs_bix, bix))) return rc;
+  std::vector<double> zeros(n, 0.0);
+  if ((rc = dev_upload(h, &h->d_v0, zeros))) return rc;
+  if ((rc = dev_upload(h, &h->d_v1, zeros))) return rc;
+  for (int d = 0; d < 3; ++d) {
+    h->cs.nx[d] = nx[d];
+    h->cs.nb[d] = nbx[d];
+    h->cs.Q[d] = nullptr;
+  }
+  h->cs.b2r = h->d_b2r;
+  h->cs.inv_eig = nullptr;
+  h->cs.v0 = h->d_v0;
+  h->cs.v1 = h->d_v1;
+  h->cs.bix = h->d_cs_bix;
+  h->cs.Ainv = h->d_Ainv;
+  h->cs.lsf_fac = any_f ? h->d_lsf_fac : nullptr;
+  h->cs_dense = true;
   h->cs_ready = true;
   return AFMG_OK;
 }
@@ -852,10 +1078,6 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
     g_create_error = "3D trees must be Cartesian";
     return AFMG_ERR_ARG;
   }
-  if (opts->has_eps) {
-    g_create_error = "variable-coefficient (eps) operators are not supported by this build";
-    return AFMG_ERR_UNSUPPORTED;
-  }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -901,6 +1123,16 @@ int afmg_destroy(afmg_handle* h) {
   close_peers(h);
   cudaFree(h->d_slab);
   cudaFree(h->d_owner);
+  cudaFree(h->d_opk);
+  cudaFree(h->d_pk);
+  cudaFree(h->d_rule_flag);
+  cudaFree(h->d_opoff);
+  cudaFree(h->d_foff);
+  cudaFree(h->d_poff);
+  cudaFree(h->d_stv);
+  cudaFree(h->d_spec);
+  cudaFree(h->d_Ainv);
+  cudaFree(h->d_lsf_fac);
   int* ip[] = {h->d_nbr, h->d_aux, h->d_nmat, h->d_parent, h->d_child0, h->d_coff, h->d_lvl, h->d_rb_slot,
                h->d_rb_face, h->d_stage_slots, h->d_cs_bix};
   for (auto p : ip) cudaFree(p);
@@ -1098,6 +1330,16 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
     if ((rc = dev_upload(h, &h->d_owner, h->h_owner))) return rc;
   }
   h->connected = (h->nranks == 1);
+  // explicit stencils belong to the previous tree: the shim re-ships them (afmg_set_stencils)
+  h->have_stencils = false;
+  h->l1_st.clear();
+  h->spec_off.assign(L + 2, 0);
+  h->cx.opk = nullptr;
+  h->cx.pk = nullptr;
+  h->cx.opoff = h->cx.foff = h->cx.poff = nullptr;
+  h->cx.stv = nullptr;
+  h->cx.rule_flag = nullptr;
+  h->cx.lsf_value = h->o.lsf_boundary_value;
 
   for (int v = 0; v < 4; ++v) h->cx.cc[v] = h->d_cc[v];
   h->cx.nranks = h->nranks;
@@ -1194,14 +1436,126 @@ int afmg_set_helmholtz_lambda(afmg_handle* h, double lambda) {
 
 int afmg_set_lsf_boundary_value(afmg_handle* h, double value) {
   if (!h) return AFMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
   h->o.lsf_boundary_value = value;
+  h->cx.lsf_value = value;  // a kernel argument: cached graphs are stale
+  drop_graphs(h);
+  h->resid_fresh = false;
   return AFMG_OK;
 }
 
-int afmg_set_lsf_distances(afmg_handle* h, int32_t n, const int32_t*, const double*) {
+int afmg_set_stencils(afmg_handle* h, int32_t n, const afmg_stencil_desc* desc, const double* blob, int64_t blob_len) {
   if (!h) return AFMG_ERR_ARG;
-  if (n == 0) return AFMG_OK;
-  return h->fail(AFMG_ERR_UNSUPPORTED, "level-set (electrode) stencils are not supported by this build");
+  if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
+  if (n < 0 || (n > 0 && (!desc || !blob))) return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  drop_graphs(h);
+  h->cs_ready = false;
+  h->resid_fresh = false;
+  const int total = h->nslots, nc = h->o.n_cell, ncell = nc * nc * nc;
+  h->h_opk.assign(total, 0);
+  h->h_pk.assign(total, 0);
+  h->h_opoff.assign(total, 0);
+  h->h_foff.assign(total, -1);
+  h->h_poff.assign(total, 0);
+  h->h_tag.assign(total, 0);
+  h->l1_st.clear();
+  std::vector<double> pool;
+  auto need = [&](int64_t off, int64_t len) { return off >= 0 && off + len <= blob_len; };
+  for (int q = 0; q < n; ++q) {
+    const afmg_stencil_desc& d = desc[q];
+    if (d.box_id < 1 || d.box_id > h->highest_id || h->id2slot[d.box_id] < 0)
+      return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: unknown box %d", d.box_id);
+    const int s = h->id2slot[d.box_id];
+    h->h_tag[s] = d.tag;
+    if (d.op_stype == 1 || d.op_stype == 2) {
+      const int64_t len = d.op_stype == 1 ? 7 : (int64_t)7 * ncell;
+      if (!need(d.op_offset, len)) return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: operator of box %d outside the blob", d.box_id);
+      h->h_opk[s] = (unsigned char)d.op_stype;
+      h->h_opoff[s] = (long long)pool.size();
+      if (d.op_stype == 1) {
+        pool.insert(pool.end(), blob + d.op_offset, blob + d.op_offset + 7);
+        pool.push_back(0.0);
+      } else {
+        DISPATCH_NC(h, NC, planes_from_ref<NC>(blob + d.op_offset, 7, pool));
+      }
+      if (h->h_lvl[s] == 1) {
+        auto& e = h->l1_st[s];
+        e.first.resize((size_t)7 * ncell);
+        for (int c = 0; c < ncell; ++c)
+          for (int m = 0; m < 7; ++m)
+            e.first[(size_t)7 * c + m] = d.op_stype == 1 ? blob[d.op_offset + m] : blob[d.op_offset + (int64_t)7 * c + m];
+      }
+    } else if (d.op_stype != 0) {
+      return h->fail(AFMG_ERR_UNSUPPORTED, "afmg_set_stencils: stencil type %d (sparse stencils are not implemented in the "
+                                           "reference either, m_af_stencil.f90:853)", d.op_stype);
+    }
+    if (d.f_offset >= 0) {
+      if (!need(d.f_offset, ncell)) return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: f of box %d outside the blob", d.box_id);
+      if (h->h_opk[s] == 0) return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: box %d has f but an implicit operator", d.box_id);
+      h->h_foff[s] = (long long)pool.size();
+      DISPATCH_NC(h, NC, planes_from_ref<NC>(blob + d.f_offset, 1, pool));
+      if (h->h_lvl[s] == 1) h->l1_st[s].second.assign(blob + d.f_offset, blob + d.f_offset + ncell);
+    }
+    if (d.prolong_shape != 0) {
+      if (h->h_lvl[s] < 2) return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: level-1 box %d has no prolongation", d.box_id);
+      int kind;
+      if (d.prolong_shape == AFMG_STENCIL_P248 && d.prolong_stype == 1) kind = 1;
+      else if (d.prolong_shape == AFMG_STENCIL_P234 && d.prolong_stype == 1) kind = 2;
+      else if (d.prolong_shape == AFMG_STENCIL_P234 && d.prolong_stype == 2) kind = 3;
+      else return h->fail(AFMG_ERR_UNSUPPORTED, "afmg_set_stencils: prolongation shape %d / type %d of box %d",
+                          d.prolong_shape, d.prolong_stype, d.box_id);
+      const int64_t len = kind == 1 ? 8 : (kind == 2 ? 4 : (int64_t)4 * ncell);
+      if (!need(d.prolong_offset, len))
+        return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: prolongation of box %d outside the blob", d.box_id);
+      h->h_pk[s] = (unsigned char)kind;
+      h->h_poff[s] = (long long)pool.size();
+      if (kind == 3) {
+        DISPATCH_NC(h, NC, planes_from_ref<NC>(blob + d.prolong_offset, 4, pool));
+      } else {
+        pool.insert(pool.end(), blob + d.prolong_offset, blob + d.prolong_offset + len);
+        pool.resize(pool.size() + (8 - len), 0.0);
+      }
+    }
+  }
+  // this rank's boxes with an explicit operator, by level
+  std::vector<int> spec;
+  h->spec_off.assign(h->L + 2, 0);
+  bool any = false;
+  for (int l = 1; l <= h->L; ++l) {
+    h->spec_off[l] = (int)spec.size();
+    const Range r = own(h, l);
+    for (int s = r.s0; s < r.s0 + r.n; ++s)
+      if (h->h_opk[s]) spec.push_back(s);
+  }
+  h->spec_off[h->L + 1] = (int)spec.size();
+  for (int s = 0; s < total; ++s) any = any || h->h_opk[s] || h->h_pk[s] || h->h_tag[s];
+  // refinement-boundary faces of variable-eps boxes use mg_sides_rb_extrap (mg_auto_rb)
+  const int nrules = h->nbc + h->nrb;
+  h->h_rule_flag.assign(std::max(nrules, 1), 0);
+  for (int r = 0; r < h->nrb; ++r)
+    if ((h->h_tag[h->h_rb_slot[r]] & h->o.operator_mask) == AFMG_TAG_VEPS_BOX) h->h_rule_flag[h->nbc + r] = 1;
+  h->have_stencils = any;
+  int rc;
+  if ((rc = dev_upload(h, &h->d_opk, h->h_opk))) return rc;
+  if ((rc = dev_upload(h, &h->d_pk, h->h_pk))) return rc;
+  if ((rc = dev_upload(h, &h->d_opoff, h->h_opoff))) return rc;
+  if ((rc = dev_upload(h, &h->d_foff, h->h_foff))) return rc;
+  if ((rc = dev_upload(h, &h->d_poff, h->h_poff))) return rc;
+  if ((rc = dev_upload(h, &h->d_stv, pool))) return rc;
+  if ((rc = dev_upload(h, &h->d_spec, spec))) return rc;
+  if ((rc = dev_upload(h, &h->d_rule_flag, h->h_rule_flag))) return rc;
+  h->cx.opk = any ? h->d_opk : nullptr;
+  h->cx.pk = any ? h->d_pk : nullptr;
+  h->cx.opoff = h->d_opoff;
+  h->cx.foff = h->d_foff;
+  h->cx.poff = h->d_poff;
+  h->cx.stv = h->d_stv;
+  h->cx.rule_flag = any ? h->d_rule_flag : nullptr;
+  h->cx.lsf_value = h->o.lsf_boundary_value;
+  return AFMG_OK;
 }
 
 int afmg_update_operator_stencil(afmg_handle* h) {

@@ -36,6 +36,17 @@ struct DevCtx {
   int rb_row0;           // first rule row that is a refinement-boundary face
   const double* pcoef;   // [8] constant prolongation coefficients
   int pshape;            // 8 = stencil_prolong_248 (linear), 4 = stencil_prolong_234 (sparse)
+  // ---- per-box stencils shipped by the host (afmg_set_stencils); all null / 0 when every box uses the
+  // implicit constant Laplacian and the default prolongation
+  const unsigned char* opk;  // [nslots] operator: 0 implicit constant (coef), 1 explicit constant, 2 variable
+  const long long* opoff;    // [nslots] offset in stv: 7 doubles (kind 1) or 7 planes [m][colour][NI] (kind 2)
+  const long long* foff;     // [nslots] offset of f [colour][NI] (bc_correction = f * lsf_value), -1: none
+  const unsigned char* pk;   // [nslots] prolongation of a child box: 0 default, 1 constant p248 (8), 2 constant
+                             //          p234 (4), 3 variable p234 (4 planes [m][colour][NI])
+  const long long* poff;     // [nslots] offset in stv
+  const double* stv;         // coefficient pool
+  double lsf_value;          // mg%lsf_boundary_value
+  const unsigned char* rule_flag;  // [nrules] 1: refinement-boundary face of a variable-eps box (mg_sides_rb_extrap)
   // ---- multi-GPU (one process per GPU): every rank allocates the same slot-indexed arrays and
   // maps its peers' arrays through CUDA IPC, so a box is addressed as (owner rank, slot) on every
   // GPU.  nranks == 1: ccr is unused.
@@ -185,7 +196,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // the box are recomputed from their rule (bc_to_gc :173-279; mg_sides_rb m_af_multigrid.f90:383-459).
 // t = index among the TPB threads working on this box.  The z faces are contiguous in shared memory
 // and leave as TMA bulk copies issued by t == 0; the CALLER commits and waits for the bulk group.
-template <int NC, int TPB>
+template <int NC, int TPB, bool SRC_SMEM = true>
 __device__ __forceinline__ void epilogue_faces(const DevCtx& cx, int slot, const double* I0, const double* I1, int mask,
                                                int t) {
   using L = Lay3<NC>;
@@ -202,9 +213,9 @@ __device__ __forceinline__ void epilogue_faces(const DevCtx& cx, int slot, const
       if (nb < 0) continue;
       double* dst = cx.at<BOX>(V_PHI, nb) + c * COL + NI + (f ^ 1) * NF;
       const double* srcz = (f == 4) ? Ic : Ic + (NC - 1) * NC * H;
-      if (!cx.remote(nb)) {
+      if (SRC_SMEM && !cx.remote(nb)) {
         if (t == 0) bulk_s2g(dst, srcz, NF * 8);
-      } else {  // peer GPU: plain coalesced stores over NVLink
+      } else {  // peer GPU (plain coalesced stores over NVLink) or source not in shared memory
         for (int fi = t; fi < NF; fi += TPB) dst[fi] = srcz[fi];
       }
     }
@@ -236,12 +247,15 @@ __device__ __forceinline__ void epilogue_faces(const DevCtx& cx, int slot, const
     const double r0 = rc[0], r1 = rc[1], r2 = rc[2];
     const double* B = cx.rule_B + (size_t)row * L::NC2;
     const int d = f >> 1, hi = f & 1;
+    // mg_sides_rb_extrap (m_af_multigrid.f90:468-621): the second point is the DIAGONAL layer-2 cell
+    const bool diag = cx.rule_flag && cx.rule_flag[row];
     for (int n = t; n < L::NC2; n += TPB) {
       const int a = n % NC + 1, bb = n / NC + 1;
       const int l1 = hi ? NC : 1, l2 = hi ? NC - 1 : 2;
+      const int a2 = diag ? a - 1 + 2 * (a & 1) : a, b2 = diag ? bb - 1 + 2 * (bb & 1) : bb;
       // (x, y, z) of the layer-1 / layer-2 cells: dim d takes the layer, the others (a, bb) in order
       const int px1 = (d == 0) ? l1 : a, py1 = (d == 0) ? a : (d == 1 ? l1 : bb), pz1 = (d == 2) ? l1 : bb;
-      const int px2 = (d == 0) ? l2 : a, py2 = (d == 0) ? a : (d == 1 ? l2 : bb), pz2 = (d == 2) ? l2 : bb;
+      const int px2 = (d == 0) ? l2 : a2, py2 = (d == 0) ? a2 : (d == 1 ? l2 : b2), pz2 = (d == 2) ? l2 : b2;
       const int col1 = (px1 + py1 + pz1) & 1;  // colour of the layer-1 cell; ghost has colour 1 - col1
       const int i1 = L::iidx((px1 - 1) >> 1, py1, pz1), i2 = L::iidx((px2 - 1) >> 1, py2, pz2);
       const double x1 = (col1 ? I1 : I0)[i1];
@@ -266,17 +280,21 @@ __global__ void __launch_bounds__(BPC* KS* NC* NC / 2, MINB) k_gsrb2(DevCtx cx, 
   double* const phi = cx.cc[V_PHI];
   if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
+  // boxes with an explicit (variable-coefficient / level-set) stencil are left to k_gsrb_gen
   if (tid == 0) {
-    mbar_expect_tx(&bar, (uint32_t)(nhere * SBOX * 8));
+    int nload = 0;
+    for (int b = 0; b < nhere; ++b) nload += (cx.opk && cx.opk[slot0 + box0 + b]) ? 0 : 1;
+    mbar_expect_tx(&bar, (uint32_t)(nload * SBOX * 8));
     for (int b = 0; b < nhere; ++b) {
+      if (cx.opk && cx.opk[slot0 + box0 + b]) continue;
       const size_t base = (size_t)(slot0 + box0 + b) * BOX;
       bulk_g2s(smem + b * SBOX, phi + base + (1 - C) * COL, COL * 8, &bar);
       bulk_g2s(smem + b * SBOX + COL, cx.cc[V_RHS] + base + C * COL, NI * 8, &bar);
     }
   }
   const int b = tid / TPB, t = tid % TPB;
-  const bool active = b < nhere;
-  const int slot = slot0 + box0 + (active ? b : 0);
+  const bool active = b < nhere && !(cx.opk && cx.opk[slot0 + box0 + (b < nhere ? b : 0)]);
+  const int slot = slot0 + box0 + (b < nhere ? b : 0);
   const double* const S = smem + b * SBOX;
   double* const R = smem + b * SBOX + COL;
   const double* cf = cx.coef + 8 * lvl;
@@ -401,6 +419,7 @@ __global__ void __launch_bounds__(KS* NC* NC / 2, MINB)
   __shared__ uint64_t bar;
   const int slot = slot0 + blockIdx.x;
   const int t = threadIdx.x;
+  if (cx.opk && cx.opk[slot]) return;  // explicit stencil: k_resid_gen
   if (t == 0) mbar_init(&bar, 1);
   __syncthreads();
   if (t == 0) {
@@ -516,6 +535,139 @@ __global__ void __launch_bounds__(KS* NC* NC / 2, MINB)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Boxes with an explicit operator stencil (afmg_set_stencils: variable-epsilon boxes, level-set /
+// electrode boxes, constant stencils that differ from the level's Laplacian).  They are a small
+// fraction of a tree (near electrodes and dielectrics), are listed per level and handled by the
+// generic kernels below; the fast kernels skip them.
+// ---------------------------------------------------------------------------------------------
+// coefficient m (0 = centre, 1..6 = -x,+x,-y,+y,-z,+z) of the operator at interior cell (col, idx)
+template <int NC>
+__device__ __forceinline__ double op_coef(const DevCtx& cx, int kind, const double* sv, const double* cf, int m, int col,
+                                          int idx) {
+  if (kind == 2) return sv[(size_t)(m * 2 + col) * Lay3<NC>::NI + idx];
+  return kind == 1 ? sv[m] : cf[m];
+}
+
+// L phi at interior cell (i,j,k) of box record `box` (global memory), any stencil kind, including the
+// "- bc_correction" of stencil_apply_357 (m_af_stencil.f90:462-493)
+template <int NC>
+__device__ __forceinline__ double apply_gen(const DevCtx& cx, int kind, const double* sv, const double* fv,
+                                            const double* cf, const double* box, int i, int j, int k) {
+  using L = Lay3<NC>;
+  const int col = (i + j + k) & 1, idx = L::iidx((i - 1) >> 1, j, k);
+  double acc = op_coef<NC>(cx, kind, sv, cf, 0, col, idx) * box[col * L::COL + idx];
+  acc = acc + op_coef<NC>(cx, kind, sv, cf, 1, col, idx) * ldcell<NC>(box, i - 1, j, k);
+  acc = acc + op_coef<NC>(cx, kind, sv, cf, 2, col, idx) * ldcell<NC>(box, i + 1, j, k);
+  acc = acc + op_coef<NC>(cx, kind, sv, cf, 3, col, idx) * ldcell<NC>(box, i, j - 1, k);
+  acc = acc + op_coef<NC>(cx, kind, sv, cf, 4, col, idx) * ldcell<NC>(box, i, j + 1, k);
+  acc = acc + op_coef<NC>(cx, kind, sv, cf, 5, col, idx) * ldcell<NC>(box, i, j, k - 1);
+  acc = acc + op_coef<NC>(cx, kind, sv, cf, 6, col, idx) * ldcell<NC>(box, i, j, k + 1);
+  if (fv) acc = acc - fv[col * L::NI + idx] * cx.lsf_value;
+  return acc;
+}
+
+// k_gsrb_gen: half-sweep of colour C + side ghost fill for the listed boxes (stencil_gsrb_357,
+// m_af_stencil.f90:838-998, all stencil kinds).  With a bc_correction the reference adds it to rhs
+// before the sweep and subtracts it afterwards on ALL interior cells (:856-859, :993-996): the rounding
+// of (rhs + b) - b is reproduced.  One CTA per box; phi of the other colour is read in place (it is not
+// written by this half-sweep).
+template <int NC>
+__global__ void __launch_bounds__(256) k_gsrb_gen(DevCtx cx, const int* list, int nbox, int C) {
+  using L = Lay3<NC>;
+  constexpr int NI = L::NI, COL = L::COL, BOX = L::BOX;
+  const int slot = list[blockIdx.x];
+  const int t = threadIdx.x;
+  const int kind = cx.opk[slot];
+  const double* sv = cx.stv + cx.opoff[slot];
+  const double* fv = cx.foff[slot] >= 0 ? cx.stv + cx.foff[slot] : nullptr;
+  const double* cf = cx.coef + 8 * cx.lvl[slot];
+  double* gbox = cx.cc[V_PHI] + (size_t)slot * BOX;
+  double* grhs = cx.cc[V_RHS] + (size_t)slot * BOX;
+  const double inv_c1 = (kind == 2) ? 0.0 : 1 / op_coef<NC>(cx, kind, sv, cf, 0, 0, 0);
+  for (int n = t; n < 2 * NI; n += 256) {
+    const int col = n / NI, idx = n % NI;
+    double r = grhs[col * COL + idx];
+    double bc = 0.0;
+    if (fv) {
+      bc = fv[col * NI + idx] * cx.lsf_value;
+      r = r + bc;
+    }
+    if (col == C) {
+      int i, j, k;
+      L::uncell(col * COL + idx, i, j, k);
+      double acc = r;
+      acc = acc - op_coef<NC>(cx, kind, sv, cf, 1, col, idx) * ldcell<NC>(gbox, i - 1, j, k);
+      acc = acc - op_coef<NC>(cx, kind, sv, cf, 2, col, idx) * ldcell<NC>(gbox, i + 1, j, k);
+      acc = acc - op_coef<NC>(cx, kind, sv, cf, 3, col, idx) * ldcell<NC>(gbox, i, j - 1, k);
+      acc = acc - op_coef<NC>(cx, kind, sv, cf, 4, col, idx) * ldcell<NC>(gbox, i, j + 1, k);
+      acc = acc - op_coef<NC>(cx, kind, sv, cf, 5, col, idx) * ldcell<NC>(gbox, i, j, k - 1);
+      acc = acc - op_coef<NC>(cx, kind, sv, cf, 6, col, idx) * ldcell<NC>(gbox, i, j, k + 1);
+      gbox[col * COL + idx] = (kind == 2) ? acc / op_coef<NC>(cx, kind, sv, cf, 0, col, idx) : acc * inv_c1;
+    }
+    if (fv) grhs[col * COL + idx] = r - bc;
+  }
+  __syncthreads();
+  epilogue_faces<NC, 256, false>(cx, slot, gbox, gbox + COL, 1 << C, t);
+}
+
+// k_resid_gen: residual_box (MODE 0, + leaf max-norm) or the child part of update_coarse /
+// set_coarse_phi_rhs (MODE 1) for the listed boxes, any stencil kind.  One thread per fine cell; for
+// MODE 1 the residuals go through shared memory and one thread per coarse cell adds the 2x2x2 values in
+// the reference's order (m_af_restrict.f90:120-133).
+template <int NC, int MODE>
+__global__ void __launch_bounds__(256) k_resid_gen(DevCtx cx, const int* list, int nbox, unsigned long long* maxabs_bits,
+                                                   int keep_res) {
+  using L = Lay3<NC>;
+  constexpr int H = L::H, BOX = L::BOX, NI = L::NI, COL = L::COL;
+  extern __shared__ __align__(16) double sres[];  // MODE 1: 2 * NI residuals in interior-block order
+  const int slot = list[blockIdx.x];
+  const int kind = cx.opk[slot];
+  const double* sv = cx.stv + cx.opoff[slot];
+  const double* fv = cx.foff[slot] >= 0 ? cx.stv + cx.foff[slot] : nullptr;
+  const double* cf = cx.coef + 8 * cx.lvl[slot];
+  const double* phi = cx.cc[V_PHI] + (size_t)slot * BOX;
+  const double* rhs = cx.cc[V_RHS] + (size_t)slot * BOX;
+  double* tmp = cx.cc[V_TMP] + (size_t)slot * BOX;
+  double mx = 0.0;
+  for (int n = threadIdx.x; n < 2 * NI; n += blockDim.x) {
+    const int col = n / NI, idx = n - col * NI;
+    const int o = col * COL + idx;
+    int i, j, k;
+    L::uncell(o, i, j, k);
+    const double res = rhs[o] - apply_gen<NC>(cx, kind, sv, fv, cf, phi, i, j, k);
+    if (MODE == 0 || keep_res) tmp[o] = res;
+    if (MODE == 1) sres[n] = res;
+    mx = fmax(mx, fabs(res));
+  }
+  if (MODE == 1) {
+    __syncthreads();
+    const int p = cx.parent[slot], cof = cx.coff[slot];
+    double* ptmp = cx.at<BOX>(V_TMP, p);
+    double* pphi = cx.at<BOX>(V_PHI, p);
+    const int ox = (cof & 1) * H, oy = ((cof >> 1) & 1) * H, oz = ((cof >> 2) & 1) * H;
+    for (int n = threadIdx.x; n < H * H * H; n += blockDim.x) {
+      const int ic = n % H + 1, jc = (n / H) % H + 1, kc = n / (H * H) + 1;
+      double sr = 0.0, sp = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int i = 2 * ic - 1 + (q & 1), j = 2 * jc - 1 + ((q >> 1) & 1), k = 2 * kc - 1 + (q >> 2);
+        const int col = (i + j + k) & 1, idx = L::iidx((i - 1) >> 1, j, k);
+        sr = sr + sres[col * NI + idx];
+        sp = sp + phi[col * COL + idx];
+      }
+      const int qp = L::interior(ox + ic, oy + jc, oz + kc);
+      ptmp[qp] = 0.125 * sr;
+      pphi[qp] = 0.125 * sp;
+    }
+  }
+  if (MODE == 0 && maxabs_bits && cx.child0[slot] < 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.0) atomic_max_nonneg(maxabs_bits, mx);
+  }
+}
+
 // k_correct3: k_correct2 with the child's interior staged in shared memory by TMA (bulk load, update
 // in place, bulk store).  With push != 0 it also performs the side ghost fill of the af_gc_lvl that
 // follows correct_children in the cycle (m_af_multigrid.f90:222, :171): boundary layers of both
@@ -566,10 +718,14 @@ __global__ void __launch_bounds__(256) k_correct3(DevCtx cx, int slot0, int nbox
   }
   mbar_wait(&bar, 0);
   __syncthreads();
+  // prolongation stencil of this child: the default one, or what the host shipped for the box
+  // (constant p248 / p234, or variable p234 for variable-epsilon boxes, m_af_multigrid.f90:1308-1388)
+  const int pkind = cx.pk ? cx.pk[cslot] : 0;
+  const double* pv = pkind ? cx.stv + cx.poff[cslot] : cx.pcoef;
   double pc[8];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) pc[q] = cx.pcoef[q];
-  const int pshape = cx.pshape;
+  for (int q = 0; q < 8; ++q) pc[q] = (pkind == 3 || (pkind == 2 && q >= 4)) ? 0.0 : pv[q];
+  const int pshape = (pkind == 0) ? cx.pshape : (pkind == 1 ? 8 : 4);
   constexpr int TPBX = H * NC;  // threads per k-range
   constexpr int KSX = (256 / TPBX < NC) ? 256 / TPBX : NC;
   constexpr int KLX = NC / KSX;
@@ -600,11 +756,16 @@ __global__ void __launch_bounds__(256) k_correct3(DevCtx cx, int slot0, int nbox
           acc = acc + pc[5] * r12[i2];
           acc = acc + pc[6] * r22[i1];
           acc = acc + pc[7] * r22[i2];
-        } else {
+        } else if (pkind != 3) {
           acc = acc + pc[0] * r11[i1];
           acc = acc + pc[1] * r11[i2];
           acc = acc + pc[2] * r21[i1];
           acc = acc + pc[3] * r12[i1];
+        } else {
+          acc = acc + pv[(size_t)(0 * 2 + c) * NI + idx] * r11[i1];
+          acc = acc + pv[(size_t)(1 * 2 + c) * NI + idx] * r11[i2];
+          acc = acc + pv[(size_t)(2 * 2 + c) * NI + idx] * r21[i1];
+          acc = acc + pv[(size_t)(3 * 2 + c) * NI + idx] * r12[i1];
         }
         Ic[idx] = acc;
       }
@@ -663,12 +824,17 @@ __global__ void __launch_bounds__(256) k_gc2(DevCtx cx, int slot0, int nbox, int
   double* tmp = cx.cc[V_TMP] + (size_t)slot * BOX;
   const double* cf = cx.coef + 8 * cx.lvl[slot];
   const double c1 = cf[0];
+  // explicit stencil of this box, if any (apply_gen only reads interior + face cells: both are staged)
+  const int okind = cx.opk ? cx.opk[slot] : 0;
+  const double* osv = okind ? cx.stv + cx.opoff[slot] : nullptr;
+  const double* ofv = (okind && cx.foff[slot] >= 0) ? cx.stv + cx.foff[slot] : nullptr;
   for (int q = t; q < BOX; q += 256) {
     const bool is_interior = (q < L::OFF_E) && ((q % COL) < NI);
     if (is_interior) {
       int i, j, k;
       L::uncell(q, i, j, k);
-      const double lp = apply357_smem<NC>(smem, cf, c1, i, j, k);
+      const double lp = okind ? apply_gen<NC>(cx, okind, osv, ofv, cf, smem, i, j, k)
+                              : apply357_smem<NC>(smem, cf, c1, i, j, k);
       rhs[q] = lp + tmp[q];
     }
     if (mode == 1) tmp[q] = (q < 2 * COL) ? smem[q] : gphi[q];
@@ -716,6 +882,22 @@ __global__ void k_rb_prepare(DevCtx cx, int r0, int nr, int var) {
     return ldcell<NC>(cb, q[0], q[1], q[2]);
   };
   double* out = cx.rule_B + (size_t)(cx.rb_row0 + r) * L::NC2;
+  if (cx.rule_flag && cx.rule_flag[cx.rb_row0 + r]) {
+    // mg_sides_rb_extrap: the ghost cell first takes the value of the PARENT's cell covering it
+    // (af_gc_prolong_copy, m_af_ghostcell.f90:378-390: i_c1 = offset + (i+1)/2 with i the ghost index)
+    const double* pb = cx.at<L::BOX>(var, p);
+    const int g = (f & 1) ? NC + 1 : 0;
+    const int cod = ((cof >> d) & 1) * H;
+    for (int n = threadIdx.x; n < L::NC2; n += blockDim.x) {
+      const int a = n % NC + 1, b = n / NC + 1;
+      int q[3];
+      q[d] = cod + ((g + 1) >> 1);
+      q[ta] = coa + ((a + 1) >> 1);
+      q[tb] = cob + ((b + 1) >> 1);
+      out[n] = ldcell<NC>(pb, q[0], q[1], q[2]);
+    }
+    return;
+  }
   for (int n = threadIdx.x; n < L::NC2; n += blockDim.x) {
     const int a = n % NC + 1, b = n / NC + 1;
     const int ia = (a + 1) >> 1, ib = (b + 1) >> 1;
@@ -755,6 +937,10 @@ __device__ void gc_sides(const DevCtx& cx, int slot, int var) {
       q[d] = hi ? NC : 1;
       const double x1 = ldcell<NC>(box, q[0], q[1], q[2]);
       q[d] = hi ? NC - 1 : 2;
+      if (cx.rule_flag && cx.rule_flag[row]) {  // mg_sides_rb_extrap: diagonal second point
+        q[ta] = a - 1 + 2 * (a & 1);
+        q[tb] = b - 1 + 2 * (b & 1);
+      }
       const double x2 = ldcell<NC>(box, q[0], q[1], q[2]);
       v = (rc[0] * B + rc[1] * x1) + rc[2] * x2;
     }
@@ -813,11 +999,8 @@ __device__ void gc_edges_corners(const DevCtx& cx, int slot, int var) {
   }
 }
 
-// k_gc: af_gc_lvl (m_af_ghostcell.f90:49-61) for boxes [slot0, slot0+nbox), optionally followed, for
-// boxes that have children, by the parent part of update_coarse (m_af_multigrid.f90:724-737):
-//   rhs = L(phi) + tmp (interior), tmp = phi (full box) when mode == 1
-//   rhs = L(phi) + tmp only (set_coarse_phi_rhs :769-774) when mode == 2
-// One CTA per box.
+// k_gc: af_gc_lvl (m_af_ghostcell.f90:49-61) for boxes [slot0, slot0+nbox).  One CTA per box.  (The
+// variant that also performs the parent part of update_coarse is k_gc2.)
 template <int NC>
 __global__ void k_gc(DevCtx cx, int slot0, int nbox, int var, int corners, int mode) {
   using L = Lay3<NC>;
@@ -827,23 +1010,6 @@ __global__ void k_gc(DevCtx cx, int slot0, int nbox, int var, int corners, int m
   if (corners) {
     __syncthreads();
     gc_edges_corners<NC>(cx, slot, var);
-  }
-  if (mode == 0 || cx.child0[slot] < 0) return;
-  __syncthreads();
-  const double* phi = cx.cc[V_PHI] + (size_t)slot * L::BOX;
-  double* rhs = cx.cc[V_RHS] + (size_t)slot * L::BOX;
-  double* tmp = cx.cc[V_TMP] + (size_t)slot * L::BOX;
-  const double* cf = cx.coef + 8 * cx.lvl[slot];
-  const double c1 = cf[0];
-  for (int q = threadIdx.x; q < L::BOX; q += blockDim.x) {
-    const bool is_interior = (q < L::OFF_E) && ((q % L::COL) < L::NI);
-    if (is_interior) {
-      int i, j, k;
-      L::uncell(q, i, j, k);
-      const double lp = apply357<NC>(phi, cf, c1, i, j, k);
-      rhs[q] = lp + tmp[q];
-    }
-    if (mode == 1) tmp[q] = phi[q];
   }
 }
 
@@ -992,6 +1158,8 @@ struct CoarseCtx {
   const double* inv_eig;  // [n] 1 / (lx(i)+ly(j)+lz(k) - lambda)
   double* v0;           // [n] work vectors
   double* v1;
+  const double* lsf_fac;  // [nbox1][nc^3] stencil%f of level-1 boxes (rhs += f * lsf_boundary_value), or null
+  const double* Ainv;     // [n][n] dense inverse (general path: explicit stencils on level 1), or null
 };
 
 // coarse_solver_set_rhs_phi (m_coarse_solver.f90:286-338): b = rhs + bc_to_rhs * bc_val per face
@@ -1016,6 +1184,8 @@ __global__ void k_cs_gather(DevCtx cx, CoarseCtx cs, int nbox1) {
     const int row = cx.aux[bx * 6 + f];
     t = t + cs.b2r[((size_t)bx * 6 + f) * L::NC2 + fi] * cx.rule_B[(size_t)row * L::NC2 + fi];
   }
+  // level-set boundary inside the coarse grid (m_coarse_solver.f90:320-324)
+  if (cs.lsf_fac) t = t + cs.lsf_fac[(size_t)bx * ncell + r] * cx.lsf_value;
   const int gi = cs.bix[bx * 3] * NC + i - 1, gj = cs.bix[bx * 3 + 1] * NC + j - 1, gk = cs.bix[bx * 3 + 2] * NC + k - 1;
   cs.v0[gi + cs.nx[0] * (gj + cs.nx[1] * gk)] = t;
 }
@@ -1038,6 +1208,19 @@ __global__ void k_cs_apply(CoarseCtx cs, const double* in, double* out, int d, i
   }
   if (scale) s = s * cs.inv_eig[n];
   out[n] = s;
+}
+
+// general path: x = A^-1 b with the dense inverse computed on the host at set-up; one warp per row
+__global__ void k_cs_dense(CoarseCtx cs, const double* in, double* out) {
+  const int n = cs.nx[0] * cs.nx[1] * cs.nx[2];
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const double* a = cs.Ainv + (size_t)row * n;
+  double s = 0.0;
+  for (int c = lane; c < n; c += 32) s = s + a[c] * in[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[row] = s;
 }
 
 // coarse_solver_get_phi (m_coarse_solver.f90:341-358)

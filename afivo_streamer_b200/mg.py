@@ -105,6 +105,44 @@ class mg_t:
         ids = np.ascontiguousarray(ids, np.int32)
         self._check(_lib.lib().afmg_download(self._h, var, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)), host_ptr))
 
+    def set_stencils(self, entries):
+        """Ship per-box operator / prolongation stencils (what mg_set_operators_lvl stored in
+        box%stencils, afivo/src/m_af_multigrid.f90:1147-1185).  entries: iterable of dicts with keys
+        box_id, tag, op=(stype, coeff) or None, f=array or None, prolong=(stype, shape, coeff) or None;
+        coeff in the reference layout (c(n) or v(n, cells) with n fastest)."""
+        self._need_init()
+        entries = list(entries)
+        descs = (_lib.StencilDesc * max(1, len(entries)))()
+        blob = []
+        off = 0
+
+        def put(a):
+            nonlocal off
+            a = np.ascontiguousarray(a, np.float64).reshape(-1)
+            blob.append(a)
+            off += a.size
+            return off - a.size
+
+        for d, e in zip(descs, entries):
+            d.box_id, d.tag = int(e["box_id"]), int(e.get("tag", 0))
+            d.op_stype, d.f_offset, d.prolong_shape = 0, -1, 0
+            if e.get("op") is not None:
+                d.op_stype = int(e["op"][0])
+                d.op_offset = put(e["op"][1])
+            if e.get("f") is not None:
+                d.f_offset = put(e["f"])
+            if e.get("prolong") is not None:
+                d.prolong_stype, d.prolong_shape = int(e["prolong"][0]), int(e["prolong"][1])
+                d.prolong_offset = put(e["prolong"][2])
+        flat = np.concatenate(blob) if blob else np.zeros(1)
+        self._check(_lib.lib().afmg_set_stencils(self._h, len(entries), C.byref(descs),
+                                                 flat.ctypes.data_as(C.POINTER(C.c_double)), flat.size))
+
+    def set_lsf_boundary_value(self, value):
+        self.lsf_boundary_value = float(value)
+        if self.initialized:
+            self._check(_lib.lib().afmg_set_lsf_boundary_value(self._h, float(value)))
+
     def clear(self, var):
         self._need_init()
         self._check(_lib.lib().afmg_clear(self._h, var))

@@ -124,13 +124,42 @@ int afmg_set_bc(afmg_handle* h, int32_t n_faces, const int32_t* box_id, const in
  * members that enter the stencils */
 int afmg_set_helmholtz_lambda(afmg_handle* h, double lambda);
 int afmg_set_lsf_boundary_value(afmg_handle* h, double value);
-/* Level-set distances all_distances(2*ndim, nc^ndim) (store_lsf_distance_matrix,
- * m_af_multigrid.f90:977-1097) for the n boxes that contain an electrode boundary; the host
- * evaluates mg%lsf.  Boxes not listed have no boundary.  n = 0 clears. */
-int afmg_set_lsf_distances(afmg_handle* h, int32_t n, const int32_t* box_id, const double* dd);
-/* (Re)build the operator and prolongation stencils after eps (AFMG_EPS data), lsf distances or
- * lambda changed: mg_update_operator_stencil(tree, mg, new_lsf, new_eps). */
+/* Rebuild the implicit constant stencils and the coarse-grid factorisation after lambda changed
+ * (mg_update_operator_stencil, m_af_multigrid.f90:1188-1214); explicit stencils are re-shipped with
+ * afmg_set_stencils by the shim. */
 int afmg_update_operator_stencil(afmg_handle* h);
+
+/* ---- operator / prolongation stencils as data.  The builders stay on the host in the reference
+ * (mg_set_operators_lvl m_af_multigrid.f90:1147-1185: mg_box_lpld_stencil :1493-1532 for variable eps,
+ * mg_box_lsf_stencil :1782-1854 for level-set boxes, mg_box_prolong_eps_stencil :1308-1388; they call user
+ * callbacks), so the shim ships what they stored in box%stencils (stencil_t, m_af_types.f90:260-282) for
+ * every box whose operator is not the plain constant Laplacian or whose prolongation is not the default:
+ *   op_stype       0 = implicit (library derives 1/dr^2, lambda), 1 = stencil_constant: c(7) at op_offset,
+ *                  2 = stencil_variable: v(7, nc, nc, nc) at op_offset (first index fastest)
+ *   f_offset       >= 0: stencil%f (nc^3) -- the library applies bc_correction = f * lsf_boundary_value
+ *                  (m_af_multigrid.f90:1171-1174); -1: none
+ *   prolong_shape  0 = default (mg%prolongation_type), AFMG_STENCIL_P248 (8 coefficients) or
+ *                  AFMG_STENCIL_P234 (4); prolong_stype 1 = constant c(n) / 2 = variable v(4, nc, nc, nc)
+ *   tag            box%tag (mg_lsf_box = 1, mg_veps_box = 2, mg_ceps_box = 4, m_af_types.f90:497-508); boxes
+ *                  with iand(tag, operator_mask) == mg_veps_box get mg_sides_rb_extrap ghost cells on
+ *                  refinement boundaries (mg_auto_rb, :926-940)
+ * Offsets count doubles inside coeff_blob.  The call replaces all previously shipped stencils; boxes
+ * not listed use the implicit Laplacian and the default prolongation.  n = 0 clears. */
+enum { AFMG_STENCIL_P234 = 2, AFMG_STENCIL_P248 = 3 };
+enum { AFMG_TAG_LSF_BOX = 1, AFMG_TAG_VEPS_BOX = 2, AFMG_TAG_CEPS_BOX = 4 };
+typedef struct afmg_stencil_desc {
+  int32_t box_id;
+  int32_t op_stype;
+  int32_t prolong_shape;
+  int32_t prolong_stype;
+  int32_t tag;
+  int32_t reserved;
+  int64_t op_offset;
+  int64_t f_offset;
+  int64_t prolong_offset;
+} afmg_stencil_desc;
+int afmg_set_stencils(afmg_handle* h, int32_t n, const afmg_stencil_desc* desc, const double* coeff_blob,
+                      int64_t blob_len);
 
 /* ---- cell data: box%cc(:, :, :, iv) of n boxes, (nc+2)^ndim doubles each, packed in the order of
  * `box_id` (m_af_types.f90:302).  upload/download take host memory; the _device variants take

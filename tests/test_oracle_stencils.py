@@ -1,0 +1,108 @@
+"""CPU: known answers for the oracle's variable-coefficient and level-set paths (SURVEY 8 rows a9, a17,
+a22, a25), which the GPU parity tests of tests/test_gpu_stencils.py rely on."""
+import numpy as np
+
+from afivo_streamer_b200 import mg as M
+from afivo_streamer_b200 import tree as T
+from afivo_streamer_b200 import workloads as W
+from oracle.oracle import Oracle
+
+from util import all_ids, bc_mixed
+
+
+def solve(tree, eps=None, lsf_dd=None, lsf_value=0.0, n_v=3):
+    orc = Oracle(tree, with_eps=eps is not None, lsf_boundary_value=lsf_value)
+    orc.set_bc(W.bc_table(tree, bc_mixed))
+    ids = all_ids(tree)
+    if eps is not None:
+        orc.set_cc(M.I_EPS, ids, eps(W.cell_centres(tree, ids, ghosts=True)))
+    if lsf_dd is not None:
+        orc.set_lsf_distances(*lsf_dd)
+    orc.mg_init()
+    i, r = W.random_rhs_on_leaves(tree)
+    orc.set_cc(M.I_RHS, i, r)
+    orc.fas_fmg(True, False)
+    for _ in range(n_v):
+        orc.fas_vcycle(True)
+    return orc, orc.get_cc(M.I_PHI, ids)
+
+
+def test_eps_one_is_the_plain_laplacian_bit_for_bit():
+    tree = T.corner_refined_tree(3, 8, 8, 3)
+    o0, p0 = solve(tree)
+    o1, p1 = solve(tree, eps=lambda r: np.ones(r.shape[:-1]))
+    assert {o1.tag(b) for b in all_ids(tree)} == {0}  # mg_normal_box (m_af_multigrid.f90:1100-1145)
+    assert np.array_equal(p0, p1)
+
+
+def test_constant_eps_box_tags_and_stencil():
+    tree = T.uniform_tree(3, 8, 8, 2)
+    orc, _ = solve(tree, eps=lambda r: np.full(r.shape[:-1], 2.0), n_v=0)
+    for b in all_ids(tree):
+        assert orc.tag(b) == 4  # mg_ceps_box
+        stype, c, f, _ = orc.op_stencil(b)
+        dr = tree.dr[b, 0]
+        assert stype == 1 and f is None  # constant after stencil_try_constant
+        np.testing.assert_allclose(c[1:], 2.0 / dr ** 2, rtol=1e-15)  # harmonic mean of equal eps
+        np.testing.assert_allclose(c[0], -12.0 / dr ** 2, rtol=1e-15)
+
+
+def test_variable_eps_harmonic_mean_and_prolongation():
+    tree = T.uniform_tree(3, 8, 8, 2)
+    eps = lambda r: 1.0 + r[..., 0]
+    orc, _ = solve(tree, eps=eps, n_v=0)
+    b = int(tree.lvl_ids[1][0])
+    assert orc.tag(b) == 2  # mg_veps_box
+    stype, v, f, _ = orc.op_stencil(b)
+    assert stype == 2 and f is None
+    e = eps(W.cell_centres(tree, np.array([b]), ghosts=True))[0]
+    dr = tree.dr[b, 0]
+    a0, am, ap = e[3, 3, 3], e[3, 3, 2], e[3, 3, 4]  # cell (i,j,k) = (3,3,3)
+    cell = (3 - 1) + 8 * ((3 - 1) + 8 * (3 - 1))
+    np.testing.assert_allclose(v[cell, 1], 2 * a0 * am / (a0 + am) / dr ** 2, rtol=1e-14)  # mg_box_lpld_stencil :1493-1532
+    np.testing.assert_allclose(v[cell, 2], 2 * a0 * ap / (a0 + ap) / dr ** 2, rtol=1e-14)
+    np.testing.assert_allclose(v[cell, 0], -v[cell, 1:].sum(), rtol=1e-14)
+    pst, shape, pv = orc.prolong_stencil(b)
+    assert shape == 2 and pst == 2  # variable af_stencil_p234 (mg_box_prolong_eps_stencil :1308-1388)
+    np.testing.assert_allclose(pv.sum(axis=1), 1.0, rtol=1e-13)  # weights of an interpolation
+
+
+def test_lsf_stencil_coefficients():
+    tree = T.uniform_tree(3, 8, 8, 1)
+    dd = np.ones((1, 8 ** 3, 6))
+    cell = (4 - 1) + 8 * ((4 - 1) + 8 * (4 - 1))
+    dd[0, cell, 1] = 0.25  # boundary at a quarter of the way to the +x neighbour
+    orc, _ = solve(tree, lsf_dd=(np.array([1], np.int32), dd.reshape(1, -1)), lsf_value=2.0, n_v=0)
+    assert orc.tag(1) == 1  # mg_lsf_box
+    stype, v, f, _ = orc.op_stencil(1)
+    dr2 = tree.dr[1, 0] ** 2
+    # mg_box_lsf_stencil (:1782-1854): 1 / (0.5 dr^2 (d- + d+) d+-), boundary coupling moved into f
+    cm = 1 / (0.5 * dr2 * 1.25 * 1.0)
+    cp = 1 / (0.5 * dr2 * 1.25 * 0.25)
+    np.testing.assert_allclose(v[cell, 1], cm, rtol=1e-14)
+    assert v[cell, 2] == 0.0
+    np.testing.assert_allclose(f[cell], -cp, rtol=1e-14)
+    np.testing.assert_allclose(v[cell, 0], -(cm + cp + 4 / dr2), rtol=1e-14)
+    other = 0
+    np.testing.assert_allclose(v[other, 1:], 1 / dr2, rtol=1e-14)
+    assert f[other] == 0.0
+
+
+def test_constant_eps_scales_the_solution():
+    tree = T.uniform_tree(3, 8, 8, 3)
+    # Dirichlet-0 / Neumann-0 problem: eps * laplace(phi) = rhs  =>  phi(eps=2) = phi(eps=1) / 2
+    def run(eps):
+        orc = Oracle(tree, with_eps=eps is not None)
+        orc.set_bc(W.bc_field_homogeneous(tree, 0.0))
+        ids = all_ids(tree)
+        if eps is not None:
+            orc.set_cc(M.I_EPS, ids, np.full((len(ids),) + (10,) * 3, eps))
+        orc.mg_init()
+        i, r = W.random_rhs_on_leaves(tree)
+        orc.set_cc(M.I_RHS, i, r)
+        orc.fas_fmg(True, False)
+        for _ in range(8):
+            orc.fas_vcycle(True)
+        return orc.get_cc(M.I_PHI, ids)
+    p1, p2 = run(None), run(2.0)
+    assert np.max(np.abs(p1 - 2 * p2)) <= 1e-9 * np.max(np.abs(p1))

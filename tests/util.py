@@ -79,3 +79,22 @@ TREES = {
                                                 lambda l, ix, c: np.linalg.norm(c - 0.4, axis=1) < 0.45),
     "permuted_ids": lambda: T.corner_refined_tree(3, 8, 8, 3).permuted_ids(np.random.default_rng(7)),
 }
+
+
+def stencils_from_oracle(tree, orc):
+    """What the Fortran shim ships with afmg_set_stencils: the stencils mg_set_operators_lvl stored for
+    every box that is not a plain constant-Laplacian box (the oracle's builders stand in for the
+    reference's host-side ones)."""
+    out = []
+    for lvl in range(1, tree.highest_lvl + 1):
+        for bid in tree.lvl_ids[lvl - 1]:
+            tag = orc.tag(bid)
+            if tag == 0:
+                continue
+            stype, coeff, f, _ = orc.op_stencil(bid)
+            e = dict(box_id=int(bid), tag=tag, op=(stype, coeff), f=f)
+            if lvl > 1:
+                pst, pshape, pco = orc.prolong_stencil(bid)
+                e["prolong"] = (pst, pshape, pco)
+            out.append(e)
+    return out

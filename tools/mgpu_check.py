@@ -39,12 +39,39 @@ CASES = {
     "corner_nc8_l4_corners_mean": (lambda: T.corner_refined_tree(3, 8, 8, 4),
                                    dict(use_corners=True, helmholtz_lambda=50.0)),
     "channel_nc8": (lambda: T.channel_tree(8, 8, 6, 3), {}),
+    "eps_smooth_corner_nc8": (lambda: T.corner_refined_tree(3, 8, 8, 4), dict(stencils=("eps", "eps_smooth", 0.0))),
+    "eps_jump_uniform_nc8": (lambda: T.uniform_tree(3, 8, 8, 4), dict(stencils=("eps", "eps_jump", 0.0))),
+    "lsf_sphere_uniform_nc8": (lambda: T.uniform_tree(3, 8, 8, 4),
+                               dict(stencils=("lsf", "lsf_sphere", 1.5), lsf_boundary_value=1.5)),
 }
 
 
+def explicit_stencils(tree, bc, spec):
+    """Stencils for variable-eps / level-set cases, built by the oracle (test infrastructure standing in
+    for the reference's host-side builders) exactly as tests/test_gpu_stencils.py does."""
+    import test_gpu_stencils as TS
+    from oracle.oracle import Oracle
+    from util import all_ids, stencils_from_oracle
+    kind, fn, val = spec
+    orc = Oracle(tree, with_eps=(kind == "eps"), lsf_boundary_value=val)
+    orc.set_bc(bc)
+    ids = all_ids(tree)
+    if kind == "eps":
+        orc.set_cc(M.I_EPS, ids, getattr(TS, fn)(W.cell_centres(tree, ids, ghosts=True)))
+    else:
+        lids, dd = TS.lsf_distances(tree, getattr(TS, fn))
+        orc.set_lsf_distances(lids, dd)
+    orc.mg_init()
+    return stencils_from_oracle(tree, orc)
+
+
 def solve(tree, bc, ids, rhs, comm, local, opts, n_v=3):
+    opts = dict(opts)
+    spec = opts.pop("stencils", None)
     mg = M.mg_t(sides_bc=bc, device=local, comm=comm, **opts)
     M.mg_init(tree, mg)
+    if spec is not None:
+        mg.set_stencils(explicit_stencils(tree, bc, spec))
     mg.set_cc(M.I_RHS, ids, rhs)
     hist = []
     M.mg_fas_fmg(tree, mg, True, False)
