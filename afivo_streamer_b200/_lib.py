@@ -39,7 +39,7 @@ class Opts(C.Structure):
 class StencilDesc(C.Structure):
     _fields_ = [
         ("box_id", C.c_int32), ("op_stype", C.c_int32), ("prolong_shape", C.c_int32), ("prolong_stype", C.c_int32),
-        ("tag", C.c_int32), ("reserved", C.c_int32), ("op_offset", C.c_int64), ("f_offset", C.c_int64),
+        ("tag", C.c_int32), ("cylindrical_gradient", C.c_int32), ("op_offset", C.c_int64), ("f_offset", C.c_int64),
         ("prolong_offset", C.c_int64),
     ]
 

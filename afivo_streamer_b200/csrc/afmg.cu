@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/afmg.h"
+#include "kernels2d.cuh"
 #include "kernels3d.cuh"
 
 using namespace afmg;
@@ -39,8 +40,13 @@ struct ProfEntry {
 
 }  // namespace
 
+namespace {
+struct S2State;  // 2D solver state (afmg2d.inc)
+}
+
 struct afmg_handle {
   afmg_opts o{};
+  S2State* s2 = nullptr;
   std::string err;
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -970,8 +976,11 @@ int coarse_setup_dense(afmg_handle* h) {
   return AFMG_OK;
 }
 
+int s2_ensure_ready(afmg_handle* h);
+
 int ensure_ready(afmg_handle* h) {
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
+  if (h->o.ndim == 2) return s2_ensure_ready(h);
   for (int r = 0; r < h->nbc; ++r)
     if (!h->bc_set[r])
       return h->fail(AFMG_ERR_STATE, "boundary condition not set for box %d face %d (call afmg_set_bc)",
@@ -1051,6 +1060,8 @@ int finish_op(afmg_handle* h) {
   return AFMG_OK;
 }
 
+#include "afmg2d.inc"
+
 }  // namespace
 
 // =================================================================================================
@@ -1066,16 +1077,24 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
     return AFMG_ERR_ARG;
   }
   *out = nullptr;
-  if (opts->ndim != 3) {
-    g_create_error = "only ndim = 3 is supported by this build";
+  if (opts->ndim != 2 && opts->ndim != 3) {
+    g_create_error = "ndim must be 2 or 3 (1D trees are not part of the accelerated path)";
     return AFMG_ERR_UNSUPPORTED;
   }
-  if (opts->n_cell != 4 && opts->n_cell != 8 && opts->n_cell != 16) {
-    g_create_error = "n_cell must be 4, 8 or 16";
+  if (opts->ndim == 3 && opts->n_cell != 4 && opts->n_cell != 8 && opts->n_cell != 16) {
+    g_create_error = "n_cell must be 4, 8 or 16 in 3D";
     return AFMG_ERR_UNSUPPORTED;
   }
-  if (opts->coord_t != AFMG_XYZ) {
+  if (opts->ndim == 2 && opts->n_cell != 4 && opts->n_cell != 8 && opts->n_cell != 16 && opts->n_cell != 32) {
+    g_create_error = "n_cell must be 4, 8, 16 or 32 in 2D";
+    return AFMG_ERR_UNSUPPORTED;
+  }
+  if (opts->ndim == 3 && opts->coord_t != AFMG_XYZ) {
     g_create_error = "3D trees must be Cartesian";
+    return AFMG_ERR_ARG;
+  }
+  if (opts->coord_t != AFMG_XYZ && opts->coord_t != AFMG_CYL) {
+    g_create_error = "unknown coordinate system";
     return AFMG_ERR_ARG;
   }
   int ndev = 0;
@@ -1108,9 +1127,9 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
     delete h;
     return AFMG_ERR_CUDA;
   }
-  configure_kernels(h);
+  if (opts->ndim == 3) configure_kernels(h);
   h->nc2 = opts->n_cell * opts->n_cell;
-  h->box_len = (opts->n_cell + 2) * (opts->n_cell + 2) * (opts->n_cell + 2);
+  h->box_len = (opts->n_cell + 2) * (opts->n_cell + 2) * (opts->ndim == 3 ? opts->n_cell + 2 : 1);
   *out = h;
   return AFMG_OK;
 }
@@ -1120,6 +1139,7 @@ int afmg_destroy(afmg_handle* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   drop_graphs(h);
+  s2_free(h);
   close_peers(h);
   cudaFree(h->d_slab);
   cudaFree(h->d_owner);
@@ -1157,6 +1177,7 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
   h->resid_fresh = false;
   const int L = t->highest_lvl, N = t->highest_id;
   if (L < 1 || N < 1) return h->fail(AFMG_ERR_ARG, "empty tree");
+  if (h->o.ndim == 2) return s2_set_tree(h, t);
   int total = 0;
   for (int l = 0; l < L; ++l) total += t->lvl_counts[l];
   h->L = L;
@@ -1374,6 +1395,7 @@ int afmg_set_bc(afmg_handle* h, int32_t n_faces, const int32_t* box_id, const in
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
+  if (h->o.ndim == 2) return s2_set_bc(h, n_faces, box_id, nb, bc_type, bc_val);
   const int nc2 = h->nc2;
   std::vector<double> rc3((size_t)3);
   bool types_changed = false;
@@ -1430,7 +1452,8 @@ int afmg_set_helmholtz_lambda(afmg_handle* h, double lambda) {
   CK(cudaStreamSynchronize(h->stream));
   h->o.helmholtz_lambda = lambda;
   h->cs_ready = false;
-  if (h->have_tree) return build_constant_stencils(h);
+  drop_graphs(h);
+  if (h->have_tree) return h->o.ndim == 2 ? s2_constant_stencils(h) : build_constant_stencils(h);
   return AFMG_OK;
 }
 
@@ -1440,6 +1463,7 @@ int afmg_set_lsf_boundary_value(afmg_handle* h, double value) {
   CK(cudaStreamSynchronize(h->stream));
   h->o.lsf_boundary_value = value;
   h->cx.lsf_value = value;  // a kernel argument: cached graphs are stale
+  if (h->s2) h->s2->cx.lsf_value = value;
   drop_graphs(h);
   h->resid_fresh = false;
   return AFMG_OK;
@@ -1454,6 +1478,7 @@ int afmg_set_stencils(afmg_handle* h, int32_t n, const afmg_stencil_desc* desc, 
   drop_graphs(h);
   h->cs_ready = false;
   h->resid_fresh = false;
+  if (h->o.ndim == 2) return s2_set_stencils(h, n, desc, blob, blob_len);
   const int total = h->nslots, nc = h->o.n_cell, ncell = nc * nc * nc;
   h->h_opk.assign(total, 0);
   h->h_pk.assign(total, 0);
@@ -1563,7 +1588,8 @@ int afmg_update_operator_stencil(afmg_handle* h) {
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   h->cs_ready = false;
-  if (h->have_tree) return build_constant_stencils(h);
+  drop_graphs(h);
+  if (h->have_tree) return h->o.ndim == 2 ? s2_constant_stencils(h) : build_constant_stencils(h);
   return AFMG_OK;
 }
 
@@ -1573,6 +1599,7 @@ static int transfer(afmg_handle* h, int var, int n, const int32_t* box_id, doubl
   if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
   if (n == 0) return AFMG_OK;
   CK(cudaSetDevice(h->device));
+  if (h->o.ndim == 2) return s2_transfer(h, var, n, box_id, packed, up, device_ptr);
   // slot < 0 marks a box owned by another rank: its packed record is skipped (k_pack / k_unpack)
   std::vector<int> slots(n);
   for (int q = 0; q < n; ++q) {
@@ -1627,7 +1654,8 @@ int afmg_clear(afmg_handle* h, int32_t var) {
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
   if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
   CK(cudaSetDevice(h->device));
-  CK(cudaMemsetAsync(h->d_cc[var], 0, (size_t)h->nslots * h->box_len * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(h->o.ndim == 2 ? h->s2->cx.cc[var] : h->d_cc[var], 0, (size_t)h->nslots * h->box_len * sizeof(double),
+                     h->stream));
   h->resid_fresh = false;
   return finish_op(h);
 }
@@ -1640,7 +1668,10 @@ int afmg_fas_vcycle_async(afmg_handle* h, int32_t set_residual, int32_t highest_
   const int max_lvl = highest_lvl > 0 ? highest_lvl : h->L;
   if ((rc = check_lvl(h, max_lvl))) return rc;
   CK(cudaEventRecord(h->ev0, h->stream));
-  rc = run_graph(h, {0, set_residual ? 1 : 0, max_lvl}, n_cycles, [&] { enq_vcycle(h, set_residual != 0, max_lvl); });
+  rc = run_graph(h, {0, set_residual ? 1 : 0, max_lvl}, n_cycles, [&] {
+    if (h->o.ndim == 2) s2_vcycle(h, set_residual != 0, max_lvl);
+    else enq_vcycle(h, set_residual != 0, max_lvl);
+  });
   if (rc) return rc;
   CK(cudaEventRecord(h->ev1, h->stream));
   h->ev_valid = true;
@@ -1655,7 +1686,10 @@ int afmg_fas_fmg_async(afmg_handle* h, int32_t set_residual, int32_t have_guess,
   CK(cudaSetDevice(h->device));
   CK(cudaEventRecord(h->ev0, h->stream));
   rc = run_graph(h, {1, set_residual ? 1 : 0, have_guess ? 1 : 0}, n_cycles,
-                 [&] { enq_fmg(h, set_residual != 0, have_guess != 0); });
+                 [&] {
+                   if (h->o.ndim == 2) s2_fmg(h, set_residual != 0, have_guess != 0);
+                   else enq_fmg(h, set_residual != 0, have_guess != 0);
+                 });
   if (rc) return rc;
   CK(cudaEventRecord(h->ev1, h->stream));
   h->ev_valid = true;
@@ -1697,6 +1731,11 @@ int afmg_gsrb_boxes(afmg_handle* h, int32_t lvl, int32_t type_cycle) {
   int rc = check_lvl(h, lvl);
   if (rc) return rc;
   if (type_cycle != 1 && type_cycle != 3) return h->fail(AFMG_ERR_ARG, "gsrb_boxes: invalid cycle type");
+  if (h->o.ndim == 2) {
+    s2_rb_prepare(h, lvl);
+    s2_gsrb_boxes(h, lvl, type_cycle == 3);
+    return finish_op(h);
+  }
   enq_rb_prepare(h, lvl);
   enq_gsrb_boxes(h, lvl, type_cycle == 3);
   return finish_op(h);
@@ -1706,6 +1745,12 @@ int afmg_gsrb_halfsweep(afmg_handle* h, int32_t lvl, int32_t redblack) {
   SINGLE_OP_PROLOGUE();
   int rc = check_lvl(h, lvl);
   if (rc) return rc;
+  if (h->o.ndim == 2) {
+    s2_rb_prepare(h, lvl);
+    s2_gsrb(h, lvl, redblack);
+    s2_gc(h, lvl, 0);
+    return finish_op(h);
+  }
   enq_rb_prepare(h, lvl);
   enq_gsrb(h, lvl, redblack);
   return finish_op(h);
@@ -1716,6 +1761,11 @@ int afmg_gc_lvl(afmg_handle* h, int32_t lvl, int32_t var, int32_t corners) {
   int rc = check_lvl(h, lvl);
   if (rc) return rc;
   if (var != AFMG_PHI) return h->fail(AFMG_ERR_UNSUPPORTED, "ghost cells are only defined for phi on this path");
+  if (h->o.ndim == 2) {
+    s2_rb_prepare(h, lvl);
+    s2_gc(h, lvl, corners);
+    return finish_op(h);
+  }
   enq_rb_prepare(h, lvl);
   enq_gc(h, lvl, var, corners, 0);
   return finish_op(h);
@@ -1726,7 +1776,8 @@ int afmg_update_coarse(afmg_handle* h, int32_t lvl, int32_t with_tmp) {
   int rc = check_lvl(h, lvl);
   if (rc) return rc;
   if (lvl < 2) return h->fail(AFMG_ERR_ARG, "update_coarse needs lvl >= 2");
-  enq_update_coarse(h, lvl, with_tmp != 0);
+  if (h->o.ndim == 2) s2_update_coarse(h, lvl, with_tmp != 0);
+  else enq_update_coarse(h, lvl, with_tmp != 0);
   return finish_op(h);
 }
 
@@ -1734,7 +1785,8 @@ int afmg_correct_children(afmg_handle* h, int32_t lvl_parents) {
   SINGLE_OP_PROLOGUE();
   int rc = check_lvl(h, lvl_parents);
   if (rc) return rc;
-  enq_correct(h, lvl_parents, true, false);
+  if (h->o.ndim == 2) s2_correct(h, lvl_parents, true);
+  else enq_correct(h, lvl_parents, true, false);
   return finish_op(h);
 }
 
@@ -1743,7 +1795,8 @@ int afmg_correct_children_gc(afmg_handle* h, int32_t lvl_parents) {
   int rc = check_lvl(h, lvl_parents);
   if (rc) return rc;
   if (lvl_parents >= h->L) return h->fail(AFMG_ERR_ARG, "no level above %d", lvl_parents);
-  enq_correct_gc(h, lvl_parents, true);
+  if (h->o.ndim == 2) s2_correct_gc(h, lvl_parents, true);
+  else enq_correct_gc(h, lvl_parents, true);
   return finish_op(h);
 }
 
@@ -1751,19 +1804,22 @@ int afmg_residual_lvl(afmg_handle* h, int32_t lvl) {
   SINGLE_OP_PROLOGUE();
   int rc = check_lvl(h, lvl);
   if (rc) return rc;
-  enq_residual(h, lvl, lvl, false);
+  if (h->o.ndim == 2) s2_residual(h, lvl, lvl, false);
+  else enq_residual(h, lvl, lvl, false);
   return finish_op(h);
 }
 
 int afmg_solve_coarse_grid(afmg_handle* h) {
   SINGLE_OP_PROLOGUE();
-  enq_coarse(h);
+  if (h->o.ndim == 2) s2_coarse(h);
+  else enq_coarse(h);
   return finish_op(h);
 }
 
 int afmg_init_phi_rhs(afmg_handle* h) {
   SINGLE_OP_PROLOGUE();
-  enq_init_phi_rhs(h);
+  if (h->o.ndim == 2) s2_init_phi_rhs(h);
+  else enq_init_phi_rhs(h);
   return finish_op(h);
 }
 
@@ -1779,7 +1835,11 @@ int afmg_max_abs(afmg_handle* h, int32_t var, double* out) {
   } else {
     if (h->nranks > 1 && !h->connected) return h->fail(AFMG_ERR_STATE, "multi-GPU handle is not connected");
     CK(cudaMemsetAsync(h->d_scal + 1, 0, sizeof(unsigned long long), h->stream));
-    for (int l = 1; l <= h->L; ++l) {
+    if (h->o.ndim == 2) {
+      Launch L_(h, "maxabs");
+      DISPATCH_NC2(h, NC, { afmg2::k2_maxabs<NC><<<h->nslots, 64, 0, h->stream>>>(h->s2->cx, 0, h->nslots, var, h->d_scal + 1); });
+    }
+    for (int l = 1; l <= h->L && h->o.ndim == 3; ++l) {
       const Range r = (h->nranks == 1) ? Range{0, h->nslots} : own(h, l);
       if (r.n > 0) {
         Launch L_(h, "maxabs");
@@ -1802,18 +1862,21 @@ int afmg_tree_sum(afmg_handle* h, int32_t var, double* out) {
   if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
   CK(cudaSetDevice(h->device));
   if (h->nranks > 1 && !h->connected) return h->fail(AFMG_ERR_STATE, "multi-GPU handle is not connected");
-  enq_box_sums(h, var);
+  if (h->o.ndim == 2) s2_box_sums(h, var);
+  else enq_box_sums(h, var);
   std::vector<double> sums(h->nslots);
-  CK(cudaMemcpyAsync(sums.data(), h->d_boxsum, (size_t)h->nslots * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(sums.data(), h->o.ndim == 2 ? h->s2->d_boxsum : h->d_boxsum, (size_t)h->nslots * sizeof(double),
+                     cudaMemcpyDeviceToHost, h->stream));
   int rc = finish_op(h);
   if (rc) return rc;
   // af_tree_sum_cc: my_sum += fac(lvl) * box_sum over leaves, in level / list order
   double s = 0.0;
   for (int l = 1; l <= h->L; ++l) {
     double fac = 1.0;
-    for (int d = 0; d < 3; ++d) fac *= h->o.dr_base[d] * std::pow(0.5, l - 1);
+    for (int d = 0; d < h->o.ndim; ++d) fac *= h->o.dr_base[d] * std::pow(0.5, l - 1);
+    const std::vector<int>& child0 = h->o.ndim == 2 ? h->s2->h_child0 : h->h_child0;
     for (int q = h->lvl_off[l]; q < h->lvl_off[l + 1]; ++q)
-      if (h->h_child0[q] < 0) s = s + fac * sums[q];
+      if (child0[q] < 0) s = s + fac * sums[q];
   }
   *out = s;
   return AFMG_OK;
@@ -1859,7 +1922,7 @@ int afmg_cell_updates(afmg_handle* h, int32_t highest_lvl, int32_t fmg, double* 
   if (!h || !out) return AFMG_ERR_ARG;
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
   const int maxl = highest_lvl > 0 ? highest_lvl : h->L;
-  const double ncell = (double)h->o.n_cell * h->o.n_cell * h->o.n_cell;
+  const double ncell = (double)h->o.n_cell * h->o.n_cell * (h->o.ndim == 3 ? h->o.n_cell : 1);
   auto vc = [&](int m) {
     double s = 0;
     for (int l = 2; l <= m; ++l) s += (double)(h->o.n_cycle_down + h->o.n_cycle_up) * nlev(h, l) * ncell;
@@ -1881,12 +1944,8 @@ int32_t afmg_layout_offset(int32_t ndim, int32_t nc, int32_t i, int32_t j, int32
       case 32: return Lay3<32>::cell(i, j, k);
     }
   } else if (ndim == 2) {
-    switch (nc) {
-      case 4: return Lay2<4>::cell(i, j);
-      case 8: return Lay2<8>::cell(i, j);
-      case 16: return Lay2<16>::cell(i, j);
-      case 32: return Lay2<32>::cell(i, j);
-    }
+    // 2D box records keep the reference's own order cc(0:nc+1, 0:nc+1), first index fastest
+    if (nc == 4 || nc == 8 || nc == 16 || nc == 32) return i + (nc + 2) * j;
   }
   return -1;
 }

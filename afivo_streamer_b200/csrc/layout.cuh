@@ -110,56 +110,5 @@ struct Lay3 {
   }
 };
 
-// 2D layout: same idea, colour = (i+j)&1.
-//   [ colour 0 : interior(j,m) | face 0..3 ] [ colour 1 : ... ] [ 4 corners ]
-// (NC/2 doubles per colour per face are not 16-byte multiples for all nc, so 2D kernels use plain
-// loads; 2D boxes are tiny and this path is the CPU-runnable config of the reference.)
-template <int NC>
-struct Lay2 {
-  static constexpr int H = NC / 2;
-  static constexpr int NI = NC * H;
-  static constexpr int NF = H;
-  static constexpr int COL = NI + 4 * NF;
-  static constexpr int OFF_C = 2 * COL;
-  static constexpr int BOX = OFF_C + 4;
-  static constexpr int NC2 = NC;
-  static_assert(BOX == (NC + 2) * (NC + 2), "layout must be a permutation of the box");
-
-  static AFMG_HD int iidx(int m, int j) { return (j - 1) * H + m; }
-  static AFMG_HD int fidx(int f, int a) { return NI + f * NF + ((a - 1) >> 1); }
-  static AFMG_HD int interior(int i, int j) { return ((i + j) & 1) * COL + iidx((i - 1) >> 1, j); }
-  static AFMG_HD int face(int f, int a) {
-    int g = (f & 1) ? NC + 1 : 0;
-    return ((g + a) & 1) * COL + fidx(f, a);
-  }
-  static AFMG_HD int corner(int c) { return OFF_C + c; }
-  static AFMG_HD int cell(int i, int j) {
-    const bool bi = (i == 0) | (i == NC + 1), bj = (j == 0) | (j == NC + 1);
-    if (!bi && !bj) return interior(i, j);
-    if (bi && bj) return corner((i ? 1 : 0) + (j ? 2 : 0));
-    if (bi) return face(i ? 1 : 0, j);
-    return face(j ? 3 : 2, i);
-  }
-  static AFMG_HD void uncell(int q, int& i, int& j) {
-    if (q < OFF_C) {
-      const int c = q >= COL ? 1 : 0;
-      int r = q - c * COL;
-      if (r < NI) {
-        const int m = r % H;
-        j = r / H + 1;
-        i = 2 * m + 2 - ((c + j) & 1);
-        return;
-      }
-      r -= NI;
-      const int f = r / NF, ah = r % NF;
-      const int g = (f & 1) ? NC + 1 : 0;
-      const int a = 2 * ah + 2 - ((c + g) & 1);
-      if (f < 2) { i = g; j = a; }
-      else { i = a; j = g; }
-      return;
-    }
-    const int c = q - OFF_C;
-    i = (c & 1) ? NC + 1 : 0;
-    j = (c & 2) ? NC + 1 : 0;
-  }
-};
+// 2D boxes keep the reference's own (nc+2)^2 order (kernels2d.cuh): they are tiny and the 2D path is
+// launch-latency bound, so there is nothing to gain from a colour split.

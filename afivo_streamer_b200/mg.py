@@ -125,6 +125,7 @@ class mg_t:
 
         for d, e in zip(descs, entries):
             d.box_id, d.tag = int(e["box_id"]), int(e.get("tag", 0))
+            d.cylindrical_gradient = int(bool(e.get("cyl", False)))
             d.op_stype, d.f_offset, d.prolong_shape = 0, -1, 0
             if e.get("op") is not None:
                 d.op_stype = int(e["op"][0])

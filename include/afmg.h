@@ -134,12 +134,12 @@ int afmg_update_operator_stencil(afmg_handle* h);
  * mg_box_lsf_stencil :1782-1854 for level-set boxes, mg_box_prolong_eps_stencil :1308-1388; they call user
  * callbacks), so the shim ships what they stored in box%stencils (stencil_t, m_af_types.f90:260-282) for
  * every box whose operator is not the plain constant Laplacian or whose prolongation is not the default:
- *   op_stype       0 = implicit (library derives 1/dr^2, lambda), 1 = stencil_constant: c(7) at op_offset,
- *                  2 = stencil_variable: v(7, nc, nc, nc) at op_offset (first index fastest)
+ *   op_stype       0 = implicit (library derives 1/dr^2, lambda), 1 = stencil_constant: c(2*ndim+1) at
+ *                  op_offset, 2 = stencil_variable: v(2*ndim+1, nc, nc[, nc]) at op_offset (first index fastest)
  *   f_offset       >= 0: stencil%f (nc^3) -- the library applies bc_correction = f * lsf_boundary_value
  *                  (m_af_multigrid.f90:1171-1174); -1: none
- *   prolong_shape  0 = default (mg%prolongation_type), AFMG_STENCIL_P248 (8 coefficients) or
- *                  AFMG_STENCIL_P234 (4); prolong_stype 1 = constant c(n) / 2 = variable v(4, nc, nc, nc)
+ *   prolong_shape  0 = default (mg%prolongation_type), AFMG_STENCIL_P248 (2^ndim coefficients) or
+ *                  AFMG_STENCIL_P234 (ndim+1); prolong_stype 1 = constant c(n) / 2 = variable v(ndim+1, cells)
  *   tag            box%tag (mg_lsf_box = 1, mg_veps_box = 2, mg_ceps_box = 4, m_af_types.f90:497-508); boxes
  *                  with iand(tag, operator_mask) == mg_veps_box get mg_sides_rb_extrap ghost cells on
  *                  refinement boundaries (mg_auto_rb, :926-940)
@@ -153,7 +153,7 @@ typedef struct afmg_stencil_desc {
   int32_t prolong_shape;
   int32_t prolong_stype;
   int32_t tag;
-  int32_t reserved;
+  int32_t cylindrical_gradient; /* stencil%cylindrical_gradient (2D cylindrical trees, m_af_types.f90:272) */
   int64_t op_offset;
   int64_t f_offset;
   int64_t prolong_offset;

@@ -91,8 +91,8 @@ def stencils_from_oracle(tree, orc):
             tag = orc.tag(bid)
             if tag == 0:
                 continue
-            stype, coeff, f, _ = orc.op_stencil(bid)
-            e = dict(box_id=int(bid), tag=tag, op=(stype, coeff), f=f)
+            stype, coeff, f, cyl = orc.op_stencil(bid)
+            e = dict(box_id=int(bid), tag=tag, op=(stype, coeff), f=f, cyl=cyl)
             if lvl > 1:
                 pst, pshape, pco = orc.prolong_stencil(bid)
                 e["prolong"] = (pst, pshape, pco)
