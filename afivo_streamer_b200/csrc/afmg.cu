@@ -123,6 +123,7 @@ struct afmg_handle {
   bool capturing = false;
   int64_t launches = 0;
   bool profiling = false;
+  bool pdl = false;  // programmatic dependent launch (launch_k), AFMG_PDL=1
   std::map<std::string, ProfEntry> prof;
   std::vector<std::tuple<std::string, cudaEvent_t, cudaEvent_t>> prof_pending;
 
@@ -228,6 +229,28 @@ struct Launch {
   }
 };
 
+// All kernels go through this helper.  With programmatic dependent launch (PDL; AFMG_PDL=1 enables
+// it) the next kernel of the stream / graph is allowed to start launching while the previous one
+// drains; every kernel begins with griddepcontrol.wait (pdl_wait()), which returns once the preceding
+// grid has completed and its memory is visible, so the data dependencies are the same as with plain
+// stream order -- only the launch latency could overlap.  Measured on B200 inside CUDA graphs it gains
+// < 1 % (S2: 0.7045 vs 0.7090 ms per V-cycle; graph replay already hides the launch), so it is off by
+// default; the ~3.3 us per graph node that bound the coarse levels are kernel drain + ramp-up.
+template <class... KArgs, class... Args>
+void launch_k(afmg_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = h->pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
 void prof_resolve(afmg_handle* h) {
   for (auto& t : h->prof_pending) {
     float ms = 0;
@@ -265,7 +288,7 @@ inline Range own(const afmg_handle* h, int l) {
 void enq_barrier(afmg_handle* h) {
   if (h->nranks == 1) return;
   Launch L_(h, "barrier");
-  k_barrier<<<1, 32, 0, h->stream>>>(h->d_comm, h->peers, h->nranks, h->me, h->barrier_timeout_ns);
+  launch_k(h, k_barrier, 1, 32, 0, h->d_comm, h->peers, h->nranks, h->me, h->barrier_timeout_ns);
 }
 
 // one half-sweep + side ghost fill on level l
@@ -295,12 +318,12 @@ void enq_gsrb(afmg_handle* h, int l, int redblack) {
       constexpr int threads = G::BPC * G::KS * NC * NC / 2;
       const size_t smem = (size_t)G::BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double);
       auto kern = k_gsrb2<NC, G::BPC, G::KS, G::MINB>;
-      kern<<<(r.n + G::BPC - 1) / G::BPC, threads, smem, h->stream>>>(h->cx, r.s0, r.n, redblack & 1, l);
+      launch_k(h, kern, (r.n + G::BPC - 1) / G::BPC, threads, smem, h->cx, r.s0, r.n, redblack & 1, l);
     });
   }
   if (const int ns = nspec(h, l)) {  // boxes with an explicit stencil (skipped by the kernel above)
     Launch L_(h, "gsrb_gen", l);
-    DISPATCH_NC(h, NC, { k_gsrb_gen<NC><<<ns, 256, 0, h->stream>>>(h->cx, h->d_spec + h->spec_off[l], ns, redblack & 1); });
+    DISPATCH_NC(h, NC, { launch_k(h, k_gsrb_gen<NC>, ns, 256, 0, h->cx, h->d_spec + h->spec_off[l], ns, redblack & 1); });
   }
   enq_barrier(h);
 }
@@ -311,7 +334,7 @@ void enq_rb_prepare(afmg_handle* h, int l) {
   const int r0 = c[h->me], n = c[h->me + 1] - c[h->me];
   if (n == 0) return;
   Launch L_(h, "rb_prepare", l);
-  DISPATCH_NC(h, NC, { k_rb_prepare<NC><<<n, 128, 0, h->stream>>>(h->cx, r0, n, V_PHI); });
+  DISPATCH_NC(h, NC, { launch_k(h, k_rb_prepare<NC>, n, 128, 0, h->cx, r0, n, V_PHI); });
 }
 
 // af_gc_lvl (+ parent update when mode != 0)
@@ -321,9 +344,9 @@ void enq_gc(afmg_handle* h, int l, int var, int corners, int mode) {
     Launch L_(h, mode ? "gc_parent" : "gc", l);
     DISPATCH_NC(h, NC, {
       if (var == V_PHI && mode != 0)
-        k_gc2<NC><<<r.n, 256, (size_t)2 * Lay3<NC>::COL * sizeof(double), h->stream>>>(h->cx, r.s0, r.n, corners, mode);
+        launch_k(h, k_gc2<NC>, r.n, 256, (size_t)2 * Lay3<NC>::COL * sizeof(double), h->cx, r.s0, r.n, corners, mode);
       else
-        k_gc<NC><<<r.n, 256, 0, h->stream>>>(h->cx, r.s0, r.n, var, corners, mode);
+        launch_k(h, k_gc<NC>, r.n, 256, 0, h->cx, r.s0, r.n, var, corners, mode);
     });
   }
   enq_barrier(h);
@@ -333,7 +356,7 @@ void enq_edges_corners(afmg_handle* h, int l) {
   const Range r = own(h, l);
   if (r.n > 0) {
     Launch L_(h, "edges_corners", l);
-    DISPATCH_NC(h, NC, { k_edges_corners<NC><<<r.n, 64, 0, h->stream>>>(h->cx, r.s0, r.n, V_PHI); });
+    DISPATCH_NC(h, NC, { launch_k(h, k_edges_corners<NC>, r.n, 64, 0, h->cx, r.s0, r.n, V_PHI); });
   }
   enq_barrier(h);
 }
@@ -351,14 +374,14 @@ void enq_restrict(afmg_handle* h, int l, int keep_res) {
     Launch L_(h, "restrict", l);
     DISPATCH_NC(h, NC, {
       constexpr int KS = OpCfg<NC>::KS;
-      k_resid3<NC, KS, 1, OpCfg<NC>::RES_MINB><<<r.n, KS * NC * NC / 2, OpCfg<NC>::TILE, h->stream>>>(
+      launch_k(h, k_resid3<NC, KS, 1, OpCfg<NC>::RES_MINB>, r.n, KS * NC * NC / 2, OpCfg<NC>::TILE, 
           h->cx, r.s0, r.n, nullptr, keep_res);
     });
   }
   if (const int ns = nspec(h, l)) {
     Launch L_(h, "restrict_gen", l);
     DISPATCH_NC(h, NC, {
-      k_resid_gen<NC, 1><<<ns, 256, (size_t)2 * Lay3<NC>::NI * sizeof(double), h->stream>>>(
+      launch_k(h, k_resid_gen<NC, 1>, ns, 256, (size_t)2 * Lay3<NC>::NI * sizeof(double), 
           h->cx, h->d_spec + h->spec_off[l], ns, nullptr, keep_res);
     });
   }
@@ -376,7 +399,7 @@ void enq_correct(afmg_handle* h, int lp, bool store_corr, bool push) {
     DISPATCH_NC(h, NC, {
       constexpr int W = NC / 2 + 2;
       const size_t smem = (size_t)(2 * Lay3<NC>::NI + W * W * W) * sizeof(double);
-      k_correct3<NC><<<rc.n, 256, smem, h->stream>>>(h->cx, rc.s0, rc.n, push ? 1 : 0);
+      launch_k(h, k_correct3<NC>, rc.n, 256, smem, h->cx, rc.s0, rc.n, push ? 1 : 0);
     });
   }
   enq_barrier(h);  // all children have read the old tmp of their parents
@@ -384,16 +407,19 @@ void enq_correct(afmg_handle* h, int lp, bool store_corr, bool push) {
     const Range rp = own(h, lp);
     if (rp.n > 0) {
       Launch L_(h, "store_corr", lp);
-      DISPATCH_NC(h, NC, { k_store_corr<NC><<<rp.n, 256, 0, h->stream>>>(h->cx, rp.s0, rp.n); });
+      DISPATCH_NC(h, NC, { launch_k(h, k_store_corr<NC>, rp.n, 256, 0, h->cx, rp.s0, rp.n); });
     }
   }
 }
 
 // correct_children(lp) followed by af_gc_lvl(lp + 1) (m_af_multigrid.f90:219-222)
-void enq_correct_gc(afmg_handle* h, int lp, bool store_corr) {
+// Inside the cycles the edge / corner ghost cells written by that af_gc_lvl are dead: the upward
+// gsrb_boxes that follows only reads face ghost cells and ends with its own edge / corner refresh
+// (m_af_multigrid.f90:676-684), so they are skipped there (corners = false) unless n_cycle_up == 0.
+void enq_correct_gc(afmg_handle* h, int lp, bool store_corr, bool corners = true) {
   enq_rb_prepare(h, lp + 1);
   enq_correct(h, lp, store_corr, true);
-  enq_edges_corners(h, lp + 1);
+  if (corners) enq_edges_corners(h, lp + 1);
 }
 
 // max over ranks of scal[idx] -> scal[4 + idx] on every rank
@@ -402,7 +428,7 @@ void enq_allmax(afmg_handle* h, int idx) {
   enq_barrier(h);
   {
     Launch L_(h, "allmax");
-    k_allmax<<<1, 1, 0, h->stream>>>(h->d_comm, h->peers, h->nranks, idx);
+    launch_k(h, k_allmax, 1, 1, 0, h->d_comm, h->peers, h->nranks, idx);
   }
   enq_barrier(h);  // nobody resets scal[idx] while a peer still reads it
 }
@@ -414,7 +440,7 @@ void enq_residual(afmg_handle* h, int l_lo, int l_hi, bool with_max) {
     Launch L_(h, "residual");
     DISPATCH_NC(h, NC, {
       constexpr int KS = OpCfg<NC>::KS;
-      k_resid3<NC, KS, 0, OpCfg<NC>::RES_MINB><<<n, KS * NC * NC / 2, OpCfg<NC>::TILE, h->stream>>>(
+      launch_k(h, k_resid3<NC, KS, 0, OpCfg<NC>::RES_MINB>, n, KS * NC * NC / 2, OpCfg<NC>::TILE, 
           h->cx, s0, n, with_max ? h->d_scal : nullptr, 0);
     });
   };
@@ -423,7 +449,7 @@ void enq_residual(afmg_handle* h, int l_lo, int l_hi, bool with_max) {
     if (ns > 0) {
       Launch L_(h, "residual_gen");
       DISPATCH_NC(h, NC, {
-        k_resid_gen<NC, 0><<<ns, 256, 0, h->stream>>>(h->cx, h->d_spec + s0, ns, with_max ? h->d_scal : nullptr, 0);
+        launch_k(h, k_resid_gen<NC, 0>, ns, 256, 0, h->cx, h->d_spec + s0, ns, with_max ? h->d_scal : nullptr, 0);
       });
     }
   }
@@ -458,7 +484,7 @@ void enq_copy_lvl(afmg_handle* h, int l, int dst, int src) {
   Launch L_(h, "copy", l);
   const size_t off = (size_t)r.s0 * h->box_len;
   const int blocks = (int)std::min<size_t>((n + 1023) / 1024, 148 * 8);
-  k_copy<<<blocks, 256, 0, h->stream>>>(h->d_cc[dst] + off, h->d_cc[src] + off, n);
+  launch_k(h, k_copy, blocks, 256, 0, h->d_cc[dst] + off, h->d_cc[src] + off, n);
 }
 
 // solve_coarse_grid (m_af_multigrid.f90:266-291)
@@ -472,28 +498,28 @@ void enq_coarse(afmg_handle* h) {
   const int blocks = (ntot + 127) / 128;
   {
     Launch L_(h, "coarse");
-    DISPATCH_NC(h, NC, { k_cs_gather<NC><<<blocks, 128, 0, h->stream>>>(h->cx, h->cs, nbox1); });
+    DISPATCH_NC(h, NC, { launch_k(h, k_cs_gather<NC>, blocks, 128, 0, h->cx, h->cs, nbox1); });
   }
   double *a = h->d_v0, *b = h->d_v1;
   if (h->cs_dense) {
     Launch L_(h, "coarse");
-    k_cs_dense<<<(ntot * 32 + 255) / 256, 256, 0, h->stream>>>(h->cs, a, b);
+    launch_k(h, k_cs_dense, (ntot * 32 + 255) / 256, 256, 0, h->cs, a, b);
     std::swap(a, b);
   } else {
     for (int d = 0; d < 3; ++d) {
       Launch L_(h, "coarse");
-      k_cs_apply<<<blocks, 128, 0, h->stream>>>(h->cs, a, b, d, 1, d == 2);
+      launch_k(h, k_cs_apply, blocks, 128, 0, h->cs, a, b, d, 1, d == 2);
       std::swap(a, b);
     }
     for (int d = 0; d < 3; ++d) {
       Launch L_(h, "coarse");
-      k_cs_apply<<<blocks, 128, 0, h->stream>>>(h->cs, a, b, d, 0, 0);
+      launch_k(h, k_cs_apply, blocks, 128, 0, h->cs, a, b, d, 0, 0);
       std::swap(a, b);
     }
   }
   {
     Launch L_(h, "coarse");
-    DISPATCH_NC(h, NC, { k_cs_scatter<NC><<<blocks, 128, 0, h->stream>>>(h->cx, h->cs, nbox1, a); });
+    DISPATCH_NC(h, NC, { launch_k(h, k_cs_scatter<NC>, blocks, 128, 0, h->cx, h->cs, nbox1, a); });
   }
   enq_gc(h, 1, V_PHI, 1, 0);
 }
@@ -523,14 +549,17 @@ void enq_subtract_mean(afmg_handle* h, int max_lvl);
 
 // mg_fas_vcycle (m_af_multigrid.f90:185-264)
 void enq_vcycle(afmg_handle* h, bool set_residual, int max_lvl, bool final_state = true) {
+  const bool dead_corners = h->o.n_cycle_up > 0;
   for (int l = max_lvl; l >= 2; --l) {
-    enq_rb_prepare(h, l);
+    // below max_lvl the refinement-boundary rows of level l were interpolated by update_coarse(l + 1)
+    // and level l - 1 has not changed since
+    if (l == max_lvl) enq_rb_prepare(h, l);
     enq_gsrb_boxes(h, l, false);
     enq_update_coarse(h, l, true);
   }
   enq_coarse(h);
   for (int l = 2; l <= max_lvl; ++l) {
-    enq_correct_gc(h, l - 1, final_state && !set_residual);
+    enq_correct_gc(h, l - 1, final_state && !set_residual, !dead_corners);
     enq_gsrb_boxes(h, l, true);
   }
   if (set_residual) {
@@ -544,6 +573,7 @@ void enq_vcycle(afmg_handle* h, bool set_residual, int max_lvl, bool final_state
 __global__ void k_weighted_sum(const double* boxsum, const int* child0, const int* lvl, const double* lvl_fac, int n,
                                double inv_volume, double* out) {
   // deterministic single-CTA reduction: thread t sums slots t, t+T, ...; then a fixed tree
+  pdl_wait();
   __shared__ double sh[256];
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x)
@@ -563,7 +593,7 @@ void enq_box_sums(afmg_handle* h, int var) {
     const Range r = (h->nranks == 1) ? Range{0, h->nslots} : own(h, l);
     if (r.n > 0) {
       Launch L_(h, "sum");
-      DISPATCH_NC(h, NC, { k_box_sums<NC><<<r.n, 128, 0, h->stream>>>(h->cx, r.s0, r.n, var, h->d_boxsum); });
+      DISPATCH_NC(h, NC, { launch_k(h, k_box_sums<NC>, r.n, 128, 0, h->cx, r.s0, r.n, var, h->d_boxsum); });
     }
     if (h->nranks == 1) break;
   }
@@ -577,7 +607,7 @@ void enq_subtract_mean(afmg_handle* h, int max_lvl) {
   for (int d = 0; d < 3; ++d) vol *= h->o.n_cell * h->o.dr_base[d];
   {
     Launch L_(h, "sum");
-    k_weighted_sum<<<1, 256, 0, h->stream>>>(h->d_boxsum, h->d_child0, h->d_lvl, h->d_coef + 8 * (h->L + 1), h->nslots,
+    launch_k(h, k_weighted_sum, 1, 256, 0, h->d_boxsum, h->d_child0, h->d_lvl, h->d_coef + 8 * (h->L + 1), h->nslots,
                                             1.0 / vol, (double*)(h->d_scal + 2));
   }
   for (int l = 1; l <= max_lvl; ++l) {
@@ -586,7 +616,7 @@ void enq_subtract_mean(afmg_handle* h, int max_lvl) {
     if (n > 0) {
       Launch L_(h, "sub_mean");
       const int blocks = (int)std::min<size_t>((n + 1023) / 1024, 148 * 8);
-      k_sub_scalar<<<blocks, 256, 0, h->stream>>>(h->d_cc[V_PHI] + (size_t)r.s0 * h->box_len,
+      launch_k(h, k_sub_scalar, blocks, 256, 0, h->d_cc[V_PHI] + (size_t)r.s0 * h->box_len,
                                                   (const double*)(h->d_scal + 2), n);
     }
     if (h->nranks == 1) break;
@@ -602,7 +632,7 @@ void enq_init_phi_rhs(afmg_handle* h) {
       Launch L_(h, "init_phi_rhs", l);
       DISPATCH_NC(h, NC, {
         constexpr int T = (NC == 16) ? 256 : (NC == 8 ? 64 : 32);
-        k_restrict_var<NC><<<r.n, T, 0, h->stream>>>(h->cx, r.s0, r.n, V_RHS, 1);
+        launch_k(h, k_restrict_var<NC>, r.n, T, 0, h->cx, r.s0, r.n, V_RHS, 1);
       });
     }
     enq_barrier(h);
@@ -621,7 +651,7 @@ void enq_fmg(afmg_handle* h, bool set_residual, bool have_guess) {
   for (int l = 2; l <= h->L; ++l) {
     enq_copy_lvl(h, l, V_TMP, V_PHI);
     // the correction stored in tmp of the parents is overwritten on the way down of the next cycle
-    enq_correct_gc(h, l - 1, l == h->L && !set_residual);
+    enq_correct_gc(h, l - 1, l == h->L && !set_residual, h->o.n_cycle_up == 0);
     enq_vcycle(h, set_residual && l == h->L, l, l == h->L);
   }
 }
@@ -1118,6 +1148,7 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
   if (e == cudaSuccess) e = cudaMemset(h->d_comm, 0, sizeof(CommBlock));
   if (e == cudaSuccess) h->d_scal = h->d_comm->scal;  // address arithmetic only
   h->peers.p[0] = h->d_comm;
+  if (const char* env = getenv("AFMG_PDL")) h->pdl = atoi(env) != 0;
   if (const char* env = getenv("AFMG_BARRIER_TIMEOUT_S")) {
     const double sec = atof(env);
     if (sec > 0) h->barrier_timeout_ns = (unsigned long long)(sec * 1e9);
@@ -1620,11 +1651,11 @@ static int transfer(afmg_handle* h, int var, int n, const int32_t* box_id, doubl
     if (up) {
       if (!device_ptr) CK(cudaMemcpyAsync(dp, hp, (size_t)m * box_bytes, cudaMemcpyHostToDevice, h->stream));
       Launch L_(h, "unpack");
-      DISPATCH_NC(h, NC, { k_unpack<NC><<<m, 256, 0, h->stream>>>(h->d_cc[var], h->d_stage_slots + q0, m, dp); });
+      DISPATCH_NC(h, NC, { launch_k(h, k_unpack<NC>, m, 256, 0, h->d_cc[var], h->d_stage_slots + q0, m, dp); });
     } else {
       {
         Launch L_(h, "pack");
-        DISPATCH_NC(h, NC, { k_pack<NC><<<m, 256, 0, h->stream>>>(h->d_cc[var], h->d_stage_slots + q0, m, dp); });
+        DISPATCH_NC(h, NC, { launch_k(h, k_pack<NC>, m, 256, 0, h->d_cc[var], h->d_stage_slots + q0, m, dp); });
       }
       if (!device_ptr) CK(cudaMemcpyAsync(hp, dp, (size_t)m * box_bytes, cudaMemcpyDeviceToHost, h->stream));
     }
@@ -1837,13 +1868,13 @@ int afmg_max_abs(afmg_handle* h, int32_t var, double* out) {
     CK(cudaMemsetAsync(h->d_scal + 1, 0, sizeof(unsigned long long), h->stream));
     if (h->o.ndim == 2) {
       Launch L_(h, "maxabs");
-      DISPATCH_NC2(h, NC, { afmg2::k2_maxabs<NC><<<h->nslots, 64, 0, h->stream>>>(h->s2->cx, 0, h->nslots, var, h->d_scal + 1); });
+      DISPATCH_NC2(h, NC, { launch_k(h, afmg2::k2_maxabs<NC>, h->nslots, 64, 0, h->s2->cx, 0, h->nslots, var, h->d_scal + 1); });
     }
     for (int l = 1; l <= h->L && h->o.ndim == 3; ++l) {
       const Range r = (h->nranks == 1) ? Range{0, h->nslots} : own(h, l);
       if (r.n > 0) {
         Launch L_(h, "maxabs");
-        DISPATCH_NC(h, NC, { k_maxabs<NC><<<r.n, 256, 0, h->stream>>>(h->cx, r.s0, r.n, var, h->d_scal + 1); });
+        DISPATCH_NC(h, NC, { launch_k(h, k_maxabs<NC>, r.n, 256, 0, h->cx, r.s0, r.n, var, h->d_scal + 1); });
       }
       if (h->nranks == 1) break;
     }

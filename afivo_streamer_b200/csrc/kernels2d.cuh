@@ -14,6 +14,8 @@ namespace afmg2 {
 
 enum { V_PHI = 0, V_RHS = 1, V_TMP = 2 };
 
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct Ctx {
   double* cc[3];         // per variable: nslots * (nc+2)^2 doubles, box record = cc(0:nc+1, 0:nc+1)
   const int* nbr;        // [nslots*4]  >= 0 neighbour slot; -1: own-ghost rule row in aux
@@ -109,6 +111,7 @@ __device__ __forceinline__ double apply2(const Ctx& cx, int slot, const double* 
 // k2_gc afterwards (gsrb_boxes, m_af_multigrid.f90:648-687)
 template <int NC>
 __global__ void k2_gsrb(Ctx cx, int slot0, int nbox, int C) {
+  pdl_wait();
   using B = B2<NC>;
   const int slot = slot0 + blockIdx.x;
   double* phi = cx.cc[V_PHI] + (size_t)slot * B::BOX;
@@ -138,6 +141,7 @@ __global__ void k2_gsrb(Ctx cx, int slot0, int nbox, int C) {
 // first half of mg_sides_rb in 2D (m_af_multigrid.f90:294-369) / af_gc_prolong_copy for extrapolated faces
 template <int NC>
 __global__ void k2_rb_prepare(Ctx cx, int r0, int nr, int var) {
+  pdl_wait();
   using B = B2<NC>;
   constexpr int H = B::H;
   const int r = r0 + blockIdx.x;
@@ -179,6 +183,7 @@ __global__ void k2_rb_prepare(Ctx cx, int r0, int nr, int var) {
 // af_gc_box in 2D (m_af_ghostcell.f90:64-170): sides, then the four corners
 template <int NC>
 __global__ void k2_gc(Ctx cx, int slot0, int nbox, int var, int corners) {
+  pdl_wait();
   using B = B2<NC>;
   const int slot = slot0 + blockIdx.x;
   double* vb = cx.cc[var];
@@ -239,6 +244,7 @@ __global__ void k2_gc(Ctx cx, int slot0, int nbox, int var, int corners) {
 // residual with the cylindrical child weights (af_cyl_child_weights, m_af_types.f90:1187-1196)
 template <int NC, int MODE>
 __global__ void k2_resid(Ctx cx, int slot0, int nbox, unsigned long long* maxabs_bits, int keep_res) {
+  pdl_wait();
   using B = B2<NC>;
   constexpr int H = B::H;
   __shared__ double sres[NC * NC];
@@ -304,6 +310,7 @@ __global__ void k2_resid(Ctx cx, int slot0, int nbox, unsigned long long* maxabs
 // (full record); mode 2 (set_coarse_phi_rhs :769-774): rhs only
 template <int NC>
 __global__ void k2_parent(Ctx cx, int slot0, int nbox, int mode) {
+  pdl_wait();
   using B = B2<NC>;
   const int slot = slot0 + blockIdx.x;
   if (cx.child0[slot] < 0) return;
@@ -325,6 +332,7 @@ __global__ void k2_parent(Ctx cx, int slot0, int nbox, int mode) {
 // stencil_prolong_248 / _234 in 2D (m_af_stencil.f90:610-648, :715-764)
 template <int NC>
 __global__ void k2_correct(Ctx cx, int slot0, int nbox) {
+  pdl_wait();
   using B = B2<NC>;
   constexpr int H = B::H, W = H + 2;
   __shared__ double sub[W * W];
@@ -360,6 +368,7 @@ __global__ void k2_correct(Ctx cx, int slot0, int nbox) {
 // tmp_p = phi_p - tmp_p on the full record of boxes with children (m_af_multigrid.f90:636-637)
 template <int NC>
 __global__ void k2_store_corr(Ctx cx, int slot0, int nbox) {
+  pdl_wait();
   using B = B2<NC>;
   const int slot = slot0 + blockIdx.x;
   if (cx.child0[slot] < 0) return;
@@ -372,6 +381,7 @@ __global__ void k2_store_corr(Ctx cx, int slot0, int nbox) {
 // cylindrical weights: mg_box_rstr_lpl uses geometry for every variable but phi)
 template <int NC>
 __global__ void k2_restrict_var(Ctx cx, int slot0, int nbox, int var, int clear_phi) {
+  pdl_wait();
   using B = B2<NC>;
   constexpr int H = B::H;
   const int slot = slot0 + blockIdx.x;
@@ -413,6 +423,7 @@ __global__ void k2_restrict_var(Ctx cx, int slot0, int nbox, int var, int clear_
 // max |var| over the interior of leaves (af_tree_maxabs_cc)
 template <int NC>
 __global__ void k2_maxabs(Ctx cx, int slot0, int nbox, int var, unsigned long long* maxabs_bits) {
+  pdl_wait();
   using B = B2<NC>;
   const int slot = slot0 + blockIdx.x;
   if (cx.child0[slot] >= 0) return;
@@ -427,6 +438,7 @@ __global__ void k2_maxabs(Ctx cx, int slot0, int nbox, int var, unsigned long lo
 // (af_tree_sum_cc, m_af_utils.f90:966-1027); one thread per box (2D boxes are tiny)
 template <int NC>
 __global__ void k2_box_sums(Ctx cx, int nslots, int var, double* out) {
+  pdl_wait();
   using B = B2<NC>;
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= nslots) return;
@@ -446,6 +458,7 @@ __global__ void k2_box_sums(Ctx cx, int nslots, int var, double* out) {
 
 // box records are already in the reference's order: upload / download are row copies
 __global__ void k2_copy_boxes(double* var_base, const int* slots, int n, double* packed, int box_len, int to_device) {
+  pdl_wait();
   const int q = blockIdx.x;
   if (q >= n || slots[q] < 0) return;
   double* a = var_base + (size_t)slots[q] * box_len;
@@ -470,6 +483,7 @@ struct Coarse2 {
 
 template <int NC>
 __global__ void k2_cs_gather(Ctx cx, Coarse2 cs, int nbox1) {
+  pdl_wait();
   using B = B2<NC>;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nbox1 * NC * NC) return;
@@ -492,6 +506,7 @@ __global__ void k2_cs_gather(Ctx cx, Coarse2 cs, int nbox1) {
 }
 
 __global__ void k2_cs_dense(Coarse2 cs, const double* in, double* out) {
+  pdl_wait();
   const int n = cs.nx[0] * cs.nx[1];
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -504,6 +519,7 @@ __global__ void k2_cs_dense(Coarse2 cs, const double* in, double* out) {
 
 template <int NC>
 __global__ void k2_cs_scatter(Ctx cx, Coarse2 cs, int nbox1, const double* x) {
+  pdl_wait();
   using B = B2<NC>;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nbox1 * NC * NC) return;

@@ -67,6 +67,9 @@ struct DevCtx {
 // ---------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1D TMA bulk copy (cp.async.bulk -> SASS UBLKCP)
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch: wait for the preceding grid (and its memory) before touching data
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -135,6 +138,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 __global__ void k_barrier(CommBlock* mine, CommPeers peers, int nranks, int me, unsigned long long timeout_ns) {
+  pdl_wait();
   __shared__ unsigned long long ep;
   const int t = threadIdx.x;
   if (t == 0) {
@@ -161,6 +165,7 @@ __global__ void k_barrier(CommBlock* mine, CommPeers peers, int nranks, int me, 
 
 // scal[4 + idx] = max over ranks of scal[idx] (after a barrier); non-negative doubles order like uint64
 __global__ void k_allmax(CommBlock* mine, CommPeers peers, int nranks, int idx) {
+  pdl_wait();
   unsigned long long m = 0;
   for (int r = 0; r < nranks; ++r) {
     const unsigned long long v = ld_acquire_sys(&peers.p[r]->scal[idx]);
@@ -267,6 +272,7 @@ __device__ __forceinline__ void epilogue_faces(const DevCtx& cx, int slot, const
 
 template <int NC, int BPC, int KS, int MINB>
 __global__ void __launch_bounds__(BPC* KS* NC* NC / 2, MINB) k_gsrb2(DevCtx cx, int slot0, int nbox, int C, int lvl) {
+  pdl_wait();
   using L = Lay3<NC>;
   constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX;
   constexpr int TPB = H * NC * KS;  // threads per box
@@ -412,6 +418,7 @@ __device__ __forceinline__ double apply357_smem(const double* S, const double* c
 template <int NC, int KS, int MODE, int MINB>
 __global__ void __launch_bounds__(KS* NC* NC / 2, MINB)
     k_resid3(DevCtx cx, int slot0, int nbox, unsigned long long* maxabs_bits, int keep_res) {
+  pdl_wait();
   using L = Lay3<NC>;
   constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX, KL = NC / KS;
   static_assert(KL % 2 == 0, "z pairs must stay inside one thread");
@@ -574,6 +581,7 @@ __device__ __forceinline__ double apply_gen(const DevCtx& cx, int kind, const do
 // written by this half-sweep).
 template <int NC>
 __global__ void __launch_bounds__(256) k_gsrb_gen(DevCtx cx, const int* list, int nbox, int C) {
+  pdl_wait();
   using L = Lay3<NC>;
   constexpr int NI = L::NI, COL = L::COL, BOX = L::BOX;
   const int slot = list[blockIdx.x];
@@ -618,6 +626,7 @@ __global__ void __launch_bounds__(256) k_gsrb_gen(DevCtx cx, const int* list, in
 template <int NC, int MODE>
 __global__ void __launch_bounds__(256) k_resid_gen(DevCtx cx, const int* list, int nbox, unsigned long long* maxabs_bits,
                                                    int keep_res) {
+  pdl_wait();
   using L = Lay3<NC>;
   constexpr int H = L::H, BOX = L::BOX, NI = L::NI, COL = L::COL;
   extern __shared__ __align__(16) double sres[];  // MODE 1: 2 * NI residuals in interior-block order
@@ -675,6 +684,7 @@ __global__ void __launch_bounds__(256) k_resid_gen(DevCtx cx, const int* list, i
 // are done by k_edges_corners afterwards.
 template <int NC>
 __global__ void __launch_bounds__(256) k_correct3(DevCtx cx, int slot0, int nbox, int push) {
+  pdl_wait();
   using L = Lay3<NC>;
   constexpr int H = L::H, W = H + 2, NI = L::NI, COL = L::COL, BOX = L::BOX;
   extern __shared__ __align__(128) double smem[];  // I0[NI], I1[NI], sub[W^3]
@@ -793,6 +803,7 @@ __device__ void gc_edges_corners(const DevCtx& cx, int slot, int var);
 // (see k_gc) computed from a shared-memory copy of the box (TMA bulk load) instead of global loads.
 template <int NC>
 __global__ void __launch_bounds__(256) k_gc2(DevCtx cx, int slot0, int nbox, int corners, int mode) {
+  pdl_wait();
   using L = Lay3<NC>;
   constexpr int NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX;
   extern __shared__ __align__(128) double smem[];  // 2*COL
@@ -845,6 +856,7 @@ __global__ void __launch_bounds__(256) k_gc2(DevCtx cx, int slot0, int nbox, int
 // (first statement of correct_children, m_af_multigrid.f90:636-637)
 template <int NC>
 __global__ void k_store_corr(DevCtx cx, int slot0, int nbox) {
+  pdl_wait();
   using L = Lay3<NC>;
   const int slot = slot0 + blockIdx.x;
   if (cx.child0[slot] < 0) return;
@@ -861,6 +873,7 @@ __global__ void k_store_corr(DevCtx cx, int slot0, int nbox) {
 // ---------------------------------------------------------------------------------------------
 template <int NC>
 __global__ void k_rb_prepare(DevCtx cx, int r0, int nr, int var) {
+  pdl_wait();
   using L = Lay3<NC>;
   constexpr int H = L::H;
   const int r = r0 + blockIdx.x;
@@ -1003,6 +1016,7 @@ __device__ void gc_edges_corners(const DevCtx& cx, int slot, int var) {
 // variant that also performs the parent part of update_coarse is k_gc2.)
 template <int NC>
 __global__ void k_gc(DevCtx cx, int slot0, int nbox, int var, int corners, int mode) {
+  pdl_wait();
   using L = Lay3<NC>;
   const int slot = slot0 + blockIdx.x;
   if ((int)blockIdx.x >= nbox) return;
@@ -1017,6 +1031,7 @@ __global__ void k_gc(DevCtx cx, int slot0, int nbox, int var, int corners, int m
 // mg%use_corners, m_af_multigrid.f90:676-684)
 template <int NC>
 __global__ void k_edges_corners(DevCtx cx, int slot0, int nbox, int var) {
+  pdl_wait();
   const int slot = slot0 + blockIdx.x;
   if ((int)blockIdx.x >= nbox) return;
   gc_edges_corners<NC>(cx, slot, var);
@@ -1025,6 +1040,7 @@ __global__ void k_edges_corners(DevCtx cx, int slot0, int nbox, int var) {
 // restriction of one variable only (init_phi_rhs, m_af_multigrid.f90:779-799: phi = 0, restrict rhs)
 template <int NC>
 __global__ void k_restrict_var(DevCtx cx, int slot0, int nbox, int var, int clear_phi) {
+  pdl_wait();
   using L = Lay3<NC>;
   constexpr int H = L::H;
   const int slot = slot0 + blockIdx.x;
@@ -1053,6 +1069,7 @@ __global__ void k_restrict_var(DevCtx cx, int slot0, int nbox, int var, int clea
 // max |var| over the interior of leaves
 template <int NC>
 __global__ void k_maxabs(DevCtx cx, int slot0, int nbox, int var, unsigned long long* maxabs_bits) {
+  pdl_wait();
   using L = Lay3<NC>;
   const int slot = slot0 + blockIdx.x;
   if ((int)blockIdx.x >= nbox || cx.child0[slot] >= 0) return;
@@ -1071,6 +1088,7 @@ __global__ void k_maxabs(DevCtx cx, int slot0, int nbox, int var, unsigned long 
 // host adds fac(lvl) * sum in box order.  One warp per box is plenty (only used by subtract_mean).
 template <int NC>
 __global__ void k_box_sums(DevCtx cx, int slot0, int nbox, int var, double* out) {
+  pdl_wait();
   using L = Lay3<NC>;
   const int slot = slot0 + blockIdx.x;
   if ((int)blockIdx.x >= nbox) return;
@@ -1097,16 +1115,19 @@ __global__ void k_box_sums(DevCtx cx, int slot0, int nbox, int var, double* out)
 // (af_box_clear_cc :385), add constant (subtract_mean, m_af_multigrid.f90:247-257)
 // ---------------------------------------------------------------------------------------------
 __global__ void k_copy(double* __restrict__ dst, const double* __restrict__ src, size_t n) {
+  pdl_wait();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) dst[i] = src[i];
 }
 __global__ void k_fill(double* dst, double v, size_t n) {
+  pdl_wait();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) dst[i] = v;
 }
 __global__ void k_sub_scalar(double* dst, const double* scalar, size_t n) {
+  pdl_wait();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const double s = *scalar;
@@ -1118,6 +1139,7 @@ __global__ void k_sub_scalar(double* dst, const double* scalar, size_t n) {
 // ---------------------------------------------------------------------------------------------
 template <int NC>
 __global__ void k_unpack(double* var_base, const int* slots, int n, const double* packed) {
+  pdl_wait();
   using L = Lay3<NC>;
   constexpr int N2 = NC + 2;
   if ((int)blockIdx.x >= n || slots[blockIdx.x] < 0) return;
@@ -1131,6 +1153,7 @@ __global__ void k_unpack(double* var_base, const int* slots, int n, const double
 }
 template <int NC>
 __global__ void k_pack(const double* var_base, const int* slots, int n, double* packed) {
+  pdl_wait();
   using L = Lay3<NC>;
   constexpr int N2 = NC + 2;
   if ((int)blockIdx.x >= n || slots[blockIdx.x] < 0) return;
@@ -1165,6 +1188,7 @@ struct CoarseCtx {
 // coarse_solver_set_rhs_phi (m_coarse_solver.f90:286-338): b = rhs + bc_to_rhs * bc_val per face
 template <int NC>
 __global__ void k_cs_gather(DevCtx cx, CoarseCtx cs, int nbox1) {
+  pdl_wait();
   using L = Lay3<NC>;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int ncell = NC * NC * NC;
@@ -1193,6 +1217,7 @@ __global__ void k_cs_gather(DevCtx cx, CoarseCtx cs, int nbox1) {
 // out = (M applied along dimension d) in, M = Q^T (trans = 1) or Q (trans = 0); optional scaling of
 // the result by inv_eig (fused into the last forward transform)
 __global__ void k_cs_apply(CoarseCtx cs, const double* in, double* out, int d, int trans, int scale) {
+  pdl_wait();
   const int ntot = cs.nx[0] * cs.nx[1] * cs.nx[2];
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= ntot) return;
@@ -1212,6 +1237,7 @@ __global__ void k_cs_apply(CoarseCtx cs, const double* in, double* out, int d, i
 
 // general path: x = A^-1 b with the dense inverse computed on the host at set-up; one warp per row
 __global__ void k_cs_dense(CoarseCtx cs, const double* in, double* out) {
+  pdl_wait();
   const int n = cs.nx[0] * cs.nx[1] * cs.nx[2];
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -1226,6 +1252,7 @@ __global__ void k_cs_dense(CoarseCtx cs, const double* in, double* out) {
 // coarse_solver_get_phi (m_coarse_solver.f90:341-358)
 template <int NC>
 __global__ void k_cs_scatter(DevCtx cx, CoarseCtx cs, int nbox1, const double* x) {
+  pdl_wait();
   using L = Lay3<NC>;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int ncell = NC * NC * NC;

@@ -122,6 +122,12 @@ def build_workload(name, want_rhs=True):
         desc = ("S3: 1024^3-equivalent refined octree (BASELINE.json configs[4]): 512^3 uniform (levels 1-6) + level 7 "
                 "on all but the outermost box layer, 16^3 boxes, 1.04e9 cells, field_bc_homogeneous; it fits one B200 "
                 "and is the >=1e8-cell tree the north-star target is quoted on")
+    elif name == "S0":
+        tree = T.build_tree(2, 8, [8, 8], 7, None, coord_t=T.AF_CYL)
+        bc = W.bc_table(tree, lambda nb, c: (W.AF_BC_DIRICHLET, 0.0 if nb == 3 else 1.0) if (nb - 1) // 2 == 1
+                        else (W.AF_BC_NEUMANN, 0.0))
+        ids, rhs = W.random_rhs_on_leaves(tree)
+        desc = "S0: 2D cylindrical (BASELINE.json configs[0] stand-in), nc=8, coarse 8^2, 7 uniform levels (512^2 cells)"
     elif name == "S2":
         tree = T.channel_tree(8, 8, 9, 3)
         bc = W.bc_field_homogeneous(tree, 1.0)

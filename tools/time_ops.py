@@ -33,6 +33,9 @@ for lv in range(1, L + 1):
     cur = mg.last_cycle_ms() / 20
     print(f"  V-cycle(highest_lvl={lv}) {1e3 * cur:9.1f} us   (+{1e3 * (cur - prev):.1f} us for this level)")
     prev = cur
+if tree.ndim == 2:
+    M.mg_destroy(mg)
+    sys.exit(0)
 mg.set_profiling(True)
 for _ in range(reps):
     for lv in range(L, 1, -1):
