@@ -20,6 +20,12 @@ module m_af_multigrid_gpu
      real(c_double)     :: dr_base(3), r_base(3)
   end type afmg_opts
 
+  !> afmg_stencil_desc (include/afmg.h): one box whose operator is not the implicit constant Laplacian
+  type, bind(c) :: afmg_stencil_desc
+     integer(c_int32_t) :: box_id, op_stype, prolong_shape, prolong_stype, tag, cylindrical_gradient
+     integer(c_int64_t) :: op_offset, f_offset, prolong_offset
+  end type afmg_stencil_desc
+
   type, bind(c) :: afmg_tree
      integer(c_int32_t) :: highest_lvl, highest_id
      type(c_ptr) :: lvl_counts, lvl_ids, lvl, ix, parent, children, neighbors, neighbor_mat, r_min
@@ -38,6 +44,14 @@ module m_af_multigrid_gpu
      integer(c_int) function afmg_set_bc(h, n, ids, nbs, types, vals) bind(c, name="afmg_set_bc")
        import; type(c_ptr), value :: h; integer(c_int32_t), value :: n
        integer(c_int32_t), intent(in) :: ids(*), nbs(*), types(*); real(c_double), intent(in) :: vals(*)
+     end function
+     integer(c_int) function afmg_set_stencils(h, n, desc, blob, blob_len) bind(c, name="afmg_set_stencils")
+       import; type(c_ptr), value :: h; integer(c_int32_t), value :: n
+       type(afmg_stencil_desc), intent(in) :: desc(*); real(c_double), intent(in) :: blob(*)
+       integer(c_int64_t), value :: blob_len
+     end function
+     integer(c_int) function afmg_set_lsf_boundary_value(h, v) bind(c, name="afmg_set_lsf_boundary_value")
+       import; type(c_ptr), value :: h; real(c_double), value :: v
      end function
      integer(c_int) function afmg_upload(h, var, n, ids, packed) bind(c, name="afmg_upload")
        import; type(c_ptr), value :: h; integer(c_int32_t), value :: var, n
@@ -179,7 +193,81 @@ contains
        end do
     end do
     call check(afmg_set_bc(solvers(slot)%h, n_faces, f_ids, f_nbs, f_types, f_vals), "afmg_set_bc")
+    call sync_stencils(tree, mg, slot)
   end subroutine sync_tree
+
+  !> Ship the stencils mg_set_operators_lvl (m_af_multigrid.f90:1147-1185) stored in box%stencils for
+  !> every box that is not a plain constant-Laplacian box: variable / constant eps operators
+  !> (mg_box_lpld_stencil), level-set boxes (mg_box_lsf_stencil: v and f) and their prolongation
+  !> stencils.  The builders themselves stay in afivo (they call mg%lsf and friends).  Also called from
+  !> mg_gpu_update_operator_stencil after mg_update_operator_stencil changed eps / lsf stencils.
+  subroutine sync_stencils(tree, mg, slot)
+    use m_af_stencil, only: af_stencil_index, af_stencil_none, stencil_constant, stencil_variable
+    type(af_t), intent(inout) :: tree
+    type(mg_t), intent(in)    :: mg
+    integer, intent(in)       :: slot
+    type(afmg_stencil_desc), allocatable :: desc(:)
+    real(c_double), allocatable :: blob(:)
+    integer :: lvl, i, id, n, ix, ixp, pass
+    integer(c_int64_t) :: off
+
+    ! two passes: count (sizes), then fill
+    do pass = 1, 2
+       n = 0; off = 0
+       do lvl = 1, tree%highest_lvl
+          do i = 1, size(tree%lvls(lvl)%ids)
+             id = tree%lvls(lvl)%ids(i)
+             associate (box => tree%boxes(id))
+               if (iand(box%tag, mg%operator_mask) == mg_normal_box) cycle
+               ix = af_stencil_index(box, mg%operator_key)
+               if (ix == af_stencil_none) cycle
+               n = n + 1
+               if (pass == 2) then
+                  desc(n)%box_id = id; desc(n)%tag = box%tag
+                  desc(n)%op_stype = box%stencils(ix)%stype
+                  desc(n)%cylindrical_gradient = merge(1, 0, box%stencils(ix)%cylindrical_gradient)
+                  desc(n)%op_offset = off; desc(n)%f_offset = -1; desc(n)%prolong_shape = 0
+                  desc(n)%prolong_stype = 0; desc(n)%prolong_offset = 0
+               end if
+               if (box%stencils(ix)%stype == stencil_constant) then
+                  if (pass == 2) blob(off+1:off+size(box%stencils(ix)%c)) = box%stencils(ix)%c
+                  off = off + size(box%stencils(ix)%c)
+               else
+                  if (pass == 2) blob(off+1:off+size(box%stencils(ix)%v)) = &
+                       reshape(box%stencils(ix)%v, [size(box%stencils(ix)%v)])
+                  off = off + size(box%stencils(ix)%v)
+               end if
+               if (allocated(box%stencils(ix)%f)) then
+                  if (pass == 2) then
+                     desc(n)%f_offset = off
+                     blob(off+1:off+size(box%stencils(ix)%f)) = reshape(box%stencils(ix)%f, [size(box%stencils(ix)%f)])
+                  end if
+                  off = off + size(box%stencils(ix)%f)
+               end if
+               ixp = af_stencil_index(box, mg%prolongation_key)
+               if (lvl > 1 .and. ixp /= af_stencil_none) then
+                  if (pass == 2) then
+                     desc(n)%prolong_shape = box%stencils(ixp)%shape    ! af_stencil_p234 = 2, af_stencil_p248 = 3
+                     desc(n)%prolong_stype = box%stencils(ixp)%stype
+                     desc(n)%prolong_offset = off
+                  end if
+                  if (box%stencils(ixp)%stype == stencil_constant) then
+                     if (pass == 2) blob(off+1:off+size(box%stencils(ixp)%c)) = box%stencils(ixp)%c
+                     off = off + size(box%stencils(ixp)%c)
+                  else
+                     if (pass == 2) blob(off+1:off+size(box%stencils(ixp)%v)) = &
+                          reshape(box%stencils(ixp)%v, [size(box%stencils(ixp)%v)])
+                     off = off + size(box%stencils(ixp)%v)
+                  end if
+               end if
+             end associate
+          end do
+       end do
+       if (pass == 1) allocate(desc(max(n, 1)), blob(max(off, 1_c_int64_t)))
+    end do
+    call check(afmg_set_lsf_boundary_value(solvers(slot)%h, mg%lsf_boundary_value), "afmg_set_lsf_boundary_value")
+    call check(afmg_set_stencils(solvers(slot)%h, n, desc, blob, off), "afmg_set_stencils")
+  end subroutine sync_stencils
 
   !> Pack box%cc(:, :, :, iv) of a list of boxes and upload / download
   subroutine transfer(tree, slot, iv, var, ids, up)
@@ -271,12 +359,15 @@ contains
     call check(afmg_max_abs(solvers(slot)%h, afmg_tmp, val), "afmg_max_abs")
   end subroutine mg_gpu_tree_maxabs_tmp
 
-  !> mg_update_operator_stencil (m_af_multigrid.f90:1188-1214), constant-coefficient part
-  subroutine mg_gpu_update_operator_stencil(mg, slot)
-    type(mg_t), intent(in) :: mg
-    integer, intent(in)    :: slot
+  !> mg_update_operator_stencil (m_af_multigrid.f90:1188-1214): call after the reference routine rebuilt
+  !> the host stencils (new_lsf / new_eps); lambda and the explicit stencils are forwarded
+  subroutine mg_gpu_update_operator_stencil(tree, mg, slot)
+    type(af_t), intent(inout) :: tree
+    type(mg_t), intent(in)    :: mg
+    integer, intent(in)       :: slot
     call check(afmg_set_helmholtz_lambda(solvers(slot)%h, mg%helmholtz_lambda), "afmg_set_helmholtz_lambda")
     call check(afmg_update_operator_stencil(solvers(slot)%h), "afmg_update_operator_stencil")
+    call sync_stencils(tree, mg, slot)
   end subroutine mg_gpu_update_operator_stencil
 
   !> mg_destroy (m_af_multigrid.f90:111-115)
