@@ -71,6 +71,7 @@ SYMBOLS = {
     "afmg_update_operator_stencil": (C.c_int, [_H]),
     "afmg_upload": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
     "afmg_download": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
+    "afmg_upload_interior": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
     "afmg_upload_device": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
     "afmg_download_device": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
     "afmg_clear": (C.c_int, [_H, _I]),

@@ -1624,13 +1624,14 @@ int afmg_update_operator_stencil(afmg_handle* h) {
   return AFMG_OK;
 }
 
-static int transfer(afmg_handle* h, int var, int n, const int32_t* box_id, double* packed, bool up, bool device_ptr) {
+static int transfer(afmg_handle* h, int var, int n, const int32_t* box_id, double* packed, bool up, bool device_ptr,
+                    bool interior = false) {
   if (!h) return AFMG_ERR_ARG;
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
   if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
   if (n == 0) return AFMG_OK;
   CK(cudaSetDevice(h->device));
-  if (h->o.ndim == 2) return s2_transfer(h, var, n, box_id, packed, up, device_ptr);
+  if (h->o.ndim == 2) return s2_transfer(h, var, n, box_id, packed, up, device_ptr, interior);
   // slot < 0 marks a box owned by another rank: its packed record is skipped (k_pack / k_unpack)
   std::vector<int> slots(n);
   for (int q = 0; q < n; ++q) {
@@ -1639,19 +1640,24 @@ static int transfer(afmg_handle* h, int var, int n, const int32_t* box_id, doubl
     slots[q] = h->id2slot[id];
     if (h->nranks > 1 && h->h_owner[slots[q]] != h->me) slots[q] = -1;
   }
-  const size_t box_bytes = (size_t)h->box_len * sizeof(double);
+  const size_t rec_len = interior ? (size_t)h->o.n_cell * h->o.n_cell * h->o.n_cell : (size_t)h->box_len;
+  const size_t box_bytes = rec_len * sizeof(double);
   const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)256 << 20) / box_bytes));
   int rc = ensure_stage(h, device_ptr ? 16 : (size_t)chunk * box_bytes, (size_t)n);
   if (rc) return rc;
   CK(cudaMemcpyAsync(h->d_stage_slots, slots.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   for (int q0 = 0; q0 < n; q0 += chunk) {
     const int m = std::min(chunk, n - q0);
-    double* hp = packed + (size_t)q0 * h->box_len;
+    double* hp = packed + (size_t)q0 * rec_len;
     double* dp = device_ptr ? hp : h->d_stage;
     if (up) {
       if (!device_ptr) CK(cudaMemcpyAsync(dp, hp, (size_t)m * box_bytes, cudaMemcpyHostToDevice, h->stream));
       Launch L_(h, "unpack");
-      DISPATCH_NC(h, NC, { launch_k(h, k_unpack<NC>, m, 256, 0, h->d_cc[var], h->d_stage_slots + q0, m, dp); });
+      if (interior) {
+        DISPATCH_NC(h, NC, { launch_k(h, k_unpack_interior<NC>, m, 256, 0, h->d_cc[var], h->d_stage_slots + q0, m, dp); });
+      } else {
+        DISPATCH_NC(h, NC, { launch_k(h, k_unpack<NC>, m, 256, 0, h->d_cc[var], h->d_stage_slots + q0, m, dp); });
+      }
     } else {
       {
         Launch L_(h, "pack");
@@ -1669,6 +1675,9 @@ static int transfer(afmg_handle* h, int var, int n, const int32_t* box_id, doubl
 
 int afmg_upload(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, const double* packed) {
   return transfer(h, var, n, box_id, const_cast<double*>(packed), true, false);
+}
+int afmg_upload_interior(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, const double* packed) {
+  return transfer(h, var, n, box_id, const_cast<double*>(packed), true, false, true);
 }
 int afmg_download(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, double* packed) {
   return transfer(h, var, n, box_id, packed, false, false);

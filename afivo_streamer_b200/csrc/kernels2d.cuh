@@ -469,6 +469,16 @@ __global__ void k2_copy_boxes(double* var_base, const int* slots, int n, double*
   }
 }
 
+// interior cells only: packed holds cc(1:nc, 1:nc) per box
+__global__ void k2_unpack_interior(double* var_base, const int* slots, int n, const double* packed, int nc) {
+  pdl_wait();
+  const int q = blockIdx.x;
+  if (q >= n || slots[q] < 0) return;
+  double* a = var_base + (size_t)slots[q] * (nc + 2) * (nc + 2);
+  const double* b = packed + (size_t)q * nc * nc;
+  for (int t = threadIdx.x; t < nc * nc; t += blockDim.x) a[(t % nc + 1) + (nc + 2) * (t / nc + 1)] = b[t];
+}
+
 // ---- coarse grid: dense inverse of the BC-folded level-1 operator (cylindrical and variable stencils
 // are not separable); same matrix as coarse_solver_initialize (m_coarse_solver.f90:71-194, :442-491)
 struct Coarse2 {

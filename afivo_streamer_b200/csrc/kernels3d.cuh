@@ -1151,6 +1151,21 @@ __global__ void k_unpack(double* var_base, const int* slots, int n, const double
     box[q] = src[(k * N2 + j) * N2 + i];
   }
 }
+// interior cells only: packed holds cc(1:nc, 1:nc, 1:nc) per box (ghost cells of the record are kept)
+template <int NC>
+__global__ void k_unpack_interior(double* var_base, const int* slots, int n, const double* packed) {
+  pdl_wait();
+  using L = Lay3<NC>;
+  if ((int)blockIdx.x >= n || slots[blockIdx.x] < 0) return;
+  double* box = var_base + (size_t)slots[blockIdx.x] * L::BOX;
+  const double* src = packed + (size_t)blockIdx.x * (NC * NC * NC);
+  for (int q = threadIdx.x; q < 2 * L::NI; q += blockDim.x) {
+    const int o = (q < L::NI) ? q : (L::COL + q - L::NI);
+    int i, j, k;
+    L::uncell(o, i, j, k);
+    box[o] = src[((k - 1) * NC + (j - 1)) * NC + (i - 1)];
+  }
+}
 template <int NC>
 __global__ void k_pack(const double* var_base, const int* slots, int n, double* packed) {
   pdl_wait();

@@ -101,6 +101,18 @@ class mg_t:
         ids = np.ascontiguousarray(ids, np.int32)
         self._check(_lib.lib().afmg_upload(self._h, var, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)), host_ptr))
 
+    def upload_interior_ptr(self, var, ids, host_ptr):
+        """Interior cells only (nc^ndim doubles per box): what the rhs needs."""
+        ids = np.ascontiguousarray(ids, np.int32)
+        self._check(_lib.lib().afmg_upload_interior(self._h, var, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                    host_ptr))
+
+    def set_cc_interior(self, var, ids, data):
+        self._need_init()
+        data = np.ascontiguousarray(data, np.float64)
+        assert data.size == len(ids) * self._tree.nc ** self._tree.ndim
+        self.upload_interior_ptr(var, ids, data.ctypes.data)
+
     def download_ptr(self, var, ids, host_ptr):
         ids = np.ascontiguousarray(ids, np.int32)
         self._check(_lib.lib().afmg_download(self._h, var, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)), host_ptr))

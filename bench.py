@@ -348,8 +348,16 @@ def run_gpu(args):
     cu_fmg = mg.cell_updates(0, True)
 
     # ---- e2e: host buffers through the C ABI -----------------------------------------------
+    # e2e: rhs goes up as interior cells only (its ghost cells are never read), phi comes back with ghost cells
+    ncell = tree.nc ** tree.ndim
+    h_rhs_int = torch.empty(len(ids) * ncell, dtype=torch.float64).pin_memory()
+    nd = tree.ndim
+    full = h_rhs.view((len(ids),) + (tree.nc + 2,) * nd)
+    h_rhs_int.view((len(ids),) + (tree.nc,) * nd).copy_(full[(slice(None),) + (slice(1, -1),) * nd])
+    nbytes_up = h_rhs_int.numel() * 8
+
     def e2e_step():
-        mg.upload_ptr(M.I_RHS, ids, h_rhs.data_ptr())
+        mg.upload_interior_ptr(M.I_RHS, ids, h_rhs_int.data_ptr())
         M.mg_fas_vcycle(tree, mg, True)
         r = M.af_tree_maxabs_cc(tree, mg, M.I_TMP)
         mg.download_ptr(M.I_PHI, ids, h_phi.data_ptr())
@@ -368,7 +376,7 @@ def run_gpu(args):
     wall = time.perf_counter() - t0  # the C ABI calls are blocking: host wall time == end-to-end time
     wall_max = allmax(wall)
     e2e_val = cu * e2e_steps / wall_max
-    h2d_total, d2h_total = allsum(nbytes), allsum(nbytes + 8)
+    h2d_total, d2h_total = allsum(nbytes_up), allsum(nbytes + 8)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel timing with CUDA events (library profiling mode, no graph) -----------------

@@ -166,6 +166,10 @@ int afmg_set_stencils(afmg_handle* h, int32_t n, const afmg_stencil_desc* desc, 
  * device memory (for callers that keep rhs / phi resident). */
 int afmg_upload(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, const double* packed);
 int afmg_download(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, double* packed);
+/* upload of interior cells only: n boxes of nc^ndim doubles, cc(1:nc, 1:nc[, 1:nc]); ghost cells on the
+ * device are left as they are.  For the right-hand side, whose ghost cells are never read (callers set rhs
+ * on the interior of leaves only, src/m_field.f90:422-435): 30 % fewer bytes over PCIe for nc = 16. */
+int afmg_upload_interior(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, const double* packed);
 int afmg_upload_device(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id_host,
                        const double* packed_device);
 int afmg_download_device(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id_host,

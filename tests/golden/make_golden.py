@@ -16,17 +16,19 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from afivo_streamer_b200 import workloads as W  # noqa: E402
 from oracle.oracle import I_PHI, I_RHS, I_TMP, Oracle  # noqa: E402
-from util import TREES, all_ids, bc_mixed  # noqa: E402
+from util import TREES, TREES2D, all_ids, bc_mixed  # noqa: E402
 
 CASES = {
     "corner_nc8_l4": dict(),
     "uniform_nc16_l2": dict(),
     "multibox_coarse_nc8": dict(helmholtz_lambda=250.0),
+    "xy2d_uniform_nc8_l4": dict(),
+    "cyl2d_corner_nc8_l5": dict(helmholtz_lambda=30.0),
 }
 
 
 def run_case(name, opts, n_v=3):
-    tree = TREES[name]()
+    tree = (TREES.get(name) or TREES2D[name])()
     bc = W.bc_table(tree, bc_mixed)
     orc = Oracle(tree, **opts)
     orc.set_bc(bc)

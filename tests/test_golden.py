@@ -10,7 +10,7 @@ import pytest
 from afivo_streamer_b200 import mg as M
 from afivo_streamer_b200 import workloads as W
 
-from util import TREES, bc_mixed
+from util import TREES, TREES2D, bc_mixed
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "*.npz")))
@@ -40,7 +40,7 @@ def test_oracle_reproduces_golden(name):
 @pytest.mark.parametrize("name", CASES)
 def test_cuda_matches_golden(name):
     g, opts = _load(name)
-    tree = TREES[name]()
+    tree = (TREES.get(name) or TREES2D[name])()
     mg = M.mg_t(sides_bc=W.bc_table(tree, bc_mixed), **opts)
     M.mg_init(tree, mg)
     ids, rhs = W.random_rhs_on_leaves(tree)

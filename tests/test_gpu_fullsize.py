@@ -1,0 +1,100 @@
+"""-m gpu: BASELINE.json's full sizes through size-independent properties (the oracle needs minutes
+there): S1 = poisson_benchmark 16 16 5 (256^3) and the S3s shell-refined octree (1.1e8 cells)."""
+import numpy as np
+import pytest
+
+from afivo_streamer_b200 import mg as M
+from afivo_streamer_b200 import tree as T
+from afivo_streamer_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def leaves_of(tree):
+    return np.concatenate([tree.leaves(l) for l in range(1, tree.highest_lvl + 1)]).astype(np.int32)
+
+
+def solve(tree, bc, ids, rhs_interior, n_v=4):
+    mg = M.mg_t(sides_bc=bc)
+    M.mg_init(tree, mg)
+    mg.set_cc_interior(M.I_RHS, ids, rhs_interior)
+    hist = []
+    M.mg_fas_fmg(tree, mg, True, False)
+    hist.append(M.af_tree_maxabs_cc(tree, mg, M.I_TMP))
+    for _ in range(n_v):
+        M.mg_fas_vcycle(tree, mg, True)
+        hist.append(M.af_tree_maxabs_cc(tree, mg, M.I_TMP))
+    return mg, np.array(hist)
+
+
+def test_interior_upload_equals_full_upload():
+    tree = T.corner_refined_tree(3, 8, 8, 4)
+    ids, rhs = W.random_rhs_on_leaves(tree)
+    a = M.mg_t(sides_bc=W.bc_dirichlet_zero(tree))
+    M.mg_init(tree, a)
+    a.set_cc(M.I_RHS, ids, rhs)
+    b = M.mg_t(sides_bc=W.bc_dirichlet_zero(tree))
+    M.mg_init(tree, b)
+    b.set_cc_interior(M.I_RHS, ids, rhs[W.interior(tree)])
+    for m in (a, b):
+        M.mg_fas_fmg(tree, m, True, False)
+    assert np.array_equal(a.get_cc(M.I_PHI, ids), b.get_cc(M.I_PHI, ids))
+    assert np.array_equal(a.get_cc(M.I_RHS, ids)[W.interior(tree)], rhs[W.interior(tree)])
+    M.mg_destroy(a)
+    M.mg_destroy(b)
+
+
+def test_s1_full_size_convergence_and_linearity():
+    tree = T.uniform_tree(3, 16, 16, 5)  # 4681 boxes (afivo/tests/answers/test_refinement_3d), 256^3
+    assert tree.n_boxes == 4681
+    bc = W.bc_dirichlet_zero(tree)
+    ids = leaves_of(tree)
+    rng = np.random.default_rng(1)
+    r1 = rng.uniform(-1, 1, (len(ids), 16, 16, 16))
+    r2 = rng.uniform(-1, 1, (len(ids), 16, 16, 16))
+    m1, h1 = solve(tree, bc, ids, r1)
+    # residual falls by about an order of magnitude per V-cycle, monotonically (poisson_basic behaviour)
+    assert np.all(h1[1:] < 0.25 * h1[:-1]), h1
+    sample = ids[:: max(1, len(ids) // 64)]
+    p1 = m1.get_cc(M.I_PHI, sample)
+    M.mg_destroy(m1)
+    m2, _ = solve(tree, bc, ids, r2)
+    p2 = m2.get_cc(M.I_PHI, sample)
+    M.mg_destroy(m2)
+    # the cycle is a linear map of (phi, rhs) for homogeneous boundary conditions
+    m3, _ = solve(tree, bc, ids, 2.0 * r1 - 0.5 * r2)
+    p3 = m3.get_cc(M.I_PHI, sample)
+    M.mg_destroy(m3)
+    scale = np.max(np.abs(p1)) + np.max(np.abs(p2))
+    assert np.max(np.abs(p3 - (2.0 * p1 - 0.5 * p2))) <= 1e-10 * scale
+
+
+def test_s1_constant_solution_is_a_fixed_point():
+    # rhs = 0 with Dirichlet value 1 on every face: phi == 1 is reproduced exactly by every operation
+    tree = T.uniform_tree(3, 16, 16, 5)
+    bc = W.bc_table(tree, lambda nb, c: (W.AF_BC_DIRICHLET, 1.0))
+    mg = M.mg_t(sides_bc=bc)
+    M.mg_init(tree, mg)
+    M.mg_fas_fmg(tree, mg, True, False)
+    for _ in range(6):
+        M.mg_fas_vcycle(tree, mg, True)
+    ids = leaves_of(tree)[::97]
+    phi = mg.get_cc(M.I_PHI, ids)
+    assert np.max(np.abs(phi - 1.0)) <= 1e-12
+    assert M.af_tree_maxabs_cc(tree, mg, M.I_TMP) <= 1e-7  # residual = O(eps / dr^2)
+    M.mg_destroy(mg)
+
+
+def test_s3s_refined_octree_converges():
+    tree = T.shell_tree(16, 16, 5)  # 1.09e8 cells, closed refinement boundary
+    bc = W.bc_field_homogeneous(tree, 1.0)
+    ids = leaves_of(tree)
+    rng = np.random.default_rng(2)
+    rhs = rng.uniform(-1, 1, (len(ids), 16, 16, 16))
+    mg, h = solve(tree, bc, ids, rhs, n_v=5)
+    assert np.all(h[1:] < 0.3 * h[:-1]), h
+    # the potential obeys the boundary data: 0 at z = 0, 1 at z = 1 (ghost cell = 2 b - interior)
+    top = [b for b in tree.lvl_ids[-2] if tree.neighbors[b, 5] < 0 and not tree.has_children(np.array([b]))[0]][:4]
+    phi = mg.get_cc(M.I_PHI, np.array(top, np.int32))
+    assert np.allclose(0.5 * (phi[:, 17, 1:-1, 1:-1] + phi[:, 16, 1:-1, 1:-1]), 1.0, atol=1e-12)
+    M.mg_destroy(mg)

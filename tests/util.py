@@ -80,6 +80,13 @@ TREES = {
     "permuted_ids": lambda: T.corner_refined_tree(3, 8, 8, 3).permuted_ids(np.random.default_rng(7)),
 }
 
+# 2D trees of the golden fixtures (Cartesian and cylindrical, SURVEY config C1)
+TREES2D = {
+    "xy2d_uniform_nc8_l4": lambda: T.uniform_tree(2, 8, 8, 4),
+    "cyl2d_corner_nc8_l5": lambda: T.build_tree(2, 8, [8, 16], 5, lambda l, ix, c: np.all(ix == 1, axis=1),
+                                                r_max=[1.0, 2.0], coord_t=T.AF_CYL),
+}
+
 
 def stencils_from_oracle(tree, orc):
     """What the Fortran shim ships with afmg_set_stencils: the stencils mg_set_operators_lvl stored for
