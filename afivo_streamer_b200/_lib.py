@@ -16,7 +16,7 @@ AFMG_OK = 0
 AFMG_MAX_RANKS = 8
 AFMG_COMM_BLOB_BYTES = 192
 ERR_NAMES = {-1: "AFMG_ERR_ARG", -2: "AFMG_ERR_CUDA", -3: "AFMG_ERR_UNSUPPORTED", -4: "AFMG_ERR_STATE",
-             -5: "AFMG_ERR_SINGULAR", -6: "AFMG_ERR_COMM"}
+             -5: "AFMG_ERR_SINGULAR", -6: "AFMG_ERR_COMM", -7: "AFMG_ERR_NOT_CONVERGED"}
 
 
 class AfmgError(RuntimeError):
@@ -80,6 +80,7 @@ SYMBOLS = {
     "afmg_fas_fmg_async": (C.c_int, [_H, _I, _I, _I]),
     "afmg_fas_vcycle_async": (C.c_int, [_H, _I, _I, _I]),
     "afmg_sync": (C.c_int, [_H]),
+    "afmg_field_solve": (C.c_int, [_H, _I, C.c_double, C.c_double, _I, _I, _DP, _IP, _IP]),
     "afmg_gsrb_boxes": (C.c_int, [_H, _I, _I]),
     "afmg_gsrb_halfsweep": (C.c_int, [_H, _I, _I]),
     "afmg_gc_lvl": (C.c_int, [_H, _I, _I, _I]),

@@ -1756,6 +1756,45 @@ int afmg_fas_fmg(afmg_handle* h, int32_t set_residual, int32_t have_guess) {
   return afmg_sync(h);
 }
 
+int afmg_field_solve(afmg_handle* h, int32_t have_guess, double residual_threshold, double max_residual, int32_t max_fmg,
+                     int32_t n_vcycles, double* residuals, int32_t* n_fmg, int32_t* n_vc) {
+  if (!h || !residuals || !n_fmg || !n_vc) return AFMG_ERR_ARG;
+  *n_fmg = 0;
+  *n_vc = 0;
+  int rc, k = 0;
+  if (!have_guess) {
+    bool ok = false;
+    for (int i = 0; i < max_fmg; ++i) {
+      if ((rc = afmg_fas_fmg_async(h, 1, 1, 1))) return rc;
+      if ((rc = afmg_max_abs(h, AFMG_TMP, &residuals[k]))) return rc;
+      ++k;
+      ++*n_fmg;
+      if (residuals[k - 1] < residual_threshold) {
+        ok = true;
+        break;
+      }
+      if (i >= 2) {  // i > 2 in the reference's 1-based loop
+        const double lo = std::min({residuals[k - 3], residuals[k - 2], residuals[k - 1]});
+        const double hi = std::max({residuals[k - 3], residuals[k - 2], residuals[k - 1]});
+        const double ratio = lo / hi;
+        if (ratio < 2.0 && ratio > 0.5 && residuals[k - 1] < max_residual) {
+          ok = true;
+          break;
+        }
+      }
+    }
+    if (!ok) return h->fail(AFMG_ERR_NOT_CONVERGED, "no convergence in initial field computation after %d FMG cycles", max_fmg);
+  }
+  for (int i = 0; i < n_vcycles; ++i) {
+    if ((rc = afmg_fas_vcycle_async(h, 1, 0, 1))) return rc;
+    if ((rc = afmg_max_abs(h, AFMG_TMP, &residuals[k]))) return rc;
+    ++k;
+    ++*n_vc;
+    if (residuals[k - 1] < residual_threshold) break;
+  }
+  return afmg_sync(h);
+}
+
 // ---- single operations ------------------------------------------------------------------------------
 #define SINGLE_OP_PROLOGUE()          \
   if (!h) return AFMG_ERR_ARG;        \

@@ -352,6 +352,19 @@ def mg_fas_vcycle(tree: Tree, mg: mg_t, set_residual: bool, highest_lvl: Optiona
     mg._check(_lib.lib().afmg_fas_vcycle(mg._h, int(set_residual), int(highest_lvl or 0), int(standalone)))
 
 
+def field_solve(tree: Tree, mg: mg_t, have_guess: bool, residual_threshold: float, *, max_residual: float = 1e8,
+                max_initial_iterations: int = 100, num_vcycles: int = 2):
+    """The FMG / V-cycle convergence loop of field_compute (src/m_field.f90:491-524) run next to the
+    device; returns (residuals, n_fmg, n_vcycles)."""
+    mg._need_init()
+    res = np.zeros(max_initial_iterations + num_vcycles)
+    n_fmg, n_vc = C.c_int32(0), C.c_int32(0)
+    mg._check(_lib.lib().afmg_field_solve(mg._h, int(have_guess), float(residual_threshold), float(max_residual),
+                                          int(max_initial_iterations), int(num_vcycles),
+                                          res.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n_fmg), C.byref(n_vc)))
+    return res[: n_fmg.value + n_vc.value], n_fmg.value, n_vc.value
+
+
 def mg_update_operator_stencil(tree: Tree, mg: mg_t):
     """mg_update_operator_stencil (afivo/src/m_af_multigrid.f90:1188-1214)."""
     mg._need_init()

@@ -36,6 +36,7 @@ enum {
   AFMG_ERR_UNSUPPORTED = -3,  /* valid in the reference, not (yet) supported here          */
   AFMG_ERR_STATE = -4,        /* call order violated (e.g. solve before afmg_set_tree)     */
   AFMG_ERR_SINGULAR = -5,     /* coarse-grid operator is singular (all-Neumann, lambda=0)   */
+  AFMG_ERR_NOT_CONVERGED = -7, /* afmg_field_solve: residual criterion not met                  */
   AFMG_ERR_COMM = -6           /* a peer GPU did not reach a barrier in time               */
 };
 
@@ -189,6 +190,17 @@ int afmg_fas_vcycle(afmg_handle* h, int32_t set_residual, int32_t highest_lvl, i
 int afmg_fas_fmg_async(afmg_handle* h, int32_t set_residual, int32_t have_guess, int32_t n_cycles);
 int afmg_fas_vcycle_async(afmg_handle* h, int32_t set_residual, int32_t highest_lvl, int32_t n_cycles);
 int afmg_sync(afmg_handle* h);
+
+/* ---- the caller's convergence loop, run next to the device.  field_compute
+ * (src/m_field.f90:491-524): without a guess, repeat mg_fas_fmg(set_residual = T, have_guess = T) up to
+ * max_fmg times until the max-norm of the residual over the leaves is below residual_threshold, or has
+ * stalled (ratio of min / max over the last three cycles within (0.5, 2)) below max_residual; then up to
+ * n_vcycles mg_fas_vcycle(set_residual = T), stopping at the threshold.  Only the 8-byte max-norm crosses
+ * PCIe per cycle.  residuals receives the max-norms in order (capacity max_fmg + n_vcycles); n_fmg / n_vc
+ * the number of cycles run.  Returns AFMG_ERR_NOT_CONVERGED if the FMG loop ends without meeting either
+ * criterion (the reference: error stop "No convergence in initial field computation"). */
+int afmg_field_solve(afmg_handle* h, int32_t have_guess, double residual_threshold, double max_residual,
+                     int32_t max_fmg, int32_t n_vcycles, double* residuals, int32_t* n_fmg, int32_t* n_vc);
 
 /* ---- single operations (the mg_t per-level building blocks; exported for parity tests) -------- */
 int afmg_gsrb_boxes(afmg_handle* h, int32_t lvl, int32_t type_cycle /*1 = down, 3 = up*/); /* :648-687 */

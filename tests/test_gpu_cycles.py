@@ -101,3 +101,31 @@ def test_errors_are_codes_not_aborts():
     M.mg_destroy(mg)
     with pytest.raises(M.AfmgError):
         M.mg_fas_vcycle(tree, mg, True)
+
+
+def test_field_solve_loop_matches_explicit_cycles():
+    """afmg_field_solve = the FMG / V-cycle loop of field_compute (src/m_field.f90:491-524)."""
+    tree = T.corner_refined_tree(3, 8, 8, 4)
+    bc = W.bc_table(tree, bc_mixed)
+    ids, rhs = W.random_rhs_on_leaves(tree)
+    a = M.mg_t(sides_bc=bc)
+    M.mg_init(tree, a)
+    a.set_cc(M.I_RHS, ids, rhs)
+    res, n_fmg, n_vc = M.field_solve(tree, a, False, 1e-4, num_vcycles=2)
+    b = M.mg_t(sides_bc=bc)
+    M.mg_init(tree, b)
+    b.set_cc(M.I_RHS, ids, rhs)
+    ref = []
+    for _ in range(n_fmg):
+        M.mg_fas_fmg(tree, b, True, True)
+        ref.append(M.af_tree_maxabs_cc(tree, b, M.I_TMP))
+    for _ in range(n_vc):
+        M.mg_fas_vcycle(tree, b, True)
+        ref.append(M.af_tree_maxabs_cc(tree, b, M.I_TMP))
+    assert n_fmg >= 2 and np.array_equal(res, np.array(ref))
+    assert res[n_fmg - 1] < 1e-4 and np.all(res[: n_fmg - 1] >= 1e-4)
+    assert np.array_equal(a.get_cc(M.I_PHI, all_ids(tree)), b.get_cc(M.I_PHI, all_ids(tree)))
+    with pytest.raises(M.AfmgError):
+        M.field_solve(tree, a, False, 1e-300, max_residual=0.0, max_initial_iterations=3)
+    M.mg_destroy(a)
+    M.mg_destroy(b)
