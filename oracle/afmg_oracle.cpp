@@ -945,7 +945,17 @@ int coarse_solver_initialize(Tree& t) {
   int nx[3] = {1, 1, 1};
   for (int d = 0; d < ND; ++d) nx[d] = t.coarse_grid_size[d];
   const int n = nx[0] * nx[1] * nx[2];
-  const int bw = (ND == 3) ? nx[0] * nx[1] : nx[0];
+  // periodic dimensions (the level-1 boxes at the domain edge then have a real neighbour there) couple
+  // the first and last cells: the band becomes the whole matrix
+  bool any_periodic = false;
+  for (int ib = 0; ib < nb1; ++ib)
+    for (int nb = 1; nb <= 2 * ND; ++nb) {
+      const Box& b = t.boxes[ids1[ib]];
+      const int d = nb_dim(nb);
+      const bool at_edge = nb_low(nb) ? (b.ix[d] == 1) : (b.ix[d] * nc == nx[d]);
+      if (at_edge && b.neighbors[nb - 1] > af_no_box) any_periodic = true;
+    }
+  const int bw = any_periodic ? n - 1 : ((ND == 3) ? nx[0] * nx[1] : nx[0]);
   const int nface = (ND == 3) ? nc * nc : nc;
   t.cs_n = n;
   t.cs_bw = bw;
@@ -1008,11 +1018,14 @@ int coarse_solver_initialize(Tree& t) {
             if (s[m + 1] == 0.0) continue;
             int d = m >> 1, sgn = (m & 1) ? 1 : -1;
             int q = gi[d] + sgn;
-            if (q < 0 || q >= nx[d]) {
-              std::fprintf(stderr, "coarse matrix: coupling outside the grid (periodic not supported)\n");
-              return 2;
-            }
             int c = r + sgn * gstride[d];
+            if (q < 0 || q >= nx[d]) {
+              if (!any_periodic) {
+                std::fprintf(stderr, "coarse matrix: coupling outside the grid\n");
+                return 2;
+              }
+              c = r - sgn * (nx[d] - 1) * gstride[d];  // periodic wrap (Hypre: HYPRE_StructGridSetPeriodic)
+            }
             ab[(size_t)(bw + r - c) + (size_t)ldab * c] += s[m + 1];
           }
         }

@@ -129,3 +129,21 @@ def test_field_solve_loop_matches_explicit_cycles():
         M.field_solve(tree, a, False, 1e-300, max_residual=0.0, max_initial_iterations=3)
     M.mg_destroy(a)
     M.mg_destroy(b)
+
+
+PERIODIC = {
+    "periodic_xy_single_coarse_box": lambda: T.uniform_tree(3, 8, 8, 3, periodic=[True, True, False]),
+    "periodic_x_multibox_refined": lambda: T.build_tree(3, 8, [16, 8, 8], 3, lambda l, ix, c: c[:, 2] < 0.55,
+                                                        periodic=[True, False, False]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(PERIODIC))
+def test_periodic_domains(name):
+    """tree%periodic (m_af_types.f90:345): neighbours wrap around, the coarse grid couples first and last
+    cells (HYPRE_StructGridSetPeriodic, m_coarse_solver.f90:97-104)."""
+    tree = PERIODIC[name]()
+    ho, hg, a, b = run_both(tree, bc_mixed)
+    assert ho[-1] < 0.1 * ho[0]
+    assert np.all(np.abs(ho - hg) <= 1e-9 * ho[0] + 1e-6 * ho), (ho, hg)
+    assert np.max(np.abs(a - b)) <= RTOL * np.max(np.abs(a))
