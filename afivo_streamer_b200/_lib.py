@@ -81,6 +81,14 @@ SYMBOLS = {
     "afmg_fas_vcycle_async": (C.c_int, [_H, _I, _I, _I]),
     "afmg_sync": (C.c_int, [_H]),
     "afmg_field_solve": (C.c_int, [_H, _I, C.c_double, C.c_double, _I, _I, _DP, _IP, _IP]),
+    "afmg_compute_phi_gradient": (C.c_int, [_H, C.c_double, _I]),
+    "afmg_compute_field_norm": (C.c_int, [_H]),
+    "afmg_gc_tree": (C.c_int, [_H, _I, _I]),
+    "afmg_field_from_potential": (C.c_int, [_H, C.c_double]),
+    "afmg_set_fld_bc": (C.c_int, [_H, _I, _IP, _IP, _IP, _DP]),
+    "afmg_set_lsf_distances": (C.c_int, [_H, _I, _IP, _IP, _IP, _DP, _DP]),
+    "afmg_upload_fc": (C.c_int, [_H, _I, _IP, C.c_void_p]),
+    "afmg_download_fc": (C.c_int, [_H, _I, _IP, C.c_void_p]),
     "afmg_gsrb_boxes": (C.c_int, [_H, _I, _I]),
     "afmg_gsrb_halfsweep": (C.c_int, [_H, _I, _I]),
     "afmg_gc_lvl": (C.c_int, [_H, _I, _I, _I]),

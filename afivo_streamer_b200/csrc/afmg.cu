@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/afmg.h"
+#include "field.cuh"
 #include "kernels2d.cuh"
 #include "kernels3d.cuh"
 
@@ -42,11 +43,13 @@ struct ProfEntry {
 
 namespace {
 struct S2State;  // 2D solver state (afmg2d.inc)
+struct FieldState;  // field from potential (afmg_field.inc)
 }
 
 struct afmg_handle {
   afmg_opts o{};
   S2State* s2 = nullptr;
+  FieldState* fs = nullptr;
   std::string err;
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -1091,6 +1094,7 @@ int finish_op(afmg_handle* h) {
 }
 
 #include "afmg2d.inc"
+#include "afmg_field.inc"
 
 }  // namespace
 
@@ -1171,6 +1175,7 @@ int afmg_destroy(afmg_handle* h) {
   cudaStreamSynchronize(h->stream);
   drop_graphs(h);
   s2_free(h);
+  fs_free(h);
   close_peers(h);
   cudaFree(h->d_slab);
   cudaFree(h->d_owner);
@@ -1203,6 +1208,7 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   drop_graphs(h);
+  fs_free(h);  // field data (fc, norm, eps, level-set distances) belongs to the previous tree
   h->have_tree = false;
   h->cs_ready = false;
   h->resid_fresh = false;
@@ -1509,6 +1515,7 @@ int afmg_set_stencils(afmg_handle* h, int32_t n, const afmg_stencil_desc* desc, 
   drop_graphs(h);
   h->cs_ready = false;
   h->resid_fresh = false;
+  if (h->fs) h->fs->veps_valid = false;  // box tags change
   if (h->o.ndim == 2) return s2_set_stencils(h, n, desc, blob, blob_len);
   const int total = h->nslots, nc = h->o.n_cell, ncell = nc * nc * nc;
   h->h_opk.assign(total, 0);
@@ -1628,6 +1635,11 @@ static int transfer(afmg_handle* h, int var, int n, const int32_t* box_id, doubl
                     bool interior = false) {
   if (!h) return AFMG_ERR_ARG;
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
+  if (var == AFMG_EPS || var == AFMG_FLD) {  // extra variables of the field computation (afmg_field.inc)
+    if (device_ptr || interior) return h->fail(AFMG_ERR_UNSUPPORTED, "AFMG_EPS / AFMG_FLD move through afmg_upload / afmg_download only");
+    if (var == AFMG_EPS && up && h->fs) h->fs->veps_valid = false;
+    return fs_transfer(h, var, n, box_id, packed, up);
+  }
   if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
   if (n == 0) return AFMG_OK;
   CK(cudaSetDevice(h->device));
@@ -2132,5 +2144,7 @@ int32_t afmg_owner_of_box(const afmg_handle* h, int32_t box_id) {
   if (!h || !h->have_tree || box_id < 1 || box_id > h->highest_id || h->id2slot[box_id] < 0) return -1;
   return h->h_owner[h->id2slot[box_id]];
 }
+
+#include "afmg_field_api.inc"
 
 }  // extern "C"

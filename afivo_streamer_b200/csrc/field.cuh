@@ -1,0 +1,395 @@
+// Field from potential on the device: mg_compute_phi_gradient, mg_box_lpl_gradient,
+// mg_box_lpllsf_gradient, mg_box_field_norm (afivo/src/m_af_multigrid.f90:1857-2137) and the af_gc_tree of
+// the field norm that field_from_potential issues afterwards (src/m_field.f90:531-548; cc_methods of
+// i_electric_fld = af_bc_neumann_zero + af_gc_interp, src/m_field.f90:392-393; af_gc_interp
+// m_af_ghostcell.f90:394-498).  fp64, -fmad=false: bit-identical to the CPU oracle.
+//
+// The face-centred field keeps the reference's own record: fc(nc+1, nc+1[, nc+1], NDIM) per box, first index
+// fastest (m_af_core.f90:552).  The field norm is one more cell-centred variable in the box layout of
+// layout.cuh (3D) / the reference order (2D).
+#pragma once
+#include "kernels2d.cuh"
+#include "kernels3d.cuh"
+
+namespace afmg {
+
+#define AFMG_MAX_LVL 31  // lvls(1:30) in the reference (m_af_types.f90:13)
+
+struct FieldCtx {
+  double* fc;                 // [nslots * ND*(NC+1)^ND]
+  double* fld;                // [nslots * BOX] field norm (i_norm)
+  const double* eps;          // [nslots * BOX] tree%mg_i_eps, or null
+  const unsigned char* veps;  // [nslots] 1: iand(box%tag, operator_mask) == mg_veps_box; may be null
+  const double* bc_c;         // [nbc*3]   boundary rule of the field norm per physical face (c0, c1, c2)
+  const double* bc_B;         // [nbc*NF]  its boundary values (NF = nc^2 in 3D, nc in 2D)
+  double lsf_value;           // mg%lsf_boundary_value
+  double inv_dr[AFMG_MAX_LVL][3];  // fac / box%dr per level
+};
+
+// ---------------------------------------------------------------------------------------------
+// 3D
+// ---------------------------------------------------------------------------------------------
+template <int NC>
+struct Fc3 {
+  static constexpr int N1 = NC + 1, PER = N1 * N1 * N1, LEN = 3 * PER;
+  static AFMG_HD int at(int i, int j, int k, int d) { return d * PER + (i - 1) + N1 * ((j - 1) + N1 * (k - 1)); }
+};
+
+// fc(i,j,k,d) of mg_box_lpl_gradient from a box record S holding interior + face ghosts (shared or global)
+template <int NC>
+__device__ __forceinline__ double face_val3(const double* S, const double* E, double idr, int d, int i, int j, int k) {
+  using L = Lay3<NC>;
+  int il = i, jl = j, kl = k;
+  if (d == 0) --il;
+  else if (d == 1) --jl;
+  else --kl;
+  const int qh = L::cell(i, j, k), ql = L::cell(il, jl, kl);
+  const double hi = S[qh], lo = S[ql];
+  if (E) {  // box boundaries of a variable-eps box (:1938-1997)
+    const int pos = (d == 0) ? i : (d == 1 ? j : k);
+    if (pos == 1 || pos == NC + 1) {
+      const double eh = E[qh], el = E[ql];
+      const double eg = (pos == 1) ? el : eh;
+      return 2 * idr * (hi - lo) * eg / (eh + el);
+    }
+  }
+  return idr * (hi - lo);
+}
+
+// mg_box_lpl_gradient (+ mg_box_field_norm) for boxes [slot0, slot0+nbox): one CTA per box, phi by TMA
+template <int NC>
+__global__ void __launch_bounds__(256) k_grad3(DevCtx cx, FieldCtx fx, int slot0, int nbox, int with_norm) {
+  using L = Lay3<NC>;
+  using F = Fc3<NC>;
+  constexpr int COL = L::COL, BOX = L::BOX, NI = L::NI, N1 = NC + 1;
+  extern __shared__ __align__(128) double S[];  // 2*COL
+  __shared__ uint64_t bar;
+  const int slot = slot0 + blockIdx.x;
+  const int t = threadIdx.x;
+  if (t == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (t == 0) {
+    mbar_expect_tx(&bar, 2 * COL * 8);
+    bulk_g2s(S, cx.cc[V_PHI] + (size_t)slot * BOX, 2 * COL * 8, &bar);
+  }
+  const int lv = cx.lvl[slot];
+  const double idr[3] = {fx.inv_dr[lv][0], fx.inv_dr[lv][1], fx.inv_dr[lv][2]};
+  const double* E = (fx.veps && fx.veps[slot]) ? fx.eps + (size_t)slot * BOX : nullptr;
+  double* fcb = fx.fc + (size_t)slot * F::LEN;
+  mbar_wait(&bar, 0);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const int ni = (d == 0) ? N1 : NC, nj = (d == 1) ? N1 : NC, nk = (d == 2) ? N1 : NC;
+    for (int n = t; n < ni * nj * nk; n += 256) {
+      const int i = n % ni + 1, j = (n / ni) % nj + 1, k = n / (ni * nj) + 1;
+      fcb[F::at(i, j, k, d)] = face_val3<NC>(S, E, idr[d], d, i, j, k);
+    }
+  }
+  if (!with_norm) return;
+  double* out = fx.fld + (size_t)slot * BOX;
+  for (int n = t; n < 2 * NI; n += 256) {
+    const int q = (n < NI) ? n : COL + (n - NI);
+    int i, j, k;
+    L::uncell(q, i, j, k);
+    const double a = face_val3<NC>(S, E, idr[0], 0, i, j, k) + face_val3<NC>(S, E, idr[0], 0, i + 1, j, k);
+    const double b = face_val3<NC>(S, E, idr[1], 1, i, j, k) + face_val3<NC>(S, E, idr[1], 1, i, j + 1, k);
+    const double c = face_val3<NC>(S, E, idr[2], 2, i, j, k) + face_val3<NC>(S, E, idr[2], 2, i, j, k + 1);
+    out[q] = 0.5 * sqrt(a * a + b * b + c * c);
+  }
+}
+
+// mg_box_field_norm (:2023-2051) from the stored fc, boxes [slot0, slot0+nbox)
+template <int NC>
+__device__ __forceinline__ void norm_from_fc3(const double* fcb, double* out, int t, int nt) {
+  using L = Lay3<NC>;
+  using F = Fc3<NC>;
+  for (int n = t; n < 2 * L::NI; n += nt) {
+    const int q = (n < L::NI) ? n : L::COL + (n - L::NI);
+    int i, j, k;
+    L::uncell(q, i, j, k);
+    const double a = fcb[F::at(i, j, k, 0)] + fcb[F::at(i + 1, j, k, 0)];
+    const double b = fcb[F::at(i, j, k, 1)] + fcb[F::at(i, j + 1, k, 1)];
+    const double c = fcb[F::at(i, j, k, 2)] + fcb[F::at(i, j, k + 1, 2)];
+    out[q] = 0.5 * sqrt(a * a + b * b + c * c);
+  }
+}
+template <int NC>
+__global__ void __launch_bounds__(256) k_norm3(FieldCtx fx, int slot0, int nbox) {
+  const int slot = slot0 + blockIdx.x;
+  norm_from_fc3<NC>(fx.fc + (size_t)slot * Fc3<NC>::LEN, fx.fld + (size_t)slot * Lay3<NC>::BOX, threadIdx.x, 256);
+}
+
+// mg_box_lpllsf_gradient (:2055-2137) on the leaves that hold a level-set boundary: entries e of box b =
+// the box's sparse distance stencil (cells in IJK order with any(dd < 1)).  The reference's sequential loop
+// lets the low-side write of cell i+1 win over the high-side write of cell i on their common face; two
+// phases separated by a barrier give the same result in parallel.  Then the norm of the box is redone.
+template <int NC>
+__global__ void __launch_bounds__(256) k_lsf_fix3(DevCtx cx, FieldCtx fx, const int* slots, const int* eoff,
+                                                  const int* ecell, const double* edd, const double* elsf, int with_norm) {
+  using L = Lay3<NC>;
+  using F = Fc3<NC>;
+  const int slot = slots[blockIdx.x];
+  const int e0 = eoff[blockIdx.x], e1 = eoff[blockIdx.x + 1];
+  const int lv = cx.lvl[slot];
+  const double* phi = cx.cc[V_PHI] + (size_t)slot * L::BOX;
+  double* fcb = fx.fc + (size_t)slot * F::LEN;
+  const double bc = fx.lsf_value;
+  for (int phase = 0; phase < 2; ++phase) {
+    for (int n = threadIdx.x; n < 3 * (e1 - e0); n += 256) {
+      const int e = e0 + n / 3, d = n % 3;
+      if (!(elsf[e] >= 0)) continue;
+      int q[3] = {ecell[3 * e], ecell[3 * e + 1], ecell[3 * e + 2]};
+      const double p = phi[L::interior(q[0], q[1], q[2])];
+      const double idr = fx.inv_dr[lv][d];
+      if (phase == 0) {
+        const double dd = edd[6 * e + 2 * d + 1];
+        q[d] += 1;
+        if (dd < 1) fcb[F::at(q[0], q[1], q[2], d)] = idr * (bc - p) / dd;
+      } else {
+        const double dd = edd[6 * e + 2 * d];
+        if (dd < 1) fcb[F::at(q[0], q[1], q[2], d)] = idr * (p - bc) / dd;
+      }
+    }
+    __syncthreads();
+  }
+  if (with_norm) norm_from_fc3<NC>(fcb, fx.fld + (size_t)slot * L::BOX, threadIdx.x, 256);
+}
+
+// af_gc_box for the field norm (cx.cc[V_PHI] must point at it): neighbour copy, bc_to_gc with the variable's
+// own boundary rule, af_gc_interp on refinement boundaries; then edges and corners.
+template <int NC>
+__global__ void __launch_bounds__(256) k_gc_fld3(DevCtx cx, FieldCtx fx, int slot0, int nbox, int corners) {
+  using L = Lay3<NC>;
+  constexpr int H = L::H;
+  const int slot = slot0 + blockIdx.x;
+  double* base = cx.cc[V_PHI];
+  double* box = base + (size_t)slot * L::BOX;
+  const double third = 1 / 3.0, sixth = 1 / 6.0;
+  for (int n = threadIdx.x; n < 6 * L::NC2; n += blockDim.x) {
+    const int f = n / L::NC2, rr = n % L::NC2;
+    const int a = rr % NC + 1, b = rr / NC + 1;
+    const int d = f >> 1, hi = f & 1;
+    const int ta = (d == 0) ? 1 : 0, tb = (d == 2) ? 1 : 2;
+    int q[3];
+    q[ta] = a;
+    q[tb] = b;
+    const int nb = cx.nbr[slot * 6 + f];
+    double v;
+    if (nb >= 0) {
+      q[d] = hi ? 1 : NC;
+      v = ldcell<NC>(base + (size_t)nb * L::BOX, q[0], q[1], q[2]);
+    } else {
+      const int row = cx.aux[slot * 6 + f];
+      if (row < cx.rb_row0) {  // physical boundary: bc_to_gc
+        const double* rc = fx.bc_c + 3 * row;
+        const double B = fx.bc_B[(size_t)row * L::NC2 + rr];
+        q[d] = hi ? NC : 1;
+        const double x1 = ldcell<NC>(box, q[0], q[1], q[2]);
+        q[d] = hi ? NC - 1 : 2;
+        const double x2 = ldcell<NC>(box, q[0], q[1], q[2]);
+        v = (rc[0] * B + rc[1] * x1) + rc[2] * x2;
+      } else {  // af_gc_interp
+        const int p = cx.parent[slot], cof = cx.coff[slot];
+        const double* P = base + (size_t)cx.nbr[p * 6 + f] * L::BOX;
+        const int a1 = ((cof >> ta) & 1) * H + ((a + 1) >> 1), a2 = a1 + 1 - 2 * (a & 1);
+        const int b1 = ((cof >> tb) & 1) * H + ((b + 1) >> 1), b2 = b1 + 1 - 2 * (b & 1);
+        int c[3];
+        c[d] = hi ? 1 : NC;
+        c[ta] = a1;
+        c[tb] = b1;
+        const double v11 = ldcell<NC>(P, c[0], c[1], c[2]);
+        c[ta] = a2;
+        const double v21 = ldcell<NC>(P, c[0], c[1], c[2]);
+        c[ta] = a1;
+        c[tb] = b2;
+        const double v12 = ldcell<NC>(P, c[0], c[1], c[2]);
+        q[d] = hi ? NC : 1;
+        const double vf = ldcell<NC>(box, q[0], q[1], q[2]);
+        // order of the two sixth terms in the reference: dims 1, 2: (c2,c1) then (c1,c2); dim 3: (c1,c2) first
+        v = (d == 2) ? (third * v11 + sixth * v12 + sixth * v21 + third * vf)
+                     : (third * v11 + sixth * v21 + sixth * v12 + third * vf);
+      }
+    }
+    box[L::face(f, a, b)] = v;
+  }
+  if (corners) {
+    __syncthreads();
+    gc_edges_corners<NC>(cx, slot, V_PHI);
+  }
+}
+
+// plain records (fc) to / from a packed buffer in box order
+__global__ void k_rec_copy(double* base, const int* slots, int n, double* packed, int rec_len, int to_device) {
+  const int s = slots[blockIdx.x];
+  if (s < 0) return;
+  double* a = base + (size_t)s * rec_len;
+  double* b = packed + (size_t)blockIdx.x * rec_len;
+  for (int q = threadIdx.x; q < rec_len; q += blockDim.x) {
+    if (to_device) a[q] = b[q];
+    else b[q] = a[q];
+  }
+}
+
+}  // namespace afmg
+
+// ---------------------------------------------------------------------------------------------
+// 2D (box records in the reference order cc(0:nc+1, 0:nc+1))
+// ---------------------------------------------------------------------------------------------
+namespace afmg2 {
+
+template <int NC>
+struct Fc2 {
+  static constexpr int N1 = NC + 1, PER = N1 * N1, LEN = 2 * PER;
+  __host__ __device__ static int at(int i, int j, int d) { return d * PER + (i - 1) + N1 * (j - 1); }
+};
+
+template <int NC>
+__device__ __forceinline__ double face_val2(const double* S, const double* E, double idr, int d, int i, int j) {
+  using B = B2<NC>;
+  const int qh = B::at(i, j), ql = (d == 0) ? B::at(i - 1, j) : B::at(i, j - 1);
+  const double hi = S[qh], lo = S[ql];
+  if (E) {
+    const int pos = (d == 0) ? i : j;
+    if (pos == 1 || pos == NC + 1) {
+      const double eh = E[qh], el = E[ql];
+      const double eg = (pos == 1) ? el : eh;
+      return 2 * idr * (hi - lo) * eg / (eh + el);
+    }
+  }
+  return idr * (hi - lo);
+}
+
+template <int NC>
+__device__ __forceinline__ void norm_from_fc2(const double* fcb, double* out, int t, int nt) {
+  using B = B2<NC>;
+  using F = Fc2<NC>;
+  for (int n = t; n < NC * NC; n += nt) {
+    const int i = n % NC + 1, j = n / NC + 1;
+    const double a = fcb[F::at(i, j, 0)] + fcb[F::at(i + 1, j, 0)];
+    const double b = fcb[F::at(i, j, 1)] + fcb[F::at(i, j + 1, 1)];
+    out[B::at(i, j)] = 0.5 * sqrt(a * a + b * b);
+  }
+}
+
+template <int NC>
+__global__ void k2_grad(Ctx cx, afmg::FieldCtx fx, int slot0, int nbox, int with_norm) {
+  using B = B2<NC>;
+  using F = Fc2<NC>;
+  constexpr int N1 = NC + 1;
+  const int slot = slot0 + blockIdx.x;
+  const double* S = cx.cc[V_PHI] + (size_t)slot * B::BOX;
+  const int lv = cx.lvl[slot];
+  const double* E = (fx.veps && fx.veps[slot]) ? fx.eps + (size_t)slot * B::BOX : nullptr;
+  double* fcb = fx.fc + (size_t)slot * F::LEN;
+  for (int d = 0; d < 2; ++d) {
+    const int ni = (d == 0) ? N1 : NC, nj = (d == 1) ? N1 : NC;
+    const double idr = fx.inv_dr[lv][d];
+    for (int n = threadIdx.x; n < ni * nj; n += blockDim.x) {
+      const int i = n % ni + 1, j = n / ni + 1;
+      fcb[F::at(i, j, d)] = face_val2<NC>(S, E, idr, d, i, j);
+    }
+  }
+  if (!with_norm) return;
+  __syncthreads();
+  norm_from_fc2<NC>(fcb, fx.fld + (size_t)slot * B::BOX, threadIdx.x, blockDim.x);
+}
+
+template <int NC>
+__global__ void k2_norm(afmg::FieldCtx fx, int slot0, int nbox) {
+  const int slot = slot0 + blockIdx.x;
+  norm_from_fc2<NC>(fx.fc + (size_t)slot * Fc2<NC>::LEN, fx.fld + (size_t)slot * B2<NC>::BOX, threadIdx.x, blockDim.x);
+}
+
+template <int NC>
+__global__ void k2_lsf_fix(Ctx cx, afmg::FieldCtx fx, const int* slots, const int* eoff, const int* ecell, const double* edd,
+                           const double* elsf, int with_norm) {
+  using B = B2<NC>;
+  using F = Fc2<NC>;
+  const int slot = slots[blockIdx.x];
+  const int e0 = eoff[blockIdx.x], e1 = eoff[blockIdx.x + 1];
+  const int lv = cx.lvl[slot];
+  const double* phi = cx.cc[V_PHI] + (size_t)slot * B::BOX;
+  double* fcb = fx.fc + (size_t)slot * F::LEN;
+  const double bc = fx.lsf_value;
+  for (int phase = 0; phase < 2; ++phase) {
+    for (int n = threadIdx.x; n < 2 * (e1 - e0); n += blockDim.x) {
+      const int e = e0 + n / 2, d = n % 2;
+      if (!(elsf[e] >= 0)) continue;
+      int q[2] = {ecell[2 * e], ecell[2 * e + 1]};
+      const double p = phi[B::at(q[0], q[1])];
+      const double idr = fx.inv_dr[lv][d];
+      if (phase == 0) {
+        const double dd = edd[4 * e + 2 * d + 1];
+        q[d] += 1;
+        if (dd < 1) fcb[F::at(q[0], q[1], d)] = idr * (bc - p) / dd;
+      } else {
+        const double dd = edd[4 * e + 2 * d];
+        if (dd < 1) fcb[F::at(q[0], q[1], d)] = idr * (p - bc) / dd;
+      }
+    }
+    __syncthreads();
+  }
+  if (with_norm) norm_from_fc2<NC>(fcb, fx.fld + (size_t)slot * B::BOX, threadIdx.x, blockDim.x);
+}
+
+// af_gc_box of the field norm in 2D: af_gc_interp (m_af_ghostcell.f90:429-447) on refinement boundaries
+template <int NC>
+__global__ void k2_gc_fld(Ctx cx, afmg::FieldCtx fx, int slot0, int nbox, int corners) {
+  using B = B2<NC>;
+  constexpr int H = NC / 2;
+  const int slot = slot0 + blockIdx.x;
+  double* vb = fx.fld;
+  double* box = vb + (size_t)slot * B::BOX;
+  const double third = 1 / 3.0, sixth = 1 / 6.0;
+  for (int n = threadIdx.x; n < 4 * NC; n += blockDim.x) {
+    const int f = n / NC, a = n % NC + 1;
+    const int d = f >> 1, hi = f & 1, td = 1 - d;
+    int q[2];
+    q[td] = a;
+    const int nb = cx.nbr[slot * 4 + f];
+    double v;
+    if (nb >= 0) {
+      q[d] = hi ? 1 : NC;
+      v = vb[(size_t)nb * B::BOX + B::at(q[0], q[1])];
+    } else {
+      const int row = cx.aux[slot * 4 + f];
+      if (row < cx.rb_row0) {
+        const double* rc = fx.bc_c + 3 * row;
+        const double Bv = fx.bc_B[(size_t)row * NC + (a - 1)];
+        q[d] = hi ? NC : 1;
+        const double x1 = box[B::at(q[0], q[1])];
+        q[d] = hi ? NC - 1 : 2;
+        const double x2 = box[B::at(q[0], q[1])];
+        v = rc[0] * Bv + rc[1] * x1 + rc[2] * x2;
+      } else {
+        const int p = cx.parent[slot], cof = cx.coff[slot];
+        const double* P = vb + (size_t)cx.nbr[p * 4 + f] * B::BOX;
+        const int a1 = ((cof >> td) & 1) * H + ((a + 1) >> 1), a2 = a1 + 1 - 2 * (a & 1);
+        int c[2];
+        c[d] = hi ? 1 : NC;
+        c[td] = a1;
+        const double v1 = P[B::at(c[0], c[1])];
+        c[td] = a2;
+        const double v2 = P[B::at(c[0], c[1])];
+        q[d] = hi ? NC : 1;
+        v = 0.5 * v1 + sixth * v2 + third * box[B::at(q[0], q[1])];
+      }
+    }
+    q[d] = hi ? NC + 1 : 0;
+    box[B::at(q[0], q[1])] = v;
+  }
+  if (!corners) return;
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    const int c = threadIdx.x;
+    const int dx = (c & 1) ? 1 : -1, dy = (c & 2) ? 1 : -1;
+    const int qi = (c & 1) ? NC + 1 : 0, qj = (c & 2) ? NC + 1 : 0;
+    const int nb = cx.nmat[slot * 9 + (dx + 1) + 3 * (dy + 1)];
+    double v;
+    if (nb >= 0) v = vb[(size_t)nb * B::BOX + B::at(qi - dx * NC, qj - dy * NC)];
+    else v = box[B::at(qi - dx, qj)] + box[B::at(qi, qj - dy)] - box[B::at(qi - dx, qj - dy)];
+    box[B::at(qi, qj)] = v;
+  }
+}
+
+}  // namespace afmg2

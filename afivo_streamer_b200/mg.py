@@ -25,7 +25,7 @@ from ._lib import AfmgError, Opts, TreeDesc
 from .tree import Tree
 from .workloads import (AF_BC_DIRICHLET, AF_BC_NEUMANN, BCTable, bc_table)
 
-I_PHI, I_RHS, I_TMP, I_EPS = 0, 1, 2, 3
+I_PHI, I_RHS, I_TMP, I_EPS, I_FLD = 0, 1, 2, 3, 4
 MG_CYCLE_DOWN, MG_CYCLE_UP = 1, 3
 MG_PROLONG_LINEAR, MG_PROLONG_SPARSE, MG_PROLONG_AUTO = 17, 18, 19
 
@@ -160,6 +160,70 @@ class mg_t:
         self._need_init()
         self._check(_lib.lib().afmg_clear(self._h, var))
 
+    # ---- field from potential --------------------------------------
+    def fc_len(self):
+        t = self._tree
+        return t.ndim * (t.nc + 1) ** t.ndim
+
+    def get_fc(self, ids):
+        """box%fc(nc+1, nc+1[, nc+1], NDIM) of the face-centred field, first index fastest."""
+        self._need_init()
+        ids = np.ascontiguousarray(ids, np.int32)
+        out = np.empty((len(ids), self.fc_len()))
+        self._check(_lib.lib().afmg_download_fc(self._h, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                out.ctypes.data))
+        return out
+
+    def set_fc(self, ids, data):
+        self._need_init()
+        ids = np.ascontiguousarray(ids, np.int32)
+        data = np.ascontiguousarray(data, np.float64)
+        assert data.size == len(ids) * self.fc_len()
+        self._check(_lib.lib().afmg_upload_fc(self._h, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                              data.ctypes.data))
+
+    def set_fld_bc(self, bc: BCTable):
+        """Boundary condition of the field norm (cc_methods(i_electric_fld)%bc); default af_bc_neumann_zero."""
+        self._need_init()
+        ids = np.ascontiguousarray(bc.ids, np.int32)
+        nbs = np.ascontiguousarray(bc.nbs, np.int32)
+        ty = np.ascontiguousarray(bc.types, np.int32)
+        vals = np.ascontiguousarray(bc.vals, np.float64)
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        self._check(_lib.lib().afmg_set_fld_bc(self._h, len(ids), ip(ids), ip(nbs), ip(ty),
+                                               vals.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def set_lsf_distances(self, ids, dd, lsf=None):
+        """Ship the sparse level-set distance stencils.  dd: dense all_distances(2*ndim, cells) per box as the
+        oracle takes them; only cells with any(dd < 1) become entries, in IJK order
+        (store_lsf_distance_matrix, afivo/src/m_af_multigrid.f90:1075-1080)."""
+        self._need_init()
+        t = self._tree
+        nd, nc = t.ndim, t.nc
+        ncell = nc ** nd
+        ids = np.ascontiguousarray(ids, np.int32)
+        dd = np.ascontiguousarray(dd, np.float64).reshape(len(ids), ncell, 2 * nd)
+        lsf_a = None if lsf is None else np.ascontiguousarray(lsf, np.float64).reshape(len(ids), ncell)
+        n_ent, cells, vals, lv = [], [], [], []
+        for b in range(len(ids)):
+            sel = np.nonzero((dd[b] < 1.0).any(axis=1))[0]
+            n_ent.append(len(sel))
+            ix = np.empty((len(sel), nd), np.int32)
+            r = sel.copy()
+            for d in range(nd):
+                ix[:, d] = r % nc + 1
+                r //= nc
+            cells.append(ix)
+            vals.append(dd[b][sel])
+            lv.append(np.zeros(len(sel)) if lsf_a is None else lsf_a[b][sel])
+        n_ent = np.ascontiguousarray(n_ent, np.int32)
+        cells = np.ascontiguousarray(np.concatenate(cells) if cells else np.zeros((0, nd)), np.int32)
+        vals = np.ascontiguousarray(np.concatenate(vals) if vals else np.zeros((0, 2 * nd)), np.float64)
+        lv = np.ascontiguousarray(np.concatenate(lv) if lv else np.zeros(0), np.float64)
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        self._check(_lib.lib().afmg_set_lsf_distances(self._h, len(ids), ip(ids), ip(n_ent), ip(cells), dp(vals), dp(lv)))
+
     # ---- per-level building blocks (exported for parity tests) -----------------------
     def gsrb_boxes(self, lvl, type_cycle):
         self._check(_lib.lib().afmg_gsrb_boxes(self._h, lvl, type_cycle))
@@ -239,6 +303,31 @@ class mg_t:
         if self.comm is None or self.comm[1] == 1:
             return len(ids)
         return int(np.count_nonzero(self.owners(ids) == self.comm[0]))
+
+
+def mg_compute_phi_gradient(tree: Tree, mg: mg_t, fac: float, with_norm: bool = True):
+    """mg_compute_phi_gradient(tree, mg, i_fc, fac, i_norm) (afivo/src/m_af_multigrid.f90:1857-1898); the
+    face-centred result is read with mg.get_fc, the norm with mg.get_cc(I_FLD, ids)."""
+    mg._need_init()
+    mg._check(_lib.lib().afmg_compute_phi_gradient(mg._h, float(fac), int(with_norm)))
+
+
+def mg_compute_field_norm(tree: Tree, mg: mg_t):
+    """mg_compute_field_norm (afivo/src/m_af_multigrid.f90:2002-2020)."""
+    mg._need_init()
+    mg._check(_lib.lib().afmg_compute_field_norm(mg._h))
+
+
+def af_gc_tree(tree: Tree, mg: mg_t, var: int, corners: bool = True):
+    """af_gc_tree(tree, [var], corners) (afivo/src/m_af_ghostcell.f90:25-46) for I_PHI or I_FLD."""
+    mg._need_init()
+    mg._check(_lib.lib().afmg_gc_tree(mg._h, int(var), int(corners)))
+
+
+def field_from_potential(tree: Tree, mg: mg_t, fac: float = -1.0):
+    """field_from_potential without dielectric (src/m_field.f90:531-548)."""
+    mg._need_init()
+    mg._check(_lib.lib().afmg_field_from_potential(mg._h, float(fac)))
 
 
 def comm_from_torch(group=None):

@@ -42,7 +42,9 @@ enum {
 
 /* cell-centred variables of the solver: mg%i_phi, mg%i_rhs, mg%i_tmp, tree%mg_i_eps
  * (m_af_types.f90:574-584) */
-enum { AFMG_PHI = 0, AFMG_RHS = 1, AFMG_TMP = 2, AFMG_EPS = 3 };
+enum { AFMG_PHI = 0, AFMG_RHS = 1, AFMG_TMP = 2, AFMG_EPS = 3,
+       AFMG_FLD = 4 /* cell-centred field norm: i_norm of mg_compute_phi_gradient, the callers' i_electric_fld
+                       (src/m_streamer.f90:302) */ };
 
 /* boundary condition types (m_af_types.f90:58-69) */
 enum {
@@ -201,6 +203,45 @@ int afmg_sync(afmg_handle* h);
  * criterion (the reference: error stop "No convergence in initial field computation"). */
 int afmg_field_solve(afmg_handle* h, int32_t have_guess, double residual_threshold, double max_residual,
                      int32_t max_fmg, int32_t n_vcycles, double* residuals, int32_t* n_fmg, int32_t* n_vc);
+
+/* ---- field from potential on the device -------------------------------------
+ * The step every caller takes right after a solve (field_from_potential, src/m_field.f90:531-548).
+ * Extra device variables are allocated on first use and dropped by afmg_set_tree:
+ *   fc       box%fc(nc+1, nc+1[, nc+1], NDIM, i_fc) (m_af_core.f90:552), one face-centred variable, moved with
+ *            afmg_upload_fc / afmg_download_fc in exactly that record (first index fastest);
+ *   AFMG_FLD the cell-centred norm, AFMG_EPS tree%mg_i_eps (needed only when variable-eps boxes exist; default
+ *            1), both moved with afmg_upload / afmg_download in the box layout cc(0:nc+1, ...).
+ * Single GPU (a multi-GPU handle returns AFMG_ERR_UNSUPPORTED).
+ *
+ * mg_compute_phi_gradient(tree, mg, i_fc, fac, i_norm) m_af_multigrid.f90:1857-1898: fc = fac/dr * (phi difference)
+ * on every box (mg_box_lpl_gradient :1901-1999, with the eps-weighted boundary faces of mg_veps_box boxes),
+ * mg_box_lpllsf_gradient (:2055-2137) on leaves listed by afmg_set_lsf_distances, and, if with_norm, the norm
+ * (mg_box_field_norm :2023-2051) on the interior of every box. */
+int afmg_compute_phi_gradient(afmg_handle* h, double fac, int32_t with_norm);
+/* mg_compute_field_norm (m_af_multigrid.f90:2002-2020) from the current fc, e.g. after the host corrected fc for
+ * surface charge (surface_correct_field_fc, src/m_field.f90:537-541) and sent it back with afmg_upload_fc */
+int afmg_compute_field_norm(afmg_handle* h);
+/* af_gc_tree(tree, [var], corners) m_af_ghostcell.f90:25-46.  AFMG_PHI: the multigrid's own methods
+ * (mg%sides_bc, mg_sides_rb).  AFMG_FLD: the methods the callers register for the field norm
+ * (af_set_cc_methods(tree, i_electric_fld, af_bc_neumann_zero, af_gc_interp), src/m_field.f90:392-393):
+ * af_gc_interp (m_af_ghostcell.f90:394-498) on refinement boundaries and the boundary condition given by
+ * afmg_set_fld_bc (default af_bc_neumann_zero). */
+int afmg_gc_tree(afmg_handle* h, int32_t var, int32_t corners);
+/* field_from_potential without dielectric (src/m_field.f90:543-547): gradient with norm, then
+ * af_gc_tree(tree, [i_electric_fld]) */
+int afmg_field_from_potential(afmg_handle* h, double fac);
+/* boundary condition of AFMG_FLD on physical faces, same row format as afmg_set_bc */
+int afmg_set_fld_bc(afmg_handle* h, int32_t n_faces, const int32_t* box_id, const int32_t* nb, const int32_t* bc_type,
+                    const double* bc_val);
+/* The sparse level-set distance stencils (mg_lsf_distance_key, store_lsf_distance_matrix
+ * m_af_multigrid.f90:977-1097) of n_boxes boxes: box b has n_entries[b] entries, stored back to back in the
+ * order of stencil%sparse_ix: cell_ix (ndim per entry, 1-based), dd = sparse_v (2*ndim per entry) and lsf =
+ * cc(IJK, mg%i_lsf) of that cell (its sign decides whether the face is corrected; NULL: all >= 0).  The
+ * boundary value is mg%lsf_boundary_value (afmg_set_lsf_boundary_value).  Replaces the previous list. */
+int afmg_set_lsf_distances(afmg_handle* h, int32_t n_boxes, const int32_t* box_id, const int32_t* n_entries,
+                           const int32_t* cell_ix, const double* dd, const double* lsf);
+int afmg_upload_fc(afmg_handle* h, int32_t n, const int32_t* box_id, const double* packed);
+int afmg_download_fc(afmg_handle* h, int32_t n, const int32_t* box_id, double* packed);
 
 /* ---- single operations (the mg_t per-level building blocks; exported for parity tests) -------- */
 int afmg_gsrb_boxes(afmg_handle* h, int32_t lvl, int32_t type_cycle /*1 = down, 3 = up*/); /* :648-687 */

@@ -45,7 +45,8 @@ constexpr int stencil_constant = 1, stencil_variable = 2;
 constexpr int af_stencil_357 = 1, af_stencil_p234 = 2, af_stencil_p248 = 3;
 constexpr int mg_prolong_linear = 17, mg_prolong_sparse = 18, mg_prolong_auto = 19;
 
-enum { I_PHI = 0, I_RHS = 1, I_TMP = 2, I_EPS = 3, N_VAR = 4 };
+// I_FLD: the cell-centred field norm of the callers (i_electric_fld, src/m_streamer.f90:302)
+enum { I_PHI = 0, I_RHS = 1, I_TMP = 2, I_EPS = 3, I_FLD = 4, N_VAR = 5 };
 
 // stencil_t (afivo/src/m_af_types.f90:260-282), without the sparse variant
 struct Stencil {
@@ -74,6 +75,13 @@ struct Box {
   // reference never depend on phi: m_af_ghostcell.f90:615-652, src/m_field.f90:590-670)
   int bc_type[6] = {0};
   std::vector<double> bc_val[6];
+  // face-centred field box%fc(nc+1, nc+1[, nc+1], NDIM) of one variable (m_af_core.f90:552), first index
+  // fastest; allocated by the first gradient call
+  std::vector<double> fc;
+  std::vector<double> lsf_cc;  // cc(IJK, mg%i_lsf) on the interior (sign test of mg_box_lpllsf_gradient); empty: >= 0
+  // boundary condition of I_FLD (cc_methods(iv)%bc): default af_bc_neumann_zero (src/m_field.f90:392-393)
+  int fld_bc_type[6] = {0};
+  std::vector<double> fld_bc_val[6];
 };
 
 struct Tree {
@@ -639,6 +647,67 @@ void af_gc_box_corner(Tree& t, int id, int iv) {
   }
 }
 
+// af_gc_interp (afivo/src/m_af_ghostcell.f90:394-498): refinement-boundary ghost cells from the coarse
+// neighbour of the parent (2 or 3 coarse values) and the box's own first interior layer
+template <int ND>
+void af_gc_interp(Tree& t, int id, int nb, int iv) {
+  const int nc = t.nc;
+  G<ND> g(nc);
+  Box& box = t.boxes[id];
+  const Box& pn = t.boxes[t.boxes[box.parent].neighbors[nb - 1]];
+  int off[3];
+  child_offset<ND>(box, nc, off);  // af_get_child_offset(box, nb): the entry of dim(nb) is unused here
+  const double third = 1 / 3.0, sixth = 1 / 6.0;
+  const int d = nb_dim(nb);
+  const int ix = nb_low(nb) ? 0 : nc + 1, ix_f = nb_low(nb) ? 1 : nc, ix_c = nb_low(nb) ? nc : 1;
+  double* A = box.cc[iv].data();
+  const double* P = pn.cc[iv].data();
+  int td[2], ntd = 0;
+  for (int q = 0; q < ND; ++q)
+    if (q != d) td[ntd++] = q;
+  if (ND == 2) {
+    const int ta = td[0];
+    for (int a = 1; a <= nc; ++a) {
+      int a_c1 = off[ta] + ((a + 1) >> 1);
+      int a_c2 = a_c1 + 1 - 2 * (a & 1);
+      int q[3] = {0, 0, 0}, c1[3] = {0, 0, 0}, c2[3] = {0, 0, 0}, f[3] = {0, 0, 0};
+      q[d] = ix; q[ta] = a;
+      f[d] = ix_f; f[ta] = a;
+      c1[d] = ix_c; c1[ta] = a_c1;
+      c2[d] = ix_c; c2[ta] = a_c2;
+      A[g.at(q[0], q[1], 0)] = 0.5 * P[g.at(c1[0], c1[1], 0)] + sixth * P[g.at(c2[0], c2[1], 0)] +
+                               third * A[g.at(f[0], f[1], 0)];
+    }
+  } else {
+    // transverse dims (ta, tb) in increasing order; order of the coarse terms per case (:448-494):
+    //   dim 1: (j_c1,k_c1), (j_c2,k_c1), (j_c1,k_c2);  dim 2: (i_c1,k_c1), (i_c2,k_c1), (i_c1,k_c2);
+    //   dim 3: (i_c1,j_c1), (i_c1,j_c2), (i_c2,j_c1)
+    const int ta = td[0], tb = td[1];
+    for (int b = 1; b <= nc; ++b) {
+      int b_c1 = off[tb] + ((b + 1) >> 1);
+      int b_c2 = b_c1 + 1 - 2 * (b & 1);
+      for (int a = 1; a <= nc; ++a) {
+        int a_c1 = off[ta] + ((a + 1) >> 1);
+        int a_c2 = a_c1 + 1 - 2 * (a & 1);
+        int q[3], f[3], c11[3], c21[3], c12[3];
+        q[d] = ix; q[ta] = a; q[tb] = b;
+        f[d] = ix_f; f[ta] = a; f[tb] = b;
+        c11[d] = ix_c; c11[ta] = a_c1; c11[tb] = b_c1;
+        c21[d] = ix_c; c21[ta] = a_c2; c21[tb] = b_c1;
+        c12[d] = ix_c; c12[ta] = a_c1; c12[tb] = b_c2;
+        const double v11 = P[g.at(c11[0], c11[1], c11[2])];
+        const double v21 = P[g.at(c21[0], c21[1], c21[2])];
+        const double v12 = P[g.at(c12[0], c12[1], c12[2])];
+        const double vf = A[g.at(f[0], f[1], f[2])];
+        double r;
+        if (d == 2) r = third * v11 + sixth * v12 + sixth * v21 + third * vf;
+        else r = third * v11 + sixth * v21 + sixth * v12 + third * vf;
+        A[g.at(q[0], q[1], q[2])] = r;
+      }
+    }
+  }
+}
+
 // af_gc_box (afivo/src/m_af_ghostcell.f90:64-120)
 template <int ND>
 void af_gc_box(Tree& t, int id, int iv, bool corners) {
@@ -652,7 +721,15 @@ void af_gc_box(Tree& t, int id, int iv, bool corners) {
       dnb[nb_dim(nb)] = nb_high_pm(nb);
       copy_from_nb<ND>(box, t.boxes[nb_id], dnb, lo, hi, iv, nc);
     } else if (nb_id == af_no_box) {
-      mg_auto_rb<ND>(t, id, nb, iv, t.operator_mask);
+      if (iv == I_FLD) af_gc_interp<ND>(t, id, nb, iv);  // cc_methods(i_electric_fld)%rb (src/m_field.f90:392-393)
+      else mg_auto_rb<ND>(t, id, nb, iv, t.operator_mask);
+    } else if (iv == I_FLD) {
+      if (box.fld_bc_val[nb - 1].empty()) {  // af_bc_neumann_zero (m_af_ghostcell.f90:615-625)
+        std::vector<double> zero((ND == 3) ? nc * nc : nc, 0.0);
+        bc_to_gc<ND>(box, nb, iv, zero.data(), af_bc_neumann, nc);
+      } else {
+        bc_to_gc<ND>(box, nb, iv, box.fld_bc_val[nb - 1].data(), box.fld_bc_type[nb - 1], nc);
+      }
     } else {
       bc_to_gc<ND>(box, nb, iv, box.bc_val[nb - 1].data(), box.bc_type[nb - 1], nc);
     }
@@ -666,6 +743,159 @@ void af_gc_lvl(Tree& t, int lvl, int iv, bool corners = true) {
   const auto& ids = t.ids[lvl];
 #pragma omp parallel for
   for (int i = 0; i < (int)ids.size(); ++i) af_gc_box<ND>(t, ids[i], iv, corners);
+}
+
+// af_gc_tree (afivo/src/m_af_ghostcell.f90:25-46)
+template <int ND>
+void af_gc_tree(Tree& t, int iv, bool corners = true) {
+  for (int lvl = 1; lvl <= t.highest_lvl; ++lvl) af_gc_lvl<ND>(t, lvl, iv, corners);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Field from potential (afivo/src/m_af_multigrid.f90:1857-2140; caller src/m_field.f90:531-548)
+// ---------------------------------------------------------------------------------------------
+template <int ND>
+struct F {  // face-centred array fc(nc+1, nc+1[, nc+1], ND), 1-based, first index fastest
+  int n1;
+  explicit F(int nc) : n1(nc + 1) {}
+  size_t size() const { return (size_t)ND * (ND == 3 ? n1 * n1 * n1 : n1 * n1); }
+  size_t at(int i, int j, int k, int dim /*0-based*/) const {
+    size_t per = (ND == 3) ? (size_t)n1 * n1 * n1 : (size_t)n1 * n1;
+    return dim * per + (size_t)(i - 1) + (size_t)n1 * ((j - 1) + (ND == 3 ? (size_t)n1 * (k - 1) : 0));
+  }
+};
+
+// mg_box_lpl_gradient (afivo/src/m_af_multigrid.f90:1901-1999)
+template <int ND>
+void mg_box_lpl_gradient(Tree& t, Box& box, double fac) {
+  const int nc = t.nc;
+  G<ND> g(nc);
+  F<ND> fi(nc);
+  if (box.fc.size() != fi.size()) box.fc.assign(fi.size(), 0.0);
+  const double* cc = box.cc[I_PHI].data();
+  double inv_dr[3] = {0, 0, 0};
+  for (int d = 0; d < ND; ++d) inv_dr[d] = fac / box.dr[d];
+  for (int d = 0; d < ND; ++d) {
+    int hi[3] = {nc, nc, (ND == 3) ? nc : 0};
+    hi[d] = nc + 1;
+    const int klo = (ND == 3) ? 1 : 0;
+    for (int k = klo; k <= hi[2]; ++k)
+      for (int j = 1; j <= hi[1]; ++j)
+        for (int i = 1; i <= hi[0]; ++i)
+          box.fc[fi.at(i, j, (ND == 3) ? k : 1, d)] = inv_dr[d] * (cc[g.at(i, j, k)] - cc[g.at(i, j, k) - g.s[d]]);
+  }
+  if ((box.tag & t.operator_mask) == mg_veps_box) {
+    // fields at the box boundaries, where eps can change (:1938-1997)
+    const double* eps = box.cc[I_EPS].data();
+    for (int d = 0; d < ND; ++d) {
+      int td[2], ntd = 0;
+      for (int q = 0; q < ND; ++q)
+        if (q != d) td[ntd++] = q;
+      const int nb_b = (ND == 3) ? nc : 1;
+      for (int side = 0; side < 2; ++side) {
+        const int f = side ? nc + 1 : 1;       // face index
+        const int hi_c = side ? nc + 1 : 1;    // cell on the high side of the face
+        const int gc = side ? nc + 1 : 0;      // the ghost cell (its eps multiplies)
+        for (int b = 1; b <= nb_b; ++b)
+          for (int a = 1; a <= nc; ++a) {
+            int q[3] = {0, 0, 0};
+            q[td[0]] = a;
+            if (ND == 3) q[td[1]] = b;
+            int qh[3] = {q[0], q[1], q[2]}, ql[3] = {q[0], q[1], q[2]}, qg[3] = {q[0], q[1], q[2]}, qf[3] = {q[0], q[1], q[2]};
+            qh[d] = hi_c;
+            ql[d] = hi_c - 1;
+            qg[d] = gc;
+            qf[d] = f;
+            const int ih = g.at(qh[0], qh[1], qh[2]), il = g.at(ql[0], ql[1], ql[2]), ig = g.at(qg[0], qg[1], qg[2]);
+            // low side : 2*inv_dr*(cc(1)-cc(0))*eps(0)/(eps(1)+eps(0));  high: .. *eps(nc+1)/(eps(nc+1)+eps(nc))
+            box.fc[fi.at(qf[0], qf[1], (ND == 3) ? qf[2] : 1, d)] =
+                2 * inv_dr[d] * (cc[ih] - cc[il]) * eps[ig] / (eps[ih] + eps[il]);
+          }
+      }
+    }
+  }
+}
+
+// mg_box_lpllsf_gradient (afivo/src/m_af_multigrid.f90:2055-2137).  The sparse distance stencil lists, in
+// IJK order, the cells with any(dd < 1) (store_lsf_distance_matrix :1075-1080); the boundary value is the
+// constant mg%lsf_boundary_value (mg_lsf_boundary_value, m_coarse_solver.f90:493-510).
+template <int ND>
+void mg_box_lpllsf_gradient(Tree& t, Box& box, double fac) {
+  mg_box_lpl_gradient<ND>(t, box, fac);
+  const int nc = t.nc;
+  G<ND> g(nc);
+  F<ND> fi(nc);
+  const double* cc = box.cc[I_PHI].data();
+  double inv_dr[3] = {0, 0, 0};
+  for (int d = 0; d < ND; ++d) inv_dr[d] = fac / box.dr[d];
+  const double bc = t.lsf_boundary_value;
+  for (int k = g.klo(); k <= g.khi(); ++k)
+    for (int j = 1; j <= nc; ++j)
+      for (int i = 1; i <= nc; ++i) {
+        const int L = g.lin(i, j, k);
+        const double* dd = &box.lsf_dd[(size_t)2 * ND * L];
+        bool any = false;
+        for (int n = 0; n < 2 * ND; ++n) any = any || dd[n] < 1.0;
+        if (!any) continue;
+        const bool pos = box.lsf_cc.empty() || box.lsf_cc[L] >= 0;
+        const double phi = cc[g.at(i, j, k)];
+        for (int d = 0; d < ND; ++d) {
+          int q[3] = {i, j, (ND == 3) ? k : 1};
+          if (dd[2 * d] < 1 && pos) box.fc[fi.at(q[0], q[1], q[2], d)] = inv_dr[d] * (phi - bc) / dd[2 * d];
+          q[d] += 1;
+          if (dd[2 * d + 1] < 1 && pos) box.fc[fi.at(q[0], q[1], q[2], d)] = inv_dr[d] * (bc - phi) / dd[2 * d + 1];
+        }
+      }
+}
+
+// mg_box_field_norm (afivo/src/m_af_multigrid.f90:2023-2051)
+template <int ND>
+void mg_box_field_norm(Tree& t, Box& box) {
+  const int nc = t.nc;
+  G<ND> g(nc);
+  F<ND> fi(nc);
+  double* out = box.cc[I_FLD].data();
+  for (int k = g.klo(); k <= g.khi(); ++k)
+    for (int j = 1; j <= nc; ++j)
+      for (int i = 1; i <= nc; ++i) {
+        const int kk = (ND == 3) ? k : 1;
+        double a = box.fc[fi.at(i, j, kk, 0)] + box.fc[fi.at(i + 1, j, kk, 0)];
+        double b = box.fc[fi.at(i, j, kk, 1)] + box.fc[fi.at(i, j + 1, kk, 1)];
+        double s = a * a + b * b;
+        if (ND == 3) {
+          double c = box.fc[fi.at(i, j, kk, 2)] + box.fc[fi.at(i, j, kk + 1, 2)];
+          s = s + c * c;
+        }
+        out[g.at(i, j, k)] = 0.5 * std::sqrt(s);
+      }
+}
+
+// mg_compute_phi_gradient (afivo/src/m_af_multigrid.f90:1857-1898)
+template <int ND>
+void mg_compute_phi_gradient(Tree& t, double fac, bool with_norm) {
+  for (int lvl = 1; lvl <= t.highest_lvl; ++lvl) {
+    const auto& ids = t.ids[lvl];
+#pragma omp parallel for
+    for (int i = 0; i < (int)ids.size(); ++i) {
+      Box& box = t.boxes[ids[i]];
+      const int tag = box.tag & t.operator_mask;
+      if ((tag & mg_lsf_box) && tag != mg_veps_box && !af_has_children(box) && !box.lsf_dd.empty())
+        mg_box_lpllsf_gradient<ND>(t, box, fac);
+      else
+        mg_box_lpl_gradient<ND>(t, box, fac);
+      if (with_norm) mg_box_field_norm<ND>(t, box);
+    }
+  }
+}
+
+// mg_compute_field_norm (afivo/src/m_af_multigrid.f90:2002-2020)
+template <int ND>
+void mg_compute_field_norm(Tree& t) {
+  for (int lvl = 1; lvl <= t.highest_lvl; ++lvl) {
+    const auto& ids = t.ids[lvl];
+#pragma omp parallel for
+    for (int i = 0; i < (int)ids.size(); ++i) mg_box_field_norm<ND>(t, t.boxes[ids[i]]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1499,6 +1729,52 @@ void orc_gsrb_boxes(void* h, int lvl, int type_cycle) {
 void orc_gc_lvl(void* h, int lvl, int var, int corners) {
   Tree* t = (Tree*)h;
   DISPATCH(t, af_gc_lvl<ND>(*t, lvl, var, corners != 0));
+}
+// ---- field from potential ----
+void orc_gc_tree(void* h, int var, int corners) {
+  Tree* t = (Tree*)h;
+  DISPATCH(t, af_gc_tree<ND>(*t, var, corners != 0));
+}
+void orc_compute_phi_gradient(void* h, double fac, int with_norm) {
+  Tree* t = (Tree*)h;
+  DISPATCH(t, mg_compute_phi_gradient<ND>(*t, fac, with_norm != 0));
+}
+void orc_compute_field_norm(void* h) {
+  Tree* t = (Tree*)h;
+  DISPATCH(t, mg_compute_field_norm<ND>(*t));
+}
+// fc of n boxes, ND * (nc+1)^ND doubles each (zeros for a box without fc yet)
+void orc_get_fc(void* h, int n, const int* ids, double* data) {
+  Tree* t = (Tree*)h;
+  size_t per = (size_t)t->ndim;
+  for (int d = 0; d < t->ndim; ++d) per *= (size_t)(t->nc + 1);
+  for (int q = 0; q < n; ++q) {
+    const auto& v = t->boxes[ids[q]].fc;
+    if (v.size() == per) std::memcpy(data + q * per, v.data(), per * sizeof(double));
+    else std::memset(data + q * per, 0, per * sizeof(double));
+  }
+}
+void orc_set_fc(void* h, int n, const int* ids, const double* data) {
+  Tree* t = (Tree*)h;
+  size_t per = (size_t)t->ndim;
+  for (int d = 0; d < t->ndim; ++d) per *= (size_t)(t->nc + 1);
+  for (int q = 0; q < n; ++q) t->boxes[ids[q]].fc.assign(data + q * per, data + (q + 1) * per);
+}
+// cc(IJK, mg%i_lsf) on the interior (nc^ND) of n boxes
+void orc_set_lsf_cc(void* h, int n, const int* ids, const double* v) {
+  Tree* t = (Tree*)h;
+  const size_t per = (t->ndim == 3) ? (size_t)t->nc * t->nc * t->nc : (size_t)t->nc * t->nc;
+  for (int q = 0; q < n; ++q) t->boxes[ids[q]].lsf_cc.assign(v + q * per, v + (q + 1) * per);
+}
+// boundary conditions of the field-norm variable (default: af_bc_neumann_zero)
+void orc_set_fld_bc(void* h, int n, const int* ids, const int* nbs, const int* types, const double* vals) {
+  Tree* t = (Tree*)h;
+  const int nface = (t->ndim == 3) ? t->nc * t->nc : t->nc;
+  for (int q = 0; q < n; ++q) {
+    Box& b = t->boxes[ids[q]];
+    b.fld_bc_type[nbs[q] - 1] = types[q];
+    b.fld_bc_val[nbs[q] - 1].assign(vals + (size_t)q * nface, vals + (size_t)(q + 1) * nface);
+  }
 }
 void orc_update_coarse(void* h, int lvl, int with_tmp) {
   Tree* t = (Tree*)h;

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libafmg_oracle.so")
 
-I_PHI, I_RHS, I_TMP, I_EPS = 0, 1, 2, 3
+I_PHI, I_RHS, I_TMP, I_EPS, I_FLD = 0, 1, 2, 3, 4
 MG_CYCLE_DOWN, MG_CYCLE_UP = 1, 3
 MG_PROLONG_LINEAR, MG_PROLONG_SPARSE, MG_PROLONG_AUTO = 17, 18, 19
 
@@ -156,6 +156,43 @@ class Oracle:
 
     def tree_sum(self, var=I_PHI):
         return float(self.L.orc_tree_sum(self.h, var))
+
+    # ---- field from potential (mg_compute_phi_gradient & co) ----
+    def fc_len(self):
+        t = self.tree
+        return t.ndim * (t.nc + 1) ** t.ndim
+
+    def compute_phi_gradient(self, fac, with_norm=True):
+        self.L.orc_compute_phi_gradient(self.h, C.c_double(fac), int(with_norm))
+
+    def compute_field_norm(self):
+        self.L.orc_compute_field_norm(self.h)
+
+    def gc_tree(self, var, corners=True):
+        self.L.orc_gc_tree(self.h, var, int(corners))
+
+    def get_fc(self, ids):
+        ids = np.ascontiguousarray(ids, np.int32)
+        out = np.empty((len(ids), self.fc_len()))
+        self.L.orc_get_fc(self.h, len(ids), _ip(ids), _dp(out))
+        return out
+
+    def set_fc(self, ids, data):
+        ids = np.ascontiguousarray(ids, np.int32)
+        data = np.ascontiguousarray(data, np.float64).reshape(len(ids), self.fc_len())
+        self.L.orc_set_fc(self.h, len(ids), _ip(ids), _dp(data))
+
+    def set_lsf_cc(self, ids, vals):
+        ids = np.ascontiguousarray(ids, np.int32)
+        vals = np.ascontiguousarray(vals, np.float64).reshape(len(ids), self.tree.nc ** self.tree.ndim)
+        self.L.orc_set_lsf_cc(self.h, len(ids), _ip(ids), _dp(vals))
+
+    def set_fld_bc(self, bc):
+        ids = np.ascontiguousarray(bc.ids, np.int32)
+        nbs = np.ascontiguousarray(bc.nbs, np.int32)
+        types = np.ascontiguousarray(bc.types, np.int32)
+        vals = np.ascontiguousarray(bc.vals, np.float64)
+        self.L.orc_set_fld_bc(self.h, len(ids), _ip(ids), _ip(nbs), _ip(types), _dp(vals))
 
     # ---- stencil read-back ----
     def op_stencil(self, box_id):
