@@ -89,6 +89,7 @@ SYMBOLS = {
     "afmg_set_lsf_distances": (C.c_int, [_H, _I, _IP, _IP, _IP, _DP, _DP]),
     "afmg_upload_fc": (C.c_int, [_H, _I, _IP, C.c_void_p]),
     "afmg_download_fc": (C.c_int, [_H, _I, _IP, C.c_void_p]),
+    "afmg_helmholtz_compute": (C.c_int, [C.POINTER(_H), _I, _DP, _I, C.c_double, _IP, _DP]),
     "afmg_gsrb_boxes": (C.c_int, [_H, _I, _I]),
     "afmg_gsrb_halfsweep": (C.c_int, [_H, _I, _I]),
     "afmg_gc_lvl": (C.c_int, [_H, _I, _I, _I]),

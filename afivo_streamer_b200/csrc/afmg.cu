@@ -1635,8 +1635,8 @@ static int transfer(afmg_handle* h, int var, int n, const int32_t* box_id, doubl
                     bool interior = false) {
   if (!h) return AFMG_ERR_ARG;
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
-  if (var == AFMG_EPS || var == AFMG_FLD) {  // extra variables of the field computation (afmg_field.inc)
-    if (device_ptr || interior) return h->fail(AFMG_ERR_UNSUPPORTED, "AFMG_EPS / AFMG_FLD move through afmg_upload / afmg_download only");
+  if (var == AFMG_EPS || var == AFMG_FLD || var == AFMG_PHOTO) {  // extra variables of the field computation (afmg_field.inc)
+    if (device_ptr || interior) return h->fail(AFMG_ERR_UNSUPPORTED, "AFMG_EPS / AFMG_FLD / AFMG_PHOTO move through afmg_upload / afmg_download only");
     if (var == AFMG_EPS && up && h->fs) h->fs->veps_valid = false;
     return fs_transfer(h, var, n, box_id, packed, up);
   }

@@ -218,6 +218,15 @@ __global__ void __launch_bounds__(256) k_gc_fld3(DevCtx cx, FieldCtx fx, int slo
   }
 }
 
+// dst = dst - c * src on the full records of the leaves (photoi_helmh_compute, src/m_photoi_helmh.f90:192-201)
+__global__ void k_axpy_leaves(double* dst, const double* src, const int* child0, double c, int box_len) {
+  const int slot = blockIdx.x;
+  if (child0[slot] >= 0) return;
+  double* a = dst + (size_t)slot * box_len;
+  const double* b = src + (size_t)slot * box_len;
+  for (int q = threadIdx.x; q < box_len; q += blockDim.x) a[q] = a[q] - c * b[q];
+}
+
 // plain records (fc) to / from a packed buffer in box order
 __global__ void k_rec_copy(double* base, const int* slots, int n, double* packed, int rec_len, int to_device) {
   const int s = slots[blockIdx.x];

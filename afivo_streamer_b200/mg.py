@@ -25,7 +25,7 @@ from ._lib import AfmgError, Opts, TreeDesc
 from .tree import Tree
 from .workloads import (AF_BC_DIRICHLET, AF_BC_NEUMANN, BCTable, bc_table)
 
-I_PHI, I_RHS, I_TMP, I_EPS, I_FLD = 0, 1, 2, 3, 4
+I_PHI, I_RHS, I_TMP, I_EPS, I_FLD, I_PHOTO = 0, 1, 2, 3, 4, 5
 MG_CYCLE_DOWN, MG_CYCLE_UP = 1, 3
 MG_PROLONG_LINEAR, MG_PROLONG_SPARSE, MG_PROLONG_AUTO = 17, 18, 19
 
@@ -328,6 +328,31 @@ def field_from_potential(tree: Tree, mg: mg_t, fac: float = -1.0):
     """field_from_potential without dielectric (src/m_field.f90:531-548)."""
     mg._need_init()
     mg._check(_lib.lib().afmg_field_from_potential(mg._h, float(fac)))
+
+
+def photoi_helmh_bc(nb, coords):
+    """photoi_helmh_bc (src/m_photoi_helmh.f90:210-228): Dirichlet 0 in the last dimension, Neumann 0 elsewhere."""
+    if (nb - 1) // 2 == coords.shape[-1] - 1:
+        return AF_BC_DIRICHLET, 0.0
+    return AF_BC_NEUMANN, 0.0
+
+
+def photoi_helmh_compute(tree: Tree, mg_helm, coeffs, max_fmg_cycles: int = 10, max_rel_residual: float = 1.0e-2):
+    """photoi_helmh_compute (src/m_photoi_helmh.f90:162-204) on the device: mg_helm = the mg_t of every mode
+    (helmholtz_lambda = lambdas(n)**2), rhs uploaded to mg_helm[0]; the source is read with
+    mg_helm[0].get_cc(I_PHOTO, ids).  Returns (FMG cycles per mode, last residual max-norm per mode)."""
+    n = len(mg_helm)
+    for m in mg_helm:
+        m._need_init()
+    hs = (C.c_void_p * n)(*[m._h for m in mg_helm])
+    cf = np.ascontiguousarray(coeffs, np.float64)
+    assert cf.size == n
+    ncyc = np.zeros(n, np.int32)
+    res = np.zeros(n)
+    mg_helm[0]._check(_lib.lib().afmg_helmholtz_compute(
+        hs, n, cf.ctypes.data_as(C.POINTER(C.c_double)), int(max_fmg_cycles), float(max_rel_residual),
+        ncyc.ctypes.data_as(C.POINTER(C.c_int32)), res.ctypes.data_as(C.POINTER(C.c_double))))
+    return ncyc, res
 
 
 def comm_from_torch(group=None):

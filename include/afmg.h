@@ -44,7 +44,8 @@ enum {
  * (m_af_types.f90:574-584) */
 enum { AFMG_PHI = 0, AFMG_RHS = 1, AFMG_TMP = 2, AFMG_EPS = 3,
        AFMG_FLD = 4 /* cell-centred field norm: i_norm of mg_compute_phi_gradient, the callers' i_electric_fld
-                       (src/m_streamer.f90:302) */ };
+                       (src/m_streamer.f90:302) */,
+       AFMG_PHOTO = 5 /* photoionization source accumulated by afmg_helmholtz_compute (i_photo) */ };
 
 /* boundary condition types (m_af_types.f90:58-69) */
 enum {
@@ -242,6 +243,18 @@ int afmg_set_lsf_distances(afmg_handle* h, int32_t n_boxes, const int32_t* box_i
                            const int32_t* cell_ix, const double* dd, const double* lsf);
 int afmg_upload_fc(afmg_handle* h, int32_t n, const int32_t* box_id, const double* packed);
 int afmg_download_fc(afmg_handle* h, int32_t n, const int32_t* box_id, double* packed);
+
+/* ---- Helmholtz photoionization on the device: photoi_helmh_compute
+ * (src/m_photoi_helmh.f90:162-204).  modes[n] is the handle of mg_helm(n) (own helmholtz_lambda, own phi =
+ * i_modes(n), boundary conditions photoi_helmh_bc shipped with afmg_set_bc), all on the same tree and
+ * device; the right-hand side is the AFMG_RHS of modes[0] (leaves) and is copied device to device to the
+ * other modes, as i_rhs is one shared variable in the reference.  Per mode: up to max_fmg_cycles
+ * mg_fas_fmg(set_residual = T, have_guess = T) until max|residual| / max(max|rhs|, sqrt(epsilon)) <
+ * max_rel_residual, then i_photo = i_photo - coeffs(n) * i_modes(n) on the leaves.  The result is AFMG_PHOTO of
+ * modes[0] (afmg_download).  n_cycles / residuals (may be NULL) receive the FMG count and last residual
+ * max-norm of every mode.  Only three doubles per cycle cross PCIe. */
+int afmg_helmholtz_compute(afmg_handle* const* modes, int32_t n_modes, const double* coeffs, int32_t max_fmg_cycles,
+                           double max_rel_residual, int32_t* n_cycles, double* residuals);
 
 /* ---- single operations (the mg_t per-level building blocks; exported for parity tests) -------- */
 int afmg_gsrb_boxes(afmg_handle* h, int32_t lvl, int32_t type_cycle /*1 = down, 3 = up*/); /* :648-687 */
