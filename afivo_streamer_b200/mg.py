@@ -224,6 +224,19 @@ class mg_t:
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
         self._check(_lib.lib().afmg_set_lsf_distances(self._h, len(ids), ip(ids), ip(n_ent), ip(cells), dp(vals), dp(lv)))
 
+    def set_lsf_distances_sparse(self, ids, n_entries, cell_ix, dd, lsf=None):
+        """afmg_set_lsf_distances with the sparse stencils as stored (e.g. DatFile.lsf_distances())."""
+        self._need_init()
+        ids = np.ascontiguousarray(ids, np.int32)
+        n_ent = np.ascontiguousarray(n_entries, np.int32)
+        cells = np.ascontiguousarray(cell_ix, np.int32)
+        vals = np.ascontiguousarray(dd, np.float64)
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        lv = None if lsf is None else np.ascontiguousarray(lsf, np.float64)
+        self._check(_lib.lib().afmg_set_lsf_distances(self._h, len(ids), ip(ids), ip(n_ent), ip(cells), dp(vals),
+                                                      None if lv is None else dp(lv)))
+
     # ---- per-level building blocks (exported for parity tests) -----------------------
     def gsrb_boxes(self, lvl, type_cycle):
         self._check(_lib.lib().afmg_gsrb_boxes(self._h, lvl, type_cycle))
@@ -353,6 +366,27 @@ def photoi_helmh_compute(tree: Tree, mg_helm, coeffs, max_fmg_cycles: int = 10, 
         hs, n, cf.ctypes.data_as(C.POINTER(C.c_double)), int(max_fmg_cycles), float(max_rel_residual),
         ncyc.ctypes.data_as(C.POINTER(C.c_int32)), res.ctypes.data_as(C.POINTER(C.c_double))))
     return ncyc, res
+
+
+def mg_from_dat(dat, phi="phi", rhs="rhs", eps=None, lsf="lsf", operator_key=1, prolongation_key=2, **opts):
+    """Set a solver up from an afivo .dat file (datfile.DatFile) alone: topology, the boundary conditions
+    stored in the boxes for `phi`, phi / rhs (/ eps) data, the stored operator / prolongation stencils and
+    level-set distance stencils.  Returns (tree, mg) ready for mg_fas_fmg / mg_fas_vcycle."""
+    tree = dat.tree
+    mg = mg_t(sides_bc=dat.bc_table(phi), **opts)
+    mg_init(tree, mg)
+    entries = dat.stencil_entries(operator_key, prolongation_key, mg.operator_mask)
+    if entries:
+        mg.set_stencils(entries)
+    ids = dat.ids_in_use()
+    mg.set_cc(I_PHI, ids, dat.cc_of(phi, ids))
+    mg.set_cc(I_RHS, ids, dat.cc_of(rhs, ids))
+    if eps is not None:
+        mg.set_cc(I_EPS, ids, dat.cc_of(eps, ids))
+    ld = dat.lsf_distances(lsf)
+    if ld is not None:
+        mg.set_lsf_distances_sparse(*ld)
+    return tree, mg
 
 
 def comm_from_torch(group=None):
