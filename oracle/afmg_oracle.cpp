@@ -964,6 +964,53 @@ void mg_box_lpld_stencil(Tree& t, Box& box) {
   stencil_try_constant(st, NCF, g.ncell(), 2.220446049250313e-16);
 }
 
+// mg_box_lpld_lsf_stencil (afivo/src/m_af_multigrid.f90:1535-1623): variable permittivity AND a level-set
+// boundary in the box; distances given as data (all_distances(2*ND, IJK), 1 = no boundary)
+template <int ND>
+void mg_box_lpld_lsf_stencil(Tree& t, Box& box) {
+  const int nc = t.nc;
+  G<ND> g(nc);
+  Stencil& st = box.op;
+  st = Stencil();
+  st.shape = af_stencil_357;
+  st.stype = stencil_variable;
+  st.cylindrical_gradient = (t.coord_t == af_cyl);
+  constexpr int NCF = 2 * ND + 1;
+  st.v.assign((size_t)NCF * g.ncell(), 0.0);
+  st.f.assign(g.ncell(), 0.0);
+  double dr2[3];
+  for (int d = 0; d < ND; ++d) dr2[d] = box.dr[d] * box.dr[d];
+  const double* eps = box.cc[I_EPS].data();
+  const int off[6] = {-1, 1, -g.s[1], g.s[1], -g.s[2], g.s[2]};
+  for (int k = g.klo(); k <= g.khi(); ++k)
+    for (int j = 1; j <= nc; ++j)
+      for (int i = 1; i <= nc; ++i) {
+        const int n = g.at(i, j, k), L = g.lin(i, j, k);
+        const double* dd = &box.lsf_dd[(size_t)2 * ND * L];
+        double* v = &st.v[(size_t)NCF * L];
+        const double a0 = eps[n];
+        // generalized Laplacian for neighbours at distance dd * dx (:1594-1601)
+        for (int d = 0; d < ND; ++d) {
+          v[1 + 2 * d] = 1 / (0.5 * dr2[d] * (dd[2 * d] + dd[2 * d + 1]) * dd[2 * d]);
+          v[2 + 2 * d] = 1 / (0.5 * dr2[d] * (dd[2 * d] + dd[2 * d + 1]) * dd[2 * d + 1]);
+        }
+        // permittivity: constant up to an electrode boundary (:1603-1608)
+        double s = 0.0;
+        for (int m = 0; m < 2 * ND; ++m) {
+          const double a = (dd[m] < 1.0) ? a0 : eps[n + off[m]];
+          v[m + 1] = v[m + 1] * 2 * a0 * a / (a0 + a);
+          s = s + v[m + 1];
+        }
+        v[0] = -s;
+        for (int m = 0; m < 2 * ND; ++m)  // internal boundaries move to the right-hand side (:1612-1618)
+          if (dd[m] < 1.0) {
+            st.f[L] = st.f[L] - v[m + 1];
+            v[m + 1] = 0.0;
+          }
+      }
+  stencil_try_constant(st, NCF, g.ncell(), 2.220446049250313e-16);
+}
+
 // mg_box_lsf_stencil (afivo/src/m_af_multigrid.f90:1782-1854), distances given as data
 template <int ND>
 void mg_box_lsf_stencil(Tree& t, Box& box) {
@@ -1097,6 +1144,8 @@ void mg_set_operators_lvl(Tree& t, int lvl, bool force) {
         case mg_lsf_box: mg_box_lsf_stencil<ND>(t, box); break;
         case mg_veps_box:
         case mg_ceps_box: mg_box_lpld_stencil<ND>(t, box); break;
+        case mg_veps_box + mg_lsf_box:
+        case mg_ceps_box + mg_lsf_box: mg_box_lpld_lsf_stencil<ND>(t, box); break;
         default: std::fprintf(stderr, "mg_store_operator_stencil: unknown box tag\n"); std::abort();
       }
       box.has_op = true;

@@ -62,6 +62,12 @@ CASES = {
     "xy_lsf_uniform_nc8": (lambda: T.uniform_tree(2, 8, 8, 4), bc_mixed, dict(lsf=lsf_circle, lsf_boundary_value=1.5)),
     "cyl_lsf_uniform_nc8": (lambda: T.build_tree(2, 8, [8, 8], 4, None, coord_t=CYL), bc_cyl,
                             dict(lsf=lambda r: np.linalg.norm(r - np.array([0.0, 0.5]), axis=-1) - 0.2, lsf_boundary_value=-0.5)),
+    # mg_box_lpld_lsf_stencil: permittivity and electrode in the same boxes, Cartesian and cylindrical
+    "xy_eps_lsf_corner_nc8": (lambda: T.corner_refined_tree(2, 8, 8, 4), bc_mixed,
+                              dict(eps=eps2, lsf=lsf_circle, lsf_boundary_value=0.6)),
+    "cyl_eps_lsf_uniform_nc8": (lambda: T.build_tree(2, 8, [8, 8], 4, None, coord_t=CYL), bc_cyl,
+                                dict(eps=eps2, lsf=lambda r: np.linalg.norm(r - np.array([0.0, 0.5]), axis=-1) - 0.2,
+                                     lsf_boundary_value=-0.5)),
 }
 
 

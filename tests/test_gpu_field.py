@@ -59,6 +59,8 @@ CASES = {
     "lsf_sphere_corner_nc8": ("st3", lambda: T.corner_refined_tree(3, 8, 8, 4),
                               dict(lsf=G3.lsf_sphere, lsf_boundary_value=-0.7)),
     "lsf_sphere_uniform_nc8": ("st3", lambda: T.uniform_tree(3, 8, 8, 3), dict(lsf=G3.lsf_sphere, lsf_boundary_value=1.5)),
+    "eps_lsf_corner_nc8": ("st3", lambda: T.corner_refined_tree(3, 8, 8, 4),
+                           dict(eps=G3.eps_smooth, lsf=G3.lsf_sphere, lsf_boundary_value=0.9)),
     "xy_corner_nc8": ("plain2", lambda: T.corner_refined_tree(2, 8, 8, 5), {}),
     "cyl_channel_nc8": ("plain2", lambda: T.build_tree(2, 8, [8, 8], 6, lambda l, ix, c: (c[:, 0] < 1.5 * 0.5 ** (l - 1)) &
                                                       (np.abs(c[:, 1] - 0.5) < 0.3), coord_t=T.AF_CYL), dict(bc=G2.bc_cyl)),

@@ -84,6 +84,10 @@ CASES = {
     "eps_smooth_uniform_nc16": (lambda: T.uniform_tree(3, 16, 16, 2), dict(eps=eps_smooth)),
     "lsf_sphere_uniform_nc8": (lambda: T.uniform_tree(3, 8, 8, 3), dict(lsf=lsf_sphere, lsf_boundary_value=1.5)),
     "lsf_sphere_corner_nc8": (lambda: T.corner_refined_tree(3, 8, 8, 4), dict(lsf=lsf_sphere, lsf_boundary_value=-0.7)),
+    # mg_box_lpld_lsf_stencil (m_af_multigrid.f90:1535-1623): permittivity and electrode in the same boxes
+    "eps_lsf_corner_nc8": (lambda: T.corner_refined_tree(3, 8, 8, 4),
+                           dict(eps=eps_smooth, lsf=lsf_sphere, lsf_boundary_value=0.9)),
+    "ceps_lsf_uniform_nc8": (lambda: T.uniform_tree(3, 8, 8, 3), dict(eps=eps_const2, lsf=lsf_sphere, lsf_boundary_value=-1.2)),
 }
 
 

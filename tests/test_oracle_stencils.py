@@ -106,3 +106,55 @@ def test_constant_eps_scales_the_solution():
         return orc.get_cc(M.I_PHI, ids)
     p1, p2 = run(None), run(2.0)
     assert np.max(np.abs(p1 - 2 * p2)) <= 1e-9 * np.max(np.abs(p1))
+
+
+def test_lpld_lsf_stencil_reduces_to_its_two_parents():
+    """mg_box_lpld_lsf_stencil (m_af_multigrid.f90:1535-1623) pinned by its two limits: with a constant
+    permittivity 2 next to an electrode it is 2 x mg_box_lsf_stencil (:1782-1854) (the harmonic mean of equal
+    values, exact in binary), and in boxes of the same run without a boundary cell the tag falls back to
+    mg_veps_box / mg_ceps_box and mg_box_lpld_stencil."""
+    import test_gpu_stencils as G3
+    tree = T.uniform_tree(3, 8, 8, 3)
+    lsf_dd = G3.lsf_distances(tree, G3.lsf_sphere)
+    o_lsf, _ = solve(tree, lsf_dd=lsf_dd, lsf_value=0.5, n_v=0)
+    o_both, _ = solve(tree, eps=lambda r: np.full(r.shape[:-1], 2.0), lsf_dd=lsf_dd, lsf_value=0.5, n_v=0)
+    seen = set()
+    for b in all_ids(tree):
+        tag = o_both.tag(b)
+        seen.add(tag)
+        if tag == 5:  # mg_ceps_box + mg_lsf_box
+            assert o_lsf.tag(b) == 1
+            s1, v1, f1, _ = o_lsf.op_stencil(b)
+            s2, v2, f2, _ = o_both.op_stencil(b)
+            assert s1 == s2 == 2
+            assert np.array_equal(2.0 * v1, v2) and np.array_equal(2.0 * f1, f2)
+        else:
+            assert tag == 4 and o_lsf.tag(b) == 0
+    assert seen == {4, 5}
+    # variable permittivity: away from boundary cells the coefficients are those of mg_box_lpld_stencil
+    eps = lambda r: 1.0 + 0.5 * r[..., 0] + 0.25 * r[..., 1] * r[..., 2]
+    o_eps, _ = solve(tree, eps=eps, n_v=0)
+    o_mix, _ = solve(tree, eps=eps, lsf_dd=lsf_dd, lsf_value=0.5, n_v=0)
+    lids, dd = lsf_dd
+    dd = dd.reshape(len(lids), -1, 6)
+    checked = 0
+    for b, d in zip(lids, dd):
+        assert o_mix.tag(b) == 3  # mg_veps_box + mg_lsf_box
+        _, v_mix, f_mix, _ = o_mix.op_stencil(b)
+        _, v_eps, _, _ = o_eps.op_stencil(b)
+        free = (d >= 1.0).all(axis=1)
+        assert np.array_equal(v_mix[free], v_eps[free]) and np.all(f_mix[free] == 0.0)
+        cut = ~free
+        assert np.all(f_mix[cut] < 0)  # f = -(sum of the boundary legs), bc_correction = f * V
+        assert np.all(v_mix[cut][:, 1:][d[cut] < 1.0] == 0.0)  # boundary legs moved to the right-hand side
+        checked += int(cut.sum())
+    assert checked > 0
+    # and the solve with the mixed stencils converges
+    o, _ = solve(tree, eps=eps, lsf_dd=lsf_dd, lsf_value=0.5, n_v=0)
+    i, r = W.random_rhs_on_leaves(tree)
+    o.set_cc(M.I_RHS, i, r)
+    o.fas_fmg(True, False)
+    r0 = o.maxabs(M.I_TMP)
+    for _ in range(4):
+        o.fas_vcycle(True)
+    assert o.maxabs(M.I_TMP) < 1e-3 * r0
