@@ -74,12 +74,46 @@ module m_af_multigrid_gpu
      integer(c_int) function afmg_update_operator_stencil(h) bind(c, name="afmg_update_operator_stencil")
        import; type(c_ptr), value :: h
      end function
+     integer(c_int) function afmg_compute_phi_gradient(h, fac, with_norm) bind(c, name="afmg_compute_phi_gradient")
+       import; type(c_ptr), value :: h; real(c_double), value :: fac; integer(c_int32_t), value :: with_norm
+     end function
+     integer(c_int) function afmg_compute_field_norm(h) bind(c, name="afmg_compute_field_norm")
+       import; type(c_ptr), value :: h
+     end function
+     integer(c_int) function afmg_gc_tree(h, var, corners) bind(c, name="afmg_gc_tree")
+       import; type(c_ptr), value :: h; integer(c_int32_t), value :: var, corners
+     end function
+     integer(c_int) function afmg_set_lsf_distances(h, n_boxes, ids, n_entries, cell_ix, dd, lsf) &
+          bind(c, name="afmg_set_lsf_distances")
+       import; type(c_ptr), value :: h; integer(c_int32_t), value :: n_boxes
+       integer(c_int32_t), intent(in) :: ids(*), n_entries(*), cell_ix(*); real(c_double), intent(in) :: dd(*), lsf(*)
+     end function
+     integer(c_int) function afmg_upload_fc(h, n, ids, packed) bind(c, name="afmg_upload_fc")
+       import; type(c_ptr), value :: h; integer(c_int32_t), value :: n
+       integer(c_int32_t), intent(in) :: ids(*); real(c_double), intent(in) :: packed(*)
+     end function
+     integer(c_int) function afmg_download_fc(h, n, ids, packed) bind(c, name="afmg_download_fc")
+       import; type(c_ptr), value :: h; integer(c_int32_t), value :: n
+       integer(c_int32_t), intent(in) :: ids(*); real(c_double), intent(out) :: packed(*)
+     end function
+     integer(c_int) function afmg_helmholtz_compute(modes, n_modes, coeffs, max_fmg, max_rel, n_cycles, residuals) &
+          bind(c, name="afmg_helmholtz_compute")
+       import; type(c_ptr), intent(in) :: modes(*); integer(c_int32_t), value :: n_modes, max_fmg
+       real(c_double), intent(in) :: coeffs(*); real(c_double), value :: max_rel
+       integer(c_int32_t), intent(out) :: n_cycles(*); real(c_double), intent(out) :: residuals(*)
+     end function
+     integer(c_int) function afmg_field_solve(h, have_guess, threshold, max_residual, max_fmg, n_vcycles, &
+          residuals, n_fmg, n_vc) bind(c, name="afmg_field_solve")
+       import; type(c_ptr), value :: h; integer(c_int32_t), value :: have_guess, max_fmg, n_vcycles
+       real(c_double), value :: threshold, max_residual
+       real(c_double), intent(out) :: residuals(*); integer(c_int32_t), intent(out) :: n_fmg, n_vc
+     end function
      integer(c_int) function afmg_max_abs(h, var, val) bind(c, name="afmg_max_abs")
        import; type(c_ptr), value :: h; integer(c_int32_t), value :: var; real(c_double), intent(out) :: val
      end function
   end interface
 
-  integer, parameter :: afmg_phi = 0, afmg_rhs = 1, afmg_tmp = 2
+  integer, parameter :: afmg_phi = 0, afmg_rhs = 1, afmg_tmp = 2, afmg_eps = 3, afmg_fld = 4, afmg_photo = 5
 
   !> One GPU solver per mg_t; looked up by the address-independent key mg%i_phi/mg%i_rhs/lambda slot
   type gpu_state_t
@@ -92,6 +126,7 @@ module m_af_multigrid_gpu
 
   public :: mg_gpu_init, mg_gpu_destroy, mg_gpu_fas_fmg, mg_gpu_fas_vcycle
   public :: mg_gpu_update_operator_stencil, mg_gpu_tree_maxabs_tmp
+  public :: mg_gpu_compute_phi_gradient, mg_gpu_compute_field_norm, mg_gpu_gc_tree_norm, photoi_gpu_helmh_compute
 
 contains
 
@@ -351,6 +386,129 @@ contains
     call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .false.)
     if (set_residual) call transfer(tree, slot, mg%i_tmp, afmg_tmp, ids, .false.)
   end subroutine mg_gpu_fas_vcycle
+
+  !> mg_compute_phi_gradient(tree, mg, i_fc, fac, i_norm) (m_af_multigrid.f90:1857-1898) on the device, from the
+  !> potential the last solve left there.  The face-centred field (and the norm) are downloaded into box%fc /
+  !> box%cc.  Variable-eps boxes need tree%mg_i_eps on the device, level-set boxes their distance stencils;
+  !> both are (re-)sent when the tree changed.
+  subroutine mg_gpu_compute_phi_gradient(tree, mg, i_fc, fac, slot, i_norm)
+    type(af_t), intent(inout)     :: tree
+    type(mg_t), intent(in)        :: mg
+    integer, intent(in)           :: i_fc, slot
+    real(dp), intent(in)          :: fac
+    integer, intent(in), optional :: i_norm
+    integer, allocatable          :: ids(:)
+    real(c_double), allocatable   :: buf(:, :)
+    integer :: i, n1
+    call all_ids(tree, ids, .false.)
+    if (tree%mg_i_eps > 0) call transfer(tree, slot, tree%mg_i_eps, afmg_eps, ids, .true.)
+    if (tree%mg_i_lsf > 0) call sync_lsf_distances(tree, mg, slot, ids)
+    call check(afmg_compute_phi_gradient(solvers(slot)%h, fac, merge(1, 0, present(i_norm))), "afmg_compute_phi_gradient")
+    n1 = NDIM * (tree%n_cell + 1)**NDIM
+    allocate(buf(n1, size(ids)))
+    call check(afmg_download_fc(solvers(slot)%h, size(ids), ids, buf), "afmg_download_fc")
+    !$omp parallel do
+    do i = 1, size(ids)
+       tree%boxes(ids(i))%fc(DTIMES(:), :, i_fc) = reshape(buf(:, i), shape(tree%boxes(ids(i))%fc(DTIMES(:), :, i_fc)))
+    end do
+    if (present(i_norm)) call transfer(tree, slot, i_norm, afmg_fld, ids, .false.)
+  end subroutine mg_gpu_compute_phi_gradient
+
+  !> mg_compute_field_norm (m_af_multigrid.f90:2002-2020) after the host changed box%fc (surface_correct_field_fc)
+  subroutine mg_gpu_compute_field_norm(tree, i_fc, i_norm, slot)
+    type(af_t), intent(inout)   :: tree
+    integer, intent(in)         :: i_fc, i_norm, slot
+    integer, allocatable        :: ids(:)
+    real(c_double), allocatable :: buf(:, :)
+    integer :: i, n1
+    call all_ids(tree, ids, .false.)
+    n1 = NDIM * (tree%n_cell + 1)**NDIM
+    allocate(buf(n1, size(ids)))
+    !$omp parallel do
+    do i = 1, size(ids)
+       buf(:, i) = reshape(tree%boxes(ids(i))%fc(DTIMES(:), :, i_fc), [n1])
+    end do
+    call check(afmg_upload_fc(solvers(slot)%h, size(ids), ids, buf), "afmg_upload_fc")
+    call check(afmg_compute_field_norm(solvers(slot)%h), "afmg_compute_field_norm")
+    call transfer(tree, slot, i_norm, afmg_fld, ids, .false.)
+  end subroutine mg_gpu_compute_field_norm
+
+  !> af_gc_tree(tree, [i_norm]) (m_af_ghostcell.f90:25-46) for the field norm with af_bc_neumann_zero / af_gc_interp
+  !> (src/m_field.f90:392-393, :547); downloads the norm with its ghost cells
+  subroutine mg_gpu_gc_tree_norm(tree, i_norm, slot)
+    type(af_t), intent(inout) :: tree
+    integer, intent(in)       :: i_norm, slot
+    integer, allocatable      :: ids(:)
+    call all_ids(tree, ids, .false.)
+    call check(afmg_gc_tree(solvers(slot)%h, afmg_fld, 1), "afmg_gc_tree")
+    call transfer(tree, slot, i_norm, afmg_fld, ids, .false.)
+  end subroutine mg_gpu_gc_tree_norm
+
+  !> Ship the sparse level-set distance stencils (mg_lsf_distance_key) and the lsf value of their cells
+  subroutine sync_lsf_distances(tree, mg, slot, ids)
+    type(af_t), intent(in) :: tree
+    type(mg_t), intent(in) :: mg
+    integer, intent(in)    :: slot, ids(:)
+    integer, allocatable   :: n_entries(:), cells(:, :)
+    real(c_double), allocatable :: dd(:, :), lsf(:)
+    integer :: i, n, ix, ne, k, m
+#if NDIM == 2
+    integer :: ij(2)
+#elif NDIM == 3
+    integer :: ijk3(3)
+#endif
+    allocate(n_entries(size(ids)))
+    ne = 0
+    do i = 1, size(ids)
+       ix = af_stencil_index(tree%boxes(ids(i)), mg_lsf_distance_key)
+       n_entries(i) = 0
+       if (ix /= af_stencil_none) n_entries(i) = size(tree%boxes(ids(i))%stencils(ix)%sparse_ix, 2)
+       ne = ne + n_entries(i)
+    end do
+    allocate(cells(NDIM, max(ne, 1)), dd(2*NDIM, max(ne, 1)), lsf(max(ne, 1)))
+    k = 0
+    do i = 1, size(ids)
+       if (n_entries(i) == 0) cycle
+       ix = af_stencil_index(tree%boxes(ids(i)), mg_lsf_distance_key)
+       associate (st => tree%boxes(ids(i))%stencils(ix), box => tree%boxes(ids(i)))
+         do n = 1, n_entries(i)
+            k = k + 1
+            cells(:, k) = st%sparse_ix(:, n)
+            dd(:, k) = st%sparse_v(:, n)
+#if NDIM == 2
+            ij = st%sparse_ix(:, n); lsf(k) = box%cc(ij(1), ij(2), mg%i_lsf)
+#elif NDIM == 3
+            ijk3 = st%sparse_ix(:, n); lsf(k) = box%cc(ijk3(1), ijk3(2), ijk3(3), mg%i_lsf)
+#endif
+         end do
+       end associate
+    end do
+    m = size(ids)
+    call check(afmg_set_lsf_distances(solvers(slot)%h, m, ids, n_entries, cells, dd, lsf), "afmg_set_lsf_distances")
+  end subroutine sync_lsf_distances
+
+  !> photoi_helmh_compute (src/m_photoi_helmh.f90:162-204) with all modes solved on the device: slots(n) is the
+  !> solver of mg_helm(n); the shared rhs goes up once, the accumulated source i_photo comes back once.
+  subroutine photoi_gpu_helmh_compute(tree, mg_helm, slots, coeffs, i_photo, max_fmg_cycles, max_rel_residual)
+    type(af_t), intent(inout) :: tree
+    type(mg_t), intent(inout) :: mg_helm(:)
+    integer, intent(in)       :: slots(:), i_photo, max_fmg_cycles
+    real(dp), intent(in)      :: coeffs(:), max_rel_residual
+    type(c_ptr)               :: hs(size(slots))
+    integer(c_int32_t)        :: n_cycles(size(slots))
+    real(c_double)            :: residuals(size(slots))
+    integer, allocatable      :: ids(:), leaves(:)
+    integer :: n
+    do n = 1, size(slots)
+       call sync_tree(tree, mg_helm(n), slots(n))
+       hs(n) = solvers(slots(n))%h
+    end do
+    call all_ids(tree, leaves, .true.); call all_ids(tree, ids, .false.)
+    call transfer(tree, slots(1), mg_helm(1)%i_rhs, afmg_rhs, leaves, .true.)
+    call check(afmg_helmholtz_compute(hs, size(slots), coeffs, max_fmg_cycles, max_rel_residual, n_cycles, residuals), &
+         "afmg_helmholtz_compute")
+    call transfer(tree, slots(1), i_photo, afmg_photo, leaves, .false.)
+  end subroutine photoi_gpu_helmh_compute
 
   !> max |residual| over leaves without downloading i_tmp (af_tree_maxabs_cc, m_af_utils.f90:773)
   subroutine mg_gpu_tree_maxabs_tmp(slot, val)

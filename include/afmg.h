@@ -111,8 +111,9 @@ const char* afmg_last_error(const afmg_handle* h);
 /* ---- topology: called after mg_init and whenever af_adjust_refinement (m_af_core.f90:697) changed
  * the tree.  Copies the arrays; rebuilds slot maps, ghost-cell plans, constant stencils
  * (mg_set_operators_tree, m_af_multigrid.f90:1216-1224) and the coarse-grid factorisation
- * (coarse_solver_initialize, m_coarse_solver.f90:71-194).  Cell data of boxes that exist in both the
- * old and the new tree (same id, lvl and ix) is kept on the device. */
+ * (coarse_solver_initialize, m_coarse_solver.f90:71-194).  Cell data on the device is reset to zero: the
+ * caller uploads phi (the previous solution, prolonged onto new boxes by the reference's refinement) and rhs
+ * again, as the shim's mg_gpu_fas_* do before every solve. */
 int afmg_set_tree(afmg_handle* h, const afmg_tree* tree);
 
 /* ---- boundary conditions as data: one row per physical face.  Replaces the mg%sides_bc callback
