@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(256) k_resid_gen(DevCtx cx, const int* list, i
 // colours are pushed to the neighbours, rule faces are recomputed (epilogue_faces); edges / corners
 // are done by k_edges_corners afterwards.
 template <int NC>
-__global__ void __launch_bounds__(256) k_correct3(DevCtx cx, int slot0, int nbox, int push) {
+__global__ void __launch_bounds__(256, 4) k_correct3(DevCtx cx, int slot0, int nbox, int push) {
   pdl_wait();
   using L = Lay3<NC>;
   constexpr int H = L::H, W = H + 2, NI = L::NI, COL = L::COL, BOX = L::BOX;
@@ -739,7 +739,62 @@ __global__ void __launch_bounds__(256) k_correct3(DevCtx cx, int slot0, int nbox
   constexpr int TPBX = H * NC;  // threads per k-range
   constexpr int KSX = (256 / TPBX < NC) ? 256 / TPBX : NC;
   constexpr int KLX = NC / KSX;
-  if (t < TPBX * KSX) {
+  if (t < TPBX * KSX && pkind == 0 && pshape == 8 && (KLX % 2) == 0) {
+    // Default stencil_prolong_248 (m_af_stencil.f90:766-813), the common case.  A thread owns the cell pair
+    // i = 2m+1, 2m+2 of row j and walks k: the 3 x 2 x 3 coarse values it needs per fine k-pair stay in
+    // registers and slide along k (6 LDS per k-pair instead of 32); the coefficients are the literals of
+    // mg_box_prolong_linear_stencil (m_af_multigrid.f90:1282), which is what cx.pcoef holds here.
+    constexpr double c27 = 27 / 64.0, c9 = 9 / 64.0, c3 = 3 / 64.0, c1 = 1 / 64.0;
+    const int m = t % H, j = (t / H) % NC + 1, ks = t / TPBX;
+    const int j1 = (j + 1) >> 1, j2 = j1 + 1 - 2 * (j & 1);
+    const int K0 = ks * (KLX / 2);  // coarse plane below the first one this thread centres on
+    double A[2][3], B[2][3], C[2][3];
+    auto load_plane = [&](double (&P)[2][3], int kz) {
+      const double* r1 = sub + (kz * W + j1) * W + m;
+      const double* r2 = sub + (kz * W + j2) * W + m;
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {
+        P[0][x] = r1[x];
+        P[1][x] = r2[x];
+      }
+    };
+    load_plane(A, K0);
+    load_plane(B, K0 + 1);
+    const int jpar = j & 1;
+#pragma unroll
+    for (int kc = 0; kc < KLX / 2; ++kc) {
+      load_plane(C, K0 + kc + 2);
+#pragma unroll
+      for (int ko = 0; ko < 2; ++ko) {  // ko = 0: odd fine k (k2 = plane below), 1: even k (plane above)
+        const int k = ks * KLX + 2 * kc + ko + 1;
+        const double(&Q)[2][3] = ko ? C : A;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {  // p = 1: i = 2m+1 (i2 = i1 - 1), p = 0: i = 2m+2 (i2 = i1 + 1)
+          const int x2 = p ? 0 : 2;
+          const int c = (p + jpar + ko + 1) & 1;  // colour of that cell: (i + j + k) & 1
+          double* Ic = c ? I1 : I0;
+          const int idx = L::iidx(m, j, k);
+          double acc = Ic[idx];
+          acc = acc + c27 * B[0][1];
+          acc = acc + c9 * B[0][x2];
+          acc = acc + c9 * B[1][1];
+          acc = acc + c3 * B[1][x2];
+          acc = acc + c9 * Q[0][1];
+          acc = acc + c3 * Q[0][x2];
+          acc = acc + c3 * Q[1][1];
+          acc = acc + c1 * Q[1][x2];
+          Ic[idx] = acc;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+          A[r][x] = B[r][x];
+          B[r][x] = C[r][x];
+        }
+    }
+  } else if (t < TPBX * KSX) {
     const int m = t % H, j = (t / H) % NC + 1, ks = t / TPBX;
     const int j1 = (j + 1) >> 1, j2 = j1 + 1 - 2 * (j & 1);
 #pragma unroll
