@@ -756,8 +756,16 @@ int coarse_setup(afmg_handle* h) {
     if (ty != AFMG_BC_DIRICHLET && ty != AFMG_BC_NEUMANN)
       return h->fail(AFMG_ERR_UNSUPPORTED, "coarse grid: unsupported boundary condition %d (reference: error stop, "
                                            "m_coarse_solver.f90:486)", ty);
-    if (face_type[f] != 0 && face_type[f] != ty)
-      return h->fail(AFMG_ERR_UNSUPPORTED, "coarse grid: mixed boundary condition types on domain face %d", f + 1);
+    if (face_type[f] != 0 && face_type[f] != ty) {
+      // different level-1 boxes put different condition types on one domain face (the reference allows it:
+      // stencil_handle_boundaries works box by box, m_coarse_solver.f90:442-491): the operator is no longer
+      // separable, so the general dense coarse solve takes over
+      for (int d = 0; d < 3; ++d)
+        if (h->o.periodic[d])
+          return h->fail(AFMG_ERR_UNSUPPORTED, "coarse grid: mixed boundary condition types on domain face %d of a "
+                                               "periodic domain", f + 1);
+      return coarse_setup_dense(h);
+    }
     face_type[f] = ty;
   }
   const double* c1 = nullptr;

@@ -35,66 +35,101 @@ struct Fc3 {
   static AFMG_HD int at(int i, int j, int k, int d) { return d * PER + (i - 1) + N1 * ((j - 1) + N1 * (k - 1)); }
 };
 
-// fc(i,j,k,d) of mg_box_lpl_gradient from a box record S holding interior + face ghosts (shared or global)
-template <int NC>
-__device__ __forceinline__ double face_val3(const double* S, const double* E, double idr, int d, int i, int j, int k) {
-  using L = Lay3<NC>;
-  int il = i, jl = j, kl = k;
-  if (d == 0) --il;
-  else if (d == 1) --jl;
-  else --kl;
-  const int qh = L::cell(i, j, k), ql = L::cell(il, jl, kl);
-  const double hi = S[qh], lo = S[ql];
-  if (E) {  // box boundaries of a variable-eps box (:1938-1997)
-    const int pos = (d == 0) ? i : (d == 1 ? j : k);
-    if (pos == 1 || pos == NC + 1) {
-      const double eh = E[qh], el = E[ql];
-      const double eg = (pos == 1) ? el : eh;
-      return 2 * idr * (hi - lo) * eg / (eh + el);
-    }
-  }
-  return idr * (hi - lo);
-}
-
-// mg_box_lpl_gradient (+ mg_box_field_norm) for boxes [slot0, slot0+nbox): one CTA per box, phi by TMA
+// mg_box_lpl_gradient (+ mg_box_field_norm) for boxes [slot0, slot0+nbox): one CTA per box.  phi (interior and
+// face ghost cells) is first copied into shared memory in the reference's natural order P(0:nc+1)^3, so that the
+// three difference passes and the norm index it with plain strides and fc leaves in its own record order
+// (rows of nc+1 / nc consecutive doubles).  Boundary faces of variable-eps boxes (:1938-1997) read eps from
+// global memory (few boxes).
 template <int NC>
 __global__ void __launch_bounds__(256) k_grad3(DevCtx cx, FieldCtx fx, int slot0, int nbox, int with_norm) {
   using L = Lay3<NC>;
   using F = Fc3<NC>;
-  constexpr int COL = L::COL, BOX = L::BOX, NI = L::NI, N1 = NC + 1;
-  extern __shared__ __align__(128) double S[];  // 2*COL
-  __shared__ uint64_t bar;
+  constexpr int BOX = L::BOX, N1 = NC + 1, N2 = NC + 2;
+  extern __shared__ __align__(16) double P[];  // N2^3, natural order (i fastest); edges / corners unused
   const int slot = slot0 + blockIdx.x;
   const int t = threadIdx.x;
-  if (t == 0) mbar_init(&bar, 1);
-  __syncthreads();
-  if (t == 0) {
-    mbar_expect_tx(&bar, 2 * COL * 8);
-    bulk_g2s(S, cx.cc[V_PHI] + (size_t)slot * BOX, 2 * COL * 8, &bar);
+  const double* phi = cx.cc[V_PHI] + (size_t)slot * BOX;
+  for (int n = t; n < NC * NC * NC; n += 256) {
+    const int i = n % NC + 1, j = (n / NC) % NC + 1, k = n / (NC * NC) + 1;
+    P[(k * N2 + j) * N2 + i] = phi[L::interior(i, j, k)];
+  }
+  for (int n = t; n < 6 * NC * NC; n += 256) {
+    const int f = n / (NC * NC), a = n % NC + 1, b = (n / NC) % NC + 1;
+    const int g = (f & 1) ? N1 : 0;
+    const int i = (f < 2) ? g : a, j = (f < 2) ? a : (f < 4 ? g : b), k = (f < 4) ? b : g;
+    P[(k * N2 + j) * N2 + i] = phi[L::face(f, a, b)];
   }
   const int lv = cx.lvl[slot];
-  const double idr[3] = {fx.inv_dr[lv][0], fx.inv_dr[lv][1], fx.inv_dr[lv][2]};
+  const double idr0 = fx.inv_dr[lv][0], idr1 = fx.inv_dr[lv][1], idr2 = fx.inv_dr[lv][2];
   const double* E = (fx.veps && fx.veps[slot]) ? fx.eps + (size_t)slot * BOX : nullptr;
   double* fcb = fx.fc + (size_t)slot * F::LEN;
-  mbar_wait(&bar, 0);
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    const int ni = (d == 0) ? N1 : NC, nj = (d == 1) ? N1 : NC, nk = (d == 2) ? N1 : NC;
-    for (int n = t; n < ni * nj * nk; n += 256) {
-      const int i = n % ni + 1, j = (n / ni) % nj + 1, k = n / (ni * nj) + 1;
-      fcb[F::at(i, j, k, d)] = face_val3<NC>(S, E, idr[d], d, i, j, k);
+  double* out = fx.fld + (size_t)slot * BOX;
+  __syncthreads();
+  // thread (i, j, ks) walks k: the centre value and its z neighbours slide through registers, x / y neighbours
+  // come from shared memory; every face value is inv_dr(d) * (phi(high cell) - phi(low cell)), the eps-weighted
+  // form on the boundary faces of a variable-eps box
+  constexpr int KS = (256 / (NC * NC) < NC) ? ((256 / (NC * NC) > 0) ? 256 / (NC * NC) : 1) : NC;
+  constexpr int KL = NC / KS;
+  // Entries of the record outside a component's index range (e.g. fc(nc+1, j, k, 2)) are never assigned by the
+  // reference and keep the zero af_init_box gave them (m_af_core.f90:555).  Writing that zero here completes
+  // every 32-byte sector of the record, which spares the memory system a read-modify-write per hole.
+  {
+    constexpr int NA = N1 * N1, NH = NA + NC * N1;
+    for (int n = t; n < 3 * NH; n += 256) {
+      const int d = n / NH;
+      int r = n - d * NH;
+      const int o1 = (d == 0) ? 1 : 0, o2 = (d == 2) ? 1 : 2;
+      int q[3];
+      if (r < NA) {
+        q[o1] = N1;
+        q[d] = r % N1 + 1;
+        q[o2] = r / N1 + 1;
+      } else {
+        r -= NA;
+        q[o2] = N1;
+        q[d] = r % N1 + 1;
+        q[o1] = r / N1 + 1;
+      }
+      fcb[F::at(q[0], q[1], q[2], d)] = 0.0;
     }
   }
-  if (!with_norm) return;
-  double* out = fx.fld + (size_t)slot * BOX;
-  for (int n = t; n < 2 * NI; n += 256) {
-    const int q = (n < NI) ? n : COL + (n - NI);
-    int i, j, k;
-    L::uncell(q, i, j, k);
-    const double a = face_val3<NC>(S, E, idr[0], 0, i, j, k) + face_val3<NC>(S, E, idr[0], 0, i + 1, j, k);
-    const double b = face_val3<NC>(S, E, idr[1], 1, i, j, k) + face_val3<NC>(S, E, idr[1], 1, i, j + 1, k);
-    const double c = face_val3<NC>(S, E, idr[2], 2, i, j, k) + face_val3<NC>(S, E, idr[2], 2, i, j, k + 1);
-    out[q] = 0.5 * sqrt(a * a + b * b + c * c);
+  if (t >= NC * NC * KS) return;
+  const int i = t % NC + 1, j = (t / NC) % NC + 1, ks = t / (NC * NC);
+  auto face = [&](int d, double idr, double hi, double lo, int ih, int jh, int kh) -> double {
+    if (E) {  // (ih, jh, kh) = high cell of the face; pos = its index along d
+      const int pos = (d == 0) ? ih : (d == 1 ? jh : kh);
+      if (pos == 1 || pos == N1) {
+        const double eh = E[L::cell(ih, jh, kh)];
+        const double el = E[L::cell(ih - (d == 0), jh - (d == 1), kh - (d == 2))];
+        const double eg = (pos == 1) ? el : eh;
+        return 2 * idr * (hi - lo) * eg / (eh + el);
+      }
+    }
+    return idr * (hi - lo);
+  };
+  const int k0 = ks * KL + 1;
+  const double* Pc = P + (k0 * N2 + j) * N2 + i;
+  double zm = Pc[-N2 * N2], c = Pc[0];
+#pragma unroll 4
+  for (int kk = 0; kk < KL; ++kk) {
+    const int k = k0 + kk;
+    const double xm = Pc[-1], xp = Pc[1], ym = Pc[-N2], yp = Pc[N2], zp = Pc[N2 * N2];
+    const double fxl = face(0, idr0, c, xm, i, j, k), fxh = face(0, idr0, xp, c, i + 1, j, k);
+    const double fyl = face(1, idr1, c, ym, i, j, k), fyh = face(1, idr1, yp, c, i, j + 1, k);
+    const double fzl = face(2, idr2, c, zm, i, j, k), fzh = face(2, idr2, zp, c, i, j, k + 1);
+    fcb[F::at(i, j, k, 0)] = fxl;
+    fcb[F::at(i, j, k, 1)] = fyl;
+    fcb[F::at(i, j, k, 2)] = fzl;
+    if (i == NC) fcb[F::at(N1, j, k, 0)] = fxh;
+    if (j == NC) fcb[F::at(i, N1, k, 1)] = fyh;
+    if (k == NC) fcb[F::at(i, j, N1, 2)] = fzh;
+    if (with_norm) {
+      const double a = fxl + fxh, b = fyl + fyh, cc = fzl + fzh;
+      out[L::interior(i, j, k)] = 0.5 * sqrt(a * a + b * b + cc * cc);
+    }
+    zm = c;
+    c = zp;
+    Pc += N2 * N2;
   }
 }
 

@@ -347,6 +347,20 @@ def run_gpu(args):
     fmg_ms = allmax(mg.last_cycle_ms()) / n_fmg
     cu_fmg = mg.cell_updates(0, True)
 
+    # ---- the callers' next step, field_from_potential (src/m_field.f90:531-548), on the device (1 GPU) ------
+    field = None
+    if world == 1 and tree.ndim == 3:
+        M.field_from_potential(tree, mg, -1.0)  # allocates fc / norm
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            M.field_from_potential(tree, mg, -1.0)  # blocking C-ABI call
+        f_ms = 1e3 * (time.perf_counter() - t0) / reps
+        nc = tree.nc
+        per_cell = 8 * ((nc + 2) / nc) ** 3 + 3 * 8 * (nc + 1) / nc + 8  # read phi, write fc and the norm
+        field = {"ms": f_ms, "algorithmic_GBs": per_cell * tree.n_boxes * nc ** 3 / (f_ms * 1e-3) / 1e9,
+                 "what": "gradient + norm on all boxes, ghost cells of the norm on all levels"}
+
     # ---- e2e: host buffers through the C ABI -----------------------------------------------
     # e2e: rhs goes up as interior cells only (its ghost cells are never read), phi comes back with ghost cells
     ncell = tree.nc ** tree.ndim
@@ -432,6 +446,7 @@ def run_gpu(args):
                                     "(3 variables) exceeds the 126 MB L2; no flush needed"},
             "vcycles_per_s": args.steps / (ms_max * 1e-3),
             "fmg": {"ms": fmg_ms, "cell_updates_per_s": cu_fmg / (fmg_ms * 1e-3)},
+            "field_from_potential": field,
             "residual": {"after_fmg": res0, "after_timed_cycles": res1},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                     "steps": e2e_steps, "ms_per_step": 1e3 * wall_max / e2e_steps},

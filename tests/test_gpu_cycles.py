@@ -147,3 +147,27 @@ def test_periodic_domains(name):
     assert ho[-1] < 0.1 * ho[0]
     assert np.all(np.abs(ho - hg) <= 1e-9 * ho[0] + 1e-6 * ho), (ho, hg)
     assert np.max(np.abs(a - b)) <= RTOL * np.max(np.abs(a))
+
+
+def test_mixed_bc_types_on_one_domain_face():
+    """Level-1 boxes may put different condition types on the same domain face (stencil_handle_boundaries is
+    per box, m_coarse_solver.f90:442-491): e.g. a grounded plate covering part of the bottom.  The coarse
+    operator is then not separable and the dense coarse solve takes over."""
+    tree = T.build_tree(3, 8, [16, 16, 8], 3, lambda l, ix, c: np.linalg.norm(c - 0.4, axis=1) < 0.45)
+
+    def bc_plate(nb, coords):
+        centre_x = coords[:, :, 0].mean(axis=1)
+        if nb == 5:  # low z: Dirichlet under the plate (x < 0.5), Neumann beside it
+            ty = np.where(centre_x < 0.5, W.AF_BC_DIRICHLET, W.AF_BC_NEUMANN)
+            return ty, np.where(ty[:, None] == W.AF_BC_DIRICHLET, 1.0, 0.0) * np.ones(coords.shape[:2])
+        if nb == 6:
+            return W.AF_BC_DIRICHLET, 0.0
+        return W.AF_BC_NEUMANN, 0.0
+
+    bc = W.bc_table(tree, bc_plate)
+    on5 = bc.types[(bc.nbs == 5) & (tree.lvl[bc.ids] == 1)]
+    assert len(set(on5.tolist())) == 2, "the case must mix types on one face of the coarse grid"
+    ho, hg, a, b = run_both(tree, bc_plate)
+    assert ho[-1] < 0.1 * ho[0]
+    assert np.all(np.abs(ho - hg) <= 1e-9 * ho[0] + 1e-6 * ho), (ho, hg)
+    assert np.max(np.abs(a - b)) <= RTOL * np.max(np.abs(a))

@@ -48,4 +48,12 @@ for _ in range(reps):
     mg.solve_coarse_grid()
 for k, (ms, calls) in sorted(mg.profile().items()):
     print(f"  {k:20s} {1e3 * ms / calls:9.2f} us/launch  x{calls}")
+mg.set_profiling(False)
+M.field_from_potential(tree, mg, -1.0)
+mg.set_profiling(True)
+for _ in range(reps):
+    M.field_from_potential(tree, mg, -1.0)
+for k, (ms, calls) in sorted(mg.profile().items()):
+    if k.startswith("field"):
+        print(f"  {k:20s} {1e3 * ms / calls:9.2f} us/launch  x{calls}")
 M.mg_destroy(mg)
