@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(256) k_resid_gen(DevCtx cx, const int* list, i
   }
 }
 
-// k_correct3: k_correct2 with the child's interior staged in shared memory by TMA (bulk load, update
+// k_correct3: correct_children with the child's interior staged in shared memory by TMA (bulk load, update
 // in place, bulk store).  With push != 0 it also performs the side ghost fill of the af_gc_lvl that
 // follows correct_children in the cycle (m_af_multigrid.f90:222, :171): boundary layers of both
 // colours are pushed to the neighbours, rule faces are recomputed (epilogue_faces); edges / corners
