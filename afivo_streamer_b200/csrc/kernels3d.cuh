@@ -201,13 +201,32 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // the box are recomputed from their rule (bc_to_gc :173-279; mg_sides_rb m_af_multigrid.f90:383-459).
 // t = index among the TPB threads working on this box.  The z faces are contiguous in shared memory
 // and leave as TMA bulk copies issued by t == 0; the CALLER commits and waits for the bulk group.
+// Face metadata of one box (neighbour slots, rule rows, rule coefficients), optionally prefetched into shared
+// memory while the box data is still in flight: on small levels the three dependent global loads of the epilogue
+// (nbr -> aux -> rule_c) are otherwise a quarter of a half-sweep's duration.
+struct FaceMeta {
+  int nb[6];
+  int row[6];
+  double rc[6][3];
+};
+__device__ __forceinline__ void prefetch_face_meta(const DevCtx& cx, int slot, FaceMeta* fm, int f) {
+  const int nb = cx.nbr[slot * 6 + f], row = cx.aux[slot * 6 + f];
+  fm->nb[f] = nb;
+  fm->row[f] = row;
+  if (nb < 0) {
+    fm->rc[f][0] = cx.rule_c[3 * row];
+    fm->rc[f][1] = cx.rule_c[3 * row + 1];
+    fm->rc[f][2] = cx.rule_c[3 * row + 2];
+  }
+}
+
 template <int NC, int TPB, bool SRC_SMEM = true>
 __device__ __forceinline__ void epilogue_faces(const DevCtx& cx, int slot, const double* I0, const double* I1, int mask,
-                                               int t) {
+                                               int t, const FaceMeta* fm = nullptr) {
   using L = Lay3<NC>;
   constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX;
   double* const gbox = cx.cc[V_PHI] + (size_t)slot * BOX;
-  const int* nbp = cx.nbr + slot * 6;
+  const int* nbp = fm ? fm->nb : cx.nbr + slot * 6;
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     if (!((mask >> c) & 1)) continue;
@@ -247,8 +266,8 @@ __device__ __forceinline__ void epilogue_faces(const DevCtx& cx, int slot, const
 #pragma unroll
   for (int f = 0; f < 6; ++f) {
     if (nbp[f] >= 0) continue;
-    const int row = cx.aux[slot * 6 + f];
-    const double* rc = cx.rule_c + 3 * row;
+    const int row = fm ? fm->row[f] : cx.aux[slot * 6 + f];
+    const double* rc = fm ? fm->rc[f] : cx.rule_c + 3 * row;
     const double r0 = rc[0], r1 = rc[1], r2 = rc[2];
     const double* B = cx.rule_B + (size_t)row * L::NC2;
     const int d = f >> 1, hi = f & 1;
@@ -305,6 +324,8 @@ __global__ void __launch_bounds__(BPC* KS* NC* NC / 2, MINB) k_gsrb2(DevCtx cx, 
   double* const R = smem + b * SBOX + COL;
   const double* cf = cx.coef + 8 * lvl;
   const double c2 = cf[1], c3 = cf[2], c4 = cf[3], c5 = cf[4], c6 = cf[5], c7 = cf[6], inv = cf[7];
+  __shared__ FaceMeta fmeta[BPC];
+  if (active && t < 6) prefetch_face_meta(cx, slot, &fmeta[b], t);  // visible after the __syncthreads below
   mbar_wait(&bar, 0);
 
   if (active) {
@@ -347,7 +368,7 @@ __global__ void __launch_bounds__(BPC* KS* NC* NC / 2, MINB) k_gsrb2(DevCtx cx, 
 
   // ---- epilogue: new colour-C values are in R (layout of an interior colour block)
   if (t == 0) bulk_s2g(phi + (size_t)slot * BOX + C * COL, R, NI * 8);
-  epilogue_faces<NC, TPB>(cx, slot, C ? S : R, C ? R : S, 1 << C, t);
+  epilogue_faces<NC, TPB>(cx, slot, C ? S : R, C ? R : S, 1 << C, t, &fmeta[b]);
   if (t == 0) bulk_commit();
   if (t == 0) bulk_wait_read0();
 }
@@ -706,6 +727,8 @@ __global__ void __launch_bounds__(256, 4) k_correct3(DevCtx cx, int slot0, int n
   const double* phi = cx.at<BOX>(V_PHI, slot);
   const double* tmp = cx.at<BOX>(V_TMP, slot);
   const int ox = (ch & 1) * H, oy = ((ch >> 1) & 1) * H, oz = ((ch >> 2) & 1) * H;
+  __shared__ FaceMeta fmeta;
+  if (push && t < 6) prefetch_face_meta(cx, cslot, &fmeta, t);
   {
     // all loads of the window are issued before the first use (one round trip instead of NW)
     constexpr int NW = (W * W * W + 255) / 256;
@@ -842,7 +865,7 @@ __global__ void __launch_bounds__(256, 4) k_correct3(DevCtx cx, int slot0, int n
     bulk_s2g(cphi, I0, NI * 8);
     bulk_s2g(cphi + COL, I1, NI * 8);
   }
-  if (push) epilogue_faces<NC, 256>(cx, cslot, I0, I1, 3, t);
+  if (push) epilogue_faces<NC, 256>(cx, cslot, I0, I1, 3, t, &fmeta);
   if (t == 0) {
     bulk_commit();
     bulk_wait_read0();
