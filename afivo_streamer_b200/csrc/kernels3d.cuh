@@ -873,17 +873,19 @@ __global__ void __launch_bounds__(256, 4) k_correct3(DevCtx cx, int slot0, int n
 }
 
 template <int NC>
-__device__ void gc_sides(const DevCtx& cx, int slot, int var);
+__device__ void gc_sides(const DevCtx& cx, int slot, int var, double* stage = nullptr);
 template <int NC>
 __device__ void gc_edges_corners(const DevCtx& cx, int slot, int var);
 
 // k_gc2: af_gc_lvl for one level, and for boxes with children the parent part of update_coarse
-// (see k_gc) computed from a shared-memory copy of the box (TMA bulk load) instead of global loads.
+// (rhs = L phi + tmp; tmp = phi on the full record, m_af_multigrid.f90:722-736) computed from a shared-memory copy
+// of the box: the two interior colour blocks arrive by TMA while the ghost faces are being gathered, and the
+// gathered values go straight into the copy (no read-back of what the CTA just wrote).
 template <int NC>
 __global__ void __launch_bounds__(256) k_gc2(DevCtx cx, int slot0, int nbox, int corners, int mode) {
   pdl_wait();
   using L = Lay3<NC>;
-  constexpr int NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX;
+  constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX;
   extern __shared__ __align__(128) double smem[];  // 2*COL
   __shared__ uint64_t bar;
   const int slot = slot0 + blockIdx.x;
@@ -894,20 +896,16 @@ __global__ void __launch_bounds__(256) k_gc2(DevCtx cx, int slot0, int nbox, int
     if (t == 0) mbar_init(&bar, 1);
     __syncthreads();
     if (t == 0) {
-      mbar_expect_tx(&bar, 2 * COL * 8);
-      bulk_g2s(smem, gphi, 2 * COL * 8, &bar);
+      mbar_expect_tx(&bar, 2 * NI * 8);
+      bulk_g2s(smem, gphi, NI * 8, &bar);
+      bulk_g2s(smem + COL, gphi + COL, NI * 8, &bar);
     }
   }
-  gc_sides<NC>(cx, slot, V_PHI);
+  gc_sides<NC>(cx, slot, V_PHI, upd ? smem : nullptr);
   __syncthreads();
   if (corners) gc_edges_corners<NC>(cx, slot, V_PHI);
   if (!upd) return;
   mbar_wait(&bar, 0);
-  // the staged copy may hold stale ghost faces: refresh them from what this CTA just wrote
-  for (int n = t; n < 2 * 6 * NF; n += 256) {
-    const int c = n / (6 * NF), r = n % (6 * NF);
-    smem[c * COL + NI + r] = gphi[c * COL + NI + r];
-  }
   __syncthreads();
   double* rhs = cx.cc[V_RHS] + (size_t)slot * BOX;
   double* tmp = cx.cc[V_TMP] + (size_t)slot * BOX;
@@ -917,16 +915,23 @@ __global__ void __launch_bounds__(256) k_gc2(DevCtx cx, int slot0, int nbox, int
   const int okind = cx.opk ? cx.opk[slot] : 0;
   const double* osv = okind ? cx.stv + cx.opoff[slot] : nullptr;
   const double* ofv = (okind && cx.foff[slot] >= 0) ? cx.stv + cx.foff[slot] : nullptr;
-  for (int q = t; q < BOX; q += 256) {
-    const bool is_interior = (q < L::OFF_E) && ((q % COL) < NI);
-    if (is_interior) {
-      int i, j, k;
-      L::uncell(q, i, j, k);
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+    for (int idx = t; idx < NI; idx += 256) {
+      const int m = idx % H, j = (idx / H) % NC + 1, k = idx / (H * NC) + 1;
+      const int i = 2 * m + 2 - ((c + j + k) & 1);
+      const int q = c * COL + idx;
       const double lp = okind ? apply_gen<NC>(cx, okind, osv, ofv, cf, smem, i, j, k)
                               : apply357_smem<NC>(smem, cf, c1, i, j, k);
       rhs[q] = lp + tmp[q];
+      if (mode == 1) tmp[q] = smem[q];
     }
-    if (mode == 1) tmp[q] = (q < 2 * COL) ? smem[q] : gphi[q];
+  if (mode == 1) {  // tmp = phi on the ghost cells too: faces from the copy, edges / corners from global
+    for (int n = t; n < 2 * 6 * NF; n += 256) {
+      const int q = (n / (6 * NF)) * COL + NI + n % (6 * NF);
+      tmp[q] = smem[q];
+    }
+    for (int q = 2 * COL + t; q < BOX; q += 256) tmp[q] = gphi[q];
   }
 }
 
@@ -1005,7 +1010,7 @@ __global__ void k_rb_prepare(DevCtx cx, int r0, int nr, int var) {
 // Ghost cells by gathering (af_gc_box, m_af_ghostcell.f90:64-170): sides, then edges and corners.
 // ---------------------------------------------------------------------------------------------
 template <int NC>
-__device__ void gc_sides(const DevCtx& cx, int slot, int var) {
+__device__ void gc_sides(const DevCtx& cx, int slot, int var, double* stage) {
   using L = Lay3<NC>;
   double* box = cx.cc[var] + (size_t)slot * L::BOX;
   for (int n = threadIdx.x; n < 6 * L::NC2; n += blockDim.x) {
@@ -1036,6 +1041,7 @@ __device__ void gc_sides(const DevCtx& cx, int slot, int var) {
       v = (rc[0] * B + rc[1] * x1) + rc[2] * x2;
     }
     box[L::face(f, a, b)] = v;
+    if (stage) stage[L::face(f, a, b)] = v;  // the caller's shared-memory copy of the box
   }
 }
 
