@@ -127,6 +127,7 @@ struct afmg_handle {
   int64_t launches = 0;
   bool profiling = false;
   bool pdl = false;  // programmatic dependent launch (launch_k), AFMG_PDL=1
+  bool cs_fused = true;  // single-CTA coarse solve for small separable coarse grids (AFMG_CS_FUSED=0: off)
   std::map<std::string, ProfEntry> prof;
   std::vector<std::tuple<std::string, cudaEvent_t, cudaEvent_t>> prof_pending;
 
@@ -499,6 +500,20 @@ void enq_coarse(afmg_handle* h) {
   const int nbox1 = nlev(h, 1);
   const int ntot = h->cs.nx[0] * h->cs.nx[1] * h->cs.nx[2];
   const int blocks = (ntot + 127) / 128;
+  // one CTA does it all, ghost cells of level 1 included; measured: 8^3 cells 20.6 -> 17 us per solve, but 16^3
+  // 29 -> 80 us (one SM against 32 CTAs), so only the small coarse grids of the streamer configurations take it
+  if (!h->cs_dense && ntot <= 1024 && h->cs_fused) {
+    const bool with_gc = nbox1 <= 8;
+    {
+      Launch L_(h, "coarse");
+      DISPATCH_NC(h, NC, {
+        launch_k(h, k_cs_fused<NC>, 1, 1024, (size_t)2 * ntot * sizeof(double), h->cx, h->cs, nbox1, with_gc ? 1 : 0);
+      });
+    }
+    if (with_gc) enq_barrier(h);
+    else enq_gc(h, 1, V_PHI, 1, 0);
+    return;
+  }
   {
     Launch L_(h, "coarse");
     DISPATCH_NC(h, NC, { launch_k(h, k_cs_gather<NC>, blocks, 128, 0, h->cx, h->cs, nbox1); });
@@ -1161,6 +1176,7 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
   if (e == cudaSuccess) h->d_scal = h->d_comm->scal;  // address arithmetic only
   h->peers.p[0] = h->d_comm;
   if (const char* env = getenv("AFMG_PDL")) h->pdl = atoi(env) != 0;
+  if (const char* env = getenv("AFMG_CS_FUSED")) h->cs_fused = atoi(env) != 0;
   if (const char* env = getenv("AFMG_BARRIER_TIMEOUT_S")) {
     const double sec = atof(env);
     if (sec > 0) h->barrier_timeout_ns = (unsigned long long)(sec * 1e9);

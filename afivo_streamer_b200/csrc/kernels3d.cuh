@@ -1363,4 +1363,75 @@ __global__ void k_cs_scatter(DevCtx cx, CoarseCtx cs, int nbox1, const double* x
   phi[L::interior(i, j, k)] = x[gi + cs.nx[0] * (gj + cs.nx[1] * gk)];
 }
 
+// The whole separable coarse solve (and the af_gc_lvl(1) that follows it, m_af_multigrid.f90:289) in ONE CTA for
+// coarse grids of up to 1024 cells (8^3, the streamer default): gather, three forward transforms, eigenvalue scaling, three backward
+// transforms, scatter, ghost cells -- nine launches of ~3 us each otherwise, on the critical path of every cycle.
+// Same loops and summation order as k_cs_gather / k_cs_apply / k_cs_scatter: bit-identical results.
+template <int NC>
+__global__ void __launch_bounds__(1024) k_cs_fused(DevCtx cx, CoarseCtx cs, int nbox1, int with_gc) {
+  pdl_wait();
+  using L = Lay3<NC>;
+  extern __shared__ __align__(16) double sv[];  // two work vectors of ntot doubles
+  const int ntot = cs.nx[0] * cs.nx[1] * cs.nx[2];
+  double* a = sv;
+  double* b = sv + ntot;
+  const int ncell = NC * NC * NC;
+  for (int n = threadIdx.x; n < nbox1 * ncell; n += blockDim.x) {
+    const int bx = n / ncell, r = n % ncell;
+    const int i = r % NC + 1, j = (r / NC) % NC + 1, k = r / (NC * NC) + 1;
+    const double* rhs = cx.cc[V_RHS] + (size_t)bx * L::BOX;
+    double t = rhs[L::interior(i, j, k)];
+    const int q[3] = {i, j, k};
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+      const int d = f >> 1;
+      if (cx.nbr[bx * 6 + f] >= 0) continue;
+      if (q[d] != ((f & 1) ? NC : 1)) continue;
+      const int ta = (d == 0) ? 1 : 0, tb = (d == 2) ? 1 : 2;
+      const int fi = (q[ta] - 1) + (q[tb] - 1) * NC;
+      const int row = cx.aux[bx * 6 + f];
+      t = t + cs.b2r[((size_t)bx * 6 + f) * L::NC2 + fi] * cx.rule_B[(size_t)row * L::NC2 + fi];
+    }
+    if (cs.lsf_fac) t = t + cs.lsf_fac[(size_t)bx * ncell + r] * cx.lsf_value;
+    const int gi = cs.bix[bx * 3] * NC + i - 1, gj = cs.bix[bx * 3 + 1] * NC + j - 1, gk = cs.bix[bx * 3 + 2] * NC + k - 1;
+    a[gi + cs.nx[0] * (gj + cs.nx[1] * gk)] = t;
+  }
+  __syncthreads();
+  for (int pass = 0; pass < 6; ++pass) {
+    const int d = pass % 3, trans = pass < 3, scale = pass == 2;
+    const int stride = (d == 0) ? 1 : (d == 1 ? cs.nx[0] : cs.nx[0] * cs.nx[1]);
+    const int nd = cs.nx[d];
+    const double* Q = cs.Q[d];
+    for (int n = threadIdx.x; n < ntot; n += blockDim.x) {
+      const int o = (d == 0) ? n % cs.nx[0] : (d == 1 ? (n / cs.nx[0]) % cs.nx[1] : n / (cs.nx[0] * cs.nx[1]));
+      const int base = n - o * stride;
+      double s = 0.0;
+      for (int p = 0; p < nd; ++p) {
+        const double mval = trans ? __ldg(Q + p * nd + o) : __ldg(Q + o * nd + p);
+        s = s + mval * a[base + p * stride];
+      }
+      if (scale) s = s * cs.inv_eig[n];
+      b[n] = s;
+    }
+    __syncthreads();
+    double* tsw = a;
+    a = b;
+    b = tsw;
+  }
+  for (int n = threadIdx.x; n < nbox1 * ncell; n += blockDim.x) {
+    const int bx = n / ncell, r = n % ncell;
+    const int i = r % NC + 1, j = (r / NC) % NC + 1, k = r / (NC * NC) + 1;
+    const int gi = cs.bix[bx * 3] * NC + i - 1, gj = cs.bix[bx * 3 + 1] * NC + j - 1, gk = cs.bix[bx * 3 + 2] * NC + k - 1;
+    double* phi = cx.cc[V_PHI] + (size_t)bx * L::BOX;
+    phi[L::interior(i, j, k)] = a[gi + cs.nx[0] * (gj + cs.nx[1] * gk)];
+  }
+  if (!with_gc) return;
+  // af_gc_lvl(1): sides of every level-1 box first, then edges and corners (they read the neighbours' interiors
+  // and the box's own face ghosts, all written by this CTA)
+  __syncthreads();
+  for (int bx = 0; bx < nbox1; ++bx) gc_sides<NC>(cx, bx, V_PHI);
+  __syncthreads();
+  for (int bx = 0; bx < nbox1; ++bx) gc_edges_corners<NC>(cx, bx, V_PHI);
+}
+
 }  // namespace afmg
