@@ -73,7 +73,7 @@ struct afmg_handle {
   int box_len = 0, nc2 = 0;
 
   // ---- device data
-  double* d_cc[4] = {nullptr, nullptr, nullptr, nullptr};
+  double* d_cc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phi, rhs, tmp, (eps: field state), field norm
   int *d_nbr = nullptr, *d_aux = nullptr, *d_nmat = nullptr, *d_parent = nullptr, *d_child0 = nullptr,
       *d_coff = nullptr, *d_lvl = nullptr, *d_rb_slot = nullptr, *d_rb_face = nullptr;
   double *d_coef = nullptr, *d_rule_c = nullptr, *d_rule_B = nullptr, *d_pcoef = nullptr;
@@ -117,6 +117,7 @@ struct afmg_handle {
   CommPeers peers{};
   char* d_slab = nullptr;  // phi | rhs | tmp | box sums, one allocation so that one IPC handle covers it
   size_t slab_bytes = 0, slab_var_stride = 0;
+  int slab_nvar = 3;
   char* peer_slab[AFMG_MAX_RANKS] = {};
   unsigned long long barrier_timeout_ns = 30ull * 1000000000ull;
 
@@ -1377,12 +1378,16 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
   if (h->d_slab) cudaFree(h->d_slab);
   h->d_slab = nullptr;
   h->slab_var_stride = (((size_t)total * h->box_len * sizeof(double)) + 255) / 256 * 256;
-  h->slab_bytes = 3 * h->slab_var_stride + (size_t)total * sizeof(double);
+  // multi-GPU: the field norm lives in the slab too, so that the peers can read its halo (af_gc_tree of the norm);
+  // on one GPU it is allocated on first use (afmg_field.inc)
+  h->slab_nvar = (h->nranks > 1) ? 4 : 3;
+  h->slab_bytes = h->slab_nvar * h->slab_var_stride + (size_t)total * sizeof(double);
   CK(cudaMalloc((void**)&h->d_slab, h->slab_bytes));
   CK(cudaMemset(h->d_slab, 0, h->slab_bytes));
   for (int v = 0; v < 3; ++v) h->d_cc[v] = (double*)(h->d_slab + v * h->slab_var_stride);
   h->d_cc[3] = nullptr;
-  h->d_boxsum = (double*)(h->d_slab + 3 * h->slab_var_stride);
+  h->d_cc[4] = (h->slab_nvar == 4) ? (double*)(h->d_slab + 3 * h->slab_var_stride) : nullptr;
+  h->d_boxsum = (double*)(h->d_slab + h->slab_nvar * h->slab_var_stride);
   h->peer_slab[h->me] = h->d_slab;
 
   // ownership: contiguous Morton ranges per level, cut at sibling groups (afmg_partition)
@@ -1423,15 +1428,15 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
   h->cx.rule_flag = nullptr;
   h->cx.lsf_value = h->o.lsf_boundary_value;
 
-  for (int v = 0; v < 4; ++v) h->cx.cc[v] = h->d_cc[v];
+  for (int v = 0; v < 5; ++v) h->cx.cc[v] = h->d_cc[v];
   h->cx.nranks = h->nranks;
   h->cx.me = h->me;
   h->cx.owner = h->d_owner;
   for (int r = 0; r < AFMG_MAX_RANKS; ++r) {
-    for (int v = 0; v < 3; ++v) h->cx.ccr[r][v] = nullptr;
+    for (int v = 0; v < 5; ++v) h->cx.ccr[r][v] = nullptr;
     h->cx.bsum[r] = nullptr;
   }
-  for (int v = 0; v < 3; ++v) h->cx.ccr[h->me][v] = h->d_cc[v];
+  for (int v = 0; v < 5; ++v) h->cx.ccr[h->me][v] = h->d_cc[v];
   h->cx.bsum[h->me] = h->d_boxsum;
   h->cx.nbr = h->d_nbr;
   h->cx.aux = h->d_aux;
@@ -2158,7 +2163,8 @@ int afmg_comm_connect(afmg_handle* h, const void* blobs) {
   }
   for (int r = 0; r < h->nranks; ++r) {
     for (int v = 0; v < 3; ++v) h->cx.ccr[r][v] = (double*)(h->peer_slab[r] + v * h->slab_var_stride);
-    h->cx.bsum[r] = (double*)(h->peer_slab[r] + 3 * h->slab_var_stride);
+    h->cx.ccr[r][V_FLD] = (h->slab_nvar == 4) ? (double*)(h->peer_slab[r] + 3 * h->slab_var_stride) : nullptr;
+    h->cx.bsum[r] = (double*)(h->peer_slab[r] + h->slab_nvar * h->slab_var_stride);
   }
   h->connected = true;
   return AFMG_OK;

@@ -190,15 +190,15 @@ __global__ void __launch_bounds__(256) k_lsf_fix3(DevCtx cx, FieldCtx fx, const 
   if (with_norm) norm_from_fc3<NC>(fcb, fx.fld + (size_t)slot * L::BOX, threadIdx.x, 256);
 }
 
-// af_gc_box for the field norm (cx.cc[V_PHI] must point at it): neighbour copy, bc_to_gc with the variable's
-// own boundary rule, af_gc_interp on refinement boundaries; then edges and corners.
+// af_gc_box for the field norm (variable V_FLD): neighbour copy, bc_to_gc with the variable's own boundary rule,
+// af_gc_interp on refinement boundaries; then edges and corners.  Neighbours and the parent's neighbour may live
+// on a peer GPU (cx.at).
 template <int NC>
 __global__ void __launch_bounds__(256) k_gc_fld3(DevCtx cx, FieldCtx fx, int slot0, int nbox, int corners) {
   using L = Lay3<NC>;
   constexpr int H = L::H;
   const int slot = slot0 + blockIdx.x;
-  double* base = cx.cc[V_PHI];
-  double* box = base + (size_t)slot * L::BOX;
+  double* box = cx.cc[V_FLD] + (size_t)slot * L::BOX;
   const double third = 1 / 3.0, sixth = 1 / 6.0;
   for (int n = threadIdx.x; n < 6 * L::NC2; n += blockDim.x) {
     const int f = n / L::NC2, rr = n % L::NC2;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) k_gc_fld3(DevCtx cx, FieldCtx fx, int slo
     double v;
     if (nb >= 0) {
       q[d] = hi ? 1 : NC;
-      v = ldcell<NC>(base + (size_t)nb * L::BOX, q[0], q[1], q[2]);
+      v = ldcell<NC>(cx.at<L::BOX>(V_FLD, nb), q[0], q[1], q[2]);
     } else {
       const int row = cx.aux[slot * 6 + f];
       if (row < cx.rb_row0) {  // physical boundary: bc_to_gc
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256) k_gc_fld3(DevCtx cx, FieldCtx fx, int slo
         v = (rc[0] * B + rc[1] * x1) + rc[2] * x2;
       } else {  // af_gc_interp
         const int p = cx.parent[slot], cof = cx.coff[slot];
-        const double* P = base + (size_t)cx.nbr[p * 6 + f] * L::BOX;
+        const double* P = cx.at<L::BOX>(V_FLD, cx.nbr[p * 6 + f]);
         const int a1 = ((cof >> ta) & 1) * H + ((a + 1) >> 1), a2 = a1 + 1 - 2 * (a & 1);
         const int b1 = ((cof >> tb) & 1) * H + ((b + 1) >> 1), b2 = b1 + 1 - 2 * (b & 1);
         int c[3];
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(256) k_gc_fld3(DevCtx cx, FieldCtx fx, int slo
   }
   if (corners) {
     __syncthreads();
-    gc_edges_corners<NC>(cx, slot, V_PHI);
+    gc_edges_corners<NC>(cx, slot, V_FLD);
   }
 }
 

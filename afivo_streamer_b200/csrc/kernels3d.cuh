@@ -16,11 +16,11 @@
 
 namespace afmg {
 
-enum { V_PHI = 0, V_RHS = 1, V_TMP = 2, V_EPS = 3 };
+enum { V_PHI = 0, V_RHS = 1, V_TMP = 2, V_EPS = 3, V_FLD = 4 };
 #define AFMG_MAX_RANKS 8
 
 struct DevCtx {
-  double* cc[4];         // per variable: nslots * BOX doubles
+  double* cc[5];         // per variable: nslots * BOX doubles (V_EPS unused here; V_FLD: field norm, may be null)
   const int* nbr;        // [nslots*6]  >= 0: neighbour slot; -1: own-ghost rule row in aux
   const int* aux;        // [nslots*6]  rule row
   const int* nmat;       // [nslots*27] >= 0 slot, -1 physical boundary, -2 no box (coarser there)
@@ -52,7 +52,7 @@ struct DevCtx {
   // GPU.  nranks == 1: ccr is unused.
   int nranks, me;
   const unsigned char* owner;  // [nslots] rank that owns (computes) the box
-  double* ccr[AFMG_MAX_RANKS][3];  // phi / rhs / tmp base pointers of every rank (own entry == cc)
+  double* ccr[AFMG_MAX_RANKS][5];  // phi / rhs / tmp (/ field norm) base pointers of every rank (own entry == cc)
   double* bsum[AFMG_MAX_RANKS];    // per-box sums (k_box_sums) of every rank
 
   // base of the record of box `slot` for variable `var` in the memory of the rank that owns it

@@ -213,7 +213,7 @@ int afmg_field_solve(afmg_handle* h, int32_t have_guess, double residual_thresho
  *            afmg_upload_fc / afmg_download_fc in exactly that record (first index fastest);
  *   AFMG_FLD the cell-centred norm, AFMG_EPS tree%mg_i_eps (needed only when variable-eps boxes exist; default
  *            1), both moved with afmg_upload / afmg_download in the box layout cc(0:nc+1, ...).
- * Single GPU (a multi-GPU handle returns AFMG_ERR_UNSUPPORTED).
+ * On a multi-GPU handle every rank computes / moves the boxes it owns; the norm's halo travels through peer memory.
  *
  * mg_compute_phi_gradient(tree, mg, i_fc, fac, i_norm) m_af_multigrid.f90:1857-1898: fc = fac/dr * (phi difference)
  * on every box (mg_box_lpl_gradient :1901-1999, with the eps-weighted boundary faces of mg_veps_box boxes),

@@ -83,10 +83,46 @@ def solve(tree, bc, ids, rhs, comm, local, opts, n_v=3):
     all_ids = np.concatenate(tree.lvl_ids).astype(np.int32)
     owner = np.array([mg.owner_of_box(i) for i in all_ids])
     out = {v: mg.get_cc(v, all_ids) for v in (M.I_PHI, M.I_TMP)}
+    if spec is None:
+        # field from potential: gradient, norm and the norm's ghost cells (af_gc_interp reads peers' halos)
+        M.field_from_potential(tree, mg, -1.0)
+        out["fc"] = mg.get_fc(all_ids)
+        out["fld"] = mg.get_cc(M.I_FLD, all_ids)
     s = M.af_tree_sum_cc(tree, mg, M.I_PHI)
     mx = M.af_tree_maxabs_cc(tree, mg, M.I_PHI)
     M.mg_destroy(mg)
     return np.array(hist), out, owner, s, mx
+
+
+def helmholtz_case(rank, local, comm):
+    """photoi_helmh_compute (three modes, shared rhs) on the partitioned handles vs private single-GPU handles."""
+    lambdas = np.array([4147.85, 10950.93, 66755.67]) * 0.2 * 0.02
+    coeffs = np.array([1117314.935, 28692377.5, 2748842283.0]) * (0.2 * 0.02) ** 2
+    tree = T.uniform_tree(3, 8, 8, 4)
+    bc = W.bc_table(tree, M.photoi_helmh_bc)
+    ids, rhs = W.random_rhs_on_leaves(tree)
+    all_ids = np.concatenate(tree.lvl_ids).astype(np.int32)
+    res = []
+    for c in (None, comm):
+        mgs = []
+        for lam in lambdas:
+            mg = M.mg_t(sides_bc=bc, device=local, comm=c, helmholtz_lambda=lam ** 2, prolongation_type=M.MG_PROLONG_LINEAR)
+            M.mg_init(tree, mg)
+            mgs.append(mg)
+        mgs[0].set_cc(M.I_RHS, ids, rhs * 1.0e3)
+        ncyc, r = M.photoi_helmh_compute(tree, mgs, coeffs, 10, 1.0e-2)
+        owner = np.array([mgs[0].owner_of_box(i) for i in all_ids])
+        res.append((ncyc, r, mgs[0].get_cc(M.I_PHOTO, all_ids), owner))
+        for mg in mgs:
+            M.mg_destroy(mg)
+        dist.barrier()
+    (n1, r1, p1, _), (nN, rN, pN, owner) = res
+    mine = owner == rank
+    ndiff = int(np.count_nonzero(p1[mine] != pN[mine]))
+    ok = list(n1) == list(nN) and np.array_equal(r1, rN) and ndiff == 0 and np.abs(pN[mine]).max() > 0
+    print(f"[rank {rank}] helmholtz_modes: FMG cycles {list(nN)} residual_equal={np.array_equal(r1, rN)} "
+          f"cells_differing={ndiff} {'OK' if ok else 'MISMATCH'}", flush=True)
+    return 0 if ok else 1
 
 
 def main():
@@ -110,11 +146,14 @@ def main():
         for v in o1:
             ndiff += int(np.count_nonzero(o1[v][mine] != oN[v][mine]))
         ok = ok and ndiff == 0
+        if "fld" in oN and mine.any():
+            ok = ok and float(np.abs(oN["fld"][mine]).max()) > 0.0  # the field was really computed
         print(f"[rank {rank}] {name}: boxes {tree.n_boxes} own {int(mine.sum())} residuals {hN[0]:.3e}->{hN[-1]:.3e} "
               f"hist_equal={np.array_equal(h1, hN)} sum_equal={s1 == sN} cells_differing={ndiff} "
               f"{'OK' if ok else 'MISMATCH'}", flush=True)
         bad += 0 if ok else 1
         dist.barrier()
+    bad += helmholtz_case(rank, local, comm)
     t = torch.tensor([bad], device="cuda")
     dist.all_reduce(t)
     dist.destroy_process_group()
