@@ -334,9 +334,14 @@ void enq_gsrb(afmg_handle* h, int l, int redblack) {
 }
 
 // reads the (frozen) coarse level, writes this rank's rule rows: no barrier needed afterwards
-void enq_rb_prepare(afmg_handle* h, int l) {
+inline Range own_rb(const afmg_handle* h, int l) {  // this rank's refinement-boundary faces of level l
+  if (l < 2 || l > h->L) return {0, 0};
   const int* c = &h->rb_cut[(size_t)l * (h->nranks + 1)];
-  const int r0 = c[h->me], n = c[h->me + 1] - c[h->me];
+  return {c[h->me], c[h->me + 1] - c[h->me]};
+}
+void enq_rb_prepare(afmg_handle* h, int l) {
+  const Range rb = own_rb(h, l);
+  const int r0 = rb.s0, n = rb.n;
   if (n == 0) return;
   Launch L_(h, "rb_prepare", l);
   DISPATCH_NC(h, NC, { launch_k(h, k_rb_prepare<NC>, n, 128, 0, h->cx, r0, n, V_PHI); });
@@ -357,11 +362,15 @@ void enq_gc(afmg_handle* h, int l, int var, int corners, int mode) {
   enq_barrier(h);
 }
 
-void enq_edges_corners(afmg_handle* h, int l) {
+// rb_lvl > 0: the refinement-boundary interpolation of that (finer) level rides along as extra CTAs
+void enq_edges_corners(afmg_handle* h, int l, int rb_lvl = 0) {
   const Range r = own(h, l);
+  const Range rb = own_rb(h, rb_lvl);
   if (r.n > 0) {
     Launch L_(h, "edges_corners", l);
-    DISPATCH_NC(h, NC, { launch_k(h, k_edges_corners<NC>, r.n, 64, 0, h->cx, r.s0, r.n, V_PHI); });
+    DISPATCH_NC(h, NC, { launch_k(h, k_edges_corners<NC>, r.n + rb.n, 64, 0, h->cx, r.s0, r.n, V_PHI, rb.s0, rb.n); });
+  } else if (rb.n > 0) {
+    enq_rb_prepare(h, rb_lvl);
   }
   enq_barrier(h);
 }
@@ -373,15 +382,18 @@ struct OpCfg {
   static constexpr size_t TILE = (size_t)2 * Lay3<NC>::COL * sizeof(double);
 };
 
-void enq_restrict(afmg_handle* h, int l, int keep_res) {
+void enq_restrict(afmg_handle* h, int l, int keep_res, int rb_lvl = 0) {
   const Range r = own(h, l);
+  const Range rb = own_rb(h, rb_lvl);
   if (r.n > 0) {
     Launch L_(h, "restrict", l);
     DISPATCH_NC(h, NC, {
       constexpr int KS = OpCfg<NC>::KS;
-      launch_k(h, k_resid3<NC, KS, 1, OpCfg<NC>::RES_MINB>, r.n, KS * NC * NC / 2, OpCfg<NC>::TILE, 
-          h->cx, r.s0, r.n, nullptr, keep_res);
+      launch_k(h, k_resid3<NC, KS, 1, OpCfg<NC>::RES_MINB>, r.n + rb.n, KS * NC * NC / 2, OpCfg<NC>::TILE,
+          h->cx, r.s0, r.n, nullptr, keep_res, rb.s0, rb.n);
     });
+  } else if (rb.n > 0) {
+    enq_rb_prepare(h, rb_lvl);
   }
   if (const int ns = nspec(h, l)) {
     Launch L_(h, "restrict_gen", l);
@@ -421,8 +433,8 @@ void enq_correct(afmg_handle* h, int lp, bool store_corr, bool push) {
 // Inside the cycles the edge / corner ghost cells written by that af_gc_lvl are dead: the upward
 // gsrb_boxes that follows only reads face ghost cells and ends with its own edge / corner refresh
 // (m_af_multigrid.f90:676-684), so they are skipped there (corners = false) unless n_cycle_up == 0.
-void enq_correct_gc(afmg_handle* h, int lp, bool store_corr, bool corners = true) {
-  enq_rb_prepare(h, lp + 1);
+void enq_correct_gc(afmg_handle* h, int lp, bool store_corr, bool corners = true, bool rb_done = false) {
+  if (!rb_done) enq_rb_prepare(h, lp + 1);
   enq_correct(h, lp, store_corr, true);
   if (corners) enq_edges_corners(h, lp + 1);
 }
@@ -445,8 +457,8 @@ void enq_residual(afmg_handle* h, int l_lo, int l_hi, bool with_max) {
     Launch L_(h, "residual");
     DISPATCH_NC(h, NC, {
       constexpr int KS = OpCfg<NC>::KS;
-      launch_k(h, k_resid3<NC, KS, 0, OpCfg<NC>::RES_MINB>, n, KS * NC * NC / 2, OpCfg<NC>::TILE, 
-          h->cx, s0, n, with_max ? h->d_scal : nullptr, 0);
+      launch_k(h, k_resid3<NC, KS, 0, OpCfg<NC>::RES_MINB>, n, KS * NC * NC / 2, OpCfg<NC>::TILE,
+          h->cx, s0, n, with_max ? h->d_scal : nullptr, 0, 0, 0);
     });
   };
   if (h->have_stencils) {
@@ -544,13 +556,19 @@ void enq_coarse(afmg_handle* h) {
 }
 
 // gsrb_boxes (m_af_multigrid.f90:648-687)
-void enq_gsrb_boxes(afmg_handle* h, int l, bool up) {
+// rb_after > 0: also interpolate the refinement-boundary faces of level rb_after (= l + 1, on the way up) once
+// level l has its final values; it rides on the last edges / corners launch
+void enq_gsrb_boxes(afmg_handle* h, int l, bool up, int rb_after = 0) {
   const int ncyc = up ? h->o.n_cycle_up : h->o.n_cycle_down;
+  bool rb_done = rb_after == 0;
   for (int n = 1; n <= 2 * ncyc; ++n) {
     enq_gsrb(h, l, n);
     const bool corners = h->o.use_corners || (up && n == 2 * ncyc);
-    if (corners) enq_edges_corners(h, l);
+    const bool last = n == 2 * ncyc;
+    if (corners) enq_edges_corners(h, l, (last && !rb_done) ? rb_after : 0);
+    if (corners && last) rb_done = true;
   }
+  if (!rb_done) enq_rb_prepare(h, rb_after);
 }
 
 // update_coarse (:691-738) with_tmp = true, set_coarse_phi_rhs (:742-776) with_tmp = false
@@ -559,8 +577,7 @@ void enq_update_coarse(afmg_handle* h, int l, bool with_tmp) {
     enq_rb_prepare(h, l);
     enq_gc(h, l, V_PHI, 1, 0);
   }
-  enq_restrict(h, l, with_tmp ? 0 : 1);
-  enq_rb_prepare(h, l - 1);
+  enq_restrict(h, l, with_tmp ? 0 : 1, l - 1);  // + the refinement-boundary interpolation of level l-1
   enq_gc(h, l - 1, V_PHI, 1, with_tmp ? 1 : 2);
 }
 
@@ -578,8 +595,9 @@ void enq_vcycle(afmg_handle* h, bool set_residual, int max_lvl, bool final_state
   }
   enq_coarse(h);
   for (int l = 2; l <= max_lvl; ++l) {
-    enq_correct_gc(h, l - 1, final_state && !set_residual, !dead_corners);
-    enq_gsrb_boxes(h, l, true);
+    // the interpolation for level l was issued with the upward sweeps of level l - 1 (l > 2)
+    enq_correct_gc(h, l - 1, final_state && !set_residual, !dead_corners, l > 2);
+    enq_gsrb_boxes(h, l, true, l < max_lvl ? l + 1 : 0);
   }
   if (set_residual) {
     const bool all = (max_lvl == h->L);

@@ -436,10 +436,19 @@ __device__ __forceinline__ double apply357_smem(const double* S, const double* c
 //   MODE 1: child part of update_coarse / set_coarse_phi_rhs: the residual and phi are averaged over
 //           2x2x2 cells in the reference's summation order (m_af_restrict.f90:120-133) and written into
 //           the parent's tmp / phi; odd-j lanes accumulate, the even-j row arrives by warp shuffle.
+template <int NC>
+__device__ __forceinline__ void rb_prepare_face(const DevCtx& cx, int r, int var);
+
+// CTAs beyond nbox (rb_n of them) interpolate refinement-boundary faces rb_r0.. of ANOTHER level (k_rb_prepare's
+// work, independent of this kernel's): one graph node less per level on the launch-bound small levels.
 template <int NC, int KS, int MODE, int MINB>
 __global__ void __launch_bounds__(KS* NC* NC / 2, MINB)
-    k_resid3(DevCtx cx, int slot0, int nbox, unsigned long long* maxabs_bits, int keep_res) {
+    k_resid3(DevCtx cx, int slot0, int nbox, unsigned long long* maxabs_bits, int keep_res, int rb_r0, int rb_n) {
   pdl_wait();
+  if ((int)blockIdx.x >= nbox) {
+    rb_prepare_face<NC>(cx, rb_r0 + (int)blockIdx.x - nbox, V_PHI);
+    return;
+  }
   using L = Lay3<NC>;
   constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX, KL = NC / KS;
   static_assert(KL % 2 == 0, "z pairs must stay inside one thread");
@@ -955,12 +964,9 @@ __global__ void k_store_corr(DevCtx cx, int slot0, int nbox) {
 // af_gc_lvl group.  One CTA per face, one thread per fine face cell.
 // ---------------------------------------------------------------------------------------------
 template <int NC>
-__global__ void k_rb_prepare(DevCtx cx, int r0, int nr, int var) {
-  pdl_wait();
+__device__ __forceinline__ void rb_prepare_face(const DevCtx& cx, int r, int var) {
   using L = Lay3<NC>;
   constexpr int H = L::H;
-  const int r = r0 + blockIdx.x;
-  if (blockIdx.x >= nr) return;
   const int s = cx.rb_slot[r], f = cx.rb_face[r];
   const int p = cx.parent[s];
   const int pn = cx.nbr[p * 6 + f];  // coarse neighbour (exists by 2:1 balance)
@@ -1004,6 +1010,12 @@ __global__ void k_rb_prepare(DevCtx cx, int r0, int nr, int var) {
     v = (b & 1) ? (v - g2) : (v + g2);
     out[n] = v;
   }
+}
+template <int NC>
+__global__ void k_rb_prepare(DevCtx cx, int r0, int nr, int var) {
+  pdl_wait();
+  if ((int)blockIdx.x >= nr) return;
+  rb_prepare_face<NC>(cx, r0 + blockIdx.x, var);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1114,10 +1126,13 @@ __global__ void k_gc(DevCtx cx, int slot0, int nbox, int var, int corners, int m
 // edges + corners only (after the last half-sweep of an upward gsrb_boxes, or every half-sweep when
 // mg%use_corners, m_af_multigrid.f90:676-684)
 template <int NC>
-__global__ void k_edges_corners(DevCtx cx, int slot0, int nbox, int var) {
+__global__ void k_edges_corners(DevCtx cx, int slot0, int nbox, int var, int rb_r0, int rb_n) {
   pdl_wait();
   const int slot = slot0 + blockIdx.x;
-  if ((int)blockIdx.x >= nbox) return;
+  if ((int)blockIdx.x >= nbox) {  // piggy-backed k_rb_prepare work of the next finer level (see k_resid3)
+    if ((int)blockIdx.x < nbox + rb_n) rb_prepare_face<NC>(cx, rb_r0 + (int)blockIdx.x - nbox, V_PHI);
+    return;
+  }
   gc_edges_corners<NC>(cx, slot, var);
 }
 
