@@ -794,10 +794,6 @@ int coarse_setup(afmg_handle* h) {
       // different level-1 boxes put different condition types on one domain face (the reference allows it:
       // stencil_handle_boundaries works box by box, m_coarse_solver.f90:442-491): the operator is no longer
       // separable, so the general dense coarse solve takes over
-      for (int d = 0; d < 3; ++d)
-        if (h->o.periodic[d])
-          return h->fail(AFMG_ERR_UNSUPPORTED, "coarse grid: mixed boundary condition types on domain face %d of a "
-                                               "periodic domain", f + 1);
       return coarse_setup_dense(h);
     }
     face_type[f] = ty;
@@ -906,9 +902,12 @@ int coarse_setup_dense(afmg_handle* h) {
   const int n = nx[0] * nx[1] * nx[2];
   if (n > 8192)
     return h->fail(AFMG_ERR_UNSUPPORTED, "explicit stencils on a coarse grid of %d cells (dense inverse limited to 8192)", n);
-  for (int d = 0; d < 3; ++d)
-    if (h->o.periodic[d]) return h->fail(AFMG_ERR_UNSUPPORTED, "explicit coarse-grid stencils with periodic boundaries");
-  const int bw = nx[0] * nx[1], ldab = 2 * bw + 1;
+  // periodic dimensions couple the first and the last cell (HYPRE_StructGridSetPeriodic, m_coarse_solver.f90:
+  // 97-104): the band becomes full, so the factorisation is a dense one and is kept to small grids
+  const bool any_periodic = h->o.periodic[0] || h->o.periodic[1] || h->o.periodic[2];
+  if (any_periodic && n > 2048)
+    return h->fail(AFMG_ERR_UNSUPPORTED, "non-separable periodic coarse grid of %d cells (dense factorisation limited to 2048)", n);
+  const int bw = any_periodic ? n - 1 : nx[0] * nx[1], ldab = 2 * bw + 1;
   std::vector<double> ab((size_t)ldab * n, 0.0);  // ab[(bw + r - c) + ldab * c] = A(r, c)
   std::vector<double> b2r((size_t)nbox1 * 6 * nc2, 0.0), lsf_fac((size_t)nbox1 * ncell, 0.0);
   bool any_f = false;
@@ -974,8 +973,11 @@ int coarse_setup_dense(afmg_handle* h) {
             if (st[m + 1] == 0.0) continue;
             const int d = m >> 1, sgn = (m & 1) ? 1 : -1;
             const int qd = gi[d] + sgn;
-            if (qd < 0 || qd >= nx[d]) return h->fail(AFMG_ERR_ARG, "coarse matrix: coupling outside the grid");
-            const int c = r + sgn * gstride[d];
+            int c = r + sgn * gstride[d];
+            if (qd < 0 || qd >= nx[d]) {
+              if (!h->o.periodic[d]) return h->fail(AFMG_ERR_ARG, "coarse matrix: coupling outside the grid");
+              c = r - sgn * (nx[d] - 1) * gstride[d];  // wrap around
+            }
             ab[(size_t)(bw + r - c) + (size_t)ldab * c] += st[m + 1];
           }
         }

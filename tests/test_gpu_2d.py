@@ -57,6 +57,9 @@ CASES = {
                                                       r_max=[1.0, 2.0], coord_t=CYL), bc_cyl, dict(helmholtz_lambda=30.0)),
     "cyl_channel_nc8": (lambda: T.build_tree(2, 8, [8, 8], 6, lambda l, ix, c: (c[:, 0] < 1.5 * 0.5 ** (l - 1)) & (np.abs(c[:, 1] - 0.5) < 0.3),
                                              coord_t=CYL), bc_cyl, {}),
+    "xy_periodic_x_nc8": (lambda: T.uniform_tree(2, 8, 8, 4, periodic=[True, False]), bc_mixed, {}),
+    "xy_periodic_x_refined_multibox_nc8": (lambda: T.build_tree(2, 8, [16, 8], 4, lambda l, ix, c: c[:, 1] < 0.55,
+                                                               periodic=[True, False]), bc_mixed, {}),
     "xy_eps_corner_nc8": (lambda: T.corner_refined_tree(2, 8, 8, 4), bc_mixed, dict(eps=eps2)),
     "cyl_eps_uniform_nc8": (lambda: T.build_tree(2, 8, [8, 8], 3, None, coord_t=CYL), bc_cyl, dict(eps=eps2)),
     "xy_lsf_uniform_nc8": (lambda: T.uniform_tree(2, 8, 8, 4), bc_mixed, dict(lsf=lsf_circle, lsf_boundary_value=1.5)),

@@ -87,6 +87,8 @@ CASES = {
     # mg_box_lpld_lsf_stencil (m_af_multigrid.f90:1535-1623): permittivity and electrode in the same boxes
     "eps_lsf_corner_nc8": (lambda: T.corner_refined_tree(3, 8, 8, 4),
                            dict(eps=eps_smooth, lsf=lsf_sphere, lsf_boundary_value=0.9)),
+    # periodic domain with a non-separable coarse operator: the dense coarse solve with wrap-around couplings
+    "eps_smooth_periodic_xy_nc8": (lambda: T.uniform_tree(3, 8, 8, 3, periodic=[True, True, False]), dict(eps=eps_smooth)),
     "ceps_lsf_uniform_nc8": (lambda: T.uniform_tree(3, 8, 8, 3), dict(eps=eps_const2, lsf=lsf_sphere, lsf_boundary_value=-1.2)),
 }
 
