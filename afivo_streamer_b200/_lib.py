@@ -67,6 +67,7 @@ SYMBOLS = {
     "afmg_set_bc": (C.c_int, [_H, _I, _IP, _IP, _IP, _DP]),
     "afmg_set_helmholtz_lambda": (C.c_int, [_H, C.c_double]),
     "afmg_set_lsf_boundary_value": (C.c_int, [_H, C.c_double]),
+    "afmg_set_lsf_boundary_values": (C.c_int, [_H, _I, _IP, _DP]),
     "afmg_set_stencils": (C.c_int, [_H, _I, C.c_void_p, _DP, C.c_int64]),
     "afmg_update_operator_stencil": (C.c_int, [_H]),
     "afmg_upload": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),

@@ -104,6 +104,10 @@ struct afmg_handle {
   int* d_spec = nullptr;
   // general coarse solve (explicit stencils on level 1): dense inverse of the BC-folded matrix
   bool cs_dense = false;
+  // per-cell level-set boundary values (afmg_set_lsf_boundary_values)
+  std::vector<int> bv_ids;
+  double* d_bv = nullptr;
+  long long* d_bvoff = nullptr;
   double *d_Ainv = nullptr, *d_lsf_fac = nullptr;
 
   // ---- multi-GPU (one process per GPU; peers' arrays mapped through CUDA IPC)
@@ -1234,6 +1238,8 @@ int afmg_destroy(afmg_handle* h) {
   cudaFree(h->d_spec);
   cudaFree(h->d_Ainv);
   cudaFree(h->d_lsf_fac);
+  cudaFree(h->d_bv);
+  cudaFree(h->d_bvoff);
   int* ip[] = {h->d_nbr, h->d_aux, h->d_nmat, h->d_parent, h->d_child0, h->d_coff, h->d_lvl, h->d_rb_slot,
                h->d_rb_face, h->d_stage_slots, h->d_cs_bix};
   for (auto p : ip) cudaFree(p);
@@ -1447,6 +1453,9 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
   h->cx.stv = nullptr;
   h->cx.rule_flag = nullptr;
   h->cx.lsf_value = h->o.lsf_boundary_value;
+  h->cx.bvoff = nullptr;  // the boundary-value list belongs to the previous tree
+  h->cx.bv = nullptr;
+  h->bv_ids.clear();
 
   for (int v = 0; v < 5; ++v) h->cx.cc[v] = h->d_cc[v];
   h->cx.nranks = h->nranks;
@@ -1552,6 +1561,64 @@ int afmg_set_lsf_boundary_value(afmg_handle* h, double value) {
   if (h->s2) h->s2->cx.lsf_value = value;
   drop_graphs(h);
   h->resid_fresh = false;
+  return AFMG_OK;
+}
+
+int afmg_set_lsf_boundary_values(afmg_handle* h, int32_t n, const int32_t* box_id, const double* values) {
+  if (!h) return AFMG_ERR_ARG;
+  if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
+  if (n < 0 || (n > 0 && (!box_id || !values))) return h->fail(AFMG_ERR_ARG, "afmg_set_lsf_boundary_values: null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  const int nd = h->o.ndim, nc = h->o.n_cell;
+  const int ncell = (nd == 3) ? nc * nc * nc : nc * nc;
+  for (int q = 0; q < n; ++q)
+    if (box_id[q] < 1 || box_id[q] > h->highest_id || h->id2slot[box_id[q]] < 0)
+      return h->fail(AFMG_ERR_ARG, "afmg_set_lsf_boundary_values: unknown box %d", box_id[q]);
+  // device order of the values: the colour-split interior [colour][NI] in 3D (like stencil%f), cell order in 2D
+  std::vector<double> dev((size_t)std::max(n, 1) * ncell, 0.0);
+  for (int q = 0; q < n; ++q) {
+    const double* v = values + (size_t)q * ncell;
+    double* o = dev.data() + (size_t)q * ncell;
+    if (nd == 2) {
+      std::copy(v, v + ncell, o);
+    } else {
+      const int H = nc / 2, NI = nc * nc * H;
+      for (int k = 1; k <= nc; ++k)
+        for (int j = 1; j <= nc; ++j)
+          for (int i = 1; i <= nc; ++i)
+            o[((i + j + k) & 1) * NI + ((k - 1) * nc + (j - 1)) * H + ((i - 1) >> 1)] = v[(i - 1) + nc * ((j - 1) + nc * (k - 1))];
+    }
+  }
+  const bool same_list = (int)h->bv_ids.size() == n && std::equal(h->bv_ids.begin(), h->bv_ids.end(), box_id) && n > 0 &&
+                         h->d_bv != nullptr;
+  h->resid_fresh = false;
+  if (same_list) {  // new values for the same boxes (the voltage changed): the pointers in the cached graphs stay valid
+    CK(cudaMemcpy(h->d_bv, dev.data(), dev.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return AFMG_OK;
+  }
+  drop_graphs(h);
+  h->bv_ids.assign(box_id, box_id + n);
+  int rc;
+  if (n == 0) {
+    h->cx.bvoff = nullptr;
+    h->cx.bv = nullptr;
+    if (h->s2) {
+      h->s2->cx.bvoff = nullptr;
+      h->s2->cx.bv = nullptr;
+    }
+    return AFMG_OK;
+  }
+  std::vector<long long> off(std::max(h->nslots, 1), -1);
+  for (int q = 0; q < n; ++q) off[h->id2slot[box_id[q]]] = (long long)q * ncell;
+  if ((rc = dev_upload(h, &h->d_bv, dev))) return rc;
+  if ((rc = dev_upload(h, &h->d_bvoff, off))) return rc;
+  h->cx.bvoff = h->d_bvoff;
+  h->cx.bv = h->d_bv;
+  if (h->s2) {
+    h->s2->cx.bvoff = h->d_bvoff;
+    h->s2->cx.bv = h->d_bv;
+  }
   return AFMG_OK;
 }
 

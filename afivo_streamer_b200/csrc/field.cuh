@@ -168,13 +168,14 @@ __global__ void __launch_bounds__(256) k_lsf_fix3(DevCtx cx, FieldCtx fx, const 
   const int lv = cx.lvl[slot];
   const double* phi = cx.cc[V_PHI] + (size_t)slot * L::BOX;
   double* fcb = fx.fc + (size_t)slot * F::LEN;
-  const double bc = fx.lsf_value;
+  const double* bvp = cx.bv_of(slot);
   for (int phase = 0; phase < 2; ++phase) {
     for (int n = threadIdx.x; n < 3 * (e1 - e0); n += 256) {
       const int e = e0 + n / 3, d = n % 3;
       if (!(elsf[e] >= 0)) continue;
       int q[3] = {ecell[3 * e], ecell[3 * e + 1], ecell[3 * e + 2]};
       const double p = phi[L::interior(q[0], q[1], q[2])];
+      const double bc = bvp ? bvp[((q[0] + q[1] + q[2]) & 1) * L::NI + L::iidx((q[0] - 1) >> 1, q[1], q[2])] : fx.lsf_value;
       const double idr = fx.inv_dr[lv][d];
       if (phase == 0) {
         const double dd = edd[6 * e + 2 * d + 1];
@@ -354,13 +355,14 @@ __global__ void k2_lsf_fix(Ctx cx, afmg::FieldCtx fx, const int* slots, const in
   const int lv = cx.lvl[slot];
   const double* phi = cx.cc[V_PHI] + (size_t)slot * B::BOX;
   double* fcb = fx.fc + (size_t)slot * F::LEN;
-  const double bc = fx.lsf_value;
+  const double* bvp = (cx.bvoff && cx.bvoff[slot] >= 0) ? cx.bv + cx.bvoff[slot] : nullptr;
   for (int phase = 0; phase < 2; ++phase) {
     for (int n = threadIdx.x; n < 2 * (e1 - e0); n += blockDim.x) {
       const int e = e0 + n / 2, d = n % 2;
       if (!(elsf[e] >= 0)) continue;
       int q[2] = {ecell[2 * e], ecell[2 * e + 1]};
       const double p = phi[B::at(q[0], q[1])];
+      const double bc = bvp ? bvp[(q[0] - 1) + NC * (q[1] - 1)] : fx.lsf_value;
       const double idr = fx.inv_dr[lv][d];
       if (phase == 0) {
         const double dd = edd[4 * e + 2 * d + 1];

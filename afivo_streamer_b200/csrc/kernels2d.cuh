@@ -45,6 +45,8 @@ struct Ctx {
   const long long* poff;
   const double* stv;
   double lsf_value;
+  const long long* bvoff;    // [nslots] per-cell level-set boundary values (afmg_set_lsf_boundary_values), or null
+  const double* bv;          // nc^2 per listed box, cell order (i fastest)
   double two_pi;         // 2 * acos(-1) as the host computes it (af_tree_sum_cc in cylindrical coordinates)
 };
 
@@ -86,7 +88,9 @@ __device__ __forceinline__ void coefs2(const Ctx& cx, int slot, int i, int j, do
 template <int NC>
 __device__ __forceinline__ double bc_corr2(const Ctx& cx, int slot, int i, int j, bool& has) {
   has = cx.opk && cx.foff[slot] >= 0;
-  return has ? cx.stv[cx.foff[slot] + (i - 1) + NC * (j - 1)] * cx.lsf_value : 0.0;
+  if (!has) return 0.0;
+  const double V = (cx.bvoff && cx.bvoff[slot] >= 0) ? cx.bv[cx.bvoff[slot] + (i - 1) + NC * (j - 1)] : cx.lsf_value;
+  return cx.stv[cx.foff[slot] + (i - 1) + NC * (j - 1)] * V;
 }
 
 // stencil_apply_357, 2D (m_af_stencil.f90:367-460, :490-493)
@@ -510,7 +514,10 @@ __global__ void k2_cs_gather(Ctx cx, Coarse2 cs, int nbox1) {
     const int row = cx.aux[bx * 4 + f];
     t = t + cs.b2r[((size_t)bx * 4 + f) * NC + fi] * cx.rule_B[(size_t)row * NC + fi];
   }
-  if (cs.lsf_fac) t = t + cs.lsf_fac[(size_t)bx * NC * NC + r] * cx.lsf_value;
+  if (cs.lsf_fac) {
+    const double V = (cx.bvoff && cx.bvoff[bx] >= 0) ? cx.bv[cx.bvoff[bx] + r] : cx.lsf_value;
+    t = t + cs.lsf_fac[(size_t)bx * NC * NC + r] * V;
+  }
   const int gi = cs.bix[bx * 2] * NC + i - 1, gj = cs.bix[bx * 2 + 1] * NC + j - 1;
   cs.v0[gi + cs.nx[0] * gj] = t;
 }

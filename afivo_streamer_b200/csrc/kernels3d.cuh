@@ -46,6 +46,10 @@ struct DevCtx {
   const long long* poff;     // [nslots] offset in stv
   const double* stv;         // coefficient pool
   double lsf_value;          // mg%lsf_boundary_value
+  // mg%lsf_boundary_function as data (afmg_set_lsf_boundary_values): per-cell boundary values [colour][NI] of the
+  // boxes listed there, -1 / null: the scalar lsf_value
+  const long long* bvoff;    // [nslots] offset in bv, or null
+  const double* bv;
   const unsigned char* rule_flag;  // [nrules] 1: refinement-boundary face of a variable-eps box (mg_sides_rb_extrap)
   // ---- multi-GPU (one process per GPU): every rank allocates the same slot-indexed arrays and
   // maps its peers' arrays through CUDA IPC, so a box is addressed as (owner rank, slot) on every
@@ -62,6 +66,10 @@ struct DevCtx {
     return ccr[owner[slot]][var] + (size_t)slot * BOX;
   }
   __device__ __forceinline__ bool remote(int slot) const { return nranks > 1 && owner[slot] != me; }
+  // per-cell level-set boundary values of a box (mg_lsf_boundary_value, m_coarse_solver.f90:493-510), or null
+  __device__ __forceinline__ const double* bv_of(int slot) const {
+    return (bvoff && bvoff[slot] >= 0) ? bv + bvoff[slot] : nullptr;
+  }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -590,7 +598,8 @@ __device__ __forceinline__ double op_coef(const DevCtx& cx, int kind, const doub
 // "- bc_correction" of stencil_apply_357 (m_af_stencil.f90:462-493)
 template <int NC>
 __device__ __forceinline__ double apply_gen(const DevCtx& cx, int kind, const double* sv, const double* fv,
-                                            const double* cf, const double* box, int i, int j, int k) {
+                                            const double* cf, const double* box, int i, int j, int k,
+                                            const double* bvp = nullptr) {
   using L = Lay3<NC>;
   const int col = (i + j + k) & 1, idx = L::iidx((i - 1) >> 1, j, k);
   double acc = op_coef<NC>(cx, kind, sv, cf, 0, col, idx) * box[col * L::COL + idx];
@@ -600,7 +609,7 @@ __device__ __forceinline__ double apply_gen(const DevCtx& cx, int kind, const do
   acc = acc + op_coef<NC>(cx, kind, sv, cf, 4, col, idx) * ldcell<NC>(box, i, j + 1, k);
   acc = acc + op_coef<NC>(cx, kind, sv, cf, 5, col, idx) * ldcell<NC>(box, i, j, k - 1);
   acc = acc + op_coef<NC>(cx, kind, sv, cf, 6, col, idx) * ldcell<NC>(box, i, j, k + 1);
-  if (fv) acc = acc - fv[col * L::NI + idx] * cx.lsf_value;
+  if (fv) acc = acc - fv[col * L::NI + idx] * (bvp ? bvp[col * L::NI + idx] : cx.lsf_value);
   return acc;
 }
 
@@ -619,6 +628,7 @@ __global__ void __launch_bounds__(256) k_gsrb_gen(DevCtx cx, const int* list, in
   const int kind = cx.opk[slot];
   const double* sv = cx.stv + cx.opoff[slot];
   const double* fv = cx.foff[slot] >= 0 ? cx.stv + cx.foff[slot] : nullptr;
+  const double* bvp = cx.bv_of(slot);
   const double* cf = cx.coef + 8 * cx.lvl[slot];
   double* gbox = cx.cc[V_PHI] + (size_t)slot * BOX;
   double* grhs = cx.cc[V_RHS] + (size_t)slot * BOX;
@@ -628,7 +638,7 @@ __global__ void __launch_bounds__(256) k_gsrb_gen(DevCtx cx, const int* list, in
     double r = grhs[col * COL + idx];
     double bc = 0.0;
     if (fv) {
-      bc = fv[col * NI + idx] * cx.lsf_value;
+      bc = fv[col * NI + idx] * (bvp ? bvp[col * NI + idx] : cx.lsf_value);
       r = r + bc;
     }
     if (col == C) {
@@ -674,7 +684,7 @@ __global__ void __launch_bounds__(256) k_resid_gen(DevCtx cx, const int* list, i
     const int o = col * COL + idx;
     int i, j, k;
     L::uncell(o, i, j, k);
-    const double res = rhs[o] - apply_gen<NC>(cx, kind, sv, fv, cf, phi, i, j, k);
+    const double res = rhs[o] - apply_gen<NC>(cx, kind, sv, fv, cf, phi, i, j, k, cx.bv_of(slot));
     if (MODE == 0 || keep_res) tmp[o] = res;
     if (MODE == 1) sres[n] = res;
     mx = fmax(mx, fabs(res));
@@ -930,7 +940,7 @@ __global__ void __launch_bounds__(256) k_gc2(DevCtx cx, int slot0, int nbox, int
       const int m = idx % H, j = (idx / H) % NC + 1, k = idx / (H * NC) + 1;
       const int i = 2 * m + 2 - ((c + j + k) & 1);
       const int q = c * COL + idx;
-      const double lp = okind ? apply_gen<NC>(cx, okind, osv, ofv, cf, smem, i, j, k)
+      const double lp = okind ? apply_gen<NC>(cx, okind, osv, ofv, cf, smem, i, j, k, cx.bv_of(slot))
                               : apply357_smem<NC>(smem, cf, c1, i, j, k);
       rhs[q] = lp + tmp[q];
       if (mode == 1) tmp[q] = smem[q];
@@ -1323,7 +1333,10 @@ __global__ void k_cs_gather(DevCtx cx, CoarseCtx cs, int nbox1) {
     t = t + cs.b2r[((size_t)bx * 6 + f) * L::NC2 + fi] * cx.rule_B[(size_t)row * L::NC2 + fi];
   }
   // level-set boundary inside the coarse grid (m_coarse_solver.f90:320-324)
-  if (cs.lsf_fac) t = t + cs.lsf_fac[(size_t)bx * ncell + r] * cx.lsf_value;
+  if (cs.lsf_fac) {
+    const double* bvp = cx.bv_of(bx);
+    t = t + cs.lsf_fac[(size_t)bx * ncell + r] * (bvp ? bvp[((i + j + k) & 1) * L::NI + L::iidx((i - 1) >> 1, j, k)] : cx.lsf_value);
+  }
   const int gi = cs.bix[bx * 3] * NC + i - 1, gj = cs.bix[bx * 3 + 1] * NC + j - 1, gk = cs.bix[bx * 3 + 2] * NC + k - 1;
   cs.v0[gi + cs.nx[0] * (gj + cs.nx[1] * gk)] = t;
 }
@@ -1407,7 +1420,10 @@ __global__ void __launch_bounds__(1024) k_cs_fused(DevCtx cx, CoarseCtx cs, int 
       const int row = cx.aux[bx * 6 + f];
       t = t + cs.b2r[((size_t)bx * 6 + f) * L::NC2 + fi] * cx.rule_B[(size_t)row * L::NC2 + fi];
     }
-    if (cs.lsf_fac) t = t + cs.lsf_fac[(size_t)bx * ncell + r] * cx.lsf_value;
+    if (cs.lsf_fac) {
+      const double* bvp = cx.bv_of(bx);
+      t = t + cs.lsf_fac[(size_t)bx * ncell + r] * (bvp ? bvp[((i + j + k) & 1) * L::NI + L::iidx((i - 1) >> 1, j, k)] : cx.lsf_value);
+    }
     const int gi = cs.bix[bx * 3] * NC + i - 1, gj = cs.bix[bx * 3 + 1] * NC + j - 1, gk = cs.bix[bx * 3 + 2] * NC + k - 1;
     a[gi + cs.nx[0] * (gj + cs.nx[1] * gk)] = t;
   }

@@ -156,6 +156,16 @@ class mg_t:
         if self.initialized:
             self._check(_lib.lib().afmg_set_lsf_boundary_value(self._h, float(value)))
 
+    def set_lsf_boundary_values(self, ids, values):
+        """mg%lsf_boundary_function evaluated at the cell centres of the listed boxes (nc^ndim values per box);
+        an empty list returns to the scalar mg%lsf_boundary_value."""
+        self._need_init()
+        ids = np.ascontiguousarray(ids, np.int32)
+        ncell = self._tree.nc ** self._tree.ndim
+        vals = np.ascontiguousarray(values, np.float64).reshape(len(ids), ncell)
+        self._check(_lib.lib().afmg_set_lsf_boundary_values(
+            self._h, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)), vals.ctypes.data_as(C.POINTER(C.c_double))))
+
     def clear(self, var):
         self._need_init()
         self._check(_lib.lib().afmg_clear(self._h, var))

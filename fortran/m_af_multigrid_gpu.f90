@@ -53,6 +53,10 @@ module m_af_multigrid_gpu
      integer(c_int) function afmg_set_lsf_boundary_value(h, v) bind(c, name="afmg_set_lsf_boundary_value")
        import; type(c_ptr), value :: h; real(c_double), value :: v
      end function
+     integer(c_int) function afmg_set_lsf_boundary_values(h, n, ids, values) bind(c, name="afmg_set_lsf_boundary_values")
+       import; type(c_ptr), value :: h; integer(c_int32_t), value :: n
+       integer(c_int32_t), intent(in) :: ids(*); real(c_double), intent(in) :: values(*)
+     end function
      integer(c_int) function afmg_upload(h, var, n, ids, packed) bind(c, name="afmg_upload")
        import; type(c_ptr), value :: h; integer(c_int32_t), value :: var, n
        integer(c_int32_t), intent(in) :: ids(*); real(c_double), intent(in) :: packed(*)
@@ -304,6 +308,40 @@ contains
     call check(afmg_set_stencils(solvers(slot)%h, n, desc, blob, off), "afmg_set_stencils")
   end subroutine sync_stencils
 
+  !> mg%lsf_boundary_function (several electrodes at their own potentials, src/m_field.f90:294-374): evaluate
+  !> mg_lsf_boundary_value (m_coarse_solver.f90:493-510) for every box that carries a level-set boundary and ship
+  !> the values; call before each solve, like field_compute sets mg%lsf_boundary_value (src/m_field.f90:481-487)
+  subroutine sync_lsf_boundary_values(tree, mg, slot)
+    use m_coarse_solver, only: mg_lsf_boundary_value
+    type(af_t), intent(in) :: tree
+    type(mg_t), intent(in) :: mg
+    integer, intent(in)    :: slot
+    integer, allocatable   :: ids(:)
+    real(c_double), allocatable :: vals(:, :)
+    integer :: lvl, i, id, n, nc
+    if (.not. associated(mg%lsf_boundary_function)) return
+    nc = tree%n_cell
+    n = 0
+    do lvl = 1, tree%highest_lvl
+       do i = 1, size(tree%lvls(lvl)%ids)
+          if (iand(tree%boxes(tree%lvls(lvl)%ids(i))%tag, mg_lsf_box) > 0) n = n + 1
+       end do
+    end do
+    allocate(ids(n), vals(nc**NDIM, n))
+    n = 0
+    do lvl = 1, tree%highest_lvl
+       do i = 1, size(tree%lvls(lvl)%ids)
+          id = tree%lvls(lvl)%ids(i)
+          if (iand(tree%boxes(id)%tag, mg_lsf_box) > 0) then
+             n = n + 1
+             ids(n) = id
+             vals(:, n) = reshape(mg_lsf_boundary_value(tree%boxes(id), mg), [nc**NDIM])
+          end if
+       end do
+    end do
+    call check(afmg_set_lsf_boundary_values(solvers(slot)%h, n, ids, vals), "afmg_set_lsf_boundary_values")
+  end subroutine sync_lsf_boundary_values
+
   !> Pack box%cc(:, :, :, iv) of a list of boxes and upload / download
   subroutine transfer(tree, slot, iv, var, ids, up)
     type(af_t), intent(inout) :: tree
@@ -358,6 +396,7 @@ contains
     integer, intent(in)       :: slot
     integer, allocatable      :: ids(:), leaves(:)
     call sync_tree(tree, mg, slot)
+    call sync_lsf_boundary_values(tree, mg, slot)
     call all_ids(tree, leaves, .true.); call all_ids(tree, ids, .false.)
     call transfer(tree, slot, mg%i_rhs, afmg_rhs, leaves, .true.)      ! callers set rhs on leaves only
     if (have_guess) call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .true.)
@@ -379,6 +418,7 @@ contains
     max_lvl = 0; if (present(highest_lvl)) max_lvl = highest_lvl
     alone = 1; if (present(standalone)) alone = merge(1, 0, standalone)
     call sync_tree(tree, mg, slot)
+    call sync_lsf_boundary_values(tree, mg, slot)
     call all_ids(tree, leaves, .true.); call all_ids(tree, ids, .false.)
     call transfer(tree, slot, mg%i_rhs, afmg_rhs, leaves, .true.)
     call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .true.)

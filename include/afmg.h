@@ -129,6 +129,14 @@ int afmg_set_bc(afmg_handle* h, int32_t n_faces, const int32_t* box_id, const in
  * members that enter the stencils */
 int afmg_set_helmholtz_lambda(afmg_handle* h, double lambda);
 int afmg_set_lsf_boundary_value(afmg_handle* h, double value);
+/* mg%lsf_boundary_function as data (m_af_types.f90:628; several electrodes at different potentials, e.g.
+ * rod_rod_get_potential src/m_field.f90:802-825): values holds, for each listed box, mg_lsf_boundary_value(box, mg)
+ * (m_coarse_solver.f90:493-510) = the function at the nc^ndim cell centres (first index fastest).  They replace the
+ * scalar mg%lsf_boundary_value in bc_correction = f * value (m_af_multigrid.f90:1171-1174), in the coarse-grid
+ * right-hand side (m_coarse_solver.f90:320-326) and in mg_box_lpllsf_gradient; boxes not listed keep the scalar.
+ * Call it with the same box list before every solve whose electrode potentials changed (values only are updated);
+ * n = 0 returns to the scalar everywhere.  afmg_set_tree drops the list. */
+int afmg_set_lsf_boundary_values(afmg_handle* h, int32_t n, const int32_t* box_id, const double* values);
 /* Rebuild the implicit constant stencils and the coarse-grid factorisation after lambda changed
  * (mg_update_operator_stencil, m_af_multigrid.f90:1188-1214); explicit stencils are re-shipped with
  * afmg_set_stencils by the shim. */

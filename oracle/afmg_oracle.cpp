@@ -78,6 +78,9 @@ struct Box {
   // face-centred field box%fc(nc+1, nc+1[, nc+1], NDIM) of one variable (m_af_core.f90:552), first index
   // fastest; allocated by the first gradient call
   std::vector<double> fc;
+  // mg_lsf_boundary_value(box, mg) with mg%lsf_boundary_function evaluated by the caller (m_coarse_solver.f90:
+  // 493-510): per interior cell; empty = the constant mg%lsf_boundary_value
+  std::vector<double> lsf_bv;
   std::vector<double> lsf_cc;  // cc(IJK, mg%i_lsf) on the interior (sign test of mg_box_lpllsf_gradient); empty: >= 0
   // boundary condition of I_FLD (cc_methods(iv)%bc): default af_bc_neumann_zero (src/m_field.f90:392-393)
   int fld_bc_type[6] = {0};
@@ -816,6 +819,11 @@ void mg_box_lpl_gradient(Tree& t, Box& box, double fac) {
   }
 }
 
+// mg_lsf_boundary_value (afivo/src/m_coarse_solver.f90:493-510) at interior cell L (IJK order)
+inline double lsf_boundary_value_at(const Tree& t, const Box& box, int L) {
+  return box.lsf_bv.empty() ? t.lsf_boundary_value : box.lsf_bv[L];
+}
+
 // mg_box_lpllsf_gradient (afivo/src/m_af_multigrid.f90:2055-2137).  The sparse distance stencil lists, in
 // IJK order, the cells with any(dd < 1) (store_lsf_distance_matrix :1075-1080); the boundary value is the
 // constant mg%lsf_boundary_value (mg_lsf_boundary_value, m_coarse_solver.f90:493-510).
@@ -828,11 +836,11 @@ void mg_box_lpllsf_gradient(Tree& t, Box& box, double fac) {
   const double* cc = box.cc[I_PHI].data();
   double inv_dr[3] = {0, 0, 0};
   for (int d = 0; d < ND; ++d) inv_dr[d] = fac / box.dr[d];
-  const double bc = t.lsf_boundary_value;
   for (int k = g.klo(); k <= g.khi(); ++k)
     for (int j = 1; j <= nc; ++j)
       for (int i = 1; i <= nc; ++i) {
         const int L = g.lin(i, j, k);
+        const double bc = lsf_boundary_value_at(t, box, L);
         const double* dd = &box.lsf_dd[(size_t)2 * ND * L];
         bool any = false;
         for (int n = 0; n < 2 * ND; ++n) any = any || dd[n] < 1.0;
@@ -1152,7 +1160,7 @@ void mg_set_operators_lvl(Tree& t, int lvl, bool force) {
     }
     if (!box.op.f.empty()) {  // :1171-1174
       box.op.bc_correction.resize(box.op.f.size());
-      for (size_t n = 0; n < box.op.f.size(); ++n) box.op.bc_correction[n] = box.op.f[n] * t.lsf_boundary_value;
+      for (size_t n = 0; n < box.op.f.size(); ++n) box.op.bc_correction[n] = box.op.f[n] * lsf_boundary_value_at(t, box, (int)n);
     }
     if (lvl > 1 && (force || !box.has_prolong)) {
       const Box& box_p = t.boxes[box.parent];
@@ -1372,7 +1380,8 @@ void solve_coarse_grid(Tree& t) {
     for (auto& b2 : t.boxes)
       if (!b2.lsf_dd.empty()) { any_lsf = true; break; }
     if (any_lsf)
-      for (int m = 0; m < g.ncell(); ++m) tmp[m] = tmp[m] + t.cs_lsf_fac[(size_t)g.ncell() * ib + m] * t.lsf_boundary_value;
+      for (int m = 0; m < g.ncell(); ++m)
+        tmp[m] = tmp[m] + t.cs_lsf_fac[(size_t)g.ncell() * ib + m] * lsf_boundary_value_at(t, box, m);
     for (int k = g.klo(); k <= g.khi(); ++k)
       for (int j = 1; j <= nc; ++j)
         for (int i = 1; i <= nc; ++i) {
@@ -1808,6 +1817,13 @@ void orc_set_fc(void* h, int n, const int* ids, const double* data) {
   size_t per = (size_t)t->ndim;
   for (int d = 0; d < t->ndim; ++d) per *= (size_t)(t->nc + 1);
   for (int q = 0; q < n; ++q) t->boxes[ids[q]].fc.assign(data + q * per, data + (q + 1) * per);
+}
+// mg%lsf_boundary_function evaluated at the cell centres of n boxes (nc^ND each); n = 0 clears
+void orc_set_lsf_boundary_values(void* h, int n, const int* ids, const double* v) {
+  Tree* t = (Tree*)h;
+  const size_t per = (t->ndim == 3) ? (size_t)t->nc * t->nc * t->nc : (size_t)t->nc * t->nc;
+  for (auto& b : t->boxes) b.lsf_bv.clear();
+  for (int q = 0; q < n; ++q) t->boxes[ids[q]].lsf_bv.assign(v + q * per, v + (q + 1) * per);
 }
 // cc(IJK, mg%i_lsf) on the interior (nc^ND) of n boxes
 void orc_set_lsf_cc(void* h, int n, const int* ids, const double* v) {

@@ -182,6 +182,13 @@ class Oracle:
         data = np.ascontiguousarray(data, np.float64).reshape(len(ids), self.fc_len())
         self.L.orc_set_fc(self.h, len(ids), _ip(ids), _dp(data))
 
+    def set_lsf_boundary_values(self, ids, vals):
+        """mg%lsf_boundary_function evaluated at the cell centres of the listed boxes; call mg_init() again
+        afterwards (bc_correction = f * value is rebuilt there, m_af_multigrid.f90:1171-1174)."""
+        ids = np.ascontiguousarray(ids, np.int32)
+        vals = np.ascontiguousarray(vals, np.float64).reshape(len(ids), self.tree.nc ** self.tree.ndim)
+        self.L.orc_set_lsf_boundary_values(self.h, len(ids), _ip(ids), _dp(vals))
+
     def set_lsf_cc(self, ids, vals):
         ids = np.ascontiguousarray(ids, np.int32)
         vals = np.ascontiguousarray(vals, np.float64).reshape(len(ids), self.tree.nc ** self.tree.ndim)

@@ -160,3 +160,78 @@ def test_lsf_boundary_value_can_change():
     M.mg_fas_fmg(tree, mg, True, True)
     assert_same_state(tree, orc, mg, exact=False, rtol=1e-10, what=("phi",))
     M.mg_destroy(mg)
+
+
+def two_spheres(r):
+    a = np.linalg.norm(r - np.array([0.3, 0.35, 0.4]), axis=-1) - 0.14
+    b = np.linalg.norm(r - np.array([0.7, 0.65, 0.6]), axis=-1) - 0.12
+    return np.minimum(a, b)
+
+
+def two_sphere_potential(r, v1=1.7, v2=-0.6):
+    """mg%lsf_boundary_function of a two-electrode set-up (rod_rod_get_potential, src/m_field.f90:802-825): the
+    potential of whichever electrode is closer."""
+    a = np.linalg.norm(r - np.array([0.3, 0.35, 0.4]), axis=-1) - 0.14
+    b = np.linalg.norm(r - np.array([0.7, 0.65, 0.6]), axis=-1) - 0.12
+    return np.where(a < b, v1, v2)
+
+
+def test_lsf_boundary_function_two_electrodes():
+    """Per-cell boundary values (afmg_set_lsf_boundary_values) in bc_correction, in the coarse-grid right-hand
+    side and in the level-set gradient; then new potentials for the same boxes without re-shipping anything else."""
+    tree = T.uniform_tree(3, 8, 8, 3)
+    orc, mg, _ = make_pair(tree, lsf=two_spheres, lsf_boundary_value=9.9)  # the scalar must not be used
+    ids = all_ids(tree)
+    lids, dd = lsf_distances(tree, two_spheres)
+    inner = (slice(None),) + (slice(1, -1),) * 3
+    for v1, v2 in ((1.7, -0.6), (0.25, 3.0)):
+        bv = two_sphere_potential(W.cell_centres(tree, lids, ghosts=True), v1, v2)[inner].reshape(len(lids), -1)
+        assert len(np.unique(bv)) == 2
+        orc.set_lsf_boundary_values(lids, bv)
+        orc.mg_init()
+        mg.set_lsf_boundary_values(lids, bv)
+        zeros = np.zeros((len(ids),) + (tree.nc + 2,) * 3)
+        rng = np.random.default_rng(11)
+        for var, data in ((M.I_PHI, zeros), (M.I_RHS, rng.uniform(-1, 1, zeros.shape)), (M.I_TMP, rng.uniform(-1, 1, zeros.shape))):
+            orc.set_cc(var, ids, data)  # identical state in all three variables (cycles leave unobservable
+            mg.set_cc(var, ids, data)   # differences in tmp / rhs ghost cells behind)
+        # single operations bit for bit
+        fill_all_ghosts(tree, orc, mg)
+        for lvl in range(tree.highest_lvl, 1, -1):
+            orc.gsrb_boxes(lvl, M.MG_CYCLE_DOWN)
+            mg.gsrb_boxes(lvl, M.MG_CYCLE_DOWN)
+            orc.update_coarse(lvl, True)
+            mg.update_coarse(lvl, True)
+            assert_same_state(tree, orc, mg)
+        # cycles
+        orc.fas_fmg(True, False)
+        M.mg_fas_fmg(tree, mg, True, False)
+        for _ in range(3):
+            orc.fas_vcycle(True)
+            M.mg_fas_vcycle(tree, mg, True)
+        ro, rg = orc.maxabs(M.I_TMP), M.af_tree_maxabs_cc(tree, mg, M.I_TMP)
+        assert abs(ro - rg) <= 1e-6 * ro + 1e-9
+        assert_same_state(tree, orc, mg, exact=False, rtol=1e-10, what=("phi",))
+        # the electrodes really sit at their own potentials: phi next to electrode 1 is close to v1
+        phi = mg.get_cc(M.I_PHI, lids)[inner].reshape(len(lids), -1)
+        cut = (dd.reshape(len(lids), -1, 6) < 1.0).any(axis=2)
+        near1 = cut & (bv == v1)
+        assert near1.any() and np.all(np.abs(phi[near1] - v1) < 0.75 * abs(v1 - v2))
+        # field with the level-set correction
+        vals = two_spheres(W.cell_centres(tree, lids, ghosts=True))[inner].reshape(len(lids), -1)
+        orc.set_lsf_cc(lids, vals)
+        mg.set_lsf_distances(lids, dd, vals)
+        orc.compute_phi_gradient(-1.0, True)
+        M.mg_compute_phi_gradient(tree, mg, -1.0, True)
+        fa, fb = orc.get_fc(ids), mg.get_fc(ids)
+        assert np.max(np.abs(fa - fb)) <= 1e-8 * np.max(np.abs(fa))
+    # back to the scalar
+    orc.set_lsf_boundary_values(np.zeros(0, np.int32), np.zeros((0, 8 ** 3)))
+    orc.set_opts(lsf_boundary_value=0.4)
+    orc.mg_init()
+    mg.set_lsf_boundary_values(np.zeros(0, np.int32), np.zeros((0, 8 ** 3)))
+    mg.set_lsf_boundary_value(0.4)
+    orc.fas_fmg(True, True)
+    M.mg_fas_fmg(tree, mg, True, True)
+    assert_same_state(tree, orc, mg, exact=False, rtol=1e-10, what=("phi",))
+    M.mg_destroy(mg)
