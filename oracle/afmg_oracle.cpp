@@ -71,6 +71,9 @@ struct Box {
   Stencil op, prolong;
   bool has_op = false, has_prolong = false;
   std::vector<double> lsf_dd;  // all_distances(2*ND, IJK); empty = no level-set boundary in box
+  // distances from each fine cell centre to its ND+1 coarse prolongation points (mg%lsf_dist evaluated by the
+  // caller) for mg_box_prolong_lsf_stencil; dd(1) < 0 marks a cell outside the root mask; empty = not given
+  std::vector<double> lsf_pdd;
   // boundary conditions as data: type and values per physical face (sides_bc callbacks in the
   // reference never depend on phi: m_af_ghostcell.f90:615-652, src/m_field.f90:590-670)
   int bc_type[6] = {0};
@@ -99,6 +102,7 @@ struct Tree {
   bool use_corners = false, subtract_mean = false;
   double helmholtz_lambda = 0.0, lsf_boundary_value = 0.0;
   int operator_mask = -1, prolongation_type = mg_prolong_auto;
+  bool lsf_use_custom_prolongation = false;
   // coarse solver (replaces Hypre): banded LU of the BC-folded level-1 matrix
   int cs_n = 0, cs_bw = 0;
   int cs_nx[3] = {1, 1, 1};
@@ -1122,6 +1126,43 @@ void mg_box_prolong_eps_stencil(Tree& t, Box& box, const Box& box_p) {
   stencil_try_constant(st, ncf, g.ncell(), 2.220446049250313e-16);
 }
 
+// mg_box_prolong_lsf_stencil (afivo/src/m_af_multigrid.f90:1392-1482): prolongation weights that shrink towards
+// an electrode surface; the distances to the ND+1 coarse points are given as data (lsf_pdd)
+template <int ND>
+void mg_box_prolong_lsf_stencil(Tree& t, Box& box) {
+  const int nc = t.nc;
+  G<ND> g(nc);
+  Stencil& st = box.prolong;
+  st = Stencil();
+  st.shape = af_stencil_p234;
+  st.stype = stencil_variable;
+  const int ncf = ND + 1;
+  st.v.assign((size_t)ncf * g.ncell(), 0.0);
+  for (int L = 0; L < g.ncell(); ++L) {
+    double* v = &st.v[(size_t)ncf * L];
+    if (ND == 2) { v[0] = 0.5; v[1] = 0.25; v[2] = 0.25; }
+    else { v[0] = v[1] = v[2] = v[3] = 0.25; }
+    const double* dd = &box.lsf_pdd[(size_t)ncf * L];
+    if (dd[0] < 0) continue;  // not in the root mask
+    if (ND == 2) {
+      v[0] = 2 * dd[1] * dd[2];
+      v[1] = dd[0] * dd[2];
+      v[2] = dd[0] * dd[1];
+    } else {
+      v[0] = dd[1] * dd[2] * dd[3];
+      v[1] = dd[0] * dd[2] * dd[3];
+      v[2] = dd[0] * dd[1] * dd[3];
+      v[3] = dd[0] * dd[1] * dd[2];
+    }
+    double s = 0.0;
+    for (int m = 0; m < ncf; ++m) s = s + v[m];
+    for (int m = 0; m < ncf; ++m) v[m] = v[m] / s;
+    for (int m = 0; m < ncf; ++m)
+      if (dd[m] < 1) v[m] = 0.0;
+  }
+  stencil_try_constant(st, ncf, g.ncell(), 2.220446049250313e-16);
+}
+
 // mg_set_box_tag (afivo/src/m_af_multigrid.f90:1100-1145); lsf presence given by lsf_dd data
 template <int ND>
 void mg_set_box_tag(Tree& t, Box& box) {
@@ -1170,9 +1211,12 @@ void mg_set_operators_lvl(Tree& t, int lvl, bool force) {
         default:
           switch (box.tag & t.operator_mask) {
             case mg_normal_box:
-            case mg_ceps_box:
+            case mg_ceps_box: mg_box_prolong_const<ND>(box, false); break;
             case mg_lsf_box:
-            case mg_ceps_box + mg_lsf_box: mg_box_prolong_const<ND>(box, false); break;
+            case mg_ceps_box + mg_lsf_box:
+              if (t.lsf_use_custom_prolongation && !box.lsf_pdd.empty()) mg_box_prolong_lsf_stencil<ND>(t, box);
+              else mg_box_prolong_const<ND>(box, false);
+              break;
             case mg_veps_box:
             case mg_veps_box + mg_lsf_box: mg_box_prolong_eps_stencil<ND>(t, box, box_p); break;
             default: std::fprintf(stderr, "mg_store_prolongation_stencil: unknown box tag\n"); std::abort();
@@ -1824,6 +1868,13 @@ void orc_set_lsf_boundary_values(void* h, int n, const int* ids, const double* v
   const size_t per = (t->ndim == 3) ? (size_t)t->nc * t->nc * t->nc : (size_t)t->nc * t->nc;
   for (auto& b : t->boxes) b.lsf_bv.clear();
   for (int q = 0; q < n; ++q) t->boxes[ids[q]].lsf_bv.assign(v + q * per, v + (q + 1) * per);
+}
+// mg%lsf_use_custom_prolongation with the prolongation distances (ND+1 per cell) of n boxes
+void orc_set_lsf_prolong_distances(void* h, int n, const int* ids, const double* dd) {
+  Tree* t = (Tree*)h;
+  const size_t per = (size_t)(t->ndim + 1) * (t->ndim == 3 ? t->nc * t->nc * t->nc : t->nc * t->nc);
+  t->lsf_use_custom_prolongation = n > 0;
+  for (int q = 0; q < n; ++q) t->boxes[ids[q]].lsf_pdd.assign(dd + q * per, dd + (q + 1) * per);
 }
 // cc(IJK, mg%i_lsf) on the interior (nc^ND) of n boxes
 void orc_set_lsf_cc(void* h, int n, const int* ids, const double* v) {

@@ -189,6 +189,13 @@ class Oracle:
         vals = np.ascontiguousarray(vals, np.float64).reshape(len(ids), self.tree.nc ** self.tree.ndim)
         self.L.orc_set_lsf_boundary_values(self.h, len(ids), _ip(ids), _dp(vals))
 
+    def set_lsf_prolong_distances(self, ids, dd):
+        """mg%lsf_use_custom_prolongation: distances from every fine cell to its ndim+1 coarse prolongation points
+        (dd[..., 0] < 0: cell outside the root mask); before mg_init()."""
+        ids = np.ascontiguousarray(ids, np.int32)
+        dd = np.ascontiguousarray(dd, np.float64).reshape(len(ids), -1)
+        self.L.orc_set_lsf_prolong_distances(self.h, len(ids), _ip(ids), _dp(dd))
+
     def set_lsf_cc(self, ids, vals):
         ids = np.ascontiguousarray(ids, np.int32)
         vals = np.ascontiguousarray(vals, np.float64).reshape(len(ids), self.tree.nc ** self.tree.ndim)

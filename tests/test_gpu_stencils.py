@@ -51,7 +51,44 @@ def lsf_distances(tree, lsf):
     return ids[has], out[has].reshape(int(has.sum()), -1)
 
 
-def make_pair(tree, *, eps=None, lsf=None, seed=3, **opts):
+def lsf_prolong_distances(tree, lsf):
+    """Distances of mg_box_prolong_lsf_stencil (m_af_multigrid.f90:1392-1482) with mg_lsf_dist_linear: from each
+    fine cell centre to its ndim+1 coarse prolongation points (i_c1,j_c1,k_c1), (i_c2,..), (.., j_c2, ..), (.., k_c2);
+    cells away from the surface (outside the root mask) are marked by dd[0] = -1."""
+    nd, nc = tree.ndim, tree.nc
+    ids = np.array([b for b in all_ids(tree) if tree.lvl[b] > 1], np.int32)
+    a = W.cell_centres(tree, ids, ghosts=False)  # (n, [z,] y, x, nd)
+    la = lsf(a)
+    fine = np.arange(1, nc + 1)
+    out = np.ones((len(ids),) + (nc,) * nd + (nd + 1,))
+    pr = tree.parent[ids]
+    off = ((tree.ix[ids] - 1) & 1) * (nc // 2)  # af_get_child_offset
+    c1 = [off[:, d][:, None] + (fine[None, :] + 1) // 2 for d in range(nd)]       # (n, nc) per dim
+    c2 = [c1[d] + 1 - 2 * (fine[None, :] & 1) for d in range(nd)]
+
+    def coarse_point(sel):  # sel[d] in {1, 2}: which coarse index along dim d
+        shape = (len(ids),) + (nc,) * nd + (nd,)
+        r = np.empty(shape)
+        for d in range(nd):
+            cidx = (c1 if sel[d] == 1 else c2)[d]  # (n, nc) along dim d
+            coord = tree.r_min[pr][:, d][:, None] + (cidx - 0.5) * tree.dr[pr][:, d][:, None]
+            view = [1] * (nd + 1)
+            view[0] = len(ids)
+            view[nd - d] = nc  # arrays are ordered ([z,] y, x)
+            r[..., d] = coord.reshape(view)
+        return r
+
+    sels = [[1] * nd] + [[2 if q == d else 1 for q in range(nd)] for d in range(nd)]
+    for m, sel in enumerate(sels):
+        lb = lsf(coarse_point(sel))
+        cut = la * lb < 0
+        out[..., m] = np.where(cut, np.maximum(la / np.where(cut, la - lb, 1.0), 1e-4), 1.0)
+    norm_dr = np.linalg.norm(tree.dr[ids], axis=1).reshape((len(ids),) + (1,) * nd)
+    out[..., 0] = np.where(np.abs(la) < 2 * norm_dr, out[..., 0], -1.0)
+    return ids, out.reshape(len(ids), -1)
+
+
+def make_pair(tree, *, eps=None, lsf=None, seed=3, custom_prolong=False, **opts):
     bc = W.bc_table(tree, bc_mixed)
     orc = Oracle(tree, with_eps=eps is not None, **opts)
     orc.set_bc(bc)
@@ -62,6 +99,8 @@ def make_pair(tree, *, eps=None, lsf=None, seed=3, **opts):
         lids, dd = lsf_distances(tree, lsf)
         assert len(lids) > 0
         orc.set_lsf_distances(lids, dd)
+        if custom_prolong:  # mg%lsf_use_custom_prolongation
+            orc.set_lsf_prolong_distances(*lsf_prolong_distances(tree, lsf))
     orc.mg_init()
     mg = M.mg_t(sides_bc=bc, **opts)
     M.mg_init(tree, mg)
@@ -87,6 +126,9 @@ CASES = {
     # mg_box_lpld_lsf_stencil (m_af_multigrid.f90:1535-1623): permittivity and electrode in the same boxes
     "eps_lsf_corner_nc8": (lambda: T.corner_refined_tree(3, 8, 8, 4),
                            dict(eps=eps_smooth, lsf=lsf_sphere, lsf_boundary_value=0.9)),
+    # mg%lsf_use_custom_prolongation: mg_box_prolong_lsf_stencil (variable p234 weights that vanish behind the surface)
+    "lsf_custom_prolong_corner_nc8": (lambda: T.corner_refined_tree(3, 8, 8, 4),
+                                      dict(lsf=lsf_sphere, lsf_boundary_value=0.8, custom_prolong=True)),
     # periodic domain with a non-separable coarse operator: the dense coarse solve with wrap-around couplings
     "eps_smooth_periodic_xy_nc8": (lambda: T.uniform_tree(3, 8, 8, 3, periodic=[True, True, False]), dict(eps=eps_smooth)),
     "ceps_lsf_uniform_nc8": (lambda: T.uniform_tree(3, 8, 8, 3), dict(eps=eps_const2, lsf=lsf_sphere, lsf_boundary_value=-1.2)),
