@@ -361,6 +361,33 @@ def run_gpu(args):
         field = {"ms": f_ms, "algorithmic_GBs": per_cell * tree.n_boxes * nc ** 3 / (f_ms * 1e-3) / 1e9,
                  "what": "gradient + norm on all boxes, ghost cells of the norm on all levels"}
 
+    # ---- BASELINE.json configs[3]: the three Helmholtz photoionization solves on the standard_3d-like tree ----
+    helm = None
+    if world == 1 and args.workload == "S2":
+        lambdas = np.array([4147.85, 10950.93, 66755.67]) * 0.2 * 0.02   # Bourdon-3, 20 % O2 at 1 bar, 2 cm domain
+        coeffs = np.array([1117314.935, 28692377.5, 2748842283.0]) * (0.2 * 0.02) ** 2
+        from afivo_streamer_b200 import workloads as Wk
+        hbc = Wk.bc_table(tree, M.photoi_helmh_bc)
+        modes = []
+        for lam in lambdas:
+            m = M.mg_t(sides_bc=hbc, device=local, helmholtz_lambda=float(lam ** 2), prolongation_type=M.MG_PROLONG_LINEAR)
+            M.mg_init(tree, m)
+            modes.append(m)
+        modes[0].upload_ptr(M.I_RHS, ids, h_rhs.data_ptr())
+        t0 = time.perf_counter()
+        n_cold, _ = M.photoi_helmh_compute(tree, modes, coeffs, 10, 1.0e-2)   # from zero modes (first time step)
+        t_cold = time.perf_counter() - t0
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            n_warm, _ = M.photoi_helmh_compute(tree, modes, coeffs, 10, 1.0e-2)  # from the previous modes (every later step)
+        t_warm = (time.perf_counter() - t0) / reps
+        helm = {"what": "photoi_helmh_compute, 3 modes (src/m_photoi_helmh.f90:162-204), blocking C-ABI call",
+                "first_call_ms": 1e3 * t_cold, "fmg_cycles_first": [int(x) for x in n_cold],
+                "steady_ms": 1e3 * t_warm, "fmg_cycles_steady": [int(x) for x in n_warm]}
+        for m in modes:
+            M.mg_destroy(m)
+
     # ---- e2e: host buffers through the C ABI -----------------------------------------------
     # e2e: rhs goes up as interior cells only (its ghost cells are never read), phi comes back with ghost cells
     ncell = tree.nc ** tree.ndim
@@ -447,6 +474,7 @@ def run_gpu(args):
             "vcycles_per_s": args.steps / (ms_max * 1e-3),
             "fmg": {"ms": fmg_ms, "cell_updates_per_s": cu_fmg / (fmg_ms * 1e-3)},
             "field_from_potential": field,
+            "helmholtz_photoionization": helm,
             "residual": {"after_fmg": res0, "after_timed_cycles": res1},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                     "steps": e2e_steps, "ms_per_step": 1e3 * wall_max / e2e_steps},
