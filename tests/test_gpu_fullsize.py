@@ -98,3 +98,51 @@ def test_s3s_refined_octree_converges():
     phi = mg.get_cc(M.I_PHI, np.array(top, np.int32))
     assert np.allclose(0.5 * (phi[:, 17, 1:-1, 1:-1] + phi[:, 16, 1:-1, 1:-1]), 1.0, atol=1e-12)
     M.mg_destroy(mg)
+
+
+def test_s1r_full_size_parity_with_oracle():
+    """BASELINE.md S1r at its full size (256^3 = poisson_benchmark 16 16 5): random rhs on the leaves,
+    field_bc_homogeneous with voltage 1 (Dirichlet 0 / 1 in z, Neumann 0 in x, y), 1 FMG + 10 V-cycles: same
+    per-cycle residual history, potential within 1e-10 relative max-norm of the CPU oracle (north_star tolerance).
+    The oracle needs a few seconds on the host cores here (1.7e7 finest cells)."""
+    from oracle.oracle import Oracle
+    tree = T.uniform_tree(3, 16, 16, 5)
+    bc = W.bc_field_homogeneous(tree, 1.0)
+    ids = leaves_of(tree)
+    rhs = np.random.default_rng(12345).uniform(-1.0, 1.0, (len(ids), 16, 16, 16))
+    full = W.box_array(tree, len(ids))
+    full[W.interior(tree)] = rhs
+    orc = Oracle(tree)
+    orc.set_bc(bc)
+    orc.mg_init()
+    orc.set_cc(M.I_RHS, ids, full)
+    del full
+    mg = M.mg_t(sides_bc=bc)
+    M.mg_init(tree, mg)
+    mg.set_cc_interior(M.I_RHS, ids, rhs)
+    ho, hg = [], []
+    orc.fas_fmg(True, False)
+    M.mg_fas_fmg(tree, mg, True, False)
+    for _ in range(10):
+        ho.append(orc.maxabs(M.I_TMP))
+        hg.append(M.af_tree_maxabs_cc(tree, mg, M.I_TMP))
+        orc.fas_vcycle(True)
+        M.mg_fas_vcycle(tree, mg, True)
+    ho.append(orc.maxabs(M.I_TMP))
+    hg.append(M.af_tree_maxabs_cc(tree, mg, M.I_TMP))
+    ho, hg = np.array(ho), np.array(hg)
+    assert ho[-1] < 1e-8 * ho[0], ho
+    # the residual is rhs - L(phi): seven terms of size |phi| / dr^2 = 6.6e4 cancel to O(1e-10) at the end, so the
+    # two histories can only agree to the rounding of that sum (the potentials themselves agree to 1e-10 below)
+    floor = 16 * np.finfo(float).eps * 7 * 256.0 ** 2 * 1.0
+    assert np.all(np.abs(ho - hg) <= floor + 1e-6 * ho), (ho, hg, floor)
+    worst = 0.0
+    scale = 0.0
+    for q0 in range(0, len(ids), 512):  # compare in slabs to bound host memory
+        sub = ids[q0:q0 + 512]
+        a = orc.get_cc(M.I_PHI, sub)
+        b = mg.get_cc(M.I_PHI, sub).reshape(len(sub), -1)
+        worst = max(worst, float(np.max(np.abs(a - b))))
+        scale = max(scale, float(np.max(np.abs(a))))
+    assert worst <= 1e-10 * scale, worst / scale
+    M.mg_destroy(mg)
