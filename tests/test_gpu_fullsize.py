@@ -1,4 +1,4 @@
-"""-m gpu: BASELINE.json's full sizes through size-independent properties (the oracle needs minutes
+"""-m gpu: BASELINE.json's full sizes: S1r and S2 directly against the oracle (seconds on the host cores), S1 and
 there): S1 = poisson_benchmark 16 16 5 (256^3) and the S3s shell-refined octree (1.1e8 cells)."""
 import numpy as np
 import pytest
@@ -146,3 +146,79 @@ def test_s1r_full_size_parity_with_oracle():
         scale = max(scale, float(np.max(np.abs(a))))
     assert worst <= 1e-10 * scale, worst / scale
     M.mg_destroy(mg)
+
+
+def test_s2_field_and_helmholtz_patterns_parity():
+    """BASELINE.md S2 at its full size (standard_3d-like channel-refined tree, nc = 8, 9 levels, 8905 boxes): the field
+    pattern of field_compute (FMG from scratch, then 2 V-cycles with the residual test, src/m_field.f90:491-524)
+    and the Helmholtz pattern of photoi_helmh_compute (3 modes, <= 10 FMG each, src/m_photoi_helmh.f90:162-204),
+    GPU against the CPU oracle: same residual histories / FMG counts, results within 1e-10."""
+    from oracle.oracle import Oracle
+    tree = T.channel_tree(8, 8, 9, 3)
+    assert tree.highest_lvl == 9
+    all_ids = np.concatenate(tree.lvl_ids).astype(np.int32)
+    ids, rhs = W.random_rhs_on_leaves(tree)
+    # ---- field pattern
+    bc = W.bc_field_homogeneous(tree, 1.0)
+    orc = Oracle(tree)
+    orc.set_bc(bc)
+    orc.mg_init()
+    orc.set_cc(M.I_RHS, ids, rhs)
+    mg = M.mg_t(sides_bc=bc)
+    M.mg_init(tree, mg)
+    mg.set_cc(M.I_RHS, ids, rhs)
+    ho, hg = [], []
+    orc.fas_fmg(True, False)
+    M.mg_fas_fmg(tree, mg, True, False)
+    for _ in range(2):
+        ho.append(orc.maxabs(M.I_TMP))
+        hg.append(M.af_tree_maxabs_cc(tree, mg, M.I_TMP))
+        orc.fas_vcycle(True)
+        M.mg_fas_vcycle(tree, mg, True)
+    ho.append(orc.maxabs(M.I_TMP))
+    hg.append(M.af_tree_maxabs_cc(tree, mg, M.I_TMP))
+    ho, hg = np.array(ho), np.array(hg)
+    dr_min = float(np.min(tree.dr[all_ids]))
+    floor = 16 * np.finfo(float).eps * 7 / dr_min ** 2
+    assert np.all(np.abs(ho - hg) <= floor + 1e-6 * ho), (ho, hg, floor)
+    a = orc.get_cc(M.I_PHI, all_ids)
+    b = mg.get_cc(M.I_PHI, all_ids).reshape(len(all_ids), -1)
+    assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(a))
+    M.mg_destroy(mg)
+    del orc
+    # ---- Helmholtz pattern (Bourdon-3 at 1 bar, 20 % O2, 2 cm domain scaled to the unit cube)
+    lambdas = np.array([4147.85, 10950.93, 66755.67]) * 0.2 * 0.02
+    coeffs = np.array([1117314.935, 28692377.5, 2748842283.0]) * (0.2 * 0.02) ** 2
+    hbc = W.bc_table(tree, M.photoi_helmh_bc)
+    leaves = tree.children[all_ids, 0] == 0
+    photo = np.zeros((len(all_ids), tree.box_len))
+    ncyc_o = []
+    max_rhs = None
+    for lam, c in zip(lambdas, coeffs):
+        o = Oracle(tree, helmholtz_lambda=lam ** 2, prolongation_type=M.MG_PROLONG_LINEAR)
+        o.set_bc(hbc)
+        o.mg_init()
+        o.set_cc(M.I_RHS, ids, rhs)
+        if max_rhs is None:
+            max_rhs = max(o.maxabs(M.I_RHS), np.sqrt(np.finfo(float).eps))
+        n = 0
+        for n in range(1, 11):
+            o.fas_fmg(True, True)
+            if o.maxabs(M.I_TMP) / max_rhs < 1e-2:
+                break
+        ncyc_o.append(n)
+        phi = o.get_cc(M.I_PHI, all_ids)
+        photo[leaves] = photo[leaves] - c * phi[leaves]
+        del o
+    mgs = []
+    for lam in lambdas:
+        m = M.mg_t(sides_bc=hbc, helmholtz_lambda=float(lam ** 2), prolongation_type=M.MG_PROLONG_LINEAR)
+        M.mg_init(tree, m)
+        mgs.append(m)
+    mgs[0].set_cc(M.I_RHS, ids, rhs)
+    ncyc, _ = M.photoi_helmh_compute(tree, mgs, coeffs, 10, 1.0e-2)
+    assert list(ncyc) == ncyc_o, (ncyc, ncyc_o)
+    got = mgs[0].get_cc(M.I_PHOTO, all_ids).reshape(len(all_ids), -1)
+    assert np.max(np.abs(got - photo)) <= 1e-10 * np.max(np.abs(photo))
+    for m in mgs:
+        M.mg_destroy(m)
