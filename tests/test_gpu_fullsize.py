@@ -1,5 +1,6 @@
-"""-m gpu: BASELINE.json's full sizes: S1r and S2 directly against the oracle (seconds on the host cores), S1 and
-there): S1 = poisson_benchmark 16 16 5 (256^3) and the S3s shell-refined octree (1.1e8 cells)."""
+"""-m gpu: BASELINE.json's full sizes.  S1r (256^3) and S2 (9-level channel tree) directly against the oracle
+(seconds on the host cores); S1 = poisson_benchmark 16 16 5 and the S3s shell-refined octree (1.1e8 cells) through
+size-independent properties (linearity, fixed point, convergence)."""
 import numpy as np
 import pytest
 
