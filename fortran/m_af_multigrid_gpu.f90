@@ -131,6 +131,7 @@ module m_af_multigrid_gpu
   public :: mg_gpu_init, mg_gpu_destroy, mg_gpu_fas_fmg, mg_gpu_fas_vcycle
   public :: mg_gpu_update_operator_stencil, mg_gpu_tree_maxabs_tmp
   public :: mg_gpu_compute_phi_gradient, mg_gpu_compute_field_norm, mg_gpu_gc_tree_norm, photoi_gpu_helmh_compute
+  public :: mg_gpu_field_solve
 
 contains
 
@@ -549,6 +550,33 @@ contains
          "afmg_helmholtz_compute")
     call transfer(tree, slots(1), i_photo, afmg_photo, leaves, .false.)
   end subroutine photoi_gpu_helmh_compute
+
+  !> The solve loop of field_compute (src/m_field.f90:491-524) in one call: FMG cycles until the residual criterion
+  !> is met (only without a guess), then up to n_vcycles V-cycles; only the residual max-norms cross PCIe per
+  !> cycle.  rhs goes up before, phi (and the residual in i_tmp) come back after.
+  subroutine mg_gpu_field_solve(tree, mg, have_guess, residual_threshold, max_residual, max_fmg, n_vcycles, slot, &
+       residuals, n_fmg, n_vc)
+    type(af_t), intent(inout) :: tree
+    type(mg_t), intent(inout) :: mg
+    logical, intent(in)       :: have_guess
+    real(dp), intent(in)      :: residual_threshold, max_residual
+    integer, intent(in)       :: max_fmg, n_vcycles, slot
+    real(dp), intent(out)     :: residuals(max_fmg + n_vcycles)
+    integer, intent(out)      :: n_fmg, n_vc
+    integer, allocatable      :: ids(:), leaves(:)
+    integer(c_int)            :: rc
+    call sync_tree(tree, mg, slot)
+    call sync_lsf_boundary_values(tree, mg, slot)
+    call all_ids(tree, leaves, .true.); call all_ids(tree, ids, .false.)
+    call transfer(tree, slot, mg%i_rhs, afmg_rhs, leaves, .true.)
+    if (have_guess) call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .true.)
+    rc = afmg_field_solve(solvers(slot)%h, merge(1, 0, have_guess), residual_threshold, max_residual, max_fmg, &
+         n_vcycles, residuals, n_fmg, n_vc)
+    if (rc == -7) error stop "No convergence in initial field computation"  ! AFMG_ERR_NOT_CONVERGED
+    call check(rc, "afmg_field_solve")
+    call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .false.)
+    call transfer(tree, slot, mg%i_tmp, afmg_tmp, ids, .false.)
+  end subroutine mg_gpu_field_solve
 
   !> max |residual| over leaves without downloading i_tmp (af_tree_maxabs_cc, m_af_utils.f90:773)
   subroutine mg_gpu_tree_maxabs_tmp(slot, val)
