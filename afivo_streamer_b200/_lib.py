@@ -109,6 +109,7 @@ SYMBOLS = {
     "afmg_cell_updates": (C.c_int, [_H, _I, _I, _DP]),
     "afmg_layout_offset": (C.c_int32, [_I, _I, _I, _I, _I]),
     "afmg_layout_box_len": (C.c_int32, [_I, _I]),
+    "afmg_morton_key": (C.c_int64, [_I, _I, _I, _I]),
     "afmg_slot_of_box": (C.c_int32, [_H, _I]),
     "afmg_comm_init": (C.c_int, [_H, _I, _I]),
     "afmg_comm_export": (C.c_int, [_H, C.c_void_p]),

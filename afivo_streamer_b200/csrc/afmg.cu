@@ -2161,6 +2161,19 @@ int32_t afmg_layout_box_len(int32_t ndim, int32_t nc) {
   return ndim == 3 ? (nc + 2) * (nc + 2) * (nc + 2) : (nc + 2) * (nc + 2);
 }
 
+// Morton (Z-order) key with x in the lowest bit, afivo's convention (m_morton.f90; known answers
+// afivo/tests/answers/test_morton_2d, _3d).  The device slot order inside a level and the multi-GPU cuts follow
+// this key of ix - 1 (in 2D the 3D interleave with z = 0 is used internally: same order, different key values).
+int64_t afmg_morton_key(int32_t ndim, int32_t ix, int32_t iy, int32_t iz) {
+  if (ndim == 3) return (int64_t)morton3((uint32_t)ix, (uint32_t)iy, (uint32_t)iz);
+  uint64_t r = 0;
+  for (int b = 0; b < 31; ++b) {
+    r |= (uint64_t)(((uint32_t)ix >> b) & 1u) << (2 * b);
+    r |= (uint64_t)(((uint32_t)iy >> b) & 1u) << (2 * b + 1);
+  }
+  return (int64_t)r;
+}
+
 int32_t afmg_slot_of_box(const afmg_handle* h, int32_t box_id) {
   if (!h || !h->have_tree || box_id < 1 || box_id > h->highest_id) return -1;
   return h->id2slot[box_id];

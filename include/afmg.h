@@ -300,6 +300,10 @@ int afmg_cell_updates(afmg_handle* h, int32_t highest_lvl, int32_t fmg, double* 
  * box record; a bijection onto 0 .. (nc+2)^ndim - 1.  See DESIGN.md "data layout". */
 int32_t afmg_layout_offset(int32_t ndim, int32_t nc, int32_t i, int32_t j, int32_t k);
 int32_t afmg_layout_box_len(int32_t ndim, int32_t nc);
+/* Morton (Z-order) key, x in the lowest bit as in afivo's m_morton (morton_from_ix2 / _ix3; known answers
+ * afivo/tests/answers/test_morton_2d, _3d).  Boxes of a level are stored, and cut into per-GPU ranges, in the order
+ * of this key of box%ix - 1. */
+int64_t afmg_morton_key(int32_t ndim, int32_t ix, int32_t iy, int32_t iz);
 /* slot (position in the device arrays) of a box id, -1 if unknown */
 int32_t afmg_slot_of_box(const afmg_handle* h, int32_t box_id);
 

@@ -113,3 +113,15 @@ def test_cell_update_count_matches_definition():
     import bench
     t = T.uniform_tree(3, 16, 16, 5)
     assert bench.cell_updates_vcycle(t) == 4 * 16 ** 3 * (8 + 64 + 512 + 4096)
+
+
+def test_morton_key_matches_the_reference_answers():
+    """afivo/tests/answers/test_morton_3d: index (15, 2047, 2047) -> 7362801663; test_morton_2d: (15, 2047) ->
+    2796287 (x in the lowest bit).  The slot order of a level and the multi-GPU cuts are built on this key."""
+    L = _lib.lib()
+    assert L.afmg_morton_key(3, 15, 2047, 2047) == 7362801663
+    assert L.afmg_morton_key(2, 15, 2047, 0) == 2796287
+    # Z-order: the eight children of a box (2 ix - 1 + af_child_dix) are consecutive, in af_child_dix order
+    base = L.afmg_morton_key(3, 2 * 5, 2 * 3, 2 * 9)
+    keys = [L.afmg_morton_key(3, 2 * 5 + (c & 1), 2 * 3 + ((c >> 1) & 1), 2 * 9 + ((c >> 2) & 1)) for c in range(8)]
+    assert keys == [base + c for c in range(8)]
