@@ -1,0 +1,319 @@
+// afmg.hpp -- C++ host-side mirror of afivo's multigrid interface on top of the C ABI (afmg.h).
+//
+// The reference's callers are compiled Fortran (src/m_field.f90, src/m_photoi_helmh.f90, afivo/examples/*.f90); this
+// header gives a compiled-language caller the same vocabulary: `mg_t` with the option members of
+// afivo/src/m_af_types.f90:572-665, `mg_init / mg_destroy / mg_fas_fmg / mg_fas_vcycle / mg_update_operator_stencil`
+// with the argument lists of afivo/src/m_af_multigrid.f90:43, :111, :137, :185, :1188, the reductions
+// `af_tree_maxabs_cc / af_tree_sum_cc` (m_af_utils.f90:773, :966) and the field routines
+// `mg_compute_phi_gradient / mg_compute_field_norm` (:1857, :2002).  `error stop` becomes `afmg::error`.
+// Header only; link with -lafmg.  tools/poisson_benchmark.cpp is written against it.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "afmg.h"
+
+namespace afmg {
+
+struct error : std::runtime_error {
+  int code;
+  error(int c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+
+// The parts of af_t / box_t the solver reads (m_af_types.f90:286-393) as flat arrays with reference conventions:
+// 1-based ids (row 0 unused), af_no_box = 0, af_phys_boundary = -1.  Cell data lives on the device.
+struct af_t {
+  int ndim = 3, n_cell = 0, coord_t = AFMG_XYZ;
+  int highest_lvl = 0, highest_id = 0;
+  int coarse_grid_size[3] = {1, 1, 1};
+  bool periodic[3] = {false, false, false};
+  double r_base[3] = {0, 0, 0}, dr_base[3] = {0, 0, 0};
+  std::vector<std::vector<int32_t>> lvl_ids;  // [highest_lvl + 1]: lvls(l)%ids
+  std::vector<int32_t> lvl, ix, parent, children, neighbors, neighbor_mat;
+  std::vector<double> r_min;                  // (n+1, ndim), needed for cylindrical trees only
+
+  int num_children() const { return 1 << ndim; }
+  int num_neighbors() const { return 2 * ndim; }
+  bool has_children(int id) const { return children[(size_t)id * num_children()] != 0; }
+  std::vector<int32_t> ids(bool leaves_only) const {
+    std::vector<int32_t> out;
+    for (int l = 1; l <= highest_lvl; ++l)
+      for (int32_t id : lvl_ids[l])
+        if (!leaves_only || !has_children(id)) out.push_back(id);
+    return out;
+  }
+  size_t box_len() const {
+    size_t n = 1;
+    for (int d = 0; d < ndim; ++d) n *= (size_t)(n_cell + 2);
+    return n;
+  }
+};
+
+// subroutine sides_bc(box, nb, iv, coords, bc_val, bc_type) (m_af_types.f90:401-420) reduced to what the built-in
+// conditions need: (box id, nb) -> type and one value for the whole face; use mg_t::set_bc for per-cell values
+using sides_bc_t = std::function<void(int id, int nb, int& bc_type, double& bc_val)>;
+inline void af_bc_dirichlet_zero(int, int, int& bc_type, double& bc_val) {  // m_af_ghostcell.f90:628-638
+  bc_type = AFMG_BC_DIRICHLET;
+  bc_val = 0.0;
+}
+inline void af_bc_neumann_zero(int, int, int& bc_type, double& bc_val) {  // m_af_ghostcell.f90:615-625
+  bc_type = AFMG_BC_NEUMANN;
+  bc_val = 0.0;
+}
+
+struct mg_t {
+  // options a caller sets before mg_init (m_af_types.f90:572-665)
+  int n_cycle_down = 2, n_cycle_up = 2;
+  bool use_corners = false, subtract_mean = false;
+  double helmholtz_lambda = 0.0, lsf_boundary_value = 0.0;
+  int operator_mask = -1, prolongation_type = AFMG_PROLONG_AUTO;
+  sides_bc_t sides_bc;
+  int device = -1;
+  bool initialized = false;
+  afmg_handle* h = nullptr;
+
+  mg_t() = default;
+  mg_t(const mg_t&) = delete;
+  mg_t& operator=(const mg_t&) = delete;
+  ~mg_t() {
+    if (h) afmg_destroy(h);
+  }
+  void check(int rc, const char* what) const {
+    if (rc != AFMG_OK) throw error(rc, std::string(what) + ": " + afmg_last_error(h));
+  }
+  void need_init() const {
+    if (!initialized) throw error(AFMG_ERR_STATE, "mg_t not initialized");  // the reference: error stop in mg_use
+  }
+  // box%cc(:, ..., iv) of the listed boxes, packed in list order (first index fastest)
+  void set_cc(int var, const std::vector<int32_t>& ids, const double* packed) {
+    need_init();
+    check(afmg_upload(h, var, (int32_t)ids.size(), ids.data(), packed), "afmg_upload");
+  }
+  void set_cc_interior(int var, const std::vector<int32_t>& ids, const double* packed) {
+    need_init();
+    check(afmg_upload_interior(h, var, (int32_t)ids.size(), ids.data(), packed), "afmg_upload_interior");
+  }
+  void get_cc(int var, const std::vector<int32_t>& ids, double* packed) {
+    need_init();
+    check(afmg_download(h, var, (int32_t)ids.size(), ids.data(), packed), "afmg_download");
+  }
+  // per-face boundary rows: ids, nb (1..2*ndim), types, values (nc^(ndim-1) each)
+  void set_bc(const std::vector<int32_t>& ids, const std::vector<int32_t>& nb, const std::vector<int32_t>& types,
+              const std::vector<double>& vals) {
+    need_init();
+    check(afmg_set_bc(h, (int32_t)ids.size(), ids.data(), nb.data(), types.data(), vals.data()), "afmg_set_bc");
+  }
+};
+
+// Forward a (new) topology, e.g. after af_adjust_refinement, and evaluate mg%sides_bc on every physical face
+inline void mg_set_tree(const af_t& tree, mg_t& mg) {
+  mg.need_init();
+  std::vector<int32_t> counts, concat;
+  for (int l = 1; l <= tree.highest_lvl; ++l) {
+    counts.push_back((int32_t)tree.lvl_ids[l].size());
+    concat.insert(concat.end(), tree.lvl_ids[l].begin(), tree.lvl_ids[l].end());
+  }
+  afmg_tree td{};
+  td.highest_lvl = tree.highest_lvl;
+  td.highest_id = tree.highest_id;
+  td.lvl_counts = counts.data();
+  td.lvl_ids = concat.data();
+  td.lvl = tree.lvl.data();
+  td.ix = tree.ix.data();
+  td.parent = tree.parent.data();
+  td.children = tree.children.data();
+  td.neighbors = tree.neighbors.data();
+  td.neighbor_mat = tree.neighbor_mat.data();
+  td.r_min = tree.r_min.empty() ? nullptr : tree.r_min.data();
+  mg.check(afmg_set_tree(mg.h, &td), "afmg_set_tree");
+  size_t nface = 1;
+  for (int d = 1; d < tree.ndim; ++d) nface *= (size_t)tree.n_cell;
+  std::vector<int32_t> bid, bnb, bty;
+  std::vector<double> bval;
+  for (int32_t id : concat)
+    for (int nb = 1; nb <= tree.num_neighbors(); ++nb)
+      if (tree.neighbors[(size_t)id * tree.num_neighbors() + nb - 1] == -1) {
+        int ty = 0;
+        double v = 0.0;
+        mg.sides_bc(id, nb, ty, v);
+        bid.push_back(id);
+        bnb.push_back(nb);
+        bty.push_back(ty);
+        bval.insert(bval.end(), nface, v);
+      }
+  mg.set_bc(bid, bnb, bty, bval);
+}
+
+// mg_init (afivo/src/m_af_multigrid.f90:43-109)
+inline void mg_init(const af_t& tree, mg_t& mg) {
+  if (!mg.sides_bc) throw error(AFMG_ERR_ARG, "mg_init: sides_bc not set");  // :50-51 stop
+  afmg_opts o{};
+  o.ndim = tree.ndim;
+  o.n_cell = tree.n_cell;
+  o.coord_t = tree.coord_t;
+  o.n_cycle_down = mg.n_cycle_down;
+  o.n_cycle_up = mg.n_cycle_up;
+  o.use_corners = mg.use_corners;
+  o.subtract_mean = mg.subtract_mean;
+  o.prolongation_type = mg.prolongation_type;
+  o.operator_mask = mg.operator_mask;
+  o.device = mg.device;
+  o.helmholtz_lambda = mg.helmholtz_lambda;
+  o.lsf_boundary_value = mg.lsf_boundary_value;
+  for (int d = 0; d < 3; ++d) {
+    o.coarse_grid_size[d] = d < tree.ndim ? tree.coarse_grid_size[d] : 1;
+    o.periodic[d] = d < tree.ndim && tree.periodic[d];
+    o.dr_base[d] = d < tree.ndim ? tree.dr_base[d] : 0.0;
+    o.r_base[d] = d < tree.ndim ? tree.r_base[d] : 0.0;
+  }
+  const int rc = afmg_create(&mg.h, &o);
+  if (rc != AFMG_OK) throw error(rc, std::string("afmg_create: ") + afmg_last_error(nullptr));
+  mg.initialized = true;
+  mg_set_tree(tree, mg);
+}
+
+// mg_destroy (:111-115)
+inline void mg_destroy(mg_t& mg) {
+  if (mg.h) afmg_destroy(mg.h);
+  mg.h = nullptr;
+  mg.initialized = false;
+}
+
+// mg_fas_fmg(tree, mg, set_residual, have_guess) (:137-180)
+inline void mg_fas_fmg(const af_t&, mg_t& mg, bool set_residual, bool have_guess) {
+  mg.need_init();
+  mg.check(afmg_fas_fmg(mg.h, set_residual, have_guess), "afmg_fas_fmg");
+}
+
+// mg_fas_vcycle(tree, mg, set_residual, highest_lvl, standalone) (:185-264); highest_lvl = 0: tree%highest_lvl
+inline void mg_fas_vcycle(const af_t&, mg_t& mg, bool set_residual, int highest_lvl = 0, bool standalone = true) {
+  mg.need_init();
+  mg.check(afmg_fas_vcycle(mg.h, set_residual, highest_lvl, standalone), "afmg_fas_vcycle");
+}
+
+// mg_update_operator_stencil (:1188-1214) after mg%helmholtz_lambda / mg%lsf_boundary_value changed
+inline void mg_update_operator_stencil(const af_t&, mg_t& mg) {
+  mg.need_init();
+  mg.check(afmg_set_helmholtz_lambda(mg.h, mg.helmholtz_lambda), "afmg_set_helmholtz_lambda");
+  mg.check(afmg_set_lsf_boundary_value(mg.h, mg.lsf_boundary_value), "afmg_set_lsf_boundary_value");
+  mg.check(afmg_update_operator_stencil(mg.h), "afmg_update_operator_stencil");
+}
+
+// af_tree_maxabs_cc (m_af_utils.f90:773-785): max |cc| over the interior of the leaves
+inline double af_tree_maxabs_cc(const af_t&, mg_t& mg, int var) {
+  mg.need_init();
+  double v = 0.0;
+  mg.check(afmg_max_abs(mg.h, var, &v), "afmg_max_abs");
+  return v;
+}
+
+// af_tree_sum_cc (m_af_utils.f90:966-1027): volume-weighted sum over the leaves
+inline double af_tree_sum_cc(const af_t&, mg_t& mg, int var) {
+  mg.need_init();
+  double v = 0.0;
+  mg.check(afmg_tree_sum(mg.h, var, &v), "afmg_tree_sum");
+  return v;
+}
+
+// mg_compute_phi_gradient(tree, mg, i_fc, fac, i_norm) (:1857-1898); results stay on the device
+// (afmg_download_fc, get_cc(AFMG_FLD, ...))
+inline void mg_compute_phi_gradient(const af_t&, mg_t& mg, double fac, bool with_norm = true) {
+  mg.need_init();
+  mg.check(afmg_compute_phi_gradient(mg.h, fac, with_norm), "afmg_compute_phi_gradient");
+}
+
+// mg_compute_field_norm (:2002-2020)
+inline void mg_compute_field_norm(const af_t&, mg_t& mg) {
+  mg.need_init();
+  mg.check(afmg_compute_field_norm(mg.h), "afmg_compute_field_norm");
+}
+
+// af_gc_tree(tree, [iv], corners) (m_af_ghostcell.f90:25-46) for AFMG_PHI or AFMG_FLD
+inline void af_gc_tree(const af_t&, mg_t& mg, int var, bool corners = true) {
+  mg.need_init();
+  mg.check(afmg_gc_tree(mg.h, var, corners), "afmg_gc_tree");
+}
+
+// af_init + "refine everything up to max_lvl" (af_adjust_refinement with af_do_ref below max_lvl), the tree of
+// afivo/examples/poisson_benchmark.f90:72-90, in the reference's conventions: level-1 ids i + (j-1) nx + (k-1) nx ny
+// (m_af_core.f90:436-501), children appended parent by parent in af_child_dix order (:1187-1254), neighbours /
+// neighbor_mat with af_phys_boundary = -1 outside the domain (:595-661).  3D, unit cube.
+inline af_t af_init_fully_refined(int n_cell, int coarse_grid_size, int max_lvl) {
+  af_t t;
+  t.ndim = 3;
+  t.n_cell = n_cell;
+  t.highest_lvl = max_lvl;
+  const int nb1 = coarse_grid_size / n_cell;
+  long total = 0;
+  for (int l = 1; l <= max_lvl; ++l) total += (long)nb1 * nb1 * nb1 * (1L << (3 * (l - 1)));
+  t.highest_id = (int)total;
+  for (int d = 0; d < 3; ++d) {
+    t.coarse_grid_size[d] = coarse_grid_size;
+    t.dr_base[d] = 1.0 / coarse_grid_size;
+  }
+  const size_t N = (size_t)t.highest_id + 1;
+  t.lvl.assign(N, 0);
+  t.ix.assign(N * 3, 0);
+  t.parent.assign(N, 0);
+  t.children.assign(N * 8, 0);
+  t.neighbors.assign(N * 6, 0);
+  t.neighbor_mat.assign(N * 27, 0);
+  t.lvl_ids.assign(max_lvl + 1, {});
+  std::vector<std::vector<int32_t>> at(max_lvl + 1);  // dense (level, ix) -> id: every position exists
+  int next = 1;
+  at[1].assign((size_t)nb1 * nb1 * nb1, 0);
+  for (int k = 1; k <= nb1; ++k)
+    for (int j = 1; j <= nb1; ++j)
+      for (int i = 1; i <= nb1; ++i) {
+        const int id = next++;
+        t.lvl[id] = 1;
+        t.ix[(size_t)id * 3 + 0] = i;
+        t.ix[(size_t)id * 3 + 1] = j;
+        t.ix[(size_t)id * 3 + 2] = k;
+        at[1][(size_t)(i - 1) + nb1 * ((j - 1) + (size_t)nb1 * (k - 1))] = id;
+        t.lvl_ids[1].push_back(id);
+      }
+  for (int l = 1; l < max_lvl; ++l) {
+    const int nbl = nb1 << l;  // boxes per dimension on level l + 1
+    at[l + 1].assign((size_t)nbl * nbl * nbl, 0);
+    for (int32_t p : t.lvl_ids[l])
+      for (int c = 0; c < 8; ++c) {
+        const int id = next++;
+        t.lvl[id] = l + 1;
+        t.parent[id] = p;
+        t.children[(size_t)p * 8 + c] = id;
+        int q[3];
+        for (int d = 0; d < 3; ++d) {
+          q[d] = 2 * t.ix[(size_t)p * 3 + d] - 1 + ((c >> d) & 1);  // af_child_dix
+          t.ix[(size_t)id * 3 + d] = q[d];
+        }
+        at[l + 1][(size_t)(q[0] - 1) + nbl * ((q[1] - 1) + (size_t)nbl * (q[2] - 1))] = id;
+        t.lvl_ids[l + 1].push_back(id);
+      }
+  }
+  for (int l = 1; l <= max_lvl; ++l) {
+    const int nbl = nb1 << (l - 1);
+    for (int32_t id : t.lvl_ids[l]) {
+      const int32_t* q = &t.ix[(size_t)id * 3];
+      for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int x = q[0] + dx, y = q[1] + dy, z = q[2] + dz;
+            const bool out = x < 1 || x > nbl || y < 1 || y > nbl || z < 1 || z > nbl;
+            t.neighbor_mat[(size_t)id * 27 + (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)] =
+                out ? -1 : at[l][(size_t)(x - 1) + nbl * ((y - 1) + (size_t)nbl * (z - 1))];
+          }
+      for (int nb = 0; nb < 6; ++nb) {
+        int d[3] = {0, 0, 0};
+        d[nb >> 1] = (nb & 1) ? 1 : -1;
+        t.neighbors[(size_t)id * 6 + nb] = t.neighbor_mat[(size_t)id * 27 + (d[0] + 1) + 3 * (d[1] + 1) + 9 * (d[2] + 1)];
+      }
+    }
+  }
+  return t;
+}
+
+}  // namespace afmg
