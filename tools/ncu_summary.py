@@ -51,8 +51,35 @@ def launches_summary(path):
     return agg
 
 
+def vcycle_windows(path, finest_grid, all_grid):
+    """Split a launch list of bench.py into V-cycles (each ends with the final residual over all boxes) and give,
+    per window, the summed duration and the share of the finest-level half-sweeps: the figure bench.py reports
+    as roofline.share_of_step from CUDA events."""
+    rows = list(csv.reader(open(path, errors="ignore")))
+    start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    col = {h: i for i, h in enumerate(rows[start])}
+    seq = []
+    for r in rows[start + 1:]:
+        if len(r) <= col["Metric Value"] or r[col["Metric Name"]] != "gpu__time_duration.sum":
+            continue
+        v = float(r[col["Metric Value"]].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r[col["Metric Unit"]], 1.0)
+        seq.append((r[col["Kernel Name"]], r[col["Grid Size"]], v))
+    ends = [i for i, (n, g, _) in enumerate(seq) if "k_resid3" in n and ", 0, " in n.split("(")[0] and g.startswith(f"({all_grid},")]
+    out = []
+    for a, b in zip(ends[:-1], ends[1:]):
+        w = seq[a + 1:b + 1]
+        tot = sum(v for _, _, v in w)
+        top = sum(v for n, g, v in w if "k_gsrb2" in n and g.startswith(f"({finest_grid},"))
+        out.append((len(w), tot, top / tot))
+    return out
+
+
 if __name__ == "__main__":
     kind, path = sys.argv[1], sys.argv[2]
+    if kind == "vcycle":
+        for n, tot, share in vcycle_windows(path, sys.argv[3], sys.argv[4]):
+            print(f"{n} launches, {tot / 1e3:.2f} ms, finest-level k_gsrb2 share {100 * share:.1f} %")
+        sys.exit(0)
     if kind == "rep":
         for d in rep_summary(path):
             t, tu = d["gpu__time_duration.sum"]
