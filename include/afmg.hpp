@@ -8,6 +8,7 @@
 // `mg_compute_phi_gradient / mg_compute_field_norm` (:1857, :2002).  `error stop` becomes `afmg::error`.
 // Header only; link with -lafmg.  tools/poisson_benchmark.cpp is written against it.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <functional>
 #include <stdexcept>
@@ -33,7 +34,8 @@ struct af_t {
   double r_base[3] = {0, 0, 0}, dr_base[3] = {0, 0, 0};
   std::vector<std::vector<int32_t>> lvl_ids;  // [highest_lvl + 1]: lvls(l)%ids
   std::vector<int32_t> lvl, ix, parent, children, neighbors, neighbor_mat;
-  std::vector<double> r_min;                  // (n+1, ndim), needed for cylindrical trees only
+  std::vector<double> r_min;                  // (n+1, ndim): box%r_min
+  std::vector<double> dr;                     // (n+1, ndim): box%dr
 
   int num_children() const { return 1 << ndim; }
   int num_neighbors() const { return 2 * ndim; }
@@ -44,6 +46,30 @@ struct af_t {
       for (int32_t id : lvl_ids[l])
         if (!leaves_only || !has_children(id)) out.push_back(id);
     return out;
+  }
+  // af_r_cc (m_af_types.f90:1035-1040): centre of cell (i, j, k), ghost indices allowed
+  void r_cc(int id, const int* ijk, double* r) const {
+    for (int d = 0; d < ndim; ++d) r[d] = r_min[(size_t)id * ndim + d] + (ijk[d] - 0.5) * dr[(size_t)id * ndim + d];
+  }
+  // af_get_face_coords (m_af_types.f90:1215-1253): coords(ndim, nc^(ndim-1)) of the cell-face centres on side nb,
+  // the transverse dimensions in increasing order, first one fastest
+  void face_coords(int id, int nb, std::vector<double>& coords) const {
+    const int d = (nb - 1) / 2;
+    const bool low = (nb % 2) == 1;
+    size_t nface = 1;
+    for (int q = 1; q < ndim; ++q) nface *= (size_t)n_cell;
+    coords.assign(nface * ndim, 0.0);
+    int td[2] = {0, 0}, ntd = 0;
+    for (int q = 0; q < ndim; ++q)
+      if (q != d) td[ntd++] = q;
+    const double* rm = &r_min[(size_t)id * ndim];
+    const double* h = &dr[(size_t)id * ndim];
+    for (size_t n = 0; n < nface; ++n) {
+      double* c = &coords[n * ndim];
+      c[d] = low ? rm[d] : rm[d] + n_cell * h[d];
+      c[td[0]] = (rm[td[0]] + 0.5 * h[td[0]]) + (double)(n % n_cell) * h[td[0]];
+      if (ndim == 3) c[td[1]] = (rm[td[1]] + 0.5 * h[td[1]]) + (double)(n / n_cell) * h[td[1]];
+    }
   }
   size_t box_len() const {
     size_t n = 1;
@@ -64,6 +90,11 @@ inline void af_bc_neumann_zero(int, int, int& bc_type, double& bc_val) {  // m_a
   bc_val = 0.0;
 }
 
+// the full callback: coords(ndim, nface) in, bc_val(nface) and bc_type out (e.g. sides_bc of
+// afivo/examples/poisson_basic.f90:219-235: Dirichlet values from an analytic solution)
+using sides_bc_coords_t =
+    std::function<void(int id, int nb, const std::vector<double>& coords, std::vector<double>& bc_val, int& bc_type)>;
+
 struct mg_t {
   // options a caller sets before mg_init (m_af_types.f90:572-665)
   int n_cycle_down = 2, n_cycle_up = 2;
@@ -71,6 +102,7 @@ struct mg_t {
   double helmholtz_lambda = 0.0, lsf_boundary_value = 0.0;
   int operator_mask = -1, prolongation_type = AFMG_PROLONG_AUTO;
   sides_bc_t sides_bc;
+  sides_bc_coords_t sides_bc_coords;  // takes precedence over sides_bc when set
   int device = -1;
   bool initialized = false;
   afmg_handle* h = nullptr;
@@ -137,19 +169,26 @@ inline void mg_set_tree(const af_t& tree, mg_t& mg) {
     for (int nb = 1; nb <= tree.num_neighbors(); ++nb)
       if (tree.neighbors[(size_t)id * tree.num_neighbors() + nb - 1] == -1) {
         int ty = 0;
-        double v = 0.0;
-        mg.sides_bc(id, nb, ty, v);
+        if (mg.sides_bc_coords) {
+          std::vector<double> coords, vals(nface, 0.0);
+          tree.face_coords(id, nb, coords);
+          mg.sides_bc_coords(id, nb, coords, vals, ty);
+          bval.insert(bval.end(), vals.begin(), vals.end());
+        } else {
+          double v = 0.0;
+          mg.sides_bc(id, nb, ty, v);
+          bval.insert(bval.end(), nface, v);
+        }
         bid.push_back(id);
         bnb.push_back(nb);
         bty.push_back(ty);
-        bval.insert(bval.end(), nface, v);
       }
   mg.set_bc(bid, bnb, bty, bval);
 }
 
 // mg_init (afivo/src/m_af_multigrid.f90:43-109)
 inline void mg_init(const af_t& tree, mg_t& mg) {
-  if (!mg.sides_bc) throw error(AFMG_ERR_ARG, "mg_init: sides_bc not set");  // :50-51 stop
+  if (!mg.sides_bc && !mg.sides_bc_coords) throw error(AFMG_ERR_ARG, "mg_init: sides_bc not set");  // :50-51 stop
   afmg_opts o{};
   o.ndim = tree.ndim;
   o.n_cell = tree.n_cell;
@@ -237,74 +276,147 @@ inline void af_gc_tree(const af_t&, mg_t& mg, int var, bool corners = true) {
   mg.check(afmg_gc_tree(mg.h, var, corners), "afmg_gc_tree");
 }
 
-// af_init + "refine everything up to max_lvl" (af_adjust_refinement with af_do_ref below max_lvl), the tree of
-// afivo/examples/poisson_benchmark.f90:72-90, in the reference's conventions: level-1 ids i + (j-1) nx + (k-1) nx ny
-// (m_af_core.f90:436-501), children appended parent by parent in af_child_dix order (:1187-1254), neighbours /
-// neighbor_mat with af_phys_boundary = -1 outside the domain (:595-661).  3D, unit cube.
-inline af_t af_init_fully_refined(int n_cell, int coarse_grid_size, int max_lvl) {
+// af_init followed by af_adjust_refinement until nothing is added: a 2:1 balanced 3D tree in the reference's
+// conventions -- level-1 ids i + (j-1) nx + (k-1) nx ny (m_af_core.f90:436-501), children appended parent by parent
+// in af_child_dix order (:1187-1254), neighbours / neighbor_mat with af_phys_boundary = -1 outside a non-periodic
+// domain (:595-661), 2:1 balance over faces from the finest level down (ensure_two_one_balance, :1016-1057).
+// refine(lvl, ix, centre) is asked for every existing box of level lvl < max_lvl (the union over the cells of a box
+// of the reference's per-cell flags); nullptr refines everything.
+using refine_t = std::function<bool(int lvl, const int* ix, const double* centre)>;
+
+inline af_t af_build_tree(int n_cell, const int* coarse_grid_size, int max_lvl, const refine_t& refine = nullptr,
+                          const double* r_lo = nullptr, const double* r_hi = nullptr, const bool* periodic = nullptr) {
   af_t t;
   t.ndim = 3;
   t.n_cell = n_cell;
-  t.highest_lvl = max_lvl;
-  const int nb1 = coarse_grid_size / n_cell;
-  long total = 0;
-  for (int l = 1; l <= max_lvl; ++l) total += (long)nb1 * nb1 * nb1 * (1L << (3 * (l - 1)));
-  t.highest_id = (int)total;
+  int nb1[3];
   for (int d = 0; d < 3; ++d) {
-    t.coarse_grid_size[d] = coarse_grid_size;
-    t.dr_base[d] = 1.0 / coarse_grid_size;
+    t.coarse_grid_size[d] = coarse_grid_size[d];
+    t.periodic[d] = periodic ? periodic[d] : false;
+    t.r_base[d] = r_lo ? r_lo[d] : 0.0;
+    t.dr_base[d] = ((r_hi ? r_hi[d] : 1.0) - t.r_base[d]) / coarse_grid_size[d];
+    nb1[d] = coarse_grid_size[d] / n_cell;
   }
-  const size_t N = (size_t)t.highest_id + 1;
+  auto nbl = [&](int l, int d) { return nb1[d] << (l - 1); };
+  auto lin = [&](int l, int x, int y, int z) { return (size_t)x + (size_t)nbl(l, 0) * ((size_t)y + (size_t)nbl(l, 1) * z); };
+  auto cells = [&](int l) { return (size_t)nbl(l, 0) * nbl(l, 1) * nbl(l, 2); };
+  std::vector<std::vector<char>> exists(max_lvl + 2), refined(max_lvl + 2);
+  exists[1].assign(cells(1), 1);
+  auto upsample = [&](int l) {  // children of the refined boxes of level l
+    exists[l + 1].assign(cells(l + 1), 0);
+    for (int z = 0; z < nbl(l, 2); ++z)
+      for (int y = 0; y < nbl(l, 1); ++y)
+        for (int x = 0; x < nbl(l, 0); ++x)
+          if (refined[l][lin(l, x, y, z)])
+            for (int c = 0; c < 8; ++c) exists[l + 1][lin(l + 1, 2 * x + (c & 1), 2 * y + ((c >> 1) & 1), 2 * z + ((c >> 2) & 1))] = 1;
+  };
+  for (int l = 1; l < max_lvl; ++l) {
+    refined[l].assign(cells(l), 0);
+    for (int z = 0; z < nbl(l, 2); ++z)
+      for (int y = 0; y < nbl(l, 1); ++y)
+        for (int x = 0; x < nbl(l, 0); ++x) {
+          if (!exists[l][lin(l, x, y, z)]) continue;
+          bool r = true;
+          if (refine) {
+            const int ix[3] = {x + 1, y + 1, z + 1};
+            double ctr[3];
+            for (int d = 0; d < 3; ++d) ctr[d] = t.r_base[d] + (ix[d] - 0.5) * (t.dr_base[d] * std::pow(0.5, l - 1)) * n_cell;
+            r = refine(l, ix, ctr);
+          }
+          refined[l][lin(l, x, y, z)] = r;
+        }
+    upsample(l);
+  }
+  refined[max_lvl].assign(cells(max_lvl), 0);
+  for (int l = max_lvl - 1; l > 1; --l)  // 2:1 balance over faces
+    for (int z = 0; z < nbl(l, 2); ++z)
+      for (int y = 0; y < nbl(l, 1); ++y)
+        for (int x = 0; x < nbl(l, 0); ++x) {
+          if (!refined[l][lin(l, x, y, z)]) continue;
+          for (int nb = -1; nb < 6; ++nb) {  // the box itself and its six face neighbours must exist
+            int q[3] = {x, y, z};
+            if (nb >= 0) {
+              q[nb >> 1] += (nb & 1) ? 1 : -1;
+              const int d = nb >> 1;
+              if (q[d] < 0 || q[d] >= nbl(l, d)) {
+                if (!t.periodic[d]) continue;
+                q[d] = (q[d] + nbl(l, d)) % nbl(l, d);
+              }
+            }
+            refined[l - 1][lin(l - 1, q[0] / 2, q[1] / 2, q[2] / 2)] = 1;
+          }
+        }
+  for (int l = 1; l < max_lvl; ++l) upsample(l);
+  int highest = 1;
+  for (int l = 1; l <= max_lvl; ++l)
+    for (char e : exists[l])
+      if (e) {
+        highest = l;
+        break;
+      }
+  t.highest_lvl = highest;
+  // enumerate level by level in the reference's list order
+  struct P { int x, y, z; };
+  std::vector<std::vector<P>> order(highest + 1);
+  for (int z = 0; z < nbl(1, 2); ++z)
+    for (int y = 0; y < nbl(1, 1); ++y)
+      for (int x = 0; x < nbl(1, 0); ++x) order[1].push_back({x, y, z});
+  for (int l = 1; l < highest; ++l)
+    for (const P& p : order[l])
+      if (refined[l][lin(l, p.x, p.y, p.z)])
+        for (int c = 0; c < 8; ++c) order[l + 1].push_back({2 * p.x + (c & 1), 2 * p.y + ((c >> 1) & 1), 2 * p.z + ((c >> 2) & 1)});
+  size_t total = 0;
+  for (int l = 1; l <= highest; ++l) total += order[l].size();
+  t.highest_id = (int)total;
+  const size_t N = total + 1;
   t.lvl.assign(N, 0);
   t.ix.assign(N * 3, 0);
   t.parent.assign(N, 0);
   t.children.assign(N * 8, 0);
   t.neighbors.assign(N * 6, 0);
   t.neighbor_mat.assign(N * 27, 0);
-  t.lvl_ids.assign(max_lvl + 1, {});
-  std::vector<std::vector<int32_t>> at(max_lvl + 1);  // dense (level, ix) -> id: every position exists
+  t.r_min.assign(N * 3, 0.0);
+  t.dr.assign(N * 3, 0.0);
+  t.lvl_ids.assign(highest + 1, {});
+  std::vector<std::vector<int32_t>> idgrid(highest + 1);
   int next = 1;
-  at[1].assign((size_t)nb1 * nb1 * nb1, 0);
-  for (int k = 1; k <= nb1; ++k)
-    for (int j = 1; j <= nb1; ++j)
-      for (int i = 1; i <= nb1; ++i) {
-        const int id = next++;
-        t.lvl[id] = 1;
-        t.ix[(size_t)id * 3 + 0] = i;
-        t.ix[(size_t)id * 3 + 1] = j;
-        t.ix[(size_t)id * 3 + 2] = k;
-        at[1][(size_t)(i - 1) + nb1 * ((j - 1) + (size_t)nb1 * (k - 1))] = id;
-        t.lvl_ids[1].push_back(id);
+  for (int l = 1; l <= highest; ++l) {
+    idgrid[l].assign(cells(l), 0);
+    for (const P& p : order[l]) {
+      const int id = next++;
+      t.lvl_ids[l].push_back(id);
+      t.lvl[id] = l;
+      const int q[3] = {p.x, p.y, p.z};
+      for (int d = 0; d < 3; ++d) {
+        t.ix[(size_t)id * 3 + d] = q[d] + 1;
+        t.dr[(size_t)id * 3 + d] = t.dr_base[d] * std::pow(0.5, l - 1);
       }
-  for (int l = 1; l < max_lvl; ++l) {
-    const int nbl = nb1 << l;  // boxes per dimension on level l + 1
-    at[l + 1].assign((size_t)nbl * nbl * nbl, 0);
-    for (int32_t p : t.lvl_ids[l])
-      for (int c = 0; c < 8; ++c) {
-        const int id = next++;
-        t.lvl[id] = l + 1;
-        t.parent[id] = p;
-        t.children[(size_t)p * 8 + c] = id;
-        int q[3];
-        for (int d = 0; d < 3; ++d) {
-          q[d] = 2 * t.ix[(size_t)p * 3 + d] - 1 + ((c >> d) & 1);  // af_child_dix
-          t.ix[(size_t)id * 3 + d] = q[d];
-        }
-        at[l + 1][(size_t)(q[0] - 1) + nbl * ((q[1] - 1) + (size_t)nbl * (q[2] - 1))] = id;
-        t.lvl_ids[l + 1].push_back(id);
+      idgrid[l][lin(l, p.x, p.y, p.z)] = id;
+      if (l == 1) {
+        for (int d = 0; d < 3; ++d) t.r_min[(size_t)id * 3 + d] = t.r_base[d] + q[d] * t.dr_base[d] * n_cell;
+      } else {
+        const int pid = idgrid[l - 1][lin(l - 1, p.x / 2, p.y / 2, p.z / 2)];
+        t.parent[id] = pid;
+        const int c = (p.x & 1) | ((p.y & 1) << 1) | ((p.z & 1) << 2);
+        t.children[(size_t)pid * 8 + c] = id;
+        for (int d = 0; d < 3; ++d)  // add_children: r_min = r_min_p + 0.5 * dr_p * dix * n_cell
+          t.r_min[(size_t)id * 3 + d] = t.r_min[(size_t)pid * 3 + d] + 0.5 * t.dr[(size_t)pid * 3 + d] * (q[d] & 1) * n_cell;
       }
+    }
   }
-  for (int l = 1; l <= max_lvl; ++l) {
-    const int nbl = nb1 << (l - 1);
+  for (int l = 1; l <= highest; ++l)
     for (int32_t id : t.lvl_ids[l]) {
       const int32_t* q = &t.ix[(size_t)id * 3];
       for (int dz = -1; dz <= 1; ++dz)
         for (int dy = -1; dy <= 1; ++dy)
           for (int dx = -1; dx <= 1; ++dx) {
-            const int x = q[0] + dx, y = q[1] + dy, z = q[2] + dz;
-            const bool out = x < 1 || x > nbl || y < 1 || y > nbl || z < 1 || z > nbl;
-            t.neighbor_mat[(size_t)id * 27 + (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)] =
-                out ? -1 : at[l][(size_t)(x - 1) + nbl * ((y - 1) + (size_t)nbl * (z - 1))];
+            int p[3] = {q[0] - 1 + dx, q[1] - 1 + dy, q[2] - 1 + dz};
+            bool out = false;
+            for (int d = 0; d < 3; ++d) {
+              if (t.periodic[d]) p[d] = (p[d] + nbl(l, d)) % nbl(l, d);
+              else out = out || p[d] < 0 || p[d] >= nbl(l, d);
+            }
+            t.neighbor_mat[(size_t)id * 27 + (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)] = out ? -1 : idgrid[l][lin(l, p[0], p[1], p[2])];
           }
       for (int nb = 0; nb < 6; ++nb) {
         int d[3] = {0, 0, 0};
@@ -312,8 +424,13 @@ inline af_t af_init_fully_refined(int n_cell, int coarse_grid_size, int max_lvl)
         t.neighbors[(size_t)id * 6 + nb] = t.neighbor_mat[(size_t)id * 27 + (d[0] + 1) + 3 * (d[1] + 1) + 9 * (d[2] + 1)];
       }
     }
-  }
   return t;
+}
+
+// the tree of afivo/examples/poisson_benchmark.f90:72-90: unit cube, everything refined up to max_lvl
+inline af_t af_init_fully_refined(int n_cell, int coarse_grid_size, int max_lvl) {
+  const int cgs[3] = {coarse_grid_size, coarse_grid_size, coarse_grid_size};
+  return af_build_tree(n_cell, cgs, max_lvl);
 }
 
 }  // namespace afmg

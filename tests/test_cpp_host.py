@@ -12,17 +12,35 @@ from afivo_streamer_b200 import tree as T
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("nc,coarse,lvl", [(8, 8, 3), (4, 8, 3), (16, 16, 2)])
-def test_cpp_tree_matches_python_builder(tmp_path, nc, coarse, lvl):
+CASES = {
+    "uniform_8_8_3": ("uniform", 8, [8, 8, 8], 3, lambda: T.uniform_tree(3, 8, 8, 3)),
+    "uniform_16_16_2": ("uniform", 16, [16, 16, 16], 2, lambda: T.uniform_tree(3, 16, 16, 2)),
+    "corner_8_8_4": ("corner", 8, [8, 8, 8], 4, lambda: T.corner_refined_tree(3, 8, 8, 4)),
+    "sphere_multibox_8": ("sphere", 8, [16, 8, 24], 3,
+                          lambda: T.build_tree(3, 8, [16, 8, 24], 3, lambda l, ix, c: np.linalg.norm(c - 0.4, axis=1) < 0.45)),
+    "sphere_4_deep": ("sphere", 4, [8, 8, 8], 4,
+                      lambda: T.build_tree(3, 4, [8, 8, 8], 4, lambda l, ix, c: np.linalg.norm(c - 0.4, axis=1) < 0.45)),
+}
+
+
+@pytest.fixture(scope="module")
+def dump_exe(tmp_path_factory):
     lib_dir = os.path.join(ROOT, "afivo_streamer_b200")
-    exe = str(tmp_path / "cpp_tree_dump")
-    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+    exe = str(tmp_path_factory.mktemp("cpp") / "cpp_tree_dump")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
                            os.path.join(ROOT, "tests", "cpp_tree_dump.cpp"), "-o", exe, "-L", lib_dir, "-lafmg",
                            "-Wl,-rpath," + lib_dir])
-    out = subprocess.run([exe, str(nc), str(coarse), str(lvl)], capture_output=True, text=True, timeout=120)
+    return exe
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cpp_tree_matches_python_builder(dump_exe, name):
+    kind, nc, cgs, lvl, mk = CASES[name]
+    out = subprocess.run([dump_exe, kind, str(nc)] + [str(c) for c in cgs] + [str(lvl)], capture_output=True, text=True,
+                         timeout=120)
     assert out.returncode == 0, out.stderr
     lines = out.stdout.strip().splitlines()
-    t = T.uniform_tree(3, nc, coarse, lvl)
+    t = mk()
     hl, hid = map(int, lines[0].split())
     assert (hl, hid) == (t.highest_lvl, t.highest_id)
     for l in range(hl):
@@ -36,4 +54,9 @@ def test_cpp_tree_matches_python_builder(tmp_path, nc, coarse, lvl):
     assert np.array_equal(boxes[:, 5:13], t.children[ids])
     assert np.array_equal(boxes[:, 13:19], t.neighbors[ids])
     assert np.array_equal(boxes[:, 19:46], t.neighbor_mat[ids])
+    geo = np.array([list(map(float, ln.split()[1:])) for ln in lines[1 + hl + hid:1 + hl + 2 * hid]])
+    assert np.array_equal(geo[:, 0:3], t.r_min[ids]) and np.array_equal(geo[:, 3:6], t.dr[ids])
+    from afivo_streamer_b200 import workloads as W
+    fc = W.face_coords(t, ids, 3)  # af_get_face_coords on the low-y side
+    assert np.array_equal(geo[:, 6:9], fc[:, 0, :]) and np.array_equal(geo[:, 9:12], fc[:, -1, :])
     assert lines[-1] in ("device present", "error -2")  # AFMG_ERR_CUDA without a GPU: no CPU fallback
