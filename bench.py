@@ -90,35 +90,27 @@ CPU_SAMPLE = {"S3": "S3s"}  # bounded CPU sample of a workload too large to time
 
 
 def build_workload(name, want_rhs=True):
+    """(tree, bc, leaf ids, rhs, description) of a named workload; want_rhs=False skips the host-side right-hand
+    side (ids, rhs = None, None) for callers that generate it on the device."""
     from afivo_streamer_b200 import tree as T
     from afivo_streamer_b200 import workloads as W
-    if not want_rhs:  # only the tree and the boundary conditions (rhs is made on the device)
-        saved = (W.random_rhs_on_leaves, W.constant_rhs_on_leaves)
-        W.random_rhs_on_leaves = lambda tree, seed=12345: (None, None)
-        W.constant_rhs_on_leaves = lambda tree, value=1.0: (None, None)
-        try:
-            return build_workload(name, True)
-        finally:
-            W.random_rhs_on_leaves, W.constant_rhs_on_leaves = saved
+    rhs_kind = "random"
     if name == "S1":
         tree = T.uniform_tree(3, 16, 16, 5)
         bc = W.bc_dirichlet_zero(tree)
-        ids, rhs = W.constant_rhs_on_leaves(tree, 1.0)
+        rhs_kind = "one"
         desc = "S1: poisson_benchmark 16 16 5 = uniform 256^3 grid of 16^3 boxes, rhs=1, Dirichlet-0"
     elif name == "S1r":
         tree = T.uniform_tree(3, 16, 16, 5)
         bc = W.bc_field_homogeneous(tree, 1.0)
-        ids, rhs = W.random_rhs_on_leaves(tree)
         desc = "S1r: uniform 256^3 of 16^3 boxes, random rhs, field_bc_homogeneous"
     elif name == "S3s":
         tree = T.shell_tree(16, 16, 5)
         bc = W.bc_field_homogeneous(tree, 1.0)
-        ids, rhs = W.random_rhs_on_leaves(tree)
         desc = "S3s: 256^3 uniform + one refined level inside (512^3-equivalent shell-refined octree)"
     elif name == "S3":
         tree = T.shell_tree(16, 16, 6)
         bc = W.bc_field_homogeneous(tree, 1.0)
-        ids, rhs = W.random_rhs_on_leaves(tree)
         desc = ("S3: 1024^3-equivalent refined octree (BASELINE.json configs[4]): 512^3 uniform (levels 1-6) + level 7 "
                 "on all but the outermost box layer, 16^3 boxes, 1.04e9 cells, field_bc_homogeneous; it fits one B200 "
                 "and is the >=1e8-cell tree the north-star target is quoted on")
@@ -126,15 +118,16 @@ def build_workload(name, want_rhs=True):
         tree = T.build_tree(2, 8, [8, 8], 7, None, coord_t=T.AF_CYL)
         bc = W.bc_table(tree, lambda nb, c: (W.AF_BC_DIRICHLET, 0.0 if nb == 3 else 1.0) if (nb - 1) // 2 == 1
                         else (W.AF_BC_NEUMANN, 0.0))
-        ids, rhs = W.random_rhs_on_leaves(tree)
         desc = "S0: 2D cylindrical (BASELINE.json configs[0] stand-in), nc=8, coarse 8^2, 7 uniform levels (512^2 cells)"
     elif name == "S2":
         tree = T.channel_tree(8, 8, 9, 3)
         bc = W.bc_field_homogeneous(tree, 1.0)
-        ids, rhs = W.random_rhs_on_leaves(tree)
         desc = "S2: standard_3d-like channel-refined tree, nc=8, 9 levels"
     else:
         raise SystemExit(f"unknown workload {name}")
+    ids = rhs = None
+    if want_rhs:
+        ids, rhs = W.constant_rhs_on_leaves(tree, 1.0) if rhs_kind == "one" else W.random_rhs_on_leaves(tree)
     return tree, bc, ids, rhs, desc
 
 
