@@ -173,3 +173,46 @@ def test_gsrb_colour_convention():
     inner = (i >= 1) & (i <= 8) & (j >= 1) & (j <= 8) & (k >= 1) & (k <= 8)
     assert np.all(changed[inner & ((i + j + k) % 2 == 1)])
     assert not np.any(changed[~(inner & ((i + j + k) % 2 == 1))])
+
+
+def test_discrete_eigenfunction_of_the_cell_centred_laplacian():
+    """Analytic pin of stencil + Dirichlet ghost cells + coarse solve: on a cell-centred grid with ghost = 2 b - phi_1
+    (bc_to_gc, m_af_ghostcell.f90:192-214, b = 0) the product of sines sin(pi x) sin(2 pi y) sin(3 pi z) sampled at
+    the cell centres is an exact eigenvector of the 7-point operator (mg_box_lpl_stencil, m_af_multigrid.f90:1246-1264)
+    with eigenvalue -(4 / h^2) (sin^2(pi h / 2) + sin^2(2 pi h / 2) + sin^2(3 pi h / 2)).  So with rhs = lambda_h * phi
+    the residual of phi vanishes on every level, a V-cycle leaves phi unchanged, and the coarse-grid solve returns it."""
+    t = T.uniform_tree(3, 8, 8, 3)
+    o = Oracle(t)
+    o.set_bc(W.bc_dirichlet_zero(t))
+    o.mg_init()
+    ids = np.concatenate(t.lvl_ids).astype(np.int32)
+    r = W.cell_centres(t, ids, ghosts=True)
+    modes = np.array([1.0, 2.0, 3.0])
+    phi = np.prod(np.sin(np.pi * modes * r), axis=-1)
+    lam = np.zeros(len(ids))
+    for q, b in enumerate(ids):
+        h = t.dr[b, 0]
+        lam[q] = -(4 / h ** 2) * np.sum(np.sin(np.pi * modes * h / 2) ** 2)
+    rhs = lam[:, None, None, None] * phi
+    o.set_cc(I_PHI, ids, phi)
+    o.set_cc(I_RHS, ids, rhs)
+    for lvl in range(1, t.highest_lvl + 1):
+        o.gc_lvl(lvl, I_PHI, True)      # Dirichlet ghost cells reproduce the odd extension of the sines
+        o.residual_lvl(lvl)
+    tmp = o.get_cc(I_TMP, ids).reshape(phi.shape)[W.interior(t)]
+    scale = np.max(np.abs(rhs))
+    assert np.max(np.abs(tmp)) < 1e-12 * scale, np.max(np.abs(tmp)) / scale
+    # coarse grid: the direct solve of the BC-folded level-1 matrix returns the eigenvector
+    one = ids[:1]
+    o.set_cc(I_PHI, one, np.zeros_like(phi[:1]))
+    o.solve_coarse_grid()
+    got = o.get_cc(I_PHI, one).reshape(phi[:1].shape)[W.interior(t)]
+    assert np.max(np.abs(got - phi[:1][W.interior(t)])) < 1e-12
+    # on the finest level the eigenvector with its own rhs is a fixed point of the smoother
+    leaves = t.leaves(t.highest_lvl).astype(np.int32)
+    before = o.get_cc(I_PHI, leaves).copy()
+    o.gsrb_boxes(t.highest_lvl, 1)
+    after = o.get_cc(I_PHI, leaves)
+    inner = W.interior(t)
+    shape = (len(leaves),) + (t.nc + 2,) * 3
+    assert np.max(np.abs(after.reshape(shape)[inner] - before.reshape(shape)[inner])) < 1e-13
