@@ -216,3 +216,31 @@ def test_discrete_eigenfunction_of_the_cell_centred_laplacian():
     inner = W.interior(t)
     shape = (len(leaves),) + (t.nc + 2,) * 3
     assert np.max(np.abs(after.reshape(shape)[inner] - before.reshape(shape)[inner])) < 1e-13
+
+
+def test_cylindrical_operator_is_exact_for_r2_plus_z2():
+    """The conservative cylindrical 5-point form (cc_cyl, m_af_stencil.f90:886-925, af_cyl_flux_factors
+    m_af_types.f90:1199-1211) differentiates r^2 and z^2 exactly: [(r + h/2)(2 r h + h^2) - (r - h/2)(2 r h - h^2)]
+    / (r h^2) = 4 and the z part gives 2, so L(r^2 + z^2) = 6 in every cell whose stencil does not touch a domain
+    boundary ghost cell -- on the axis too, where the inner flux factor vanishes."""
+    t = T.build_tree(2, 8, [8, 8], 4, lambda l, ix, c: (c[:, 0] < 0.6) & (np.abs(c[:, 1] - 0.5) < 0.3), coord_t=T.AF_CYL)
+    o = Oracle(t)
+    o.set_bc(W.bc_table(t, lambda nb, c: (W.AF_BC_NEUMANN, 0.0) if nb == 1 else (W.AF_BC_DIRICHLET, (c ** 2).sum(axis=-1))))
+    o.mg_init()
+    ids = np.concatenate(t.lvl_ids).astype(np.int32)
+    r = W.cell_centres(t, ids, ghosts=True)
+    phi = (r ** 2).sum(axis=-1)          # exact values in ALL cells incl. ghost cells: no ghost fill needed
+    rhs = np.full_like(phi, 6.0)
+    o.set_cc(I_PHI, ids, phi)
+    o.set_cc(I_RHS, ids, rhs)
+    for lvl in range(1, t.highest_lvl + 1):
+        o.residual_lvl(lvl)
+    res = o.get_cc(I_TMP, ids).reshape(phi.shape)[W.interior(t)]
+    assert np.max(np.abs(res)) < 1e-9, np.max(np.abs(res))  # 1/h^2 = 4096^... rounding of O(1e3) terms
+    # and with ghost cells filled by the library's own rules the cells next to the axis stay exact (Neumann-0 there
+    # multiplies a vanishing flux factor), those next to refinement boundaries only to second order
+    lv1 = t.lvl_ids[0].astype(np.int32)
+    o.gc_lvl(1, I_PHI, True)
+    o.residual_lvl(1)
+    res1 = o.get_cc(I_TMP, lv1).reshape((len(lv1), t.nc + 2, t.nc + 2))
+    assert np.max(np.abs(res1[:, 2:-2, 1:-2])) < 1e-9   # rows away from the z boundaries, columns from the axis on
