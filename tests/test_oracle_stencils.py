@@ -158,3 +158,59 @@ def test_lpld_lsf_stencil_reduces_to_its_two_parents():
     for _ in range(4):
         o.fas_vcycle(True)
     assert o.maxabs(M.I_TMP) < 1e-3 * r0
+
+
+def test_harmonic_mean_operator_is_exact_for_a_flux_continuous_piecewise_linear_potential():
+    """mg_box_lpld_stencil (m_af_multigrid.f90:1493-1532): with the permittivity jumping from 1 to 3 at the cell face
+    z = 0.5, the potential a z (z < 0.5), a / 2 + (a / 3)(z - 1/2) (z > 0.5) has a continuous flux eps dphi/dz; the
+    harmonic-mean coefficient 2 a0 a / (a0 + a) makes the discrete operator vanish on it exactly, in the two cell
+    layers next to the interface as well."""
+    tree = T.uniform_tree(3, 8, 8, 3)
+    ids = all_ids(tree)
+    orc = Oracle(tree, with_eps=True)
+    orc.set_bc(W.bc_table(tree, bc_mixed))
+    r = W.cell_centres(tree, ids, ghosts=True)
+    z = r[..., 2]
+    orc.set_cc(M.I_EPS, ids, np.where(z < 0.5, 1.0, 3.0))
+    orc.mg_init()
+    a = 1.7
+    phi = np.where(z < 0.5, a * z, 0.5 * a + (a / 3.0) * (z - 0.5))
+    orc.set_cc(M.I_PHI, ids, phi)      # exact values in the ghost cells too
+    orc.set_cc(M.I_RHS, ids, np.zeros_like(phi))
+    for lvl in range(1, tree.highest_lvl + 1):
+        orc.residual_lvl(lvl)
+    res = orc.get_cc(M.I_TMP, ids).reshape(phi.shape)[W.interior(tree)]
+    scale = a / np.min(tree.dr[ids]) ** 2
+    assert np.max(np.abs(res)) < 1e-12 * scale, np.max(np.abs(res)) / scale
+    tags = {orc.tag(b) for b in ids}
+    assert 2 in tags  # boxes straddling the interface are mg_veps_box
+
+
+def test_level_set_operator_is_exact_for_a_linear_potential_through_the_electrode_value():
+    """mg_box_lsf_stencil (m_af_multigrid.f90:1782-1854) + bc_correction = f * V (:1171-1174): next to a planar
+    electrode at x = x0 the neighbour value is replaced by V at distance dd h with the non-uniform second-difference
+    weights 1 / (h^2/2 (dd1 + dd2) dd); a potential that is linear and equals V on the plane is annihilated exactly."""
+    tree = T.uniform_tree(3, 8, 8, 3)
+    ids = all_ids(tree)
+    x0, V, s = 0.4321, 0.7, 2.0
+    r = W.cell_centres(tree, ids, ghosts=True)
+    lsf = r[..., 0] - x0
+    nc = tree.nc
+    c = lsf[:, 1:-1, 1:-1, 1:-1]
+    dd = np.ones((len(ids), nc, nc, nc, 6))
+    for m, b in enumerate([lsf[:, 1:-1, 1:-1, :-2], lsf[:, 1:-1, 1:-1, 2:]]):
+        cut = c * b < 0
+        dd[..., m] = np.where(cut, c / np.where(cut, c - b, 1.0), 1.0)
+    has = np.any(dd < 1.0, axis=(1, 2, 3, 4))
+    orc = Oracle(tree, lsf_boundary_value=V)
+    orc.set_bc(W.bc_table(tree, bc_mixed))
+    orc.set_lsf_distances(ids[has], dd[has].reshape(int(has.sum()), -1))
+    orc.mg_init()
+    phi = V + s * lsf
+    orc.set_cc(M.I_PHI, ids, phi)
+    orc.set_cc(M.I_RHS, ids, np.zeros_like(phi))
+    for lvl in range(1, tree.highest_lvl + 1):
+        orc.residual_lvl(lvl)
+    res = orc.get_cc(M.I_TMP, ids).reshape(phi.shape)[W.interior(tree)]
+    scale = s / np.min(tree.dr[ids]) ** 2
+    assert has.any() and np.max(np.abs(res)) < 1e-11 * scale, np.max(np.abs(res)) / scale
