@@ -244,3 +244,22 @@ def test_cylindrical_operator_is_exact_for_r2_plus_z2():
     o.residual_lvl(1)
     res1 = o.get_cc(I_TMP, lv1).reshape((len(lv1), t.nc + 2, t.nc + 2))
     assert np.max(np.abs(res1[:, 2:-2, 1:-2])) < 1e-9   # rows away from the z boundaries, columns from the axis on
+
+
+def test_helmholtz_with_neumann_everywhere_has_the_constant_solution():
+    """Sign convention and Neumann folding in one known answer: lpl(phi) - lambda * phi = f (m_af_types.f90:595-597,
+    mg_box_lpl_stencil c(1) = -sum(c(2:)) - lambda) with zero-flux boundaries on all faces (stencil_handle_boundaries:
+    diag += c_nb, m_coarse_solver.f90:466-476) and constant f has the constant solution phi = -f / lambda; one FMG
+    cycle on a refined tree must land on it to rounding."""
+    t = T.corner_refined_tree(3, 8, 8, 4)
+    lam, f = 50.0, 3.0
+    o = Oracle(t, helmholtz_lambda=lam)
+    o.set_bc(W.bc_neumann_zero(t))
+    o.mg_init()
+    ids, rhs = W.constant_rhs_on_leaves(t, f)
+    o.set_cc(I_RHS, ids, rhs)
+    o.fas_fmg(True, False)
+    all_ids = np.concatenate(t.lvl_ids).astype(np.int32)
+    phi = o.get_cc(I_PHI, all_ids)
+    assert np.max(np.abs(phi + f / lam)) < 1e-13, np.max(np.abs(phi + f / lam))
+    assert o.maxabs(I_TMP) < 1e-11
