@@ -44,6 +44,14 @@ class StencilDesc(C.Structure):
     ]
 
 
+class LsfOpts(C.Structure):
+    _fields_ = [("dist_method", C.c_int32), ("gradient_safety_factor", C.c_double), ("length_scale", C.c_double),
+                ("tol", C.c_double), ("min_rel_distance", C.c_double)]
+
+
+LSF_FN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_void_p)  # afmg_lsf_fn
+
+
 class TreeDesc(C.Structure):
     _fields_ = [
         ("highest_lvl", C.c_int32), ("highest_id", C.c_int32), ("lvl_counts", C.POINTER(C.c_int32)),
@@ -116,6 +124,14 @@ SYMBOLS = {
     "afmg_comm_connect": (C.c_int, [_H, C.c_void_p]),
     "afmg_owner_of_box": (C.c_int32, [_H, _I]),
     "afmg_partition": (C.c_int, [_I, _I, _IP, _IP]),
+    "afmg_lsf_opts_default": (None, [C.POINTER(LsfOpts)]),
+    "afmg_build_box_tag": (C.c_int32, [_I, _I, _DP, _I]),
+    "afmg_build_box_operator": (C.c_int, [_I, _I, _I, _I, _DP, _DP, _DP, _DP, _DP, _DP, _IP, _IP, _IP]),
+    "afmg_build_box_prolongation": (C.c_int, [_I, _I, _I, _IP, _DP, _DP, _DP, _IP, _IP]),
+    "afmg_build_box_lsf_distances": (C.c_int, [_I, _I, _DP, _DP, LSF_FN, C.c_void_p, C.POINTER(LsfOpts), _DP,
+                                               C.POINTER(C.c_uint8), _DP, _IP]),
+    "afmg_build_box_lsf_prolong_distances": (C.c_int, [_I, _I, _DP, _DP, _IP, _DP, _DP, LSF_FN, C.c_void_p,
+                                                       C.POINTER(LsfOpts), C.POINTER(C.c_uint8), _DP]),
 }
 
 _lib = None

@@ -2278,3 +2278,5 @@ int32_t afmg_owner_of_box(const afmg_handle* h, int32_t box_id) {
 #include "afmg_field_api.inc"
 
 }  // extern "C"
+
+#include "afmg_builders.inc"

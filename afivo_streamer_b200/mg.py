@@ -530,6 +530,30 @@ def mg_update_operator_stencil(tree: Tree, mg: mg_t):
     mg._check(_lib.lib().afmg_update_operator_stencil(mg._h))
 
 
+def mg_set_operators_tree(tree: Tree, mg: mg_t, *, eps_cc=None, lsf=None, lsf_options=None,
+                          lsf_use_custom_prolongation: bool = False):
+    """What mg_init does for a tree with mg_i_eps / mg_i_lsf set (mg_set_operators_tree,
+    afivo/src/m_af_multigrid.f90:1216-1225 -> mg_set_box_tag :1100-1145, mg_store_operator_stencil :823-859,
+    mg_store_prolongation_stencil :862-903): tag every box, build the explicit operator / prolongation stencils with
+    the library's host-side builders (stencils.build_stencils) and ship them, the permittivity (AFMG_EPS, for the
+    eps-weighted field of mg_box_lpl_gradient) and the level-set distances (for mg_box_lpllsf_gradient).
+
+    eps_cc: (highest_id + 1, nc+2, ...) permittivity indexed by box id, ghost cells filled; lsf: mg%lsf as a function
+    of one point.  Returns (entries, lsf_data) for inspection."""
+    from . import stencils as S
+    mg._need_init()
+    entries, data = S.build_stencils(tree, eps_cc=eps_cc, lsf=lsf, lsf_options=lsf_options,
+                                     operator_mask=mg.operator_mask, prolongation_type=mg.prolongation_type,
+                                     lsf_use_custom_prolongation=lsf_use_custom_prolongation)
+    mg.set_stencils(entries)
+    if eps_cc is not None:
+        ids = np.concatenate(tree.lvl_ids).astype(np.int32)
+        mg.set_cc(I_EPS, ids, np.ascontiguousarray(eps_cc)[ids])
+    if data is not None:
+        mg.set_lsf_distances(data.ids, data.dd, data.lsf_cells)
+    return entries, data
+
+
 def af_tree_maxabs_cc(tree: Tree, mg: mg_t, iv: int) -> float:
     """af_tree_maxabs_cc (afivo/src/m_af_utils.f90:773-785): max |cc| over leaves, interior cells."""
     v = C.c_double()

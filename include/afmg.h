@@ -174,6 +174,45 @@ typedef struct afmg_stencil_desc {
 int afmg_set_stencils(afmg_handle* h, int32_t n, const afmg_stencil_desc* desc, const double* coeff_blob,
                       int64_t blob_len);
 
+/* ---- host-side stencil builders: what mg_set_operators_lvl (m_af_multigrid.f90:1147-1185) stores in
+ * box%stencils, for hosts that are not the Fortran reference (include/afmg.hpp, afivo_streamer_b200/stencils.py).  The
+ * Fortran shim does not need them: it ships the stencils the reference itself built.  Pure host functions (no handle,
+ * no device, usable without a GPU); same expression order as the reference, results identical bit for bit.  Cell
+ * arrays: cc = (nc+2)^ndim doubles incl. ghost cells, per-cell outputs in IJK order (first index fastest).  Sizes and
+ * exact meaning: see afivo_streamer_b200/csrc/afmg_builders.inc. */
+/* mg%lsf: the level-set function (m_af_types.f90:667-722 mg_func_lsf), user = caller context */
+typedef double (*afmg_lsf_fn)(const double* r, void* user);
+enum { AFMG_LSF_DIST_LINEAR = 0, AFMG_LSF_DIST_GSS = 1 }; /* mg%lsf_dist => mg_lsf_dist_linear (:1627) / _gss (:1651) */
+typedef struct afmg_lsf_opts {
+  int32_t dist_method;
+  double gradient_safety_factor; /* mg%lsf_gradient_safety_factor = 1.5   (m_af_types.f90:607) */
+  double length_scale;           /* mg%lsf_length_scale = 1e100           (:610)               */
+  double tol;                    /* mg%lsf_tol = 1e-8                     (:613)               */
+  double min_rel_distance;       /* mg%lsf_min_rel_distance = 1e-4        (:616)               */
+} afmg_lsf_opts;
+void afmg_lsf_opts_default(afmg_lsf_opts* o);
+/* mg_set_box_tag (:1100-1145): returns the tag (>= 0) or AFMG_ERR_ARG; eps_cc may be NULL (no mg_i_eps) */
+int32_t afmg_build_box_tag(int32_t ndim, int32_t nc, const double* eps_cc, int32_t has_lsf);
+/* mg_store_operator_stencil (:823-859) of a box with iand(tag, operator_mask) /= mg_normal_box: mg_box_lpld_stencil
+ * (:1493-1532), mg_box_lsf_stencil (:1782-1854), mg_box_lpld_lsf_stencil (:1535-1623) */
+int afmg_build_box_operator(int32_t ndim, int32_t nc, int32_t coord_t, int32_t masked_tag, const double* dr,
+                            const double* r_min, const double* eps_cc, const double* lsf_dd, double* v, double* f,
+                            int32_t* stype, int32_t* has_f, int32_t* cylindrical_gradient);
+/* mg_store_prolongation_stencil (:862-903), variable cases: mg_box_prolong_eps_stencil (:1308-1388) or
+ * mg_box_prolong_lsf_stencil (:1392-1482) */
+int afmg_build_box_prolongation(int32_t ndim, int32_t nc, int32_t masked_tag, const int32_t* ix,
+                                const double* eps_parent_cc, const double* lsf_pdd, double* v, int32_t* stype,
+                                int32_t* shape);
+/* get_possible_lsf_root_mask + store_lsf_distance_matrix (:954-1097) with mg_lsf_dist_linear / _gss, bisection, gss
+ * and numerical_gradient (:1627-1776, :2164-2190) */
+int afmg_build_box_lsf_distances(int32_t ndim, int32_t nc, const double* r_min, const double* dr, afmg_lsf_fn lsf,
+                                 void* user, const afmg_lsf_opts* opts, const double* lsf_cc, uint8_t* root_mask,
+                                 double* dd, int32_t* n_boundary);
+/* the coarse-point distances mg_box_prolong_lsf_stencil evaluates (:1392-1482) */
+int afmg_build_box_lsf_prolong_distances(int32_t ndim, int32_t nc, const double* r_min, const double* dr,
+                                         const int32_t* ix, const double* r_min_p, const double* dr_p, afmg_lsf_fn lsf,
+                                         void* user, const afmg_lsf_opts* opts, const uint8_t* root_mask, double* pdd);
+
 /* ---- cell data: box%cc(:, :, :, iv) of n boxes, (nc+2)^ndim doubles each, packed in the order of
  * `box_id` (m_af_types.f90:302).  upload/download take host memory; the _device variants take
  * device memory (for callers that keep rhs / phi resident). */

@@ -1,0 +1,241 @@
+"""CPU: the library's host-side stencil builders (afmg_build_box_*, afivo_streamer_b200/stencils.py)
+against the oracle's restatement of the same reference routines, bit for bit, on the trees and coefficient fields of
+the GPU stencil suites -- so that what `build_stencils` hands to afmg_set_stencils is exactly what those suites ship --
+and against analytic answers for the level-set distance search (mg_lsf_dist_linear / _gss, the gradient search)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from afivo_streamer_b200 import _lib
+from afivo_streamer_b200 import mg as M
+from afivo_streamer_b200 import stencils as S
+from afivo_streamer_b200 import tree as T
+from afivo_streamer_b200 import workloads as W
+from oracle.oracle import Oracle
+
+import test_gpu_2d as G2
+import test_gpu_stencils as G3
+from util import all_ids, bc_mixed, stencils_from_oracle
+
+CASES = {}
+for name, (mk, kw) in G3.CASES.items():
+    CASES["3d_" + name] = (mk, kw, G3.lsf_distances, bc_mixed)
+for name, (mk, _bc, kw) in G2.CASES.items():
+    if "eps" in kw or "lsf" in kw:
+        CASES["2d_" + name] = (mk, kw, G2.lsf_distances2, _bc)
+
+
+def dense(tree, a):
+    """Per-box data of all_ids(tree) order -> array indexed by box id."""
+    ids = all_ids(tree)
+    out = np.zeros((tree.highest_id + 1,) + a.shape[1:])
+    out[ids] = a
+    return out
+
+
+def default_prolong(nd):
+    return (1, S.STENCIL_P248, np.array([9, 3, 3, 1]) / 16.0 if nd == 2 else np.array([27, 9, 9, 3, 9, 3, 3, 1]) / 64.0)
+
+
+def same_entries(tree, got, want):
+    assert [e["box_id"] for e in got] == [e["box_id"] for e in want]
+    for g, w in zip(got, want):
+        b = g["box_id"]
+        assert g["tag"] == w["tag"], b
+        assert g["op"][0] == w["op"][0], (b, "stype")
+        assert np.array_equal(np.asarray(g["op"][1]).reshape(-1), np.asarray(w["op"][1]).reshape(-1)), (b, "operator")
+        assert (g["f"] is None) == (w["f"] is None), (b, "f")
+        if g["f"] is not None:
+            assert np.array_equal(g["f"], w["f"]), (b, "f")
+        assert bool(g["cyl"]) == bool(w["cyl"]), (b, "cylindrical_gradient")
+        if "prolong" in w:
+            gp = g.get("prolong") or default_prolong(tree.ndim)
+            assert gp[0] == w["prolong"][0] and gp[1] == w["prolong"][1], (b, "prolongation kind", gp[:2], w["prolong"][:2])
+            assert np.array_equal(np.asarray(gp[2]).reshape(-1), np.asarray(w["prolong"][2]).reshape(-1)), (b, "prolongation")
+        else:
+            assert "prolong" not in g
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_builders_equal_the_oracle_bit_for_bit(name):
+    mk, kw, dist_fn, bc_fn = CASES[name]
+    kw = dict(kw)
+    tree = mk()
+    ids = all_ids(tree)
+    eps, lsf = kw.pop("eps", None), kw.pop("lsf", None)
+    custom = kw.pop("custom_prolong", False)
+    kw.pop("lsf_boundary_value", None)
+    orc = Oracle(tree, with_eps=eps is not None, **kw)
+    orc.set_bc(W.bc_table(tree, bc_fn))
+    eps_cc = lsf_data = None
+    if eps is not None:
+        e = eps(W.cell_centres(tree, ids, ghosts=True))
+        orc.set_cc(M.I_EPS, ids, e)
+        eps_cc = dense(tree, e)
+    if lsf is not None:
+        lids, dd = dist_fn(tree, lsf)
+        orc.set_lsf_distances(lids, dd)
+        pdd = None
+        if custom:
+            pids, p = G3.lsf_prolong_distances(tree, lsf)
+            orc.set_lsf_prolong_distances(pids, p)
+            pdd = {int(b): p[n].reshape(-1, tree.ndim + 1) for n, b in enumerate(pids)}
+        ncell = tree.nc ** tree.ndim
+        lsf_data = S.LsfData(np.asarray(lids, np.int32), dd.reshape(len(lids), ncell, 2 * tree.ndim),
+                             np.zeros((len(lids), ncell)), {}, pdd)
+    orc.mg_init()
+    want = stencils_from_oracle(tree, orc)
+    assert want
+    got, _ = S.build_stencils(tree, eps_cc=eps_cc, lsf_data=lsf_data, lsf_use_custom_prolongation=custom, **kw)
+    same_entries(tree, got, want)
+
+
+@pytest.mark.parametrize("nd", [2, 3])
+def test_linear_distances_equal_the_suites_own(nd):
+    """store_lsf_distance_matrix with mg_lsf_dist_linear through the callback interface == the vectorised numpy
+    statement the GPU suites use; every boundary cell lies inside the root mask."""
+    if nd == 3:
+        tree, lsf, ref = T.corner_refined_tree(3, 8, 8, 3), G3.lsf_sphere, G3.lsf_distances
+    else:
+        tree, lsf, ref = T.uniform_tree(2, 8, 8, 4), G2.lsf_circle, G2.lsf_distances2
+    data = S.lsf_distances(tree, lsf)
+    lids, dd = ref(tree, lsf)
+    assert np.array_equal(data.ids, lids)
+    want = dd.reshape(data.dd.shape)
+    assert np.max(np.abs(data.dd - want)) < 1e-12
+    for n, b in enumerate(data.ids):
+        assert np.all(data.root_mask[int(b)][np.any(data.dd[n] < 1, axis=1)] == 1)
+    # the built operator agrees with the one made from the suite's distances (up to the rounding of lsf itself)
+    got, _ = S.build_stencils(tree, lsf_data=data)
+    ref_data = S.LsfData(np.asarray(lids, np.int32), want, data.lsf_cells, {}, None)
+    exp, _ = S.build_stencils(tree, lsf_data=ref_data)
+    for g, e in zip(got, exp):
+        np.testing.assert_allclose(g["op"][1], e["op"][1], rtol=1e-9)
+        np.testing.assert_allclose(g["f"], e["f"], rtol=1e-9, atol=1e-6)
+
+
+def test_custom_prolongation_distances_give_the_suites_stencils():
+    tree = T.corner_refined_tree(3, 8, 8, 4)
+    data = S.lsf_distances(tree, G3.lsf_sphere, custom_prolongation=True)
+    got, _ = S.build_stencils(tree, lsf_data=data, lsf_use_custom_prolongation=True)
+    lids, dd = G3.lsf_distances(tree, G3.lsf_sphere)
+    pids, p = G3.lsf_prolong_distances(tree, G3.lsf_sphere)
+    ref = S.LsfData(np.asarray(lids, np.int32), dd.reshape(len(lids), 8 ** 3, 6), data.lsf_cells, {},
+                    {int(b): p[n].reshape(-1, 4) for n, b in enumerate(pids)})
+    exp, _ = S.build_stencils(tree, lsf_data=ref, lsf_use_custom_prolongation=True)
+    n_var = 0
+    for g, e in zip(got, exp):
+        gp, ep = g.get("prolong"), e.get("prolong")
+        assert (gp is None) == (ep is None), g["box_id"]
+        if gp is not None:
+            assert gp[:2] == ep[:2]
+            np.testing.assert_allclose(gp[2], ep[2], rtol=0, atol=1e-10)
+            n_var += gp[0] == 2
+    assert n_var > 0
+
+
+def box_distances(lsf, opts, nd=3, nc=4, r_min=(0.0, 0.0, 0.0), dr=0.25):
+    L = _lib.lib()
+    ncell = nc ** nd
+    cb = _lib.LSF_FN(lambda r, _u: float(lsf(np.array([r[d] for d in range(nd)]))))
+    mask = np.zeros(ncell, np.uint8)
+    dd = np.zeros((ncell, 2 * nd))
+    nb = C.c_int32(0)
+    rm = np.array(r_min[:nd], np.float64)
+    drv = np.full(nd, dr)
+    rc = L.afmg_build_box_lsf_distances(nd, nc, rm.ctypes.data_as(C.POINTER(C.c_double)),
+                                        drv.ctypes.data_as(C.POINTER(C.c_double)), cb, None, C.byref(opts), None,
+                                        mask.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                        dd.ctypes.data_as(C.POINTER(C.c_double)), C.byref(nb))
+    assert rc == 0
+    return mask, dd, nb.value
+
+
+def test_gss_distance_finds_the_surface_of_a_sphere():
+    """mg_lsf_dist_gss: relative distance from a cell centre to the sphere along each axis = the analytic
+    intersection, to lsf_tol; the linear method is only exact for a level set that is linear along the line."""
+    centre, R, dr, nc = np.array([0.5, 0.5, 0.5]), 0.3, 0.25, 4
+    lsf = lambda r: np.linalg.norm(r - centre) - R
+    _, dd, n = box_distances(lsf, S.lsf_opts(S.LSF_DIST_GSS), dr=dr)
+    assert n > 0
+    checked = 0
+    for cell in range(nc ** 3):
+        ijk = np.array([cell % nc, (cell // nc) % nc, cell // nc ** 2])
+        a = (ijk + 0.5) * dr
+        for m in range(6):
+            step = np.zeros(3)
+            step[m // 2] = dr if m % 2 else -dr
+            la, lb = lsf(a), lsf(a + step)
+            if la * lb < 0:  # one crossing: |a + t step - c| = R
+                u = step / dr
+                p = a - centre
+                bq, cq = 2 * p @ u, p @ p - R * R
+                roots = [(-bq + s * np.sqrt(bq * bq - 4 * cq)) / 2 for s in (-1, 1)]
+                t = min(r for r in roots if 0 <= r <= dr) / dr
+                assert abs(dd[cell, m] - max(t, 1e-4)) < 1e-7 / dr, (cell, m)
+                checked += 1
+            elif la > 0 and lb > 0:
+                pass  # may or may not graze the sphere: covered by the test below
+    assert checked > 10
+
+
+def test_gss_distance_sees_a_thin_electrode_the_linear_method_misses():
+    """Both end points outside (lsf_a * lsf_b > 0) with the electrode in between: golden-section search brackets
+    the minimum, bisection finds the first crossing; mg_lsf_dist_linear returns 1 (m_af_multigrid.f90:1651-1684)."""
+    dr, nc = 0.25, 4
+    x0, half = 0.5, 0.03  # slab |x - 0.5| < 0.03 between the cell centres 0.375 and 0.625
+    lsf = lambda r: abs(r[0] - x0) - half
+    _, lin, n_lin = box_distances(lsf, S.lsf_opts(S.LSF_DIST_LINEAR), dr=dr)
+    assert n_lin == 0 and np.all(lin == 1.0)
+    _, dd, n = box_distances(lsf, S.lsf_opts(S.LSF_DIST_GSS), dr=dr)
+    assert n == 2 * nc * nc
+    want = (x0 - half - 0.375) / dr
+    for cell in range(nc ** 3):
+        i = cell % nc
+        if i == 1:
+            assert abs(dd[cell, 1] - want) < 1e-6 and np.all(np.delete(dd[cell], 1) == 1.0)
+        elif i == 2:
+            assert abs(dd[cell, 0] - want) < 1e-6 and np.all(np.delete(dd[cell], 0) == 1.0)
+        else:
+            assert np.all(dd[cell] == 1.0)
+
+
+def test_gradient_search_finds_a_boundary_smaller_than_the_grid():
+    """store_lsf_distance_matrix :1044-1074: an electrode tip thinner than the cell spacing, between cell centres, is
+    found by walking down the gradient in steps of mg%lsf_length_scale; the distance is rescaled to the grid and
+    assigned to the closest direction."""
+    dr, nc = 0.25, 4
+    a = np.array([0.375, 0.375, 0.375])  # centre of cell (2, 2, 2)
+    centre = a + np.array([0.4 * dr, 0.0, 0.0])
+    R = 0.3 * dr
+    lsf = lambda r: np.linalg.norm(r - centre) - R
+    _, dd0, n0 = box_distances(lsf, S.lsf_opts(), dr=dr)
+    assert n0 == 0  # no sign change between any pair of neighbouring cell centres
+    _, dd, n = box_distances(lsf, S.lsf_opts(length_scale=dr / 8), dr=dr)
+    cell = 1 + nc * (1 + nc * 1)
+    assert n >= 1
+    assert abs(dd[cell, 1] - 0.1) < 1e-6, dd[cell]  # surface at 0.1 dr in +x
+    assert np.all(np.delete(dd[cell], 1) == 1.0)
+
+
+def test_tags_and_argument_checks():
+    L = _lib.lib()
+    one = np.ones(10 ** 3)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    assert L.afmg_build_box_tag(3, 8, None, 0) == 0
+    assert L.afmg_build_box_tag(3, 8, None, 1) == S.MG_LSF_BOX
+    assert L.afmg_build_box_tag(3, 8, dp(one), 0) == 0  # eps == 1: a normal box
+    assert L.afmg_build_box_tag(3, 8, dp(one * (1 + 5e-9)), 0) == 0  # within 1e-8 of one
+    assert L.afmg_build_box_tag(3, 8, dp(one * 2), 1) == S.MG_CEPS_BOX + S.MG_LSF_BOX
+    var = one.copy()
+    var[-1] = 1.5  # a ghost cell counts (minval / maxval over the whole array, :1131-1132)
+    assert L.afmg_build_box_tag(3, 8, dp(var), 0) == S.MG_VEPS_BOX
+    assert L.afmg_build_box_tag(1, 8, None, 0) == -1  # AFMG_ERR_ARG
+    st, hf, cy = C.c_int32(), C.c_int32(), C.c_int32()
+    v, f = np.zeros(7 * 512), np.zeros(512)
+    dr = np.full(3, 0.1)
+    assert L.afmg_build_box_operator(3, 8, 1, 0, dp(dr), None, None, None, dp(v), dp(f), C.byref(st), C.byref(hf),
+                                     C.byref(cy)) == -1  # a normal box has no explicit stencil
+    assert L.afmg_build_box_operator(3, 8, 1, S.MG_VEPS_BOX, dp(dr), None, None, None, dp(v), dp(f), C.byref(st),
+                                     C.byref(hf), C.byref(cy)) == -1  # eps missing
