@@ -241,6 +241,148 @@ inline void mg_update_operator_stencil(const af_t&, mg_t& mg) {
   mg.check(afmg_update_operator_stencil(mg.h), "afmg_update_operator_stencil");
 }
 
+// mg%lsf (m_af_types.f90:667-722, mg_func_lsf): level-set function of a point r(ndim)
+using lsf_t = std::function<double(const double* r)>;
+
+// The stencils of one tree as afmg_set_stencils takes them, plus the dense level-set distances
+struct stencil_set_t {
+  std::vector<afmg_stencil_desc> desc;
+  std::vector<double> blob;
+  std::vector<int32_t> lsf_ids;                   // boxes with mg_lsf_box
+  std::vector<std::vector<double>> lsf_dd;        // per such box: 2*ndim * nc^ndim relative distances
+  std::vector<std::vector<double>> lsf_cells;     // per such box: mg%lsf at the cell centres
+};
+
+// mg_set_operators_tree (m_af_multigrid.f90:1216-1225) for a tree with permittivity and / or a level-set function:
+// mg_set_box_tag (:1100-1145) with store_lsf_distance_matrix (:977-1097), mg_store_operator_stencil (:823-859),
+// mg_store_prolongation_stencil (:862-903), evaluated by the library's host-side builders (afmg_build_box_*).  No
+// device is needed.  eps_cc: nullptr or (highest_id + 1) * (nc+2)^ndim doubles, box id major, ghost cells filled.
+inline stencil_set_t mg_build_stencils(const af_t& tree, const mg_t& mg, const double* eps_cc, const lsf_t& lsf = nullptr,
+                                       const afmg_lsf_opts* lsf_opts = nullptr, bool lsf_use_custom_prolongation = false) {
+  stencil_set_t out;
+  const int nd = tree.ndim, nc = tree.n_cell;
+  size_t ncell = 1;
+  for (int d = 0; d < nd; ++d) ncell *= (size_t)nc;
+  const size_t blen = tree.box_len();
+  auto trampoline = [](const double* r, void* user) -> double { return (*static_cast<const lsf_t*>(user))(r); };
+  auto fail = [](int rc, const char* what) {
+    if (rc != AFMG_OK) throw error(rc, what);
+  };
+  auto put = [&out](const double* a, size_t n) {
+    const int64_t off = (int64_t)out.blob.size();
+    out.blob.insert(out.blob.end(), a, a + n);
+    return off;
+  };
+  std::vector<double> v((2 * nd + 1) * ncell), f(ncell), pv((nd + 1) * ncell), dd(2 * nd * ncell), pdd((nd + 1) * ncell);
+  std::vector<uint8_t> mask(ncell);
+  for (int l = 1; l <= tree.highest_lvl; ++l)
+    for (int32_t id : tree.lvl_ids[l]) {
+      const double* rmin = &tree.r_min[(size_t)id * nd];
+      const double* dr = &tree.dr[(size_t)id * nd];
+      const double* eps = eps_cc ? eps_cc + (size_t)id * blen : nullptr;
+      int32_t n_boundary = 0;
+      if (lsf)
+        fail(afmg_build_box_lsf_distances(nd, nc, rmin, dr, trampoline, (void*)&lsf, lsf_opts, nullptr, mask.data(),
+                                          dd.data(), &n_boundary), "afmg_build_box_lsf_distances");
+      const int32_t tag = afmg_build_box_tag(nd, nc, eps, n_boundary > 0);
+      if (tag < 0) throw error(tag, "afmg_build_box_tag");
+      if (n_boundary > 0) {
+        out.lsf_ids.push_back(id);
+        out.lsf_dd.push_back(dd);
+        std::vector<double> cells(ncell);
+        for (size_t c = 0; c < ncell; ++c) {
+          int ijk[3] = {(int)(c % nc) + 1, (int)((c / nc) % nc) + 1, (int)(c / ((size_t)nc * nc)) + 1};
+          double r[3];
+          tree.r_cc(id, ijk, r);
+          cells[c] = lsf(r);
+        }
+        out.lsf_cells.push_back(std::move(cells));
+      }
+      if (tag == 0) continue;
+      const int32_t masked = tag & mg.operator_mask;
+      afmg_stencil_desc d{};
+      d.box_id = id;
+      d.tag = tag;
+      d.f_offset = -1;
+      if (masked != 0) {
+        int32_t stype = 0, has_f = 0, cyl = 0;
+        fail(afmg_build_box_operator(nd, nc, tree.coord_t, masked, dr, rmin, eps, dd.data(), v.data(), f.data(), &stype,
+                                     &has_f, &cyl), "afmg_build_box_operator");
+        d.op_stype = stype;
+        d.cylindrical_gradient = cyl;
+        d.op_offset = put(v.data(), stype == 1 ? (size_t)(2 * nd + 1) : v.size());
+        if (has_f) d.f_offset = put(f.data(), ncell);
+      }
+      if (l > 1 && mg.prolongation_type == AFMG_PROLONG_AUTO) {
+        const bool veps = masked & AFMG_TAG_VEPS_BOX;
+        const bool vlsf = !veps && (masked & AFMG_TAG_LSF_BOX) && lsf_use_custom_prolongation;
+        if (veps || vlsf) {
+          const int32_t p = tree.parent[id];
+          if (vlsf)
+            fail(afmg_build_box_lsf_prolong_distances(nd, nc, rmin, dr, &tree.ix[(size_t)id * nd],
+                                                      &tree.r_min[(size_t)p * nd], &tree.dr[(size_t)p * nd], trampoline,
+                                                      (void*)&lsf, lsf_opts, mask.data(), pdd.data()),
+                 "afmg_build_box_lsf_prolong_distances");
+          int32_t pst = 0, psh = 0;
+          fail(afmg_build_box_prolongation(nd, nc, masked, &tree.ix[(size_t)id * nd],
+                                           veps ? eps_cc + (size_t)p * blen : nullptr, vlsf ? pdd.data() : nullptr,
+                                           pv.data(), &pst, &psh), "afmg_build_box_prolongation");
+          d.prolong_stype = pst;
+          d.prolong_shape = psh;
+          d.prolong_offset = put(pv.data(), pst == 1 ? (size_t)(nd + 1) : pv.size());
+        }
+      }
+      out.desc.push_back(d);
+    }
+  return out;
+}
+
+// Build (mg_build_stencils) and ship: stencils, permittivity (AFMG_EPS) and level-set distances
+inline stencil_set_t mg_set_operators_tree(const af_t& tree, mg_t& mg, const double* eps_cc, const lsf_t& lsf = nullptr,
+                                           const afmg_lsf_opts* lsf_opts = nullptr,
+                                           bool lsf_use_custom_prolongation = false) {
+  mg.need_init();
+  stencil_set_t st = mg_build_stencils(tree, mg, eps_cc, lsf, lsf_opts, lsf_use_custom_prolongation);
+  const double zero = 0.0;
+  mg.check(afmg_set_stencils(mg.h, (int32_t)st.desc.size(), st.desc.data(), st.blob.empty() ? &zero : st.blob.data(),
+                             (int64_t)st.blob.size()), "afmg_set_stencils");
+  const int nd = tree.ndim, nc = tree.n_cell;
+  if (eps_cc) {
+    const std::vector<int32_t> ids = tree.ids(false);
+    std::vector<double> packed(ids.size() * tree.box_len());
+    for (size_t n = 0; n < ids.size(); ++n)
+      std::copy(eps_cc + (size_t)ids[n] * tree.box_len(), eps_cc + (size_t)(ids[n] + 1) * tree.box_len(),
+                packed.begin() + n * tree.box_len());
+    mg.set_cc(AFMG_EPS, ids, packed.data());
+  }
+  if (!st.lsf_ids.empty()) {  // the sparse form of the distance stencils (store_lsf_distance_matrix :1075-1094)
+    std::vector<int32_t> n_entries, cell_ix;
+    std::vector<double> dd, lv;
+    for (size_t b = 0; b < st.lsf_ids.size(); ++b) {
+      int32_t n = 0;
+      const size_t ncell = st.lsf_cells[b].size();
+      for (size_t c = 0; c < ncell; ++c) {
+        const double* q = &st.lsf_dd[b][c * 2 * nd];
+        bool any = false;
+        for (int m = 0; m < 2 * nd; ++m) any = any || q[m] < 1.0;
+        if (!any) continue;
+        ++n;
+        size_t r = c;
+        for (int d = 0; d < nd; ++d) {
+          cell_ix.push_back((int32_t)(r % nc) + 1);
+          r /= nc;
+        }
+        dd.insert(dd.end(), q, q + 2 * nd);
+        lv.push_back(st.lsf_cells[b][c]);
+      }
+      n_entries.push_back(n);
+    }
+    mg.check(afmg_set_lsf_distances(mg.h, (int32_t)st.lsf_ids.size(), st.lsf_ids.data(), n_entries.data(), cell_ix.data(),
+                                    dd.data(), lv.data()), "afmg_set_lsf_distances");
+  }
+  return st;
+}
+
 // af_tree_maxabs_cc (m_af_utils.f90:773-785): max |cc| over the interior of the leaves
 inline double af_tree_maxabs_cc(const af_t&, mg_t& mg, int var) {
   mg.need_init();

@@ -60,3 +60,65 @@ def test_cpp_tree_matches_python_builder(dump_exe, name):
     fc = W.face_coords(t, ids, 3)  # af_get_face_coords on the low-y side
     assert np.array_equal(geo[:, 6:9], fc[:, 0, :]) and np.array_equal(geo[:, 9:12], fc[:, -1, :])
     assert lines[-1] in ("device present", "error -2")  # AFMG_ERR_CUDA without a GPU: no CPU fallback
+
+
+@pytest.fixture(scope="module")
+def stencil_exe(tmp_path_factory):
+    lib_dir = os.path.join(ROOT, "afivo_streamer_b200")
+    exe = str(tmp_path_factory.mktemp("cpp") / "cpp_stencil_dump")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp_stencil_dump.cpp"), "-o", exe, "-L", lib_dir, "-lafmg",
+                           "-Wl,-rpath," + lib_dir])
+    return exe
+
+
+@pytest.mark.parametrize("custom,method", [(0, 0), (1, 0), (0, 1)])
+def test_cpp_stencil_builder_matches_python_mirror(stencil_exe, tmp_path, custom, method):
+    """afmg::mg_build_stencils (C++ mirror) == stencils.build_stencils (Python mirror): same tags, kinds and
+    coefficients for a refined tree with variable permittivity and a spherical electrode; both only walk the tree, the
+    arithmetic is the library's (afmg_build_box_*)."""
+    from afivo_streamer_b200 import stencils as S
+    from afivo_streamer_b200 import workloads as W
+    out_bin = str(tmp_path / "st.bin")
+    out = subprocess.run([stencil_exe, out_bin, str(custom), str(method)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    n_desc, n_blob, n_lsf = map(int, lines[0].split())
+    desc = [list(map(int, ln.split()[1:])) for ln in lines[1:1 + n_desc]]
+    lsf_ids = [int(ln.split()[1]) for ln in lines[1 + n_desc:1 + n_desc + n_lsf]]
+    raw = np.fromfile(out_bin)
+    blob, rest = raw[:n_blob], raw[n_blob:]
+
+    t = T.corner_refined_tree(3, 8, 8, 4)
+    ids = np.concatenate(t.lvl_ids).astype(np.int32)
+    r = W.cell_centres(t, ids, ghosts=True)
+    eps_cc = np.ones((t.highest_id + 1,) + r.shape[1:-1])
+    eps_cc[ids] = 1.0 + 0.5 * (r[..., 0] * r[..., 1]) + 0.25 * r[..., 2]
+
+    def lsf(p):
+        dx, dy, dz = p[0] - 0.2, p[1] - 0.25, p[2] - 0.15
+        return np.sqrt(dx * dx + dy * dy + dz * dz) - 0.11
+
+    entries, data = S.build_stencils(t, eps_cc=eps_cc, lsf=lsf, lsf_options=S.lsf_opts(method),
+                                     lsf_use_custom_prolongation=bool(custom))
+    assert n_desc == len(entries) and n_lsf == len(data.ids) and lsf_ids == list(map(int, data.ids))
+    assert any(e["tag"] & 1 for e in entries) and any(e["tag"] & 2 for e in entries)
+    ncell = 8 ** 3
+    for d, e in zip(desc, entries):
+        box_id, tag, op_stype, cyl, pst, psh, op_off, f_off, p_off = d
+        assert (box_id, tag, op_stype, bool(cyl)) == (e["box_id"], e["tag"], e["op"][0], e["cyl"])
+        n_op = 7 if op_stype == 1 else 7 * ncell
+        assert np.array_equal(blob[op_off:op_off + n_op], np.asarray(e["op"][1]).reshape(-1)), box_id
+        assert (f_off >= 0) == (e["f"] is not None)
+        if f_off >= 0:
+            assert np.array_equal(blob[f_off:f_off + ncell], e["f"])
+        if e.get("prolong") is None:
+            assert psh == 0
+        else:
+            assert (pst, psh) == e["prolong"][:2]
+            n_p = 4 if pst == 1 else 4 * ncell
+            assert np.array_equal(blob[p_off:p_off + n_p], np.asarray(e["prolong"][2]).reshape(-1)), box_id
+    per = 6 * ncell + ncell
+    for n in range(n_lsf):
+        assert np.array_equal(rest[n * per:n * per + 6 * ncell], data.dd[n].reshape(-1))
+        assert np.array_equal(rest[n * per + 6 * ncell:(n + 1) * per], data.lsf_cells[n])
