@@ -52,6 +52,18 @@ class LsfOpts(C.Structure):
 LSF_FN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_void_p)  # afmg_lsf_fn
 
 
+class Electrode(C.Structure):
+    """afmg_electrode: the built-in electrode shapes of src/m_field.f90:254-362."""
+    _fields_ = [("type", C.c_int32), ("ndim", C.c_int32), ("electrode_grounded", C.c_int32),
+                ("electrode2_grounded", C.c_int32), ("current_voltage", C.c_double),
+                ("rod_r0", C.c_double * 3), ("rod_r1", C.c_double * 3), ("rod_radius", C.c_double),
+                ("cone_tip_radius", C.c_double), ("cone_length_frac", C.c_double),
+                ("rod2_r0", C.c_double * 3), ("rod2_r1", C.c_double * 3), ("rod2_radius", C.c_double),
+                ("cone2_tip_radius", C.c_double), ("cone2_length_frac", C.c_double), ("domain_center", C.c_double * 3),
+                ("cone_tip_center", C.c_double * 3), ("cone_tip_r_curvature", C.c_double),
+                ("cone2_tip_center", C.c_double * 3), ("cone2_tip_r_curvature", C.c_double)]
+
+
 class TreeDesc(C.Structure):
     _fields_ = [
         ("highest_lvl", C.c_int32), ("highest_id", C.c_int32), ("lvl_counts", C.POINTER(C.c_int32)),
@@ -125,6 +137,9 @@ SYMBOLS = {
     "afmg_owner_of_box": (C.c_int32, [_H, _I]),
     "afmg_partition": (C.c_int, [_I, _I, _IP, _IP]),
     "afmg_lsf_opts_default": (None, [C.POINTER(LsfOpts)]),
+    "afmg_electrode_prepare": (C.c_int, [C.POINTER(Electrode)]),
+    "afmg_electrode_lsf": (C.c_double, [_DP, C.c_void_p]),
+    "afmg_electrode_potential": (C.c_double, [_DP, C.c_void_p]),
     "afmg_build_box_tag": (C.c_int32, [_I, _I, _DP, _I]),
     "afmg_build_box_operator": (C.c_int, [_I, _I, _I, _I, _DP, _DP, _DP, _DP, _DP, _DP, _IP, _IP, _IP]),
     "afmg_build_box_prolongation": (C.c_int, [_I, _I, _I, _IP, _DP, _DP, _DP, _IP, _IP]),

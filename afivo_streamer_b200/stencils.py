@@ -56,6 +56,58 @@ def lsf_opts(dist_method=LSF_DIST_LINEAR, **kw) -> _lib.LsfOpts:
     return o
 
 
+ELECTRODE_TYPES = {"sphere": 1, "rod": 2, "rod_cone_top": 3, "rod_rod": 4, "sphere_rod": 5,
+                   "two_rod_cone_electrodes": 6, "coaxial": 7}  # field_electrode_type, src/m_field.f90:254-362
+
+
+def electrode(kind: str, ndim: int, **params) -> _lib.Electrode:
+    """One of the streamer code's built-in electrode shapes (src/m_field.f90:686-904) as a C-side level-set function:
+    pass the result as `lsf` to lsf_distances / build_stencils / mg_set_operators_tree.  params: rod_r0, rod_r1,
+    rod_radius, cone_tip_radius, cone_length_frac, rod2_*, cone2_*, domain_center, current_voltage,
+    electrode_grounded, electrode2_grounded.  Raises AFMG_ERR_ARG where the reference would `error stop`."""
+    e = _lib.Electrode()
+    e.type, e.ndim = ELECTRODE_TYPES[kind], ndim
+    for k, v in params.items():
+        if not hasattr(e, k) or k in ("type", "ndim", "cone_tip_center", "cone2_tip_center", "cone_tip_r_curvature",
+                                      "cone2_tip_r_curvature"):  # the last four are derived by afmg_electrode_prepare
+            raise TypeError(f"unknown electrode parameter {k}")
+        if isinstance(getattr(e, k), C.Array):
+            for d, x in enumerate(v):
+                getattr(e, k)[d] = float(x)
+        else:
+            setattr(e, k, v)
+    _check(_lib.lib().afmg_electrode_prepare(C.byref(e)), "afmg_electrode_prepare")
+    return e
+
+
+def _callback(lsf, nd):
+    """(afmg_lsf_fn, user pointer, python callable of one point) for a Python function or a built-in electrode."""
+    L = _lib.lib()
+    if isinstance(lsf, _lib.Electrode):
+        user = C.cast(C.pointer(lsf), C.c_void_p)
+
+        def point(r):
+            a = (C.c_double * 3)(*[float(x) for x in r], *([0.0] * (3 - len(r))))
+            return L.afmg_electrode_lsf(a, user)
+
+        return C.cast(L.afmg_electrode_lsf, _lib.LSF_FN), user, point
+    return _lib.LSF_FN(lambda r, _u: float(lsf(np.array([r[d] for d in range(nd)])))), None, lsf
+
+
+def electrode_potential(el: _lib.Electrode, points: np.ndarray) -> np.ndarray:
+    """mg%lsf_boundary_function at the given points (..., ndim) -- the values afmg_set_lsf_boundary_values takes."""
+    L = _lib.lib()
+    pts = np.asarray(points, np.float64)
+    out = np.empty(pts.shape[:-1])
+    user = C.cast(C.pointer(el), C.c_void_p)
+    flat = pts.reshape(-1, pts.shape[-1])
+    res = out.reshape(-1)
+    for n, r in enumerate(flat):
+        a = (C.c_double * 3)(*r, *([0.0] * (3 - len(r))))
+        res[n] = L.afmg_electrode_potential(a, user)
+    return out
+
+
 def _check(rc, what):
     if rc != 0:
         raise _lib.AfmgError(rc, what)
@@ -69,7 +121,7 @@ def lsf_distances(tree: Tree, lsf: Callable[[np.ndarray], float], opts: Optional
     nd, nc = tree.ndim, tree.nc
     ncell = nc ** nd
     opts = opts or lsf_opts()
-    cb = _lib.LSF_FN(lambda r, _u: float(lsf(np.array([r[d] for d in range(nd)]))))
+    cb, user, lsf = _callback(lsf, nd)
     ids, dds, vals, masks, pdds = [], [], [], {}, {}
     for lvl_ids in tree.lvl_ids:
         for b in lvl_ids:
@@ -79,7 +131,7 @@ def lsf_distances(tree: Tree, lsf: Callable[[np.ndarray], float], opts: Optional
             mask = np.zeros(ncell, np.uint8)
             dd = np.empty((ncell, 2 * nd))
             nb = C.c_int32(0)
-            _check(L.afmg_build_box_lsf_distances(nd, nc, _dp(rmin), _dp(dr), cb, None, C.byref(opts), None,
+            _check(L.afmg_build_box_lsf_distances(nd, nc, _dp(rmin), _dp(dr), cb, user, C.byref(opts), None,
                                                   mask.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(dd), C.byref(nb)),
                    "afmg_build_box_lsf_distances")
             if mask.any():
@@ -97,7 +149,7 @@ def lsf_distances(tree: Tree, lsf: Callable[[np.ndarray], float], opts: Optional
                 ix = np.ascontiguousarray(tree.ix[b], np.int32)
                 _check(L.afmg_build_box_lsf_prolong_distances(
                     nd, nc, _dp(rmin), _dp(dr), _ip(ix), _dp(np.ascontiguousarray(tree.r_min[p], np.float64)),
-                    _dp(np.ascontiguousarray(tree.dr[p], np.float64)), cb, None, C.byref(opts),
+                    _dp(np.ascontiguousarray(tree.dr[p], np.float64)), cb, user, C.byref(opts),
                     mask.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(pdd)), "afmg_build_box_lsf_prolong_distances")
                 pdds[b] = pdd
     if not ids:

@@ -213,6 +213,37 @@ int afmg_build_box_lsf_prolong_distances(int32_t ndim, int32_t nc, const double*
                                          const int32_t* ix, const double* r_min_p, const double* dr_p, afmg_lsf_fn lsf,
                                          void* user, const afmg_lsf_opts* opts, const uint8_t* root_mask, double* pdd);
 
+/* The built-in electrode shapes of the streamer code (field_electrode_type, src/m_field.f90:254-362; level-set
+ * functions :686-904 on GM_dist_vec_line, src/m_geometry.f90:23-51) as afmg_lsf_fn-compatible host functions, so that
+ * the distance search above runs without a callback into the host language.  Fill the parameters the shape uses (the
+ * reference's field_rod_r0, field_rod_r1, field_rod_radius, cone_tip_radius, cone_length_frac, the same for rod2;
+ * domain_center(1:2) for coaxial), call afmg_electrode_prepare (argument checks = the reference's error stops; derived
+ * cone parameters, get_conical_rod_properties :698-719), then pass afmg_electrode_lsf with user = the struct.
+ * afmg_electrode_potential is mg%lsf_boundary_function (*_get_potential), or the scalar mg%lsf_boundary_value of the
+ * single-electrode shapes (:482-487). */
+enum {
+  AFMG_ELECTRODE_SPHERE = 1,
+  AFMG_ELECTRODE_ROD = 2,
+  AFMG_ELECTRODE_ROD_CONE_TOP = 3,
+  AFMG_ELECTRODE_ROD_ROD = 4,
+  AFMG_ELECTRODE_SPHERE_ROD = 5,
+  AFMG_ELECTRODE_TWO_ROD_CONE = 6,
+  AFMG_ELECTRODE_COAXIAL = 7
+};
+typedef struct afmg_electrode {
+  int32_t type, ndim;
+  int32_t electrode_grounded, electrode2_grounded;
+  double current_voltage;
+  double rod_r0[3], rod_r1[3], rod_radius, cone_tip_radius, cone_length_frac;
+  double rod2_r0[3], rod2_r1[3], rod2_radius, cone2_tip_radius, cone2_length_frac;
+  double domain_center[3];
+  /* derived by afmg_electrode_prepare */
+  double cone_tip_center[3], cone_tip_r_curvature, cone2_tip_center[3], cone2_tip_r_curvature;
+} afmg_electrode;
+int afmg_electrode_prepare(afmg_electrode* e);
+double afmg_electrode_lsf(const double* r, void* electrode);
+double afmg_electrode_potential(const double* r, void* electrode);
+
 /* ---- cell data: box%cc(:, :, :, iv) of n boxes, (nc+2)^ndim doubles each, packed in the order of
  * `box_id` (m_af_types.f90:302).  upload/download take host memory; the _device variants take
  * device memory (for callers that keep rhs / phi resident). */

@@ -244,6 +244,16 @@ inline void mg_update_operator_stencil(const af_t&, mg_t& mg) {
 // mg%lsf (m_af_types.f90:667-722, mg_func_lsf): level-set function of a point r(ndim)
 using lsf_t = std::function<double(const double* r)>;
 
+// one of the built-in electrode shapes (afmg_electrode, src/m_field.f90:254-362) as mg%lsf / mg%lsf_boundary_function;
+// the struct must outlive the returned function
+inline lsf_t electrode_lsf(afmg_electrode& e) {
+  if (afmg_electrode_prepare(&e) != AFMG_OK) throw error(AFMG_ERR_ARG, "afmg_electrode_prepare: invalid electrode parameters");
+  return [&e](const double* r) { return afmg_electrode_lsf(r, &e); };
+}
+inline lsf_t electrode_potential(afmg_electrode& e) {
+  return [&e](const double* r) { return afmg_electrode_potential(r, &e); };
+}
+
 // The stencils of one tree as afmg_set_stencils takes them, plus the dense level-set distances
 struct stencil_set_t {
   std::vector<afmg_stencil_desc> desc;

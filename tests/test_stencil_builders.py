@@ -239,3 +239,100 @@ def test_tags_and_argument_checks():
                                      C.byref(cy)) == -1  # a normal box has no explicit stencil
     assert L.afmg_build_box_operator(3, 8, 1, S.MG_VEPS_BOX, dp(dr), None, None, None, dp(v), dp(f), C.byref(st),
                                      C.byref(hf), C.byref(cy)) == -1  # eps missing
+
+
+# ---- the built-in electrode shapes (src/m_field.f90:686-904) ------------------------------------------------------
+
+def test_rod_and_sphere_level_sets_are_signed_distances():
+    rod = S.electrode("rod", 3, rod_r0=(0.5, 0.5, 0.0), rod_r1=(0.5, 0.5, 0.4), rod_radius=0.05)
+    _, _, f = S._callback(rod, 3)
+    assert abs(f([0.5, 0.7, 0.2]) - (0.2 - 0.05)) < 1e-15          # beside the rod: distance to the axis - radius
+    assert abs(f([0.5, 0.5, 0.6]) - (0.2 - 0.05)) < 1e-15          # beyond the end: the semi-spherical cap
+    assert abs(f([0.5, 0.5, 0.1]) + 0.05) < 1e-15                  # on the axis
+    q = np.array([0.5 + 0.03, 0.5 + 0.04, 0.4 + 0.12])             # off-axis beyond the end: distance to r1
+    assert abs(f(q) - (np.sqrt(0.03 ** 2 + 0.04 ** 2 + 0.12 ** 2) - 0.05)) < 1e-15
+    sph = S.electrode("sphere", 2, rod_r0=(0.3, 0.4), rod_radius=0.1)
+    _, _, g = S._callback(sph, 2)
+    assert abs(g([0.6, 0.8]) - 0.4) < 1e-15
+
+
+def test_conical_rod_surface_is_continuous_and_its_tip_sphere_touches_the_cone():
+    """get_conical_rod_properties (:698-719): the tip sphere passes through the circle of radius tip_radius at the end
+    of the cone; the surface of conical_rod_lsf_arg (:722-749) is continuous where cylinder, cone and tip meet."""
+    r0, r1, R, rt, frac = np.array([0.5, 0.5, 0.0]), np.array([0.5, 0.5, 0.5]), 0.06, 0.02, 0.3
+    el = S.electrode("rod_cone_top", 3, rod_r0=r0, rod_r1=r1, rod_radius=R, cone_tip_radius=rt, cone_length_frac=frac)
+    _, _, f = S._callback(el, 3)
+    angle = np.arctan((R - rt) / (frac * 0.5))
+    assert abs(el.cone_tip_r_curvature - rt / np.cos(angle)) < 1e-15
+    assert abs(el.cone_tip_center[2] - (0.5 - np.sin(angle) * rt / np.cos(angle))) < 1e-15
+    # surface points: on the cylinder, at the cylinder / cone junction, half-way up the cone, on the rim of the tip
+    for z, rad in ((0.1, R), (0.5 * (1 - frac), R), (0.5 * (1 - frac / 2), (R + rt) / 2), (0.5 - 1e-12, rt)):
+        assert abs(f([0.5 + rad, 0.5, z])) < 1e-10, (z, rad)
+    assert abs(f([0.5 + rt, 0.5, 0.5])) < 1e-12                     # the rim, evaluated by the spherical branch
+    # away from the surface the reference's piecewise function jumps across frac = 1 (cone: distance to the axis minus
+    # the local radius; tip: distance to the tip sphere); only the zero level set matters and that one is continuous
+    assert abs(f([0.53, 0.5, 0.5 - 1e-9]) - 0.01) < 1e-8
+    assert abs(f([0.53, 0.5, 0.5]) - (np.hypot(0.03, 0.5 - el.cone_tip_center[2]) - el.cone_tip_r_curvature)) < 1e-15
+    assert abs(f([0.5, 0.5, 0.7]) - (0.7 - el.cone_tip_center[2] - el.cone_tip_r_curvature)) < 1e-15
+
+
+def test_two_electrode_shapes_pick_the_nearest_for_the_potential():
+    el = S.electrode("rod_rod", 3, rod_r0=(0.5, 0.5, 0.0), rod_r1=(0.5, 0.5, 0.3), rod_radius=0.05,
+                     rod2_r0=(0.5, 0.5, 1.0), rod2_r1=(0.5, 0.5, 0.7), rod2_radius=0.04, current_voltage=2.5,
+                     electrode2_grounded=1)
+    _, _, f = S._callback(el, 3)
+    assert abs(f([0.5, 0.5, 0.45]) - 0.10) < 1e-15 and abs(f([0.5, 0.5, 0.6]) - 0.06) < 1e-15
+    pot = S.electrode_potential(el, np.array([[0.5, 0.5, 0.35], [0.5, 0.5, 0.65], [0.2, 0.5, 0.1]]))
+    assert list(pot) == [2.5, 0.0, 2.5]
+    sr = S.electrode("sphere_rod", 3, rod_r0=(0.5, 0.5, 0.2), rod_radius=0.1, rod2_r0=(0.5, 0.5, 1.0),
+                     rod2_r1=(0.5, 0.5, 0.8), rod2_radius=0.05, current_voltage=-1.0, electrode_grounded=1)
+    assert list(S.electrode_potential(sr, np.array([[0.5, 0.5, 0.35], [0.5, 0.5, 0.7]]))) == [0.0, -1.0]
+    two = S.electrode("two_rod_cone_electrodes", 3, rod_r0=(0.5, 0.5, 0.0), rod_r1=(0.5, 0.5, 0.3), rod_radius=0.05,
+                      cone_tip_radius=0.02, cone_length_frac=0.5, rod2_r0=(0.5, 0.5, 1.0), rod2_r1=(0.5, 0.5, 0.7),
+                      rod2_radius=0.05, cone2_tip_radius=0.02, cone2_length_frac=0.5, current_voltage=1.0,
+                      electrode2_grounded=1)
+    _, _, g = S._callback(two, 3)
+    assert abs(g([0.5, 0.5, 0.4]) - g([0.5, 0.5, 0.6])) < 1e-15     # mirror-symmetric pair
+    assert list(S.electrode_potential(two, np.array([[0.5, 0.5, 0.4], [0.5, 0.5, 0.6]]))) == [1.0, 0.0]
+    co = S.electrode("coaxial", 3, rod_radius=0.1, rod2_radius=0.45, domain_center=(0.5, 0.5, 0.5), current_voltage=3.0)
+    _, _, h = S._callback(co, 3)
+    assert abs(h([0.7, 0.5, 0.9]) - 0.1) < 1e-15 and abs(h([0.9, 0.5, 0.1]) - 0.05) < 1e-15
+    assert list(S.electrode_potential(co, np.array([[0.62, 0.5, 0.3], [0.93, 0.5, 0.3]]))) == [3.0, 0.0]
+
+
+def test_electrode_parameter_checks_are_the_references_error_stops():
+    with pytest.raises(_lib.AfmgError):
+        S.electrode("rod", 3, rod_r0=(0, 0, 0), rod_r1=(0, 0, 1), rod_radius=0.0)
+    with pytest.raises(_lib.AfmgError):  # cone tip radius larger than the rod radius (:271-272)
+        S.electrode("rod_cone_top", 3, rod_r0=(0, 0, 0), rod_r1=(0, 0, 1), rod_radius=0.1, cone_tip_radius=0.2,
+                    cone_length_frac=0.5)
+    with pytest.raises(_lib.AfmgError):
+        S.electrode("rod_rod", 3, rod_r0=(0, 0, 0), rod_r1=(0, 0, 1), rod_radius=0.1)  # rod2_radius missing
+    with pytest.raises(TypeError):
+        S.electrode("rod", 3, cone_tip_center=(0, 0, 0))
+
+
+def test_builtin_electrode_gives_the_same_stencils_as_the_equivalent_python_function():
+    """The C-side level-set function goes through the same distance search as a Python callback."""
+    tree = T.corner_refined_tree(3, 8, 8, 3)
+    r0, r1, R = np.array([0.2, 0.25, 0.0]), np.array([0.2, 0.25, 0.3]), 0.07
+    el = S.electrode("rod", 3, rod_r0=r0, rod_r1=r1, rod_radius=R)
+
+    def rod(r):
+        h = r1 - r0
+        f = np.dot(r - r0, h)
+        if f <= 0:
+            v = r - r0
+        elif f >= np.dot(h, h):
+            v = r - r1
+        else:
+            v = r - (r0 + f / np.dot(h, h) * h)
+        return np.sqrt(np.sum(v * v)) - R
+
+    a, da = S.build_stencils(tree, lsf=el, lsf_options=S.lsf_opts(S.LSF_DIST_GSS))
+    b, db = S.build_stencils(tree, lsf=rod, lsf_options=S.lsf_opts(S.LSF_DIST_GSS))
+    assert len(a) == len(b) > 0 and np.array_equal(da.ids, db.ids)
+    np.testing.assert_allclose(da.dd, db.dd, rtol=0, atol=1e-9)
+    for x, y in zip(a, b):
+        assert x["box_id"] == y["box_id"] and x["tag"] == y["tag"]
+        np.testing.assert_allclose(x["op"][1], y["op"][1], rtol=1e-6)
