@@ -263,3 +263,98 @@ def test_helmholtz_with_neumann_everywhere_has_the_constant_solution():
     phi = o.get_cc(I_PHI, all_ids)
     assert np.max(np.abs(phi + f / lam)) < 1e-13, np.max(np.abs(phi + f / lam))
     assert o.maxabs(I_TMP) < 1e-11
+
+
+def _neumann_tree(ndim, coord_t=T.AF_XYZ):
+    """afivo/examples/poisson_neumann.f90:88-97: refine while lvl <= 4 and all(r_min < 0.25)."""
+    nc = 8
+    dr1 = 1.0 / nc
+
+    def refine(l, ixs, ctr):
+        rmin = (ixs - 1) * (nc * dr1 / 2 ** (l - 1))
+        return (l <= 4) & np.all(rmin < 0.25, axis=1)
+
+    return T.build_tree(ndim, nc, [nc] * ndim, 5, refine, coord_t=coord_t)
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_poisson_neumann_linear_solution_is_reproduced_exactly(ndim):
+    """afivo/examples/poisson_neumann.f90 (Cartesian): rhs = 0, Dirichlet 0 at low x, Neumann 1 at high x, Neumann 0
+    elsewhere -> phi = x.  A linear potential is exact for the 2nd-order operator, the Neumann / Dirichlet ghost
+    cells and the refinement-boundary interpolation, so the multigrid converges to it up to rounding."""
+    t = _neumann_tree(ndim)
+    assert t.highest_lvl == 5
+
+    def sides(nb, c):
+        if nb == 1:
+            return W.AF_BC_DIRICHLET, 0.0
+        return W.AF_BC_NEUMANN, 1.0 if nb == 2 else 0.0
+
+    o = Oracle(t)
+    o.set_bc(W.bc_table(t, sides))
+    o.mg_init()
+    leaves = np.concatenate([t.leaves(l) for l in range(1, t.highest_lvl + 1)]).astype(np.int32)
+    x = W.cell_centres(t, leaves, ghosts=True)[..., 0]
+    err = []
+    for it in range(10):
+        o.fas_fmg(True, it > 0)
+        phi = o.get_cc(I_PHI, leaves).reshape(x.shape)
+        err.append(np.max(np.abs(phi - x)[W.interior(t)]))
+    assert err[-1] < 1e-12, err
+    assert o.maxabs(I_TMP) < 1e-9
+
+
+def test_poisson_neumann_cylindrical_r_squared():
+    """afivo/examples/poisson_neumann.f90 with cylindrical = T: rhs = 4, zero flux on the axis, d(phi)/dr = 2 at
+    r = 1, Dirichlet r^2 in z -> phi = r^2.  Operator and Neumann ghost cells (central difference of a quadratic) are
+    exact for r^2, so a uniform grid reproduces it to rounding; on the example's corner-refined tree only the linear
+    refinement-boundary interpolation is inexact and the error stays at the 1e-4 level."""
+    def sides(nb, c):
+        if nb == 1:
+            return W.AF_BC_NEUMANN, 0.0
+        if nb == 2:
+            return W.AF_BC_NEUMANN, 2.0
+        return W.AF_BC_DIRICHLET, c[..., 0] ** 2
+
+    errs = []
+    for t in (T.build_tree(2, 8, [8, 8], 4, None, coord_t=T.AF_CYL), _neumann_tree(2, T.AF_CYL)):
+        o = Oracle(t)
+        o.set_bc(W.bc_table(t, sides))
+        o.mg_init()
+        ids, rhs = W.constant_rhs_on_leaves(t, 4.0)
+        o.set_cc(I_RHS, ids, rhs)
+        for it in range(10):
+            o.fas_fmg(True, it > 0)
+        r = W.cell_centres(t, ids, ghosts=True)[..., 0]
+        phi = o.get_cc(I_PHI, ids).reshape(r.shape)
+        errs.append(np.max(np.abs(phi - r ** 2)[W.interior(t)]))
+        assert o.maxabs(I_TMP) < 1e-8
+    assert errs[0] < 1e-11 and 0 < errs[1] < 1e-3, errs
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_poisson_helmholtz_gaussians_second_order(ndim):
+    """afivo/examples/poisson_helmholtz.f90:18,32-34,119-128,145-161: lpl(phi) - lambda phi = lpl(g) - lambda g with
+    lambda = 1e3, two Gaussians (sigma 0.04) at 0.25 and 0.75, Dirichlet = analytic.  On uniform grids the error of
+    the converged solution falls by ~4 per halving of the spacing (2nd order), and it is smaller than for lambda = 0
+    (the Helmholtz term damps it)."""
+    g = W.Gaussians([[0.25] * ndim, [0.75] * ndim], 0.04)
+    lam = 1.0e3
+    errs = {}
+    lo, hi = 4, 5  # 64 and 128 cells per side: sigma / h = 2.6 and 5.1 (coarser grids are pre-asymptotic)
+    for lam_, lvls in ((lam, lo), (lam, hi), (0.0, lo)):
+        t = T.uniform_tree(ndim, 8, 8, lvls)
+        o = Oracle(t, helmholtz_lambda=lam_)
+        o.set_bc(W.bc_dirichlet_function(t, g.value))
+        o.mg_init()
+        leaves = t.leaves(t.highest_lvl).astype(np.int32)
+        ctr = W.cell_centres(t, leaves, ghosts=True)
+        o.set_cc(I_RHS, leaves, g.laplacian(ctr) - lam_ * g.value(ctr))
+        for it in range(5):
+            o.fas_fmg(True, it > 0)
+        assert o.maxabs(I_TMP) < 1e-6 * np.max(np.abs(g.laplacian(ctr)))
+        phi = o.get_cc(I_PHI, leaves).reshape(ctr.shape[:-1])
+        errs[(lam_, lvls)] = np.max(np.abs(phi - g.value(ctr))[W.interior(t)])
+    ratio = errs[(lam, lo)] / errs[(lam, hi)]
+    assert 3.0 < ratio < 5.0, (ratio, errs)
+    assert errs[(lam, lo)] < errs[(0.0, lo)]
