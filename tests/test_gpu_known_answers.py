@@ -104,3 +104,24 @@ def test_linear_potential_gives_constant_field_and_exact_norm_ghost_cells(mk):
     fld = mg.get_cc(M.I_FLD, ids)
     assert np.allclose(fld, np.linalg.norm(g), rtol=0, atol=1e-10), np.abs(fld - np.linalg.norm(g)).max()
     M.mg_destroy(mg)
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_poisson_neumann_linear_solution(ndim):
+    """afivo/examples/poisson_neumann.f90 (Cartesian): rhs = 0, Dirichlet 0 at low x, Neumann 1 at high x, Neumann 0
+    elsewhere, refined while lvl <= 4 and all(r_min < 0.25): phi = x, reproduced to rounding."""
+    nc = 8
+    t = T.build_tree(ndim, nc, [nc] * ndim, 5,
+                     lambda l, ixs, ctr: (l <= 4) & np.all((ixs - 1) * (1.0 / 2 ** (l - 1)) < 0.25, axis=1))
+    assert t.highest_lvl == 5
+    bc = W.bc_table(t, lambda nb, c: (W.AF_BC_DIRICHLET, 0.0) if nb == 1 else (W.AF_BC_NEUMANN, 1.0 if nb == 2 else 0.0))
+    mg = M.mg_t(sides_bc=bc)
+    M.mg_init(t, mg)
+    leaves = np.concatenate([t.leaves(l) for l in range(1, t.highest_lvl + 1)]).astype(np.int32)
+    x = W.cell_centres(t, leaves, ghosts=True)[..., 0]
+    for it in range(10):
+        M.mg_fas_fmg(t, mg, True, it > 0)
+    err = np.max(np.abs(mg.get_cc(M.I_PHI, leaves) - x)[W.interior(t)])
+    assert err < 1e-11, err
+    assert M.af_tree_maxabs_cc(t, mg, M.I_TMP) < 1e-9
+    M.mg_destroy(mg)
