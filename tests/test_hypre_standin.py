@@ -316,3 +316,82 @@ def test_reference_coarse_solve_sequence_matches_the_oracle(hy):
         got = H.get_box(H.phi, ilo, ilo + nc - 1).reshape(nc, nc, nc)
         assert np.max(np.abs(got - want[n])) <= 1e-12 * np.max(np.abs(want)), (n, np.max(np.abs(got - want[n])))
     H.destroy()
+
+
+def test_cylindrical_coarse_solve_sequence_matches_the_oracle(hy):
+    """2D cylindrical: the reference switches to the non-symmetric 5-entry storage (hypre_set_matrix :110-115) and
+    af_stencil_get_box expands the constant stencil with the flux factors (r -+ dr/2) / r (SURVEY a10:
+    cc_cyl(2:3) = rfac * c(2:3), cc_cyl(1) = c(1) - (cc_cyl(2) - c(2)) - (cc_cyl(3) - c(3)))."""
+    tree = T.build_tree(2, 8, [16, 8], 2, None, coord_t=T.AF_CYL, r_max=[2.0, 1.0])
+    nc = tree.nc
+
+    def sides(nb, c):
+        if nb == 1:
+            return W.AF_BC_NEUMANN, 0.0
+        if nb == 2:
+            return W.AF_BC_NEUMANN, 0.3 + c[..., 1]
+        return W.AF_BC_DIRICHLET, 1.0 + c[..., 0] * (nb == 4)
+
+    bc = W.bc_table(tree, sides)
+    orc = Oracle(tree)
+    orc.set_bc(bc)
+    orc.mg_init()
+    l1 = np.asarray(tree.lvl_ids[0], np.int32)
+    assert len(l1) == 2
+    rng = np.random.default_rng(13)
+    rhs = np.zeros((len(l1), nc + 2, nc + 2))
+    rhs[:, 1:-1, 1:-1] = rng.standard_normal((len(l1), nc, nc))
+    orc.set_cc(M.I_RHS, l1, rhs)
+    orc.set_cc(M.I_PHI, l1, np.zeros_like(rhs))
+    orc.solve_coarse_grid()
+    want = orc.get_cc(M.I_PHI, l1).reshape(rhs.shape)[:, 1:-1, 1:-1]
+
+    nx = [int(v) for v in tree.coarse_grid_size]
+    H = Hypre(hy, nx, (0, 0), [1, 2, 3, 4, 5], symmetric=0)
+    bcmap = {(int(i), int(n)): (int(t), v) for i, n, t, v in zip(bc.ids, bc.nbs, bc.types, bc.vals)}
+    bc_to_rhs = {}
+    for b in l1:
+        dr = tree.dr[b]
+        c = np.array([0.0, 1 / dr[0] ** 2, 1 / dr[0] ** 2, 1 / dr[1] ** 2, 1 / dr[1] ** 2])
+        c[0] = -c[1:].sum()
+        r = tree.r_min[b, 0] + (np.arange(1, nc + 1) - 0.5) * dr[0]
+        full = np.zeros((nc, nc, 5))  # [j, i, entry]
+        full[..., 3:] = c[3:]
+        full[..., 1] = (r - 0.5 * dr[0]) / r * c[1]
+        full[..., 2] = (r + 0.5 * dr[0]) / r * c[2]
+        full[..., 0] = c[0] - (full[..., 1] - c[1]) - (full[..., 2] - c[2])
+        for nb in range(1, 5):
+            if tree.neighbors[b, nb - 1] >= 0:
+                continue
+            d, hi = (nb - 1) // 2, (nb - 1) % 2
+            sl = [slice(None)] * 2
+            sl[1 - d] = nc - 1 if hi else 0
+            sl = tuple(sl)
+            if bcmap[(int(b), nb)][0] == W.AF_BC_DIRICHLET:
+                full[sl + (0,)] -= full[sl + (nb,)]
+                bc_to_rhs[(int(b), nb)] = (-2 * full[sl + (nb,)]).ravel()
+            else:
+                full[sl + (0,)] += full[sl + (nb,)]
+                bc_to_rhs[(int(b), nb)] = -(full[sl + (nb,)] * dr[d]).ravel() * (1 if hi else -1)
+            full[sl + (nb,)] = 0
+        ilo = (tree.ix[b] - 1) * nc + 1
+        H.set_matrix_box(ilo, ilo + nc - 1, full.reshape(-1, 5))
+    H.prepare_solve()
+    for n, b in enumerate(l1):
+        tmp = rhs[n, 1:-1, 1:-1].copy()
+        for nb in range(1, 5):
+            if tree.neighbors[b, nb - 1] >= 0:
+                continue
+            d, hi = (nb - 1) // 2, (nb - 1) % 2
+            sl = [slice(None)] * 2
+            sl[1 - d] = nc - 1 if hi else 0
+            tmp[tuple(sl)] += bc_to_rhs[(int(b), nb)] * bcmap[(int(b), nb)][1]
+        ilo = (tree.ix[b] - 1) * nc + 1
+        H.set_box(H.rhs, ilo, ilo + nc - 1, tmp)
+        H.set_box(H.phi, ilo, ilo + nc - 1, np.zeros(nc ** 2))
+    H.solve()
+    for n, b in enumerate(l1):
+        ilo = (tree.ix[b] - 1) * nc + 1
+        got = H.get_box(H.phi, ilo, ilo + nc - 1).reshape(nc, nc)
+        assert np.max(np.abs(got - want[n])) <= 1e-12 * np.max(np.abs(want)), (n, np.max(np.abs(got - want[n])))
+    H.destroy()
