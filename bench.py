@@ -191,6 +191,9 @@ def time_oracle(tree, bc, ids, rhs, steps, warmup):
     """CPU oracle: `steps` V-cycles (set_residual + max-norm each), all host threads."""
     from oracle.oracle import I_RHS, I_TMP, Oracle
     orc = Oracle(tree)
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its ranks when the variable
+    # is unset, which would time a 1-thread run; AFMG_CPU_THREADS overrides
+    orc.set_num_threads(int(os.environ.get("AFMG_CPU_THREADS", 0)) or len(os.sched_getaffinity(0)))
     orc.set_bc(bc)
     orc.set_cc(I_RHS, ids, rhs)
     orc.mg_init()
