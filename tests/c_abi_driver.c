@@ -47,6 +47,37 @@ int main(void) {
     printf("afmg_create returned %d\n", rc);
     ++fails;
   }
+  /* host-side builders from C: a rod electrode, one box of distances, its tag and operator (no device involved) */
+  {
+    afmg_electrode el;
+    memset(&el, 0, sizeof el);
+    el.type = AFMG_ELECTRODE_ROD; el.ndim = 3; el.rod_radius = 0.1;
+    el.rod_r0[0] = el.rod_r0[1] = el.rod_r1[0] = el.rod_r1[1] = 0.5; el.rod_r0[2] = 0.0; el.rod_r1[2] = 0.45;
+    if (afmg_electrode_prepare(&el) != AFMG_OK) { printf("electrode_prepare\n"); ++fails; }
+    const double p[3] = {0.5, 0.8, 0.2};
+    const double lsf = afmg_electrode_lsf(p, &el);
+    if (lsf < 0.2 - 1e-14 || lsf > 0.2 + 1e-14) { printf("rod lsf %g\n", lsf); ++fails; }
+    afmg_lsf_opts lo;
+    afmg_lsf_opts_default(&lo);
+    if (lo.dist_method != AFMG_LSF_DIST_LINEAR || lo.tol != 1e-8) { printf("lsf opts\n"); ++fails; }
+    static unsigned char mask[8 * 8 * 8];
+    static double dd[6 * 8 * 8 * 8], v[7 * 8 * 8 * 8], f[8 * 8 * 8];
+    const double r_min[3] = {0.0, 0.0, 0.0}, dr[3] = {0.125, 0.125, 0.125};
+    int32_t n_boundary = 0, stype = 0, has_f = 0, cyl = 0;
+    if (afmg_build_box_lsf_distances(3, 8, r_min, dr, afmg_electrode_lsf, &el, &lo, NULL, mask, dd, &n_boundary) != AFMG_OK ||
+        n_boundary <= 0) { printf("lsf distances: %d boundary cells\n", n_boundary); ++fails; }
+    const int32_t tag = afmg_build_box_tag(3, 8, NULL, n_boundary > 0);
+    if (tag != AFMG_TAG_LSF_BOX) { printf("tag %d\n", tag); ++fails; }
+    if (afmg_build_box_operator(3, 8, AFMG_XYZ, tag, dr, r_min, NULL, dd, v, f, &stype, &has_f, &cyl) != AFMG_OK ||
+        stype != 2 || !has_f || cyl) { printf("operator stype %d has_f %d\n", stype, has_f); ++fails; }
+    /* every row sums to f = -(the weights moved to the right-hand side): what is missing from the stencil */
+    for (int c = 0; c < 512; ++c) {
+      double s = 0.0, scale = 0.0;
+      for (int m = 0; m < 7; ++m) { s += v[7 * c + m]; scale += v[7 * c + m] < 0 ? -v[7 * c + m] : v[7 * c + m]; }
+      const double e = s - f[c];
+      if (e > 1e-12 * scale || e < -1e-12 * scale) { printf("row %d: sum %g f %g\n", c, s, f[c]); ++fails; break; }
+    }
+  }
   /* null handles are argument errors everywhere */
   if (afmg_fas_fmg(NULL, 1, 0) != AFMG_ERR_ARG || afmg_field_from_potential(NULL, -1.0) != AFMG_ERR_ARG ||
       afmg_helmholtz_compute(NULL, 0, NULL, 0, 0.0, NULL, NULL) != AFMG_ERR_ARG ||
