@@ -125,3 +125,27 @@ def test_morton_key_matches_the_reference_answers():
     base = L.afmg_morton_key(3, 2 * 5, 2 * 3, 2 * 9)
     keys = [L.afmg_morton_key(3, 2 * 5 + (c & 1), 2 * 3 + ((c >> 1) & 1), 2 * 9 + ((c >> 2) & 1)) for c in range(8)]
     assert keys == [base + c for c in range(8)]
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_tree_builder_reproduces_the_reference_refinement_counts_in_a_periodic_domain(ndim):
+    """afivo/tests/test_reduction.f90 + answers/test_reduction_2d, _3d: a fully periodic domain of length 2 pi, one
+    coarse box of 8^D, refined where all(r_min < 0.4); the 2:1 balance reaches across the periodic boundary (the
+    low-side neighbours of the corner box are the wrapped high-side boxes).  highest_id before the i-th
+    af_adjust_refinement and max(sum(box%ix)) after it are the reference's printed answers."""
+    from afivo_streamer_b200 import tree as T
+    highest_id = {3: [1, 9, 17, 49, 105, 273, 713, 2033, 8545], 2: [1, 5, 9, 21, 37, 81, 153, 281, 649, 1881]}[ndim]
+    max_ix_sum = {3: [6, 6, 8, 12, 20, 40, 76, 148], 2: [4, 4, 6, 10, 18, 36, 70, 138, 274]}[ndim]
+    dlen = 2 * np.arccos(-1.0)
+
+    def refine(l, ixs, ctr):
+        r_min = (ixs - 1) * (dlen / 2 ** (l - 1))
+        return np.all(r_min < 0.4, axis=1) & (l < 10)
+
+    for lvl, want in enumerate(highest_id, start=1):
+        t = T.build_tree(ndim, 8, [8] * ndim, lvl, refine, r_max=[dlen] * ndim, periodic=[True] * ndim)
+        assert t.highest_id == want, (lvl, t.highest_id, want)
+        ids = np.concatenate(t.lvl_ids)
+        assert t.ix[ids].sum(axis=1).min() == ndim  # the reference's "min" column: 3 (2 in 2D)
+        if lvl >= 2:
+            assert t.ix[ids].sum(axis=1).max() == max_ix_sum[lvl - 2], lvl
