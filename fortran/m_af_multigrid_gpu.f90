@@ -409,7 +409,7 @@ contains
   !> mg_fas_vcycle(tree, mg, set_residual, highest_lvl, standalone)  (m_af_multigrid.f90:185-264)
   subroutine mg_gpu_fas_vcycle(tree, mg, set_residual, slot, highest_lvl, standalone)
     type(af_t), intent(inout)     :: tree
-    type(mg_t), intent(inout)     :: mg
+    type(mg_t), intent(in)        :: mg
     logical, intent(in)           :: set_residual
     integer, intent(in)           :: slot
     integer, intent(in), optional :: highest_lvl

@@ -115,3 +115,42 @@ def test_shim_entry_points_extend_the_reference_signatures():
     for name in ("mg_gpu_init", "mg_gpu_destroy", "mg_gpu_fas_fmg", "mg_gpu_fas_vcycle", "mg_gpu_update_operator_stencil",
                  "mg_gpu_compute_phi_gradient", "mg_gpu_field_solve", "photoi_gpu_helmh_compute"):
         assert name in public, name
+
+
+def test_dropin_module_has_the_references_names_and_argument_lists():
+    """fortran/m_af_multigrid_dropin.f90: the entry points under the reference's own names and argument lists
+    (afivo/src/m_af_multigrid.f90:43, :111, :137, :185, :1188, :1857, :1997), each forwarding to the shim routine of
+    the same purpose with the slot resolved from the mg_t."""
+    raw = open(os.path.join(ROOT, "fortran", "m_af_multigrid_dropin.f90")).read()
+    src = "\n".join(ln.split("!")[0].rstrip() for ln in raw.splitlines()).lower()
+    src = re.sub(r"&\s*\n\s*&?", " ", src)
+    want = {
+        "mg_init": ("tree, mg", "mg_gpu_init"),
+        "mg_destroy": ("mg", "mg_gpu_destroy"),
+        "mg_fas_fmg": ("tree, mg, set_residual, have_guess", "mg_gpu_fas_fmg"),
+        "mg_fas_vcycle": ("tree, mg, set_residual, highest_lvl, standalone", "mg_gpu_fas_vcycle"),
+        "mg_update_operator_stencil": ("tree, mg, new_lsf, new_eps", "mg_gpu_update_operator_stencil"),
+        "mg_compute_phi_gradient": ("tree, mg, i_fc, fac, i_norm", "mg_gpu_compute_phi_gradient"),
+        "mg_compute_field_norm": ("tree, i_fc, i_norm", "mg_gpu_compute_field_norm"),
+    }
+    shim = fortran_source().lower()
+    public = " ".join(re.findall(r"public\s*::([^\n]*)", src))
+    for name, (args, target) in want.items():
+        m = re.search(rf"subroutine {name}\(([^)]*)\)(.*?)end subroutine {name}", src, flags=re.S)
+        assert m, name
+        assert re.sub(r"\s+", " ", m.group(1).strip()) == args, (name, m.group(1))
+        call = re.search(rf"call {target}\(([^\n]*)\)", m.group(2))
+        assert call, (name, target)
+        # the forwarded call has as many arguments as the shim routine declares
+        decl = re.search(rf"subroutine {target}\(([^)]*)\)", shim).group(1)
+        depth, n = 0, 1
+        for ch in call.group(1):
+            depth += ch == "("
+            depth -= ch == ")"
+            n += ch == "," and depth == 0
+        assert n == len(decl.split(",")), (name, call.group(1), decl)
+        assert name in public
+    # optional arguments stay optional, intents are the reference's
+    assert re.search(r"integer, intent\(in\), optional :: highest_lvl", src)
+    assert re.search(r"logical, intent\(in\), optional :: standalone", src)
+    assert re.search(r"subroutine mg_fas_vcycle.*?type\(mg_t\), intent\(in\)\s+:: mg", src, flags=re.S)
