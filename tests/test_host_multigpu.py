@@ -77,8 +77,12 @@ def test_world_size_2_gloo(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     env = dict(os.environ, OMP_NUM_THREADS="1")
+    import socket
+    with socket.socket() as sock:  # a free port: a fixed one may be held by another job on the machine
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script), ROOT],
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script), ROOT],
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert r.stdout.count("ok") == 2
