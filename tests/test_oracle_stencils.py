@@ -214,3 +214,88 @@ def test_level_set_operator_is_exact_for_a_linear_potential_through_the_electrod
     res = orc.get_cc(M.I_TMP, ids).reshape(phi.shape)[W.interior(tree)]
     scale = s / np.min(tree.dr[ids]) ** 2
     assert has.any() and np.max(np.abs(res)) < 1e-11 * scale, np.max(np.abs(res)) / scale
+
+
+def _cyl_dielectric_problem():
+    """afivo/examples/poisson_cyl_dielectric.f90:27-28,128-172: manufactured Gaussian (sigma 0.1 at r = 0, z = 0.25) in
+    a cylindrical domain whose corner r, z < 0.5 has eps = 100; rhs = eps * lpl_cyl(g) plus the surface charge that
+    the jump of eps times the normal gradient puts on every face, split over the two adjacent cells with the
+    weights eps_other / (eps_a + eps_b)."""
+    r0, s = np.array([0.0, 0.25]), 0.1
+
+    def g(r):
+        return np.exp(-np.sum((r - r0) ** 2, axis=-1) / s ** 2)
+
+    def lap_cyl(r):  # gauss_laplacian_cyl, afivo/examples/m_gaussians.f90:107-120
+        x = (r - r0) / s
+        return 4 / s ** 2 * (np.sum(x ** 2, axis=-1) - 1 - 0.5 * (r[..., 0] - r0[0]) / r[..., 0]) * g(r)
+
+    def grad(r):     # gauss_gradient, :76-89
+        return -2 * (r - r0) / s ** 2 * g(r)[..., None]
+
+    def eps_f(r):
+        return np.where((r[..., 0] < 0.5) & (r[..., 1] < 0.5), 100.0, 1.0)
+
+    def make_rhs(t, ids):
+        c = W.cell_centres(t, ids, ghosts=True)  # (n, z, r, 2)
+        e = eps_f(c)
+        rhs = lap_cyl(c) * e
+        dr = t.dr[ids]
+        fx = 0.5 * (c[:, 1:-1, :-1] + c[:, 1:-1, 1:])  # r faces between cells i and i+1, i = 0 .. nc
+        q = (e[:, 1:-1, 1:] - e[:, 1:-1, :-1]) * grad(fx)[..., 0] / dr[:, 0][:, None, None]
+        w = e[:, 1:-1, 1:] / (e[:, 1:-1, :-1] + e[:, 1:-1, 1:])
+        rhs[:, 1:-1, 1:] += w * q
+        rhs[:, 1:-1, :-1] += (1 - w) * q
+        fy = 0.5 * (c[:, :-1, 1:-1] + c[:, 1:, 1:-1])
+        q = (e[:, 1:, 1:-1] - e[:, :-1, 1:-1]) * grad(fy)[..., 1] / dr[:, 1][:, None, None]
+        w = e[:, 1:, 1:-1] / (e[:, :-1, 1:-1] + e[:, 1:, 1:-1])
+        rhs[:, 1:, 1:-1] += w * q
+        rhs[:, :-1, 1:-1] += (1 - w) * q
+        return rhs
+
+    def solve_error(t):
+        ids = all_ids(t)
+        o = Oracle(t, with_eps=True)
+        o.set_bc(W.bc_table(t, lambda nb, c: (W.AF_BC_NEUMANN, 0.0) if nb == 1 else (W.AF_BC_DIRICHLET, g(c))))
+        o.set_cc(M.I_EPS, ids, eps_f(W.cell_centres(t, ids, ghosts=True)))
+        o.mg_init()
+        leaves = np.concatenate([t.leaves(l) for l in range(1, t.highest_lvl + 1)]).astype(np.int32)
+        o.set_cc(M.I_RHS, leaves, make_rhs(t, leaves))
+        res = []
+        for it in range(10):
+            o.fas_fmg(True, it > 0)
+            res.append(o.maxabs(M.I_TMP))
+        assert res[-1] < 1e-8 * res[0], res
+        c = W.cell_centres(t, leaves, ghosts=True)
+        phi = o.get_cc(M.I_PHI, leaves).reshape(c.shape[:-1])
+        return o, np.max(np.abs(phi - g(c))[W.interior(t)])
+
+    return lap_cyl, solve_error
+
+
+def test_poisson_cyl_dielectric_manufactured_solution_second_order():
+    """Uniform grids: the error of the converged solution falls by 4 per halving of the spacing across a jump of
+    eps by a factor 100 (harmonic-mean operator + cylindrical form)."""
+    _, solve_error = _cyl_dielectric_problem()
+    errs = [solve_error(T.build_tree(2, 8, [8, 8], lv, None, coord_t=T.AF_CYL))[1] for lv in (4, 5)]
+    assert errs[0] < 2e-2 and 3.5 < errs[0] / errs[1] < 4.5, errs
+
+
+def test_poisson_cyl_dielectric_on_the_adaptive_tree():
+    """The example's adaptively refined tree (7 levels): variable-eps, constant-eps and plain boxes side by side,
+    refinement boundaries with mg_sides_rb_extrap and mg_box_prolong_eps_stencil on the jump."""
+    lap_cyl, solve_error = _cyl_dielectric_problem()
+    nc = 8
+
+    def refine(l, ixs, ctr):
+        dr = 1.0 / (nc * 2 ** (l - 1))
+        off = (np.arange(nc) - (nc - 1) / 2) * dr
+        gy, gx = np.meshgrid(off, off, indexing="ij")
+        pts = ctr[:, None, :] + np.stack([gx, gy], axis=-1).reshape(1, -1, 2)
+        return (dr * dr * np.max(np.abs(lap_cyl(pts)), axis=1) > 1e-3) & (l < 7)
+
+    t = T.build_tree(2, nc, [nc, nc], 7, refine, coord_t=T.AF_CYL)
+    assert t.highest_lvl == 7
+    o, err = solve_error(t)
+    assert {o.tag(int(b)) for b in all_ids(t)} == {0, 2, 4}
+    assert err < 3e-4, err
