@@ -407,3 +407,41 @@ def test_poisson_cyl_analytic_gaussian_charge_on_the_axis():
         phi = o.get_cc(I_PHI, leaves).reshape(ctr.shape[:-1])
         rel.append(np.max(np.abs(phi - sol(ctr))[W.interior(t)]) / np.max(sol(ctr)))
     assert rel[0] < 5e-3 and rel[1] < 3e-4 and rel[1] < 0.1 * rel[0], rel
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_implicit_diffusion_in_a_periodic_domain_follows_the_discrete_decay(ndim):
+    """afivo/examples/helmholtz_variable_stencil.f90:9-21,40-47,66-71,113-128: backward-Euler diffusion steps
+    (lpl - 1/(D dt)) phi_new = -phi_old / (D dt) in a fully periodic domain of length 2 pi, started from
+    1 + cos(x) cos(y).  cos(x) cos(y) is an eigenvector of the periodic 5/7-point operator with eigenvalue
+    -mu = -(4 / h^2) * 2 sin^2(h / 2), so every converged step multiplies its amplitude by exactly 1 / (1 + D dt mu)
+    and leaves the constant 1 alone; mg_update_operator_stencil's role (lambda changes with dt) is played by a new
+    oracle per dt."""
+    dlen = 2 * np.arccos(-1.0)
+    D = 1.0
+    t = T.build_tree(ndim, 8, [8] * ndim, 3, None, r_max=[dlen] * ndim, periodic=[True] * ndim)
+    h = t.dr[t.leaves(3)[0], 0]
+    mu = (4 / h ** 2) * 2 * np.sin(h / 2) ** 2
+    ids = np.concatenate(t.lvl_ids).astype(np.int32)
+    leaves = t.leaves(3).astype(np.int32)
+    rr = W.cell_centres(t, ids, ghosts=True)
+    mode = np.cos(rr[..., 0]) * np.cos(rr[..., 1])
+    for k_factor in (1, 4):
+        dt = 0.1 / k_factor
+        o = Oracle(t, helmholtz_lambda=1 / (D * dt))
+        o.set_bc(W.bc_table(t, lambda nb, c: (W.AF_BC_DIRICHLET, 0.0)))  # no physical faces: an empty table
+        o.mg_init()
+        o.set_cc(I_PHI, ids, 1 + mode)
+        amp = 1.0
+        sel = np.isin(ids, leaves)
+        for step in range(3):
+            phi_old = o.get_cc(I_PHI, leaves)
+            o.set_cc(I_RHS, leaves, -phi_old / (dt * D))
+            for it in range(4):
+                o.fas_fmg(True, True)
+            amp /= 1 + D * dt * mu
+            phi = o.get_cc(I_PHI, leaves).reshape(mode[sel].shape)
+            err = np.max(np.abs(phi - (1 + amp * mode[sel]))[W.interior(t)])
+            assert err < 1e-9, (k_factor, step, err)
+        # the continuum decay exp(-2 D t) is matched to first order in dt and second order in h
+        assert abs(amp - np.exp(-2 * D * 3 * dt)) < 0.6 * dt
