@@ -344,6 +344,12 @@ inline stencil_set_t mg_build_stencils(const af_t& tree, const mg_t& mg, const d
       }
       out.desc.push_back(d);
     }
+  if (lsf) {  // check_coarse_representation_lsf (m_af_multigrid.f90:2142-2161): error stop in the reference
+    bool on_coarse = false;
+    for (int32_t id : out.lsf_ids) on_coarse = on_coarse || tree.lvl[id] == 1;
+    if (!on_coarse)
+      throw error(AFMG_ERR_ARG, "level set function not resolved on coarse grid: no roots found on level 1, use a finer coarse grid");
+  }
   return out;
 }
 

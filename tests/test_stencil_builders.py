@@ -336,3 +336,50 @@ def test_builtin_electrode_gives_the_same_stencils_as_the_equivalent_python_func
     for x, y in zip(a, b):
         assert x["box_id"] == y["box_id"] and x["tag"] == y["tag"]
         np.testing.assert_allclose(x["op"][1], y["op"][1], rtol=1e-6)
+
+
+def test_two_rods_at_different_potentials_on_the_oracle():
+    """field_electrode_type = rod_rod (src/m_field.f90:280-294): level set min(rod 1, rod 2) and
+    mg%lsf_boundary_function = rod_rod_get_potential (rod 1 at the applied voltage, rod 2 grounded), both evaluated
+    by the library's C-side functions, distances by the library's search; solved by the oracle.  Physics: the
+    potential obeys the maximum principle and each electrode's interior sits at its own potential."""
+    V = 2.0
+    t = T.build_tree(2, 8, [32, 32], 2, None)  # 4 x 4 coarse boxes (the electrodes are resolved on level 1), 64 x 64
+    el = S.electrode("rod_rod", 2, rod_r0=(0.5, 0.0), rod_r1=(0.5, 0.3), rod_radius=0.06, rod2_r0=(0.5, 1.0),
+                     rod2_r1=(0.5, 0.72), rod2_radius=0.06, current_voltage=V, electrode2_grounded=1)
+    data = S.lsf_distances(t, el)
+    nc = t.nc
+    o = Oracle(t, lsf_boundary_value=99.0)  # the scalar must not be used where per-cell values are given
+    # grounded side walls, zero flux at the ends
+    o.set_bc(W.bc_table(t, lambda nb, c: (W.AF_BC_DIRICHLET, 0.0) if nb <= 2 else (W.AF_BC_NEUMANN, 0.0)))
+    o.set_lsf_distances(data.ids, data.dd.reshape(len(data.ids), -1))
+    centres = W.cell_centres(t, data.ids, ghosts=False).reshape(len(data.ids), -1, 2)
+    o.set_lsf_boundary_values(data.ids, S.electrode_potential(el, centres))
+    o.mg_init()
+    res = []
+    for it in range(8):
+        o.fas_fmg(True, it > 0)
+        res.append(o.maxabs(M.I_TMP))
+    assert res[-1] < 1e-8 * max(res[0], 1.0), res
+    leaves = t.leaves(2).astype(np.int32)
+    c = W.cell_centres(t, leaves, ghosts=False)
+    phi = o.get_cc(M.I_PHI, leaves).reshape((len(leaves), nc + 2, nc + 2))[:, 1:-1, 1:-1]
+    assert phi.min() > -1e-6 and phi.max() < V + 1e-6
+    _, _, f = S._callback(el, 2)
+    lsf = np.array([f(p) for p in c.reshape(-1, 2)]).reshape(phi.shape)
+    dr = t.dr[leaves[0], 0]
+    deep = lsf < -1.5 * dr
+    in1, in2 = deep & (c[..., 1] < 0.5), deep & (c[..., 1] > 0.5)
+    assert in1.sum() > 10 and in2.sum() > 10
+    assert np.max(np.abs(phi[in1] - V)) < 1e-6 and np.max(np.abs(phi[in2])) < 1e-6
+    mid = (np.abs(c[..., 0] - 0.5) < dr) & (np.abs(c[..., 1] - 0.5) < dr)  # between the tips: strictly in between
+    assert np.all((phi[mid] > 0.2 * V) & (phi[mid] < 0.8 * V))
+
+
+def test_unresolved_electrode_on_the_coarse_grid_is_refused_like_the_reference():
+    """check_coarse_representation_lsf (m_af_multigrid.f90:2142-2161): "level set function not resolved on coarse
+    grid" -- an 8 x 8 coarse grid does not see a rod of radius 0.01."""
+    t = T.uniform_tree(2, 8, 8, 4)
+    el = S.electrode("rod", 2, rod_r0=(0.53, 0.0), rod_r1=(0.53, 0.3), rod_radius=0.01)
+    with pytest.raises(_lib.AfmgError, match="not resolved on coarse grid"):
+        S.build_stencils(t, lsf=el)
