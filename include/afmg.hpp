@@ -434,7 +434,7 @@ inline void af_gc_tree(const af_t&, mg_t& mg, int var, bool corners = true) {
   mg.check(afmg_gc_tree(mg.h, var, corners), "afmg_gc_tree");
 }
 
-// af_init followed by af_adjust_refinement until nothing is added: a 2:1 balanced 3D tree in the reference's
+// af_init followed by af_adjust_refinement until nothing is added: a 2:1 balanced 2D or 3D tree in the reference's
 // conventions -- level-1 ids i + (j-1) nx + (k-1) nx ny (m_af_core.f90:436-501), children appended parent by parent
 // in af_child_dix order (:1187-1254), neighbours / neighbor_mat with af_phys_boundary = -1 outside a non-periodic
 // domain (:595-661), 2:1 balance over faces from the finest level down (ensure_two_one_balance, :1016-1057).
@@ -442,20 +442,24 @@ inline void af_gc_tree(const af_t&, mg_t& mg, int var, bool corners = true) {
 // of the reference's per-cell flags); nullptr refines everything.
 using refine_t = std::function<bool(int lvl, const int* ix, const double* centre)>;
 
-inline af_t af_build_tree(int n_cell, const int* coarse_grid_size, int max_lvl, const refine_t& refine = nullptr,
-                          const double* r_lo = nullptr, const double* r_hi = nullptr, const bool* periodic = nullptr) {
+inline af_t af_build_tree_nd(int ndim, int n_cell, const int* coarse_grid_size, int max_lvl, const refine_t& refine = nullptr,
+                             const double* r_lo = nullptr, const double* r_hi = nullptr, const bool* periodic = nullptr,
+                             int coord_t = AFMG_XYZ) {
+  if (ndim != 2 && ndim != 3) throw error(AFMG_ERR_UNSUPPORTED, "af_build_tree_nd: ndim must be 2 or 3");
   af_t t;
-  t.ndim = 3;
+  const int nd = ndim, nch = 1 << ndim, nnb = 2 * ndim, nmat = ndim == 3 ? 27 : 9;
+  t.ndim = ndim;
+  t.coord_t = coord_t;
   t.n_cell = n_cell;
-  int nb1[3];
-  for (int d = 0; d < 3; ++d) {
+  int nb1[3] = {1, 1, 1};
+  for (int d = 0; d < nd; ++d) {
     t.coarse_grid_size[d] = coarse_grid_size[d];
     t.periodic[d] = periodic ? periodic[d] : false;
     t.r_base[d] = r_lo ? r_lo[d] : 0.0;
     t.dr_base[d] = ((r_hi ? r_hi[d] : 1.0) - t.r_base[d]) / coarse_grid_size[d];
     nb1[d] = coarse_grid_size[d] / n_cell;
   }
-  auto nbl = [&](int l, int d) { return nb1[d] << (l - 1); };
+  auto nbl = [&](int l, int d) { return d < nd ? nb1[d] << (l - 1) : 1; };  // the unused third dimension has one box
   auto lin = [&](int l, int x, int y, int z) { return (size_t)x + (size_t)nbl(l, 0) * ((size_t)y + (size_t)nbl(l, 1) * z); };
   auto cells = [&](int l) { return (size_t)nbl(l, 0) * nbl(l, 1) * nbl(l, 2); };
   std::vector<std::vector<char>> exists(max_lvl + 2), refined(max_lvl + 2);
@@ -466,7 +470,7 @@ inline af_t af_build_tree(int n_cell, const int* coarse_grid_size, int max_lvl, 
       for (int y = 0; y < nbl(l, 1); ++y)
         for (int x = 0; x < nbl(l, 0); ++x)
           if (refined[l][lin(l, x, y, z)])
-            for (int c = 0; c < 8; ++c) exists[l + 1][lin(l + 1, 2 * x + (c & 1), 2 * y + ((c >> 1) & 1), 2 * z + ((c >> 2) & 1))] = 1;
+            for (int c = 0; c < nch; ++c) exists[l + 1][lin(l + 1, 2 * x + (c & 1), 2 * y + ((c >> 1) & 1), nd == 3 ? 2 * z + ((c >> 2) & 1) : 0)] = 1;
   };
   for (int l = 1; l < max_lvl; ++l) {
     refined[l].assign(cells(l), 0);
@@ -477,8 +481,8 @@ inline af_t af_build_tree(int n_cell, const int* coarse_grid_size, int max_lvl, 
           bool r = true;
           if (refine) {
             const int ix[3] = {x + 1, y + 1, z + 1};
-            double ctr[3];
-            for (int d = 0; d < 3; ++d) ctr[d] = t.r_base[d] + (ix[d] - 0.5) * (t.dr_base[d] * std::pow(0.5, l - 1)) * n_cell;
+            double ctr[3] = {0, 0, 0};
+            for (int d = 0; d < nd; ++d) ctr[d] = t.r_base[d] + (ix[d] - 0.5) * (t.dr_base[d] * std::pow(0.5, l - 1)) * n_cell;
             r = refine(l, ix, ctr);
           }
           refined[l][lin(l, x, y, z)] = r;
@@ -491,7 +495,7 @@ inline af_t af_build_tree(int n_cell, const int* coarse_grid_size, int max_lvl, 
       for (int y = 0; y < nbl(l, 1); ++y)
         for (int x = 0; x < nbl(l, 0); ++x) {
           if (!refined[l][lin(l, x, y, z)]) continue;
-          for (int nb = -1; nb < 6; ++nb) {  // the box itself and its six face neighbours must exist
+          for (int nb = -1; nb < nnb; ++nb) {  // the box itself and its face neighbours must exist
             int q[3] = {x, y, z};
             if (nb >= 0) {
               q[nb >> 1] += (nb & 1) ? 1 : -1;
@@ -501,7 +505,7 @@ inline af_t af_build_tree(int n_cell, const int* coarse_grid_size, int max_lvl, 
                 q[d] = (q[d] + nbl(l, d)) % nbl(l, d);
               }
             }
-            refined[l - 1][lin(l - 1, q[0] / 2, q[1] / 2, q[2] / 2)] = 1;
+            refined[l - 1][lin(l - 1, q[0] / 2, q[1] / 2, nd == 3 ? q[2] / 2 : 0)] = 1;
           }
         }
   for (int l = 1; l < max_lvl; ++l) upsample(l);
@@ -522,19 +526,19 @@ inline af_t af_build_tree(int n_cell, const int* coarse_grid_size, int max_lvl, 
   for (int l = 1; l < highest; ++l)
     for (const P& p : order[l])
       if (refined[l][lin(l, p.x, p.y, p.z)])
-        for (int c = 0; c < 8; ++c) order[l + 1].push_back({2 * p.x + (c & 1), 2 * p.y + ((c >> 1) & 1), 2 * p.z + ((c >> 2) & 1)});
+        for (int c = 0; c < nch; ++c) order[l + 1].push_back({2 * p.x + (c & 1), 2 * p.y + ((c >> 1) & 1), nd == 3 ? 2 * p.z + ((c >> 2) & 1) : 0});
   size_t total = 0;
   for (int l = 1; l <= highest; ++l) total += order[l].size();
   t.highest_id = (int)total;
   const size_t N = total + 1;
   t.lvl.assign(N, 0);
-  t.ix.assign(N * 3, 0);
+  t.ix.assign(N * nd, 0);
   t.parent.assign(N, 0);
-  t.children.assign(N * 8, 0);
-  t.neighbors.assign(N * 6, 0);
-  t.neighbor_mat.assign(N * 27, 0);
-  t.r_min.assign(N * 3, 0.0);
-  t.dr.assign(N * 3, 0.0);
+  t.children.assign(N * nch, 0);
+  t.neighbors.assign(N * nnb, 0);
+  t.neighbor_mat.assign(N * nmat, 0);
+  t.r_min.assign(N * nd, 0.0);
+  t.dr.assign(N * nd, 0.0);
   t.lvl_ids.assign(highest + 1, {});
   std::vector<std::vector<int32_t>> idgrid(highest + 1);
   int next = 1;
@@ -545,44 +549,50 @@ inline af_t af_build_tree(int n_cell, const int* coarse_grid_size, int max_lvl, 
       t.lvl_ids[l].push_back(id);
       t.lvl[id] = l;
       const int q[3] = {p.x, p.y, p.z};
-      for (int d = 0; d < 3; ++d) {
-        t.ix[(size_t)id * 3 + d] = q[d] + 1;
-        t.dr[(size_t)id * 3 + d] = t.dr_base[d] * std::pow(0.5, l - 1);
+      for (int d = 0; d < nd; ++d) {
+        t.ix[(size_t)id * nd + d] = q[d] + 1;
+        t.dr[(size_t)id * nd + d] = t.dr_base[d] * std::pow(0.5, l - 1);
       }
       idgrid[l][lin(l, p.x, p.y, p.z)] = id;
       if (l == 1) {
-        for (int d = 0; d < 3; ++d) t.r_min[(size_t)id * 3 + d] = t.r_base[d] + q[d] * t.dr_base[d] * n_cell;
+        for (int d = 0; d < nd; ++d) t.r_min[(size_t)id * nd + d] = t.r_base[d] + q[d] * t.dr_base[d] * n_cell;
       } else {
-        const int pid = idgrid[l - 1][lin(l - 1, p.x / 2, p.y / 2, p.z / 2)];
+        const int pid = idgrid[l - 1][lin(l - 1, p.x / 2, p.y / 2, nd == 3 ? p.z / 2 : 0)];
         t.parent[id] = pid;
-        const int c = (p.x & 1) | ((p.y & 1) << 1) | ((p.z & 1) << 2);
-        t.children[(size_t)pid * 8 + c] = id;
-        for (int d = 0; d < 3; ++d)  // add_children: r_min = r_min_p + 0.5 * dr_p * dix * n_cell
-          t.r_min[(size_t)id * 3 + d] = t.r_min[(size_t)pid * 3 + d] + 0.5 * t.dr[(size_t)pid * 3 + d] * (q[d] & 1) * n_cell;
+        const int c = (p.x & 1) | ((p.y & 1) << 1) | (nd == 3 ? (p.z & 1) << 2 : 0);
+        t.children[(size_t)pid * nch + c] = id;
+        for (int d = 0; d < nd; ++d)  // add_children: r_min = r_min_p + 0.5 * dr_p * dix * n_cell
+          t.r_min[(size_t)id * nd + d] = t.r_min[(size_t)pid * nd + d] + 0.5 * t.dr[(size_t)pid * nd + d] * (q[d] & 1) * n_cell;
       }
     }
   }
   for (int l = 1; l <= highest; ++l)
     for (int32_t id : t.lvl_ids[l]) {
-      const int32_t* q = &t.ix[(size_t)id * 3];
-      for (int dz = -1; dz <= 1; ++dz)
+      const int32_t* q = &t.ix[(size_t)id * nd];
+      for (int dz = (nd == 3 ? -1 : 0); dz <= (nd == 3 ? 1 : 0); ++dz)
         for (int dy = -1; dy <= 1; ++dy)
           for (int dx = -1; dx <= 1; ++dx) {
-            int p[3] = {q[0] - 1 + dx, q[1] - 1 + dy, q[2] - 1 + dz};
+            int p[3] = {q[0] - 1 + dx, q[1] - 1 + dy, nd == 3 ? q[2] - 1 + dz : 0};
             bool out = false;
-            for (int d = 0; d < 3; ++d) {
+            for (int d = 0; d < nd; ++d) {
               if (t.periodic[d]) p[d] = (p[d] + nbl(l, d)) % nbl(l, d);
               else out = out || p[d] < 0 || p[d] >= nbl(l, d);
             }
-            t.neighbor_mat[(size_t)id * 27 + (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)] = out ? -1 : idgrid[l][lin(l, p[0], p[1], p[2])];
+            t.neighbor_mat[(size_t)id * nmat + (dx + 1) + 3 * (dy + 1) + (nd == 3 ? 9 * (dz + 1) : 0)] = out ? -1 : idgrid[l][lin(l, p[0], p[1], p[2])];
           }
-      for (int nb = 0; nb < 6; ++nb) {
+      for (int nb = 0; nb < nnb; ++nb) {
         int d[3] = {0, 0, 0};
         d[nb >> 1] = (nb & 1) ? 1 : -1;
-        t.neighbors[(size_t)id * 6 + nb] = t.neighbor_mat[(size_t)id * 27 + (d[0] + 1) + 3 * (d[1] + 1) + 9 * (d[2] + 1)];
+        t.neighbors[(size_t)id * nnb + nb] = t.neighbor_mat[(size_t)id * nmat + (d[0] + 1) + 3 * (d[1] + 1) + (nd == 3 ? 9 * (d[2] + 1) : 0)];
       }
     }
   return t;
+}
+
+// the 3D form used by the examples in tools/
+inline af_t af_build_tree(int n_cell, const int* coarse_grid_size, int max_lvl, const refine_t& refine = nullptr,
+                          const double* r_lo = nullptr, const double* r_hi = nullptr, const bool* periodic = nullptr) {
+  return af_build_tree_nd(3, n_cell, coarse_grid_size, max_lvl, refine, r_lo, r_hi, periodic, AFMG_XYZ);
 }
 
 // the tree of afivo/examples/poisson_benchmark.f90:72-90: unit cube, everything refined up to max_lvl

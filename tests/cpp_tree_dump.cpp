@@ -1,6 +1,6 @@
 // Dumps the tree afmg.hpp builds (af_build_tree) so that tests/test_cpp_host.py can compare it, array by array,
 // with the Python builder that follows the reference's conventions (afivo_streamer_b200/tree.py).
-//   cpp_tree_dump <kind: uniform|corner|sphere> n_cell cx cy cz max_lvl
+//   cpp_tree_dump <kind: uniform|corner|sphere> n_cell cx cy cz max_lvl [ndim = 3 [cylindrical = 0]]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -14,12 +14,36 @@ int main(int argc, char** argv) {
   const int nc = std::atoi(argv[2]);
   const int cgs[3] = {std::atoi(argv[3]), std::atoi(argv[4]), std::atoi(argv[5])};
   const int lvl = std::atoi(argv[6]);
+  const int nd = argc > 7 ? std::atoi(argv[7]) : 3;
+  const bool cyl = argc > 8 && std::atoi(argv[8]) != 0;
   afmg::refine_t fn = nullptr;
   if (!std::strcmp(kind, "corner")) fn = [](int, const int* ix, const double*) { return ix[0] == 1 && ix[1] == 1 && ix[2] == 1; };
   if (!std::strcmp(kind, "sphere"))
-    fn = [](int, const int*, const double* c) {
-      return std::sqrt((c[0] - 0.4) * (c[0] - 0.4) + (c[1] - 0.4) * (c[1] - 0.4) + (c[2] - 0.4) * (c[2] - 0.4)) < 0.45;
+    fn = [nd](int, const int*, const double* c) {
+      double s = 0;
+      for (int d = 0; d < nd; ++d) s += (c[d] - 0.4) * (c[d] - 0.4);
+      return std::sqrt(s) < 0.45;
     };
+  if (nd == 2) {  // the 2D / cylindrical builder: same dump with 4 children, 4 neighbours, a 3 x 3 neighbour matrix
+    afmg::af_t t2 = afmg::af_build_tree_nd(2, nc, cgs, lvl, fn, nullptr, nullptr, nullptr, cyl ? AFMG_CYL : AFMG_XYZ);
+    std::printf("%d %d\n", t2.highest_lvl, t2.highest_id);
+    for (int l = 1; l <= t2.highest_lvl; ++l) {
+      std::printf("L %zu", t2.lvl_ids[l].size());
+      for (int id : t2.lvl_ids[l]) std::printf(" %d", id);
+      std::printf("\n");
+    }
+    for (int id = 1; id <= t2.highest_id; ++id) {
+      std::printf("B %d %d %d %d", t2.lvl[id], t2.ix[id * 2], t2.ix[id * 2 + 1], t2.parent[id]);
+      for (int c = 0; c < 4; ++c) std::printf(" %d", t2.children[id * 4 + c]);
+      for (int c = 0; c < 4; ++c) std::printf(" %d", t2.neighbors[id * 4 + c]);
+      for (int c = 0; c < 9; ++c) std::printf(" %d", t2.neighbor_mat[id * 9 + c]);
+      std::printf("\n");
+    }
+    for (int id = 1; id <= t2.highest_id; ++id)
+      std::printf("G %.17g %.17g %.17g %.17g\n", t2.r_min[id * 2], t2.r_min[id * 2 + 1], t2.dr[id * 2], t2.dr[id * 2 + 1]);
+    std::printf("coord %d\n", t2.coord_t);
+    return 0;
+  }
   afmg::af_t t = afmg::af_build_tree(nc, cgs, lvl, fn);
   std::printf("%d %d\n", t.highest_lvl, t.highest_id);
   for (int l = 1; l <= t.highest_lvl; ++l) {

@@ -122,3 +122,39 @@ def test_cpp_stencil_builder_matches_python_mirror(stencil_exe, tmp_path, custom
     for n in range(n_lsf):
         assert np.array_equal(rest[n * per:n * per + 6 * ncell], data.dd[n].reshape(-1))
         assert np.array_equal(rest[n * per + 6 * ncell:(n + 1) * per], data.lsf_cells[n])
+
+
+CASES2D = {
+    "uniform2d_8_4": ("uniform", 8, [8, 8], 4, 0, lambda: T.uniform_tree(2, 8, 8, 4)),
+    "corner2d_8_5": ("corner", 8, [8, 8], 5, 0, lambda: T.corner_refined_tree(2, 8, 8, 5)),
+    "sphere2d_multibox_cyl": ("sphere", 8, [16, 24], 4, 1,
+                              lambda: T.build_tree(2, 8, [16, 24], 4, lambda l, ix, c: np.linalg.norm(c - 0.4, axis=1) < 0.45,
+                                                   coord_t=T.AF_CYL)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES2D))
+def test_cpp_2d_tree_matches_python_builder(dump_exe, name):
+    """afmg::af_build_tree_nd(2, ...): the 2D / cylindrical trees of config C1 from the C++ mirror."""
+    kind, nc, cgs, lvl, cyl, mk = CASES2D[name]
+    out = subprocess.run([dump_exe, kind, str(nc), str(cgs[0]), str(cgs[1]), "1", str(lvl), "2", str(cyl)],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    t = mk()
+    hl, hid = map(int, lines[0].split())
+    assert (hl, hid) == (t.highest_lvl, t.highest_id)
+    for l in range(hl):
+        vals = list(map(int, lines[1 + l].split()[1:]))
+        assert vals[0] == len(t.lvl_ids[l]) and vals[1:] == list(map(int, t.lvl_ids[l]))
+    boxes = np.array([list(map(int, ln.split()[1:])) for ln in lines[1 + hl:1 + hl + hid]])
+    ids = np.arange(1, hid + 1)
+    assert np.array_equal(boxes[:, 0], t.lvl[ids])
+    assert np.array_equal(boxes[:, 1:3], t.ix[ids])
+    assert np.array_equal(boxes[:, 3], t.parent[ids])
+    assert np.array_equal(boxes[:, 4:8], t.children[ids])
+    assert np.array_equal(boxes[:, 8:12], t.neighbors[ids])
+    assert np.array_equal(boxes[:, 12:21], t.neighbor_mat[ids])
+    geo = np.array([list(map(float, ln.split()[1:])) for ln in lines[1 + hl + hid:1 + hl + 2 * hid]])
+    assert np.array_equal(geo[:, 0:2], t.r_min[ids]) and np.array_equal(geo[:, 2:4], t.dr[ids])
+    assert lines[-1] == f"coord {t.coord_t}"
