@@ -158,3 +158,26 @@ def test_cpp_2d_tree_matches_python_builder(dump_exe, name):
     geo = np.array([list(map(float, ln.split()[1:])) for ln in lines[1 + hl + hid:1 + hl + 2 * hid]])
     assert np.array_equal(geo[:, 0:2], t.r_min[ids]) and np.array_equal(geo[:, 2:4], t.dr[ids])
     assert lines[-1] == f"coord {t.coord_t}"
+
+
+@pytest.mark.parametrize("cyl", [0, 1])
+def test_native_electrode_example_sets_up_the_same_problem_as_the_python_mirror(cyl):
+    """tools/electrode_example.cpp --dry-run (afivo/examples/electrode_example.f90 in 2D on the C++ mirror: 2D tree
+    builder, built-in rod level set, mg_build_stencils) against the Python mirror's set-up of the same problem,
+    which tests/test_gpu_electrode_example.py solves on the GPU."""
+    from afivo_streamer_b200 import stencils as S
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tools"), "-s", "electrode_example_2d"])
+    out = subprocess.run([os.path.join(ROOT, "tools", "electrode_example_2d")] + (["cyl"] if cyl else []) + ["--dry-run"],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    hl, hid, n_desc, n_lsf, n_blob, blob_sum = out.stdout.split()
+    nc = 8
+    t = T.build_tree(2, nc, [4 * nc] * 2, 5, lambda l, ixs, ctr: (l < 5) & ((ixs[:, 0] - 1) * (0.25 / 2 ** (l - 1)) < 0.5),
+                     coord_t=T.AF_CYL if cyl else T.AF_XYZ)
+    el = S.electrode("rod", 2, rod_r0=(0.4, 0.4), rod_r1=(0.6, 0.6), rod_radius=0.02)
+    entries, data = S.build_stencils(t, lsf=el)
+    assert (int(hl), int(hid)) == (t.highest_lvl, t.highest_id)
+    assert int(n_desc) == len(entries) and int(n_lsf) == len(data.ids)
+    blob = np.concatenate([np.concatenate([np.asarray(e["op"][1]).reshape(-1), e["f"]]) for e in entries])
+    assert int(n_blob) == blob.size
+    assert abs(float(blob_sum) - blob.sum()) <= 1e-12 * np.abs(blob).sum()
