@@ -383,3 +383,41 @@ def test_unresolved_electrode_on_the_coarse_grid_is_refused_like_the_reference()
     el = S.electrode("rod", 2, rod_r0=(0.53, 0.0), rod_r1=(0.53, 0.3), rod_radius=0.01)
     with pytest.raises(_lib.AfmgError, match="not resolved on coarse grid"):
         S.build_stencils(t, lsf=el)
+
+
+@pytest.mark.parametrize("nd,coord,lvl", [(2, T.AF_XYZ, 4), (2, T.AF_CYL, 4), (3, T.AF_XYZ, 3)])
+def test_poisson_lsf_test_spherical_electrode_against_its_analytic_potential(nd, coord, lvl):
+    """afivo/examples/poisson_lsf_test.f90 (shape 1; :27-31, 223-240, 262-275): an electrode of radius 0.25 at
+    potential 1 in the middle of the unit box (on the axis when cylindrical), Dirichlet = the analytic potential
+    1 + log(d) in 2D, 2 - 1/d in 3D and cylindrical (d = r / radius) on the outer boundary; mg%lsf_dist =
+    mg_lsf_dist_gss, mg%lsf_length_scale = 1e-3, uniform refinement.  The example prints residual, max error and rmse
+    per FMG cycle: here the residual reaches rounding and the errors stay at the cut-cell level."""
+    V, R = 1.0, 0.25
+    r0 = np.full(nd, 0.5)
+    if coord == T.AF_CYL:
+        r0[0] = 0.0
+
+    def sol(r):
+        d = np.maximum(np.linalg.norm(r - r0, axis=-1) / R, 1e-300)
+        out = V + (np.log(d) if (nd == 2 and coord == T.AF_XYZ) else 1 - 1 / d)
+        return np.where(d < 1, V, out)
+
+    t = T.build_tree(nd, 8, [8] * nd, lvl, None, coord_t=coord)
+    # the example's level set is |r - r0| / R - 1; the built-in sphere |r - r0| - R has the same roots and the same
+    # (scale-invariant) root mask, and is evaluated on the C side
+    el = S.electrode("sphere", nd, rod_r0=r0, rod_radius=R)
+    data = S.lsf_distances(t, el, S.lsf_opts(S.LSF_DIST_GSS, length_scale=1e-3))
+    assert any(t.lvl[int(b)] == 1 for b in data.ids)  # resolved on the coarse grid
+    o = Oracle(t, lsf_boundary_value=V)
+    o.set_bc(W.bc_dirichlet_function(t, sol))
+    o.set_lsf_distances(data.ids, data.dd.reshape(len(data.ids), -1))
+    o.mg_init()
+    res = []
+    for it in range(10):
+        o.fas_fmg(True, it > 0)
+        res.append(o.maxabs(M.I_TMP))
+    assert res[-1] < 1e-9 * res[0], res
+    leaves = t.leaves(lvl).astype(np.int32)
+    c = W.cell_centres(t, leaves, ghosts=True)
+    err = np.abs(o.get_cc(M.I_PHI, leaves).reshape(c.shape[:-1]) - sol(c))[W.interior(t)]
+    assert err.max() < 1.5e-2 and np.sqrt((err ** 2).mean()) < 2e-3, (err.max(), np.sqrt((err ** 2).mean()))
