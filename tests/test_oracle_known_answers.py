@@ -445,3 +445,36 @@ def test_implicit_diffusion_in_a_periodic_domain_follows_the_discrete_decay(ndim
             assert err < 1e-9, (k_factor, step, err)
         # the continuum decay exp(-2 D t) is matched to first order in dt and second order in h
         assert abs(amp - np.exp(-2 * D * 3 * dt)) < 0.6 * dt
+
+
+@pytest.mark.parametrize("ndim,seed", [(2, 1), (2, 2), (2, 3), (3, 4), (3, 5)])
+def test_ghost_cells_and_prolongation_exact_for_linear_field_on_random_trees(ndim, seed):
+    """afivo/examples/check_ghostcells.f90 / check_prolongation.f90 refine and derefine at random and assert that ghost
+    cells and prolongation reproduce a linear field exactly; here: random 2:1-balanced trees (level 1 refined, each finer box
+    with probability 0.4), all levels, sides + edges + corners, then a full correct_children pass."""
+    rng = np.random.default_rng(seed)
+    t = T.build_tree(ndim, 8, [16] * ndim if ndim == 2 else [8] * ndim, 4 if ndim == 2 else 3,
+                     lambda l, ixs, ctr: (rng.random(len(ixs)) < 0.4) | (l == 1))
+    assert t.highest_lvl >= 2
+    o = Oracle(t)
+    o.set_bc(W.bc_dirichlet_function(t, _linear))
+    o.mg_init()
+    ids = all_ids(t)
+    exact = _linear(W.cell_centres(t, ids, ghosts=True))
+    inner = W.interior(t)
+    data = np.zeros_like(exact)
+    data[inner] = exact[inner]
+    o.set_cc(I_PHI, ids, data)
+    for lvl in range(1, t.highest_lvl + 1):
+        o.gc_lvl(lvl, I_PHI, True)
+    got = o.get_cc(I_PHI, ids).reshape(exact.shape)
+    assert np.max(np.abs(got - exact)) < 1e-13
+    # prolongation: children of level-1 parents start from zero, tmp = 0, so the correction is the parent's phi
+    phi = exact.copy()
+    lvl2 = t.lvl[ids] == 2
+    phi[lvl2] = 0.0
+    o.set_cc(I_PHI, ids, phi)
+    o.set_cc(I_TMP, ids, np.zeros_like(phi))
+    o.correct_children(1)
+    got = o.get_cc(I_PHI, ids).reshape(exact.shape)
+    assert lvl2.any() and np.max(np.abs(got[lvl2][inner] - exact[lvl2][inner])) < 1e-13
