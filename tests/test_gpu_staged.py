@@ -6,6 +6,7 @@ run them with
 
 on a B200, fix what they find, and move the passing ones into the regular suites.  Each is the GPU twin of an
 oracle known-answer test that passes on the CPU (same problem set-up, so a failure points at the device path):
+(the test code itself -- shapes, thresholds -- was exercised on the CPU against an oracle-backed stand-in of mg_t)
 the reference's examples poisson_helmholtz, poisson_cyl_analytic, poisson_cyl_dielectric, poisson_lsf_test,
 helmholtz_variable_stencil (fully periodic domain), the two-rod electrode problem, and the native 2D electrode example."""
 import os
