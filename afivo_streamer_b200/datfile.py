@@ -169,6 +169,43 @@ class DatFile:
                 np.concatenate(dd).astype(np.float64), np.concatenate(lv) if iv is not None else None)
 
 
+def rebuild_stencil_entries(dat: "DatFile", eps: Optional[str] = None, operator_mask: int = -1,
+                            prolongation_type: int = 19):
+    """Entries for mg_t.set_stencils rebuilt from the DATA of a .dat file instead of its stored operator /
+    prolongation stencils: the permittivity variable `eps` and the stored level-set distance stencils
+    (mg_lsf_distance_key) go through the library's host-side builders (stencils.build_stencils = the reference's
+    mg_set_operators_lvl).  For files written without operator stencils (before mg_init, or by a tool that strips
+    them); for a file that has them the result equals DatFile.stencil_entries()."""
+    from . import stencils as S
+    t = dat.tree
+    nd, nc = t.ndim, t.nc
+    ncell = nc ** nd
+    eps_cc = None
+    if eps is not None:
+        ids = dat.ids_in_use()
+        eps_cc = np.ones((t.highest_id + 1,) + (nc + 2,) * nd)
+        eps_cc[ids] = dat.cc_of(eps, ids).reshape((len(ids),) + (nc + 2,) * nd)
+    lsf_data = None
+    ld = dat.lsf_distances(None)
+    if ld is not None:
+        ids, n_ent, cells, dd, _ = ld
+        dense = np.ones((len(ids), ncell, 2 * nd))
+        pos = 0
+        for b, n in enumerate(n_ent):
+            cx = cells[pos:pos + n] - 1
+            lin = np.zeros(n, np.int64)
+            for d in reversed(range(nd)):
+                lin = lin * nc + cx[:, d]
+            dense[b, lin] = dd[pos:pos + n]
+            pos += n
+        lsf_data = S.LsfData(np.asarray(ids, np.int32), dense, np.zeros((len(ids), ncell)), {}, None)
+    if eps_cc is None and lsf_data is None:
+        return []
+    entries, _ = S.build_stencils(t, eps_cc=eps_cc, lsf_data=lsf_data, operator_mask=operator_mask,
+                                  prolongation_type=prolongation_type)
+    return entries
+
+
 class _Cursor:
     def __init__(self, buf: bytes):
         self.buf = memoryview(buf)

@@ -380,12 +380,16 @@ def photoi_helmh_compute(tree: Tree, mg_helm, coeffs, max_fmg_cycles: int = 10, 
 
 def mg_from_dat(dat, phi="phi", rhs="rhs", eps=None, lsf="lsf", operator_key=1, prolongation_key=2, **opts):
     """Set a solver up from an afivo .dat file (datfile.DatFile) alone: topology, the boundary conditions
-    stored in the boxes for `phi`, phi / rhs (/ eps) data, the stored operator / prolongation stencils and
-    level-set distance stencils.  Returns (tree, mg) ready for mg_fas_fmg / mg_fas_vcycle."""
+    stored in the boxes for `phi`, phi / rhs (/ eps) data, the stored operator / prolongation stencils (rebuilt with
+    the library's builders from eps and the distance stencils when the file holds none) and level-set distance
+    stencils.  Returns (tree, mg) ready for mg_fas_fmg / mg_fas_vcycle."""
     tree = dat.tree
     mg = mg_t(sides_bc=dat.bc_table(phi), **opts)
     mg_init(tree, mg)
     entries = dat.stencil_entries(operator_key, prolongation_key, mg.operator_mask)
+    if not entries:  # a file without stored operator stencils: rebuild them from eps / the distance stencils
+        from .datfile import rebuild_stencil_entries
+        entries = rebuild_stencil_entries(dat, eps, mg.operator_mask, mg.prolongation_type)
     if entries:
         mg.set_stencils(entries)
     ids = dat.ids_in_use()

@@ -97,3 +97,54 @@ def test_wrong_version_and_wrong_ndim(tmp_path):
     open(path, "wb").write(raw)
     with pytest.raises(ValueError, match="incompatible file versions"):
         D.read_tree(path, ndim=3)
+
+
+@pytest.mark.parametrize("case", ["eps", "lsf", "eps_lsf_2d_cyl"])
+def test_stencils_rebuilt_from_file_data_equal_the_stored_ones(tmp_path, case):
+    """A .dat file holds the permittivity variable and the level-set distance stencils next to the operator /
+    prolongation stencils built from them: datfile.rebuild_stencil_entries (library builders on the file's data)
+    must give back exactly the stored stencils (here the oracle's), so files without stored operators are usable."""
+    import test_gpu_2d as G2
+    import test_gpu_stencils as G3
+    from oracle.oracle import Oracle
+    from util import bc_mixed
+    if case == "eps":
+        tree, eps, lsf, dist, bc_fn = T.corner_refined_tree(3, 8, 8, 3), G3.eps_smooth, None, None, bc_mixed
+    elif case == "lsf":
+        tree, eps, lsf, dist, bc_fn = T.corner_refined_tree(3, 8, 8, 3), None, G3.lsf_sphere, G3.lsf_distances, bc_mixed
+    else:
+        tree = T.build_tree(2, 8, [8, 8], 4, None, coord_t=T.AF_CYL)
+        eps, lsf, dist, bc_fn = G2.eps2, (lambda r: np.linalg.norm(r - np.array([0.0, 0.5]), axis=-1) - 0.2), \
+            G2.lsf_distances2, G2.bc_cyl
+    ids = np.concatenate(tree.lvl_ids).astype(np.int32)
+    bc = W.bc_table(tree, bc_fn)
+    orc = Oracle(tree, with_eps=eps is not None)
+    orc.set_bc(bc)
+    extra, lsf_dd = {}, None
+    if eps is not None:
+        e = np.ones((tree.highest_id + 1, tree.box_len))
+        e[ids] = eps(W.cell_centres(tree, ids, ghosts=True)).reshape(len(ids), -1)
+        orc.set_cc(3, ids, e[ids])
+        extra["eps"] = e
+    if lsf is not None:
+        lsf_dd = dist(tree, lsf)
+        orc.set_lsf_distances(*lsf_dd)
+    orc.mg_init()
+    path = str(tmp_path / "t.dat")
+    D.write_tree(path, make_dat(tree, orc, bc, extra_cc=extra, lsf_dd=lsf_dd))
+    dat = D.read_tree(path)
+    stored = dat.stencil_entries()
+    rebuilt = D.rebuild_stencil_entries(dat, "eps" if eps is not None else None)
+    assert stored and [e["box_id"] for e in stored] == [e["box_id"] for e in rebuilt]
+    nd = tree.ndim
+    default_p = np.array([9, 3, 3, 1]) / 16.0 if nd == 2 else np.array([27, 9, 9, 3, 9, 3, 3, 1]) / 64.0
+    for s, r in zip(stored, rebuilt):
+        assert s["tag"] == r["tag"] and s["op"][0] == r["op"][0] and bool(s.get("cyl")) == bool(r["cyl"])
+        assert np.array_equal(np.asarray(s["op"][1]).reshape(-1), np.asarray(r["op"][1]).reshape(-1)), s["box_id"]
+        assert (s.get("f") is None) == (r["f"] is None)
+        if r["f"] is not None:
+            assert np.array_equal(s["f"], r["f"])
+        if "prolong" in s:
+            rp = r.get("prolong") or (1, 3, default_p)
+            assert (s["prolong"][0], s["prolong"][1]) == (rp[0], rp[1])
+            assert np.array_equal(np.asarray(s["prolong"][2]).reshape(-1), np.asarray(rp[2]).reshape(-1))
