@@ -501,6 +501,14 @@ def mg_destroy(mg: mg_t):
     mg._h, mg.initialized = None, False
 
 
+def mg_use(tree: Tree, mg: mg_t):
+    """mg_use (afivo/src/m_af_multigrid.f90:118-126): "make sure box tags and operators are set".  The library keeps
+    the operators of a handle current itself (afmg_set_tree / afmg_set_stencils / afmg_update_operator_stencil), and
+    every mg_t has its own handle, so nothing is switched here; what remains is the reference's check."""
+    if not mg.initialized:
+        raise _lib.AfmgError(-4, "mg%initialized is false")  # error stop in the reference
+
+
 def mg_fas_fmg(tree: Tree, mg: mg_t, set_residual: bool, have_guess: bool):
     """mg_fas_fmg (afivo/src/m_af_multigrid.f90:137-180)."""
     mg._need_init()

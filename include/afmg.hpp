@@ -221,6 +221,10 @@ inline void mg_destroy(mg_t& mg) {
   mg.initialized = false;
 }
 
+// mg_use (:118-126): the library keeps the operators of a handle current itself and every mg_t owns its handle, so only
+// the reference's check remains
+inline void mg_use(const af_t&, const mg_t& mg) { mg.need_init(); }
+
 // mg_fas_fmg(tree, mg, set_residual, have_guess) (:137-180)
 inline void mg_fas_fmg(const af_t&, mg_t& mg, bool set_residual, bool have_guess) {
   mg.need_init();

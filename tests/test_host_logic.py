@@ -149,3 +149,13 @@ def test_tree_builder_reproduces_the_reference_refinement_counts_in_a_periodic_d
         assert t.ix[ids].sum(axis=1).min() == ndim  # the reference's "min" column: 3 (2 in 2D)
         if lvl >= 2:
             assert t.ix[ids].sum(axis=1).max() == max_ix_sum[lvl - 2], lvl
+
+
+def test_mg_use_checks_initialisation_like_the_reference():
+    from afivo_streamer_b200 import mg as M
+    from afivo_streamer_b200 import tree as T
+    from afivo_streamer_b200 import workloads as W
+    t = T.uniform_tree(3, 8, 8, 2)
+    mg = M.mg_t(sides_bc=W.bc_dirichlet_zero(t))
+    with pytest.raises(_lib.AfmgError, match="initialized is false"):  # m_af_multigrid.f90:122
+        M.mg_use(t, mg)
