@@ -181,3 +181,100 @@ def test_native_electrode_example_sets_up_the_same_problem_as_the_python_mirror(
     blob = np.concatenate([np.concatenate([np.asarray(e["op"][1]).reshape(-1), e["f"]]) for e in entries])
     assert int(n_blob) == blob.size
     assert abs(float(blob_sum) - blob.sum()) <= 1e-12 * np.abs(blob).sum()
+
+
+@pytest.fixture(scope="module")
+def dat_exe(tmp_path_factory):
+    lib_dir = os.path.join(ROOT, "afivo_streamer_b200")
+    exe = str(tmp_path_factory.mktemp("cpp") / "cpp_dat_dump")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp_dat_dump.cpp"), "-o", exe, "-L", lib_dir, "-lafmg",
+                           "-Wl,-rpath," + lib_dir])
+    return exe
+
+
+@pytest.mark.parametrize("case", ["plain3d", "eps_lsf_3d", "lsf_cyl_2d"])
+def test_cpp_dat_reader_matches_python_reader(dat_exe, tmp_path, case):
+    """include/afmg_dat.hpp (af_read_tree for compiled hosts) against afivo_streamer_b200/datfile.py on files written
+    by the Python writer: header, variables, topology, stored boundary conditions, and the stencil set handed to
+    afmg_set_stencils (descriptors and blob offsets equal, blob checksum equal)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_gpu_2d as G2
+    import test_gpu_stencils as G3
+    from afivo_streamer_b200 import datfile as D
+    from afivo_streamer_b200 import workloads as W
+    from dat_util import make_dat
+    from oracle.oracle import Oracle
+    from util import bc_mixed
+    if case == "plain3d":
+        tree, eps, lsf, dist, bc_fn = T.corner_refined_tree(3, 8, 8, 3), None, None, None, bc_mixed
+    elif case == "eps_lsf_3d":
+        tree, eps, lsf, dist, bc_fn = T.corner_refined_tree(3, 8, 8, 3), G3.eps_smooth, G3.lsf_sphere, G3.lsf_distances, bc_mixed
+    else:
+        tree = T.build_tree(2, 8, [8, 8], 4, lambda l, ix, c: np.linalg.norm(c - 0.5, axis=1) < 0.4, coord_t=T.AF_CYL)
+        eps, lsf, dist, bc_fn = None, G2.lsf_circle, G2.lsf_distances2, G2.bc_cyl
+    ids = np.concatenate(tree.lvl_ids).astype(np.int32)
+    bc = W.bc_table(tree, bc_fn)
+    orc = Oracle(tree, with_eps=eps is not None)
+    orc.set_bc(bc)
+    extra, lsf_dd = {}, None
+    if eps is not None:
+        e = np.ones((tree.highest_id + 1, tree.box_len))
+        e[ids] = eps(W.cell_centres(tree, ids, ghosts=True)).reshape(len(ids), -1)
+        orc.set_cc(3, ids, e[ids])
+        extra["eps"] = e
+    if lsf is not None:
+        lsf_dd = dist(tree, lsf)
+        orc.set_lsf_distances(*lsf_dd)
+    orc.mg_init()
+    rng = np.random.default_rng(5)
+    orc.set_cc(0, ids, rng.uniform(-1, 1, (len(ids), tree.box_len)))
+    orc.set_cc(1, ids, rng.uniform(-1, 1, (len(ids), tree.box_len)))
+    path = str(tmp_path / "t.dat")
+    D.write_tree(path, make_dat(tree, orc, bc, extra_cc=extra, lsf_dd=lsf_dd))
+    dat = D.read_tree(path)
+    out = subprocess.run([dat_exe, path], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rows = [ln.split() for ln in out.stdout.strip().splitlines()]
+    t = dat.tree
+    assert list(map(int, rows[0][1:])) == [t.ndim, t.highest_lvl, t.highest_id, t.nc, t.coord_t, int(dat.ready)]
+    assert float(rows[1][7]) == t.dr_base[0] and list(map(int, rows[1][1:1 + t.ndim])) == list(map(int, t.coarse_grid_size))
+    vrows = [r for r in rows if r[0] == "V"]
+    assert [r[1] for r in vrows] == dat.cc_names
+    for r, iv in zip(vrows, range(1, len(dat.cc_names) + 1)):
+        assert int(r[2]) == int(iv in dat.cc)
+        if iv in dat.cc:
+            assert abs(float(r[3]) - dat.cc[iv].sum()) <= 1e-11 * np.abs(dat.cc[iv]).sum()
+    n = t.highest_id
+    idr = np.arange(1, n + 1)
+    topo = int((t.lvl[idr].astype(np.int64) * 3 + t.parent[idr] * 5 + dat.tag[idr] * 7).sum()
+               + (t.ix[idr].astype(np.int64) * (11 + np.arange(t.ndim))).sum()
+               + (t.children[idr].astype(np.int64) * (1 + np.arange(1 << t.ndim))).sum()
+               + (t.neighbors[idr].astype(np.int64) * (2 + np.arange(2 * t.ndim))).sum())
+    assert int(next(r for r in rows if r[0] == "T")[1]) == topo
+    brow = next(r for r in rows if r[0] == "B")
+    assert int(brow[1]) == len(dat.bc) and int(brow[2]) == sum(int(b.bc_type.sum()) for b in dat.bc.values())
+    assert abs(float(brow[3]) - sum(b.bc_val.sum() for b in dat.bc.values())) < 1e-9
+    entries = dat.stencil_entries()
+    srow = next(r for r in rows if r[0] == "S")
+    drows = [list(map(int, r[1:])) for r in rows if r[0] == "D"]
+    assert int(srow[1]) == len(entries) == len(drows)
+    off, total = 0, 0.0
+    for e, dr in zip(entries, drows):
+        want = [e["box_id"], e["tag"], 0, int(bool(e.get("cyl", False))), 0, 0, 0, -1, 0]
+        if e.get("op") is not None:
+            want[2], want[6] = int(e["op"][0]), off
+            off += np.asarray(e["op"][1]).size
+            total += float(np.asarray(e["op"][1]).sum())
+        if e.get("f") is not None:
+            want[7] = off
+            off += e["f"].size
+            total += float(e["f"].sum())
+        if e.get("prolong") is not None:
+            want[4], want[5], want[8] = int(e["prolong"][0]), int(e["prolong"][1]), off
+            off += np.asarray(e["prolong"][2]).size
+            total += float(np.asarray(e["prolong"][2]).sum())
+        assert dr == want, (dr, want)
+    assert int(srow[2]) == off
+    assert abs(float(srow[3]) - total) <= 1e-9 * max(1.0, abs(total))
