@@ -244,3 +244,38 @@ def test_native_electrode_example_runs(cyl):
     assert res[5] < 1e-6 * res[0], res
     lo, hi = float(rows[-1][4]), float(rows[-1][5])
     assert lo > -1e-3 and hi < 1 + 1e-3
+
+
+def test_native_solve_dat_matches_python_solve_dat(tmp_path):
+    """tools/solve_dat (C++, include/afmg_dat.hpp) and tools/solve_dat.py print the same residual history for an
+    eps + electrode file written by the Python writer."""
+    import sys
+    import test_gpu_stencils as G3
+    from afivo_streamer_b200 import datfile as D
+    from dat_util import make_dat
+    from oracle.oracle import Oracle
+    from util import bc_mixed
+    tree = T.corner_refined_tree(3, 8, 8, 3)
+    ids = all_ids(tree)
+    bc = W.bc_table(tree, bc_mixed)
+    orc = Oracle(tree, with_eps=True, lsf_boundary_value=0.9)
+    orc.set_bc(bc)
+    e = np.ones((tree.highest_id + 1, tree.box_len))
+    e[ids] = G3.eps_smooth(W.cell_centres(tree, ids, ghosts=True)).reshape(len(ids), -1)
+    orc.set_cc(3, ids, e[ids])
+    lsf_dd = G3.lsf_distances(tree, G3.lsf_sphere)
+    orc.set_lsf_distances(*lsf_dd)
+    orc.mg_init()
+    rng = np.random.default_rng(5)
+    orc.set_cc(1, ids, rng.uniform(-1, 1, (len(ids), tree.box_len)))
+    path = str(tmp_path / "t.dat")
+    D.write_tree(path, make_dat(tree, orc, bc, extra_cc={"eps": e}, lsf_dd=lsf_dd))
+    py = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "solve_dat.py"), path, "--eps", "eps",
+                         "--lsf-boundary-value", "0.9"], capture_output=True, text=True, timeout=300)
+    cc = subprocess.run([os.path.join(ROOT, "tools", "solve_dat"), path, "3", "eps", "5", "0.9"], capture_output=True,
+                        text=True, timeout=300)
+    assert py.returncode == 0 and cc.returncode == 0, py.stderr + cc.stderr
+    pick = lambda out: [float(ln.split()[-1]) for ln in out.splitlines() if "residual" in ln]
+    a, b = pick(py.stdout), pick(cc.stdout)
+    assert len(a) == len(b) == 6
+    assert np.allclose(a, b, rtol=1e-6, atol=1e-12), (a, b)
