@@ -438,6 +438,68 @@ inline void af_gc_tree(const af_t&, mg_t& mg, int var, bool corners = true) {
   mg.check(afmg_gc_tree(mg.h, var, corners), "afmg_gc_tree");
 }
 
+// field_from_potential without dielectric (src/m_field.f90:543-547): gradient with norm, then af_gc_tree of the norm
+inline void field_from_potential(const af_t&, mg_t& mg, double fac = -1.0) {
+  mg.need_init();
+  mg.check(afmg_field_from_potential(mg.h, fac), "afmg_field_from_potential");
+}
+
+// box%fc(:, ..., i_fc) of the listed boxes: ndim * (nc+1)^ndim doubles per box, in the reference's element order
+inline std::vector<double> get_fc(const af_t& tree, mg_t& mg, const std::vector<int32_t>& ids) {
+  mg.need_init();
+  size_t per = (size_t)tree.ndim;
+  for (int d = 0; d < tree.ndim; ++d) per *= (size_t)(tree.n_cell + 1);
+  std::vector<double> out(ids.size() * per);
+  mg.check(afmg_download_fc(mg.h, (int32_t)ids.size(), ids.data(), out.data()), "afmg_download_fc");
+  return out;
+}
+
+// mg%lsf_boundary_function as data (m_af_types.f90:628): its values at the nc^ndim cell centres of the listed boxes,
+// e.g. from electrode_potential(); an empty list returns to the scalar mg%lsf_boundary_value
+inline void mg_set_lsf_boundary_values(const af_t&, mg_t& mg, const std::vector<int32_t>& ids, const std::vector<double>& values) {
+  mg.need_init();
+  mg.check(afmg_set_lsf_boundary_values(mg.h, (int32_t)ids.size(), ids.data(), values.data()), "afmg_set_lsf_boundary_values");
+}
+
+// The FMG / V-cycle convergence loop of field_compute (src/m_field.f90:491-524) run next to the device
+struct field_solve_result_t {
+  std::vector<double> residuals;
+  int n_fmg = 0, n_vcycles = 0;
+};
+inline field_solve_result_t field_solve(const af_t&, mg_t& mg, bool have_guess, double residual_threshold,
+                                        double max_residual = 1e8, int max_initial_iterations = 100, int num_vcycles = 2) {
+  mg.need_init();
+  field_solve_result_t r;
+  r.residuals.assign((size_t)max_initial_iterations + num_vcycles, 0.0);
+  int32_t n_fmg = 0, n_vc = 0;
+  mg.check(afmg_field_solve(mg.h, have_guess, residual_threshold, max_residual, max_initial_iterations, num_vcycles,
+                            r.residuals.data(), &n_fmg, &n_vc), "afmg_field_solve");
+  r.n_fmg = n_fmg;
+  r.n_vcycles = n_vc;
+  r.residuals.resize((size_t)n_fmg + n_vc);
+  return r;
+}
+
+// photoi_helmh_compute (src/m_photoi_helmh.f90:162-204) on the device: mg_helm = the mg_t of every mode
+// (helmholtz_lambda = lambdas(n)**2, boundary conditions photoi_helmh_bc), right-hand side uploaded to mg_helm[0]; the
+// source is read with mg_helm[0]->get_cc(AFMG_PHOTO, ...).  Returns the FMG count of every mode.
+inline std::vector<int32_t> photoi_helmh_compute(const af_t&, const std::vector<mg_t*>& mg_helm, const std::vector<double>& coeffs,
+                                                 int max_fmg_cycles = 10, double max_rel_residual = 1.0e-2,
+                                                 std::vector<double>* residuals = nullptr) {
+  if (mg_helm.empty() || coeffs.size() != mg_helm.size()) throw error(AFMG_ERR_ARG, "photoi_helmh_compute: one coefficient per mode");
+  std::vector<afmg_handle*> hs;
+  for (mg_t* m : mg_helm) {
+    m->need_init();
+    hs.push_back(m->h);
+  }
+  std::vector<int32_t> n_cycles(hs.size(), 0);
+  std::vector<double> res(hs.size(), 0.0);
+  mg_helm[0]->check(afmg_helmholtz_compute(hs.data(), (int32_t)hs.size(), coeffs.data(), max_fmg_cycles, max_rel_residual,
+                                           n_cycles.data(), res.data()), "afmg_helmholtz_compute");
+  if (residuals) *residuals = res;
+  return n_cycles;
+}
+
 // af_init followed by af_adjust_refinement until nothing is added: a 2:1 balanced 2D or 3D tree in the reference's
 // conventions -- level-1 ids i + (j-1) nx + (k-1) nx ny (m_af_core.f90:436-501), children appended parent by parent
 // in af_child_dix order (:1187-1254), neighbours / neighbor_mat with af_phys_boundary = -1 outside a non-periodic

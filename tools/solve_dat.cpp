@@ -34,6 +34,13 @@ int main(int argc, char** argv) {
       afmg::mg_fas_vcycle(t, mg, true);
       std::printf("V-cycle %d residual %.6e\n", i + 1, afmg::af_tree_maxabs_cc(t, mg, AFMG_TMP));
     }
+    afmg::field_from_potential(t, mg, -1.0);
+    const std::vector<int32_t> leaves = t.ids(true);
+    std::vector<double> fld(leaves.size() * t.box_len());
+    mg.get_cc(AFMG_FLD, leaves, fld.data());
+    double emax = 0;
+    for (double v : fld) emax = v > emax ? v : emax;  // ghost cells included: they mirror interior values or are interpolated
+    std::printf("max |E| on leaves %.6e\n", emax);
     afmg::mg_destroy(mg);
   } catch (const afmg::error& e) {
     std::fprintf(stderr, "error stop: %s (code %d)\n", e.what(), e.code);
