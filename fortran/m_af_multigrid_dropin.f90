@@ -61,14 +61,14 @@ contains
   end function slot_of
 
   subroutine mg_init(tree, mg)
-    type(af_t), intent(inout) :: tree !< Tree to do multigrid on
-    type(mg_t), intent(inout) :: mg   !< Multigrid options
+    type(af_t), intent(inout) :: tree ! the af_t the solver works on
+    type(mg_t), intent(inout) :: mg   ! the caller's mg_t
     call ref_mg_init(tree, mg)
     call mg_gpu_init(tree, mg, slot_of(mg, .true.))
   end subroutine mg_init
 
   subroutine mg_destroy(mg)
-    type(mg_t), intent(inout) :: mg   !< Multigrid options
+    type(mg_t), intent(inout) :: mg   ! the caller's mg_t
     integer                   :: slot
     slot = slot_of(mg, .false.)
     call mg_gpu_destroy(mg, slot)
@@ -79,27 +79,27 @@ contains
   end subroutine mg_destroy
 
   subroutine mg_fas_fmg(tree, mg, set_residual, have_guess)
-    type(af_t), intent(inout) :: tree         !< Tree to do multigrid on
-    type(mg_t), intent(inout) :: mg           !< Multigrid options
-    logical, intent(in)       :: set_residual !< If true, store residual in i_tmp
-    logical, intent(in)       :: have_guess   !< If false, start from phi = 0
+    type(af_t), intent(inout) :: tree         ! the af_t the solver works on
+    type(mg_t), intent(inout) :: mg           ! the caller's mg_t
+    logical, intent(in)       :: set_residual ! leave rhs - L(phi) in mg%i_tmp on return
+    logical, intent(in)       :: have_guess   ! .false.: phi is cleared first
     call mg_gpu_fas_fmg(tree, mg, set_residual, have_guess, slot_of(mg, .false.))
   end subroutine mg_fas_fmg
 
   subroutine mg_fas_vcycle(tree, mg, set_residual, highest_lvl, standalone)
-    type(af_t), intent(inout)     :: tree         !< Tree to do multigrid on
-    type(mg_t), intent(in)        :: mg           !< Multigrid options
-    logical, intent(in)           :: set_residual !< If true, store residual in i_tmp
-    integer, intent(in), optional :: highest_lvl  !< Maximum level for V-cycle
-    logical, intent(in), optional :: standalone   !< False if called by other cycle
+    type(af_t), intent(inout)     :: tree         ! the af_t the solver works on
+    type(mg_t), intent(in)        :: mg           ! the caller's mg_t
+    logical, intent(in)           :: set_residual ! leave rhs - L(phi) in mg%i_tmp on return
+    integer, intent(in), optional :: highest_lvl  ! cycle only up to this level
+    logical, intent(in), optional :: standalone   ! .false. when nested inside an FMG cycle
     call mg_gpu_fas_vcycle(tree, mg, set_residual, slot_of(mg, .false.), highest_lvl, standalone)
   end subroutine mg_fas_vcycle
 
   subroutine mg_update_operator_stencil(tree, mg, new_lsf, new_eps)
     type(af_t), intent(inout) :: tree
     type(mg_t), intent(inout) :: mg
-    logical, intent(in)       :: new_lsf !< Whether the lsf has changed
-    logical, intent(in)       :: new_eps !< Whether epsilon has changed
+    logical, intent(in)       :: new_lsf ! the level-set function changed
+    logical, intent(in)       :: new_eps ! the permittivity changed
     call ref_mg_update_operator_stencil(tree, mg, new_lsf, new_eps)
     call mg_gpu_update_operator_stencil(tree, mg, slot_of(mg, .false.))
   end subroutine mg_update_operator_stencil
@@ -107,8 +107,8 @@ contains
   subroutine mg_compute_phi_gradient(tree, mg, i_fc, fac, i_norm)
     type(af_t), intent(inout)     :: tree
     type(mg_t), intent(in)        :: mg
-    integer, intent(in)           :: i_fc !< Face-centered indices
-    real(dp), intent(in)          :: fac  !< Multiply with this factor
+    integer, intent(in)           :: i_fc ! face-centred variable that receives the field
+    real(dp), intent(in)          :: fac  ! field = fac * grad(phi)
     integer, intent(in), optional :: i_norm
     field_slot = slot_of(mg, .false.)
     call mg_gpu_compute_phi_gradient(tree, mg, i_fc, fac, field_slot, i_norm)
@@ -116,8 +116,8 @@ contains
 
   subroutine mg_compute_field_norm(tree, i_fc, i_norm)
     type(af_t), intent(inout) :: tree
-    integer, intent(in)       :: i_fc   !< Index of face-centered variable
-    integer, intent(in)       :: i_norm !< Index of cell-centered variable
+    integer, intent(in)       :: i_fc   ! face-centred field variable
+    integer, intent(in)       :: i_norm ! cell-centred variable that receives the norm
     call mg_gpu_compute_field_norm(tree, i_fc, i_norm, field_slot)
   end subroutine mg_compute_field_norm
 
