@@ -360,6 +360,48 @@ def photoi_helmh_bc(nb, coords):
     return AF_BC_NEUMANN, 0.0
 
 
+def photoi_helmh_parameters(author: str = "Bourdon-3", frac_O2: float = 0.2, gas_pressure: float = 1.0, eta: float = 1.0,
+                            lambdas=None, coeffs=None):
+    """The Helmholtz expansion of the photoionization source the streamer code offers (photoi_helmh%author,
+    src/m_photoi_helmh.f90:80-136): (lambdas [1/m], coeffs [1/m^2]) scaled by the O2 fraction and the pressure in bar
+    exactly as there; "custom" takes lambdas / coeffs and scales by the pressure only."""
+    if author != "custom" and frac_O2 <= 0.0:
+        raise ValueError("Photoionization: no oxygen present")  # error stop in the reference
+    if author == "Luque":
+        if abs(eta - 1.0) > 0:
+            raise ValueError("With Luque photoionization, photoi%eta should be 1.0")
+        lam, cf, scale = [4425.38, 750.06], [337557.38, 19972.14], (frac_O2 / 0.2) * gas_pressure
+    elif author == "Bourdon-2":
+        lam, cf, scale = [7305.62, 44081.25], [11814508.38, 998607256.0], frac_O2 * gas_pressure
+    elif author == "Bourdon-3":
+        lam, cf, scale = [4147.85, 10950.93, 66755.67], [1117314.935, 28692377.5, 2748842283.0], frac_O2 * gas_pressure
+    elif author == "custom":
+        if lambdas is None or coeffs is None or len(lambdas) < 1 or len(lambdas) != len(coeffs):
+            raise ValueError("Custom photoionization lambdas and coeffs missing.")
+        lam, cf, scale = list(lambdas), list(coeffs), gas_pressure
+    else:
+        raise ValueError(f"Unknown photoi_helmh_author: {author}")
+    return np.asarray(lam, float) * scale, np.asarray(cf, float) * scale ** 2
+
+
+def photoi_helmh_initialize(tree: Tree, author: str = "Bourdon-3", *, length_unit: float = 1.0, **kw):
+    """photoi_helmh_initialize (src/m_photoi_helmh.f90:138-156): one mg_t per mode with helmholtz_lambda =
+    lambdas(n)**2, mg_prolong_linear and photoi_helmh_bc, initialised on `tree`.  length_unit = metres per unit of the
+    tree's coordinates (lambdas are 1/m).  Returns (mg_helm, coeffs) for photoi_helmh_compute; device and the other
+    mg_t options pass through **kw, the parameter-set options (frac_O2, gas_pressure, eta, lambdas, coeffs) too."""
+    from . import workloads as W
+    par = {k: kw.pop(k) for k in ("frac_O2", "gas_pressure", "eta", "lambdas", "coeffs") if k in kw}
+    lam, cf = photoi_helmh_parameters(author, **par)
+    lam, cf = lam * length_unit, cf * length_unit ** 2
+    bc = W.bc_table(tree, photoi_helmh_bc)
+    mg_helm = []
+    for l in lam:
+        m = mg_t(sides_bc=bc, helmholtz_lambda=float(l ** 2), prolongation_type=MG_PROLONG_LINEAR, **kw)
+        mg_init(tree, m)
+        mg_helm.append(m)
+    return mg_helm, cf
+
+
 def photoi_helmh_compute(tree: Tree, mg_helm, coeffs, max_fmg_cycles: int = 10, max_rel_residual: float = 1.0e-2):
     """photoi_helmh_compute (src/m_photoi_helmh.f90:162-204) on the device: mg_helm = the mg_t of every mode
     (helmholtz_lambda = lambdas(n)**2), rhs uploaded to mg_helm[0]; the source is read with

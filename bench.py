@@ -360,8 +360,8 @@ def run_gpu(args):
     # ---- BASELINE.json configs[3]: the three Helmholtz photoionization solves on the standard_3d-like tree ----
     helm = None
     if world == 1 and args.workload == "S2":
-        lambdas = np.array([4147.85, 10950.93, 66755.67]) * 0.2 * 0.02   # Bourdon-3, 20 % O2 at 1 bar, 2 cm domain
-        coeffs = np.array([1117314.935, 28692377.5, 2748842283.0]) * (0.2 * 0.02) ** 2
+        lambdas, coeffs = M.photoi_helmh_parameters("Bourdon-3", frac_O2=0.2, gas_pressure=1.0)  # 1/m, 1/m^2
+        lambdas, coeffs = lambdas * 0.02, coeffs * 0.02 ** 2                                      # 2 cm domain
         from afivo_streamer_b200 import workloads as Wk
         hbc = Wk.bc_table(tree, M.photoi_helmh_bc)
         modes = []

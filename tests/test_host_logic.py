@@ -159,3 +159,22 @@ def test_mg_use_checks_initialisation_like_the_reference():
     mg = M.mg_t(sides_bc=W.bc_dirichlet_zero(t))
     with pytest.raises(_lib.AfmgError, match="initialized is false"):  # m_af_multigrid.f90:122
         M.mg_use(t, mg)
+
+
+def test_photoi_helmh_parameter_sets_are_the_references():
+    """src/m_photoi_helmh.f90:80-136: Luque scales by (frac_O2 / 0.2) p, Bourdon by frac_O2 p, coefficients by the
+    square; the reference's error stops become exceptions."""
+    from afivo_streamer_b200 import mg as M
+    lam, cf = M.photoi_helmh_parameters("Bourdon-3")
+    assert np.allclose(lam, np.array([4147.85, 10950.93, 66755.67]) * 0.2, rtol=1e-15)
+    assert np.allclose(cf, np.array([1117314.935, 28692377.5, 2748842283.0]) * 0.04, rtol=1e-15)
+    lam, cf = M.photoi_helmh_parameters("Bourdon-2", frac_O2=0.1, gas_pressure=0.5)
+    assert np.allclose(lam, np.array([7305.62, 44081.25]) * 0.05) and np.allclose(cf, np.array([11814508.38, 998607256.0]) * 0.0025)
+    lam, cf = M.photoi_helmh_parameters("Luque", frac_O2=0.2, gas_pressure=2.0)
+    assert np.allclose(lam, np.array([4425.38, 750.06]) * 2) and np.allclose(cf, np.array([337557.38, 19972.14]) * 4)
+    lam, cf = M.photoi_helmh_parameters("custom", gas_pressure=0.5, lambdas=[100.0], coeffs=[8.0])
+    assert lam[0] == 50.0 and cf[0] == 2.0
+    for bad in (dict(author="Luque", eta=0.5), dict(author="Bourdon-3", frac_O2=0.0), dict(author="custom"),
+                dict(author="Zheleznyak")):
+        with pytest.raises(ValueError):
+            M.photoi_helmh_parameters(**bad)
