@@ -92,6 +92,36 @@ def bc_field_homogeneous(tree: Tree, voltage: float = 1.0) -> BCTable:
     return bc_table(tree, fn)
 
 
+def bc_field_neumann(tree: Tree, voltage: float = 1.0) -> BCTable:
+    """field_bc_neumann (src/m_field.f90:614-634; field_bc_type = "neumann"): last dim Dirichlet 0 at the low side and
+    Neumann voltage / domain_len at the high side, others Neumann 0."""
+    nd = tree.ndim
+    length = float(tree.coarse_grid_size[nd - 1] * tree.dr_base[nd - 1])
+
+    def fn(nb, c):
+        if (nb - 1) // 2 == nd - 1:
+            return (AF_BC_DIRICHLET, 0.0) if nb % 2 == 1 else (AF_BC_NEUMANN, voltage / length)
+        return AF_BC_NEUMANN, 0.0
+
+    return bc_table(tree, fn)
+
+
+def bc_field_all_neumann(tree: Tree) -> BCTable:
+    """field_bc_all_neumann (src/m_field.f90:637-647; "all_neumann", used with electrodes that fix the potential)."""
+    return bc_neumann_zero(tree)
+
+
+def bc_field_all_dirichlet(tree: Tree) -> BCTable:
+    """field_bc_all_dirichlet (src/m_field.f90:650-669; the coaxial electrode set-up): Dirichlet 0 everywhere, except
+    zero flux on the axis of a cylindrical domain."""
+    cyl = tree.coord_t == 2
+
+    def fn(nb, c):
+        return (AF_BC_NEUMANN, 0.0) if (cyl and nb == 1) else (AF_BC_DIRICHLET, 0.0)
+
+    return bc_table(tree, fn)
+
+
 def bc_helmholtz(tree: Tree) -> BCTable:
     """photoi_helmh_bc (src/m_photoi_helmh.f90:210-228): last dim Dirichlet 0, others Neumann 0."""
     return bc_field_homogeneous(tree, 0.0)

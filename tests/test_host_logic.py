@@ -178,3 +178,26 @@ def test_photoi_helmh_parameter_sets_are_the_references():
                 dict(author="Zheleznyak")):
         with pytest.raises(ValueError):
             M.photoi_helmh_parameters(**bad)
+
+
+def test_field_boundary_condition_callbacks_of_the_streamer_code():
+    """field_bc_homogeneous / _neumann / _all_neumann / _all_dirichlet (src/m_field.f90:590-669) as rows of afmg_set_bc."""
+    from afivo_streamer_b200 import tree as T
+    from afivo_streamer_b200 import workloads as W
+    t3 = T.build_tree(3, 8, [8, 8, 16], 2, None, r_max=[1.0, 1.0, 2.0])
+    t2 = T.build_tree(2, 8, [8, 8], 2, None, coord_t=T.AF_CYL)
+
+    def rows(bc, nb):
+        m = bc.nbs == nb
+        return set(bc.types[m]), set(np.unique(bc.vals[m]))
+
+    h = W.bc_field_homogeneous(t3, 5.0)
+    assert rows(h, 5) == ({W.AF_BC_DIRICHLET}, {0.0}) and rows(h, 6) == ({W.AF_BC_DIRICHLET}, {5.0})
+    assert all(rows(h, nb) == ({W.AF_BC_NEUMANN}, {0.0}) for nb in (1, 2, 3, 4))
+    n = W.bc_field_neumann(t3, 5.0)
+    assert rows(n, 5) == ({W.AF_BC_DIRICHLET}, {0.0}) and rows(n, 6) == ({W.AF_BC_NEUMANN}, {2.5})  # voltage / domain_len(3)
+    a = W.bc_field_all_neumann(t3)
+    assert set(a.types) == {W.AF_BC_NEUMANN} and not a.vals.any()
+    d3, d2 = W.bc_field_all_dirichlet(t3), W.bc_field_all_dirichlet(t2)
+    assert set(d3.types) == {W.AF_BC_DIRICHLET}
+    assert rows(d2, 1) == ({W.AF_BC_NEUMANN}, {0.0}) and all(rows(d2, nb)[0] == {W.AF_BC_DIRICHLET} for nb in (2, 3, 4))
