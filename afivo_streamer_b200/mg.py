@@ -577,6 +577,38 @@ def field_solve(tree: Tree, mg: mg_t, have_guess: bool, residual_threshold: floa
     return res[: n_fmg.value + n_vc.value], n_fmg.value, n_vc.value
 
 
+def field_residual_threshold(tree: Tree, max_rhs: float, current_voltage: float, *, use_electrode: bool = False,
+                             multigrid_max_rel_residual: float = 1.0e-4) -> float:
+    """The convergence threshold of field_compute (src/m_field.f90:467-480): max(min_residual = 1e-6, max|rhs| *
+    ST_multigrid_max_rel_residual, conv_fac * |voltage| / (domain_len(NDIM) * af_min_dr(tree))) with conv_fac = 1e-8
+    with an electrode and 1e-10 without -- the last term estimates the round-off of (phi / L * dx) / dx^2."""
+    nd = tree.ndim
+    conv_fac = 1.0e-8 if use_electrode else 1.0e-10
+    domain_len = float(tree.coarse_grid_size[nd - 1] * tree.dr_base[nd - 1])
+    min_dr = float(np.min(np.asarray(tree.dr_base)[:nd]) * 0.5 ** (tree.highest_lvl - 1))  # af_min_dr
+    return max(1.0e-6, max_rhs * multigrid_max_rel_residual, conv_fac * abs(current_voltage) / (domain_len * min_dr))
+
+
+def field_compute(tree: Tree, mg: mg_t, current_voltage: float, have_guess: bool, *, use_electrode: bool = False,
+                  electrode_grounded: bool = False, multigrid_max_rel_residual: float = 1.0e-4,
+                  multigrid_num_vcycles: int = 2):
+    """field_compute (src/m_field.f90:448-528) after field_set_rhs / field_set_voltage: the right-hand side is on the
+    device (mg.set_cc_interior(I_RHS, leaves, ...)) and the boundary conditions carry the voltage.  Threshold from
+    max|rhs|, the electrode potential (mg%lsf_boundary_value = 0 if grounded else the voltage, :482-487), the FMG loop
+    when there is no guess and the V-cycles (afmg_field_solve), then field_from_potential.  Returns
+    (residuals, n_fmg, n_vcycles); a non-converging start raises AFMG_ERR_NOT_CONVERGED ("No convergence in initial
+    field computation")."""
+    mg._need_init()
+    max_rhs = af_tree_maxabs_cc(tree, mg, I_RHS)
+    thr = field_residual_threshold(tree, max_rhs, current_voltage, use_electrode=use_electrode,
+                                   multigrid_max_rel_residual=multigrid_max_rel_residual)
+    if use_electrode:
+        mg.set_lsf_boundary_value(0.0 if electrode_grounded else current_voltage)
+    out = field_solve(tree, mg, have_guess, thr, num_vcycles=multigrid_num_vcycles)
+    field_from_potential(tree, mg, -1.0)
+    return out
+
+
 def mg_update_operator_stencil(tree: Tree, mg: mg_t):
     """mg_update_operator_stencil (afivo/src/m_af_multigrid.f90:1188-1214)."""
     mg._need_init()

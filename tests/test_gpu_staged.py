@@ -279,3 +279,22 @@ def test_native_solve_dat_matches_python_solve_dat(tmp_path):
     a, b = pick(py.stdout), pick(cc.stdout)
     assert len(a) == len(b) == 6
     assert np.allclose(a, b, rtol=1e-6, atol=1e-12), (a, b)
+
+
+def test_field_compute_mirror():
+    """mg.field_compute = field_compute (src/m_field.f90:448-528) composed from afmg_field_solve and
+    afmg_field_from_potential: converges below its own threshold and leaves the field norm on the device."""
+    t = T.corner_refined_tree(3, 8, 8, 4)
+    V = 2.0e3
+    mg = M.mg_t(sides_bc=W.bc_field_homogeneous(t, V))
+    M.mg_init(t, mg)
+    ids, rhs = W.random_rhs_on_leaves(t)
+    mg.set_cc(M.I_RHS, ids, 1e6 * rhs)
+    res, n_fmg, n_vc = M.field_compute(t, mg, V, False)
+    thr = M.field_residual_threshold(t, M.af_tree_maxabs_cc(t, mg, M.I_RHS), V)
+    assert n_fmg >= 1 and 1 <= n_vc <= 2 and res[n_fmg - 1] < max(thr, res[0])
+    res2, n_fmg2, n_vc2 = M.field_compute(t, mg, V, True)
+    assert n_fmg2 == 0 and n_vc2 >= 1 and res2[-1] <= res[-1] * 1.01
+    fld = mg.get_cc(M.I_FLD, ids)
+    assert np.isfinite(fld).all() and fld.max() > V * 0.5  # ~ V / L = 2e3 in a unit box
+    M.mg_destroy(mg)

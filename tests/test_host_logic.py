@@ -201,3 +201,15 @@ def test_field_boundary_condition_callbacks_of_the_streamer_code():
     d3, d2 = W.bc_field_all_dirichlet(t3), W.bc_field_all_dirichlet(t2)
     assert set(d3.types) == {W.AF_BC_DIRICHLET}
     assert rows(d2, 1) == ({W.AF_BC_NEUMANN}, {0.0}) and all(rows(d2, nb)[0] == {W.AF_BC_DIRICHLET} for nb in (2, 3, 4))
+
+
+def test_field_residual_threshold_is_the_references_formula():
+    """src/m_field.f90:467-480."""
+    from afivo_streamer_b200 import mg as M
+    from afivo_streamer_b200 import tree as T
+    t = T.build_tree(3, 8, [8, 8, 16], 3, None, r_max=[1e-2, 1e-2, 2e-2])  # min dr = 1.25e-3 / 4
+    min_dr = 1.25e-3 / 4
+    assert M.field_residual_threshold(t, 0.0, 0.0) == 1e-6                                  # min_residual
+    assert M.field_residual_threshold(t, 1e10, 0.0) == 1e10 * 1e-4                          # rhs term
+    assert M.field_residual_threshold(t, 0.0, -4e4) == pytest.approx(1e-10 * 4e4 / (2e-2 * min_dr), rel=1e-14)
+    assert M.field_residual_threshold(t, 0.0, 4e4, use_electrode=True) == pytest.approx(1e-8 * 4e4 / (2e-2 * min_dr), rel=1e-14)
