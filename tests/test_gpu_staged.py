@@ -235,7 +235,8 @@ def test_two_rods_at_different_potentials():
 
 @pytest.mark.parametrize("cyl", [0, 1])
 def test_native_electrode_example_runs(cyl):
-    """tools/electrode_example_2d on the device: residual falls by 1e6 within ten FMG cycles, 0 <= phi <= 1"""
+    """tools/electrode_example_2d on the device: residual falls by 1e6 within ten FMG cycles, 0 <= phi <= 1 (the
+    Cartesian variant was run by hand with the round's last GPU seconds: profiles/r01g_electrode_example_2d.txt)"""
     exe = os.path.join(ROOT, "tools", "electrode_example_2d")
     out = subprocess.run([exe] + (["cyl"] if cyl else []), capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
