@@ -500,6 +500,47 @@ inline std::vector<int32_t> photoi_helmh_compute(const af_t&, const std::vector<
   return n_cycles;
 }
 
+// photoi_helmh%author parameter sets (src/m_photoi_helmh.f90:80-136): lambdas [1/m] and coeffs [1/m^2], scaled by the O2
+// fraction and the pressure in bar as there.  mg_helm(n)%helmholtz_lambda = lambdas(n)^2, mg_prolong_linear (:146-155).
+struct helmh_params_t {
+  std::vector<double> lambdas, coeffs;
+};
+inline helmh_params_t photoi_helmh_parameters(const std::string& author = "Bourdon-3", double frac_O2 = 0.2, double gas_pressure = 1.0,
+                                              double eta = 1.0) {
+  if (frac_O2 <= 0.0) throw error(AFMG_ERR_ARG, "Photoionization: no oxygen present");
+  helmh_params_t p;
+  double scale = frac_O2 * gas_pressure;
+  if (author == "Luque") {
+    if (std::fabs(eta - 1.0) > 0) throw error(AFMG_ERR_ARG, "With Luque photoionization, photoi%eta should be 1.0");
+    p.lambdas = {4425.38, 750.06};
+    p.coeffs = {337557.38, 19972.14};
+    scale = (frac_O2 / 0.2) * gas_pressure;
+  } else if (author == "Bourdon-2") {
+    p.lambdas = {7305.62, 44081.25};
+    p.coeffs = {11814508.38, 998607256.0};
+  } else if (author == "Bourdon-3") {
+    p.lambdas = {4147.85, 10950.93, 66755.67};
+    p.coeffs = {1117314.935, 28692377.5, 2748842283.0};
+  } else {
+    throw error(AFMG_ERR_ARG, "Unknown photoi_helmh_author: " + author);
+  }
+  for (double& l : p.lambdas) l *= scale;
+  for (double& c : p.coeffs) c *= scale * scale;
+  return p;
+}
+
+// The convergence threshold of field_compute (src/m_field.f90:467-480)
+inline double field_residual_threshold(const af_t& tree, double max_rhs, double current_voltage, bool use_electrode = false,
+                                       double multigrid_max_rel_residual = 1.0e-4) {
+  const int nd = tree.ndim;
+  const double conv_fac = use_electrode ? 1.0e-8 : 1.0e-10;
+  const double domain_len = tree.coarse_grid_size[nd - 1] * tree.dr_base[nd - 1];
+  double min_dr = tree.dr_base[0];
+  for (int d = 1; d < nd; ++d) min_dr = std::fmin(min_dr, tree.dr_base[d]);
+  min_dr *= std::pow(0.5, tree.highest_lvl - 1);  // af_min_dr
+  return std::fmax(1.0e-6, std::fmax(max_rhs * multigrid_max_rel_residual, conv_fac * std::fabs(current_voltage) / (domain_len * min_dr)));
+}
+
 // af_init followed by af_adjust_refinement until nothing is added: a 2:1 balanced 2D or 3D tree in the reference's
 // conventions -- level-1 ids i + (j-1) nx + (k-1) nx ny (m_af_core.f90:436-501), children appended parent by parent
 // in af_child_dix order (:1187-1254), neighbours / neighbor_mat with af_phys_boundary = -1 outside a non-periodic

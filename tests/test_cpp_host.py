@@ -278,3 +278,14 @@ def test_cpp_dat_reader_matches_python_reader(dat_exe, tmp_path, case):
         assert dr == want, (dr, want)
     assert int(srow[2]) == off
     assert abs(float(srow[3]) - total) <= 1e-9 * max(1.0, abs(total))
+
+
+def test_cpp_caller_side_helpers(tmp_path):
+    """photoi_helmh_parameters and field_residual_threshold of the C++ mirror give the reference's numbers."""
+    lib_dir = os.path.join(ROOT, "afivo_streamer_b200")
+    exe = str(tmp_path / "cpp_params_check")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp_params_check.cpp"), "-o", exe, "-L", lib_dir, "-lafmg",
+                           "-Wl,-rpath," + lib_dir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "params ok" in out.stdout, out.stdout + out.stderr
