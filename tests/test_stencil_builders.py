@@ -421,3 +421,30 @@ def test_poisson_lsf_test_spherical_electrode_against_its_analytic_potential(nd,
     c = W.cell_centres(t, leaves, ghosts=True)
     err = np.abs(o.get_cc(M.I_PHI, leaves).reshape(c.shape[:-1]) - sol(c))[W.interior(t)]
     assert err.max() < 1.5e-2 and np.sqrt((err ** 2).mean()) < 2e-3, (err.max(), np.sqrt((err ** 2).mean()))
+
+
+def test_stored_level_set_values_give_the_same_distances_as_evaluating_the_function():
+    """afmg_build_box_lsf_distances reads box%cc(IJK, mg%i_lsf) when the caller has it (the reference's path) and
+    evaluates mg%lsf at the cell centres otherwise: same mask, same distances; with a length scale the gradient search
+    takes its starting sign from the same values."""
+    L = _lib.lib()
+    nd, nc, dr = 3, 8, 0.125
+    centre = np.array([0.45, 0.55, 0.5])
+    lsf = lambda r: np.linalg.norm(r - centre) - 0.2
+    cb = _lib.LSF_FN(lambda r, _u: float(lsf(np.array([r[0], r[1], r[2]]))))
+    rm, drv = np.zeros(3), np.full(3, dr)
+    idx = np.arange(-1, nc + 1) + 0.5  # cell centres of cc(0:nc+1) along one dimension
+    zz, yy, xx = np.meshgrid(idx * dr, idx * dr, idx * dr, indexing="ij")
+    cc = np.linalg.norm(np.stack([xx, yy, zz], axis=-1) - centre, axis=-1) - 0.2
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    for opts in (S.lsf_opts(), S.lsf_opts(S.LSF_DIST_GSS, length_scale=dr / 4)):
+        out = []
+        for stored in (None, np.ascontiguousarray(cc).reshape(-1)):
+            mask, dd, nb = np.zeros(nc ** 3, np.uint8), np.zeros((nc ** 3, 6)), C.c_int32(0)
+            rc = L.afmg_build_box_lsf_distances(nd, nc, dp(rm), dp(drv), cb, None, C.byref(opts),
+                                                None if stored is None else dp(stored),
+                                                mask.ctypes.data_as(C.POINTER(C.c_uint8)), dp(dd), C.byref(nb))
+            assert rc == 0 and nb.value > 0
+            out.append((mask.copy(), dd.copy(), nb.value))
+        assert np.array_equal(out[0][0], out[1][0]) and out[0][2] == out[1][2]
+        assert np.max(np.abs(out[0][1] - out[1][1])) < 1e-12
