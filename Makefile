@@ -1,7 +1,7 @@
 # Convenience targets; the driver uses __graft_entry__.py, pytest and bench.py directly.
 PY ?= python
 
-.PHONY: build test-cpu test-gpu test-staged smoke bench bench-reference clean
+.PHONY: build test-cpu test-gpu smoke bench bench-reference clean
 
 build:            ## libafmg.so (nvcc, sm_100a), the CPU oracle + Hypre stand-in (g++/gcc), the native drivers in tools/
 	$(PY) __graft_entry__.py
@@ -11,9 +11,6 @@ test-cpu: build   ## oracle, host logic, builders, C / C++ / Fortran-shim consis
 
 test-gpu:         ## parity tests through the C ABI (needs a B200)
 	$(PY) -m pytest tests -q -m gpu
-
-test-staged:      ## GPU tests written after round 1's GPU budget ran out (not yet run on a device)
-	AFMG_RUN_STAGED=1 $(PY) -m pytest tests/test_gpu_staged.py -q -m gpu_staged
 
 smoke:
 	$(PY) __graft_entry__.py smoke

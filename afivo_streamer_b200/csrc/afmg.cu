@@ -772,6 +772,9 @@ void planes_from_ref(const double* v, int ncf, std::vector<double>& out) {
 int coarse_setup_dense(afmg_handle* h);
 
 int coarse_setup(afmg_handle* h) {
+  // the coarse buffers are reallocated below and the coarse path (separable / fused / dense) may change: cached
+  // graphs hold the old pointers and launch topology by value
+  drop_graphs(h);
   const int nc = h->o.n_cell, nc2 = h->nc2;
   const int nbox1 = nlev(h, 1);
   h->cs_dense = false;

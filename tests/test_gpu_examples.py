@@ -1,14 +1,9 @@
-"""STAGED GPU tests: written at the end of round 1, after the round's GPU minutes were spent, and therefore NOT yet
-run on a device.  They are skipped by default (marker gpu_staged, neither in `-m gpu` nor failing in `-m "not gpu"`);
-run them with
-
-    AFMG_RUN_STAGED=1 python -m pytest tests/test_gpu_staged.py -m gpu_staged -q
-
-on a B200, fix what they find, and move the passing ones into the regular suites.  Each is the GPU twin of an
-oracle known-answer test that passes on the CPU (same problem set-up, so a failure points at the device path):
-(the test code itself -- shapes, thresholds -- was exercised on the CPU against an oracle-backed stand-in of mg_t)
-the reference's examples poisson_helmholtz, poisson_cyl_analytic, poisson_cyl_dielectric, poisson_lsf_test,
-helmholtz_variable_stencil (fully periodic domain), the two-rod electrode problem, and the native 2D electrode example."""
+"""GPU twins of the reference's self-checking examples (each mirrors an oracle known-answer test that passes on the
+CPU, same problem set-up, so a failure points at the device path): poisson_helmholtz, poisson_cyl_analytic,
+poisson_cyl_dielectric, poisson_lsf_test, helmholtz_variable_stencil (fully periodic domain), the two-rod electrode
+problem, the native 2D electrode example, solve-from-.dat and the field_compute mirror.  Written at the end of round 1
+as "staged" tests; first run on a B200 in round 2 (profiles/r02a_staged_tests.log: 14 passed) and since then part of
+the regular `-m gpu` suite."""
 import os
 import subprocess
 
@@ -20,7 +15,7 @@ from afivo_streamer_b200 import stencils as S
 from afivo_streamer_b200 import tree as T
 from afivo_streamer_b200 import workloads as W
 
-pytestmark = pytest.mark.gpu_staged
+pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
