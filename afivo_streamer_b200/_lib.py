@@ -93,6 +93,9 @@ SYMBOLS = {
     "afmg_upload": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
     "afmg_download": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
     "afmg_upload_interior": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
+    "afmg_download_interior": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
+    "afmg_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "afmg_host_free": (None, [C.c_void_p]),
     "afmg_upload_device": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
     "afmg_download_device": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
     "afmg_clear": (C.c_int, [_H, _I]),
@@ -122,6 +125,7 @@ SYMBOLS = {
     "afmg_init_phi_rhs": (C.c_int, [_H]),
     "afmg_max_abs": (C.c_int, [_H, _I, _DP]),
     "afmg_tree_sum": (C.c_int, [_H, _I, _DP]),
+    "afmg_checksum": (C.c_int, [_H, _I, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "afmg_kernel_launches": (C.c_int64, [_H]),
     "afmg_last_cycle_ms": (C.c_int, [_H, _DP]),
     "afmg_set_profiling": (C.c_int, [_H, _I]),

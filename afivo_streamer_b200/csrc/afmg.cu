@@ -79,8 +79,10 @@ struct afmg_handle {
   double *d_coef = nullptr, *d_rule_c = nullptr, *d_rule_B = nullptr, *d_pcoef = nullptr;
   unsigned long long* d_scal = nullptr;  // [0] fused residual max, [1] generic max, [2] mean (double bits)
   double* d_boxsum = nullptr;
-  double* d_stage = nullptr;
+  double* d_stage = nullptr;  // two halves: chunk c uses half c & 1 (copy of c + 1 overlaps the kernel of c)
   size_t stage_bytes = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   int* d_stage_slots = nullptr;
   size_t stage_slots_n = 0;
   DevCtx cx{};
@@ -1197,11 +1199,17 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
     e = cudaGetDevice(&h->device);
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+    e = cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_consumed[b], cudaEventDisableTiming);
+  }
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_comm, sizeof(CommBlock));
   if (e == cudaSuccess) e = cudaMemset(h->d_comm, 0, sizeof(CommBlock));
   if (e == cudaSuccess) h->d_scal = h->d_comm->scal;  // address arithmetic only
+  if (e == cudaSuccess) e = cudaMemcpy(&h->d_comm->lsf_value, &opts->lsf_boundary_value, sizeof(double), cudaMemcpyHostToDevice);
   h->peers.p[0] = h->d_comm;
   if (const char* env = getenv("AFMG_PDL")) h->pdl = atoi(env) != 0;
   if (const char* env = getenv("AFMG_CS_FUSED")) h->cs_fused = atoi(env) != 0;
@@ -1252,6 +1260,11 @@ int afmg_destroy(afmg_handle* h) {
   cudaFree(h->d_comm);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
+  for (int b = 0; b < 2; ++b) {
+    if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
+    if (h->ev_consumed[b]) cudaEventDestroy(h->ev_consumed[b]);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaStreamDestroy(h->stream);
   delete h;
   return AFMG_OK;
@@ -1455,7 +1468,7 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
   h->cx.opoff = h->cx.foff = h->cx.poff = nullptr;
   h->cx.stv = nullptr;
   h->cx.rule_flag = nullptr;
-  h->cx.lsf_value = h->o.lsf_boundary_value;
+  h->cx.lsf_value_p = &h->d_comm->lsf_value;
   h->cx.bvoff = nullptr;  // the boundary-value list belongs to the previous tree
   h->cx.bv = nullptr;
   h->bv_ids.clear();
@@ -1560,9 +1573,10 @@ int afmg_set_lsf_boundary_value(afmg_handle* h, double value) {
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   h->o.lsf_boundary_value = value;
-  h->cx.lsf_value = value;  // a kernel argument: cached graphs are stale
-  if (h->s2) h->s2->cx.lsf_value = value;
-  drop_graphs(h);
+  // the kernels read it from device memory (DevCtx::lsf_value_p), so the cached graphs stay valid: the value
+  // changes with the applied voltage on every time step (src/m_field.f90:481-487)
+  CK(cudaMemcpyAsync(&h->d_comm->lsf_value, &h->o.lsf_boundary_value, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   h->resid_fresh = false;
   return AFMG_OK;
 }
@@ -1736,7 +1750,7 @@ int afmg_set_stencils(afmg_handle* h, int32_t n, const afmg_stencil_desc* desc, 
   h->cx.poff = h->d_poff;
   h->cx.stv = h->d_stv;
   h->cx.rule_flag = any ? h->d_rule_flag : nullptr;
-  h->cx.lsf_value = h->o.lsf_boundary_value;
+  h->cx.lsf_value_p = &h->d_comm->lsf_value;
   return AFMG_OK;
 }
 
@@ -1773,33 +1787,56 @@ static int transfer(afmg_handle* h, int var, int n, const int32_t* box_id, doubl
   }
   const size_t rec_len = interior ? (size_t)h->o.n_cell * h->o.n_cell * h->o.n_cell : (size_t)h->box_len;
   const size_t box_bytes = rec_len * sizeof(double);
-  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)256 << 20) / box_bytes));
-  int rc = ensure_stage(h, device_ptr ? 16 : (size_t)chunk * box_bytes, (size_t)n);
+  // host transfers go through a two-halves staging area: the PCIe copy of chunk c + 1 (copy stream) overlaps the
+  // pack / unpack kernel of chunk c (solver stream)
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)128 << 20) / box_bytes));
+  int rc = ensure_stage(h, device_ptr ? 16 : (size_t)2 * chunk * box_bytes, (size_t)n);
   if (rc) return rc;
   CK(cudaMemcpyAsync(h->d_stage_slots, slots.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  for (int q0 = 0; q0 < n; q0 += chunk) {
-    const int m = std::min(chunk, n - q0);
+  int c = 0;
+  bool used[2] = {false, false};
+  for (int q0 = 0; q0 < n; q0 += chunk, ++c) {
+    const int m = std::min(chunk, n - q0), hb = c & 1;
     double* hp = packed + (size_t)q0 * rec_len;
-    double* dp = device_ptr ? hp : h->d_stage;
+    double* dp = device_ptr ? hp : h->d_stage + (size_t)hb * chunk * rec_len;
     if (up) {
-      if (!device_ptr) CK(cudaMemcpyAsync(dp, hp, (size_t)m * box_bytes, cudaMemcpyHostToDevice, h->stream));
-      Launch L_(h, "unpack");
-      if (interior) {
-        DISPATCH_NC(h, NC, { launch_k(h, k_unpack_interior<NC>, m, 256, 0, h->d_cc[var], h->d_stage_slots + q0, m, dp); });
-      } else {
-        DISPATCH_NC(h, NC, { launch_k(h, k_unpack<NC>, m, 256, 0, h->d_cc[var], h->d_stage_slots + q0, m, dp); });
+      if (!device_ptr) {
+        if (used[hb]) CK(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[hb], 0));
+        CK(cudaMemcpyAsync(dp, hp, (size_t)m * box_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        CK(cudaEventRecord(h->ev_copied[hb], h->copy_stream));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_copied[hb], 0));
       }
+      {
+        Launch L_(h, "unpack");
+        if (interior) {
+          DISPATCH_NC(h, NC, { launch_k(h, k_unpack_interior<NC>, m, 256, 0, h->d_cc[var], h->d_stage_slots + q0, m, dp); });
+        } else {
+          DISPATCH_NC(h, NC, { launch_k(h, k_unpack<NC>, m, 256, 0, h->d_cc[var], h->d_stage_slots + q0, m, dp); });
+        }
+      }
+      if (!device_ptr) CK(cudaEventRecord(h->ev_consumed[hb], h->stream));
     } else {
+      if (!device_ptr && used[hb]) CK(cudaStreamWaitEvent(h->stream, h->ev_consumed[hb], 0));
       {
         Launch L_(h, "pack");
-        DISPATCH_NC(h, NC, { launch_k(h, k_pack<NC>, m, 256, 0, h->d_cc[var], h->d_stage_slots + q0, m, dp); });
+        if (interior) {
+          DISPATCH_NC(h, NC, { launch_k(h, k_pack_interior<NC>, m, 256, 0, h->d_cc[var], h->d_stage_slots + q0, m, dp); });
+        } else {
+          DISPATCH_NC(h, NC, { launch_k(h, k_pack<NC>, m, 256, 0, h->d_cc[var], h->d_stage_slots + q0, m, dp); });
+        }
       }
-      if (!device_ptr) CK(cudaMemcpyAsync(hp, dp, (size_t)m * box_bytes, cudaMemcpyDeviceToHost, h->stream));
+      if (!device_ptr) {
+        CK(cudaEventRecord(h->ev_copied[hb], h->stream));
+        CK(cudaStreamWaitEvent(h->copy_stream, h->ev_copied[hb], 0));
+        CK(cudaMemcpyAsync(hp, dp, (size_t)m * box_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+        CK(cudaEventRecord(h->ev_consumed[hb], h->copy_stream));
+      }
     }
+    used[hb] = true;
   }
-  if (up && var == AFMG_TMP) h->resid_fresh = false;
   if (up) h->resid_fresh = false;
   CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->copy_stream));
   CK(cudaStreamSynchronize(h->stream));  // slots vector and (pageable) host buffers must outlive the copies
   return AFMG_OK;
 }
@@ -1812,6 +1849,22 @@ int afmg_upload_interior(afmg_handle* h, int32_t var, int32_t n, const int32_t* 
 }
 int afmg_download(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, double* packed) {
   return transfer(h, var, n, box_id, packed, false, false);
+}
+int afmg_download_interior(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, double* packed) {
+  return transfer(h, var, n, box_id, packed, false, false, true);
+}
+// page-locked host memory for the caller's packed buffers: copies from / to it are true DMA transfers (a pageable
+// buffer is staged by the driver at a fraction of the PCIe rate)
+void* afmg_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void afmg_host_free(void* p) {
+  if (p) cudaFreeHost(p);
 }
 int afmg_upload_device(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, const double* packed) {
   return transfer(h, var, n, box_id, const_cast<double*>(packed), true, true);
@@ -2089,6 +2142,33 @@ int afmg_tree_sum(afmg_handle* h, int32_t var, double* out) {
       if (child0[q] < 0) s = s + fac * sums[q];
   }
   *out = s;
+  return AFMG_OK;
+}
+
+int afmg_checksum(afmg_handle* h, int32_t var, uint64_t* sum_out, uint64_t* xor_out) {
+  if (!h || !sum_out || !xor_out) return AFMG_ERR_ARG;
+  if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
+  if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
+  CK(cudaSetDevice(h->device));
+  unsigned long long* d_out = h->d_scal + 6;  // scal[6], scal[7]: not used by the reductions
+  CK(cudaMemsetAsync(d_out, 0, 2 * sizeof(unsigned long long), h->stream));
+  const double* base = h->o.ndim == 2 ? h->s2->cx.cc[var] : h->d_cc[var];
+  for (int l = 1; l <= h->L; ++l) {
+    const Range r = (h->nranks == 1) ? Range{0, h->nslots} : own(h, l);
+    const size_t n = (size_t)r.n * h->box_len;
+    if (n > 0) {
+      Launch L_(h, "checksum");
+      const int blocks = (int)std::min<size_t>((n + 1023) / 1024, 148 * 8);
+      launch_k(h, k_checksum, blocks, 256, 0, base + (size_t)r.s0 * h->box_len, n, d_out);
+    }
+    if (h->nranks == 1) break;
+  }
+  unsigned long long out[2] = {0, 0};
+  CK(cudaMemcpyAsync(out, d_out, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+  int rc = finish_op(h);
+  if (rc) return rc;
+  *sum_out = out[0];
+  *xor_out = out[1];
   return AFMG_OK;
 }
 

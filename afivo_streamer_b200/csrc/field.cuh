@@ -22,7 +22,8 @@ struct FieldCtx {
   const unsigned char* veps;  // [nslots] 1: iand(box%tag, operator_mask) == mg_veps_box; may be null
   const double* bc_c;         // [nbc*3]   boundary rule of the field norm per physical face (c0, c1, c2)
   const double* bc_B;         // [nbc*NF]  its boundary values (NF = nc^2 in 3D, nc in 2D)
-  double lsf_value;           // mg%lsf_boundary_value
+  const double* lsf_value_p;  // mg%lsf_boundary_value (device memory, see DevCtx::lsf_value_p)
+  __device__ __forceinline__ double lsf_value() const { return *lsf_value_p; }
   double inv_dr[AFMG_MAX_LVL][3];  // fac / box%dr per level
 };
 
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(256) k_lsf_fix3(DevCtx cx, FieldCtx fx, const 
       if (!(elsf[e] >= 0)) continue;
       int q[3] = {ecell[3 * e], ecell[3 * e + 1], ecell[3 * e + 2]};
       const double p = phi[L::interior(q[0], q[1], q[2])];
-      const double bc = bvp ? bvp[((q[0] + q[1] + q[2]) & 1) * L::NI + L::iidx((q[0] - 1) >> 1, q[1], q[2])] : fx.lsf_value;
+      const double bc = bvp ? bvp[((q[0] + q[1] + q[2]) & 1) * L::NI + L::iidx((q[0] - 1) >> 1, q[1], q[2])] : fx.lsf_value();
       const double idr = fx.inv_dr[lv][d];
       if (phase == 0) {
         const double dd = edd[6 * e + 2 * d + 1];
@@ -362,7 +363,7 @@ __global__ void k2_lsf_fix(Ctx cx, afmg::FieldCtx fx, const int* slots, const in
       if (!(elsf[e] >= 0)) continue;
       int q[2] = {ecell[2 * e], ecell[2 * e + 1]};
       const double p = phi[B::at(q[0], q[1])];
-      const double bc = bvp ? bvp[(q[0] - 1) + NC * (q[1] - 1)] : fx.lsf_value;
+      const double bc = bvp ? bvp[(q[0] - 1) + NC * (q[1] - 1)] : fx.lsf_value();
       const double idr = fx.inv_dr[lv][d];
       if (phase == 0) {
         const double dd = edd[4 * e + 2 * d + 1];

@@ -44,7 +44,8 @@ struct Ctx {
   const unsigned char* pk;   // [nslots] 0 default, 1 constant p248, 2 constant p234, 3 variable p234
   const long long* poff;
   const double* stv;
-  double lsf_value;
+  const double* lsf_value_p;  // see DevCtx::lsf_value_p (kernels3d.cuh)
+  __device__ __forceinline__ double lsf_value() const { return *lsf_value_p; }
   const long long* bvoff;    // [nslots] per-cell level-set boundary values (afmg_set_lsf_boundary_values), or null
   const double* bv;          // nc^2 per listed box, cell order (i fastest)
   double two_pi;         // 2 * acos(-1) as the host computes it (af_tree_sum_cc in cylindrical coordinates)
@@ -89,7 +90,7 @@ template <int NC>
 __device__ __forceinline__ double bc_corr2(const Ctx& cx, int slot, int i, int j, bool& has) {
   has = cx.opk && cx.foff[slot] >= 0;
   if (!has) return 0.0;
-  const double V = (cx.bvoff && cx.bvoff[slot] >= 0) ? cx.bv[cx.bvoff[slot] + (i - 1) + NC * (j - 1)] : cx.lsf_value;
+  const double V = (cx.bvoff && cx.bvoff[slot] >= 0) ? cx.bv[cx.bvoff[slot] + (i - 1) + NC * (j - 1)] : cx.lsf_value();
   return cx.stv[cx.foff[slot] + (i - 1) + NC * (j - 1)] * V;
 }
 
@@ -474,13 +475,17 @@ __global__ void k2_copy_boxes(double* var_base, const int* slots, int n, double*
 }
 
 // interior cells only: packed holds cc(1:nc, 1:nc) per box
-__global__ void k2_unpack_interior(double* var_base, const int* slots, int n, const double* packed, int nc) {
+__global__ void k2_unpack_interior(double* var_base, const int* slots, int n, double* packed, int nc, int up) {
   pdl_wait();
   const int q = blockIdx.x;
   if (q >= n || slots[q] < 0) return;
   double* a = var_base + (size_t)slots[q] * (nc + 2) * (nc + 2);
-  const double* b = packed + (size_t)q * nc * nc;
-  for (int t = threadIdx.x; t < nc * nc; t += blockDim.x) a[(t % nc + 1) + (nc + 2) * (t / nc + 1)] = b[t];
+  double* b = packed + (size_t)q * nc * nc;
+  for (int t = threadIdx.x; t < nc * nc; t += blockDim.x) {
+    double* cell = a + (t % nc + 1) + (nc + 2) * (t / nc + 1);
+    if (up) *cell = b[t];
+    else b[t] = *cell;
+  }
 }
 
 // ---- coarse grid: dense inverse of the BC-folded level-1 operator (cylindrical and variable stencils
@@ -515,7 +520,7 @@ __global__ void k2_cs_gather(Ctx cx, Coarse2 cs, int nbox1) {
     t = t + cs.b2r[((size_t)bx * 4 + f) * NC + fi] * cx.rule_B[(size_t)row * NC + fi];
   }
   if (cs.lsf_fac) {
-    const double V = (cx.bvoff && cx.bvoff[bx] >= 0) ? cx.bv[cx.bvoff[bx] + r] : cx.lsf_value;
+    const double V = (cx.bvoff && cx.bvoff[bx] >= 0) ? cx.bv[cx.bvoff[bx] + r] : cx.lsf_value();
     t = t + cs.lsf_fac[(size_t)bx * NC * NC + r] * V;
   }
   const int gi = cs.bix[bx * 2] * NC + i - 1, gj = cs.bix[bx * 2 + 1] * NC + j - 1;

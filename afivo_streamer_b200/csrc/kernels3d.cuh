@@ -45,7 +45,9 @@ struct DevCtx {
                              //          p234 (4), 3 variable p234 (4 planes [m][colour][NI])
   const long long* poff;     // [nslots] offset in stv
   const double* stv;         // coefficient pool
-  double lsf_value;          // mg%lsf_boundary_value
+  const double* lsf_value_p;  // mg%lsf_boundary_value, in device memory (CommBlock::lsf_value): it changes every
+                              // time step (the applied voltage), and cached graphs must stay valid
+  __device__ __forceinline__ double lsf_value() const { return *lsf_value_p; }
   // mg%lsf_boundary_function as data (afmg_set_lsf_boundary_values): per-cell boundary values [colour][NI] of the
   // boxes listed there, -1 / null: the scalar lsf_value
   const long long* bvoff;    // [nslots] offset in bv, or null
@@ -126,6 +128,7 @@ struct CommBlock {
   unsigned long long err;                    // != 0 after a barrier time-out
   unsigned long long scal[8];                // reduction scratch: [0] residual max, [1] generic max,
                                              // [2] mean, [4],[5] = [0],[1] combined over all ranks
+  double lsf_value;                          // mg%lsf_boundary_value (DevCtx::lsf_value_p points here)
 };
 struct CommPeers {
   CommBlock* p[AFMG_MAX_RANKS];
@@ -609,7 +612,7 @@ __device__ __forceinline__ double apply_gen(const DevCtx& cx, int kind, const do
   acc = acc + op_coef<NC>(cx, kind, sv, cf, 4, col, idx) * ldcell<NC>(box, i, j + 1, k);
   acc = acc + op_coef<NC>(cx, kind, sv, cf, 5, col, idx) * ldcell<NC>(box, i, j, k - 1);
   acc = acc + op_coef<NC>(cx, kind, sv, cf, 6, col, idx) * ldcell<NC>(box, i, j, k + 1);
-  if (fv) acc = acc - fv[col * L::NI + idx] * (bvp ? bvp[col * L::NI + idx] : cx.lsf_value);
+  if (fv) acc = acc - fv[col * L::NI + idx] * (bvp ? bvp[col * L::NI + idx] : cx.lsf_value());
   return acc;
 }
 
@@ -638,7 +641,7 @@ __global__ void __launch_bounds__(256) k_gsrb_gen(DevCtx cx, const int* list, in
     double r = grhs[col * COL + idx];
     double bc = 0.0;
     if (fv) {
-      bc = fv[col * NI + idx] * (bvp ? bvp[col * NI + idx] : cx.lsf_value);
+      bc = fv[col * NI + idx] * (bvp ? bvp[col * NI + idx] : cx.lsf_value());
       r = r + bc;
     }
     if (col == C) {
@@ -1193,6 +1196,28 @@ __global__ void k_maxabs(DevCtx cx, int slot0, int nbox, int var, unsigned long 
   if ((threadIdx.x & 31) == 0 && mx > 0.0) atomic_max_nonneg(maxabs_bits, mx);
 }
 
+// Order-independent bitwise checksum of whole box records (interior + ghost cells): wrapping sum and XOR of the
+// 64-bit patterns.  Used to prove that N-GPU solves are bit-identical to the 1-GPU solve (bench.py, mgpu_check).
+__global__ void k_checksum(const double* base, size_t n, unsigned long long* out) {
+  pdl_wait();
+  unsigned long long s = 0, x = 0;
+  const unsigned long long* p = reinterpret_cast<const unsigned long long*>(base);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long v = p[i];
+    s += v;
+    x ^= v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    x ^= __shfl_xor_sync(0xffffffffu, x, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out, s);
+    atomicXor(out + 1, x);
+  }
+}
+
 // per-leaf-box sums of the interior in (k,j,i) order (af_tree_sum_cc, m_af_utils.f90:966-1027); the
 // host adds fac(lvl) * sum in box order.  One warp per box is plenty (only used by subtract_mean).
 template <int NC>
@@ -1275,6 +1300,20 @@ __global__ void k_unpack_interior(double* var_base, const int* slots, int n, con
     box[o] = src[((k - 1) * NC + (j - 1)) * NC + (i - 1)];
   }
 }
+// interior cells only: packed receives cc(1:nc, 1:nc, 1:nc) per box
+template <int NC>
+__global__ void k_pack_interior(const double* var_base, const int* slots, int n, double* packed) {
+  pdl_wait();
+  using L = Lay3<NC>;
+  if ((int)blockIdx.x >= n || slots[blockIdx.x] < 0) return;
+  const double* box = var_base + (size_t)slots[blockIdx.x] * L::BOX;
+  double* dst = packed + (size_t)blockIdx.x * (NC * NC * NC);
+  // one thread per output cell (coalesced stores; the two colour blocks are read with stride 2)
+  for (int q = threadIdx.x; q < NC * NC * NC; q += blockDim.x) {
+    const int i = q % NC + 1, j = (q / NC) % NC + 1, k = q / (NC * NC) + 1;
+    dst[q] = box[L::interior(i, j, k)];
+  }
+}
 template <int NC>
 __global__ void k_pack(const double* var_base, const int* slots, int n, double* packed) {
   pdl_wait();
@@ -1335,7 +1374,7 @@ __global__ void k_cs_gather(DevCtx cx, CoarseCtx cs, int nbox1) {
   // level-set boundary inside the coarse grid (m_coarse_solver.f90:320-324)
   if (cs.lsf_fac) {
     const double* bvp = cx.bv_of(bx);
-    t = t + cs.lsf_fac[(size_t)bx * ncell + r] * (bvp ? bvp[((i + j + k) & 1) * L::NI + L::iidx((i - 1) >> 1, j, k)] : cx.lsf_value);
+    t = t + cs.lsf_fac[(size_t)bx * ncell + r] * (bvp ? bvp[((i + j + k) & 1) * L::NI + L::iidx((i - 1) >> 1, j, k)] : cx.lsf_value());
   }
   const int gi = cs.bix[bx * 3] * NC + i - 1, gj = cs.bix[bx * 3 + 1] * NC + j - 1, gk = cs.bix[bx * 3 + 2] * NC + k - 1;
   cs.v0[gi + cs.nx[0] * (gj + cs.nx[1] * gk)] = t;
@@ -1422,7 +1461,7 @@ __global__ void __launch_bounds__(1024) k_cs_fused(DevCtx cx, CoarseCtx cs, int 
     }
     if (cs.lsf_fac) {
       const double* bvp = cx.bv_of(bx);
-      t = t + cs.lsf_fac[(size_t)bx * ncell + r] * (bvp ? bvp[((i + j + k) & 1) * L::NI + L::iidx((i - 1) >> 1, j, k)] : cx.lsf_value);
+      t = t + cs.lsf_fac[(size_t)bx * ncell + r] * (bvp ? bvp[((i + j + k) & 1) * L::NI + L::iidx((i - 1) >> 1, j, k)] : cx.lsf_value());
     }
     const int gi = cs.bix[bx * 3] * NC + i - 1, gj = cs.bix[bx * 3 + 1] * NC + j - 1, gk = cs.bix[bx * 3 + 2] * NC + k - 1;
     a[gi + cs.nx[0] * (gj + cs.nx[1] * gk)] = t;

@@ -113,6 +113,19 @@ class mg_t:
         assert data.size == len(ids) * self._tree.nc ** self._tree.ndim
         self.upload_interior_ptr(var, ids, data.ctypes.data)
 
+    def download_interior_ptr(self, var, ids, host_ptr):
+        """Interior cells only (nc^ndim doubles per box) into a raw host pointer."""
+        ids = np.ascontiguousarray(ids, np.int32)
+        self._check(_lib.lib().afmg_download_interior(self._h, var, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                      host_ptr))
+
+    def get_cc_interior(self, var, ids):
+        self._need_init()
+        ids = np.ascontiguousarray(ids, np.int32)
+        out = np.empty((len(ids),) + (self._tree.nc,) * self._tree.ndim)
+        self.download_interior_ptr(var, ids, out.ctypes.data)
+        return out
+
     def download_ptr(self, var, ids, host_ptr):
         ids = np.ascontiguousarray(ids, np.int32)
         self._check(_lib.lib().afmg_download(self._h, var, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)), host_ptr))
@@ -289,6 +302,12 @@ class mg_t:
         v = C.c_double()
         self._check(_lib.lib().afmg_last_cycle_ms(self._h, C.byref(v)))
         return v.value
+
+    def checksum(self, var):
+        """(wrapping sum, xor) of the 64-bit patterns of `var` over the full records of this rank's boxes"""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(_lib.lib().afmg_checksum(self._h, var, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def kernel_launches(self):
         return int(_lib.lib().afmg_kernel_launches(self._h))

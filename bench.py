@@ -4,20 +4,28 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload S3|S1|S1r|S3s|S2]
 
 One step = one standalone ``mg_fas_vcycle(set_residual=.true.)`` (afivo/src/m_af_multigrid.f90:185)
-on the 3D Poisson benchmark tree of BASELINE.json configs[1]: uniform 256^3 grid of 16^3 boxes
-(``poisson_benchmark 16 16 5``, afivo/examples/poisson_benchmark.f90), rhs = 1, Dirichlet-0.
+on the default workload S3 = BASELINE.json configs[4]: the 1024^3-equivalent refined octree (512^3 uniform +
+level 7 on all but the outermost box layer, 16^3 boxes, 1.04e9 cells), the >= 1e8-cell tree the north-star
+target is quoted on; it fits one B200 and is used at every N (strong scaling).  ``--workload S1`` is
+BASELINE.json configs[1] (``poisson_benchmark 16 16 5``, afivo/examples/poisson_benchmark.f90: uniform 256^3,
+rhs = 1, Dirichlet-0), S2 the standard_3d-like channel tree (configs[2], [3]), S0 the 2D cylindrical one.
 Metric: cell-updates/s = Gauss-Seidel relaxations per V-cycle x K / device time of the K complete
 cycles (ghost fills, transfers, residual, coarse solve included).
 
   value     V-cycles replayed back to back with all data resident in HBM (CUDA events, max over ranks)
   e2e       the same step through the C ABI with HOST buffers: upload rhs (pinned) -> V-cycle ->
             max-norm of the residual -> download phi, copies inside the timed region
-  roofline  dominant kernel = the fused half-sweep k_gsrb on the finest level, timed per launch with
-            CUDA events (library profiling mode) right after the timed region
+  roofline  dominant kernel = the fused half-sweep k_gsrb2 on the finest level, timed per launch with
+            CUDA events (library profiling mode) right after the timed region; achieved = the bytes
+            the colour-split layout makes one launch move (COL + 2 NI + 6 NF doubles per box
+            = 15 B per cell for nc = 16) / that time; the reference-layout figure of SURVEY 8(d)
+            (30 B per cell) is reported next to it as reference_layout_equivalent
   cpu_baseline  the CPU oracle (OpenMP port of the reference path) on the box's host cores
 
-``--impl reference`` times the oracle port on the host cores for the same workload and metric (the
-Fortran reference cannot be built here: no Fortran compiler, Hypre not vendored).
+``--impl reference`` times the oracle port on all host cores for the same metric: on the SAME tree when
+the host has the memory for it (S3 needs ~50 GB), else on the bounded sample S3s (the Fortran reference
+cannot be built: no Fortran compiler here or on the GPU box, profiles/r02a_fortran_probe.txt; Hypre not
+vendored).
 """
 from __future__ import annotations
 
@@ -39,9 +47,19 @@ UNIT = "cell-updates/s"
 ALGO_BYTES_PER_CELL_HALFSWEEP = 24.0  # R phi, R rhs, W phi
 
 
-def algo_bytes_gsrb(nc):
-    # fused kernel = half-sweep pass + the face ghost fill that follows it: 24 + 96/nc B per cell
+def ref_layout_bytes_gsrb(nc):
+    # reference layout: half-sweep pass + the face ghost fill that follows it: 24 + 96/nc B per cell
     return ALGO_BYTES_PER_CELL_HALFSWEEP + 96.0 / nc
+
+
+def layout_bytes_gsrb_per_box(nc):
+    """Algorithmic bytes one half-sweep moves per box in the colour-split record layout (csrc/layout.cuh):
+    read the other colour's block (interior + its 6 ghost faces: COL), read the own colour's rhs (NI), write the own
+    colour's interior (NI), push six boundary layers into the neighbours' ghost faces (6 NF)."""
+    h = nc // 2
+    ni, nf = nc * nc * h, nc * h
+    col = ni + 6 * nf
+    return 8.0 * (col + 2 * ni + 6 * nf)
 
 
 def algo_bytes_vcycle(tree):
@@ -59,18 +77,38 @@ def algo_bytes_vcycle(tree):
     return total
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def host_ram_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) / 2 ** 20
+    except OSError:
+        pass
+    return 0.0
+
+
 def cpu_baseline(workload):
     name = CPU_SAMPLE.get(workload, workload)
     tree, bc, ids, rhs, desc = build_workload(name)
     n_cpu = 3
-    dt, cores, _ = time_oracle(tree, bc, ids, rhs, n_cpu, 1)
+    dt, cores, _, _ = time_oracle(tree, bc, ids, rhs, n_cpu, 1)
     cu = cell_updates_vcycle(tree)
     what = f"{n_cpu} full V-cycles (set_residual + max-norm) with the OpenMP oracle after 1 FMG + 1 warm-up on {name}"
     if name != workload:
         what += f" = the same shell-refined octree one level coarser ({tree.n_boxes * tree.nc ** 3 / 1e6:.0f} M cells), " \
                 f"a bounded sample of {workload} (cell-updates/s is size-independent at this scale)"
     return {"value": cu * n_cpu / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": what,
-            "vcycles_per_s_on_sample": n_cpu / dt}
+            "vcycles_per_s_on_sample": n_cpu / dt, "cpu_model": cpu_model()}
 
 
 def peaks():
@@ -187,60 +225,128 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def time_oracle(tree, bc, ids, rhs, steps, warmup):
-    """CPU oracle: `steps` V-cycles (set_residual + max-norm each), all host threads."""
+_M64 = (1 << 64) - 1
+_H1, _H2 = 0xBF58476D1CE4E5B9, 0x94D049BB133111EB  # splitmix64 finaliser
+
+
+def _s64(x):
+    x &= _M64
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def synthetic_rhs_host(leaf_index, box_len):
+    """The benchmark's right-hand side on the host: an integer hash (splitmix64 finaliser) of the global index
+    leaf * box_len + cell, mapped to (-1, 1).  Pure 64-bit integer arithmetic, so it is bit-identical to
+    synthetic_rhs_device(): the CPU arm and the GPU arm (at every N) solve the same problem."""
+    idx = (np.asarray(leaf_index, dtype=np.uint64)[:, None] * np.uint64(box_len)
+           + np.arange(box_len, dtype=np.uint64)[None, :]) + np.uint64(1)
+    with np.errstate(over="ignore"):
+        z = idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(_H1)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(_H2)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (2.0 ** -52) - 1.0
+
+
+def time_oracle(tree, bc, ids, rhs, steps, warmup, budget_s=None, rhs_from_hash=False):
+    """CPU oracle: `steps` V-cycles (set_residual + max-norm each), all host threads.  rhs_from_hash: generate the
+    benchmark rhs (synthetic_rhs_host) slab by slab instead of taking `rhs`.  budget_s bounds the timed region:
+    the loop stops after the step that crosses it.  Returns (seconds, threads, residual history, steps done)."""
+    from concurrent.futures import ThreadPoolExecutor
+
     from oracle.oracle import I_RHS, I_TMP, Oracle
     orc = Oracle(tree)
     # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its ranks when the variable
     # is unset, which would time a 1-thread run; AFMG_CPU_THREADS overrides
-    orc.set_num_threads(int(os.environ.get("AFMG_CPU_THREADS", 0)) or len(os.sched_getaffinity(0)))
+    nthr = int(os.environ.get("AFMG_CPU_THREADS", 0)) or len(os.sched_getaffinity(0))
+    orc.set_num_threads(nthr)
     orc.set_bc(bc)
-    orc.set_cc(I_RHS, ids, rhs)
+    if rhs_from_hash:
+        slab = 2048
+        starts = list(range(0, len(ids), slab))
+
+        def put(q0):
+            sel = np.arange(q0, min(len(ids), q0 + slab))
+            return q0, synthetic_rhs_host(sel, tree.box_len)
+        with ThreadPoolExecutor(max_workers=min(nthr, 16)) as ex:
+            for q0, data in ex.map(put, starts):
+                orc.set_cc(I_RHS, ids[q0:q0 + slab], data)
+    else:
+        orc.set_cc(I_RHS, ids, rhs)
     orc.mg_init()
     orc.fas_fmg(True, False)
+    hist = [orc.maxabs(I_TMP)]
     for _ in range(warmup):
         orc.fas_vcycle(True)
     t0 = time.perf_counter()
-    res = None
+    done = 0
     for _ in range(steps):
         orc.fas_vcycle(True)
-        res = orc.maxabs(I_TMP)
+        hist.append(orc.maxabs(I_TMP))
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
     dt = time.perf_counter() - t0
-    return dt, orc.num_threads(), res
+    return dt, orc.num_threads(), hist, done
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_name = CPU_SAMPLE.get(args.workload, args.workload)
-    tree, bc, ids, rhs, desc = build_workload(sample_name)
-    if sample_name != args.workload:
-        desc = build_workload(args.workload, want_rhs=False)[4] + f" [CPU steps run on the bounded sample {sample_name}: {desc}]"
-    steps = max(1, min(args.steps, 10))
-    dt, cores, _ = time_oracle(tree, bc, ids, rhs, steps, min(args.warmup, 1))
+    # the same tree as the GPU arm when the host can hold it (S3: 36 GB for the oracle's three variables), else
+    # the bounded sample (S3s, the same octree one level coarser)
+    need_gb = {"S3": 60.0}.get(args.workload, 0.0)
+    same = host_ram_gb() >= need_gb or os.environ.get("AFMG_REF_FULL") == "1"
+    if os.environ.get("AFMG_REF_FULL") == "0":
+        same = False
+    sample_name = args.workload if same else CPU_SAMPLE.get(args.workload, args.workload)
+    tree, bc, _, _, desc = build_workload(sample_name, want_rhs=False)
+    gpu_desc = build_workload(args.workload, want_rhs=False)[4] if sample_name != args.workload else desc
+    leaves = np.concatenate([tree.leaves(l) for l in range(1, tree.highest_lvl + 1)]).astype(np.int32)
+    if args.workload == "S1":
+        from afivo_streamer_b200 import workloads as W
+        ids, rhs = W.constant_rhs_on_leaves(tree, 1.0)
+        dt, cores, hist, steps = time_oracle(tree, bc, ids, rhs, args.steps, args.warmup, budget_s=150.0)
+    else:
+        dt, cores, hist, steps = time_oracle(tree, bc, leaves, None, args.steps, args.warmup, budget_s=150.0,
+                                             rhs_from_hash=True)
     cu = cell_updates_vcycle(tree)
     val = cu * steps / dt
-    sample = f"{steps} full V-cycles (set_residual + max-norm) of {sample_name} after 1 FMG"
+    sample = (f"{steps} full V-cycles (set_residual + max-norm) of {sample_name} after 1 FMG + {args.warmup} warm-up "
+              f"cycles; same rhs hash as the GPU arm" + ("" if same else
+              f"; bounded sample of {args.workload} (host memory {host_ram_gb():.0f} GB < {need_gb:.0f} GB)"))
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "n_boxes": tree.n_boxes, "n_cell": tree.nc, "levels": tree.highest_lvl},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": gpu_desc, "n_boxes": tree.n_boxes, "n_cell": tree.nc, "levels": tree.highest_lvl,
+                   "cells_all_levels": tree.n_boxes * tree.nc ** 3, "cpu_tree": desc, "same_tree_as_gpu_arm": bool(same)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "cpu_model": cpu_model(), "host_ram_gb": round(host_ram_gb(), 1)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU oracle (C++/OpenMP port of the reference path); the Fortran reference cannot be built here",
+        "residual": {"after_fmg": hist[0], "after_timed_cycles": hist[-1]},
+        "note": "CPU oracle (C++/OpenMP port of the reference path, oracle/afmg_oracle.cpp) on all host threads; the "
+                "Fortran reference cannot be built: no Fortran compiler in the image or on the GPU box "
+                "(profiles/r02a_fortran_probe.txt)",
     }
     print(json.dumps(out))
 
 
 def synthetic_rhs_device(torch, leaf_index, box_len):
-    """Deterministic pseudo-random rhs in (-1, 1), a function of the global (leaf index, cell) only, so
-    every GPU count solves the same problem; generated on the device in packed box order."""
-    base = torch.as_tensor(np.asarray(leaf_index, dtype=np.float64) * box_len, device="cuda")
-    idx = base[:, None] + torch.arange(box_len, dtype=torch.float64, device="cuda")[None, :]
-    v = torch.sin(idx * 12.9898) * 43758.5453
-    return ((v - torch.floor(v)) * 2.0 - 1.0).reshape(-1)
+    """Deterministic pseudo-random rhs in (-1, 1), a function of the global (leaf index, cell) only, so every GPU
+    count -- and the CPU arm, synthetic_rhs_host() -- solves the same problem; generated on the device in packed box
+    order.  int64 arithmetic wraps like uint64; logical right shifts are arithmetic shifts + mask."""
+    base = torch.as_tensor(np.asarray(leaf_index, dtype=np.int64) * box_len, device="cuda")
+    z = (base[:, None] + torch.arange(box_len, dtype=torch.int64, device="cuda")[None, :]) + 1
+
+    def lsr(x, n):
+        return torch.bitwise_and(torch.bitwise_right_shift(x, n), (1 << (64 - n)) - 1)
+    z = z * _s64(0x9E3779B97F4A7C15)
+    z = torch.bitwise_xor(z, lsr(z, 30)) * _s64(_H1)
+    z = torch.bitwise_xor(z, lsr(z, 27)) * _s64(_H2)
+    z = torch.bitwise_xor(z, lsr(z, 31))
+    return (lsr(z, 11).to(torch.float64) * (2.0 ** -52) - 1.0).reshape(-1)
 
 
 def run_gpu(args):
@@ -329,6 +435,16 @@ def run_gpu(args):
     ms_max = allmax(ms)
     launches = int(allsum(l1 - l0))
     res1 = M.af_tree_maxabs_cc(tree, mg, M.I_TMP)
+    # bitwise checksum of phi (whole records, ghost cells included) over all boxes of all ranks after the same
+    # W + K cycles: equal at every N when the partitioned solve is bit-identical to the single-GPU one
+    csum, cxor = mg.checksum(M.I_PHI)
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, (csum, cxor))
+        csum, cxor = 0, 0
+        for a, b in parts:
+            csum = (csum + a) & _M64
+            cxor ^= b
     cu = mg.cell_updates(0, False)  # whole tree, all ranks together
     value = cu * args.steps / (ms_max * 1e-3)
 
@@ -429,31 +545,60 @@ def run_gpu(args):
     g_ms, g_calls = prof.get(top, (0.0, 0))
     peak, peak_src = peaks()
     roof = None
-    if g_calls:
-        cells = mg.own_boxes(tree.highest_lvl) * tree.nc ** 3  # finest-level cells this rank sweeps per launch
-        per_launch_bytes = algo_bytes_gsrb(tree.nc) * cells
+    if g_calls and tree.ndim == 3:
+        own = mg.own_boxes(tree.highest_lvl)   # finest-level boxes this rank sweeps per launch
+        cells = own * tree.nc ** 3
+        per_launch_bytes = layout_bytes_gsrb_per_box(tree.nc) * own
         dur = g_ms / g_calls * 1e-3
         achieved = per_launch_bytes / dur / 1e9
-        traffic = None
+        # DRAM traffic of one launch from the ncu --set full capture of this kernel (dram__bytes_read + write, N = 1),
+        # per box, times the boxes THIS rank sweeps: profiles/gsrb_traffic.json says which capture it came from
+        traffic = traffic_src = None
         tpath = os.path.join(ROOT, "profiles", "gsrb_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(args.workload)
+                t = json.load(open(tpath)).get(args.workload)
+                if t:
+                    traffic = t["dram_bytes_per_box"] * own
+                    traffic_src = t["source"]
             except Exception:
                 traffic = None
-        cyc_bytes = algo_bytes_vcycle(tree)
+        # whole V-cycle: DRAM bytes of all its launches from the ncu launch list (N = 1), against the cycle time
+        whole = {"reference_layout_bytes_per_vcycle": algo_bytes_vcycle(tree)}
+        wpath = os.path.join(ROOT, "profiles", "vcycle_dram.json")
+        if os.path.exists(wpath):
+            try:
+                w = json.load(open(wpath)).get(args.workload)
+                if w:
+                    per_gpu = w["dram_bytes_per_vcycle"] / world
+                    cyc_s = ms_max / args.steps * 1e-3
+                    whole.update({"dram_bytes_per_gpu": per_gpu, "dram_GBs_per_gpu": per_gpu / cyc_s / 1e9,
+                                  "frac_per_gpu": per_gpu / cyc_s / 1e9 / peak, "source": w["source"]})
+            except Exception:
+                pass
         roof = {"bound": "hbm", "kernel": "k_gsrb2 (finest level, rank 0)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": per_launch_bytes, "launch_us": dur * 1e6,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": per_launch_bytes,
+                "algorithmic_bytes_per_cell": layout_bytes_gsrb_per_box(tree.nc) / tree.nc ** 3,
+                "launch_us": dur * 1e6, "boxes_per_launch": own,
                 "share_of_step": g_ms / total_prof if total_prof else None,
-                "whole_cycle": {"algorithmic_bytes_per_vcycle": cyc_bytes,
-                                "achieved_GBs_per_gpu": cyc_bytes / (ms_max / args.steps * 1e-3) / 1e9 / world,
-                                "frac_per_gpu": cyc_bytes / (ms_max / args.steps * 1e-3) / 1e9 / world / peak}}
+                "reference_layout_equivalent": {
+                    "bytes_per_cell": ref_layout_bytes_gsrb(tree.nc),
+                    "GBs": ref_layout_bytes_gsrb(tree.nc) * cells / dur / 1e9,
+                    "note": "SURVEY 8(d) counts 24 + 96/nc B per cell for the reference's record layout; the "
+                            "colour-split layout moves half of it, so this figure is not a roofline fraction"},
+                "whole_cycle": whole}
+    barrier_stat = None
+    if world > 1:
+        b_ms, b_calls = prof.get("barrier", (0.0, 0))
+        barrier_stat = {"ms_per_cycle_rank0": b_ms / nprof, "count_per_cycle": b_calls / nprof}
 
     # ---- CPU baseline on the host cores (rank 0, N=1 only): bounded sample ---------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(args.workload)
+
 
     if rank == 0:
         out = {
@@ -472,6 +617,10 @@ def run_gpu(args):
             "field_from_potential": field,
             "helmholtz_photoionization": helm,
             "residual": {"after_fmg": res0, "after_timed_cycles": res1},
+            "phi_checksum": {"sum_u64": f"{csum:016x}", "xor_u64": f"{cxor:016x}",
+                             "what": "wrapping sum / xor of the bit patterns of phi over the complete records of all "
+                                     "boxes, all ranks combined, after the FMG + W + K cycles"},
+            "barrier": barrier_stat,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                     "steps": e2e_steps, "ms_per_step": 1e3 * wall_max / e2e_steps},
             "gpu_launches": launches,

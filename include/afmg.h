@@ -21,6 +21,7 @@
 #ifndef AFMG_H
 #define AFMG_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -253,6 +254,16 @@ int afmg_download(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id,
  * device are left as they are.  For the right-hand side, whose ghost cells are never read (callers set rhs
  * on the interior of leaves only, src/m_field.f90:422-435): 30 % fewer bytes over PCIe for nc = 16. */
 int afmg_upload_interior(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, const double* packed);
+/* download of interior cells only (nc^ndim doubles per box): what a caller needs when it refills the ghost cells
+ * itself or only reads cell centres (af_loop_box kernels over cc(1:nc, ...), e.g. the particle / fluid updates that
+ * follow field_compute); the ghost cells of phi stay valid on the device. */
+int afmg_download_interior(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, double* packed);
+/* Page-locked host buffers for `packed`: upload / download split a transfer into chunks and overlap the PCIe copy
+ * of one chunk with the pack / unpack kernel of the previous one; with page-locked memory the copies are DMA
+ * transfers at the full PCIe rate (pageable memory is staged by the driver).  The Fortran shim packs box%cc into
+ * such a buffer (c_f_pointer) instead of an allocatable temporary.  NULL on failure. */
+void* afmg_host_alloc(size_t bytes);
+void afmg_host_free(void* p);
 int afmg_upload_device(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id_host,
                        const double* packed_device);
 int afmg_download_device(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id_host,
@@ -351,6 +362,11 @@ int afmg_init_phi_rhs(afmg_handle* h);                                    /* :77
  * af_tree_sum_cc (m_af_utils.f90:966-1027, volume-weighted leaf sum) */
 int afmg_max_abs(afmg_handle* h, int32_t var, double* out);
 int afmg_tree_sum(afmg_handle* h, int32_t var, double* out);
+/* Order-independent bitwise checksum of a variable over the complete records (interior and ghost cells) of the
+ * boxes this rank owns: wrapping sum and XOR of the 64-bit patterns.  Combining the ranks' values (sum mod 2^64,
+ * XOR) gives the checksum of the whole tree, equal for every number of GPUs when the solves are bit-identical
+ * (the reference has no such routine; it is the evidence tool for "ghost-cell and index mapping bit-exact"). */
+int afmg_checksum(afmg_handle* h, int32_t var, uint64_t* sum_out, uint64_t* xor_out);
 
 /* ---- instrumentation ------------------------------------------------------------------------- */
 /* number of kernel launches the handle issued since creation (graph nodes counted per replay) */

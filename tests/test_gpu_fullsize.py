@@ -101,6 +101,88 @@ def test_s3s_refined_octree_converges():
     M.mg_destroy(mg)
 
 
+def parity_with_oracle(tree, rhs, n_v, n_finest):
+    """1 FMG + n_v V-cycles on the GPU and on the CPU oracle from the same leaf rhs (interior cells): the residual
+    histories agree to the rounding floor of rhs - L(phi), the potentials to 1e-10 relative max-norm."""
+    from oracle.oracle import Oracle
+    bc = W.bc_field_homogeneous(tree, 1.0)
+    ids = leaves_of(tree)
+    orc = Oracle(tree)
+    orc.set_bc(bc)
+    orc.mg_init()
+    for q0 in range(0, len(ids), 4096):  # slabs bound the host memory of the ghost-padded copy
+        sub = ids[q0:q0 + 4096]
+        full = W.box_array(tree, len(sub))
+        full[W.interior(tree)] = rhs[q0:q0 + 4096]
+        orc.set_cc(M.I_RHS, sub, full)
+    mg = M.mg_t(sides_bc=bc)
+    M.mg_init(tree, mg)
+    mg.set_cc_interior(M.I_RHS, ids, rhs)
+    ho, hg = [], []
+    orc.fas_fmg(True, False)
+    M.mg_fas_fmg(tree, mg, True, False)
+    for _ in range(n_v):
+        ho.append(orc.maxabs(M.I_TMP))
+        hg.append(M.af_tree_maxabs_cc(tree, mg, M.I_TMP))
+        orc.fas_vcycle(True)
+        M.mg_fas_vcycle(tree, mg, True)
+    ho.append(orc.maxabs(M.I_TMP))
+    hg.append(M.af_tree_maxabs_cc(tree, mg, M.I_TMP))
+    ho, hg = np.array(ho), np.array(hg)
+    assert np.all(ho[1:] < 0.3 * ho[:-1]) or ho[-1] < 1e-8 * ho[0], ho
+    floor = 16 * np.finfo(float).eps * 7 * float(n_finest) ** 2
+    assert np.all(np.abs(ho - hg) <= floor + 1e-6 * ho), (ho, hg, floor)
+    worst = scale = 0.0
+    allb = np.concatenate(tree.lvl_ids).astype(np.int32)
+    for q0 in range(0, len(allb), 2048):
+        sub = allb[q0:q0 + 2048]
+        a = orc.get_cc(M.I_PHI, sub)
+        b = mg.get_cc(M.I_PHI, sub).reshape(len(sub), -1)
+        worst = max(worst, float(np.max(np.abs(a - b))))
+        scale = max(scale, float(np.max(np.abs(a))))
+    # one-shot interior download of all leaves (many staging chunks, copies overlapping the pack kernels)
+    inner = mg.get_cc_interior(M.I_PHI, ids)
+    for q0 in range(0, len(ids), 4096):
+        a = orc.get_cc(M.I_PHI, ids[q0:q0 + 4096]).reshape((-1,) + (tree.nc + 2,) * 3)[W.interior(tree)]
+        assert np.max(np.abs(a.reshape(inner[q0:q0 + 4096].shape) - inner[q0:q0 + 4096])) <= 1e-10 * scale
+    del inner
+    M.mg_destroy(mg)
+    assert worst <= 1e-10 * scale, worst / scale
+    return ho, hg, worst / scale
+
+
+def test_s3s_parity_with_oracle():
+    """The bounded CPU sample of the benchmark (S3s: 256^3 uniform + refined shell, 1.1e8 cells, closed refinement
+    boundary): 1 FMG + 5 V-cycles, GPU vs oracle on all boxes of all levels."""
+    tree = T.shell_tree(16, 16, 5)
+    rhs = np.random.default_rng(2).uniform(-1, 1, (len(leaves_of(tree)), 16, 16, 16))
+    parity_with_oracle(tree, rhs, 5, 512)
+
+
+def _host_ram_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable"):
+                    return int(line.split()[1]) / 2 ** 20
+    except OSError:
+        pass
+    return 0.0
+
+
+@pytest.mark.skipif(_host_ram_gb() < 110, reason="S3 on the CPU oracle needs ~80 GB of host memory")
+def test_s3_benchmark_tree_parity_with_oracle():
+    """THE benchmarked configuration (bench.py default, BASELINE.json configs[4]): S3, 1.04e9 cells, 253 449 boxes.
+    1 FMG + 2 V-cycles on the GPU and on the oracle (36 GB for its three variables), all boxes compared."""
+    tree = T.shell_tree(16, 16, 6)
+    n = len(leaves_of(tree))
+    rhs = np.empty((n, 16, 16, 16))
+    rng = np.random.default_rng(3)
+    for q0 in range(0, n, 8192):
+        rhs[q0:q0 + 8192] = rng.uniform(-1, 1, rhs[q0:q0 + 8192].shape)
+    parity_with_oracle(tree, rhs, 2, 1024)
+
+
 def test_s1r_full_size_parity_with_oracle():
     """BASELINE.md S1r at its full size (256^3 = poisson_benchmark 16 16 5): random rhs on the leaves,
     field_bc_homogeneous with voltage 1 (Dirichlet 0 / 1 in z, Neumann 0 in x, y), 1 FMG + 10 V-cycles: same

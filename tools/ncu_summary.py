@@ -74,8 +74,75 @@ def vcycle_windows(path, finest_grid, all_grid):
     return out
 
 
+def vcycle_dram(path, all_grid, workload=None, out_json=None):
+    """Launch list taken with --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum: per complete
+    V-cycle (the launches between two final residuals over all boxes) the summed duration and DRAM bytes, and a
+    per-kernel table of the last complete cycle.  Optionally records the figure in a json bench.py reads."""
+    import json
+    rows = list(csv.reader(open(path, errors="ignore")))
+    start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    col = {h: i for i, h in enumerate(rows[start])}
+    by_id = {}
+    order = []
+    for r in rows[start + 1:]:
+        if len(r) <= col["Metric Value"]:
+            continue
+        i = r[col["ID"]]
+        if i not in by_id:
+            by_id[i] = {"name": r[col["Kernel Name"]], "grid": r[col["Grid Size"]], "us": 0.0, "rd": 0.0, "wr": 0.0}
+            order.append(i)
+        m, u = r[col["Metric Name"]], r[col["Metric Unit"]]
+        v = float(r[col["Metric Value"]].replace(",", ""))
+        if m == "gpu__time_duration.sum":
+            by_id[i]["us"] = v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(u, 1.0)
+        elif m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            b = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            by_id[i]["rd" if "read" in m else "wr"] = b
+    seq = [by_id[i] for i in order]
+    ends = [i for i, d in enumerate(seq)
+            if "k_resid3" in d["name"] and ", 0, " in d["name"].split("(")[0] and d["grid"].startswith(f"({all_grid},")]
+    wins = []
+    for a, b in zip(ends[:-1], ends[1:]):
+        w = seq[a + 1:b + 1]
+        wins.append((len(w), sum(d["us"] for d in w), sum(d["rd"] + d["wr"] for d in w), w))
+    # complete V-cycles all have the same number of launches; other windows (FMG, set-up) differ
+    if not wins:
+        print("no complete V-cycle in the list")
+        return
+    from collections import Counter
+    nl = Counter(w[0] for w in wins).most_common(1)[0][0]
+    cyc = [w for w in wins if w[0] == nl]
+    for n, us, by, _ in cyc:
+        print(f"{n} launches, {us / 1e3:.3f} ms (serialised, cold cache), DRAM {by / 1e9:.3f} GB "
+              f"-> {by / us / 1e3:.0f} GB/s over the serialised time")
+    agg = defaultdict(lambda: [0, 0.0, 0.0])
+    for d in cyc[-1][3]:
+        k = d["name"].split("(")[0].replace("void ", "")
+        agg[k][0] += 1
+        agg[k][1] += d["us"]
+        agg[k][2] += d["rd"] + d["wr"]
+    print("| kernel | launches | us | DRAM MB | GB/s |")
+    print("|---|---|---|---|---|")
+    for k, (n, us, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"| {k} | {n} | {us:.1f} | {by / 1e6:.1f} | {by / us / 1e3 if us else 0:.0f} |")
+    if out_json and workload:
+        try:
+            cur = json.load(open(out_json))
+        except Exception:
+            cur = {}
+        med = sorted(w[2] for w in cyc)[len(cyc) // 2]
+        cur[workload] = {"dram_bytes_per_vcycle": med, "launches_per_vcycle": nl,
+                         "serialised_ms": sorted(w[1] for w in cyc)[len(cyc) // 2] / 1e3,
+                         "source": f"ncu launch list {path} (dram__bytes_read.sum + dram__bytes_write.sum summed over the "
+                                   f"{nl} launches of one V-cycle, median of {len(cyc)} cycles, N = 1)"}
+        json.dump(cur, open(out_json, "w"), indent=1)
+
+
 if __name__ == "__main__":
     kind, path = sys.argv[1], sys.argv[2]
+    if kind == "vcycle_dram":  # vcycle_dram <csv> <all_boxes grid> [workload out.json]
+        vcycle_dram(path, sys.argv[3], *(sys.argv[4:6]))
+        sys.exit(0)
     if kind == "vcycle":
         for n, tot, share in vcycle_windows(path, sys.argv[3], sys.argv[4]):
             print(f"{n} launches, {tot / 1e3:.2f} ms, finest-level k_gsrb2 share {100 * share:.1f} %")
