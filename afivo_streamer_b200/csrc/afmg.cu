@@ -22,6 +22,7 @@
 #include "field.cuh"
 #include "kernels2d.cuh"
 #include "kernels3d.cuh"
+#include "mega.cuh"
 
 using namespace afmg;
 
@@ -29,9 +30,19 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// device copy of the phase lists of the persistent-kernel segments of one cycle (mega.cuh)
+struct MegaProgram {
+  MegaPhase* d_phases = nullptr;
+  MegaOp* d_ops = nullptr;
+  int nphase = 0;
+  std::vector<MegaOp> h_ops;        // host copies: labels for the per-phase profile
+  std::vector<MegaPhase> h_phases;
+};
+
 struct Graph {
   cudaGraphExec_t exec = nullptr;
   int64_t launches = 0;
+  std::vector<MegaProgram> progs;
 };
 
 struct ProfEntry {
@@ -126,6 +137,26 @@ struct afmg_handle {
   int slab_nvar = 3;
   char* peer_slab[AFMG_MAX_RANKS] = {};
   unsigned long long barrier_timeout_ns = 30ull * 1000000000ull;
+
+  // ---- persistent-kernel segments (mega.cuh)
+  bool mega_enabled = true;      // AFMG_MEGA=0 / afmg_set_mega: launch path only
+  int mega_max_boxes = 0;        // levels with at most this many boxes run inside k_mega (0: default per n_cell)
+  int mega_grid = 0;             // co-resident CTAs of k_mega on this device
+  size_t mega_smem = 0;
+  int mega_mode = 0;             // 0 off, 1 plan (record phases, launch nothing), 2 exec (launch recorded programs)
+  bool mega_open = false;        // a segment is being recorded / waiting to be launched
+  std::vector<MegaOp> rec_ops;
+  std::vector<MegaPhase> rec_phases;
+  std::vector<MegaProgram>* progs = nullptr;  // programs of the cycle being planned / executed
+  size_t prog_idx = 0;
+  std::vector<MegaProgram> direct_progs;      // programs of the last direct (no graph) run
+  MegaSync* d_msync = nullptr;
+  bool mega_launched = false;                 // since the last check of d_msync->err
+  unsigned long long mega_timeout_ns = 2ull * 1000000000ull;
+  unsigned long long* d_stamps = nullptr;     // per-phase time stamps (profiling mode)
+  int stamps_cap = 0;
+  std::vector<std::pair<size_t, const MegaProgram*>> stamp_runs;  // (offset in d_stamps, program) of profiled launches
+  int stamps_used = 0;
 
   // ---- state
   bool resid_fresh = false;
@@ -224,6 +255,7 @@ struct Launch {
   std::string name;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   Launch(afmg_handle* h_, const char* name_, int lvl = 0) : h(h_) {
+    if (h->mega_mode == 1) return;  // planning pass of the persistent-kernel segments: nothing is launched
     if (h->profiling && !h->capturing) name = lvl > 0 ? std::string(name_) + "_L" + std::to_string(lvl) : std::string(name_);
     h->launches++;
     if (h->profiling && !h->capturing) {
@@ -249,6 +281,7 @@ struct Launch {
 // default; the ~3.3 us per graph node that bound the coarse levels are kernel drain + ramp-up.
 template <class... KArgs, class... Args>
 void launch_k(afmg_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  if (h->mega_mode == 1) return;  // planning pass (see mega_route)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -293,6 +326,133 @@ struct Range {
 inline Range own(const afmg_handle* h, int l) {
   const int* c = &h->cut[(size_t)l * (h->nranks + 1)];
   return {c[h->me], c[h->me + 1] - c[h->me]};
+}
+
+// ---- persistent-kernel segments (mega.cuh) ----------------------------------------------------------
+// The enq_* functions below are the single description of a cycle.  With the persistent kernel enabled a cycle is
+// walked twice: a PLAN pass (mega_mode 1) in which operations on small levels are recorded as phases of a program
+// instead of being launched (and nothing else is launched either), and an EXEC pass (mega_mode 2, usually under
+// graph capture) in which those operations are skipped and each recorded program is launched as one k_mega where
+// its segment ends (mega_flush).  Both passes take identical decisions (mega_route), so programs and launch sites
+// pair up by index.
+inline int mega_items(const afmg_handle* h, int kind) {
+  const bool big = h->o.n_cell == 16;
+  switch (kind) {
+    case MK_GSRB: return big ? MegaCfg<16>::GS_BPC : MegaCfg<8>::GS_BPC;
+    case MK_RB: return big ? MegaCfg<16>::RB_PER : MegaCfg<8>::RB_PER;
+    case MK_EC: return big ? MegaCfg<16>::EC_PER : MegaCfg<8>::EC_PER;
+    case MK_RESTRICT:
+    case MK_RESID: return big ? MegaCfg<16>::RES_PER : MegaCfg<8>::RES_PER;
+    default: return 1;
+  }
+}
+
+inline bool mega_possible(const afmg_handle* h) {
+  return h->mega_enabled && h->mega_grid > 0 && h->o.ndim == 3 && h->nranks == 1 && !h->have_stencils &&
+         !h->o.subtract_mean && (h->o.n_cell == 8 || h->o.n_cell == 16);
+}
+
+void free_programs(std::vector<MegaProgram>& v) {
+  for (auto& p : v) {
+    cudaFree(p.d_phases);
+    cudaFree(p.d_ops);
+  }
+  v.clear();
+}
+
+inline void mega_end_phase(afmg_handle* h) {
+  if (h->mega_mode != 1) return;
+  const int op0 = h->rec_phases.empty() ? 0 : h->rec_phases.back().op0 + h->rec_phases.back().nops;
+  const int nops = (int)h->rec_ops.size() - op0;
+  if (nops == 0) return;
+  MegaPhase ph{op0, nops, 0, 0};
+  for (int q = op0; q < op0 + nops; ++q) ph.nvb += h->rec_ops[q].nvb;
+  h->rec_phases.push_back(ph);
+}
+
+// record one operation of the open phase (plan pass only); nvb < 0: ceil(n / items per block of that kind)
+inline void mega_op(afmg_handle* h, int kind, int lvl, int s0, int n, int a0 = 0, int a1 = 0, int a2 = 0, int a3 = 0,
+                    int nvb = -1) {
+  if (h->mega_mode != 1 || n <= 0) return;
+  const int per = mega_items(h, kind);
+  MegaOp op{kind, lvl, s0, n, nvb >= 0 ? nvb : (n + per - 1) / per, a0, a1, a2, a3, 0};
+  if (op.nvb > 0) h->rec_ops.push_back(op);
+}
+
+// an operation that only has to precede the NEXT phase joins the phase that was closed last, if there is one
+inline void mega_op_prev_phase(afmg_handle* h, int kind, int lvl, int s0, int n, int a0 = 0) {
+  if (h->mega_mode != 1) return;
+  mega_op(h, kind, lvl, s0, n, a0);
+  if (h->rec_phases.empty()) {
+    mega_end_phase(h);
+  } else {
+    h->rec_phases.back().nops += 1;
+    h->rec_phases.back().nvb += h->rec_ops.back().nvb;
+  }
+}
+
+void mega_flush(afmg_handle* h) {
+  if (!h->mega_open) return;
+  h->mega_open = false;
+  if (h->mega_mode == 1) {
+    mega_end_phase(h);
+    MegaProgram pr;
+    pr.nphase = (int)h->rec_phases.size();
+    if (pr.nphase > 0) {
+      cudaMalloc((void**)&pr.d_phases, h->rec_phases.size() * sizeof(MegaPhase));
+      cudaMalloc((void**)&pr.d_ops, h->rec_ops.size() * sizeof(MegaOp));
+      cudaMemcpy(pr.d_phases, h->rec_phases.data(), h->rec_phases.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice);
+      cudaMemcpy(pr.d_ops, h->rec_ops.data(), h->rec_ops.size() * sizeof(MegaOp), cudaMemcpyHostToDevice);
+    }
+    pr.h_ops.swap(h->rec_ops);
+    pr.h_phases.swap(h->rec_phases);
+    h->rec_ops.clear();
+    h->rec_phases.clear();
+    h->progs->push_back(std::move(pr));
+    return;
+  }
+  if (h->mega_mode != 2 || !h->progs || h->prog_idx >= h->progs->size()) return;
+  const MegaProgram& pr = (*h->progs)[h->prog_idx++];
+  if (pr.nphase == 0) return;
+  int max_nvb = 1;
+  for (const auto& ph : pr.h_phases) max_nvb = std::max(max_nvb, ph.nvb);
+  Launch L_(h, "mega");
+  unsigned long long* stamps = nullptr;
+  if (h->profiling && !h->capturing && h->d_stamps && h->stamps_used + pr.nphase + 1 <= h->stamps_cap) {
+    stamps = h->d_stamps + h->stamps_used;
+    h->stamp_runs.emplace_back((size_t)h->stamps_used, &pr);
+    h->stamps_used += pr.nphase + 1;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(std::min(h->mega_grid, max_nvb));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = h->mega_smem;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident, or the launch waits: the grid barrier cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  h->mega_launched = true;
+  if (h->o.n_cell == 16)
+    cudaLaunchKernelEx(&cfg, k_mega<16>, h->cx, h->cs, (const MegaPhase*)pr.d_phases, (const MegaOp*)pr.d_ops, pr.nphase,
+                       h->d_msync, h->d_scal, h->mega_timeout_ns, stamps);
+  else
+    cudaLaunchKernelEx(&cfg, k_mega<8>, h->cx, h->cs, (const MegaPhase*)pr.d_phases, (const MegaOp*)pr.d_ops, pr.nphase,
+                       h->d_msync, h->d_scal, h->mega_timeout_ns, stamps);
+}
+
+// true: the operation (on a level of `nboxes` boxes) belongs to the persistent-kernel segment -- the caller records it
+// (plan pass) or skips it (exec pass); false: it takes the launch path, after the open segment has been closed
+inline bool mega_route(afmg_handle* h, int nboxes, bool ok = true) {
+  if (h->mega_mode == 0) return false;
+  const int lim = h->mega_max_boxes > 0 ? h->mega_max_boxes : (h->o.n_cell == 16 ? 1024 : 8192);
+  if (ok && nboxes <= lim) {
+    h->mega_open = true;
+    return true;
+  }
+  mega_flush(h);
+  return false;
 }
 
 // Cross-GPU barrier between dependent kernels (no-op on one GPU, where stream order suffices)

@@ -300,32 +300,31 @@ __device__ __forceinline__ void epilogue_faces(const DevCtx& cx, int slot, const
   }
 }
 
-template <int NC, int BPC, int KS, int MINB>
-__global__ void __launch_bounds__(BPC* KS* NC* NC / 2, MINB) k_gsrb2(DevCtx cx, int slot0, int nbox, int C, int lvl) {
-  pdl_wait();
+// One virtual block (BPC boxes starting at slot0 + vb * BPC) of a half-sweep.  `bar` is an initialised mbarrier of
+// the CTA (count 1) and `par` the parity of its next completion (flipped here), so that a persistent kernel can
+// call this repeatedly (k_mega); k_gsrb2 calls it once with vb = blockIdx.x.
+template <int NC, int BPC, int KS>
+__device__ __forceinline__ void gsrb2_vblock(const DevCtx& cx, int slot0, int nbox, int C, int lvl, int vb, double* smem,
+                                             uint64_t* bar, uint32_t& par) {
   using L = Lay3<NC>;
   constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX;
   constexpr int TPB = H * NC * KS;  // threads per box
   constexpr int KL = NC / KS;       // k-steps per thread
   constexpr int SBOX = COL + NI;    // smem doubles per box: phi block of the other colour, rhs/out
-  extern __shared__ __align__(128) double smem[];
-  __shared__ uint64_t bar;
   const int tid = threadIdx.x;
-  const int box0 = blockIdx.x * BPC;
+  const int box0 = vb * BPC;
   const int nhere = min(BPC, nbox - box0);
   double* const phi = cx.cc[V_PHI];
-  if (tid == 0) mbar_init(&bar, 1);
-  __syncthreads();
   // boxes with an explicit (variable-coefficient / level-set) stencil are left to k_gsrb_gen
   if (tid == 0) {
     int nload = 0;
     for (int b = 0; b < nhere; ++b) nload += (cx.opk && cx.opk[slot0 + box0 + b]) ? 0 : 1;
-    mbar_expect_tx(&bar, (uint32_t)(nload * SBOX * 8));
+    mbar_expect_tx(bar, (uint32_t)(nload * SBOX * 8));
     for (int b = 0; b < nhere; ++b) {
       if (cx.opk && cx.opk[slot0 + box0 + b]) continue;
       const size_t base = (size_t)(slot0 + box0 + b) * BOX;
-      bulk_g2s(smem + b * SBOX, phi + base + (1 - C) * COL, COL * 8, &bar);
-      bulk_g2s(smem + b * SBOX + COL, cx.cc[V_RHS] + base + C * COL, NI * 8, &bar);
+      bulk_g2s(smem + b * SBOX, phi + base + (1 - C) * COL, COL * 8, bar);
+      bulk_g2s(smem + b * SBOX + COL, cx.cc[V_RHS] + base + C * COL, NI * 8, bar);
     }
   }
   const int b = tid / TPB, t = tid % TPB;
@@ -337,7 +336,8 @@ __global__ void __launch_bounds__(BPC* KS* NC* NC / 2, MINB) k_gsrb2(DevCtx cx, 
   const double c2 = cf[1], c3 = cf[2], c4 = cf[3], c5 = cf[4], c6 = cf[5], c7 = cf[6], inv = cf[7];
   __shared__ FaceMeta fmeta[BPC];
   if (active && t < 6) prefetch_face_meta(cx, slot, &fmeta[b], t);  // visible after the __syncthreads below
-  mbar_wait(&bar, 0);
+  mbar_wait(bar, par);
+  par ^= 1u;
 
   if (active) {
     const int m = t % H, j = (t / H) % NC + 1, ks = t / (H * NC);
@@ -375,13 +375,24 @@ __global__ void __launch_bounds__(BPC* KS* NC* NC / 2, MINB) k_gsrb2(DevCtx cx, 
   }
   fence_async_smem();
   __syncthreads();
-  if (!active) return;
+  if (active) {
+    // ---- epilogue: new colour-C values are in R (layout of an interior colour block)
+    if (t == 0) bulk_s2g(phi + (size_t)slot * BOX + C * COL, R, NI * 8);
+    epilogue_faces<NC, TPB>(cx, slot, C ? S : R, C ? R : S, 1 << C, t, &fmeta[b]);
+    if (t == 0) bulk_commit();
+    if (t == 0) bulk_wait_read0();
+  }
+}
 
-  // ---- epilogue: new colour-C values are in R (layout of an interior colour block)
-  if (t == 0) bulk_s2g(phi + (size_t)slot * BOX + C * COL, R, NI * 8);
-  epilogue_faces<NC, TPB>(cx, slot, C ? S : R, C ? R : S, 1 << C, t, &fmeta[b]);
-  if (t == 0) bulk_commit();
-  if (t == 0) bulk_wait_read0();
+template <int NC, int BPC, int KS, int MINB>
+__global__ void __launch_bounds__(BPC* KS* NC* NC / 2, MINB) k_gsrb2(DevCtx cx, int slot0, int nbox, int C, int lvl) {
+  pdl_wait();
+  extern __shared__ __align__(128) double smem[];
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  uint32_t par = 0;
+  gsrb2_vblock<NC, BPC, KS>(cx, slot0, nbox, C, lvl, blockIdx.x, smem, &bar, par);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -448,32 +459,17 @@ __device__ __forceinline__ double apply357_smem(const double* S, const double* c
 //           2x2x2 cells in the reference's summation order (m_af_restrict.f90:120-133) and written into
 //           the parent's tmp / phi; odd-j lanes accumulate, the even-j row arrives by warp shuffle.
 template <int NC>
-__device__ __forceinline__ void rb_prepare_face(const DevCtx& cx, int r, int var);
+__device__ __forceinline__ void rb_prepare_face(const DevCtx& cx, int r, int var, int t0 = -1, int nt = 0);
 
-// CTAs beyond nbox (rb_n of them) interpolate refinement-boundary faces rb_r0.. of ANOTHER level (k_rb_prepare's
-// work, independent of this kernel's): one graph node less per level on the launch-bound small levels.
-template <int NC, int KS, int MODE, int MINB>
-__global__ void __launch_bounds__(KS* NC* NC / 2, MINB)
-    k_resid3(DevCtx cx, int slot0, int nbox, unsigned long long* maxabs_bits, int keep_res, int rb_r0, int rb_n) {
-  pdl_wait();
-  if ((int)blockIdx.x >= nbox) {
-    rb_prepare_face<NC>(cx, rb_r0 + (int)blockIdx.x - nbox, V_PHI);
-    return;
-  }
+// One box of k_resid3: `t` = index among the KS * NC * NC / 2 threads working on it, S = its staged record (2 * COL
+// doubles, TMA load in flight on `bar`, whose completion parity is `par`).  LDG: read rhs through the read-only path
+// (only valid when rhs is not written during the kernel: not in the persistent k_mega).
+template <int NC, int KS, int MODE, bool LDG>
+__device__ __forceinline__ void resid3_box(const DevCtx& cx, int slot, int t, const double* S,
+                                           unsigned long long* maxabs_bits, int keep_res, uint64_t* bar, uint32_t par) {
   using L = Lay3<NC>;
   constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX, KL = NC / KS;
   static_assert(KL % 2 == 0, "z pairs must stay inside one thread");
-  extern __shared__ __align__(128) double smem[];
-  __shared__ uint64_t bar;
-  const int slot = slot0 + blockIdx.x;
-  const int t = threadIdx.x;
-  if (cx.opk && cx.opk[slot]) return;  // explicit stencil: k_resid_gen
-  if (t == 0) mbar_init(&bar, 1);
-  __syncthreads();
-  if (t == 0) {
-    mbar_expect_tx(&bar, 2 * COL * 8);
-    bulk_g2s(smem, cx.cc[V_PHI] + (size_t)slot * BOX, 2 * COL * 8, &bar);
-  }
   const double* grhs = cx.cc[V_RHS] + (size_t)slot * BOX;
   double* gtmp = cx.cc[V_TMP] + (size_t)slot * BOX;
   const int m = t % H, j = (t / H) % NC + 1, ks = t / (H * NC);
@@ -485,8 +481,8 @@ __global__ void __launch_bounds__(KS* NC* NC / 2, MINB)
   for (int kk = 0; kk < KL; ++kk) {
     const int cA = (cA0 + kk) & 1;
     const int idx = L::iidx(m, j, k0 + kk);
-    rA[kk] = __ldg(grhs + cA * COL + idx);
-    rB[kk] = __ldg(grhs + (1 - cA) * COL + idx);
+    rA[kk] = (LDG ? __ldg(grhs + cA * COL + idx) : grhs[cA * COL + idx]);
+    rB[kk] = (LDG ? __ldg(grhs + (1 - cA) * COL + idx) : grhs[(1 - cA) * COL + idx]);
   }
   const double* cf = cx.coef + 8 * cx.lvl[slot];
   const double c1 = cf[0], c2 = cf[1], c3 = cf[2], c4 = cf[3], c5 = cf[4], c6 = cf[5], c7 = cf[6];
@@ -502,11 +498,11 @@ __global__ void __launch_bounds__(KS* NC* NC / 2, MINB)
     oz = ((cof >> 2) & 1) * H;
   }
   const unsigned lanes = __activemask();  // a box of 4^3 cells has fewer than 32 threads
-  mbar_wait(&bar, 0);
+  mbar_wait(bar, par);
   double mx = 0.0, sr = 0.0, sp = 0.0;
   // chain registers: a0/b0 = centre values at k, azm/bzm = values below
-  const double* SA = smem + cA0 * COL;        // block holding cell A at k0
-  const double* SB = smem + (1 - cA0) * COL;  // block holding cell B at k0
+  const double* SA = S + cA0 * COL;        // block holding cell A at k0
+  const double* SB = S + (1 - cA0) * COL;  // block holding cell B at k0
   double a0 = SA[L::iidx(m, j, k0)], b0 = SB[L::iidx(m, j, k0)];
   double azm = (k0 == 1) ? SB[NI + 4 * NF + (j - 1) * H + m] : SB[L::iidx(m, j, k0 - 1)];
   double bzm = (k0 == 1) ? SA[NI + 4 * NF + (j - 1) * H + m] : SA[L::iidx(m, j, k0 - 1)];
@@ -581,6 +577,31 @@ __global__ void __launch_bounds__(KS* NC* NC / 2, MINB)
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(lanes, mx, o, 32));
     if ((t & 31) == 0 && mx > 0.0) atomic_max_nonneg(maxabs_bits, mx);
   }
+}
+
+// CTAs beyond nbox (rb_n of them) interpolate refinement-boundary faces rb_r0.. of ANOTHER level (k_rb_prepare's
+// work, independent of this kernel's): one graph node less per level on the launch-bound small levels.
+template <int NC, int KS, int MODE, int MINB>
+__global__ void __launch_bounds__(KS* NC* NC / 2, MINB)
+    k_resid3(DevCtx cx, int slot0, int nbox, unsigned long long* maxabs_bits, int keep_res, int rb_r0, int rb_n) {
+  pdl_wait();
+  if ((int)blockIdx.x >= nbox) {
+    rb_prepare_face<NC>(cx, rb_r0 + (int)blockIdx.x - nbox, V_PHI);
+    return;
+  }
+  using L = Lay3<NC>;
+  extern __shared__ __align__(128) double smem[];
+  __shared__ uint64_t bar;
+  const int slot = slot0 + blockIdx.x;
+  const int t = threadIdx.x;
+  if (cx.opk && cx.opk[slot]) return;  // explicit stencil: k_resid_gen
+  if (t == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (t == 0) {
+    mbar_expect_tx(&bar, 2 * L::COL * 8);
+    bulk_g2s(smem, cx.cc[V_PHI] + (size_t)slot * L::BOX, 2 * L::COL * 8, &bar);
+  }
+  resid3_box<NC, KS, MODE, true>(cx, slot, t, smem, maxabs_bits, keep_res, &bar, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -725,26 +746,23 @@ __global__ void __launch_bounds__(256) k_resid_gen(DevCtx cx, const int* list, i
 // follows correct_children in the cycle (m_af_multigrid.f90:222, :171): boundary layers of both
 // colours are pushed to the neighbours, rule faces are recomputed (epilogue_faces); edges / corners
 // are done by k_edges_corners afterwards.
-template <int NC>
-__global__ void __launch_bounds__(256, 4) k_correct3(DevCtx cx, int slot0, int nbox, int push) {
-  pdl_wait();
+template <int NC, bool LDG>
+__device__ __forceinline__ void correct3_box(const DevCtx& cx, int cslot, int push, double* smem, uint64_t* bar,
+                                             uint32_t& par) {
   using L = Lay3<NC>;
   constexpr int H = L::H, W = H + 2, NI = L::NI, COL = L::COL, BOX = L::BOX;
-  extern __shared__ __align__(128) double smem[];  // I0[NI], I1[NI], sub[W^3]
-  __shared__ uint64_t bar;
+  // smem: I0[NI], I1[NI], sub[W^3]
   double* I0 = smem;
   double* I1 = smem + NI;
   double* sub = smem + 2 * NI;
-  const int cslot = slot0 + blockIdx.x;  // child box (this rank's); its parent may live on a peer GPU
+  // cslot: child box (this rank's); its parent may live on a peer GPU
   const int slot = cx.parent[cslot], ch = cx.coff[cslot];
   const int t = threadIdx.x;
   double* cphi = cx.cc[V_PHI] + (size_t)cslot * BOX;
-  if (t == 0) mbar_init(&bar, 1);
-  __syncthreads();
   if (t == 0) {
-    mbar_expect_tx(&bar, 2 * NI * 8);
-    bulk_g2s(I0, cphi, NI * 8, &bar);
-    bulk_g2s(I1, cphi + COL, NI * 8, &bar);
+    mbar_expect_tx(bar, 2 * NI * 8);
+    bulk_g2s(I0, cphi, NI * 8, bar);
+    bulk_g2s(I1, cphi + COL, NI * 8, bar);
   }
   const double* phi = cx.at<BOX>(V_PHI, slot);
   const double* tmp = cx.at<BOX>(V_TMP, slot);
@@ -761,8 +779,8 @@ __global__ void __launch_bounds__(256, 4) k_correct3(DevCtx cx, int slot0, int n
       if (n < W * W * W) {
         const int a = n % W, b = (n / W) % W, c = n / (W * W);
         const int q = L::cell(ox + a, oy + b, oz + c);
-        pv[u] = __ldg(phi + q);
-        tv[u] = __ldg(tmp + q);
+        pv[u] = LDG ? __ldg(phi + q) : phi[q];
+        tv[u] = LDG ? __ldg(tmp + q) : tmp[q];
       }
     }
 #pragma unroll
@@ -771,7 +789,8 @@ __global__ void __launch_bounds__(256, 4) k_correct3(DevCtx cx, int slot0, int n
       if (n < W * W * W) sub[n] = pv[u] - tv[u];
     }
   }
-  mbar_wait(&bar, 0);
+  mbar_wait(bar, par);
+  par ^= 1u;
   __syncthreads();
   // prolongation stencil of this child: the default one, or what the host shipped for the box
   // (constant p248 / p234, or variable p234 for variable-epsilon boxes, m_af_multigrid.f90:1308-1388)
@@ -895,39 +914,45 @@ __global__ void __launch_bounds__(256, 4) k_correct3(DevCtx cx, int slot0, int n
 }
 
 template <int NC>
+__global__ void __launch_bounds__(256, 4) k_correct3(DevCtx cx, int slot0, int nbox, int push) {
+  pdl_wait();
+  extern __shared__ __align__(128) double smem[];
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  uint32_t par = 0;
+  correct3_box<NC, true>(cx, slot0 + blockIdx.x, push, smem, &bar, par);
+}
+
+template <int NC>
 __device__ void gc_sides(const DevCtx& cx, int slot, int var, double* stage = nullptr);
 template <int NC>
-__device__ void gc_edges_corners(const DevCtx& cx, int slot, int var);
+__device__ void gc_edges_corners(const DevCtx& cx, int slot, int var, int t0 = -1, int nt = 0);
 
 // k_gc2: af_gc_lvl for one level, and for boxes with children the parent part of update_coarse
 // (rhs = L phi + tmp; tmp = phi on the full record, m_af_multigrid.f90:722-736) computed from a shared-memory copy
 // of the box: the two interior colour blocks arrive by TMA while the ghost faces are being gathered, and the
 // gathered values go straight into the copy (no read-back of what the CTA just wrote).
 template <int NC>
-__global__ void __launch_bounds__(256) k_gc2(DevCtx cx, int slot0, int nbox, int corners, int mode) {
-  pdl_wait();
+__device__ __forceinline__ void gc2_box(const DevCtx& cx, int slot, int corners, int mode, double* smem, uint64_t* bar,
+                                        uint32_t& par) {
   using L = Lay3<NC>;
   constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX;
-  extern __shared__ __align__(128) double smem[];  // 2*COL
-  __shared__ uint64_t bar;
-  const int slot = slot0 + blockIdx.x;
+  // smem: 2 * COL doubles
   const int t = threadIdx.x;
   double* gphi = cx.cc[V_PHI] + (size_t)slot * BOX;
   const bool upd = mode != 0 && cx.child0[slot] >= 0;
-  if (upd) {
-    if (t == 0) mbar_init(&bar, 1);
-    __syncthreads();
-    if (t == 0) {
-      mbar_expect_tx(&bar, 2 * NI * 8);
-      bulk_g2s(smem, gphi, NI * 8, &bar);
-      bulk_g2s(smem + COL, gphi + COL, NI * 8, &bar);
-    }
+  if (upd && t == 0) {
+    mbar_expect_tx(bar, 2 * NI * 8);
+    bulk_g2s(smem, gphi, NI * 8, bar);
+    bulk_g2s(smem + COL, gphi + COL, NI * 8, bar);
   }
   gc_sides<NC>(cx, slot, V_PHI, upd ? smem : nullptr);
   __syncthreads();
   if (corners) gc_edges_corners<NC>(cx, slot, V_PHI);
   if (!upd) return;
-  mbar_wait(&bar, 0);
+  mbar_wait(bar, par);
+  par ^= 1u;
   __syncthreads();
   double* rhs = cx.cc[V_RHS] + (size_t)slot * BOX;
   double* tmp = cx.cc[V_TMP] + (size_t)slot * BOX;
@@ -957,6 +982,17 @@ __global__ void __launch_bounds__(256) k_gc2(DevCtx cx, int slot0, int nbox, int
   }
 }
 
+template <int NC>
+__global__ void __launch_bounds__(256) k_gc2(DevCtx cx, int slot0, int nbox, int corners, int mode) {
+  pdl_wait();
+  extern __shared__ __align__(128) double smem[];  // 2*COL
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  uint32_t par = 0;
+  gc2_box<NC>(cx, slot0 + blockIdx.x, corners, mode, smem, &bar, par);
+}
+
 // tmp_p = phi_p - tmp_p on the full record of every box of [slot0, slot0+nbox) that has children
 // (first statement of correct_children, m_af_multigrid.f90:636-637)
 template <int NC>
@@ -976,10 +1012,15 @@ __global__ void k_store_corr(DevCtx cx, int slot0, int nbox) {
 // coarse level is frozen while the fine level is smoothed, so this runs once per gsrb_boxes /
 // af_gc_lvl group.  One CTA per face, one thread per fine face cell.
 // ---------------------------------------------------------------------------------------------
+// t0 / nt: index of the calling thread among the nt threads that share this face (default: the whole CTA)
 template <int NC>
-__device__ __forceinline__ void rb_prepare_face(const DevCtx& cx, int r, int var) {
+__device__ __forceinline__ void rb_prepare_face(const DevCtx& cx, int r, int var, int t0, int nt) {
   using L = Lay3<NC>;
   constexpr int H = L::H;
+  if (t0 < 0) {
+    t0 = threadIdx.x;
+    nt = blockDim.x;
+  }
   const int s = cx.rb_slot[r], f = cx.rb_face[r];
   const int p = cx.parent[s];
   const int pn = cx.nbr[p * 6 + f];  // coarse neighbour (exists by 2:1 balance)
@@ -1003,7 +1044,7 @@ __device__ __forceinline__ void rb_prepare_face(const DevCtx& cx, int r, int var
     const double* pb = cx.at<L::BOX>(var, p);
     const int g = (f & 1) ? NC + 1 : 0;
     const int cod = ((cof >> d) & 1) * H;
-    for (int n = threadIdx.x; n < L::NC2; n += blockDim.x) {
+    for (int n = t0; n < L::NC2; n += nt) {
       const int a = n % NC + 1, b = n / NC + 1;
       int q[3];
       q[d] = cod + ((g + 1) >> 1);
@@ -1013,7 +1054,7 @@ __device__ __forceinline__ void rb_prepare_face(const DevCtx& cx, int r, int var
     }
     return;
   }
-  for (int n = threadIdx.x; n < L::NC2; n += blockDim.x) {
+  for (int n = t0; n < L::NC2; n += nt) {
     const int a = n % NC + 1, b = n / NC + 1;
     const int ia = (a + 1) >> 1, ib = (b + 1) >> 1;
     const double t0 = T(ia, ib);
@@ -1073,10 +1114,14 @@ __device__ void gc_sides(const DevCtx& cx, int slot, int var, double* stage) {
 // af_gc_box_corner (m_af_ghostcell.f90:125-170): needs the box's own face ghosts (call after a
 // __syncthreads following gc_sides, or in a later kernel)
 template <int NC>
-__device__ void gc_edges_corners(const DevCtx& cx, int slot, int var) {
+__device__ void gc_edges_corners(const DevCtx& cx, int slot, int var, int t0, int nt) {
   using L = Lay3<NC>;
   double* box = cx.cc[var] + (size_t)slot * L::BOX;
-  for (int n = threadIdx.x; n < 12 * NC + 8; n += blockDim.x) {
+  if (t0 < 0) {
+    t0 = threadIdx.x;
+    nt = blockDim.x;
+  }
+  for (int n = t0; n < 12 * NC + 8; n += nt) {
     if (n < 12 * NC) {
       const int e = n / NC, pos = n % NC + 1, dim = e >> 2;
       const int o1 = (dim == 0) ? 1 : 0, o2 = (dim == 2) ? 1 : 2;
@@ -1350,10 +1395,15 @@ struct CoarseCtx {
 
 // coarse_solver_set_rhs_phi (m_coarse_solver.f90:286-338): b = rhs + bc_to_rhs * bc_val per face
 template <int NC>
+__device__ __forceinline__ void cs_gather_cell(const DevCtx& cx, const CoarseCtx& cs, int nbox1, int n);
+template <int NC>
 __global__ void k_cs_gather(DevCtx cx, CoarseCtx cs, int nbox1) {
   pdl_wait();
+  cs_gather_cell<NC>(cx, cs, nbox1, blockIdx.x * blockDim.x + threadIdx.x);
+}
+template <int NC>
+__device__ __forceinline__ void cs_gather_cell(const DevCtx& cx, const CoarseCtx& cs, int nbox1, int n) {
   using L = Lay3<NC>;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int ncell = NC * NC * NC;
   if (n >= nbox1 * ncell) return;
   const int bx = n / ncell, r = n % ncell;
@@ -1382,10 +1432,15 @@ __global__ void k_cs_gather(DevCtx cx, CoarseCtx cs, int nbox1) {
 
 // out = (M applied along dimension d) in, M = Q^T (trans = 1) or Q (trans = 0); optional scaling of
 // the result by inv_eig (fused into the last forward transform)
+__device__ __forceinline__ void cs_apply_cell(const CoarseCtx& cs, const double* in, double* out, int d, int trans,
+                                              int scale, int n);
 __global__ void k_cs_apply(CoarseCtx cs, const double* in, double* out, int d, int trans, int scale) {
   pdl_wait();
+  cs_apply_cell(cs, in, out, d, trans, scale, blockIdx.x * blockDim.x + threadIdx.x);
+}
+__device__ __forceinline__ void cs_apply_cell(const CoarseCtx& cs, const double* in, double* out, int d, int trans,
+                                              int scale, int n) {
   const int ntot = cs.nx[0] * cs.nx[1] * cs.nx[2];
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= ntot) return;
   int q[3] = {n % cs.nx[0], (n / cs.nx[0]) % cs.nx[1], n / (cs.nx[0] * cs.nx[1])};
   const int stride = (d == 0) ? 1 : (d == 1 ? cs.nx[0] : cs.nx[0] * cs.nx[1]);
@@ -1417,10 +1472,15 @@ __global__ void k_cs_dense(CoarseCtx cs, const double* in, double* out) {
 
 // coarse_solver_get_phi (m_coarse_solver.f90:341-358)
 template <int NC>
+__device__ __forceinline__ void cs_scatter_cell(const DevCtx& cx, const CoarseCtx& cs, int nbox1, const double* x, int n);
+template <int NC>
 __global__ void k_cs_scatter(DevCtx cx, CoarseCtx cs, int nbox1, const double* x) {
   pdl_wait();
+  cs_scatter_cell<NC>(cx, cs, nbox1, x, blockIdx.x * blockDim.x + threadIdx.x);
+}
+template <int NC>
+__device__ __forceinline__ void cs_scatter_cell(const DevCtx& cx, const CoarseCtx& cs, int nbox1, const double* x, int n) {
   using L = Lay3<NC>;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int ncell = NC * NC * NC;
   if (n >= nbox1 * ncell) return;
   const int bx = n / ncell, r = n % ncell;
@@ -1435,10 +1495,9 @@ __global__ void k_cs_scatter(DevCtx cx, CoarseCtx cs, int nbox1, const double* x
 // transforms, scatter, ghost cells -- nine launches of ~3 us each otherwise, on the critical path of every cycle.
 // Same loops and summation order as k_cs_gather / k_cs_apply / k_cs_scatter: bit-identical results.
 template <int NC>
-__global__ void __launch_bounds__(1024) k_cs_fused(DevCtx cx, CoarseCtx cs, int nbox1, int with_gc) {
-  pdl_wait();
+__device__ __forceinline__ void cs_fused_body(const DevCtx& cx, const CoarseCtx& cs, int nbox1, int with_gc, double* sv) {
   using L = Lay3<NC>;
-  extern __shared__ __align__(16) double sv[];  // two work vectors of ntot doubles
+  // sv: two work vectors of ntot doubles
   const int ntot = cs.nx[0] * cs.nx[1] * cs.nx[2];
   double* a = sv;
   double* b = sv + ntot;
@@ -1502,6 +1561,13 @@ __global__ void __launch_bounds__(1024) k_cs_fused(DevCtx cx, CoarseCtx cs, int 
   for (int bx = 0; bx < nbox1; ++bx) gc_sides<NC>(cx, bx, V_PHI);
   __syncthreads();
   for (int bx = 0; bx < nbox1; ++bx) gc_edges_corners<NC>(cx, bx, V_PHI);
+}
+
+template <int NC>
+__global__ void __launch_bounds__(1024) k_cs_fused(DevCtx cx, CoarseCtx cs, int nbox1, int with_gc) {
+  pdl_wait();
+  extern __shared__ __align__(16) double sv[];
+  cs_fused_body<NC>(cx, cs, nbox1, with_gc, sv);
 }
 
 }  // namespace afmg
