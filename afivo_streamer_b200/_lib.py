@@ -126,6 +126,8 @@ SYMBOLS = {
     "afmg_max_abs": (C.c_int, [_H, _I, _DP]),
     "afmg_tree_sum": (C.c_int, [_H, _I, _DP]),
     "afmg_checksum": (C.c_int, [_H, _I, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "afmg_set_mega": (C.c_int, [_H, _I, _I]),
+    "afmg_mega_active": (C.c_int32, [_H]),
     "afmg_kernel_launches": (C.c_int64, [_H]),
     "afmg_last_cycle_ms": (C.c_int, [_H, _DP]),
     "afmg_set_profiling": (C.c_int, [_H, _I]),
@@ -140,6 +142,7 @@ SYMBOLS = {
     "afmg_comm_connect": (C.c_int, [_H, C.c_void_p]),
     "afmg_owner_of_box": (C.c_int32, [_H, _I]),
     "afmg_partition": (C.c_int, [_I, _I, _IP, _IP]),
+    "afmg_partition_min": (C.c_int, [_I, _I, _IP, _I, _IP]),
     "afmg_lsf_opts_default": (None, [C.POINTER(LsfOpts)]),
     "afmg_electrode_prepare": (C.c_int, [C.POINTER(Electrode)]),
     "afmg_electrode_lsf": (C.c_double, [_DP, C.c_void_p]),

@@ -129,6 +129,9 @@ struct afmg_handle {
   std::vector<int> cut;  // [(L+2) * (nranks+1)]: slots [cut[l][r], cut[l][r+1]) of level l belong to rank r
   std::vector<int> rb_cut;  // same for the refinement-boundary face list (rb rows of level l)
   std::vector<unsigned char> h_owner;
+  std::vector<char> lvl_multi;   // [L+2] 1: boxes of the level are owned by more than one rank
+  bool unsynced = false;         // operations ran since the last cross-GPU barrier (all of them on rank 0's levels)
+  int min_split_boxes = -1;      // levels with fewer boxes stay on rank 0 (-1: 4 Mi cells worth of boxes)
   unsigned char* d_owner = nullptr;
   CommBlock* d_comm = nullptr;
   CommPeers peers{};
@@ -139,7 +142,7 @@ struct afmg_handle {
   unsigned long long barrier_timeout_ns = 30ull * 1000000000ull;
 
   // ---- persistent-kernel segments (mega.cuh)
-  bool mega_enabled = true;      // AFMG_MEGA=0 / afmg_set_mega: launch path only
+  bool mega_enabled = false;     // opt-in (AFMG_MEGA=1 / afmg_set_mega): measured slower than the graph of launches, see mega.cuh
   int mega_max_boxes = 0;        // levels with at most this many boxes run inside k_mega (0: default per n_cell)
   int mega_grid = 0;             // co-resident CTAs of k_mega on this device
   size_t mega_smem = 0;
@@ -365,6 +368,11 @@ inline void mega_end_phase(afmg_handle* h) {
   const int op0 = h->rec_phases.empty() ? 0 : h->rec_phases.back().op0 + h->rec_phases.back().nops;
   const int nops = (int)h->rec_ops.size() - op0;
   if (nops == 0) return;
+  if (nops > MEGA_MAX_OPS) {  // cannot happen with the enq_* functions as written; never launch a broken program
+    h->rec_ops.resize(op0);
+    h->mega_enabled = false;
+    return;
+  }
   MegaPhase ph{op0, nops, 0, 0};
   for (int q = op0; q < op0 + nops; ++q) ph.nvb += h->rec_ops[q].nvb;
   h->rec_phases.push_back(ph);
@@ -455,11 +463,25 @@ inline bool mega_route(afmg_handle* h, int nboxes, bool ok = true) {
   return false;
 }
 
-// Cross-GPU barrier between dependent kernels (no-op on one GPU, where stream order suffices)
-void enq_barrier(afmg_handle* h) {
+// Cross-GPU barrier between dependent kernels (no-op on one GPU, where stream order suffices).
+// `multi` = the operation it follows involves a level whose boxes are spread over several ranks.  Operations on
+// levels that live entirely on rank 0 (the coarse grid and the small levels the partition does not split) need no
+// barrier between each other -- the reference itself drops to one thread there (m_af_multigrid.f90:276-290) -- but the
+// next operation that involves other ranks must wait for them (pre_sync).  Every rank evaluates the same static
+// rule, so all ranks enter the same number of barriers.
+inline bool lvl_multi(const afmg_handle* h, int l) { return l >= 1 && l <= h->L && h->lvl_multi[l]; }
+void enq_barrier(afmg_handle* h, bool multi = true) {
   if (h->nranks == 1) return;
+  if (!multi) {
+    h->unsynced = true;
+    return;
+  }
   Launch L_(h, "barrier");
   launch_k(h, k_barrier, 1, 32, 0, h->d_comm, h->peers, h->nranks, h->me, h->barrier_timeout_ns);
+  h->unsynced = false;
+}
+inline void pre_sync(afmg_handle* h, bool multi = true) {
+  if (h->nranks > 1 && multi && h->unsynced) enq_barrier(h, true);
 }
 
 // one half-sweep + side ghost fill on level l
@@ -482,6 +504,12 @@ inline int nspec(const afmg_handle* h, int l) { return h->have_stencils ? h->spe
 // when its results are read, or its inputs overwritten, by kernels of other ranks.
 void enq_gsrb(afmg_handle* h, int l, int redblack) {
   const Range r = own(h, l);
+  pre_sync(h, lvl_multi(h, l));
+  if (mega_route(h, nlev(h, l))) {
+    mega_op(h, MK_GSRB, l, r.s0, r.n, redblack & 1, l);
+    mega_end_phase(h);
+    return;
+  }
   if (r.n > 0) {
     Launch L_(h, "gsrb", l);
     DISPATCH_NC(h, NC, {
@@ -496,7 +524,7 @@ void enq_gsrb(afmg_handle* h, int l, int redblack) {
     Launch L_(h, "gsrb_gen", l);
     DISPATCH_NC(h, NC, { launch_k(h, k_gsrb_gen<NC>, ns, 256, 0, h->cx, h->d_spec + h->spec_off[l], ns, redblack & 1); });
   }
-  enq_barrier(h);
+  enq_barrier(h, lvl_multi(h, l));
 }
 
 // reads the (frozen) coarse level, writes this rank's rule rows: no barrier needed afterwards
@@ -508,7 +536,13 @@ inline Range own_rb(const afmg_handle* h, int l) {  // this rank's refinement-bo
 void enq_rb_prepare(afmg_handle* h, int l) {
   const Range rb = own_rb(h, l);
   const int r0 = rb.s0, n = rb.n;
+  pre_sync(h, lvl_multi(h, l) || lvl_multi(h, l - 1));  // reads the coarse neighbours, possibly on peer GPUs
   if (n == 0) return;
+  if (mega_route(h, nlev(h, l))) {
+    mega_op(h, MK_RB, l, r0, n, V_PHI);
+    mega_end_phase(h);
+    return;
+  }
   Launch L_(h, "rb_prepare", l);
   DISPATCH_NC(h, NC, { launch_k(h, k_rb_prepare<NC>, n, 128, 0, h->cx, r0, n, V_PHI); });
 }
@@ -516,6 +550,13 @@ void enq_rb_prepare(afmg_handle* h, int l) {
 // af_gc_lvl (+ parent update when mode != 0)
 void enq_gc(afmg_handle* h, int l, int var, int corners, int mode) {
   const Range r = own(h, l);
+  pre_sync(h, lvl_multi(h, l));
+  if (mega_route(h, nlev(h, l))) {
+    if (var == V_PHI && mode != 0) mega_op(h, MK_GC2, l, r.s0, r.n, corners, mode);
+    else mega_op(h, MK_GC, l, r.s0, r.n, var, corners);
+    mega_end_phase(h);
+    return;
+  }
   if (r.n > 0) {
     Launch L_(h, mode ? "gc_parent" : "gc", l);
     DISPATCH_NC(h, NC, {
@@ -525,20 +566,28 @@ void enq_gc(afmg_handle* h, int l, int var, int corners, int mode) {
         launch_k(h, k_gc<NC>, r.n, 256, 0, h->cx, r.s0, r.n, var, corners, mode);
     });
   }
-  enq_barrier(h);
+  enq_barrier(h, lvl_multi(h, l));
 }
 
 // rb_lvl > 0: the refinement-boundary interpolation of that (finer) level rides along as extra CTAs
 void enq_edges_corners(afmg_handle* h, int l, int rb_lvl = 0) {
   const Range r = own(h, l);
   const Range rb = own_rb(h, rb_lvl);
+  const bool multi = lvl_multi(h, l) || (rb_lvl > 0 && lvl_multi(h, rb_lvl));
+  pre_sync(h, multi);
+  if (mega_route(h, nlev(h, l))) {
+    mega_op(h, MK_EC, l, r.s0, r.n, V_PHI);
+    mega_op(h, MK_RB, rb_lvl, rb.s0, rb.n, V_PHI);
+    mega_end_phase(h);
+    return;
+  }
   if (r.n > 0) {
     Launch L_(h, "edges_corners", l);
     DISPATCH_NC(h, NC, { launch_k(h, k_edges_corners<NC>, r.n + rb.n, 64, 0, h->cx, r.s0, r.n, V_PHI, rb.s0, rb.n); });
   } else if (rb.n > 0) {
     enq_rb_prepare(h, rb_lvl);
   }
-  enq_barrier(h);
+  enq_barrier(h, multi);
 }
 
 template <int NC>
@@ -551,6 +600,14 @@ struct OpCfg {
 void enq_restrict(afmg_handle* h, int l, int keep_res, int rb_lvl = 0) {
   const Range r = own(h, l);
   const Range rb = own_rb(h, rb_lvl);
+  const bool multi = lvl_multi(h, l) || lvl_multi(h, l - 1) || (rb_lvl > 0 && (lvl_multi(h, rb_lvl) || lvl_multi(h, rb_lvl - 1)));
+  pre_sync(h, multi);
+  if (mega_route(h, nlev(h, l))) {
+    mega_op(h, MK_RESTRICT, l, r.s0, r.n, keep_res);
+    mega_op(h, MK_RB, rb_lvl, rb.s0, rb.n, V_PHI);
+    mega_end_phase(h);
+    return;
+  }
   if (r.n > 0) {
     Launch L_(h, "restrict", l);
     DISPATCH_NC(h, NC, {
@@ -568,7 +625,7 @@ void enq_restrict(afmg_handle* h, int l, int keep_res, int rb_lvl = 0) {
           h->cx, h->d_spec + h->spec_off[l], ns, nullptr, keep_res);
     });
   }
-  enq_barrier(h);
+  enq_barrier(h, multi);
 }
 
 // correct_children; with push the side ghost cells of the children are filled as well (the caller
@@ -577,7 +634,12 @@ void enq_restrict(afmg_handle* h, int l, int keep_res, int rb_lvl = 0) {
 void enq_correct(afmg_handle* h, int lp, bool store_corr, bool push) {
   if (lp >= h->L || h->npar[lp] == 0) return;
   const Range rc = own(h, lp + 1);
-  if (rc.n > 0) {
+  const bool multi = lvl_multi(h, lp) || lvl_multi(h, lp + 1);
+  pre_sync(h, multi);
+  if (mega_route(h, nlev(h, lp + 1))) {
+    mega_op(h, MK_CORRECT, lp, rc.s0, rc.n, push ? 1 : 0);
+    mega_end_phase(h);
+  } else if (rc.n > 0) {
     Launch L_(h, "correct", lp);
     DISPATCH_NC(h, NC, {
       constexpr int W = NC / 2 + 2;
@@ -585,10 +647,13 @@ void enq_correct(afmg_handle* h, int lp, bool store_corr, bool push) {
       launch_k(h, k_correct3<NC>, rc.n, 256, smem, h->cx, rc.s0, rc.n, push ? 1 : 0);
     });
   }
-  enq_barrier(h);  // all children have read the old tmp of their parents
+  enq_barrier(h, multi);  // all children have read the old tmp of their parents
   if (store_corr) {
     const Range rp = own(h, lp);
-    if (rp.n > 0) {
+    if (mega_route(h, nlev(h, lp))) {
+      mega_op(h, MK_STORE_CORR, lp, rp.s0, rp.n);
+      mega_end_phase(h);
+    } else if (rp.n > 0) {
       Launch L_(h, "store_corr", lp);
       DISPATCH_NC(h, NC, { launch_k(h, k_store_corr<NC>, rp.n, 256, 0, h->cx, rp.s0, rp.n); });
     }
@@ -637,7 +702,13 @@ void enq_residual(afmg_handle* h, int l_lo, int l_hi, bool with_max) {
     }
   }
   if (h->nranks == 1) {
-    launch(h->lvl_off[l_lo], h->lvl_off[l_hi + 1] - h->lvl_off[l_lo]);
+    const int s0 = h->lvl_off[l_lo], n = h->lvl_off[l_hi + 1] - h->lvl_off[l_lo];
+    if (mega_route(h, n)) {
+      mega_op(h, MK_RESID, l_hi, s0, n, with_max ? 1 : 0);
+      mega_end_phase(h);
+    } else {
+      launch(s0, n);
+    }
   } else {
     for (int l = l_lo; l <= l_hi; ++l) {
       const Range r = own(h, l);
@@ -658,12 +729,38 @@ void configure_kernels(afmg_handle* h) {
     set_max_smem(k_gc2<NC>, OpCfg<NC>::TILE);
     set_max_smem(k_correct3<NC>, (size_t)(2 * Lay3<NC>::NI + (NC / 2 + 2) * (NC / 2 + 2) * (NC / 2 + 2)) * sizeof(double));
   });
+  // persistent kernel: grid = what is co-resident on this device (cooperative launch)
+  h->mega_grid = 0;
+  int nsm = 0, per_sm = 0;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+  if (h->o.n_cell == 16) {
+    h->mega_smem = MegaCfg<16>::smem_bytes(1024);
+    set_max_smem(k_mega<16>, h->mega_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mega<16>, 256, h->mega_smem);
+  } else if (h->o.n_cell == 8) {
+    h->mega_smem = MegaCfg<8>::smem_bytes(1024);
+    set_max_smem(k_mega<8>, h->mega_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mega<8>, 256, h->mega_smem);
+  }
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+  if (coop && per_sm > 0) h->mega_grid = nsm * per_sm;
+  if (const char* env = getenv("AFMG_MEGA_GRID")) {
+    const int g = atoi(env);
+    if (g > 0 && g < h->mega_grid) h->mega_grid = g;
+  }
+  cudaGetLastError();
 }
 
 void enq_copy_lvl(afmg_handle* h, int l, int dst, int src) {
   const Range r = own(h, l);
   const size_t n = (size_t)r.n * h->box_len;
   if (n == 0) return;
+  if (mega_route(h, nlev(h, l))) {
+    mega_op(h, MK_COPY, l, r.s0, r.n, dst, src);
+    mega_end_phase(h);
+    return;
+  }
   Launch L_(h, "copy", l);
   const size_t off = (size_t)r.s0 * h->box_len;
   const int blocks = (int)std::min<size_t>((n + 1023) / 1024, 148 * 8);
@@ -672,13 +769,33 @@ void enq_copy_lvl(afmg_handle* h, int l, int dst, int src) {
 
 // solve_coarse_grid (m_af_multigrid.f90:266-291)
 void enq_coarse(afmg_handle* h) {
-  if (h->me != 0) {  // level 1 lives on rank 0; the others only keep the barrier count in step
-    enq_barrier(h);
+  if (h->me != 0) {  // level 1 lives on rank 0; the others only keep the barrier bookkeeping in step
+    enq_barrier(h, false);
     return;
   }
   const int nbox1 = nlev(h, 1);
   const int ntot = h->cs.nx[0] * h->cs.nx[1] * h->cs.nx[2];
   const int blocks = (ntot + 127) / 128;
+  if (mega_route(h, nbox1, !h->cs_dense)) {
+    const int nvb = (ntot + 255) / 256;
+    if (ntot <= 1024 && h->cs_fused) {
+      const bool with_gc = nbox1 <= 8;
+      mega_op(h, MK_CS_FUSED, 1, 0, nbox1, with_gc ? 1 : 0, 0, 0, 0, 1);
+      mega_end_phase(h);
+      if (!with_gc) enq_gc(h, 1, V_PHI, 1, 0);
+      return;
+    }
+    mega_op(h, MK_CS_GATHER, 1, 0, nbox1, 0, 0, 0, 0, nvb);
+    mega_end_phase(h);
+    for (int q = 0; q < 6; ++q) {  // three forward transforms (the last one scales by 1 / eigenvalue), three backward
+      mega_op(h, MK_CS_APPLY, 1, 0, ntot, q % 3, q < 3 ? 1 : 0, q == 2 ? 1 : 0, q & 1, nvb);
+      mega_end_phase(h);
+    }
+    mega_op(h, MK_CS_SCATTER, 1, 0, nbox1, 0, 0, 0, 0, nvb);
+    mega_end_phase(h);
+    enq_gc(h, 1, V_PHI, 1, 0);
+    return;
+  }
   // one CTA does it all, ghost cells of level 1 included; measured: 8^3 cells 20.6 -> 17 us per solve, but 16^3
   // 29 -> 80 us (one SM against 32 CTAs), so only the small coarse grids of the streamer configurations take it
   if (!h->cs_dense && ntot <= 1024 && h->cs_fused) {
@@ -689,7 +806,7 @@ void enq_coarse(afmg_handle* h) {
         launch_k(h, k_cs_fused<NC>, 1, 1024, (size_t)2 * ntot * sizeof(double), h->cx, h->cs, nbox1, with_gc ? 1 : 0);
       });
     }
-    if (with_gc) enq_barrier(h);
+    if (with_gc) enq_barrier(h, false);
     else enq_gc(h, 1, V_PHI, 1, 0);
     return;
   }
@@ -767,7 +884,10 @@ void enq_vcycle(afmg_handle* h, bool set_residual, int max_lvl, bool final_state
   }
   if (set_residual) {
     const bool all = (max_lvl == h->L);
-    if (all) cudaMemsetAsync(h->d_scal, 0, sizeof(unsigned long long), h->stream);
+    if (all) {
+      if (mega_route(h, h->lvl_off[max_lvl + 1])) mega_op_prev_phase(h, MK_CLEAR_SCAL, 0, 0, 1, 0);
+      else if (h->mega_mode != 1) cudaMemsetAsync(h->d_scal, 0, sizeof(unsigned long long), h->stream);
+    }
     enq_residual(h, 1, max_lvl, all);
   }
   if (h->o.subtract_mean) enq_subtract_mean(h, max_lvl);
@@ -831,14 +951,18 @@ void enq_subtract_mean(afmg_handle* h, int max_lvl) {
 void enq_init_phi_rhs(afmg_handle* h) {
   for (int l = h->L; l >= 2; --l) {
     const Range r = own(h, l);
-    if (r.n > 0) {
+    pre_sync(h, lvl_multi(h, l) || lvl_multi(h, l - 1));
+    if (mega_route(h, nlev(h, l))) {
+      mega_op(h, MK_RESTRICT_VAR, l, r.s0, r.n, V_RHS, 1);
+      mega_end_phase(h);
+    } else if (r.n > 0) {
       Launch L_(h, "init_phi_rhs", l);
       DISPATCH_NC(h, NC, {
         constexpr int T = (NC == 16) ? 256 : (NC == 8 ? 64 : 32);
         launch_k(h, k_restrict_var<NC>, r.n, T, 0, h->cx, r.s0, r.n, V_RHS, 1);
       });
     }
-    enq_barrier(h);
+    enq_barrier(h, lvl_multi(h, l) || lvl_multi(h, l - 1));
   }
 }
 
@@ -908,9 +1032,13 @@ void close_peers(afmg_handle* h) {
   h->connected = (h->nranks == 1);
 }
 
+void mega_resolve_stamps(afmg_handle* h);
+
 void drop_graphs(afmg_handle* h) {
-  for (auto& kv : h->graphs)
+  for (auto& kv : h->graphs) {
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    free_programs(kv.second.progs);
+  }
   h->graphs.clear();
 }
 
@@ -1256,31 +1384,113 @@ int ensure_stage(afmg_handle* h, size_t bytes, size_t nslots) {
   return AFMG_OK;
 }
 
+// per-phase durations of the profiled k_mega launches (time stamps written by CTA 0 after every grid barrier)
+const char* mega_kind_name(int k) {
+  static const char* names[MK_COUNT] = {"none", "rb_prepare", "gsrb", "edges_corners", "restrict", "residual", "gc",
+                                        "gc_parent", "coarse", "coarse", "coarse", "coarse", "correct", "store_corr",
+                                        "copy", "init_phi_rhs", "clear"};
+  return (k >= 0 && k < MK_COUNT) ? names[k] : "?";
+}
+void mega_resolve_stamps(afmg_handle* h) {
+  if (h->stamp_runs.empty()) {
+    h->stamps_used = 0;
+    return;
+  }
+  std::vector<unsigned long long> st(h->stamps_used);
+  cudaMemcpy(st.data(), h->d_stamps, st.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  for (auto& run : h->stamp_runs) {
+    const MegaProgram& pr = *run.second;
+    for (int p = 0; p < pr.nphase; ++p) {
+      const MegaOp& op = pr.h_ops[pr.h_phases[p].op0];
+      const bool with_lvl = op.lvl > 0 && op.kind != MK_RESID && (op.kind < MK_CS_FUSED || op.kind >= MK_CORRECT);
+      std::string name = std::string("mega:") + mega_kind_name(op.kind) + (with_lvl ? "_L" + std::to_string(op.lvl) : "");
+      auto& e = h->prof[name];
+      e.ms += (double)(st[run.first + p + 1] - st[run.first + p]) * 1e-6;
+      e.calls++;
+    }
+  }
+  h->stamp_runs.clear();
+  h->stamps_used = 0;
+}
+
+// walk `body` once in plan mode: the persistent-kernel programs of its segments are built and uploaded into `out`
+template <class F>
+void mega_plan(afmg_handle* h, std::vector<MegaProgram>& out, F& body) {
+  h->rec_ops.clear();
+  h->rec_phases.clear();
+  h->mega_open = false;
+  h->progs = &out;
+  h->mega_mode = 1;
+  body();
+  mega_flush(h);
+  h->mega_mode = 0;
+}
+template <class F>
+void mega_exec(afmg_handle* h, std::vector<MegaProgram>& progs, F& body) {
+  h->progs = &progs;
+  h->prog_idx = 0;
+  h->mega_open = false;
+  h->mega_mode = 2;
+  body();
+  mega_flush(h);
+  h->mega_mode = 0;
+  h->progs = nullptr;
+}
+
+// run `body` (a sequence of enq_* calls) without a graph: single operations of the C ABI, profiling mode
+template <class F>
+int run_direct(afmg_handle* h, F body) {
+  if (!mega_possible(h)) {
+    body();
+    pre_sync(h);  // every body ends with all ranks in step (see enq_barrier)
+    return AFMG_OK;
+  }
+  CK(cudaStreamSynchronize(h->stream));  // the programs of the previous direct run may still be in use
+  mega_resolve_stamps(h);
+  free_programs(h->direct_progs);
+  mega_plan(h, h->direct_progs, body);
+  mega_exec(h, h->direct_progs, body);
+  return AFMG_OK;
+}
+
 // run `body` through a cached CUDA graph (or directly when profiling)
 template <class F>
 int run_graph(afmg_handle* h, std::tuple<int, int, int> key, int n_rep, F body) {
   if (h->profiling) {
-    for (int i = 0; i < n_rep; ++i) body();
+    for (int i = 0; i < n_rep; ++i) {
+      int rc = run_direct(h, body);
+      if (rc) return rc;
+    }
     CK(cudaGetLastError());
     return AFMG_OK;
   }
   auto it = h->graphs.find(key);
   if (it == h->graphs.end()) {
     cudaGraph_t g = nullptr;
+    Graph gr;
+    const bool mega = mega_possible(h);
+    if (mega) mega_plan(h, gr.progs, body);
     const int64_t before = h->launches;
     h->capturing = true;
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    body();
+    if (mega) mega_exec(h, gr.progs, body);
+    else body();
+    pre_sync(h);  // every cycle ends with all ranks in step (see enq_barrier)
     cudaError_t e = cudaStreamEndCapture(h->stream, &g);
     h->capturing = false;
-    if (e != cudaSuccess) return h->fail(AFMG_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-    Graph gr;
+    if (e != cudaSuccess) {
+      free_programs(gr.progs);
+      return h->fail(AFMG_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    }
     gr.launches = h->launches - before;
     h->launches = before;
     e = cudaGraphInstantiate(&gr.exec, g, 0);
     cudaGraphDestroy(g);
-    if (e != cudaSuccess) return h->fail(AFMG_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
-    it = h->graphs.emplace(key, gr).first;
+    if (e != cudaSuccess) {
+      free_programs(gr.progs);
+      return h->fail(AFMG_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    }
+    it = h->graphs.emplace(key, std::move(gr)).first;
   }
   for (int i = 0; i < n_rep; ++i) {
     CK(cudaGraphLaunch(it->second.exec, h->stream));
@@ -1297,7 +1507,16 @@ int check_lvl(afmg_handle* h, int lvl) {
 int finish_op(afmg_handle* h) {
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
-  if (h->profiling) prof_resolve(h);
+  if (h->profiling) {
+    prof_resolve(h);
+    mega_resolve_stamps(h);
+  }
+  if (h->mega_launched) {
+    h->mega_launched = false;
+    unsigned long long err = 0;
+    CK(cudaMemcpy(&err, &h->d_msync->err, sizeof err, cudaMemcpyDeviceToHost));
+    if (err) return h->fail(AFMG_ERR_CUDA, "a grid barrier of the persistent kernel timed out (CTAs not co-resident?)");
+  }
   if (h->nranks > 1) {
     unsigned long long err = 0;
     CK(cudaMemcpy(&err, &h->d_comm->err, sizeof err, cudaMemcpyDeviceToHost));
@@ -1368,11 +1587,22 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_comm, sizeof(CommBlock));
   if (e == cudaSuccess) e = cudaMemset(h->d_comm, 0, sizeof(CommBlock));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_msync, sizeof(MegaSync));
+  if (e == cudaSuccess) e = cudaMemset(h->d_msync, 0, sizeof(MegaSync));
+  h->stamps_cap = 1 << 16;
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_stamps, (size_t)h->stamps_cap * sizeof(unsigned long long));
   if (e == cudaSuccess) h->d_scal = h->d_comm->scal;  // address arithmetic only
   if (e == cudaSuccess) e = cudaMemcpy(&h->d_comm->lsf_value, &opts->lsf_boundary_value, sizeof(double), cudaMemcpyHostToDevice);
   h->peers.p[0] = h->d_comm;
   if (const char* env = getenv("AFMG_PDL")) h->pdl = atoi(env) != 0;
   if (const char* env = getenv("AFMG_CS_FUSED")) h->cs_fused = atoi(env) != 0;
+  if (const char* env = getenv("AFMG_MIN_SPLIT_BOXES")) h->min_split_boxes = atoi(env);
+  if (const char* env = getenv("AFMG_MEGA")) h->mega_enabled = atoi(env) != 0;
+  if (const char* env = getenv("AFMG_MEGA_MAX_BOXES")) h->mega_max_boxes = atoi(env);
+  if (const char* env = getenv("AFMG_MEGA_TIMEOUT_S")) {
+    const double sec = atof(env);
+    if (sec > 0) h->mega_timeout_ns = (unsigned long long)(sec * 1e9);
+  }
   if (const char* env = getenv("AFMG_BARRIER_TIMEOUT_S")) {
     const double sec = atof(env);
     if (sec > 0) h->barrier_timeout_ns = (unsigned long long)(sec * 1e9);
@@ -1394,6 +1624,9 @@ int afmg_destroy(afmg_handle* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   drop_graphs(h);
+  free_programs(h->direct_progs);
+  cudaFree(h->d_msync);
+  cudaFree(h->d_stamps);
   s2_free(h);
   fs_free(h);
   close_peers(h);
@@ -1595,7 +1828,9 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
   // ownership: contiguous Morton ranges per level, cut at sibling groups (afmg_partition)
   {
     std::vector<int> rel((size_t)L * (h->nranks + 1));
-    afmg_partition(h->nranks, L, t->lvl_counts, rel.data());
+    int min_split = h->min_split_boxes;
+    if (min_split < 0) min_split = (4 << 20) / (h->o.n_cell * h->o.n_cell * h->o.n_cell);  // 4 Mi cells
+    afmg_partition_min(h->nranks, L, t->lvl_counts, min_split, rel.data());
     h->cut.assign((size_t)(L + 2) * (h->nranks + 1), 0);
     h->rb_cut.assign((size_t)(L + 2) * (h->nranks + 1), 0);
     h->h_owner.assign(total, 0);
@@ -1617,6 +1852,14 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
       if (q != h->rb_lvl_off[l + 1]) return h->fail(AFMG_ERR_ARG, "internal: refinement-boundary faces not sorted by owner");
     }
     if ((rc = dev_upload(h, &h->d_owner, h->h_owner))) return rc;
+    h->lvl_multi.assign(L + 2, 0);
+    for (int l = 1; l <= L; ++l) {
+      int owners = 0;
+      for (int r = 0; r < h->nranks; ++r)
+        owners += h->cut[(size_t)l * (h->nranks + 1) + r + 1] > h->cut[(size_t)l * (h->nranks + 1) + r] ? 1 : 0;
+      h->lvl_multi[l] = owners > 1;
+    }
+    h->unsynced = false;
   }
   h->connected = (h->nranks == 1);
   // explicit stencils belong to the previous tree: the shim re-ships them (afmg_set_stencils)
@@ -2159,8 +2402,11 @@ int afmg_gsrb_boxes(afmg_handle* h, int32_t lvl, int32_t type_cycle) {
     s2_gsrb_boxes(h, lvl, type_cycle == 3);
     return finish_op(h);
   }
-  enq_rb_prepare(h, lvl);
-  enq_gsrb_boxes(h, lvl, type_cycle == 3);
+  if (int rc_ = run_direct(h, [&] {
+        enq_rb_prepare(h, lvl);
+        enq_gsrb_boxes(h, lvl, type_cycle == 3);
+      }))
+    return rc_;
   return finish_op(h);
 }
 
@@ -2174,8 +2420,11 @@ int afmg_gsrb_halfsweep(afmg_handle* h, int32_t lvl, int32_t redblack) {
     s2_gc(h, lvl, 0);
     return finish_op(h);
   }
-  enq_rb_prepare(h, lvl);
-  enq_gsrb(h, lvl, redblack);
+  if (int rc_ = run_direct(h, [&] {
+        enq_rb_prepare(h, lvl);
+        enq_gsrb(h, lvl, redblack);
+      }))
+    return rc_;
   return finish_op(h);
 }
 
@@ -2189,8 +2438,11 @@ int afmg_gc_lvl(afmg_handle* h, int32_t lvl, int32_t var, int32_t corners) {
     s2_gc(h, lvl, corners);
     return finish_op(h);
   }
-  enq_rb_prepare(h, lvl);
-  enq_gc(h, lvl, var, corners, 0);
+  if (int rc_ = run_direct(h, [&] {
+        enq_rb_prepare(h, lvl);
+        enq_gc(h, lvl, var, corners, 0);
+      }))
+    return rc_;
   return finish_op(h);
 }
 
@@ -2200,7 +2452,7 @@ int afmg_update_coarse(afmg_handle* h, int32_t lvl, int32_t with_tmp) {
   if (rc) return rc;
   if (lvl < 2) return h->fail(AFMG_ERR_ARG, "update_coarse needs lvl >= 2");
   if (h->o.ndim == 2) s2_update_coarse(h, lvl, with_tmp != 0);
-  else enq_update_coarse(h, lvl, with_tmp != 0);
+  else if (int rc_ = run_direct(h, [&] { enq_update_coarse(h, lvl, with_tmp != 0); })) return rc_;
   return finish_op(h);
 }
 
@@ -2209,7 +2461,7 @@ int afmg_correct_children(afmg_handle* h, int32_t lvl_parents) {
   int rc = check_lvl(h, lvl_parents);
   if (rc) return rc;
   if (h->o.ndim == 2) s2_correct(h, lvl_parents, true);
-  else enq_correct(h, lvl_parents, true, false);
+  else if (int rc_ = run_direct(h, [&] { enq_correct(h, lvl_parents, true, false); })) return rc_;
   return finish_op(h);
 }
 
@@ -2219,7 +2471,7 @@ int afmg_correct_children_gc(afmg_handle* h, int32_t lvl_parents) {
   if (rc) return rc;
   if (lvl_parents >= h->L) return h->fail(AFMG_ERR_ARG, "no level above %d", lvl_parents);
   if (h->o.ndim == 2) s2_correct_gc(h, lvl_parents, true);
-  else enq_correct_gc(h, lvl_parents, true);
+  else if (int rc_ = run_direct(h, [&] { enq_correct_gc(h, lvl_parents, true); })) return rc_;
   return finish_op(h);
 }
 
@@ -2228,21 +2480,21 @@ int afmg_residual_lvl(afmg_handle* h, int32_t lvl) {
   int rc = check_lvl(h, lvl);
   if (rc) return rc;
   if (h->o.ndim == 2) s2_residual(h, lvl, lvl, false);
-  else enq_residual(h, lvl, lvl, false);
+  else if (int rc_ = run_direct(h, [&] { enq_residual(h, lvl, lvl, false); })) return rc_;
   return finish_op(h);
 }
 
 int afmg_solve_coarse_grid(afmg_handle* h) {
   SINGLE_OP_PROLOGUE();
   if (h->o.ndim == 2) s2_coarse(h);
-  else enq_coarse(h);
+  else if (int rc_ = run_direct(h, [&] { enq_coarse(h); })) return rc_;
   return finish_op(h);
 }
 
 int afmg_init_phi_rhs(afmg_handle* h) {
   SINGLE_OP_PROLOGUE();
   if (h->o.ndim == 2) s2_init_phi_rhs(h);
-  else enq_init_phi_rhs(h);
+  else if (int rc_ = run_direct(h, [&] { enq_init_phi_rhs(h); })) return rc_;
   return finish_op(h);
 }
 
@@ -2332,6 +2584,18 @@ int afmg_checksum(afmg_handle* h, int32_t var, uint64_t* sum_out, uint64_t* xor_
   return AFMG_OK;
 }
 
+int afmg_set_mega(afmg_handle* h, int32_t enabled, int32_t max_boxes) {
+  if (!h) return AFMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  drop_graphs(h);  // the cached cycles were built for the previous setting
+  h->mega_enabled = enabled != 0;
+  h->mega_max_boxes = max_boxes > 0 ? max_boxes : 0;
+  return AFMG_OK;
+}
+
+int32_t afmg_mega_active(const afmg_handle* h) { return (h && mega_possible(h)) ? h->mega_grid : 0; }
+
 int64_t afmg_kernel_launches(const afmg_handle* h) { return h ? h->launches : 0; }
 
 int afmg_last_cycle_ms(afmg_handle* h, double* ms) {
@@ -2348,6 +2612,7 @@ int afmg_set_profiling(afmg_handle* h, int32_t on) {
   if (!h) return AFMG_ERR_ARG;
   CK(cudaStreamSynchronize(h->stream));
   prof_resolve(h);
+  mega_resolve_stamps(h);
   h->profiling = on != 0;
   if (on) h->prof.clear();
   return AFMG_OK;
@@ -2356,6 +2621,7 @@ int afmg_set_profiling(afmg_handle* h, int32_t on) {
 int afmg_profile(afmg_handle* h, int32_t cap, char (*names)[32], double* ms, int64_t* calls, int32_t* n) {
   if (!h || !n) return AFMG_ERR_ARG;
   prof_resolve(h);
+  mega_resolve_stamps(h);
   int k = 0;
   for (auto& kv : h->prof) {
     if (k >= cap) break;
@@ -2426,11 +2692,19 @@ int32_t afmg_slot_of_box(const afmg_handle* h, int32_t box_id) {
 // box never straddle two ranks; level 1 (the coarse grid) stays on rank 0.  cuts[(l-1)*(n_ranks+1)+r] =
 // first box (position in the level's Morton order) of rank r on level l; the last entry is the count.
 int afmg_partition(int32_t n_ranks, int32_t highest_lvl, const int32_t* lvl_counts, int32_t* cuts) {
+  return afmg_partition_min(n_ranks, highest_lvl, lvl_counts, 0, cuts);
+}
+
+// min_split_boxes: levels with fewer boxes are not split (they stay on rank 0 with the coarse grid): below a few
+// million cells a level is launch-latency bound, splitting it buys nothing and costs a cross-GPU barrier per operation
+// (measured on S3, 8 GPUs: 512 boxes of 16^3 take 0.096 ms per gsrb_boxes on one GPU and 0.103 ms on eight)
+int afmg_partition_min(int32_t n_ranks, int32_t highest_lvl, const int32_t* lvl_counts, int32_t min_split_boxes,
+                       int32_t* cuts) {
   if (n_ranks < 1 || n_ranks > AFMG_MAX_RANKS || highest_lvl < 1 || !lvl_counts || !cuts) return AFMG_ERR_ARG;
   for (int l = 1; l <= highest_lvl; ++l) {
     int32_t* c = cuts + (size_t)(l - 1) * (n_ranks + 1);
     const int n = lvl_counts[l - 1];
-    if (l == 1 || n % 8 != 0) {
+    if (l == 1 || n % 8 != 0 || n < min_split_boxes) {
       c[0] = 0;
       for (int r = 1; r <= n_ranks; ++r) c[r] = n;
       continue;

@@ -14,10 +14,8 @@
 //
 // Memory ordering between phases (writer side -> barrier -> reader side):
 //   * every thread waits for the completion of its own TMA bulk stores (cp.async.bulk.wait_group 0, not .read);
-//   * __syncthreads(); thread 0: fence.proxy.async (async-proxy writes vs generic proxy), __threadfence(),
-//     red.release.gpu on the counter; it then spins with ld.acquire.gpu (which also drops stale L1 lines of the SM)
-//     and issues fence.proxy.async again before any TMA load of the next phase reads what other CTAs wrote with
-//     plain stores; __syncthreads() releases the CTA;
+//   * __syncthreads(); thread 0: red.release.gpu on the counter, then it spins with ld.acquire.gpu (which also drops
+//     stale L1 lines of the SM); __syncthreads() releases the CTA (see mega_grid_barrier for why one fence suffices);
 //   * data that is written during the kernel is never read through the non-coherent path (LDG = false variants).
 // The barrier has the same time-out escape as k_barrier: a CTA that waits longer than `timeout_ns` sets sync->err,
 // later barriers fall through, and the host reports AFMG_ERR_CUDA instead of hanging the device.
@@ -106,25 +104,38 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
   return v;
 }
 
-// all CTAs of the (co-resident) grid; `target` = value the arrival counter reaches when every CTA has arrived
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// All CTAs of the (co-resident) grid; `target` = value the arrival counter reaches when every CTA has arrived.
+// Cost matters here: a cycle has ~100 of these.  One GPU-scope release per CTA (red.release.gpu = MEMBAR.GPU + REDG;
+// measured: every additional GPU-scope fence -- __threadfence(), fence.proxy.async -- adds ~0.6 us to EVERY phase) and
+// acquire polls (LDG.STRONG.GPU + CCTL.IVALL, no membar).  Why no proxy fence is needed around it: the async-proxy
+// writes of this CTA (bulk stores) have been waited for to completion by their issuing threads before the
+// __syncthreads() (cp.async.bulk.wait_group 0), so they are ordinary visible writes that the release publishes; and
+// the async-proxy reads of the next phase (TMA loads) go to L2, where the release / acquire pair has made every
+// generic write of the other CTAs visible (the L1 lines an SM could still hold are dropped by the acquire).
 __device__ __forceinline__ void mega_grid_barrier(MegaSync* sync, unsigned long long target, unsigned long long timeout_ns) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    fence_proxy_async_all();
-    __threadfence();
     red_release_gpu_inc(&sync->count);
-    if (ld_acquire_gpu(&sync->err) == 0) {
-      const unsigned long long t0 = globaltimer_ns();
-      unsigned spins = 0;
-      while (ld_acquire_gpu(&sync->count) < target) {
-        if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > timeout_ns) {
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
+    while (ld_acquire_gpu(&sync->count) < target) {
+      if ((++spins & 255u) == 0) {
+        if (ld_relaxed_gpu(&sync->err) != 0) break;  // an earlier barrier timed out: fall through
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > timeout_ns) {
           sync->err = 1;
           __threadfence();
           break;
         }
       }
     }
-    fence_proxy_async_all();
   }
   __syncthreads();
 }
@@ -236,6 +247,8 @@ __device__ __forceinline__ void mega_run_op(const DevCtx& cx, const CoarseCtx& c
   }
 }
 
+constexpr int MEGA_MAX_OPS = 4;  // operations per phase (the host never records more)
+
 template <int NC>
 __global__ void __launch_bounds__(MegaCfg<NC>::THREADS, MegaCfg<NC>::MINB)
     k_mega(DevCtx cx, CoarseCtx cs, const MegaPhase* __restrict__ phases, const MegaOp* __restrict__ ops, int nphase,
@@ -243,24 +256,38 @@ __global__ void __launch_bounds__(MegaCfg<NC>::THREADS, MegaCfg<NC>::MINB)
   extern __shared__ __align__(128) double smem[];
   __shared__ uint64_t bar;
   __shared__ unsigned long long s_base;
+  // phase descriptors are double-buffered in shared memory: the one of phase p + 1 is fetched while phase p runs,
+  // so that no dependent global loads sit between a barrier and the first TMA load of the next phase
+  __shared__ MegaPhase s_ph[2];
+  __shared__ MegaOp s_op[2][MEGA_MAX_OPS];
   const int tid = threadIdx.x;
+  auto fetch = [&](int p) {  // threads 32 .. 32 + MEGA_MAX_OPS of the CTA
+    const int q = tid - 32;
+    if (q >= 0 && q < MEGA_MAX_OPS && p < nphase) {
+      const MegaPhase ph = phases[p];
+      if (q == 0) s_ph[p & 1] = ph;
+      if (q < ph.nops) s_op[p & 1][q] = ops[ph.op0 + q];
+    }
+  };
   if (tid == 0) {
     mbar_init(&bar, 1);
     s_base = ld_acquire_gpu(&sync->base);
     if (stamps && blockIdx.x == 0) stamps[0] = globaltimer_ns();
   }
+  fetch(0);
   __syncthreads();
   uint32_t par = 0;
   unsigned long long target = s_base;
   for (int p = 0; p < nphase; ++p) {
-    const MegaPhase ph = phases[p];
+    fetch(p + 1);  // visible after the barrier's __syncthreads
+    const MegaPhase ph = s_ph[p & 1];
     for (int vb = blockIdx.x; vb < ph.nvb; vb += gridDim.x) {
-      int o = ph.op0, v = vb;
-      while (v >= ops[o].nvb) {
-        v -= ops[o].nvb;
+      int o = 0, v = vb;
+      while (v >= s_op[p & 1][o].nvb) {
+        v -= s_op[p & 1][o].nvb;
         ++o;
       }
-      const MegaOp op = ops[o];
+      const MegaOp op = s_op[p & 1][o];
       mega_run_op<NC>(cx, cs, op, v, smem, &bar, par, scal);
       // the block's bulk stores are complete and its shared memory is free for the next block
       bulk_commit();

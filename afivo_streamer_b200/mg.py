@@ -309,6 +309,13 @@ class mg_t:
         self._check(_lib.lib().afmg_checksum(self._h, var, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
+    def set_mega(self, enabled=True, max_boxes=0):
+        """persistent-kernel segments on / off (afmg_set_mega); max_boxes = 0: the default level-size limit"""
+        self._check(_lib.lib().afmg_set_mega(self._h, int(enabled), int(max_boxes)))
+
+    def mega_active(self):
+        return int(_lib.lib().afmg_mega_active(self._h))
+
     def kernel_launches(self):
         return int(_lib.lib().afmg_kernel_launches(self._h))
 
@@ -480,12 +487,13 @@ def comm_from_torch(group=None):
     return rank, world, allgather
 
 
-def partition(n_ranks: int, lvl_counts):
-    """afmg_partition: per level, the first position (Morton order) of every rank; shape (L, n_ranks + 1)."""
+def partition(n_ranks: int, lvl_counts, min_split_boxes: int = 0):
+    """afmg_partition_min: per level, the first position (Morton order) of every rank; shape (L, n_ranks + 1).
+    Levels with fewer than min_split_boxes boxes stay on rank 0 (0: plain afmg_partition)."""
     counts = np.ascontiguousarray(lvl_counts, np.int32)
     cuts = np.zeros((len(counts), n_ranks + 1), np.int32)
-    rc = _lib.lib().afmg_partition(n_ranks, len(counts), counts.ctypes.data_as(C.POINTER(C.c_int32)),
-                                   cuts.ctypes.data_as(C.POINTER(C.c_int32)))
+    rc = _lib.lib().afmg_partition_min(n_ranks, len(counts), counts.ctypes.data_as(C.POINTER(C.c_int32)),
+                                       int(min_split_boxes), cuts.ctypes.data_as(C.POINTER(C.c_int32)))
     if rc != 0:
         raise AfmgError(rc, "afmg_partition: invalid arguments")
     return cuts

@@ -400,7 +400,6 @@ def run_gpu(args):
     # rhs: constant 1 for S1 (poisson_benchmark), deterministic pseudo-random otherwise; made on the device
     chunk = 4096
     h_rhs = torch.empty(len(ids) * box_len, dtype=torch.float64).pin_memory()
-    h_phi = torch.empty(len(ids) * box_len, dtype=torch.float64).pin_memory()
     for q0 in range(0, len(ids), chunk):
         q1 = min(len(ids), q0 + chunk)
         if args.workload == "S1":
@@ -501,19 +500,31 @@ def run_gpu(args):
             M.mg_destroy(m)
 
     # ---- e2e: host buffers through the C ABI -----------------------------------------------
-    # e2e: rhs goes up as interior cells only (its ghost cells are never read), phi comes back with ghost cells
+    # one step = upload rhs (interior cells of this rank's leaves: ghost cells of rhs are never read) -> V-cycle ->
+    # max-norm of the residual -> download phi (interior cells of the leaves; its ghost cells stay valid on the
+    # device).  Pinned host buffers; the library overlaps the PCIe copy of one chunk with the (un)pack kernel of the
+    # previous one.  All four calls are blocking, so host wall time is the end-to-end time.
     ncell = tree.nc ** tree.ndim
     h_rhs_int = torch.empty(len(ids) * ncell, dtype=torch.float64).pin_memory()
+    h_phi_int = torch.empty(len(ids) * ncell, dtype=torch.float64).pin_memory()
     nd = tree.ndim
     full = h_rhs.view((len(ids),) + (tree.nc + 2,) * nd)
     h_rhs_int.view((len(ids),) + (tree.nc,) * nd).copy_(full[(slice(None),) + (slice(1, -1),) * nd])
     nbytes_up = h_rhs_int.numel() * 8
+    nbytes_dn = h_phi_int.numel() * 8
+    parts = np.zeros(4)
 
     def e2e_step():
+        t0 = time.perf_counter()
         mg.upload_interior_ptr(M.I_RHS, ids, h_rhs_int.data_ptr())
+        t1 = time.perf_counter()
         M.mg_fas_vcycle(tree, mg, True)
+        t2 = time.perf_counter()
         r = M.af_tree_maxabs_cc(tree, mg, M.I_TMP)
-        mg.download_ptr(M.I_PHI, ids, h_phi.data_ptr())
+        t3 = time.perf_counter()
+        mg.download_interior_ptr(M.I_PHI, ids, h_phi_int.data_ptr())
+        t4 = time.perf_counter()
+        parts[:] += (t1 - t0, t2 - t1, t3 - t2, t4 - t3)
         return r
 
     big = nbytes > (2 << 30)
@@ -521,6 +532,7 @@ def run_gpu(args):
         barrier()
         e2e_step()
     e2e_steps = 3 if big else max(3, min(args.steps, 10))
+    parts[:] = 0
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -529,7 +541,9 @@ def run_gpu(args):
     wall = time.perf_counter() - t0  # the C ABI calls are blocking: host wall time == end-to-end time
     wall_max = allmax(wall)
     e2e_val = cu * e2e_steps / wall_max
-    h2d_total, d2h_total = allsum(nbytes_up), allsum(nbytes + 8)
+    h2d_total, d2h_total = allsum(nbytes_up), allsum(nbytes_dn + 8)
+    e2e_parts = {k: allmax(1e3 * v / e2e_steps) for k, v in zip(("upload_ms", "vcycle_ms", "maxnorm_ms", "download_ms"), parts)}
+    e2e_parts["pcie_GBs_per_gpu"] = (nbytes_up + nbytes_dn) / 1e9 / max(1e-9, (parts[0] + parts[3]) / e2e_steps)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel timing with CUDA events (library profiling mode, no graph) -----------------
@@ -622,7 +636,9 @@ def run_gpu(args):
                                      "boxes, all ranks combined, after the FMG + W + K cycles"},
             "barrier": barrier_stat,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
-                    "steps": e2e_steps, "ms_per_step": 1e3 * wall_max / e2e_steps},
+                    "steps": e2e_steps, "ms_per_step": 1e3 * wall_max / e2e_steps, "phases_max_over_ranks": e2e_parts,
+                    "what": "upload rhs (interior, leaves) -> V-cycle -> residual max-norm -> download phi (interior, "
+                            "leaves); pinned host buffers, blocking C-ABI calls"},
             "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
             "kernel_profile_ms_per_cycle_rank0": {k: v[0] / nprof for k, v in sorted(prof.items())},

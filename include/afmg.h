@@ -376,6 +376,13 @@ int64_t afmg_kernel_launches(const afmg_handle* h);
 int afmg_last_cycle_ms(afmg_handle* h, double* ms);
 /* per-kernel-family accumulated device time; fills up to cap entries, returns count via *n.
  * Only collected while profiling is enabled (it serialises launches). */
+/* Persistent-kernel segments (csrc/mega.cuh): operations on levels of at most `max_boxes` boxes (0 = default: 8192
+ * for 8^3 boxes, 1024 for 16^3) run inside ONE cooperatively launched kernel with grid-wide barriers between them
+ * instead of one launch each -- the launch-bound regime of the streamer trees (nc = 8, many small levels).  Results are
+ * bit-identical to the launch path.  On by default for 3D, single-GPU handles without explicit stencils; AFMG_MEGA=0
+ * or enabled = 0 selects the launch path.  afmg_mega_active: number of CTAs of the persistent kernel, 0 = not used. */
+int afmg_set_mega(afmg_handle* h, int32_t enabled, int32_t max_boxes);
+int32_t afmg_mega_active(const afmg_handle* h);
 int afmg_set_profiling(afmg_handle* h, int32_t on);
 int afmg_profile(afmg_handle* h, int32_t cap, char (*names)[32], double* ms, int64_t* calls, int32_t* n);
 /* cell-updates performed by one V-cycle to highest_lvl (<=0: all) and by one FMG */
@@ -417,6 +424,11 @@ int32_t afmg_owner_of_box(const afmg_handle* h, int32_t box_id);
  * highest_lvl * (n_ranks + 1) entries; rank r owns positions [cuts[(l-1)*(n_ranks+1)+r],
  * cuts[(l-1)*(n_ranks+1)+r+1]) of level l's boxes in Morton order of box%ix. */
 int afmg_partition(int32_t n_ranks, int32_t highest_lvl, const int32_t* lvl_counts, int32_t* cuts);
+/* The rule the handles use: as afmg_partition, but levels with fewer than min_split_boxes boxes are not split -- they
+ * stay on rank 0 next to the coarse grid, and operations between such levels need no cross-GPU barrier (default of a
+ * handle: 4 Mi cells worth of boxes, i.e. 1024 boxes of 16^3 or 8192 of 8^3; AFMG_MIN_SPLIT_BOXES overrides). */
+int afmg_partition_min(int32_t n_ranks, int32_t highest_lvl, const int32_t* lvl_counts, int32_t min_split_boxes,
+                       int32_t* cuts);
 
 #ifdef __cplusplus
 }

@@ -36,3 +36,32 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+# ---- the two execution paths of the 3D cycles (csrc/mega.cuh): the persistent kernel with grid barriers ("mega": every
+# level inside it), the launch path ("launch": one kernel per operation, as in round 1) and their mixture ("hybrid":
+# only levels of at most 8 boxes inside the persistent kernel, so segments open and close within a cycle).  The
+# bit-exact suites run under all three; the handle reads the environment at afmg_create.
+PATH_MODULES = {"test_gpu_kernels", "test_gpu_cycles", "test_golden"}
+PATH_ENV = {"mega": {"AFMG_MEGA": "1", "AFMG_MEGA_MAX_BOXES": "1000000"},
+            "launch": {"AFMG_MEGA": "0"},
+            "hybrid": {"AFMG_MEGA": "1", "AFMG_MEGA_MAX_BOXES": "8"}}
+
+
+@pytest.fixture
+def afmg_path(request):
+    old = {k: os.environ.get(k) for k in ("AFMG_MEGA", "AFMG_MEGA_MAX_BOXES")}
+    for k in old:
+        os.environ.pop(k, None)
+    os.environ.update(PATH_ENV[request.param])
+    yield request.param
+    for k, v in old.items():
+        os.environ.pop(k, None)
+        if v is not None:
+            os.environ[k] = v
+
+
+def pytest_generate_tests(metafunc):
+    if metafunc.module.__name__ in PATH_MODULES and "gpu" in [m.name for m in metafunc.definition.iter_markers()]:
+        metafunc.fixturenames.insert(0, "afmg_path")
+        metafunc.parametrize("afmg_path", sorted(PATH_ENV), indirect=True)

@@ -39,6 +39,16 @@ def test_partition_s3_matches_design():
     assert list(cuts[1]) == [0] + [8] * 8  # 8 boxes = one sibling group -> rank 0
 
 
+def test_partition_keeps_small_levels_on_rank_0():
+    counts = [1, 8, 64, 512, 4096, 32768, 216000]
+    cuts = M.partition(8, counts, min_split_boxes=1024)  # the default of a handle for 16^3 boxes
+    for l in range(4):  # 1, 8, 64, 512 boxes: not split
+        assert list(cuts[l]) == [0] + [counts[l]] * 8
+    assert list(np.diff(cuts[4])) == [512] * 8
+    assert list(np.diff(cuts[6])) == [27000] * 8
+    assert np.array_equal(M.partition(8, counts, 0), M.partition(8, counts))
+
+
 def test_partition_rejects_bad_arguments():
     with pytest.raises(M.AfmgError):
         M.partition(9, [1, 8])
