@@ -1,13 +1,29 @@
+#include "cpp_macros.h"
 !> Drop-in replacement for the solver entry points of afivo's m_af_multigrid
 !> (afivo/src/m_af_multigrid.f90:43, :111, :137, :185, :1188) that forwards to libafmg.so through
 !> ISO_C_BINDING.  Same signatures; the tree (af_t / box_t) stays the reference's own.
 !>
-!> NOTE: this image has no Fortran compiler, so this file is shipped as source and has not been
-!> compiled here.  It uses only m_af_types and iso_c_binding.  Build: add it to afivo/src, list it
-!> in afivo/src/definitions.make next to m_af_multigrid, link with -lafmg.
+!> What happens on every solve (mg_gpu_fas_fmg / mg_gpu_fas_vcycle / mg_gpu_field_solve), in this order:
+!>   1. mg_use(tree, mg) of the reference: boxes created by af_adjust_refinement (tag == af_init_tag) are tagged and
+!>      get their operator / prolongation stencils on the host (m_af_multigrid.f90:118-126, 1147-1185);
+!>   2. topology -> afmg_set_tree, only when a hash of the complete box lists / parents / children / neighbours
+!>      changed (or after mg_gpu_invalidate); with it the explicit stencils are re-shipped and phi is marked stale;
+!>   3. mg%sides_bc evaluated for every physical face -> afmg_set_bc, and mg%lsf_boundary_value ->
+!>      afmg_set_lsf_boundary_value: EVERY solve, because both carry the applied voltage, which changes in time
+!>      (src/m_field.f90:481-487, 590-610).  Neither invalidates the cached cycle graphs when only values change;
+!>   4. rhs of the leaves up; phi up only if the device copy is stale (tree changed, mg_gpu_mark_phi_dirty);
+!>   5. the cycle(s); phi down (with ghost cells: the reference's post-condition), i_tmp down when set_residual
+!>      (switch off with mg_gpu_set_download_tmp when only the max-norm is needed: mg_gpu_tree_maxabs_tmp).
+!> Packed buffers are page-locked memory from afmg_host_alloc, kept between calls.
+!>
+!> NOTE: neither this image nor the GPU box has a Fortran compiler (profiles/r02a_fortran_probe.txt), so this file is
+!> shipped as source and has not been compiled.  Build: add it to afivo/src (it needs cpp_macros.h like every afivo
+!> source that uses DTIMES / NDIM), list it in afivo/src/definitions.make after m_af_multigrid, link with -lafmg.
 module m_af_multigrid_gpu
   use iso_c_binding
   use m_af_types
+  use m_af_stencil, only: af_stencil_index, af_stencil_none, stencil_constant, stencil_variable
+  use m_af_multigrid, only: mg_use
   implicit none
   private
 
@@ -65,6 +81,12 @@ module m_af_multigrid_gpu
        import; type(c_ptr), value :: h; integer(c_int32_t), value :: var, n
        integer(c_int32_t), intent(in) :: ids(*); real(c_double), intent(out) :: packed(*)
      end function
+     type(c_ptr) function afmg_host_alloc(bytes) bind(c, name="afmg_host_alloc")
+       import; integer(c_size_t), value :: bytes
+     end function
+     subroutine afmg_host_free(p) bind(c, name="afmg_host_free")
+       import; type(c_ptr), value :: p
+     end subroutine
      integer(c_int) function afmg_fas_fmg(h, set_residual, have_guess) bind(c, name="afmg_fas_fmg")
        import; type(c_ptr), value :: h; integer(c_int32_t), value :: set_residual, have_guess
      end function
@@ -121,8 +143,12 @@ module m_af_multigrid_gpu
 
   !> One GPU solver per mg_t; looked up by the address-independent key mg%i_phi/mg%i_rhs/lambda slot
   type gpu_state_t
-     type(c_ptr) :: h = c_null_ptr
-     integer     :: tree_signature(3) = -1   ! highest_id, highest_lvl, sum of level sizes
+     type(c_ptr)        :: h = c_null_ptr
+     integer(c_int64_t) :: tree_hash = -1          ! hash of the topology the device holds
+     logical            :: phi_current = .false.   ! the device copy of phi equals the host copy
+     logical            :: download_tmp = .true.   ! bring i_tmp back after a solve with set_residual
+     type(c_ptr)        :: pinned = c_null_ptr     ! page-locked packing buffer (afmg_host_alloc)
+     integer(c_size_t)  :: pinned_len = 0          ! its size in doubles
   end type gpu_state_t
 
   integer, parameter :: max_solvers = 16
@@ -132,6 +158,7 @@ module m_af_multigrid_gpu
   public :: mg_gpu_update_operator_stencil, mg_gpu_tree_maxabs_tmp
   public :: mg_gpu_compute_phi_gradient, mg_gpu_compute_field_norm, mg_gpu_gc_tree_norm, photoi_gpu_helmh_compute
   public :: mg_gpu_field_solve
+  public :: mg_gpu_invalidate, mg_gpu_mark_phi_dirty, mg_gpu_set_download_tmp
 
 contains
 
@@ -164,27 +191,101 @@ contains
     o%dr_base(1:NDIM) = tree%dr_base; o%r_base(1:NDIM) = tree%r_base
     call check(afmg_create(solvers(slot)%h, o), "afmg_create")
     mg%initialized = .true.
-    call sync_tree(tree, mg, slot)
+    solvers(slot)%tree_hash = -1
+    call prepare_solve(tree, mg, slot)
   end subroutine mg_gpu_init
 
-  !> Forward topology and boundary conditions when the tree changed (after af_adjust_refinement)
+  !> Force the next solve to re-send the topology (e.g. from a wrapper of af_adjust_refinement when
+  !> ref_info%n_add + ref_info%n_rm > 0); the hash below makes this optional, not required
+  subroutine mg_gpu_invalidate(slot)
+    integer, intent(in) :: slot
+    solvers(slot)%tree_hash = -1
+    solvers(slot)%phi_current = .false.
+  end subroutine mg_gpu_invalidate
+
+  !> The host changed mg%i_phi since the last solve (anything but af_adjust_refinement, which is detected)
+  subroutine mg_gpu_mark_phi_dirty(slot)
+    integer, intent(in) :: slot
+    solvers(slot)%phi_current = .false.
+  end subroutine mg_gpu_mark_phi_dirty
+
+  subroutine mg_gpu_set_download_tmp(slot, flag)
+    integer, intent(in) :: slot
+    logical, intent(in) :: flag
+    solvers(slot)%download_tmp = flag
+  end subroutine mg_gpu_set_download_tmp
+
+  !> 64-bit mix without overflow (shifts and xor only): one step of the topology hash
+  pure subroutine hash_mix(h, v)
+    integer(c_int64_t), intent(inout) :: h
+    integer, intent(in)               :: v
+    h = ieor(h, int(v, c_int64_t) + 40503_c_int64_t)
+    h = ieor(h, ishft(h, 13))
+    h = ieor(h, ishft(h, -7))
+    h = ieor(h, ishft(h, 17))
+  end subroutine hash_mix
+
+  !> Hash of everything afmg_set_tree receives: af_adjust_refinement reuses the ids of removed boxes, so counts
+  !> and highest_id do not identify a tree; the complete id lists with parents, children and neighbours do
+  function topology_hash(tree) result(h)
+    type(af_t), intent(in) :: tree
+    integer(c_int64_t)     :: h
+    integer                :: lvl, i, id, n
+    h = 1469598103934665603_c_int64_t
+    call hash_mix(h, tree%highest_lvl)
+    call hash_mix(h, tree%highest_id)
+    do lvl = 1, tree%highest_lvl
+       call hash_mix(h, size(tree%lvls(lvl)%ids))
+       do i = 1, size(tree%lvls(lvl)%ids)
+          id = tree%lvls(lvl)%ids(i)
+          call hash_mix(h, id)
+          call hash_mix(h, tree%boxes(id)%parent)
+          call hash_mix(h, tree%boxes(id)%children(1))
+          do n = 1, af_num_neighbors
+             call hash_mix(h, tree%boxes(id)%neighbors(n))
+          end do
+          do n = 1, NDIM
+             call hash_mix(h, tree%boxes(id)%ix(n))
+          end do
+       end do
+    end do
+    if (h == -1) h = 0   ! -1 means "nothing on the device"
+  end function topology_hash
+
+  !> Steps 1-3 of the header: everything a solve needs on the device except cell data
+  subroutine prepare_solve(tree, mg, slot)
+    type(af_t), intent(inout) :: tree
+    type(mg_t), intent(in)    :: mg
+    integer, intent(in)       :: slot
+    call mg_use(tree, mg)          ! tags + stencils of new boxes, tree%mg_current_operator_mask
+    call sync_tree(tree, mg, slot) ! topology + stencils, when the tree changed
+    call sync_bc(tree, mg, slot)   ! boundary values carry the voltage: every solve
+    call check(afmg_set_lsf_boundary_value(solvers(slot)%h, mg%lsf_boundary_value), "afmg_set_lsf_boundary_value")
+    call sync_lsf_boundary_values(tree, mg, slot)
+  end subroutine prepare_solve
+
+  !> done_with_mg of the reference (m_af_multigrid.f90:128-132; private there)
+  subroutine finish_solve(tree)
+    type(af_t), intent(inout) :: tree
+    tree%mg_current_operator_mask = -1
+  end subroutine finish_solve
+
+  !> Forward the topology (and with it the explicit stencils) when the tree changed (after af_adjust_refinement)
   subroutine sync_tree(tree, mg, slot)
     type(af_t), intent(inout) :: tree
     type(mg_t), intent(in)    :: mg
     integer, intent(in)       :: slot
-    integer :: sig(3), lvl, n, i, id, nb, n_faces, nc2, bc_type
+    integer :: lvl, n, i, id
+    integer(c_int64_t) :: hash
     integer(c_int32_t), allocatable, target :: counts(:), ids(:), blvl(:), ix(:, :), parent(:), &
-         children(:, :), neighbors(:, :), nmat(:, :), f_ids(:), f_nbs(:), f_types(:)
-    real(c_double), allocatable, target :: r_min(:, :), f_vals(:, :)
-    real(dp), allocatable :: coords(:, :)
+         children(:, :), neighbors(:, :), nmat(:, :)
+    real(c_double), allocatable, target :: r_min(:, :)
     type(afmg_tree) :: t
 
-    sig = [tree%highest_id, tree%highest_lvl, 0]
-    do lvl = 1, tree%highest_lvl
-       sig(3) = sig(3) + size(tree%lvls(lvl)%ids) * (lvl + 7)
-    end do
-    if (all(sig == solvers(slot)%tree_signature)) return
-    solvers(slot)%tree_signature = sig
+    hash = topology_hash(tree)
+    if (hash == solvers(slot)%tree_hash) return
+    solvers(slot)%tree_hash = hash
+    solvers(slot)%phi_current = .false.   ! new boxes hold prolonged values the device has not seen
 
     n = tree%highest_id
     allocate(counts(tree%highest_lvl), blvl(0:n), ix(NDIM, 0:n), parent(0:n))
@@ -212,17 +313,33 @@ contains
     t%parent = c_loc(parent); t%children = c_loc(children); t%neighbors = c_loc(neighbors)
     t%neighbor_mat = c_loc(nmat); t%r_min = c_loc(r_min)
     call check(afmg_set_tree(solvers(slot)%h, t), "afmg_set_tree")
+    call sync_stencils(tree, mg, slot)
+  end subroutine sync_tree
 
-    ! mg%sides_bc evaluated on the host for every physical face (it never depends on phi)
+  !> mg%sides_bc evaluated on the host for every physical face (it never depends on phi) -> afmg_set_bc.  Called
+  !> before every solve: field_bc_homogeneous returns the current voltage (src/m_field.f90:590-610).  The library keeps
+  !> its cycle graphs when only the values change; changed types rebuild the coarse solver.
+  subroutine sync_bc(tree, mg, slot)
+    type(af_t), intent(inout) :: tree
+    type(mg_t), intent(in)    :: mg
+    integer, intent(in)       :: slot
+    integer :: lvl, i, id, nb, n_faces, nc2, bc_type
+    integer(c_int32_t), allocatable :: f_ids(:), f_nbs(:), f_types(:)
+    real(c_double), allocatable :: f_vals(:, :)
+    real(dp), allocatable :: coords(:, :)
+
     nc2 = tree%n_cell**(NDIM-1)
     n_faces = 0
-    do i = 1, size(ids)
-       n_faces = n_faces + count(tree%boxes(ids(i))%neighbors < af_no_box)
+    do lvl = 1, tree%highest_lvl
+       do i = 1, size(tree%lvls(lvl)%ids)
+          n_faces = n_faces + count(tree%boxes(tree%lvls(lvl)%ids(i))%neighbors < af_no_box)
+       end do
     end do
     allocate(f_ids(n_faces), f_nbs(n_faces), f_types(n_faces), f_vals(nc2, n_faces), coords(NDIM, nc2))
     n_faces = 0
-    do i = 1, size(ids)
-       id = ids(i)
+    do lvl = 1, tree%highest_lvl
+     do i = 1, size(tree%lvls(lvl)%ids)
+       id = tree%lvls(lvl)%ids(i)
        do nb = 1, af_num_neighbors
           if (tree%boxes(id)%neighbors(nb) < af_no_box) then
              n_faces = n_faces + 1
@@ -231,10 +348,10 @@ contains
              f_ids(n_faces) = id; f_nbs(n_faces) = nb; f_types(n_faces) = bc_type
           end if
        end do
+     end do
     end do
     call check(afmg_set_bc(solvers(slot)%h, n_faces, f_ids, f_nbs, f_types, f_vals), "afmg_set_bc")
-    call sync_stencils(tree, mg, slot)
-  end subroutine sync_tree
+  end subroutine sync_bc
 
   !> Ship the stencils mg_set_operators_lvl (m_af_multigrid.f90:1147-1185) stored in box%stencils for
   !> every box that is not a plain constant-Laplacian box: variable / constant eps operators
@@ -242,7 +359,6 @@ contains
   !> stencils.  The builders themselves stay in afivo (they call mg%lsf and friends).  Also called from
   !> mg_gpu_update_operator_stencil after mg_update_operator_stencil changed eps / lsf stencils.
   subroutine sync_stencils(tree, mg, slot)
-    use m_af_stencil, only: af_stencil_index, af_stencil_none, stencil_constant, stencil_variable
     type(af_t), intent(inout) :: tree
     type(mg_t), intent(in)    :: mg
     integer, intent(in)       :: slot
@@ -343,15 +459,32 @@ contains
     call check(afmg_set_lsf_boundary_values(solvers(slot)%h, n, ids, vals), "afmg_set_lsf_boundary_values")
   end subroutine sync_lsf_boundary_values
 
+  !> Page-locked packing buffer of at least n doubles, kept between calls (afmg_host_alloc: transfers from it are
+  !> DMA copies at the PCIe rate; a pageable temporary is staged by the driver at a fraction of it)
+  subroutine pinned_buffer(slot, n, buf_ptr)
+    integer, intent(in)            :: slot
+    integer(c_size_t), intent(in)  :: n
+    type(c_ptr), intent(out)       :: buf_ptr
+    if (n > solvers(slot)%pinned_len) then
+       if (c_associated(solvers(slot)%pinned)) call afmg_host_free(solvers(slot)%pinned)
+       solvers(slot)%pinned = afmg_host_alloc(8_c_size_t * n)
+       if (.not. c_associated(solvers(slot)%pinned)) error stop "m_af_multigrid_gpu: afmg_host_alloc failed"
+       solvers(slot)%pinned_len = n
+    end if
+    buf_ptr = solvers(slot)%pinned
+  end subroutine pinned_buffer
+
   !> Pack box%cc(:, :, :, iv) of a list of boxes and upload / download
   subroutine transfer(tree, slot, iv, var, ids, up)
     type(af_t), intent(inout) :: tree
     integer, intent(in)       :: slot, iv, var, ids(:)
     logical, intent(in)       :: up
-    real(c_double), allocatable :: buf(:, :)
+    real(c_double), pointer   :: buf(:, :)
+    type(c_ptr)               :: buf_ptr
     integer :: i, n2
     n2 = (tree%n_cell + 2)**NDIM
-    allocate(buf(n2, size(ids)))
+    call pinned_buffer(slot, int(n2, c_size_t) * int(size(ids), c_size_t), buf_ptr)
+    call c_f_pointer(buf_ptr, buf, [n2, size(ids)])
     if (up) then
        !$omp parallel do
        do i = 1, size(ids)
@@ -396,14 +529,15 @@ contains
     logical, intent(in)       :: set_residual, have_guess
     integer, intent(in)       :: slot
     integer, allocatable      :: ids(:), leaves(:)
-    call sync_tree(tree, mg, slot)
-    call sync_lsf_boundary_values(tree, mg, slot)
+    call prepare_solve(tree, mg, slot)
     call all_ids(tree, leaves, .true.); call all_ids(tree, ids, .false.)
     call transfer(tree, slot, mg%i_rhs, afmg_rhs, leaves, .true.)      ! callers set rhs on leaves only
-    if (have_guess) call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .true.)
+    if (have_guess .and. .not. solvers(slot)%phi_current) call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .true.)
     call check(afmg_fas_fmg(solvers(slot)%h, merge(1, 0, set_residual), merge(1, 0, have_guess)), "afmg_fas_fmg")
     call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .false.)
-    if (set_residual) call transfer(tree, slot, mg%i_tmp, afmg_tmp, ids, .false.)
+    solvers(slot)%phi_current = .true.
+    if (set_residual .and. solvers(slot)%download_tmp) call transfer(tree, slot, mg%i_tmp, afmg_tmp, ids, .false.)
+    call finish_solve(tree)
   end subroutine mg_gpu_fas_fmg
 
   !> mg_fas_vcycle(tree, mg, set_residual, highest_lvl, standalone)  (m_af_multigrid.f90:185-264)
@@ -418,14 +552,15 @@ contains
     integer :: max_lvl, alone
     max_lvl = 0; if (present(highest_lvl)) max_lvl = highest_lvl
     alone = 1; if (present(standalone)) alone = merge(1, 0, standalone)
-    call sync_tree(tree, mg, slot)
-    call sync_lsf_boundary_values(tree, mg, slot)
+    call prepare_solve(tree, mg, slot)
     call all_ids(tree, leaves, .true.); call all_ids(tree, ids, .false.)
     call transfer(tree, slot, mg%i_rhs, afmg_rhs, leaves, .true.)
-    call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .true.)
+    if (.not. solvers(slot)%phi_current) call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .true.)
     call check(afmg_fas_vcycle(solvers(slot)%h, merge(1, 0, set_residual), max_lvl, alone), "afmg_fas_vcycle")
     call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .false.)
-    if (set_residual) call transfer(tree, slot, mg%i_tmp, afmg_tmp, ids, .false.)
+    solvers(slot)%phi_current = .true.
+    if (set_residual .and. solvers(slot)%download_tmp) call transfer(tree, slot, mg%i_tmp, afmg_tmp, ids, .false.)
+    call finish_solve(tree)
   end subroutine mg_gpu_fas_vcycle
 
   !> mg_compute_phi_gradient(tree, mg, i_fc, fac, i_norm) (m_af_multigrid.f90:1857-1898) on the device, from the
@@ -441,6 +576,9 @@ contains
     integer, allocatable          :: ids(:)
     real(c_double), allocatable   :: buf(:, :)
     integer :: i, n1
+    call mg_use(tree, mg)            ! box tags / distance stencils of new boxes (m_af_multigrid.f90:1865)
+    call sync_tree(tree, mg, slot)
+    call check(afmg_set_lsf_boundary_value(solvers(slot)%h, mg%lsf_boundary_value), "afmg_set_lsf_boundary_value")
     call all_ids(tree, ids, .false.)
     if (tree%mg_i_eps > 0) call transfer(tree, slot, tree%mg_i_eps, afmg_eps, ids, .true.)
     if (tree%mg_i_lsf > 0) call sync_lsf_distances(tree, mg, slot, ids)
@@ -453,6 +591,7 @@ contains
        tree%boxes(ids(i))%fc(DTIMES(:), :, i_fc) = reshape(buf(:, i), shape(tree%boxes(ids(i))%fc(DTIMES(:), :, i_fc)))
     end do
     if (present(i_norm)) call transfer(tree, slot, i_norm, afmg_fld, ids, .false.)
+    call finish_solve(tree)
   end subroutine mg_gpu_compute_phi_gradient
 
   !> mg_compute_field_norm (m_af_multigrid.f90:2002-2020) after the host changed box%fc (surface_correct_field_fc)
@@ -541,7 +680,7 @@ contains
     integer, allocatable      :: ids(:), leaves(:)
     integer :: n
     do n = 1, size(slots)
-       call sync_tree(tree, mg_helm(n), slots(n))
+       call prepare_solve(tree, mg_helm(n), slots(n))
        hs(n) = solvers(slots(n))%h
     end do
     call all_ids(tree, leaves, .true.); call all_ids(tree, ids, .false.)
@@ -549,6 +688,7 @@ contains
     call check(afmg_helmholtz_compute(hs, size(slots), coeffs, max_fmg_cycles, max_rel_residual, n_cycles, residuals), &
          "afmg_helmholtz_compute")
     call transfer(tree, slots(1), i_photo, afmg_photo, leaves, .false.)
+    call finish_solve(tree)
   end subroutine photoi_gpu_helmh_compute
 
   !> The solve loop of field_compute (src/m_field.f90:491-524) in one call: FMG cycles until the residual criterion
@@ -565,17 +705,18 @@ contains
     integer, intent(out)      :: n_fmg, n_vc
     integer, allocatable      :: ids(:), leaves(:)
     integer(c_int)            :: rc
-    call sync_tree(tree, mg, slot)
-    call sync_lsf_boundary_values(tree, mg, slot)
+    call prepare_solve(tree, mg, slot)
     call all_ids(tree, leaves, .true.); call all_ids(tree, ids, .false.)
     call transfer(tree, slot, mg%i_rhs, afmg_rhs, leaves, .true.)
-    if (have_guess) call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .true.)
+    if (have_guess .and. .not. solvers(slot)%phi_current) call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .true.)
     rc = afmg_field_solve(solvers(slot)%h, merge(1, 0, have_guess), residual_threshold, max_residual, max_fmg, &
          n_vcycles, residuals, n_fmg, n_vc)
     if (rc == -7) error stop "No convergence in initial field computation"  ! AFMG_ERR_NOT_CONVERGED
     call check(rc, "afmg_field_solve")
     call transfer(tree, slot, mg%i_phi, afmg_phi, ids, .false.)
-    call transfer(tree, slot, mg%i_tmp, afmg_tmp, ids, .false.)
+    solvers(slot)%phi_current = .true.
+    if (solvers(slot)%download_tmp) call transfer(tree, slot, mg%i_tmp, afmg_tmp, ids, .false.)
+    call finish_solve(tree)
   end subroutine mg_gpu_field_solve
 
   !> max |residual| over leaves without downloading i_tmp (af_tree_maxabs_cc, m_af_utils.f90:773)
@@ -593,7 +734,11 @@ contains
     integer, intent(in)       :: slot
     call check(afmg_set_helmholtz_lambda(solvers(slot)%h, mg%helmholtz_lambda), "afmg_set_helmholtz_lambda")
     call check(afmg_update_operator_stencil(solvers(slot)%h), "afmg_update_operator_stencil")
-    call sync_stencils(tree, mg, slot)
+    if (solvers(slot)%tree_hash /= topology_hash(tree)) then
+       call sync_tree(tree, mg, slot)      ! ships the stencils as well
+    else
+       call sync_stencils(tree, mg, slot)
+    end if
   end subroutine mg_gpu_update_operator_stencil
 
   !> mg_destroy (m_af_multigrid.f90:111-115)
@@ -601,7 +746,9 @@ contains
     type(mg_t), intent(inout) :: mg
     integer, intent(in)       :: slot
     call check(afmg_destroy(solvers(slot)%h), "afmg_destroy")
-    solvers(slot)%h = c_null_ptr; solvers(slot)%tree_signature = -1
+    solvers(slot)%h = c_null_ptr; solvers(slot)%tree_hash = -1; solvers(slot)%phi_current = .false.
+    if (c_associated(solvers(slot)%pinned)) call afmg_host_free(solvers(slot)%pinned)
+    solvers(slot)%pinned = c_null_ptr; solvers(slot)%pinned_len = 0
     mg%initialized = .false.
   end subroutine mg_gpu_destroy
 

@@ -154,3 +154,32 @@ def test_dropin_module_has_the_references_names_and_argument_lists():
     assert re.search(r"integer, intent\(in\), optional :: highest_lvl", src)
     assert re.search(r"logical, intent\(in\), optional :: standalone", src)
     assert re.search(r"subroutine mg_fas_vcycle.*?type\(mg_t\), intent\(in\)\s+:: mg", src, flags=re.S)
+
+
+def test_every_solve_refreshes_what_changes_in_time():
+    """Round-1 review findings, kept fixed: the shim includes cpp_macros.h (DTIMES / NDIM), runs the reference's mg_use
+    before every solve (tags + stencils of boxes created by af_adjust_refinement), re-evaluates mg%sides_bc and
+    mg%lsf_boundary_value before EVERY solve (both carry the time-dependent voltage, src/m_field.f90:481-487,
+    590-610), and detects tree changes with a hash of the complete topology instead of three counters."""
+    raw = open(os.path.join(ROOT, "fortran", "m_af_multigrid_gpu.f90")).read()
+    assert raw.lstrip().startswith('#include "cpp_macros.h"')
+    src = fortran_source().lower()
+    assert re.search(r"use m_af_stencil, only:[^\n]*af_stencil_index", src)
+    assert "use m_af_multigrid, only: mg_use" in src
+    prep = re.search(r"subroutine prepare_solve\(tree, mg, slot\)(.*?)end subroutine prepare_solve", src, flags=re.S).group(1)
+    order = [prep.index(k) for k in ("call mg_use(tree, mg)", "call sync_tree(tree, mg, slot)", "call sync_bc(tree, mg, slot)",
+                                     "afmg_set_lsf_boundary_value(", "call sync_lsf_boundary_values(")]
+    assert order == sorted(order)
+    for entry in ("mg_gpu_fas_fmg", "mg_gpu_fas_vcycle", "mg_gpu_field_solve", "photoi_gpu_helmh_compute"):
+        body = re.search(rf"subroutine {entry}\(.*?end subroutine {entry}", src, flags=re.S).group(0)
+        assert "call prepare_solve(" in body and "call finish_solve(tree)" in body, entry
+    assert "call mg_use(tree, mg)" in re.search(r"subroutine mg_gpu_compute_phi_gradient\(.*?end subroutine", src, flags=re.S).group(0)
+    # sync_tree no longer evaluates boundary conditions and is keyed on the topology hash
+    st = re.search(r"subroutine sync_tree\(tree, mg, slot\)(.*?)end subroutine sync_tree", src, flags=re.S).group(1)
+    assert "sides_bc" not in st and "topology_hash(tree)" in st and "tree_signature" not in src
+    th = re.search(r"function topology_hash\(tree\)(.*?)end function topology_hash", src, flags=re.S).group(1)
+    for member in ("%parent", "%children(1)", "%neighbors(n)", "%ix(n)", "lvls(lvl)%ids"):
+        assert member in th, member
+    # phi goes up only when the device copy is stale; packed buffers are page-locked
+    assert "have_guess .and. .not. solvers(slot)%phi_current" in src
+    assert "afmg_host_alloc(" in src and "c_f_pointer(buf_ptr, buf" in src
