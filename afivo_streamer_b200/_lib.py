@@ -30,7 +30,7 @@ class Opts(C.Structure):
         ("ndim", C.c_int32), ("n_cell", C.c_int32), ("coord_t", C.c_int32), ("n_cycle_down", C.c_int32),
         ("n_cycle_up", C.c_int32), ("use_corners", C.c_int32), ("subtract_mean", C.c_int32),
         ("prolongation_type", C.c_int32), ("operator_mask", C.c_int32), ("has_eps", C.c_int32),
-        ("device", C.c_int32), ("reserved", C.c_int32), ("helmholtz_lambda", C.c_double),
+        ("device", C.c_int32), ("n_gpus", C.c_int32), ("helmholtz_lambda", C.c_double),
         ("lsf_boundary_value", C.c_double), ("coarse_grid_size", C.c_int32 * 3), ("periodic", C.c_int32 * 3),
         ("dr_base", C.c_double * 3), ("r_base", C.c_double * 3),
     ]
@@ -98,6 +98,7 @@ SYMBOLS = {
     "afmg_host_free": (None, [C.c_void_p]),
     "afmg_upload_device": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
     "afmg_download_device": (C.c_int, [_H, _I, _I, _IP, C.c_void_p]),
+    "afmg_field_set_rhs": (C.c_int, [_H, _I, _IP, _I, _DP, C.POINTER(C.c_void_p), _I]),
     "afmg_clear": (C.c_int, [_H, _I]),
     "afmg_fas_fmg": (C.c_int, [_H, _I, _I]),
     "afmg_fas_vcycle": (C.c_int, [_H, _I, _I, _I]),

@@ -8,6 +8,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -57,8 +60,51 @@ struct S2State;  // 2D solver state (afmg2d.inc)
 struct FieldState;  // field from potential (afmg_field.inc)
 }
 
+namespace {
+// one host thread per GPU of a single-process multi-GPU handle: runs the calls posted for its rank handle
+struct RankWorker {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::function<int()> task;
+  bool has_task = false, done = false, quit = false;
+  int rc = 0;
+  void loop() {
+    std::unique_lock<std::mutex> lk(mu);
+    for (;;) {
+      cv.wait(lk, [&] { return has_task || quit; });
+      if (quit) return;
+      std::function<int()> t = std::move(task);
+      has_task = false;
+      lk.unlock();
+      const int r = t();
+      lk.lock();
+      rc = r;
+      done = true;
+      cv.notify_all();
+    }
+  }
+  void post(std::function<int()> t) {
+    std::lock_guard<std::mutex> lk(mu);
+    task = std::move(t);
+    has_task = true;
+    done = false;
+    cv.notify_all();
+  }
+  int wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return done; });
+    return rc;
+  }
+};
+}  // namespace
+
 struct afmg_handle {
   afmg_opts o{};
+  // ---- single-process multi-GPU front (afmg_opts.n_gpus > 1): no device state of its own, only the rank handles
+  bool is_multi = false;
+  std::vector<afmg_handle*> subs;
+  std::vector<RankWorker*> workers;
   S2State* s2 = nullptr;
   FieldState* fs = nullptr;
   std::string err;
@@ -122,6 +168,8 @@ struct afmg_handle {
   double* d_bv = nullptr;
   long long* d_bvoff = nullptr;
   double *d_Ainv = nullptr, *d_lsf_fac = nullptr;
+  bool cs_planes = false;  // block-tridiagonal variant of the general coarse solve (large coarse grids)
+  double *d_Sinv = nullptr, *d_cs_lo = nullptr, *d_cs_up = nullptr, *d_cs_w = nullptr, *d_cs_xs = nullptr, *d_cs_t = nullptr;
 
   // ---- multi-GPU (one process per GPU; peers' arrays mapped through CUDA IPC)
   int nranks = 1, me = 0;
@@ -139,6 +187,7 @@ struct afmg_handle {
   size_t slab_bytes = 0, slab_var_stride = 0;
   int slab_nvar = 3;
   char* peer_slab[AFMG_MAX_RANKS] = {};
+  bool local_peers = false;  // the peers are rank handles of the same process (afmg_opts.n_gpus): no CUDA IPC
   unsigned long long barrier_timeout_ns = 30ull * 1000000000ull;
 
   // ---- persistent-kernel segments (mega.cuh)
@@ -191,6 +240,28 @@ struct afmg_handle {
   } while (0)
 
 namespace {
+
+// run fn(rank handle) on every GPU of a single-process multi-GPU handle, each on its own host thread (the calls block
+// on device-side barriers that need all ranks in flight); first error wins
+template <class F>
+int multi_call(afmg_handle* h, F fn) {
+  const int n = (int)h->subs.size();
+  for (int r = 0; r < n; ++r) {
+    afmg_handle* sub = h->subs[r];
+    h->workers[r]->post([fn, sub]() -> int { return fn(sub); });
+  }
+  int rc = 0;
+  for (int r = 0; r < n; ++r) {
+    const int q = h->workers[r]->wait();
+    if (q && !rc) {
+      rc = q;
+      h->err = "GPU " + std::to_string(r) + ": " + h->subs[r]->err;
+    }
+  }
+  return rc;
+}
+#define AFMG_MULTI(h, call) \
+  if ((h) && (h)->is_multi) return multi_call((h), [=](afmg_handle* sub_) -> int { return call; })
 
 template <class T>
 int dev_upload(afmg_handle* h, T** dptr, const std::vector<T>& v) {
@@ -815,7 +886,28 @@ void enq_coarse(afmg_handle* h) {
     DISPATCH_NC(h, NC, { launch_k(h, k_cs_gather<NC>, blocks, 128, 0, h->cx, h->cs, nbox1); });
   }
   double *a = h->d_v0, *b = h->d_v1;
-  if (h->cs_dense) {
+  if (h->cs_planes) {
+    const int m = h->cs.m, np = h->cs.np, vb = (m + 127) / 128, mb = (m * 32 + 255) / 256;
+    for (int p = 0; p < np; ++p) {  // forward: w_p = S_p^-1 (b_p - lo_p w_{p-1})
+      Launch L_(h, "coarse");
+      launch_k(h, k_cs_plane_rhs, vb, 128, 0, h->cs, (const double*)a, p, 0);
+      launch_k(h, k_cs_plane_matvec, mb, 256, 0, h->cs, p, 0);
+    }
+    {
+      Launch L_(h, "coarse");
+      launch_k(h, k_cs_plane_rhs, vb, 128, 0, h->cs, (const double*)a, np - 1, 2);
+    }
+    for (int p = np - 2; p >= 0; --p) {  // backward: x_p = w_p - S_p^-1 (up_p x_{p+1})
+      Launch L_(h, "coarse");
+      launch_k(h, k_cs_plane_rhs, vb, 128, 0, h->cs, (const double*)a, p, 1);
+      launch_k(h, k_cs_plane_matvec, mb, 256, 0, h->cs, p, 1);
+    }
+    {
+      Launch L_(h, "coarse");
+      launch_k(h, k_cs_plane_out, blocks, 128, 0, h->cs, b);
+    }
+    std::swap(a, b);
+  } else if (h->cs_dense) {
     Launch L_(h, "coarse");
     launch_k(h, k_cs_dense, (ntot * 32 + 255) / 256, 256, 0, h->cs, a, b);
     std::swap(a, b);
@@ -1026,7 +1118,7 @@ int build_constant_stencils(afmg_handle* h) {
 // unmap the peers' slabs (CUDA IPC)
 void close_peers(afmg_handle* h) {
   for (int r = 0; r < AFMG_MAX_RANKS; ++r) {
-    if (r != h->me && h->peer_slab[r]) cudaIpcCloseMemHandle(h->peer_slab[r]);
+    if (r != h->me && h->peer_slab[r] && !h->local_peers) cudaIpcCloseMemHandle(h->peer_slab[r]);
     h->peer_slab[r] = nullptr;
   }
   h->connected = (h->nranks == 1);
@@ -1068,8 +1160,10 @@ int coarse_setup(afmg_handle* h) {
   const int nc = h->o.n_cell, nc2 = h->nc2;
   const int nbox1 = nlev(h, 1);
   h->cs_dense = false;
+  h->cs_planes = false;
   h->cs.lsf_fac = nullptr;
   h->cs.Ainv = nullptr;
+  h->cs.Sinv = nullptr;
   if (!h->l1_st.empty()) return coarse_setup_dense(h);
   int nb[3], nx[3];
   for (int d = 0; d < 3; ++d) {
@@ -1183,6 +1277,92 @@ int coarse_setup(afmg_handle* h) {
   return AFMG_OK;
 }
 
+// Block-tridiagonal set-up of the general coarse solve on the device (see k_cs_plane_assemble): np dense inversions
+// of m x m Schur-complement planes, in-place Gauss-Jordan without pivoting (2 small launches per pivot).
+int coarse_setup_planes(afmg_handle* h, const int* nx, const int* nbx, int sdim, const std::vector<double>& cellst,
+                        const std::vector<double>& b2r, const std::vector<double>& lsf_fac, bool any_f) {
+  const int n = nx[0] * nx[1] * nx[2], np = nx[sdim], m = n / np, nbox1 = nlev(h, 1);
+  const int gs[3] = {1, nx[0], nx[0] * nx[1]};
+  std::vector<double> lo(n, 0.0), up(n, 0.0);
+  for (int g = 0; g < n; ++g) {
+    const int q = (g / gs[sdim]) % nx[sdim];
+    if (q > 0) lo[g] = cellst[(size_t)7 * g + 1 + 2 * sdim];
+    if (q < np - 1) up[g] = cellst[(size_t)7 * g + 2 + 2 * sdim];
+  }
+  std::vector<int> bix((size_t)nbox1 * 3), per = {h->o.periodic[0], h->o.periodic[1], h->o.periodic[2]};
+  for (int sb = 0; sb < nbox1; ++sb)
+    for (int d = 0; d < 3; ++d) bix[(size_t)sb * 3 + d] = h->h_ix[(size_t)sb * 3 + d] - 1;
+  int rc;
+  double* d_cellst = nullptr;
+  int* d_per = nullptr;
+  if ((rc = dev_upload(h, &d_cellst, cellst))) return rc;
+  if ((rc = dev_upload(h, &d_per, per))) return rc;
+  if ((rc = dev_upload(h, &h->d_b2r, b2r))) return rc;
+  if ((rc = dev_upload(h, &h->d_lsf_fac, lsf_fac))) return rc;
+  if ((rc = dev_upload(h, &h->d_cs_bix, bix))) return rc;
+  if ((rc = dev_upload(h, &h->d_cs_lo, lo))) return rc;
+  if ((rc = dev_upload(h, &h->d_cs_up, up))) return rc;
+  std::vector<double> zeros(n, 0.0);
+  if ((rc = dev_upload(h, &h->d_v0, zeros))) return rc;
+  if ((rc = dev_upload(h, &h->d_v1, zeros))) return rc;
+  if ((rc = dev_upload(h, &h->d_cs_w, zeros))) return rc;
+  if ((rc = dev_upload(h, &h->d_cs_xs, zeros))) return rc;
+  zeros.resize(2 * (size_t)m);
+  if ((rc = dev_upload(h, &h->d_cs_t, zeros))) return rc;  // tvec [m] + pivot row / column scratch shares nothing
+  if (h->d_Sinv) cudaFree(h->d_Sinv);
+  h->d_Sinv = nullptr;
+  CK(cudaMalloc((void**)&h->d_Sinv, (size_t)np * m * m * sizeof(double)));
+  double *d_row = nullptr, *d_col = nullptr;
+  CK(cudaMalloc((void**)&d_row, (size_t)m * sizeof(double)));
+  CK(cudaMalloc((void**)&d_col, (size_t)m * sizeof(double)));
+  for (int d = 0; d < 3; ++d) {
+    h->cs.nx[d] = nx[d];
+    h->cs.nb[d] = nbx[d];
+    h->cs.Q[d] = nullptr;
+  }
+  h->cs.b2r = h->d_b2r;
+  h->cs.inv_eig = nullptr;
+  h->cs.v0 = h->d_v0;
+  h->cs.v1 = h->d_v1;
+  h->cs.bix = h->d_cs_bix;
+  h->cs.Ainv = nullptr;
+  h->cs.lsf_fac = any_f ? h->d_lsf_fac : nullptr;
+  h->cs.sdim = sdim;
+  h->cs.np = np;
+  h->cs.m = m;
+  h->cs.Sinv = h->d_Sinv;
+  h->cs.lo = h->d_cs_lo;
+  h->cs.up = h->d_cs_up;
+  h->cs.w = h->d_cs_w;
+  h->cs.xs = h->d_cs_xs;
+  h->cs.tvec = h->d_cs_t;
+  const size_t mm = (size_t)m * m;
+  const int eb = (int)((mm + 255) / 256);
+  for (int p = 0; p < np; ++p) {
+    double* S = h->d_Sinv + (size_t)p * mm;
+    k_cs_plane_assemble<<<eb, 256, 0, h->stream>>>(h->cs, d_cellst, d_per, p, S, p > 0 ? S - mm : nullptr);
+    for (int q = 0; q < m; ++q) {
+      k_gj_save<<<(m + 255) / 256, 256, 0, h->stream>>>(S, m, q, d_row, d_col);
+      k_gj_update<<<eb, 256, 0, h->stream>>>(S, m, q, d_row, d_col);
+    }
+  }
+  // singular operators (all-Neumann without a Helmholtz term) show up as a vanishing last pivot: non-finite entries
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  double probe = 0.0;
+  if (e == cudaSuccess) e = cudaMemcpy(&probe, h->d_Sinv + (size_t)(np - 1) * mm + mm - 1, sizeof probe, cudaMemcpyDeviceToHost);
+  cudaFree(d_cellst);
+  cudaFree(d_per);
+  cudaFree(d_row);
+  cudaFree(d_col);
+  if (e != cudaSuccess) return h->fail(AFMG_ERR_CUDA, "coarse plane set-up failed: %s", cudaGetErrorString(e));
+  if (!std::isfinite(probe) || std::fabs(probe) > 1e10 * std::fabs(1.0 / cellst[0]))
+    return h->fail(AFMG_ERR_SINGULAR, "coarse-grid operator is singular (all-Neumann without Helmholtz term)");
+  h->cs_dense = true;
+  h->cs_planes = true;
+  h->cs_ready = true;
+  return AFMG_OK;
+}
+
 // General coarse solve: level-1 boxes carry explicit stencils (variable eps / level set), so the operator is
 // not separable.  Same matrix as coarse_solver_initialize + stencil_handle_boundaries
 // (m_coarse_solver.f90:71-194, :442-491); its inverse is formed on the host (banded LU, one solve per unit
@@ -1197,15 +1377,27 @@ int coarse_setup_dense(afmg_handle* h) {
   }
   if (nbx[0] * nbx[1] * nbx[2] != nbox1) return h->fail(AFMG_ERR_ARG, "coarse grid size does not match the level-1 boxes");
   const int n = nx[0] * nx[1] * nx[2];
-  if (n > 8192)
-    return h->fail(AFMG_ERR_UNSUPPORTED, "explicit stencils on a coarse grid of %d cells (dense inverse limited to 8192)", n);
   // periodic dimensions couple the first and the last cell (HYPRE_StructGridSetPeriodic, m_coarse_solver.f90:
   // 97-104): the band becomes full, so the factorisation is a dense one and is kept to small grids
   const bool any_periodic = h->o.periodic[0] || h->o.periodic[1] || h->o.periodic[2];
-  if (any_periodic && n > 2048)
-    return h->fail(AFMG_ERR_UNSUPPORTED, "non-separable periodic coarse grid of %d cells (dense factorisation limited to 2048)", n);
-  const int bw = any_periodic ? n - 1 : nx[0] * nx[1], ldab = 2 * bw + 1;
-  std::vector<double> ab((size_t)ldab * n, 0.0);  // ab[(bw + r - c) + ldab * c] = A(r, c)
+  // Large grids (the reference's own 3D electrode example has a 32^3 coarse grid, afivo/examples/
+  // electrode_example.f90:41-45): block-tridiagonal direct solve over planes stacked along the longest non-periodic
+  // dimension, dense plane inverses on the device (k_cs_plane_*); memory n^2 / np doubles
+  const bool use_planes = n > 8192 || (any_periodic && n > 2048);
+  int sdim = -1;
+  for (int d = 0; d < 3; ++d)
+    if (!h->o.periodic[d] && (sdim < 0 || nx[d] >= nx[sdim])) sdim = d;
+  if (use_planes) {
+    if (sdim < 0)
+      return h->fail(AFMG_ERR_UNSUPPORTED, "non-separable coarse grid of %d cells, periodic in every dimension", n);
+    const double gb = (double)n * (double)(n / nx[sdim]) * 8.0 / 1e9;
+    if (gb > 24.0)
+      return h->fail(AFMG_ERR_UNSUPPORTED, "explicit stencils on a coarse grid of %d cells: the plane inverses need %.0f GB "
+                                           "(limit 24); use more, smaller level-1 boxes with a coarser level below", n, gb);
+  }
+  const int bw = use_planes ? 0 : (any_periodic ? n - 1 : nx[0] * nx[1]), ldab = 2 * bw + 1;
+  std::vector<double> ab(use_planes ? 1 : (size_t)ldab * n, 0.0);  // ab[(bw + r - c) + ldab * c] = A(r, c)
+  std::vector<double> cellst(use_planes ? (size_t)7 * n : 0, 0.0);  // BC-folded stencil of every cell, global order
   std::vector<double> b2r((size_t)nbox1 * 6 * nc2, 0.0), lsf_fac((size_t)nbox1 * ncell, 0.0);
   bool any_f = false;
   const int gstride[3] = {1, nx[0], nx[0] * nx[1]};
@@ -1265,6 +1457,15 @@ int coarse_setup_dense(afmg_handle* h) {
           const int gi[3] = {(bix[0] - 1) * nc + i - 1, (bix[1] - 1) * nc + j - 1, (bix[2] - 1) * nc + k - 1};
           const int r = gi[0] + nx[0] * (gi[1] + nx[1] * gi[2]);
           const double* st = &full[(size_t)7 * lin(i, j, k)];
+          if (use_planes) {
+            for (int m = 0; m < 7; ++m) cellst[(size_t)7 * r + m] = st[m];
+            for (int m = 0; m < 6; ++m) {
+              const int d = m >> 1, qd = gi[d] + ((m & 1) ? 1 : -1);
+              if (st[m + 1] != 0.0 && (qd < 0 || qd >= nx[d]) && !h->o.periodic[d])
+                return h->fail(AFMG_ERR_ARG, "coarse matrix: coupling outside the grid");
+            }
+            continue;
+          }
           ab[(size_t)bw + (size_t)ldab * r] += st[0];
           for (int m = 0; m < 6; ++m) {
             if (st[m + 1] == 0.0) continue;
@@ -1278,6 +1479,10 @@ int coarse_setup_dense(afmg_handle* h) {
             ab[(size_t)(bw + r - c) + (size_t)ldab * c] += st[m + 1];
           }
         }
+  }
+  if (use_planes) {
+    int rc = coarse_setup_planes(h, nx, nbx, sdim, cellst, b2r, lsf_fac, any_f);
+    return rc;
   }
   // banded LU without pivoting (diagonally dominant M-matrix up to sign)
   for (int c = 0; c < n; ++c) {
@@ -1537,6 +1742,51 @@ extern "C" {
 
 const char* afmg_last_error(const afmg_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+// afmg_opts.n_gpus > 1: a front handle over n rank handles (one per device, one host thread each)
+static int create_multi(afmg_handle** out, const afmg_opts* opts, int ng, int ndev) {
+  const int base = opts->device >= 0 ? opts->device : 0;
+  if (opts->ndim != 3) {
+    g_create_error = "n_gpus > 1 needs a 3D tree (the 2D path runs on one GPU)";
+    return AFMG_ERR_UNSUPPORTED;
+  }
+  if (ng > AFMG_MAX_RANKS || base + ng > ndev) {
+    g_create_error = "n_gpus = " + std::to_string(ng) + " from device " + std::to_string(base) + ": only " +
+                     std::to_string(ndev) + " devices visible (limit " + std::to_string(AFMG_MAX_RANKS) + ")";
+    return AFMG_ERR_ARG;
+  }
+  afmg_handle* h = new afmg_handle();
+  h->o = *opts;
+  h->is_multi = true;
+  h->nc2 = opts->n_cell * opts->n_cell;
+  h->box_len = (opts->n_cell + 2) * (opts->n_cell + 2) * (opts->n_cell + 2);
+  for (int r = 0; r < ng; ++r) {
+    afmg_opts o = *opts;
+    o.n_gpus = 1;
+    o.device = base + r;
+    afmg_handle* sub = nullptr;
+    int rc = afmg_create(&sub, &o);
+    if (!rc) rc = afmg_comm_init(sub, ng, r);
+    if (rc) {
+      if (sub) afmg_destroy(sub);
+      for (auto* q : h->subs) afmg_destroy(q);
+      delete h;
+      return rc;
+    }
+    sub->local_peers = true;
+    h->subs.push_back(sub);
+  }
+  for (int r = 0; r < ng; ++r) {
+    RankWorker* w = new RankWorker();
+    w->th = std::thread([w] { w->loop(); });
+    h->workers.push_back(w);
+  }
+  *out = h;
+  return AFMG_OK;
+}
+
+// peer access and peer pointers between the rank handles of one process (in place of afmg_comm_export / _connect)
+static int connect_local(afmg_handle* sub, afmg_handle* front);
+
 int afmg_create(afmg_handle** out, const afmg_opts* opts) {
   if (!out || !opts) {
     g_create_error = "null argument";
@@ -1568,6 +1818,12 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
   if (e != cudaSuccess || ndev == 0) {
     g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)";
     return AFMG_ERR_CUDA;
+  }
+  {
+    int ng = opts->n_gpus;
+    if (ng == 0)
+      if (const char* env = getenv("AFMG_N_GPUS")) ng = atoi(env);
+    if (ng > 1) return create_multi(out, opts, ng, ndev);
   }
   afmg_handle* h = new afmg_handle();
   h->o = *opts;
@@ -1621,6 +1877,20 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
 
 int afmg_destroy(afmg_handle* h) {
   if (!h) return AFMG_OK;
+  if (h->is_multi) {
+    multi_call(h, [](afmg_handle* sub) -> int { return afmg_destroy(sub); });
+    for (auto* w : h->workers) {
+      {
+        std::lock_guard<std::mutex> lk(w->mu);
+        w->quit = true;
+        w->cv.notify_all();
+      }
+      w->th.join();
+      delete w;
+    }
+    delete h;
+    return AFMG_OK;
+  }
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   drop_graphs(h);
@@ -1641,6 +1911,12 @@ int afmg_destroy(afmg_handle* h) {
   cudaFree(h->d_stv);
   cudaFree(h->d_spec);
   cudaFree(h->d_Ainv);
+  cudaFree(h->d_Sinv);
+  cudaFree(h->d_cs_lo);
+  cudaFree(h->d_cs_up);
+  cudaFree(h->d_cs_w);
+  cudaFree(h->d_cs_xs);
+  cudaFree(h->d_cs_t);
   cudaFree(h->d_lsf_fac);
   cudaFree(h->d_bv);
   cudaFree(h->d_bvoff);
@@ -1664,6 +1940,15 @@ int afmg_destroy(afmg_handle* h) {
 }
 
 int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
+  if (h && h->is_multi) {
+    if (!t) return AFMG_ERR_ARG;
+    int rc = multi_call(h, [=](afmg_handle* sub_) -> int { return afmg_set_tree(sub_, t); });
+    if (rc) return rc;
+    h->have_tree = true;
+    h->L = h->subs[0]->L;
+    h->nslots = h->subs[0]->nslots;
+    return multi_call(h, [=](afmg_handle* sub_) -> int { return connect_local(sub_, h); });  // all slabs exist now
+  }
   if (!h || !t) return AFMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
@@ -1905,6 +2190,7 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
 
 int afmg_set_bc(afmg_handle* h, int32_t n_faces, const int32_t* box_id, const int32_t* nb, const int32_t* bc_type,
                 const double* bc_val) {
+  AFMG_MULTI(h, afmg_set_bc(sub_, n_faces, box_id, nb, bc_type, bc_val));
   if (!h) return AFMG_ERR_ARG;
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
   CK(cudaSetDevice(h->device));
@@ -1961,6 +2247,7 @@ int afmg_set_bc(afmg_handle* h, int32_t n_faces, const int32_t* box_id, const in
 }
 
 int afmg_set_helmholtz_lambda(afmg_handle* h, double lambda) {
+  AFMG_MULTI(h, afmg_set_helmholtz_lambda(sub_, lambda));
   if (!h) return AFMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
@@ -1972,6 +2259,7 @@ int afmg_set_helmholtz_lambda(afmg_handle* h, double lambda) {
 }
 
 int afmg_set_lsf_boundary_value(afmg_handle* h, double value) {
+  AFMG_MULTI(h, afmg_set_lsf_boundary_value(sub_, value));
   if (!h) return AFMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
@@ -1985,6 +2273,7 @@ int afmg_set_lsf_boundary_value(afmg_handle* h, double value) {
 }
 
 int afmg_set_lsf_boundary_values(afmg_handle* h, int32_t n, const int32_t* box_id, const double* values) {
+  AFMG_MULTI(h, afmg_set_lsf_boundary_values(sub_, n, box_id, values));
   if (!h) return AFMG_ERR_ARG;
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
   if (n < 0 || (n > 0 && (!box_id || !values))) return h->fail(AFMG_ERR_ARG, "afmg_set_lsf_boundary_values: null argument");
@@ -2043,6 +2332,7 @@ int afmg_set_lsf_boundary_values(afmg_handle* h, int32_t n, const int32_t* box_i
 }
 
 int afmg_set_stencils(afmg_handle* h, int32_t n, const afmg_stencil_desc* desc, const double* blob, int64_t blob_len) {
+  AFMG_MULTI(h, afmg_set_stencils(sub_, n, desc, blob, blob_len));
   if (!h) return AFMG_ERR_ARG;
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
   if (n < 0 || (n > 0 && (!desc || !blob))) return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: null argument");
@@ -2158,6 +2448,7 @@ int afmg_set_stencils(afmg_handle* h, int32_t n, const afmg_stencil_desc* desc, 
 }
 
 int afmg_update_operator_stencil(afmg_handle* h) {
+  AFMG_MULTI(h, afmg_update_operator_stencil(sub_));
   if (!h) return AFMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
@@ -2245,15 +2536,19 @@ static int transfer(afmg_handle* h, int var, int n, const int32_t* box_id, doubl
 }
 
 int afmg_upload(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, const double* packed) {
+  AFMG_MULTI(h, afmg_upload(sub_, var, n, box_id, packed));
   return transfer(h, var, n, box_id, const_cast<double*>(packed), true, false);
 }
 int afmg_upload_interior(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, const double* packed) {
+  AFMG_MULTI(h, afmg_upload_interior(sub_, var, n, box_id, packed));
   return transfer(h, var, n, box_id, const_cast<double*>(packed), true, false, true);
 }
 int afmg_download(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, double* packed) {
+  AFMG_MULTI(h, afmg_download(sub_, var, n, box_id, packed));
   return transfer(h, var, n, box_id, packed, false, false);
 }
 int afmg_download_interior(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, double* packed) {
+  AFMG_MULTI(h, afmg_download_interior(sub_, var, n, box_id, packed));
   return transfer(h, var, n, box_id, packed, false, false, true);
 }
 // page-locked host memory for the caller's packed buffers: copies from / to it are true DMA transfers (a pageable
@@ -2270,13 +2565,79 @@ void afmg_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 int afmg_upload_device(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, const double* packed) {
+  AFMG_MULTI(h, afmg_upload_device(sub_, var, n, box_id, packed));
   return transfer(h, var, n, box_id, const_cast<double*>(packed), true, true);
 }
 int afmg_download_device(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id, double* packed) {
+  AFMG_MULTI(h, afmg_download_device(sub_, var, n, box_id, packed));
   return transfer(h, var, n, box_id, packed, false, true);
 }
 
+// field_set_rhs (src/m_field.f90:406-444) with the accumulation on the device: the species densities go up (or are
+// already resident: on_device) one after the other, chunk by chunk through the two-halves staging area, and each is
+// added with its charge factor in the reference's order, so the result has the reference's bits.
+int afmg_field_set_rhs(afmg_handle* h, int32_t n, const int32_t* box_id, int32_t n_species, const double* charges,
+                       const double* const* densities, int32_t on_device) {
+  AFMG_MULTI(h, afmg_field_set_rhs(sub_, n, box_id, n_species, charges, densities, on_device));
+  if (!h) return AFMG_ERR_ARG;
+  if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
+  if (n < 0 || n_species < 1 || !charges || !densities || (n > 0 && !box_id))
+    return h->fail(AFMG_ERR_ARG, "afmg_field_set_rhs: invalid arguments");
+  for (int sp = 0; sp < n_species; ++sp)
+    if (!densities[sp]) return h->fail(AFMG_ERR_ARG, "afmg_field_set_rhs: density %d is null", sp + 1);
+  if (n == 0) return AFMG_OK;
+  CK(cudaSetDevice(h->device));
+  std::vector<int> slots(n);
+  for (int q = 0; q < n; ++q) {
+    const int id = box_id[q];
+    if (id < 1 || id > h->highest_id || h->id2slot[id] < 0) return h->fail(AFMG_ERR_ARG, "unknown box id %d", id);
+    slots[q] = h->id2slot[id];
+    if (h->nranks > 1 && h->h_owner[slots[q]] != h->me) slots[q] = -1;
+  }
+  const size_t rec_len = (size_t)h->box_len, box_bytes = rec_len * sizeof(double);
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)128 << 20) / box_bytes));
+  int rc = ensure_stage(h, on_device ? 16 : (size_t)2 * chunk * box_bytes, (size_t)n);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->d_stage_slots, slots.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  double* rhs = h->o.ndim == 2 ? h->s2->cx.cc[AFMG_RHS] : h->d_cc[AFMG_RHS];
+  int c = 0;
+  bool used[2] = {false, false};
+  for (int q0 = 0; q0 < n; q0 += chunk) {
+    const int m = std::min(chunk, n - q0);
+    for (int sp = 0; sp < n_species; ++sp, ++c) {
+      const int hb = c & 1;
+      const double* src = densities[sp] + (size_t)q0 * rec_len;
+      const double* dp = src;
+      if (!on_device) {
+        double* stage = h->d_stage + (size_t)hb * chunk * rec_len;
+        if (used[hb]) CK(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[hb], 0));
+        CK(cudaMemcpyAsync(stage, src, (size_t)m * box_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        CK(cudaEventRecord(h->ev_copied[hb], h->copy_stream));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_copied[hb], 0));
+        dp = stage;
+      }
+      {
+        Launch L_(h, "set_rhs");
+        if (h->o.ndim == 2) {
+          launch_k(h, afmg2::k2_axpy_boxes, m, 64, 0, rhs, h->d_stage_slots + q0, m, dp, (int)rec_len, charges[sp], sp == 0 ? 1 : 0);
+        } else {
+          DISPATCH_NC(h, NC, {
+            launch_k(h, k_unpack_axpy<NC>, m, 256, 0, rhs, h->d_stage_slots + q0, m, dp, charges[sp], sp == 0 ? 1 : 0);
+          });
+        }
+      }
+      if (!on_device) CK(cudaEventRecord(h->ev_consumed[hb], h->stream));
+      used[hb] = true;
+    }
+  }
+  h->resid_fresh = false;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->copy_stream));
+  return finish_op(h);
+}
+
 int afmg_clear(afmg_handle* h, int32_t var) {
+  AFMG_MULTI(h, afmg_clear(sub_, var));
   if (!h) return AFMG_ERR_ARG;
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
   if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
@@ -2288,6 +2649,7 @@ int afmg_clear(afmg_handle* h, int32_t var) {
 }
 
 int afmg_fas_vcycle_async(afmg_handle* h, int32_t set_residual, int32_t highest_lvl, int32_t n_cycles) {
+  AFMG_MULTI(h, afmg_fas_vcycle_async(sub_, set_residual, highest_lvl, n_cycles));
   if (!h) return AFMG_ERR_ARG;
   int rc = ensure_ready(h);
   if (rc) return rc;
@@ -2307,6 +2669,7 @@ int afmg_fas_vcycle_async(afmg_handle* h, int32_t set_residual, int32_t highest_
 }
 
 int afmg_fas_fmg_async(afmg_handle* h, int32_t set_residual, int32_t have_guess, int32_t n_cycles) {
+  AFMG_MULTI(h, afmg_fas_fmg_async(sub_, set_residual, have_guess, n_cycles));
   if (!h) return AFMG_ERR_ARG;
   int rc = ensure_ready(h);
   if (rc) return rc;
@@ -2325,12 +2688,14 @@ int afmg_fas_fmg_async(afmg_handle* h, int32_t set_residual, int32_t have_guess,
 }
 
 int afmg_sync(afmg_handle* h) {
+  AFMG_MULTI(h, afmg_sync(sub_));
   if (!h) return AFMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   return finish_op(h);
 }
 
 int afmg_fas_vcycle(afmg_handle* h, int32_t set_residual, int32_t highest_lvl, int32_t standalone) {
+  AFMG_MULTI(h, afmg_fas_vcycle(sub_, set_residual, highest_lvl, standalone));
   (void)standalone;  // mg_use / done_with_mg bookkeeping lives in the Fortran shim
   int rc = afmg_fas_vcycle_async(h, set_residual, highest_lvl, 1);
   if (rc) return rc;
@@ -2338,6 +2703,7 @@ int afmg_fas_vcycle(afmg_handle* h, int32_t set_residual, int32_t highest_lvl, i
 }
 
 int afmg_fas_fmg(afmg_handle* h, int32_t set_residual, int32_t have_guess) {
+  AFMG_MULTI(h, afmg_fas_fmg(sub_, set_residual, have_guess));
   int rc = afmg_fas_fmg_async(h, set_residual, have_guess, 1);
   if (rc) return rc;
   return afmg_sync(h);
@@ -2345,6 +2711,20 @@ int afmg_fas_fmg(afmg_handle* h, int32_t set_residual, int32_t have_guess) {
 
 int afmg_field_solve(afmg_handle* h, int32_t have_guess, double residual_threshold, double max_residual, int32_t max_fmg,
                      int32_t n_vcycles, double* residuals, int32_t* n_fmg, int32_t* n_vc) {
+  if (h && h->is_multi) {
+    if (!residuals || !n_fmg || !n_vc) return AFMG_ERR_ARG;
+    const int ng = (int)h->subs.size(), cap = std::max(1, max_fmg + n_vcycles);
+    std::vector<double> res((size_t)ng * cap, 0.0);
+    std::vector<int32_t> nf(ng, 0), nv(ng, 0);
+    const int rc = multi_call(h, [&, have_guess, residual_threshold, max_residual, max_fmg, n_vcycles](afmg_handle* sub_) -> int {
+      const int r = sub_->me;
+      return afmg_field_solve(sub_, have_guess, residual_threshold, max_residual, max_fmg, n_vcycles, &res[(size_t)r * cap], &nf[r], &nv[r]);
+    });
+    std::copy(res.begin(), res.begin() + cap, residuals);  // identical on every rank
+    *n_fmg = nf[0];
+    *n_vc = nv[0];
+    return rc;
+  }
   if (!h || !residuals || !n_fmg || !n_vc) return AFMG_ERR_ARG;
   *n_fmg = 0;
   *n_vc = 0;
@@ -2393,6 +2773,7 @@ int afmg_field_solve(afmg_handle* h, int32_t have_guess, double residual_thresho
   h->resid_fresh = false;
 
 int afmg_gsrb_boxes(afmg_handle* h, int32_t lvl, int32_t type_cycle) {
+  AFMG_MULTI(h, afmg_gsrb_boxes(sub_, lvl, type_cycle));
   SINGLE_OP_PROLOGUE();
   int rc = check_lvl(h, lvl);
   if (rc) return rc;
@@ -2411,6 +2792,7 @@ int afmg_gsrb_boxes(afmg_handle* h, int32_t lvl, int32_t type_cycle) {
 }
 
 int afmg_gsrb_halfsweep(afmg_handle* h, int32_t lvl, int32_t redblack) {
+  AFMG_MULTI(h, afmg_gsrb_halfsweep(sub_, lvl, redblack));
   SINGLE_OP_PROLOGUE();
   int rc = check_lvl(h, lvl);
   if (rc) return rc;
@@ -2429,6 +2811,7 @@ int afmg_gsrb_halfsweep(afmg_handle* h, int32_t lvl, int32_t redblack) {
 }
 
 int afmg_gc_lvl(afmg_handle* h, int32_t lvl, int32_t var, int32_t corners) {
+  AFMG_MULTI(h, afmg_gc_lvl(sub_, lvl, var, corners));
   SINGLE_OP_PROLOGUE();
   int rc = check_lvl(h, lvl);
   if (rc) return rc;
@@ -2447,6 +2830,7 @@ int afmg_gc_lvl(afmg_handle* h, int32_t lvl, int32_t var, int32_t corners) {
 }
 
 int afmg_update_coarse(afmg_handle* h, int32_t lvl, int32_t with_tmp) {
+  AFMG_MULTI(h, afmg_update_coarse(sub_, lvl, with_tmp));
   SINGLE_OP_PROLOGUE();
   int rc = check_lvl(h, lvl);
   if (rc) return rc;
@@ -2457,6 +2841,7 @@ int afmg_update_coarse(afmg_handle* h, int32_t lvl, int32_t with_tmp) {
 }
 
 int afmg_correct_children(afmg_handle* h, int32_t lvl_parents) {
+  AFMG_MULTI(h, afmg_correct_children(sub_, lvl_parents));
   SINGLE_OP_PROLOGUE();
   int rc = check_lvl(h, lvl_parents);
   if (rc) return rc;
@@ -2466,6 +2851,7 @@ int afmg_correct_children(afmg_handle* h, int32_t lvl_parents) {
 }
 
 int afmg_correct_children_gc(afmg_handle* h, int32_t lvl_parents) {
+  AFMG_MULTI(h, afmg_correct_children_gc(sub_, lvl_parents));
   SINGLE_OP_PROLOGUE();
   int rc = check_lvl(h, lvl_parents);
   if (rc) return rc;
@@ -2476,6 +2862,7 @@ int afmg_correct_children_gc(afmg_handle* h, int32_t lvl_parents) {
 }
 
 int afmg_residual_lvl(afmg_handle* h, int32_t lvl) {
+  AFMG_MULTI(h, afmg_residual_lvl(sub_, lvl));
   SINGLE_OP_PROLOGUE();
   int rc = check_lvl(h, lvl);
   if (rc) return rc;
@@ -2485,6 +2872,7 @@ int afmg_residual_lvl(afmg_handle* h, int32_t lvl) {
 }
 
 int afmg_solve_coarse_grid(afmg_handle* h) {
+  AFMG_MULTI(h, afmg_solve_coarse_grid(sub_));
   SINGLE_OP_PROLOGUE();
   if (h->o.ndim == 2) s2_coarse(h);
   else if (int rc_ = run_direct(h, [&] { enq_coarse(h); })) return rc_;
@@ -2492,6 +2880,7 @@ int afmg_solve_coarse_grid(afmg_handle* h) {
 }
 
 int afmg_init_phi_rhs(afmg_handle* h) {
+  AFMG_MULTI(h, afmg_init_phi_rhs(sub_));
   SINGLE_OP_PROLOGUE();
   if (h->o.ndim == 2) s2_init_phi_rhs(h);
   else if (int rc_ = run_direct(h, [&] { enq_init_phi_rhs(h); })) return rc_;
@@ -2499,6 +2888,13 @@ int afmg_init_phi_rhs(afmg_handle* h) {
 }
 
 int afmg_max_abs(afmg_handle* h, int32_t var, double* out) {
+  if (h && h->is_multi) {
+    if (!out) return AFMG_ERR_ARG;
+    std::vector<double> v(h->subs.size(), 0.0);
+    const int rc = multi_call(h, [&v, var](afmg_handle* sub_) -> int { return afmg_max_abs(sub_, var, &v[sub_->me]); });
+    *out = v[0];  // the combined value, identical on every rank
+    return rc;
+  }
   if (!h || !out) return AFMG_ERR_ARG;
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
   if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
@@ -2532,6 +2928,13 @@ int afmg_max_abs(afmg_handle* h, int32_t var, double* out) {
 }
 
 int afmg_tree_sum(afmg_handle* h, int32_t var, double* out) {
+  if (h && h->is_multi) {
+    if (!out) return AFMG_ERR_ARG;
+    std::vector<double> v(h->subs.size(), 0.0);
+    const int rc = multi_call(h, [&v, var](afmg_handle* sub_) -> int { return afmg_tree_sum(sub_, var, &v[sub_->me]); });
+    *out = v[0];
+    return rc;
+  }
   if (!h || !out) return AFMG_ERR_ARG;
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
   if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
@@ -2558,6 +2961,18 @@ int afmg_tree_sum(afmg_handle* h, int32_t var, double* out) {
 }
 
 int afmg_checksum(afmg_handle* h, int32_t var, uint64_t* sum_out, uint64_t* xor_out) {
+  if (h && h->is_multi) {
+    if (!sum_out || !xor_out) return AFMG_ERR_ARG;
+    std::vector<uint64_t> a(h->subs.size(), 0), b(h->subs.size(), 0);
+    const int rc = multi_call(h, [&a, &b, var](afmg_handle* sub_) -> int { return afmg_checksum(sub_, var, &a[sub_->me], &b[sub_->me]); });
+    *sum_out = 0;
+    *xor_out = 0;
+    for (size_t r = 0; r < a.size(); ++r) {  // every rank covers the boxes it owns
+      *sum_out += a[r];
+      *xor_out ^= b[r];
+    }
+    return rc;
+  }
   if (!h || !sum_out || !xor_out) return AFMG_ERR_ARG;
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
   if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
@@ -2585,6 +3000,7 @@ int afmg_checksum(afmg_handle* h, int32_t var, uint64_t* sum_out, uint64_t* xor_
 }
 
 int afmg_set_mega(afmg_handle* h, int32_t enabled, int32_t max_boxes) {
+  AFMG_MULTI(h, afmg_set_mega(sub_, enabled, max_boxes));
   if (!h) return AFMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
@@ -2596,9 +3012,21 @@ int afmg_set_mega(afmg_handle* h, int32_t enabled, int32_t max_boxes) {
 
 int32_t afmg_mega_active(const afmg_handle* h) { return (h && mega_possible(h)) ? h->mega_grid : 0; }
 
-int64_t afmg_kernel_launches(const afmg_handle* h) { return h ? h->launches : 0; }
+int64_t afmg_kernel_launches(const afmg_handle* h) {
+  if (!h) return 0;
+  int64_t n = h->launches;
+  for (const afmg_handle* sub : h->subs) n += sub->launches;
+  return n;
+}
 
 int afmg_last_cycle_ms(afmg_handle* h, double* ms) {
+  if (h && h->is_multi) {
+    if (!ms) return AFMG_ERR_ARG;
+    std::vector<double> v(h->subs.size(), 0.0);
+    const int rc = multi_call(h, [&v](afmg_handle* sub_) -> int { return afmg_last_cycle_ms(sub_, &v[sub_->me]); });
+    *ms = *std::max_element(v.begin(), v.end());  // device time of the slowest GPU
+    return rc;
+  }
   if (!h || !ms) return AFMG_ERR_ARG;
   if (!h->ev_valid) return h->fail(AFMG_ERR_STATE, "no cycle has been run");
   CK(cudaEventSynchronize(h->ev1));
@@ -2609,6 +3037,7 @@ int afmg_last_cycle_ms(afmg_handle* h, double* ms) {
 }
 
 int afmg_set_profiling(afmg_handle* h, int32_t on) {
+  AFMG_MULTI(h, afmg_set_profiling(sub_, on));
   if (!h) return AFMG_ERR_ARG;
   CK(cudaStreamSynchronize(h->stream));
   prof_resolve(h);
@@ -2619,6 +3048,7 @@ int afmg_set_profiling(afmg_handle* h, int32_t on) {
 }
 
 int afmg_profile(afmg_handle* h, int32_t cap, char (*names)[32], double* ms, int64_t* calls, int32_t* n) {
+  if (h && h->is_multi) return afmg_profile(h->subs[0], cap, names, ms, calls, n);  // rank 0's kernels
   if (!h || !n) return AFMG_ERR_ARG;
   prof_resolve(h);
   mega_resolve_stamps(h);
@@ -2635,6 +3065,7 @@ int afmg_profile(afmg_handle* h, int32_t cap, char (*names)[32], double* ms, int
 }
 
 int afmg_cell_updates(afmg_handle* h, int32_t highest_lvl, int32_t fmg, double* out) {
+  if (h && h->is_multi) return afmg_cell_updates(h->subs[0], highest_lvl, fmg, out);  // whole tree, host arithmetic
   if (!h || !out) return AFMG_ERR_ARG;
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
   const int maxl = highest_lvl > 0 ? highest_lvl : h->L;
@@ -2684,6 +3115,7 @@ int64_t afmg_morton_key(int32_t ndim, int32_t ix, int32_t iy, int32_t iz) {
 }
 
 int32_t afmg_slot_of_box(const afmg_handle* h, int32_t box_id) {
+  if (h && h->is_multi) return afmg_slot_of_box(h->subs[0], box_id);
   if (!h || !h->have_tree || box_id < 1 || box_id > h->highest_id) return -1;
   return h->id2slot[box_id];
 }
@@ -2717,6 +3149,7 @@ int afmg_partition_min(int32_t n_ranks, int32_t highest_lvl, const int32_t* lvl_
 }
 
 int afmg_comm_init(afmg_handle* h, int32_t n_ranks, int32_t rank) {
+  if (h && h->is_multi) return h->fail(AFMG_ERR_STATE, "afmg_comm_init: this handle drives its GPUs itself (afmg_opts.n_gpus)");
   if (!h) return AFMG_ERR_ARG;
   if (n_ranks < 1 || n_ranks > AFMG_MAX_RANKS || rank < 0 || rank >= n_ranks)
     return h->fail(AFMG_ERR_ARG, "afmg_comm_init: need 1 <= n_ranks <= %d and 0 <= rank < n_ranks", AFMG_MAX_RANKS);
@@ -2739,6 +3172,7 @@ static_assert(sizeof(CommBlob) <= AFMG_COMM_BLOB_BYTES, "blob size");
 }  // namespace
 
 int afmg_comm_export(afmg_handle* h, void* blob) {
+  if (h && h->is_multi) return h->fail(AFMG_ERR_STATE, "afmg_comm_export: this handle drives its GPUs itself (afmg_opts.n_gpus)");
   if (!h || !blob) return AFMG_ERR_ARG;
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_comm_export: call afmg_set_tree first");
   CK(cudaSetDevice(h->device));
@@ -2755,6 +3189,7 @@ int afmg_comm_export(afmg_handle* h, void* blob) {
 }
 
 int afmg_comm_connect(afmg_handle* h, const void* blobs) {
+  if (h && h->is_multi) return h->fail(AFMG_ERR_STATE, "afmg_comm_connect: this handle drives its GPUs itself (afmg_opts.n_gpus)");
   if (!h || !blobs) return AFMG_ERR_ARG;
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_comm_connect: call afmg_set_tree first");
   CK(cudaSetDevice(h->device));
@@ -2787,7 +3222,37 @@ int afmg_comm_connect(afmg_handle* h, const void* blobs) {
   return AFMG_OK;
 }
 
+static int connect_local(afmg_handle* sub, afmg_handle* front) {
+  afmg_handle* h = sub;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  drop_graphs(h);
+  for (int r = 0; r < h->nranks; ++r) {
+    afmg_handle* q = front->subs[r];
+    if (q->nslots != h->nslots || q->slab_bytes != h->slab_bytes)
+      return h->fail(AFMG_ERR_ARG, "internal: rank handles hold different trees");
+    if (r == h->me) continue;
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, h->device, q->device));
+    if (!can) return h->fail(AFMG_ERR_UNSUPPORTED, "GPU %d cannot access the memory of GPU %d (no NVLink / P2P path)", h->device, q->device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(q->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+      return h->fail(AFMG_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", q->device, cudaGetErrorString(e));
+    cudaGetLastError();
+    h->peer_slab[r] = q->d_slab;
+    h->peers.p[r] = q->d_comm;
+  }
+  for (int r = 0; r < h->nranks; ++r) {
+    for (int v = 0; v < 3; ++v) h->cx.ccr[r][v] = (double*)(h->peer_slab[r] + v * h->slab_var_stride);
+    h->cx.ccr[r][V_FLD] = (h->slab_nvar == 4) ? (double*)(h->peer_slab[r] + 3 * h->slab_var_stride) : nullptr;
+    h->cx.bsum[r] = (double*)(h->peer_slab[r] + h->slab_nvar * h->slab_var_stride);
+  }
+  h->connected = true;
+  return AFMG_OK;
+}
+
 int32_t afmg_owner_of_box(const afmg_handle* h, int32_t box_id) {
+  if (h && h->is_multi) return afmg_owner_of_box(h->subs[0], box_id);
   if (!h || !h->have_tree || box_id < 1 || box_id > h->highest_id || h->id2slot[box_id] < 0) return -1;
   return h->h_owner[h->id2slot[box_id]];
 }

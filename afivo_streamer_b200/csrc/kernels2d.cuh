@@ -474,6 +474,17 @@ __global__ void k2_copy_boxes(double* var_base, const int* slots, int n, double*
   }
 }
 
+// field_set_rhs (src/m_field.f90:406-444), one species: rhs = (first ? 0 : rhs) + q * density on whole records
+__global__ void k2_axpy_boxes(double* var_base, const int* slots, int n, const double* packed, int box_len, double q,
+                              int first) {
+  pdl_wait();
+  const int b = blockIdx.x;
+  if (b >= n || slots[b] < 0) return;
+  double* a = var_base + (size_t)slots[b] * box_len;
+  const double* s = packed + (size_t)b * box_len;
+  for (int t = threadIdx.x; t < box_len; t += blockDim.x) a[t] = (first ? 0.0 : a[t]) + q * s[t];
+}
+
 // interior cells only: packed holds cc(1:nc, 1:nc) per box
 __global__ void k2_unpack_interior(double* var_base, const int* slots, int n, double* packed, int nc, int up) {
   pdl_wait();

@@ -1330,6 +1330,23 @@ __global__ void k_unpack(double* var_base, const int* slots, int n, const double
     box[q] = src[(k * N2 + j) * N2 + i];
   }
 }
+// field_set_rhs (src/m_field.f90:406-444): rhs = 0; rhs = rhs + q_n * density_n, one call per species with the
+// packed density of the listed boxes (reference order); first != 0 starts from the reference's 0.0
+template <int NC>
+__global__ void k_unpack_axpy(double* var_base, const int* slots, int n, const double* packed, double q, int first) {
+  pdl_wait();
+  using L = Lay3<NC>;
+  constexpr int N2 = NC + 2;
+  if ((int)blockIdx.x >= n || slots[blockIdx.x] < 0) return;
+  double* box = var_base + (size_t)slots[blockIdx.x] * L::BOX;
+  const double* src = packed + (size_t)blockIdx.x * L::BOX;
+  for (int p = threadIdx.x; p < L::BOX; p += blockDim.x) {
+    int i, j, k;
+    L::uncell(p, i, j, k);
+    const double prev = first ? 0.0 : box[p];
+    box[p] = prev + q * src[(k * N2 + j) * N2 + i];
+  }
+}
 // interior cells only: packed holds cc(1:nc, 1:nc, 1:nc) per box (ghost cells of the record are kept)
 template <int NC>
 __global__ void k_unpack_interior(double* var_base, const int* slots, int n, const double* packed) {
@@ -1391,7 +1408,32 @@ struct CoarseCtx {
   double* v1;
   const double* lsf_fac;  // [nbox1][nc^3] stencil%f of level-1 boxes (rhs += f * lsf_boundary_value), or null
   const double* Ainv;     // [n][n] dense inverse (general path: explicit stencils on level 1), or null
+  // block-tridiagonal path for large non-separable coarse grids (k_cs_plane_*): planes stacked along `sdim`
+  int sdim, np, m;        // stacking dimension, number of planes, cells per plane
+  const double* Sinv;     // [np][m][m] inverses of the Schur-complement planes
+  const double* lo;       // [n] coupling of every cell to the plane below (0 on the first plane), global cell order
+  const double* up;       // [n] coupling to the plane above
+  double* w;              // [n] work vectors in (plane, in-plane) order
+  double* xs;
+  double* tvec;           // [m]
 };
+
+// (plane, in-plane index) of global coarse cell g and back: the in-plane index runs over the two other dimensions
+// in increasing dimension order
+__device__ __forceinline__ void cs_plane_of(const CoarseCtx& cs, int g, int& p, int& i) {
+  const int q[3] = {g % cs.nx[0], (g / cs.nx[0]) % cs.nx[1], g / (cs.nx[0] * cs.nx[1])};
+  const int a = cs.sdim == 0 ? 1 : 0, b = cs.sdim == 2 ? 1 : 2;
+  p = q[cs.sdim];
+  i = q[a] + cs.nx[a] * q[b];
+}
+__device__ __forceinline__ int cs_global_of(const CoarseCtx& cs, int p, int i) {
+  const int a = cs.sdim == 0 ? 1 : 0, b = cs.sdim == 2 ? 1 : 2;
+  int q[3];
+  q[cs.sdim] = p;
+  q[a] = i % cs.nx[a];
+  q[b] = i / cs.nx[a];
+  return q[0] + cs.nx[0] * (q[1] + cs.nx[1] * q[2]);
+}
 
 // coarse_solver_set_rhs_phi (m_coarse_solver.f90:286-338): b = rhs + bc_to_rhs * bc_val per face
 template <int NC>
@@ -1468,6 +1510,89 @@ __global__ void k_cs_dense(CoarseCtx cs, const double* in, double* out) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) out[row] = s;
+}
+
+// ---- block-tridiagonal direct solve for coarse grids too large for a dense inverse ------------------------------
+// A = blocktridiag(L_p, D_p, U_p) over planes p of m cells (L, U diagonal: the couplings across the planes).  Set-up
+// (once per operator): S_0 = D_0, S_p = D_p - L_p S_{p-1}^{-1} U_{p-1}, all S_p^{-1} stored dense.  Solve:
+//   forward   w_p = S_p^{-1} (b_p - lo_p * w_{p-1})           backward  x_p = w_p - S_p^{-1} (up_p * x_{p+1})
+// i.e. 2 np - 1 dense mat-vecs of m x m.  Exact (a block LU without pivoting of a diagonally dominant M-matrix),
+// like the banded LU of the oracle and the tolerance -> 0 limit of the reference's PFMG.
+//
+// S_p[i][j] from the BC-folded 7-point stencils (cellst: [n][7], global cell order) and the previous inverse
+__global__ void k_cs_plane_assemble(CoarseCtx cs, const double* cellst, const int* periodic, int p, double* S,
+                                    const double* Sinv_prev) {
+  const int m = cs.m;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)m * m) return;
+  const int i = (int)(e / m), j = (int)(e % m);
+  const int gi = cs_global_of(cs, p, i), gj = cs_global_of(cs, p, j);
+  const double* st = cellst + (size_t)7 * gi;
+  double v = 0.0;
+  if (i == j) v = st[0];
+  const int q[3] = {gi % cs.nx[0], (gi / cs.nx[0]) % cs.nx[1], gi / (cs.nx[0] * cs.nx[1])};
+  const int gs[3] = {1, cs.nx[0], cs.nx[0] * cs.nx[1]};
+  for (int f = 0; f < 6; ++f) {
+    const int d = f >> 1, sgn = (f & 1) ? 1 : -1;
+    if (d == cs.sdim || st[f + 1] == 0.0) continue;
+    int qd = q[d] + sgn, g2 = gi + sgn * gs[d];
+    if (qd < 0 || qd >= cs.nx[d]) {
+      if (!periodic[d]) continue;
+      g2 = gi - sgn * (cs.nx[d] - 1) * gs[d];
+    }
+    if (g2 == gj) v = v + st[f + 1];
+  }
+  if (Sinv_prev) v = v - cs.lo[gi] * Sinv_prev[e] * cs.up[cs_global_of(cs, p - 1, j)];
+  S[e] = v;
+}
+// in-place Gauss-Jordan inversion without pivoting, pivot step p: first the pivot row and column are saved ...
+__global__ void k_gj_save(const double* S, int m, int p, double* rowp, double* colp) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  rowp[t] = S[(size_t)p * m + t];
+  colp[t] = S[(size_t)t * m + p];
+}
+// ... then every element is updated from them
+__global__ void k_gj_update(double* S, int m, int p, const double* rowp, const double* colp) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)m * m) return;
+  const int r = (int)(e / m), c = (int)(e % m);
+  const double inv = 1.0 / rowp[p];
+  if (r == p) S[e] = (c == p) ? inv : rowp[c] * inv;
+  else if (c == p) S[e] = -(colp[r] * inv);
+  else S[e] = S[e] - (colp[r] * inv) * rowp[c];
+}
+// forward / backward substitution step on plane p; one warp per row of S_p^{-1}
+// mode 0: w_p = Sinv_p (b_p - lo_p * w_{p-1})       (b in global order, w / x in plane order)
+// mode 1: x_p = w_p - Sinv_p (up_p * x_{p+1})       (x_{np-1} = w_{np-1} is a plain copy: mode 2)
+__global__ void k_cs_plane_rhs(CoarseCtx cs, const double* b, int p, int mode) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cs.m) return;
+  const int g = cs_global_of(cs, p, i);
+  if (mode == 0) cs.tvec[i] = (p == 0) ? b[g] : b[g] - cs.lo[g] * cs.w[(size_t)(p - 1) * cs.m + i];
+  else if (mode == 1) cs.tvec[i] = cs.up[g] * cs.xs[(size_t)(p + 1) * cs.m + i];
+  else cs.xs[(size_t)p * cs.m + i] = cs.w[(size_t)p * cs.m + i];
+}
+__global__ void k_cs_plane_matvec(CoarseCtx cs, int p, int mode) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= cs.m) return;
+  const double* a = cs.Sinv + ((size_t)p * cs.m + row) * cs.m;
+  double s = 0.0;
+  for (int c = lane; c < cs.m; c += 32) s = s + a[c] * cs.tvec[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    if (mode == 0) cs.w[(size_t)p * cs.m + row] = s;
+    else cs.xs[(size_t)p * cs.m + row] = cs.w[(size_t)p * cs.m + row] - s;
+  }
+}
+// x (plane order) -> out (global order), the layout k_cs_scatter reads
+__global__ void k_cs_plane_out(CoarseCtx cs, double* out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= cs.nx[0] * cs.nx[1] * cs.nx[2]) return;
+  int p, i;
+  cs_plane_of(cs, g, p, i);
+  out[g] = cs.xs[(size_t)p * cs.m + i];
 }
 
 // coarse_solver_get_phi (m_coarse_solver.f90:341-358)

@@ -55,6 +55,8 @@ class mg_t:
     # multi-GPU: (rank, world_size, allgather) with allgather(bytes) -> list of every rank's bytes, e.g.
     # built on torch.distributed (see comm_from_torch); None = single GPU
     comm: Optional[tuple] = None
+    # single-process multi-GPU (afmg_opts.n_gpus): the handle drives devices device .. device + n_gpus - 1 itself
+    n_gpus: int = 0
     initialized: bool = False
     _h: Optional[C.c_void_p] = None
     _tree: Optional[Tree] = None
@@ -112,6 +114,25 @@ class mg_t:
         data = np.ascontiguousarray(data, np.float64)
         assert data.size == len(ids) * self._tree.nc ** self._tree.ndim
         self.upload_interior_ptr(var, ids, data.ctypes.data)
+
+    def field_set_rhs(self, ids, charges, densities, on_device=False):
+        """field_set_rhs (src/m_field.f90:406-444): rhs = sum_s charges[s] * densities[s] on the listed boxes, summed on
+        the device in the reference's order.  densities: list of packed arrays (n, (nc+2)^ndim), or raw pointers
+        (host or, with on_device, device memory)."""
+        self._need_init()
+        ids = np.ascontiguousarray(ids, np.int32)
+        q = np.ascontiguousarray(charges, np.float64)
+        keep, ptrs = [], (C.c_void_p * len(densities))()
+        for s, d in enumerate(densities):
+            if isinstance(d, (int, np.integer)):
+                ptrs[s] = int(d)
+            else:
+                a = np.ascontiguousarray(d, np.float64)
+                assert a.size == len(ids) * self._tree.box_len
+                keep.append(a)
+                ptrs[s] = a.ctypes.data
+        self._check(_lib.lib().afmg_field_set_rhs(self._h, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)), len(q),
+                                                  q.ctypes.data_as(C.POINTER(C.c_double)), ptrs, int(on_device)))
 
     def download_interior_ptr(self, var, ids, host_ptr):
         """Interior cells only (nc^ndim doubles per box) into a raw host pointer."""
@@ -506,6 +527,7 @@ def _opts_from(tree: Tree, mg: mg_t) -> Opts:
     o.use_corners, o.subtract_mean = int(mg.use_corners), int(mg.subtract_mean)
     o.prolongation_type, o.operator_mask = mg.prolongation_type, mg.operator_mask
     o.has_eps, o.device = 0, mg.device
+    o.n_gpus = mg.n_gpus
     o.helmholtz_lambda, o.lsf_boundary_value = mg.helmholtz_lambda, mg.lsf_boundary_value
     for d in range(3):
         o.coarse_grid_size[d] = int(tree.coarse_grid_size[d]) if d < tree.ndim else 1

@@ -30,7 +30,7 @@ module m_af_multigrid_gpu
   type, bind(c) :: afmg_opts
      integer(c_int32_t) :: ndim, n_cell, coord_t, n_cycle_down, n_cycle_up
      integer(c_int32_t) :: use_corners, subtract_mean, prolongation_type, operator_mask
-     integer(c_int32_t) :: has_eps, device, reserved
+     integer(c_int32_t) :: has_eps, device, n_gpus
      real(c_double)     :: helmholtz_lambda, lsf_boundary_value
      integer(c_int32_t) :: coarse_grid_size(3), periodic(3)
      real(c_double)     :: dr_base(3), r_base(3)
@@ -183,7 +183,7 @@ contains
     o%n_cycle_down = mg%n_cycle_down; o%n_cycle_up = mg%n_cycle_up
     o%use_corners = merge(1, 0, mg%use_corners); o%subtract_mean = merge(1, 0, mg%subtract_mean)
     o%prolongation_type = mg%prolongation_type; o%operator_mask = mg%operator_mask
-    o%has_eps = merge(1, 0, tree%mg_i_eps > 0); o%device = -1; o%reserved = 0
+    o%has_eps = merge(1, 0, tree%mg_i_eps > 0); o%device = -1; o%n_gpus = 0   ! 0: one GPU, or AFMG_N_GPUS GPUs of one node
     o%helmholtz_lambda = mg%helmholtz_lambda; o%lsf_boundary_value = mg%lsf_boundary_value
     o%coarse_grid_size = 1; o%periodic = 0; o%dr_base = 0; o%r_base = 0
     o%coarse_grid_size(1:NDIM) = tree%coarse_grid_size(1:NDIM)

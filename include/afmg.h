@@ -76,7 +76,13 @@ typedef struct afmg_opts {
   int32_t operator_mask;        /* mg%operator_mask (-1 = all bits)                           */
   int32_t has_eps;              /* tree%mg_i_eps > 0                                          */
   int32_t device;               /* CUDA device ordinal, -1 = current device                   */
-  int32_t reserved;
+  int32_t n_gpus;               /* 0 / 1: this handle drives ONE GPU (`device`).  N > 1: single-process multi-GPU --
+                                 * the handle drives devices device .. device + N - 1 (device = -1: 0 .. N - 1) of one
+                                 * NVLink domain with one host thread per GPU inside the library, boxes partitioned as
+                                 * by afmg_partition_min, halos through peer memory (cudaDeviceEnablePeerAccess); every
+                                 * call of this API then acts on the whole tree, exactly as with N = 1.  This is the mode
+                                 * for a single-process caller such as the reference (one OpenMP process,
+                                 * afivo/documentation/parallelization.md).  0 also reads AFMG_N_GPUS.               */
   double helmholtz_lambda;      /* mg%helmholtz_lambda (lambda^2 of L phi - lambda phi = f)   */
   double lsf_boundary_value;    /* mg%lsf_boundary_value                                      */
   int32_t coarse_grid_size[3];  /* tree%coarse_grid_size (cells)                              */
@@ -268,6 +274,15 @@ int afmg_upload_device(afmg_handle* h, int32_t var, int32_t n, const int32_t* bo
                        const double* packed_device);
 int afmg_download_device(afmg_handle* h, int32_t var, int32_t n, const int32_t* box_id_host,
                          double* packed_device);
+/* field_set_rhs (src/m_field.f90:406-444) with the sum on the device: rhs = 0, then rhs = rhs + charges[s] *
+ * densities[s] for s = 0 .. n_species-1 on the complete records of the listed boxes (the reference loops over the leaves),
+ * in that order, so the bits are the reference's.  charges[s] = charged_species_charge(s) * (-UC_elem_charge / UC_eps0);
+ * densities[s] = packed cc(:, :, :, charged_species_itree(s) + s_in) of the boxes in the order of box_id, (nc+2)^ndim
+ * doubles each, in host memory (page-locked for speed) or, with on_device != 0, in device memory -- the case this
+ * exists for: a caller that keeps its densities resident ships nothing per solve.  The surface-charge term of
+ * dielectrics (surface_surface_charge_to_rhs) stays with the caller: pass it as one more "species" with charge 1. */
+int afmg_field_set_rhs(afmg_handle* h, int32_t n, const int32_t* box_id, int32_t n_species, const double* charges,
+                       const double* const* densities, int32_t on_device);
 /* af_tree_clear_cc / af_box_clear_cc (m_af_utils.f90:385): set a variable to zero on all boxes */
 int afmg_clear(afmg_handle* h, int32_t var);
 

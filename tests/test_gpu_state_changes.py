@@ -124,3 +124,34 @@ def test_page_locked_buffers_and_chunked_transfers():
     del up, dn
     L.afmg_host_free(p_up)
     L.afmg_host_free(p_dn)
+
+
+@pytest.mark.parametrize("ndim,nc", [(3, 16), (3, 8), (2, 8)])
+def test_field_set_rhs_on_device_has_the_references_bits(ndim, nc):
+    """field_set_rhs (src/m_field.f90:406-444): cc(:, i_rhs) = 0, then += q_n * cc(:, species_n) for n = 1 .. on the
+    leaves.  numpy restates the loop (same order, no FMA); the device result must be identical bit for bit, from host
+    memory and from densities already resident on the device."""
+    import torch
+    tree = T.corner_refined_tree(ndim, nc, nc, 3)
+    leaves = np.concatenate([tree.leaves(l) for l in range(1, tree.highest_lvl + 1)]).astype(np.int32)
+    rng = np.random.default_rng(21)
+    fac = -1.602176634e-19 / 8.8541878128e-12  # -UC_elem_charge / UC_eps0
+    charges = np.array([1.0, -1.0, 2.0, -1.0]) * fac
+    dens = [rng.uniform(0, 1e18, (len(leaves), tree.box_len)) for _ in charges]
+    dens[2][:, ::3] = 0.0
+    want = np.zeros_like(dens[0])
+    for q, d in zip(charges, dens):
+        want = want + q * d
+    mg = M.mg_t(sides_bc=W.bc_dirichlet_zero(tree))
+    M.mg_init(tree, mg)
+    mg.set_cc(M.I_RHS, leaves, rng.uniform(-1, 1, want.shape))  # stale values must not survive
+    mg.field_set_rhs(leaves, charges, dens)
+    got = mg.get_cc(M.I_RHS, leaves).reshape(want.shape)
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    # densities resident on the device
+    mg.set_cc(M.I_RHS, leaves, rng.uniform(-1, 1, want.shape))
+    dev = [torch.as_tensor(d, device="cuda") for d in dens]
+    mg.field_set_rhs(leaves, charges, [int(t.data_ptr()) for t in dev], on_device=True)
+    got = mg.get_cc(M.I_RHS, leaves).reshape(want.shape)
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    M.mg_destroy(mg)
