@@ -148,6 +148,8 @@ SYMBOLS = {
     "afmg_electrode_prepare": (C.c_int, [C.POINTER(Electrode)]),
     "afmg_electrode_lsf": (C.c_double, [_DP, C.c_void_p]),
     "afmg_electrode_potential": (C.c_double, [_DP, C.c_void_p]),
+    "afmg_build_stencils_device": (C.c_int, [_H, C.POINTER(Electrode), C.POINTER(LsfOpts)]),
+    "afmg_built_stencils": (C.c_int, [_H, _IP, _IP, _IP, _IP, _DP]),
     "afmg_build_box_tag": (C.c_int32, [_I, _I, _DP, _I]),
     "afmg_build_box_operator": (C.c_int, [_I, _I, _I, _I, _DP, _DP, _DP, _DP, _DP, _DP, _IP, _IP, _IP]),
     "afmg_build_box_prolongation": (C.c_int, [_I, _I, _I, _IP, _DP, _DP, _DP, _IP, _IP]),

@@ -27,6 +27,9 @@
 #include "kernels3d.cuh"
 #include "mega.cuh"
 
+#include "afmg_builders.inc"
+#include "builders_dev.cuh"
+
 using namespace afmg;
 
 namespace {
@@ -120,6 +123,11 @@ struct afmg_handle {
   std::vector<int> id2slot, slot2id;
   std::vector<int> h_nbr, h_aux, h_nmat, h_parent, h_child0, h_coff, h_lvl;
   std::vector<int> h_ix;  // [nslots*3]
+  std::vector<double> h_rmin;  // [nslots*3] box%r_min
+  double* d_rmin = nullptr;
+  // results of the last afmg_build_stencils_device (kept for afmg_built_stencils)
+  double* d_bblob = nullptr;
+  std::vector<int> b_ids, b_tags, b_meta;
   std::vector<int> npar;  // [L+2] number of boxes with children per level
   int nbc = 0, nrb = 0;
   std::vector<int> rb_lvl_off;  // [L+2] refinement-boundary faces per level (prefix)
@@ -1730,8 +1738,206 @@ int finish_op(afmg_handle* h) {
   return AFMG_OK;
 }
 
+// device -> host copy of the records of a chunk, leaving the records of boxes this rank does not own (slot < 0)
+// untouched in the caller's buffer: with several rank handles in one process they all write into the same array
+cudaError_t copy_own_records(afmg_handle* h, double* hp, const double* dp, const int* slots, int m, size_t rec_len,
+                                    cudaStream_t st) {
+  if (h->nranks == 1) return cudaMemcpyAsync(hp, dp, (size_t)m * rec_len * sizeof(double), cudaMemcpyDeviceToHost, st);
+  int q = 0;
+  while (q < m) {
+    while (q < m && slots[q] < 0) ++q;
+    int e = q;
+    while (e < m && slots[e] >= 0) ++e;
+    if (e > q) {
+      cudaError_t rc = cudaMemcpyAsync(hp + (size_t)q * rec_len, dp + (size_t)q * rec_len, (size_t)(e - q) * rec_len * sizeof(double),
+                                       cudaMemcpyDeviceToHost, st);
+      if (rc != cudaSuccess) return rc;
+    }
+    q = e;
+  }
+  return cudaSuccess;
+}
+
 #include "afmg2d.inc"
 #include "afmg_field.inc"
+
+// Shared by afmg_set_stencils (blob in host memory) and afmg_build_stencils_device (blob produced on the device by
+// the builder kernels, builders_dev.cuh): bookkeeping of the per-box stencil kinds and of the coefficient pool, then
+// the conversion of every variable stencil from the reference's v(n, i, j, k) to the device planes -- on the host
+// for a host blob, by k_planes_from_ref for a device blob, so that in the second case no coefficient crosses PCIe.
+struct StencilJob {
+  int64_t src;    // offset in the blob
+  long long dst;  // offset in the pool
+  int ncf;        // coefficients per cell (planes); 0: plain copy of `len` doubles
+  int len;
+};
+
+template <int NC>
+__global__ void k_planes_from_ref(const double* __restrict__ blob, const StencilJob* __restrict__ jobs, int njobs, double* pool) {
+  using L = Lay3<NC>;
+  const StencilJob jb = jobs[blockIdx.x];
+  const double* src = blob + jb.src;
+  double* dst = pool + jb.dst;
+  if (jb.ncf == 0) {
+    for (int q = threadIdx.x; q < jb.len; q += blockDim.x) dst[q] = src[q];
+    return;
+  }
+  for (int c = threadIdx.x; c < NC * NC * NC; c += blockDim.x) {
+    const int i = c % NC + 1, j = (c / NC) % NC + 1, k = c / (NC * NC) + 1;
+    const int col = (i + j + k) & 1, idx = L::iidx((i - 1) >> 1, j, k);
+    for (int m = 0; m < jb.ncf; ++m) dst[(size_t)(m * 2 + col) * L::NI + idx] = src[(size_t)jb.ncf * c + m];
+  }
+}
+
+int ingest_stencils(afmg_handle* h, int32_t n, const afmg_stencil_desc* desc, const double* blob, int64_t blob_len,
+                           bool blob_on_device) {
+  const int total = h->nslots, nc = h->o.n_cell, ncell = nc * nc * nc;
+  const int NI2 = ncell;  // 2 colours x NI doubles per plane
+  h->h_opk.assign(total, 0);
+  h->h_pk.assign(total, 0);
+  h->h_opoff.assign(total, 0);
+  h->h_foff.assign(total, -1);
+  h->h_poff.assign(total, 0);
+  h->h_tag.assign(total, 0);
+  h->l1_st.clear();
+  std::vector<StencilJob> jobs;
+  long long pool_len = 0;
+  std::vector<std::pair<int, const afmg_stencil_desc*>> l1;  // level-1 boxes: the coarse solver needs them on the host
+  auto need = [&](int64_t off, int64_t len) { return off >= 0 && off + len <= blob_len; };
+  for (int q = 0; q < n; ++q) {
+    const afmg_stencil_desc& d = desc[q];
+    if (d.box_id < 1 || d.box_id > h->highest_id || h->id2slot[d.box_id] < 0)
+      return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: unknown box %d", d.box_id);
+    const int s = h->id2slot[d.box_id];
+    h->h_tag[s] = d.tag;
+    if (d.op_stype == 1 || d.op_stype == 2) {
+      const int64_t len = d.op_stype == 1 ? 7 : (int64_t)7 * ncell;
+      if (!need(d.op_offset, len)) return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: operator of box %d outside the blob", d.box_id);
+      h->h_opk[s] = (unsigned char)d.op_stype;
+      h->h_opoff[s] = pool_len;
+      if (d.op_stype == 1) {
+        jobs.push_back({d.op_offset, pool_len, 0, 7});
+        pool_len += 8;
+      } else {
+        jobs.push_back({d.op_offset, pool_len, 7, 0});
+        pool_len += (long long)7 * NI2;
+      }
+      if (h->h_lvl[s] == 1) l1.emplace_back(s, &d);
+    } else if (d.op_stype != 0) {
+      return h->fail(AFMG_ERR_UNSUPPORTED, "afmg_set_stencils: stencil type %d (sparse stencils are not implemented in the "
+                                           "reference either, m_af_stencil.f90:853)", d.op_stype);
+    }
+    if (d.f_offset >= 0) {
+      if (!need(d.f_offset, ncell)) return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: f of box %d outside the blob", d.box_id);
+      if (h->h_opk[s] == 0) return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: box %d has f but an implicit operator", d.box_id);
+      h->h_foff[s] = pool_len;
+      jobs.push_back({d.f_offset, pool_len, 1, 0});
+      pool_len += NI2;
+    }
+    if (d.prolong_shape != 0) {
+      if (h->h_lvl[s] < 2) return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: level-1 box %d has no prolongation", d.box_id);
+      int kind;
+      if (d.prolong_shape == AFMG_STENCIL_P248 && d.prolong_stype == 1) kind = 1;
+      else if (d.prolong_shape == AFMG_STENCIL_P234 && d.prolong_stype == 1) kind = 2;
+      else if (d.prolong_shape == AFMG_STENCIL_P234 && d.prolong_stype == 2) kind = 3;
+      else return h->fail(AFMG_ERR_UNSUPPORTED, "afmg_set_stencils: prolongation shape %d / type %d of box %d",
+                          d.prolong_shape, d.prolong_stype, d.box_id);
+      const int64_t len = kind == 1 ? 8 : (kind == 2 ? 4 : (int64_t)4 * ncell);
+      if (!need(d.prolong_offset, len))
+        return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: prolongation of box %d outside the blob", d.box_id);
+      h->h_pk[s] = (unsigned char)kind;
+      h->h_poff[s] = pool_len;
+      if (kind == 3) {
+        jobs.push_back({d.prolong_offset, pool_len, 4, 0});
+        pool_len += (long long)4 * NI2;
+      } else {
+        jobs.push_back({d.prolong_offset, pool_len, 0, (int)len});
+        pool_len += 8;
+      }
+    }
+  }
+  // ---- the coefficient pool
+  if (h->d_stv) cudaFree(h->d_stv);
+  h->d_stv = nullptr;
+  CK(cudaMalloc((void**)&h->d_stv, (size_t)std::max<long long>(pool_len, 1) * sizeof(double)));
+  CK(cudaMemset(h->d_stv, 0, (size_t)std::max<long long>(pool_len, 1) * sizeof(double)));
+  if (blob_on_device) {
+    if (!jobs.empty()) {
+      StencilJob* d_jobs = nullptr;
+      CK(cudaMalloc((void**)&d_jobs, jobs.size() * sizeof(StencilJob)));
+      CK(cudaMemcpy(d_jobs, jobs.data(), jobs.size() * sizeof(StencilJob), cudaMemcpyHostToDevice));
+      DISPATCH_NC(h, NC, { k_planes_from_ref<NC><<<(int)jobs.size(), 256, 0, h->stream>>>(blob, d_jobs, (int)jobs.size(), h->d_stv); });
+      CK(cudaStreamSynchronize(h->stream));
+      cudaFree(d_jobs);
+    }
+  } else {
+    std::vector<double> pool((size_t)std::max<long long>(pool_len, 1), 0.0);
+    for (const StencilJob& jb : jobs) {
+      if (jb.ncf == 0) {
+        std::copy(blob + jb.src, blob + jb.src + jb.len, pool.begin() + jb.dst);
+      } else {
+        std::vector<double> tmp;
+        DISPATCH_NC(h, NC, planes_from_ref<NC>(blob + jb.src, jb.ncf, tmp));
+        std::copy(tmp.begin(), tmp.end(), pool.begin() + jb.dst);
+      }
+    }
+    CK(cudaMemcpy(h->d_stv, pool.data(), pool.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  // ---- level-1 stencils for the coarse-grid matrix (m_coarse_solver.f90:71-194), reference layout, on the host
+  for (auto& pr : l1) {
+    const int s = pr.first;
+    const afmg_stencil_desc& d = *pr.second;
+    const int64_t len = d.op_stype == 1 ? 7 : (int64_t)7 * ncell;
+    std::vector<double> op(len), fv;
+    if (blob_on_device) CK(cudaMemcpy(op.data(), blob + d.op_offset, len * sizeof(double), cudaMemcpyDeviceToHost));
+    else std::copy(blob + d.op_offset, blob + d.op_offset + len, op.begin());
+    auto& e = h->l1_st[s];
+    e.first.resize((size_t)7 * ncell);
+    for (int c = 0; c < ncell; ++c)
+      for (int m = 0; m < 7; ++m) e.first[(size_t)7 * c + m] = d.op_stype == 1 ? op[m] : op[(size_t)7 * c + m];
+    if (d.f_offset >= 0) {
+      e.second.resize(ncell);
+      if (blob_on_device) CK(cudaMemcpy(e.second.data(), blob + d.f_offset, (size_t)ncell * sizeof(double), cudaMemcpyDeviceToHost));
+      else e.second.assign(blob + d.f_offset, blob + d.f_offset + ncell);
+    }
+  }
+  // this rank's boxes with an explicit operator, by level
+  std::vector<int> spec;
+  h->spec_off.assign(h->L + 2, 0);
+  bool any = false;
+  for (int l = 1; l <= h->L; ++l) {
+    h->spec_off[l] = (int)spec.size();
+    const Range r = own(h, l);
+    for (int s = r.s0; s < r.s0 + r.n; ++s)
+      if (h->h_opk[s]) spec.push_back(s);
+  }
+  h->spec_off[h->L + 1] = (int)spec.size();
+  for (int s = 0; s < total; ++s) any = any || h->h_opk[s] || h->h_pk[s] || h->h_tag[s];
+  // refinement-boundary faces of variable-eps boxes use mg_sides_rb_extrap (mg_auto_rb)
+  const int nrules = h->nbc + h->nrb;
+  h->h_rule_flag.assign(std::max(nrules, 1), 0);
+  for (int r = 0; r < h->nrb; ++r)
+    if ((h->h_tag[h->h_rb_slot[r]] & h->o.operator_mask) == AFMG_TAG_VEPS_BOX) h->h_rule_flag[h->nbc + r] = 1;
+  h->have_stencils = any;
+  int rc;
+  if ((rc = dev_upload(h, &h->d_opk, h->h_opk))) return rc;
+  if ((rc = dev_upload(h, &h->d_pk, h->h_pk))) return rc;
+  if ((rc = dev_upload(h, &h->d_opoff, h->h_opoff))) return rc;
+  if ((rc = dev_upload(h, &h->d_foff, h->h_foff))) return rc;
+  if ((rc = dev_upload(h, &h->d_poff, h->h_poff))) return rc;
+  if ((rc = dev_upload(h, &h->d_spec, spec))) return rc;
+  if ((rc = dev_upload(h, &h->d_rule_flag, h->h_rule_flag))) return rc;
+  h->cx.opk = any ? h->d_opk : nullptr;
+  h->cx.pk = any ? h->d_pk : nullptr;
+  h->cx.opoff = h->d_opoff;
+  h->cx.foff = h->d_foff;
+  h->cx.poff = h->d_poff;
+  h->cx.stv = h->d_stv;
+  h->cx.rule_flag = any ? h->d_rule_flag : nullptr;
+  h->cx.lsf_value_p = &h->d_comm->lsf_value;
+  return AFMG_OK;
+}
+
 
 }  // namespace
 
@@ -1911,6 +2117,8 @@ int afmg_destroy(afmg_handle* h) {
   cudaFree(h->d_stv);
   cudaFree(h->d_spec);
   cudaFree(h->d_Ainv);
+  cudaFree(h->d_rmin);
+  cudaFree(h->d_bblob);
   cudaFree(h->d_Sinv);
   cudaFree(h->d_cs_lo);
   cudaFree(h->d_cs_up);
@@ -2002,6 +2210,7 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
   h->h_coff.assign(total, 0);
   h->h_lvl.assign(total, 0);
   h->h_ix.assign((size_t)total * 3, 0);
+  h->h_rmin.assign((size_t)total * 3, 0.0);
   h->npar.assign(L + 2, 0);
   h->bc_slot.clear();
   h->bc_face.clear();
@@ -2013,6 +2222,9 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
     const int l = t->lvl[id];
     h->h_lvl[s] = l;
     for (int d = 0; d < 3; ++d) h->h_ix[(size_t)s * 3 + d] = t->ix[(size_t)id * 3 + d];
+    for (int d = 0; d < 3; ++d)  // box%r_min; without it: r_base + (ix - 1) * n_cell * dr (exact for power-of-two sizes)
+      h->h_rmin[(size_t)s * 3 + d] = t->r_min ? t->r_min[(size_t)id * 3 + d]
+                                              : h->o.r_base[d] + (t->ix[(size_t)id * 3 + d] - 1) * (h->o.n_cell * h->o.dr_base[d] * std::pow(0.5, l - 1));
     if (l > 1) {
       const int p = t->parent[id];
       if (p < 1 || p > N || h->id2slot[p] < 0) return h->fail(AFMG_ERR_ARG, "box %d has invalid parent %d", id, p);
@@ -2083,6 +2295,7 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
   if ((rc = dev_upload(h, &h->d_lvl, h->h_lvl))) return rc;
   if ((rc = dev_upload(h, &h->d_rb_slot, h->h_rb_slot))) return rc;
   if ((rc = dev_upload(h, &h->d_rb_face, h->h_rb_face))) return rc;
+  if ((rc = dev_upload(h, &h->d_rmin, h->h_rmin))) return rc;
   const int nrules = h->nbc + h->nrb;
   std::vector<double> rule_c((size_t)std::max(nrules, 1) * 3, 0.0);
   for (int r = h->nbc; r < nrules; ++r) {  // mg_sides_rb: 0.5*gc + 0.75*x1 - 0.25*x2
@@ -2343,107 +2556,168 @@ int afmg_set_stencils(afmg_handle* h, int32_t n, const afmg_stencil_desc* desc, 
   h->resid_fresh = false;
   if (h->fs) h->fs->veps_valid = false;  // box tags change
   if (h->o.ndim == 2) return s2_set_stencils(h, n, desc, blob, blob_len);
+  return ingest_stencils(h, n, desc, blob, blob_len, false);
+}
+
+// mg_set_operators_tree on the device (builders_dev.cuh): tags, operator and prolongation stencils of every box from
+// the resident permittivity (afmg_upload(AFMG_EPS)) and / or one of the built-in electrode shapes, then the same
+// ingestion as afmg_set_stencils -- without the coefficients crossing PCIe -- and the level-set distance stencils
+// of the field computation (afmg_set_lsf_distances).
+int afmg_build_stencils_device(afmg_handle* h, const afmg_electrode* electrode, const afmg_lsf_opts* lsf_opts) {
+  if (!h) return AFMG_ERR_ARG;
+  if (h->is_multi || h->nranks > 1) return h->fail(AFMG_ERR_UNSUPPORTED, "afmg_build_stencils_device: single-GPU handles only (use the host builders)");
+  if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
+  if (h->o.ndim != 3) return h->fail(AFMG_ERR_UNSUPPORTED, "afmg_build_stencils_device: 3D only (2D boxes are built on the host)");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  const double* d_eps = (h->fs && h->fs->d_eps) ? h->fs->d_eps : nullptr;
+  if (!d_eps && !electrode) return h->fail(AFMG_ERR_ARG, "afmg_build_stencils_device: neither AFMG_EPS uploaded nor an electrode given");
+  BuildCtx bc{};
+  bc.eps = d_eps;
+  bc.rmin = h->d_rmin;
+  bc.lvl = h->d_lvl;
+  bc.parent = h->d_parent;
+  bc.coff = h->d_coff;
+  for (int d = 0; d < 3; ++d) bc.dr_base[d] = h->o.dr_base[d];
+  bc.has_el = electrode ? 1 : 0;
+  if (electrode) bc.el = *electrode;
+  if (lsf_opts) bc.lo = *lsf_opts;
+  else afmg_lsf_opts_default(&bc.lo);
+  bc.operator_mask = h->o.operator_mask;
+  bc.prolong_auto = h->o.prolongation_type == AFMG_PROLONG_AUTO ? 1 : 0;
   const int total = h->nslots, nc = h->o.n_cell, ncell = nc * nc * nc;
-  h->h_opk.assign(total, 0);
-  h->h_pk.assign(total, 0);
-  h->h_opoff.assign(total, 0);
-  h->h_foff.assign(total, -1);
-  h->h_poff.assign(total, 0);
-  h->h_tag.assign(total, 0);
-  h->l1_st.clear();
-  std::vector<double> pool;
-  auto need = [&](int64_t off, int64_t len) { return off >= 0 && off + len <= blob_len; };
+  int *d_tag = nullptr, *d_nb = nullptr, *d_list = nullptr, *d_meta = nullptr;
+  CK(cudaMalloc((void**)&d_tag, (size_t)total * sizeof(int)));
+  CK(cudaMalloc((void**)&d_nb, (size_t)total * sizeof(int)));
+  auto cleanup = [&] {
+    cudaFree(d_tag);
+    cudaFree(d_nb);
+    cudaFree(d_list);
+    cudaFree(d_meta);
+  };
+  {
+    Launch L_(h, "build_tags");
+    DISPATCH_NC(h, NC, { k_dev_tags<NC><<<total, 256, 0, h->stream>>>(bc, total, d_tag, d_nb); });
+  }
+  std::vector<int> tags(total), nb(total);
+  cudaError_t e = cudaMemcpyAsync(tags.data(), d_tag, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(nb.data(), d_nb, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) {
+    cleanup();
+    return h->fail(AFMG_ERR_CUDA, "afmg_build_stencils_device: %s", cudaGetErrorString(e));
+  }
+  if (electrode) {  // check_coarse_representation_lsf (m_af_multigrid.f90:2142-2161): the reference stops here
+    bool on_coarse = false;
+    for (int s2 = 0; s2 < nlev(h, 1); ++s2) on_coarse = on_coarse || (tags[s2] & AFMG_TAG_LSF_BOX);
+    if (!on_coarse) {
+      cleanup();
+      return h->fail(AFMG_ERR_ARG, "level set function not resolved on coarse grid: no roots found on level 1, use a finer coarse grid");
+    }
+  }
+  std::vector<int> list;
+  for (int s2 = 0; s2 < total; ++s2)
+    if (tags[s2] != 0) list.push_back(s2);
+  const int n = (int)list.size();
+  size_t stride = 0;
+  DISPATCH_NC(h, NC, stride = BuildBlob<NC>::STRIDE);
+  if (h->d_bblob) cudaFree(h->d_bblob);
+  h->d_bblob = nullptr;
+  std::vector<int> meta((size_t)std::max(n, 1) * 4, 0);
+  if (n > 0) {
+    e = cudaMalloc((void**)&h->d_bblob, (size_t)n * stride * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_list, (size_t)n * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_meta, (size_t)n * 4 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_list, list.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+      Launch L_(h, "build_stencils");
+      DISPATCH_NC(h, NC, { k_dev_build<NC><<<n, 256, 0, h->stream>>>(bc, d_list, d_tag, n, h->d_bblob, d_meta); });
+      e = cudaMemcpyAsync(meta.data(), d_meta, (size_t)n * 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) {
+      cleanup();
+      return h->fail(AFMG_ERR_CUDA, "afmg_build_stencils_device: %s", cudaGetErrorString(e));
+    }
+  }
+  cleanup();
+  // ---- descriptors over the device blob, then the common ingestion
+  size_t oF = 0, oPV = 0, oDD = 0;
+  DISPATCH_NC(h, NC, { oF = BuildBlob<NC>::F; oPV = BuildBlob<NC>::PV; oDD = BuildBlob<NC>::DD; });
+  std::vector<afmg_stencil_desc> desc(std::max(n, 1));
+  h->b_ids.assign(n, 0);
+  h->b_tags.assign(n, 0);
+  h->b_meta = meta;
   for (int q = 0; q < n; ++q) {
-    const afmg_stencil_desc& d = desc[q];
-    if (d.box_id < 1 || d.box_id > h->highest_id || h->id2slot[d.box_id] < 0)
-      return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: unknown box %d", d.box_id);
-    const int s = h->id2slot[d.box_id];
-    h->h_tag[s] = d.tag;
-    if (d.op_stype == 1 || d.op_stype == 2) {
-      const int64_t len = d.op_stype == 1 ? 7 : (int64_t)7 * ncell;
-      if (!need(d.op_offset, len)) return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: operator of box %d outside the blob", d.box_id);
-      h->h_opk[s] = (unsigned char)d.op_stype;
-      h->h_opoff[s] = (long long)pool.size();
-      if (d.op_stype == 1) {
-        pool.insert(pool.end(), blob + d.op_offset, blob + d.op_offset + 7);
-        pool.push_back(0.0);
-      } else {
-        DISPATCH_NC(h, NC, planes_from_ref<NC>(blob + d.op_offset, 7, pool));
-      }
-      if (h->h_lvl[s] == 1) {
-        auto& e = h->l1_st[s];
-        e.first.resize((size_t)7 * ncell);
-        for (int c = 0; c < ncell; ++c)
-          for (int m = 0; m < 7; ++m)
-            e.first[(size_t)7 * c + m] = d.op_stype == 1 ? blob[d.op_offset + m] : blob[d.op_offset + (int64_t)7 * c + m];
-      }
-    } else if (d.op_stype != 0) {
-      return h->fail(AFMG_ERR_UNSUPPORTED, "afmg_set_stencils: stencil type %d (sparse stencils are not implemented in the "
-                                           "reference either, m_af_stencil.f90:853)", d.op_stype);
-    }
-    if (d.f_offset >= 0) {
-      if (!need(d.f_offset, ncell)) return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: f of box %d outside the blob", d.box_id);
-      if (h->h_opk[s] == 0) return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: box %d has f but an implicit operator", d.box_id);
-      h->h_foff[s] = (long long)pool.size();
-      DISPATCH_NC(h, NC, planes_from_ref<NC>(blob + d.f_offset, 1, pool));
-      if (h->h_lvl[s] == 1) h->l1_st[s].second.assign(blob + d.f_offset, blob + d.f_offset + ncell);
-    }
-    if (d.prolong_shape != 0) {
-      if (h->h_lvl[s] < 2) return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: level-1 box %d has no prolongation", d.box_id);
-      int kind;
-      if (d.prolong_shape == AFMG_STENCIL_P248 && d.prolong_stype == 1) kind = 1;
-      else if (d.prolong_shape == AFMG_STENCIL_P234 && d.prolong_stype == 1) kind = 2;
-      else if (d.prolong_shape == AFMG_STENCIL_P234 && d.prolong_stype == 2) kind = 3;
-      else return h->fail(AFMG_ERR_UNSUPPORTED, "afmg_set_stencils: prolongation shape %d / type %d of box %d",
-                          d.prolong_shape, d.prolong_stype, d.box_id);
-      const int64_t len = kind == 1 ? 8 : (kind == 2 ? 4 : (int64_t)4 * ncell);
-      if (!need(d.prolong_offset, len))
-        return h->fail(AFMG_ERR_ARG, "afmg_set_stencils: prolongation of box %d outside the blob", d.box_id);
-      h->h_pk[s] = (unsigned char)kind;
-      h->h_poff[s] = (long long)pool.size();
-      if (kind == 3) {
-        DISPATCH_NC(h, NC, planes_from_ref<NC>(blob + d.prolong_offset, 4, pool));
-      } else {
-        pool.insert(pool.end(), blob + d.prolong_offset, blob + d.prolong_offset + len);
-        pool.resize(pool.size() + (8 - len), 0.0);
-      }
-    }
+    afmg_stencil_desc& d = desc[q];
+    const int64_t base = (int64_t)q * (int64_t)stride;
+    d.box_id = h->slot2id[list[q]];
+    d.tag = tags[list[q]];
+    d.op_stype = meta[4 * q];
+    d.op_offset = base;
+    d.f_offset = meta[4 * q + 1] ? base + (int64_t)oF : -1;
+    d.prolong_shape = meta[4 * q + 2] ? AFMG_STENCIL_P234 : 0;
+    d.prolong_stype = meta[4 * q + 2];
+    d.prolong_offset = base + (int64_t)oPV;
+    d.cylindrical_gradient = 0;
+    h->b_ids[q] = d.box_id;
+    h->b_tags[q] = d.tag;
   }
-  // this rank's boxes with an explicit operator, by level
-  std::vector<int> spec;
-  h->spec_off.assign(h->L + 2, 0);
-  bool any = false;
-  for (int l = 1; l <= h->L; ++l) {
-    h->spec_off[l] = (int)spec.size();
-    const Range r = own(h, l);
-    for (int s = r.s0; s < r.s0 + r.n; ++s)
-      if (h->h_opk[s]) spec.push_back(s);
+  drop_graphs(h);
+  h->cs_ready = false;
+  h->resid_fresh = false;
+  if (h->fs) h->fs->veps_valid = false;
+  int rc = ingest_stencils(h, n, desc.data(), h->d_bblob, (int64_t)n * (int64_t)stride, true);
+  if (rc) return rc;
+  // ---- the sparse distance stencils of the field computation at the electrode (mg_box_lpllsf_gradient): only the
+  // boxes with an internal boundary, a few KB each
+  if (electrode) {
+    std::vector<int32_t> ids, nent, cells;
+    std::vector<double> dds, vals, ddbox((size_t)6 * ncell);
+    for (int q = 0; q < n; ++q) {
+      if (!(tags[list[q]] & AFMG_TAG_LSF_BOX)) continue;
+      CK(cudaMemcpy(ddbox.data(), h->d_bblob + (size_t)q * stride + oDD, ddbox.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      const int s2 = list[q];
+      const double fac = std::pow(0.5, h->h_lvl[s2] - 1);
+      int ne = 0;
+      for (int c = 0; c < ncell; ++c) {
+        bool any = false;
+        for (int m = 0; m < 6; ++m) any = any || ddbox[(size_t)6 * c + m] < 1.0;
+        if (!any) continue;
+        const int ijk[3] = {c % nc + 1, (c / nc) % nc + 1, c / (nc * nc) + 1};
+        double r[3];
+        for (int d = 0; d < 3; ++d) {
+          cells.push_back(ijk[d]);
+          r[d] = h->h_rmin[(size_t)s2 * 3 + d] + (ijk[d] - 0.5) * (h->o.dr_base[d] * fac);
+        }
+        for (int m = 0; m < 6; ++m) dds.push_back(ddbox[(size_t)6 * c + m]);
+        vals.push_back(builders::electrode_lsf_value(electrode, r));
+        ++ne;
+      }
+      ids.push_back(h->slot2id[s2]);
+      nent.push_back(ne);
+    }
+    if (!ids.empty() && (rc = afmg_set_lsf_distances(h, (int)ids.size(), ids.data(), nent.data(), cells.data(), dds.data(), vals.data())))
+      return rc;
   }
-  h->spec_off[h->L + 1] = (int)spec.size();
-  for (int s = 0; s < total; ++s) any = any || h->h_opk[s] || h->h_pk[s] || h->h_tag[s];
-  // refinement-boundary faces of variable-eps boxes use mg_sides_rb_extrap (mg_auto_rb)
-  const int nrules = h->nbc + h->nrb;
-  h->h_rule_flag.assign(std::max(nrules, 1), 0);
-  for (int r = 0; r < h->nrb; ++r)
-    if ((h->h_tag[h->h_rb_slot[r]] & h->o.operator_mask) == AFMG_TAG_VEPS_BOX) h->h_rule_flag[h->nbc + r] = 1;
-  h->have_stencils = any;
-  int rc;
-  if ((rc = dev_upload(h, &h->d_opk, h->h_opk))) return rc;
-  if ((rc = dev_upload(h, &h->d_pk, h->h_pk))) return rc;
-  if ((rc = dev_upload(h, &h->d_opoff, h->h_opoff))) return rc;
-  if ((rc = dev_upload(h, &h->d_foff, h->h_foff))) return rc;
-  if ((rc = dev_upload(h, &h->d_poff, h->h_poff))) return rc;
-  if ((rc = dev_upload(h, &h->d_stv, pool))) return rc;
-  if ((rc = dev_upload(h, &h->d_spec, spec))) return rc;
-  if ((rc = dev_upload(h, &h->d_rule_flag, h->h_rule_flag))) return rc;
-  h->cx.opk = any ? h->d_opk : nullptr;
-  h->cx.pk = any ? h->d_pk : nullptr;
-  h->cx.opoff = h->d_opoff;
-  h->cx.foff = h->d_foff;
-  h->cx.poff = h->d_poff;
-  h->cx.stv = h->d_stv;
-  h->cx.rule_flag = any ? h->d_rule_flag : nullptr;
-  h->cx.lsf_value_p = &h->d_comm->lsf_value;
+  return AFMG_OK;
+}
+
+// what the last afmg_build_stencils_device produced, in the reference's order (for checks against the host builders):
+// per tagged box its id, tag, meta (op_stype, has_f, prolongation stype, 0) and the record v(7, cells) | f(cells) |
+// pv(4, cells) | dd(6, cells).  Pass null pointers to query *n only.
+int afmg_built_stencils(afmg_handle* h, int32_t* n, int32_t* box_id, int32_t* tag, int32_t* meta, double* blob) {
+  if (!h || !n) return AFMG_ERR_ARG;
+  *n = (int32_t)h->b_ids.size();
+  if (box_id) std::copy(h->b_ids.begin(), h->b_ids.end(), box_id);
+  if (tag) std::copy(h->b_tags.begin(), h->b_tags.end(), tag);
+  if (meta) std::copy(h->b_meta.begin(), h->b_meta.begin() + 4 * h->b_ids.size(), meta);
+  if (blob && !h->b_ids.empty()) {
+    CK(cudaSetDevice(h->device));
+    size_t stride = 0;
+    DISPATCH_NC(h, NC, stride = BuildBlob<NC>::STRIDE);
+    CK(cudaMemcpy(blob, h->d_bblob, h->b_ids.size() * stride * sizeof(double), cudaMemcpyDeviceToHost));
+  }
   return AFMG_OK;
 }
 
@@ -2522,7 +2796,7 @@ static int transfer(afmg_handle* h, int var, int n, const int32_t* box_id, doubl
       if (!device_ptr) {
         CK(cudaEventRecord(h->ev_copied[hb], h->stream));
         CK(cudaStreamWaitEvent(h->copy_stream, h->ev_copied[hb], 0));
-        CK(cudaMemcpyAsync(hp, dp, (size_t)m * box_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+        CK(copy_own_records(h, hp, dp, slots.data() + q0, m, rec_len, h->copy_stream));
         CK(cudaEventRecord(h->ev_consumed[hb], h->copy_stream));
       }
     }
@@ -3261,4 +3535,3 @@ int32_t afmg_owner_of_box(const afmg_handle* h, int32_t box_id) {
 
 }  // extern "C"
 
-#include "afmg_builders.inc"

@@ -134,6 +134,29 @@ class mg_t:
         self._check(_lib.lib().afmg_field_set_rhs(self._h, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)), len(q),
                                                   q.ctypes.data_as(C.POINTER(C.c_double)), ptrs, int(on_device)))
 
+    def build_stencils_device(self, electrode=None, lsf_options=None):
+        """mg_set_operators_tree on the device (afmg_build_stencils_device): from the uploaded AFMG_EPS and / or a
+        built-in electrode (stencils.electrode(...)); replaces build_stencils + set_stencils + set_lsf_distances."""
+        self._need_init()
+        self._check(_lib.lib().afmg_build_stencils_device(
+            self._h, C.byref(electrode) if electrode is not None else None,
+            C.byref(lsf_options) if lsf_options is not None else None))
+
+    def built_stencils(self):
+        """(ids, tags, meta (n, 4), blob (n, 18 * nc^3)) of the last build_stencils_device, reference order:
+        v(7, cells) | f(cells) | pv(4, cells) | dd(6, cells) per box"""
+        L = _lib.lib()
+        n = C.c_int32(0)
+        self._check(L.afmg_built_stencils(self._h, C.byref(n), None, None, None, None))
+        nb, ncell = n.value, self._tree.nc ** 3
+        ids, tags, meta = np.zeros(nb, np.int32), np.zeros(nb, np.int32), np.zeros((nb, 4), np.int32)
+        blob = np.zeros((nb, 18 * ncell))
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        if nb:
+            self._check(L.afmg_built_stencils(self._h, C.byref(n), ip(ids), ip(tags), ip(meta),
+                                              blob.ctypes.data_as(C.POINTER(C.c_double))))
+        return ids, tags, meta, blob
+
     def download_interior_ptr(self, var, ids, host_ptr):
         """Interior cells only (nc^ndim doubles per box) into a raw host pointer."""
         ids = np.ascontiguousarray(ids, np.int32)

@@ -173,7 +173,8 @@ def build_stencils(tree: Tree, *, eps_cc: Optional[np.ndarray] = None, lsf: Opti
     if lsf is not None and lsf_data is None:
         lsf_data = lsf_distances(tree, lsf, lsf_options, lsf_use_custom_prolongation)
     dd_of = {int(b): lsf_data.dd[n] for n, b in enumerate(lsf_data.ids)} if lsf_data is not None else {}
-    if lsf_data is not None and not any(tree.lvl[int(b)] == 1 for b in lsf_data.ids):
+    if (lsf is not None and lsf_data is None) or \
+            (lsf_data is not None and not any(tree.lvl[int(b)] == 1 for b in lsf_data.ids)):
         # check_coarse_representation_lsf (m_af_multigrid.f90:2142-2161): the reference stops here, because a
         # coarse grid that does not see the electrode makes the cycles diverge
         raise _lib.AfmgError(-1, "level set function not resolved on coarse grid: no roots found on level 1, "

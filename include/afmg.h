@@ -248,6 +248,16 @@ typedef struct afmg_electrode {
   double cone_tip_center[3], cone_tip_r_curvature, cone2_tip_center[3], cone2_tip_r_curvature;
 } afmg_electrode;
 int afmg_electrode_prepare(afmg_electrode* e);
+/* mg_set_operators_tree ON THE DEVICE (csrc/builders_dev.cuh): box tags, operator and prolongation
+ * stencils of every box from the permittivity resident on the device (afmg_upload(AFMG_EPS, all boxes incl. ghost cells)
+ * and / or one of the built-in electrode shapes above (NULL: none), with the level-set options of mg_t (NULL: defaults),
+ * followed by what afmg_set_stencils and afmg_set_lsf_distances do -- but no coefficient crosses PCIe.  The
+ * arithmetic is the host builders' (same per-cell functions), hence the reference's.  3D, single-GPU handles;
+ * mg%lsf_use_custom_prolongation and user level-set callbacks stay with the host builders.  Errors like the reference:
+ * an electrode that level 1 does not resolve (check_coarse_representation_lsf) is AFMG_ERR_ARG. */
+int afmg_build_stencils_device(afmg_handle* h, const afmg_electrode* electrode, const afmg_lsf_opts* lsf_opts);
+/* the records it built, in the reference's order, for checks against afmg_build_box_* (see csrc/afmg.cu) */
+int afmg_built_stencils(afmg_handle* h, int32_t* n, int32_t* box_id, int32_t* tag, int32_t* meta, double* blob);
 double afmg_electrode_lsf(const double* r, void* electrode);
 double afmg_electrode_potential(const double* r, void* electrode);
 

@@ -31,7 +31,7 @@ needs2 = pytest.mark.skipif(n_devices() < 2, reason="needs two GPUs on one node"
 def split_small_levels():
     """the test trees are small: let the partition split every level so that halos really cross GPUs"""
     old = os.environ.get("AFMG_MIN_SPLIT_BOXES")
-    os.environ["AFMG_MIN_SPLIT_BOXES"] = "16"
+    os.environ["AFMG_MIN_SPLIT_BOXES"] = "8"
     yield
     os.environ.pop("AFMG_MIN_SPLIT_BOXES", None)
     if old is not None:
@@ -59,9 +59,10 @@ def solve(tree, bc, ids, rhs, n_gpus, **opts):
 
 
 @needs2
-@pytest.mark.parametrize("name", ["corner_nc8_l4", "shell_nc8", "uniform_nc16_l3", "channel_nc8"])
+@pytest.mark.parametrize("name", ["multibox_nc8", "shell_nc8", "uniform_nc16_l3", "channel_nc8"])
 def test_one_process_two_gpus_bit_identical(name):
-    tree = {"corner_nc8_l4": lambda: T.corner_refined_tree(3, 8, 8, 4), "shell_nc8": lambda: T.shell_tree(8, 8, 4, 0.35),
+    tree = {"multibox_nc8": lambda: T.build_tree(3, 8, [16, 8, 24], 3, lambda l, ix, c: np.linalg.norm(c - 0.4, axis=1) < 0.45),
+            "shell_nc8": lambda: T.shell_tree(8, 8, 4, 0.35),
             "uniform_nc16_l3": lambda: T.uniform_tree(3, 16, 16, 3), "channel_nc8": lambda: T.channel_tree(8, 8, 6, 3)}[name]()
     bc = W.bc_table(tree, bc_mixed)
     ids, rhs = W.random_rhs_on_leaves(tree)
