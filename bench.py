@@ -124,7 +124,7 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-CPU_SAMPLE = {"S3": "S3s"}  # bounded CPU sample of a workload too large to time on the host in seconds
+CPU_SAMPLE = {"S3": "S3s", "S2e": "S2"}  # bounded CPU sample of a workload too large to time on the host in seconds
 
 
 def build_workload(name, want_rhs=True):
@@ -157,10 +157,13 @@ def build_workload(name, want_rhs=True):
         bc = W.bc_table(tree, lambda nb, c: (W.AF_BC_DIRICHLET, 0.0 if nb == 3 else 1.0) if (nb - 1) // 2 == 1
                         else (W.AF_BC_NEUMANN, 0.0))
         desc = "S0: 2D cylindrical (BASELINE.json configs[0] stand-in), nc=8, coarse 8^2, 7 uniform levels (512^2 cells)"
-    elif name == "S2":
+    elif name in ("S2", "S2e"):
         tree = T.channel_tree(8, 8, 9, 3)
         bc = W.bc_field_homogeneous(tree, 1.0)
         desc = "S2: standard_3d-like channel-refined tree, nc=8, 9 levels"
+        if name == "S2e":
+            desc += ("; rod electrode (radius 0.1) from the top plate down to the channel + dielectric slab (eps = 3) "
+                     "below z = 0.2: boxes with explicit stencils, built on the device (afmg_build_stencils_device)")
     else:
         raise SystemExit(f"unknown workload {name}")
     ids = rhs = None
@@ -386,8 +389,28 @@ def run_gpu(args):
         return float(t.item())
 
     tree, bc, _, _, desc = build_workload(args.workload, want_rhs=False)
-    mg = M.mg_t(sides_bc=bc, device=local, comm=comm)
+    mg = M.mg_t(sides_bc=bc, device=local, comm=comm, lsf_boundary_value=1.0)
     M.mg_init(tree, mg)
+    explicit = None
+    if args.workload == "S2e":
+        # variable-coefficient / level-set boxes.  Permittivity up (one variable, once per refinement),
+        # then tags + operator + prolongation stencils are built where the data lives.
+        from afivo_streamer_b200 import stencils as St
+        from afivo_streamer_b200 import workloads as Wk
+        boxes = np.concatenate(tree.lvl_ids).astype(np.int32)
+        ctr = Wk.cell_centres(tree, boxes, ghosts=True)
+        mg.set_cc(M.I_EPS, boxes, np.where(ctr[..., 2] < 0.2, 3.0, 1.0))
+        el = St.electrode("rod", 3, rod_r0=(0.5, 0.5, 0.7), rod_r1=(0.5, 0.5, 1.2), rod_radius=0.1)
+        t0 = time.perf_counter()
+        mg.build_stencils_device(el)
+        t_build = time.perf_counter() - t0
+        b_ids, b_tags, b_meta, _ = mg.built_stencils()
+        explicit = {"boxes_with_tags": int(len(b_ids)), "electrode_boxes": int(np.count_nonzero(b_tags & 1)),
+                    "variable_eps_boxes": int(np.count_nonzero(b_tags & 2)), "constant_eps_boxes": int(np.count_nonzero(b_tags & 4)),
+                    "variable_operators": int(np.count_nonzero(b_meta[:, 0] == 2)), "of_boxes": int(tree.n_boxes),
+                    "device_build_ms": 1e3 * t_build,
+                    "what": "afmg_build_stencils_device: tags, operator and prolongation stencils from the resident "
+                            "permittivity and the built-in rod electrode (blocking call, includes the ingestion)"}
     # this rank's leaves, in the tree's (level, list) order
     leaves = np.concatenate([tree.leaves(l) for l in range(1, tree.highest_lvl + 1)]).astype(np.int32)
     if world > 1:
@@ -544,6 +567,58 @@ def run_gpu(args):
     h2d_total, d2h_total = allsum(nbytes_up), allsum(nbytes_dn + 8)
     e2e_parts = {k: allmax(1e3 * v / e2e_steps) for k, v in zip(("upload_ms", "vcycle_ms", "maxnorm_ms", "download_ms"), parts)}
     e2e_parts["pcie_GBs_per_gpu"] = (nbytes_up + nbytes_dn) / 1e9 / max(1e-9, (parts[0] + parts[3]) / e2e_steps)
+    # ---- the Fortran shim's call sequence (fortran/m_af_multigrid_gpu.f90), emulated on one GPU: per field solve it
+    # (1) packs box%cc(i_rhs) of the leaves into its page-locked buffer, (2) afmg_upload (whole records),
+    # (3) the cycle + max-norm, (4) afmg_download of phi on ALL boxes with ghost cells (the reference's post-condition)
+    # and unpacks it into the boxes, (5) the same for i_tmp unless switched off (mg_gpu_set_download_tmp).  phi is not
+    # uploaded: the device copy is current between solves.  Packing / unpacking = one host memcpy pass each.
+    shim = None
+    if world == 1 and tree.ndim == 3:
+        import ctypes as C
+        from afivo_streamer_b200 import _lib
+        Lb = _lib.lib()
+        allb = np.concatenate(tree.lvl_ids).astype(np.int32)
+        n_up, n_dn = len(ids) * box_len, len(allb) * box_len
+        p_buf = Lb.afmg_host_alloc(max(n_up, n_dn) * 8)
+        pinned = np.ctypeslib.as_array(C.cast(p_buf, C.POINTER(C.c_double)), shape=(max(n_up, n_dn),))
+        host_rhs = h_rhs.numpy()                      # stands for the boxes' own (pageable) cc arrays
+        host_phi = np.empty(n_dn)
+        tt = np.zeros(6)
+
+        def shim_step(with_tmp):
+            t = [time.perf_counter()]
+            np.copyto(pinned[:n_up], host_rhs); t.append(time.perf_counter())
+            mg.upload_ptr(M.I_RHS, ids, p_buf); t.append(time.perf_counter())
+            M.mg_fas_vcycle(tree, mg, True)
+            M.af_tree_maxabs_cc(tree, mg, M.I_TMP); t.append(time.perf_counter())
+            mg.download_ptr(M.I_PHI, allb, p_buf); t.append(time.perf_counter())
+            np.copyto(host_phi, pinned[:n_dn]); t.append(time.perf_counter())
+            if with_tmp:
+                mg.download_ptr(M.I_TMP, allb, p_buf)
+                np.copyto(host_phi, pinned[:n_dn])
+            t.append(time.perf_counter())
+            tt[:] += np.diff(t)
+
+        shim_step(True)
+        reps = 2 if big else 5
+        out_s = {}
+        for with_tmp in (True, False):
+            tt[:] = 0
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                shim_step(with_tmp)
+            out_s["ms_per_solve_with_tmp" if with_tmp else "ms_per_solve_phi_only"] = 1e3 * (time.perf_counter() - t0) / reps
+            if not with_tmp:
+                out_s["phases_ms_phi_only"] = dict(zip(("pack_rhs", "upload_rhs", "cycle_and_norm", "download_phi", "unpack_phi", "tmp"),
+                                                       (1e3 * tt / reps).round(3).tolist()))
+        out_s["bytes"] = {"h2d": n_up * 8, "d2h_phi": n_dn * 8}
+        out_s["what"] = ("fortran/m_af_multigrid_gpu.f90 call sequence for one mg_fas_vcycle: rhs of the leaves up and phi of "
+                         "all boxes down as whole records through a page-locked packing buffer, host pack / unpack passes "
+                         "included; with_tmp also brings i_tmp back (the reference's set_residual post-condition)")
+        shim = out_s
+        del pinned
+        Lb.afmg_host_free(p_buf)
+
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel timing with CUDA events (library profiling mode, no graph) -----------------
@@ -630,6 +705,7 @@ def run_gpu(args):
             "fmg": {"ms": fmg_ms, "cell_updates_per_s": cu_fmg / (fmg_ms * 1e-3)},
             "field_from_potential": field,
             "helmholtz_photoionization": helm,
+            "explicit_stencils": explicit,
             "residual": {"after_fmg": res0, "after_timed_cycles": res1},
             "phi_checksum": {"sum_u64": f"{csum:016x}", "xor_u64": f"{cxor:016x}",
                              "what": "wrapping sum / xor of the bit patterns of phi over the complete records of all "
@@ -639,6 +715,7 @@ def run_gpu(args):
                     "steps": e2e_steps, "ms_per_step": 1e3 * wall_max / e2e_steps, "phases_max_over_ranks": e2e_parts,
                     "what": "upload rhs (interior, leaves) -> V-cycle -> residual max-norm -> download phi (interior, "
                             "leaves); pinned host buffers, blocking C-ABI calls"},
+            "shim_sequence": shim,
             "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
             "kernel_profile_ms_per_cycle_rank0": {k: v[0] / nprof for k, v in sorted(prof.items())},
