@@ -147,6 +147,9 @@ struct afmg_handle {
   double* d_stage = nullptr;  // two halves: chunk c uses half c & 1 (copy of c + 1 overlaps the kernel of c)
   size_t stage_bytes = 0;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t side_stream = nullptr;  // the generic-stencil kernels of a level run beside the fast ones (fork / join)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t launch_stream = nullptr;  // where launch_k puts the next kernel (the solver stream unless forked)
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   int* d_stage_slots = nullptr;
   size_t stage_slots_n = 0;
@@ -368,7 +371,7 @@ void launch_k(afmg_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
-  cfg.stream = h->stream;
+  cfg.stream = h->launch_stream ? h->launch_stream : h->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -542,6 +545,27 @@ inline bool mega_route(afmg_handle* h, int nboxes, bool ok = true) {
   return false;
 }
 
+// Boxes with explicit stencils are handled by generic kernels next to the fast ones; the two touch disjoint boxes, so
+// inside a cycle they run concurrently: the generic launch goes to a side stream between a fork and a join event (in a
+// captured graph: two parallel branches).  On the launch-bound streamer trees this hides one of the two node
+// latencies per half-sweep (S2e, 597 of 8905 boxes with explicit stencils: 1.20 -> 0.95 ms per V-cycle, same bits).  Not in profiling mode, where every launch is timed on its own.
+struct SideLaunch {
+  afmg_handle* h;
+  bool on;
+  SideLaunch(afmg_handle* h_, bool want) : h(h_), on(want && !h_->profiling && h_->mega_mode != 1 && h_->side_stream) {
+    if (!on) return;
+    cudaEventRecord(h->ev_fork, h->stream);
+    cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0);
+  }
+  void begin() { if (on) h->launch_stream = h->side_stream; }
+  void end() {
+    if (!on) return;
+    h->launch_stream = nullptr;
+    cudaEventRecord(h->ev_join, h->side_stream);
+    cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+  }
+};
+
 // Cross-GPU barrier between dependent kernels (no-op on one GPU, where stream order suffices).
 // `multi` = the operation it follows involves a level whose boxes are spread over several ranks.  Operations on
 // levels that live entirely on rank 0 (the coarse grid and the small levels the partition does not split) need no
@@ -589,6 +613,7 @@ void enq_gsrb(afmg_handle* h, int l, int redblack) {
     mega_end_phase(h);
     return;
   }
+  SideLaunch side(h, r.n > 0 && nspec(h, l) > 0);
   if (r.n > 0) {
     Launch L_(h, "gsrb", l);
     DISPATCH_NC(h, NC, {
@@ -600,8 +625,12 @@ void enq_gsrb(afmg_handle* h, int l, int redblack) {
     });
   }
   if (const int ns = nspec(h, l)) {  // boxes with an explicit stencil (skipped by the kernel above)
-    Launch L_(h, "gsrb_gen", l);
-    DISPATCH_NC(h, NC, { launch_k(h, k_gsrb_gen<NC>, ns, 256, 0, h->cx, h->d_spec + h->spec_off[l], ns, redblack & 1); });
+    side.begin();
+    {
+      Launch L_(h, "gsrb_gen", l);
+      DISPATCH_NC(h, NC, { launch_k(h, k_gsrb_gen<NC>, ns, 256, 0, h->cx, h->d_spec + h->spec_off[l], ns, redblack & 1); });
+    }
+    side.end();
   }
   enq_barrier(h, lvl_multi(h, l));
 }
@@ -687,6 +716,7 @@ void enq_restrict(afmg_handle* h, int l, int keep_res, int rb_lvl = 0) {
     mega_end_phase(h);
     return;
   }
+  SideLaunch side(h, r.n > 0 && nspec(h, l) > 0);
   if (r.n > 0) {
     Launch L_(h, "restrict", l);
     DISPATCH_NC(h, NC, {
@@ -698,11 +728,15 @@ void enq_restrict(afmg_handle* h, int l, int keep_res, int rb_lvl = 0) {
     enq_rb_prepare(h, rb_lvl);
   }
   if (const int ns = nspec(h, l)) {
-    Launch L_(h, "restrict_gen", l);
-    DISPATCH_NC(h, NC, {
-      launch_k(h, k_resid_gen<NC, 1>, ns, 256, (size_t)2 * Lay3<NC>::NI * sizeof(double), 
-          h->cx, h->d_spec + h->spec_off[l], ns, nullptr, keep_res);
-    });
+    side.begin();
+    {
+      Launch L_(h, "restrict_gen", l);
+      DISPATCH_NC(h, NC, {
+        launch_k(h, k_resid_gen<NC, 1>, ns, 256, (size_t)2 * Lay3<NC>::NI * sizeof(double),
+            h->cx, h->d_spec + h->spec_off[l], ns, nullptr, keep_res);
+      });
+    }
+    side.end();
   }
   enq_barrier(h, multi);
 }
@@ -2041,6 +2075,9 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
     e = cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_consumed[b], cudaEventDisableTiming);
@@ -2142,6 +2179,9 @@ int afmg_destroy(afmg_handle* h) {
     if (h->ev_consumed[b]) cudaEventDestroy(h->ev_consumed[b]);
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   cudaStreamDestroy(h->stream);
   delete h;
   return AFMG_OK;

@@ -389,7 +389,10 @@ def run_gpu(args):
         return float(t.item())
 
     tree, bc, _, _, desc = build_workload(args.workload, want_rhs=False)
-    mg = M.mg_t(sides_bc=bc, device=local, comm=comm, lsf_boundary_value=1.0)
+    # --single-process: ONE process drives all GPUs (afmg_opts.n_gpus), the mode a single-process caller like the
+    # reference uses; launched without torchrun
+    sp_gpus = args.gpus if (args.single_process and world == 1) else 0
+    mg = M.mg_t(sides_bc=bc, device=local, comm=comm, lsf_boundary_value=1.0, n_gpus=sp_gpus)
     M.mg_init(tree, mg)
     explicit = None
     if args.workload == "S2e":
@@ -483,7 +486,7 @@ def run_gpu(args):
 
     # ---- the callers' next step, field_from_potential (src/m_field.f90:531-548), on the device (1 GPU) ------
     field = None
-    if world == 1 and tree.ndim == 3:
+    if world == 1 and tree.ndim == 3 and sp_gpus <= 1:
         M.field_from_potential(tree, mg, -1.0)  # allocates fc / norm
         reps = 3
         t0 = time.perf_counter()
@@ -573,7 +576,7 @@ def run_gpu(args):
     # and unpacks it into the boxes, (5) the same for i_tmp unless switched off (mg_gpu_set_download_tmp).  phi is not
     # uploaded: the device copy is current between solves.  Packing / unpacking = one host memcpy pass each.
     shim = None
-    if world == 1 and tree.ndim == 3:
+    if world == 1 and tree.ndim == 3 and sp_gpus <= 1:
         import ctypes as C
         from afivo_streamer_b200 import _lib
         Lb = _lib.lib()
@@ -636,6 +639,8 @@ def run_gpu(args):
     roof = None
     if g_calls and tree.ndim == 3:
         own = mg.own_boxes(tree.highest_lvl)   # finest-level boxes this rank sweeps per launch
+        if sp_gpus > 1:
+            own = int(np.count_nonzero(mg.owners(tree.lvl_ids[-1]) == 0))
         cells = own * tree.nc ** 3
         per_launch_bytes = layout_bytes_gsrb_per_box(tree.nc) * own
         dur = g_ms / g_calls * 1e-3
@@ -659,7 +664,7 @@ def run_gpu(args):
             try:
                 w = json.load(open(wpath)).get(args.workload)
                 if w:
-                    per_gpu = w["dram_bytes_per_vcycle"] / world
+                    per_gpu = w["dram_bytes_per_vcycle"] / max(world, sp_gpus)
                     cyc_s = ms_max / args.steps * 1e-3
                     whole.update({"dram_bytes_per_gpu": per_gpu, "dram_GBs_per_gpu": per_gpu / cyc_s / 1e9,
                                   "frac_per_gpu": per_gpu / cyc_s / 1e9 / peak, "source": w["source"]})
@@ -685,19 +690,21 @@ def run_gpu(args):
 
     # ---- CPU baseline on the host cores (rank 0, N=1 only): bounded sample ---------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and sp_gpus <= 1 and not args.no_cpu:
         cpu = cpu_baseline(args.workload)
 
 
     if rank == 0:
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": max(world, sp_gpus), "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "n_boxes": tree.n_boxes, "n_cell": tree.nc, "levels": tree.highest_lvl,
                        "cells_all_levels": tree.n_boxes * tree.nc ** 3,
                        "cells_finest": tree.n_cells_level(tree.highest_lvl), "step": "mg_fas_vcycle(set_residual=T)",
-                       "parallelism": "single GPU" if world == 1 else
+                       "parallelism": (f"ONE process, {sp_gpus} GPUs (afmg_opts.n_gpus): one host thread per GPU inside the library, "
+                                       "Morton partition, halos via NVLink peer memory") if sp_gpus > 1 else
+                       "single GPU" if world == 1 else
                        f"boxes partitioned over {world} GPUs by Morton ranges per level; halos via NVLink peer memory",
                        "l2_policy": f"working set {3 * tree.n_boxes * box_len * 8 / world / 1e6:.0f} MB per GPU "
                                     "(3 variables) exceeds the 126 MB L2; no flush needed"},
@@ -734,6 +741,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="S3")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--single-process", action="store_true",
+                    help="with --gpus N and no torchrun: one process drives N GPUs through afmg_opts.n_gpus")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
