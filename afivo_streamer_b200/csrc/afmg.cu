@@ -1775,7 +1775,24 @@ int finish_op(afmg_handle* h) {
 // device -> host copy of the records of a chunk, leaving the records of boxes this rank does not own (slot < 0)
 // untouched in the caller's buffer: with several rank handles in one process they all write into the same array
 cudaError_t copy_own_records(afmg_handle* h, double* hp, const double* dp, const int* slots, int m, size_t rec_len,
-                                    cudaStream_t st) {
+                                    cudaStream_t st, bool to_device = false) {
+  if (to_device) {  // host -> device: only the records of boxes this rank owns travel (the others are skipped by the
+                    // unpack kernel anyway; with N rank handles in one process each moves 1/N of the buffer)
+    if (h->nranks == 1) return cudaMemcpyAsync(const_cast<double*>(dp), hp, (size_t)m * rec_len * sizeof(double), cudaMemcpyHostToDevice, st);
+    int q = 0;
+    while (q < m) {
+      while (q < m && slots[q] < 0) ++q;
+      int e = q;
+      while (e < m && slots[e] >= 0) ++e;
+      if (e > q) {
+        cudaError_t rc = cudaMemcpyAsync(const_cast<double*>(dp) + (size_t)q * rec_len, hp + (size_t)q * rec_len,
+                                         (size_t)(e - q) * rec_len * sizeof(double), cudaMemcpyHostToDevice, st);
+        if (rc != cudaSuccess) return rc;
+      }
+      q = e;
+    }
+    return cudaSuccess;
+  }
   if (h->nranks == 1) return cudaMemcpyAsync(hp, dp, (size_t)m * rec_len * sizeof(double), cudaMemcpyDeviceToHost, st);
   int q = 0;
   while (q < m) {
@@ -2810,7 +2827,7 @@ static int transfer(afmg_handle* h, int var, int n, const int32_t* box_id, doubl
     if (up) {
       if (!device_ptr) {
         if (used[hb]) CK(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[hb], 0));
-        CK(cudaMemcpyAsync(dp, hp, (size_t)m * box_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        CK(copy_own_records(h, hp, dp, slots.data() + q0, m, rec_len, h->copy_stream, true));
         CK(cudaEventRecord(h->ev_copied[hb], h->copy_stream));
         CK(cudaStreamWaitEvent(h->stream, h->ev_copied[hb], 0));
       }
