@@ -14,7 +14,13 @@ namespace afmg2 {
 
 enum { V_PHI = 0, V_RHS = 1, V_TMP = 2 };
 
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// (AFMG_PDL=1).  launch_dependents first: the NEXT kernel of the stream / graph may be scheduled as soon as every CTA of
+// this one has started, so its launch latency overlaps with this kernel's execution; its own griddepcontrol.wait still
+// blocks until this grid has completed and flushed.  Both instructions are no-ops without the launch attribute.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 struct Ctx {
   double* cc[3];         // per variable: nslots * (nc+2)^2 doubles, box record = cc(0:nc+1, 0:nc+1)

@@ -78,7 +78,13 @@ struct DevCtx {
 // PTX helpers: mbarrier + 1D TMA bulk copy (cp.async.bulk -> SASS UBLKCP)
 // ---------------------------------------------------------------------------------------------
 // programmatic dependent launch: wait for the preceding grid (and its memory) before touching data
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// (AFMG_PDL=1).  launch_dependents first: the NEXT kernel of the stream / graph may be scheduled as soon as every CTA of
+// this one has started, so its launch latency overlaps with this kernel's execution; its own griddepcontrol.wait still
+// blocks until this grid has completed and flushed.  Both instructions are no-ops without the launch attribute.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
