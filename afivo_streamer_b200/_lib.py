@@ -127,6 +127,7 @@ SYMBOLS = {
     "afmg_max_abs": (C.c_int, [_H, _I, _DP]),
     "afmg_tree_sum": (C.c_int, [_H, _I, _DP]),
     "afmg_checksum": (C.c_int, [_H, _I, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "afmg_slab_bytes": (C.c_int, [_H, _I, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _IP]),
     "afmg_set_mega": (C.c_int, [_H, _I, _I]),
     "afmg_mega_active": (C.c_int32, [_H]),
     "afmg_kernel_launches": (C.c_int64, [_H]),

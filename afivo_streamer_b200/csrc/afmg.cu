@@ -5,6 +5,7 @@
 // :779-799, correct_children :624-646) as sequences of kernel launches on one stream, replayed as
 // CUDA graphs.  There is no CPU compute path: every cell-data operation is a kernel in
 // kernels3d.cuh.
+#include <cuda.h>  // driver API types only: the entry points are fetched through cudaGetDriverEntryPoint (no -lcuda)
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -199,6 +200,13 @@ struct afmg_handle {
   int slab_nvar = 3;
   char* peer_slab[AFMG_MAX_RANKS] = {};
   bool local_peers = false;  // the peers are rank handles of the same process (afmg_opts.n_gpus): no CUDA IPC
+  int dev_base = 0;          // first device of the single-process group
+  // slab trimmed to the owned boxes (single-process multi-GPU): a virtual range for the whole slot space, physical
+  // memory mapped only under the slots this rank owns (CUDA virtual memory management API)
+  bool slab_vmm = false;
+  size_t slab_va_size = 0, slab_mapped_bytes = 0;
+  std::vector<std::pair<size_t, size_t>> slab_maps;        // (offset, size) of the mapped pieces
+  std::vector<unsigned long long> slab_map_handles;        // CUmemGenericAllocationHandle of each piece
   unsigned long long barrier_timeout_ns = 30ull * 1000000000ull;
 
   // ---- persistent-kernel segments (mega.cuh)
@@ -1176,6 +1184,131 @@ void drop_graphs(afmg_handle* h) {
   h->graphs.clear();
 }
 
+// ---- slabs trimmed to the owned boxes ---------------------------------------------------------------------------
+// Every rank addresses a box as (owner's slab base) + slot * BOX, so all ranks share one slot space; but a rank only
+// ever touches its own records through its own base pointer (peers' records go through the peers' pointers).  With
+// the virtual memory management API the slot space is reserved as addresses only and physical memory is mapped under
+// the owned slot ranges (rounded to the 2 MB granularity): per-rank memory ~ 1 / N of the tree instead of all of it.
+// Used by the single-process multi-GPU mode (afmg_opts.n_gpus), where peer access is a cuMemSetAccess away; the
+// multi-process mode keeps cudaMalloc + CUDA IPC (sharing VMM allocations across processes needs file-descriptor
+// passing).  AFMG_TRIM_SLABS=0 switches it off.
+struct VmmApi {
+  CUresult (*GetGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  CUresult (*AddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*Create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  bool ok = false;
+};
+const VmmApi& vmm_api() {
+  static VmmApi api = [] {
+    VmmApi a;
+    auto get = [](const char* name, void** fn) {
+      cudaDriverEntryPointQueryResult q;
+      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+    };
+    a.ok = get("cuMemGetAllocationGranularity", (void**)&a.GetGranularity) && get("cuMemAddressReserve", (void**)&a.AddressReserve) &&
+           get("cuMemAddressFree", (void**)&a.AddressFree) && get("cuMemCreate", (void**)&a.Create) &&
+           get("cuMemRelease", (void**)&a.Release) && get("cuMemMap", (void**)&a.Map) && get("cuMemUnmap", (void**)&a.Unmap) &&
+           get("cuMemSetAccess", (void**)&a.SetAccess);
+    cudaGetLastError();
+    return a;
+  }();
+  return api;
+}
+
+void slab_free(afmg_handle* h) {
+  if (!h->d_slab) return;
+  if (h->slab_vmm) {
+    const VmmApi& a = vmm_api();
+    for (size_t q = 0; q < h->slab_maps.size(); ++q) {
+      a.Unmap((CUdeviceptr)(h->d_slab + h->slab_maps[q].first), h->slab_maps[q].second);
+      a.Release((CUmemGenericAllocationHandle)h->slab_map_handles[q]);
+    }
+    a.AddressFree((CUdeviceptr)h->d_slab, h->slab_va_size);
+    h->slab_maps.clear();
+    h->slab_map_handles.clear();
+    h->slab_vmm = false;
+  } else {
+    cudaFree(h->d_slab);
+  }
+  h->d_slab = nullptr;
+  h->slab_mapped_bytes = 0;
+}
+
+// byte ranges of the slab that hold this rank's records (per variable and level) plus the box-sum table
+std::vector<std::pair<size_t, size_t>> slab_owned_ranges(const afmg_handle* h) {
+  std::vector<std::pair<size_t, size_t>> r;
+  const size_t rec = (size_t)h->box_len * sizeof(double);
+  for (int v = 0; v < h->slab_nvar; ++v)
+    for (int l = 1; l <= h->L; ++l) {
+      const int* c = &h->cut[(size_t)l * (h->nranks + 1)];
+      if (c[h->me + 1] > c[h->me]) r.emplace_back(v * h->slab_var_stride + (size_t)c[h->me] * rec, (size_t)(c[h->me + 1] - c[h->me]) * rec);
+    }
+  r.emplace_back(h->slab_nvar * h->slab_var_stride, (size_t)h->nslots * sizeof(double));
+  return r;
+}
+
+int slab_alloc(afmg_handle* h) {
+  slab_free(h);
+  bool trim = h->local_peers && h->nranks > 1 && vmm_api().ok;
+  if (const char* env = getenv("AFMG_TRIM_SLABS")) trim = trim && atoi(env) != 0;
+  if (!trim) {
+    CK(cudaMalloc((void**)&h->d_slab, h->slab_bytes));
+    CK(cudaMemset(h->d_slab, 0, h->slab_bytes));
+    h->slab_mapped_bytes = h->slab_bytes;
+    return AFMG_OK;
+  }
+  const VmmApi& a = vmm_api();
+  CUmemAllocationProp prop = {};
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = h->device;
+  size_t g = 0;
+  if (a.GetGranularity(&g, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || g == 0)
+    return h->fail(AFMG_ERR_CUDA, "cuMemGetAllocationGranularity failed");
+  auto up = [g](size_t x) { return (x + g - 1) / g * g; };
+  h->slab_va_size = up(h->slab_bytes);
+  CUdeviceptr va = 0;
+  if (a.AddressReserve(&va, h->slab_va_size, g, 0, 0) != CUDA_SUCCESS) return h->fail(AFMG_ERR_CUDA, "cuMemAddressReserve(%zu) failed", h->slab_va_size);
+  h->d_slab = (char*)va;
+  h->slab_vmm = true;
+  // owned ranges, rounded outward to the granularity and merged
+  auto own = slab_owned_ranges(h);
+  std::vector<std::pair<size_t, size_t>> pieces;
+  for (auto& r : own) pieces.emplace_back(r.first / g * g, up(r.first + r.second));  // [begin, end)
+  std::sort(pieces.begin(), pieces.end());
+  std::vector<std::pair<size_t, size_t>> merged;
+  for (auto& p : pieces) {
+    if (!merged.empty() && p.first <= merged.back().second) merged.back().second = std::max(merged.back().second, p.second);
+    else merged.push_back(p);
+  }
+  std::vector<CUmemAccessDesc> acc(h->nranks);
+  for (int r = 0; r < h->nranks; ++r) {
+    acc[r].location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc[r].location.id = h->dev_base + r;
+    acc[r].flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  }
+  for (auto& m : merged) {
+    const size_t off = m.first, size = m.second - m.first;
+    CUmemGenericAllocationHandle mh;
+    if (a.Create(&mh, size, &prop, 0) != CUDA_SUCCESS) return h->fail(AFMG_ERR_CUDA, "cuMemCreate(%zu bytes) failed (out of device memory?)", size);
+    if (a.Map(va + off, size, 0, mh, 0) != CUDA_SUCCESS) {
+      a.Release(mh);
+      return h->fail(AFMG_ERR_CUDA, "cuMemMap failed");
+    }
+    h->slab_maps.emplace_back(off, size);
+    h->slab_map_handles.push_back((unsigned long long)mh);
+    if (a.SetAccess(va + off, size, acc.data(), acc.size()) != CUDA_SUCCESS) return h->fail(AFMG_ERR_CUDA, "cuMemSetAccess failed (peer access between the GPUs?)");
+    CK(cudaMemset(h->d_slab + off, 0, size));
+    h->slab_mapped_bytes += size;
+  }
+  return AFMG_OK;
+}
+
 // coarse_solver_initialize (m_coarse_solver.f90:71-194) + stencil_handle_boundaries (:442-491), with the
 // Hypre solve replaced by the eigen-decomposition of the separable BC-folded operator
 // reference layout v(ncf, i, j, k) -> device planes [m][colour][iidx]
@@ -2030,6 +2163,7 @@ static int create_multi(afmg_handle** out, const afmg_opts* opts, int ng, int nd
       return rc;
     }
     sub->local_peers = true;
+    sub->dev_base = base;
     h->subs.push_back(sub);
   }
   for (int r = 0; r < ng; ++r) {
@@ -2160,7 +2294,7 @@ int afmg_destroy(afmg_handle* h) {
   s2_free(h);
   fs_free(h);
   close_peers(h);
-  cudaFree(h->d_slab);
+  slab_free(h);
   cudaFree(h->d_owner);
   cudaFree(h->d_opk);
   cudaFree(h->d_pk);
@@ -2365,20 +2499,12 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
   if ((rc = dev_upload(h, &h->d_rule_B, rule_B))) return rc;
   // one slab per rank: phi | rhs | tmp | box sums (a single CUDA IPC handle covers all of it)
   close_peers(h);
-  if (h->d_slab) cudaFree(h->d_slab);
-  h->d_slab = nullptr;
+  slab_free(h);
   h->slab_var_stride = (((size_t)total * h->box_len * sizeof(double)) + 255) / 256 * 256;
   // multi-GPU: the field norm lives in the slab too, so that the peers can read its halo (af_gc_tree of the norm);
   // on one GPU it is allocated on first use (afmg_field.inc)
   h->slab_nvar = (h->nranks > 1) ? 4 : 3;
   h->slab_bytes = h->slab_nvar * h->slab_var_stride + (size_t)total * sizeof(double);
-  CK(cudaMalloc((void**)&h->d_slab, h->slab_bytes));
-  CK(cudaMemset(h->d_slab, 0, h->slab_bytes));
-  for (int v = 0; v < 3; ++v) h->d_cc[v] = (double*)(h->d_slab + v * h->slab_var_stride);
-  h->d_cc[3] = nullptr;
-  h->d_cc[4] = (h->slab_nvar == 4) ? (double*)(h->d_slab + 3 * h->slab_var_stride) : nullptr;
-  h->d_boxsum = (double*)(h->d_slab + h->slab_nvar * h->slab_var_stride);
-  h->peer_slab[h->me] = h->d_slab;
 
   // ownership: contiguous Morton ranges per level, cut at sibling groups (afmg_partition)
   {
@@ -2407,6 +2533,13 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
       if (q != h->rb_lvl_off[l + 1]) return h->fail(AFMG_ERR_ARG, "internal: refinement-boundary faces not sorted by owner");
     }
     if ((rc = dev_upload(h, &h->d_owner, h->h_owner))) return rc;
+    // the slab: all of it on one GPU / in the multi-process mode, the owned slot ranges in the single-process mode
+    if ((rc = slab_alloc(h))) return rc;
+    for (int v = 0; v < 3; ++v) h->d_cc[v] = (double*)(h->d_slab + v * h->slab_var_stride);
+    h->d_cc[3] = nullptr;
+    h->d_cc[4] = (h->slab_nvar == 4) ? (double*)(h->d_slab + 3 * h->slab_var_stride) : nullptr;
+    h->d_boxsum = (double*)(h->d_slab + h->slab_nvar * h->slab_var_stride);
+    h->peer_slab[h->me] = h->d_slab;
     h->lvl_multi.assign(L + 2, 0);
     for (int l = 1; l <= L; ++l) {
       int owners = 0;
@@ -2973,8 +3106,16 @@ int afmg_clear(afmg_handle* h, int32_t var) {
   if (!h->have_tree) return h->fail(AFMG_ERR_STATE, "afmg_set_tree has not been called");
   if (var < 0 || var > 2) return h->fail(AFMG_ERR_ARG, "invalid variable %d", var);
   CK(cudaSetDevice(h->device));
-  CK(cudaMemsetAsync(h->o.ndim == 2 ? h->s2->cx.cc[var] : h->d_cc[var], 0, (size_t)h->nslots * h->box_len * sizeof(double),
-                     h->stream));
+  if (h->o.ndim == 3 && h->nranks > 1) {  // only the records this rank owns (the others may not even be mapped)
+    for (int l = 1; l <= h->L; ++l) {
+      const Range r = own(h, l);
+      if (r.n > 0)
+        CK(cudaMemsetAsync(h->d_cc[var] + (size_t)r.s0 * h->box_len, 0, (size_t)r.n * h->box_len * sizeof(double), h->stream));
+    }
+  } else {
+    CK(cudaMemsetAsync(h->o.ndim == 2 ? h->s2->cx.cc[var] : h->d_cc[var], 0, (size_t)h->nslots * h->box_len * sizeof(double),
+                       h->stream));
+  }
   h->resid_fresh = false;
   return finish_op(h);
 }
@@ -3338,6 +3479,18 @@ int afmg_set_mega(afmg_handle* h, int32_t enabled, int32_t max_boxes) {
   drop_graphs(h);  // the cached cycles were built for the previous setting
   h->mega_enabled = enabled != 0;
   h->mega_max_boxes = max_boxes > 0 ? max_boxes : 0;
+  return AFMG_OK;
+}
+
+// device memory of the cell-data slab per GPU: bytes physically mapped and bytes of the full slot space
+int afmg_slab_bytes(afmg_handle* h, int32_t cap, int64_t* mapped, int64_t* full, int32_t* n) {
+  if (!h || !n) return AFMG_ERR_ARG;
+  std::vector<afmg_handle*> hs = h->is_multi ? h->subs : std::vector<afmg_handle*>{h};
+  *n = (int32_t)hs.size();
+  for (int r = 0; r < (int)hs.size() && r < cap; ++r) {
+    if (mapped) mapped[r] = (int64_t)hs[r]->slab_mapped_bytes;
+    if (full) full[r] = (int64_t)hs[r]->slab_bytes;
+  }
   return AFMG_OK;
 }
 

@@ -353,6 +353,13 @@ class mg_t:
         self._check(_lib.lib().afmg_checksum(self._h, var, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
+    def slab_bytes(self):
+        """(mapped, full) bytes of the cell-data slab per GPU of this handle (afmg_slab_bytes)"""
+        a, b = (C.c_int64 * 8)(), (C.c_int64 * 8)()
+        n = C.c_int32(0)
+        self._check(_lib.lib().afmg_slab_bytes(self._h, 8, a, b, C.byref(n)))
+        return np.array(a[:n.value]), np.array(b[:n.value])
+
     def set_mega(self, enabled=True, max_boxes=0):
         """persistent-kernel segments on / off (afmg_set_mega); max_boxes = 0: the default level-size limit"""
         self._check(_lib.lib().afmg_set_mega(self._h, int(enabled), int(max_boxes)))

@@ -718,6 +718,7 @@ def run_gpu(args):
                        f"boxes partitioned over {world} GPUs by Morton ranges per level; halos via NVLink peer memory",
                        "l2_policy": f"working set {3 * tree.n_boxes * box_len * 8 / world / 1e6:.0f} MB per GPU "
                                     "(3 variables) exceeds the 126 MB L2; no flush needed"},
+            "slab_GB_per_gpu": {"mapped": (mg.slab_bytes()[0] / 1e9).round(2).tolist(), "full_slot_space": float(mg.slab_bytes()[1][0] / 1e9)},
             "vcycles_per_s": args.steps / (ms_max * 1e-3),
             "fmg": {"ms": fmg_ms, "cell_updates_per_s": cu_fmg / (fmg_ms * 1e-3)},
             "field_from_potential": field,

@@ -406,6 +406,11 @@ int afmg_last_cycle_ms(afmg_handle* h, double* ms);
  * instead of one launch each -- the launch-bound regime of the streamer trees (nc = 8, many small levels).  Results are
  * bit-identical to the launch path.  On by default for 3D, single-GPU handles without explicit stencils; AFMG_MEGA=0
  * or enabled = 0 selects the launch path.  afmg_mega_active: number of CTAs of the persistent kernel, 0 = not used. */
+/* Device memory of the cell-data slab (phi, rhs, tmp [, field norm]) per GPU of the handle: bytes physically mapped and
+ * bytes of the full slot space.  A single-process multi-GPU handle (afmg_opts.n_gpus) reserves the slot space as
+ * virtual addresses and maps memory only under the boxes each GPU owns (~ 1 / N of the tree per GPU, so a tree larger
+ * than one GPU's memory can be partitioned); single-GPU and multi-process handles map all of it. */
+int afmg_slab_bytes(afmg_handle* h, int32_t cap, int64_t* mapped, int64_t* full, int32_t* n);
 int afmg_set_mega(afmg_handle* h, int32_t enabled, int32_t max_boxes);
 int32_t afmg_mega_active(const afmg_handle* h);
 int afmg_set_profiling(afmg_handle* h, int32_t on);

@@ -100,6 +100,32 @@ def test_one_process_two_gpus_helmholtz_modes():
     assert np.array_equal(res[0][2], res[1][2]) and np.abs(res[1][2]).max() > 0
 
 
+@needs2
+def test_each_gpu_maps_only_the_boxes_it_owns():
+    """the slot space is reserved as virtual addresses; physical memory sits under the owned slot ranges only, so two
+    GPUs hold about half of the 256^3 tree each (2 MB granularity) -- and still solve it bit-identically"""
+    tree = T.uniform_tree(3, 16, 16, 5)
+    bc = W.bc_dirichlet_zero(tree)
+    ids, rhs = W.constant_rhs_on_leaves(tree, 1.0)
+    out = []
+    for ng in (0, 2):
+        mg = M.mg_t(sides_bc=bc, n_gpus=ng, device=0)
+        M.mg_init(tree, mg)
+        mapped, full = mg.slab_bytes()
+        if ng == 2:
+            assert len(mapped) == 2 and np.all(mapped < 0.62 * full), (mapped, full)
+            assert mapped.sum() < 1.1 * full[0]
+        else:
+            assert mapped[0] == full[0]
+        mg.set_cc(M.I_RHS, ids, rhs)
+        M.mg_fas_fmg(tree, mg, True, False)
+        M.mg_fas_vcycle(tree, mg, True)
+        out.append((M.af_tree_maxabs_cc(tree, mg, M.I_TMP), mg.checksum(M.I_PHI)))
+        mg.clear(M.I_TMP)  # afmg_clear touches the owned records only
+        M.mg_destroy(mg)
+    assert out[0] == out[1]
+
+
 def test_n_gpus_beyond_the_visible_devices_is_an_error_not_a_fallback():
     tree = T.uniform_tree(3, 8, 8, 2)
     mg = M.mg_t(sides_bc=W.bc_dirichlet_zero(tree), n_gpus=n_devices() + 1 if n_devices() < 8 else 9, device=0)
