@@ -2212,7 +2212,7 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
   }
   {
     int ng = opts->n_gpus;
-    if (ng == 0)
+    if (ng == 0 && opts->ndim == 3)  // the environment only steers 3D handles (the 2D path runs on one GPU)
       if (const char* env = getenv("AFMG_N_GPUS")) ng = atoi(env);
     if (ng > 1) return create_multi(out, opts, ng, ndev);
   }
