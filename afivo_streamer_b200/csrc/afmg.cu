@@ -236,6 +236,9 @@ struct afmg_handle {
   int64_t launches = 0;
   bool profiling = false;
   bool pdl = false;  // programmatic dependent launch (launch_k), AFMG_PDL=1
+  bool gsrb_fused_gen = false;  // AFMG_GSRB_FUSED_GEN=1: levels with explicit-stencil boxes take ONE fused half-sweep launch
+                                // (k_gsrb2g) instead of a fast and a generic one side by side; measured slower (S2e: 1.06 vs
+                                // 0.95 ms per V-cycle: 80 registers and per-cell coefficient loads on the critical path)
   bool cs_fused = true;  // single-CTA coarse solve for small separable coarse grids (AFMG_CS_FUSED=0: off)
   std::map<std::string, ProfEntry> prof;
   std::vector<std::tuple<std::string, cudaEvent_t, cudaEvent_t>> prof_pending;
@@ -621,6 +624,18 @@ void enq_gsrb(afmg_handle* h, int l, int redblack) {
     mega_end_phase(h);
     return;
   }
+  if (r.n > 0 && nspec(h, l) > 0 && h->gsrb_fused_gen) {
+    // the level holds boxes with explicit stencils: one launch sweeps all of its boxes (k_gsrb2g)
+    Launch L_(h, "gsrb", l);
+    DISPATCH_NC(h, NC, {
+      using G = Gsrb2Cfg<NC>;
+      constexpr int threads = G::BPC * G::KS * NC * NC / 2;
+      const size_t smem = (size_t)G::BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double);
+      launch_k(h, k_gsrb2g<NC, G::BPC, G::KS>, (r.n + G::BPC - 1) / G::BPC, threads, smem, h->cx, r.s0, r.n, redblack & 1, l);
+    });
+    enq_barrier(h, lvl_multi(h, l));
+    return;
+  }
   SideLaunch side(h, r.n > 0 && nspec(h, l) > 0);
   if (r.n > 0) {
     Launch L_(h, "gsrb", l);
@@ -845,6 +860,7 @@ void configure_kernels(afmg_handle* h) {
   DISPATCH_NC(h, NC, {
     using G = Gsrb2Cfg<NC>;
     set_max_smem(k_gsrb2<NC, G::BPC, G::KS, G::MINB>, (size_t)G::BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double));
+    set_max_smem(k_gsrb2g<NC, G::BPC, G::KS>, (size_t)G::BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double));
     set_max_smem(k_resid3<NC, OpCfg<NC>::KS, 0, OpCfg<NC>::RES_MINB>, OpCfg<NC>::TILE);
     set_max_smem(k_resid3<NC, OpCfg<NC>::KS, 1, OpCfg<NC>::RES_MINB>, OpCfg<NC>::TILE);
     set_max_smem(k_gc2<NC>, OpCfg<NC>::TILE);
@@ -2246,6 +2262,7 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
   h->peers.p[0] = h->d_comm;
   if (const char* env = getenv("AFMG_PDL")) h->pdl = atoi(env) != 0;
   if (const char* env = getenv("AFMG_CS_FUSED")) h->cs_fused = atoi(env) != 0;
+  if (const char* env = getenv("AFMG_GSRB_FUSED_GEN")) h->gsrb_fused_gen = atoi(env) != 0;
   if (const char* env = getenv("AFMG_MIN_SPLIT_BOXES")) h->min_split_boxes = atoi(env);
   if (const char* env = getenv("AFMG_MEGA")) h->mega_enabled = atoi(env) != 0;
   if (const char* env = getenv("AFMG_MEGA_MAX_BOXES")) h->mega_max_boxes = atoi(env);

@@ -689,6 +689,122 @@ __global__ void __launch_bounds__(256) k_gsrb_gen(DevCtx cx, const int* list, in
   epilogue_faces<NC, 256, false>(cx, slot, gbox, gbox + COL, 1 << C, t);
 }
 
+// k_gsrb2g: the fused half-sweep of k_gsrb2 for a level that CONTAINS boxes with explicit stencils: every box of the
+// level goes through the same TMA-staged sweep; a box takes its coefficients from the level's constant Laplacian
+// (kind 0, the arithmetic of k_gsrb2), from its own 7 constants (kind 1) or per cell from its coefficient planes
+// (kind 2: `/ c(1)` as in stencil_gsrb_357, m_af_stencil.f90:974-990), with the bc_correction of level-set boxes
+// added to the right-hand side before and subtracted after the sweep on ALL cells as the reference does (:856-859,
+// :993-996; the rounding of (rhs + b) - b is reproduced and written back).  One launch per half-sweep instead of a
+// fast and a generic one (k_gsrb_gen, which stays as the unfused reference implementation): on the launch-bound
+// streamer trees the generic launch had cost as much as the fast one.  A box's threads are whole warps, so the kind
+// branch is warp-uniform.
+template <int NC, int BPC, int KS>
+__global__ void __launch_bounds__(BPC* KS* NC* NC / 2, 3) k_gsrb2g(DevCtx cx, int slot0, int nbox, int C, int lvl) {
+  pdl_wait();
+  using L = Lay3<NC>;
+  constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX;
+  constexpr int TPB = H * NC * KS, KL = NC / KS, SBOX = COL + NI;
+  extern __shared__ __align__(128) double smem[];
+  __shared__ uint64_t bar;
+  __shared__ FaceMeta fmeta[BPC];
+  const int tid = threadIdx.x;
+  const int box0 = blockIdx.x * BPC;
+  const int nhere = min(BPC, nbox - box0);
+  double* const phi = cx.cc[V_PHI];
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, (uint32_t)(nhere * SBOX * 8));
+    for (int b = 0; b < nhere; ++b) {
+      const size_t base = (size_t)(slot0 + box0 + b) * BOX;
+      bulk_g2s(smem + b * SBOX, phi + base + (1 - C) * COL, COL * 8, &bar);
+      bulk_g2s(smem + b * SBOX + COL, cx.cc[V_RHS] + base + C * COL, NI * 8, &bar);
+    }
+  }
+  const int b = tid / TPB, t = tid % TPB;
+  const bool active = b < nhere;
+  const int slot = slot0 + box0 + (active ? b : 0);
+  const double* const S = smem + b * SBOX;
+  double* const R = smem + b * SBOX + COL;
+  const double* cf = cx.coef + 8 * lvl;
+  const int kind = (active && cx.opk) ? cx.opk[slot] : 0;
+  const double* sv = kind ? cx.stv + cx.opoff[slot] : nullptr;
+  const double* fv = (kind && cx.foff[slot] >= 0) ? cx.stv + cx.foff[slot] : nullptr;
+  const double* bvp = fv ? cx.bv_of(slot) : nullptr;
+  double* const grhs = cx.cc[V_RHS] + (size_t)slot * BOX;
+  if (active && t < 6) prefetch_face_meta(cx, slot, &fmeta[b], t);
+  // constant kinds: coefficients once per thread (kind 0: the level's, with the stored reciprocal of c1)
+  const double* cc7 = kind == 1 ? sv : cf;
+  const double c2 = cc7[1], c3 = cc7[2], c4 = cc7[3], c5 = cc7[4], c6 = cc7[5], c7 = cc7[6];
+  const double inv = kind == 1 ? 1 / sv[0] : cf[7];
+  const double lsfv = fv ? cx.lsf_value() : 0.0;
+  mbar_wait(&bar, 0);
+  if (active) {
+    const int m = t % H, j = (t / H) % NC + 1, ks = t / (H * NC);
+    const int k0 = ks * KL + 1;
+    double s_km1 = (k0 == 1) ? S[NI + 4 * NF + (j - 1) * H + m] : S[L::iidx(m, j, k0 - 1)];
+    double s_k = S[L::iidx(m, j, k0)];
+#pragma unroll
+    for (int kk = 0; kk < KL; ++kk) {
+      const int k = k0 + kk;
+      const int idx = L::iidx(m, j, k);
+      const int pi = (C + j + k) & 1;
+      const double s_kp1 = (k < NC) ? S[idx + NC * H] : S[NI + 5 * NF + (j - 1) * H + m];
+      const double ym = (j > 1) ? S[idx - H] : S[NI + 2 * NF + (k - 1) * H + m];
+      const double yp = (j < NC) ? S[idx + H] : S[NI + 3 * NF + (k - 1) * H + m];
+      const int fx = (k - 1) * H + ((j - 1) >> 1);
+      double xm, xp;
+      if (pi) {
+        xm = (m > 0) ? S[idx - 1] : S[NI + 0 * NF + fx];
+        xp = s_k;
+      } else {
+        xm = s_k;
+        xp = (m < H - 1) ? S[idx + 1] : S[NI + 1 * NF + fx];
+      }
+      double r = R[idx], bc = 0.0;
+      if (fv) {
+        bc = fv[C * NI + idx] * (bvp ? bvp[C * NI + idx] : lsfv);
+        r = r + bc;
+      }
+      double acc = r;
+      if (kind == 2) {
+        const double* q = sv + (size_t)C * NI + idx;  // plane m of colour C: sv[(m * 2 + C) * NI + idx]
+        acc = acc - q[(size_t)2 * NI] * xm;
+        acc = acc - q[(size_t)4 * NI] * xp;
+        acc = acc - q[(size_t)6 * NI] * ym;
+        acc = acc - q[(size_t)8 * NI] * yp;
+        acc = acc - q[(size_t)10 * NI] * s_km1;
+        acc = acc - q[(size_t)12 * NI] * s_kp1;
+        R[idx] = acc / q[0];
+      } else {
+        acc = acc - c2 * xm;
+        acc = acc - c3 * xp;
+        acc = acc - c4 * ym;
+        acc = acc - c5 * yp;
+        acc = acc - c6 * s_km1;
+        acc = acc - c7 * s_kp1;
+        R[idx] = acc * inv;
+      }
+      if (fv) {  // rhs = (rhs + bc) - bc on both colours, like the reference's add-before / subtract-after
+        grhs[C * COL + idx] = r - bc;
+        const double bo = fv[(1 - C) * NI + idx] * (bvp ? bvp[(1 - C) * NI + idx] : lsfv);
+        const double ro = grhs[(1 - C) * COL + idx];
+        grhs[(1 - C) * COL + idx] = (ro + bo) - bo;
+      }
+      s_km1 = s_k;
+      s_k = s_kp1;
+    }
+  }
+  fence_async_smem();
+  __syncthreads();
+  if (active) {
+    if (t == 0) bulk_s2g(phi + (size_t)slot * BOX + C * COL, R, NI * 8);
+    epilogue_faces<NC, TPB>(cx, slot, C ? S : R, C ? R : S, 1 << C, t, &fmeta[b]);
+    if (t == 0) bulk_commit();
+    if (t == 0) bulk_wait_read0();
+  }
+}
+
 // k_resid_gen: residual_box (MODE 0, + leaf max-norm) or the child part of update_coarse /
 // set_coarse_phi_rhs (MODE 1) for the listed boxes, any stencil kind.  One thread per fine cell; for
 // MODE 1 the residuals go through shared memory and one thread per coarse cell adds the 2x2x2 values in

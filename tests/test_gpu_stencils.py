@@ -192,6 +192,23 @@ def test_cycles_match_oracle(name):
     M.mg_destroy(mg)
 
 
+@pytest.mark.parametrize("name", ["eps_lsf_corner_nc8", "lsf_sphere_uniform_nc8", "eps_smooth_uniform_nc16"])
+def test_fused_generic_halfsweep_bit_exact(name, monkeypatch):
+    """AFMG_GSRB_FUSED_GEN=1: k_gsrb2g sweeps all boxes of a level that holds explicit-stencil boxes in one launch
+    (opt-in: measured slower than the two launches side by side); same bits as the oracle"""
+    monkeypatch.setenv("AFMG_GSRB_FUSED_GEN", "1")
+    mk, kw = CASES[name]
+    tree = mk()
+    orc, mg, _ = make_pair(tree, **kw)
+    fill_all_ghosts(tree, orc, mg)
+    for lvl in range(tree.highest_lvl, 1, -1):
+        for cyc in (M.MG_CYCLE_DOWN, M.MG_CYCLE_UP):
+            orc.gsrb_boxes(lvl, cyc)
+            mg.gsrb_boxes(lvl, cyc)
+            assert_same_state(tree, orc, mg)
+    M.mg_destroy(mg)
+
+
 def test_lsf_boundary_value_can_change():
     tree = T.uniform_tree(3, 8, 8, 3)
     orc, mg, _ = make_pair(tree, lsf=lsf_sphere, lsf_boundary_value=1.0)
