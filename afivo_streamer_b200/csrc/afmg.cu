@@ -239,6 +239,9 @@ struct afmg_handle {
   bool gsrb_fused_gen = false;  // AFMG_GSRB_FUSED_GEN=1: levels with explicit-stencil boxes take ONE fused half-sweep launch
                                 // (k_gsrb2g) instead of a fast and a generic one side by side; measured slower (S2e: 1.06 vs
                                 // 0.95 ms per V-cycle: 80 registers and per-cell coefficient loads on the critical path)
+  int n_sm = 148;
+  bool gsrb_wide = true;  // AFMG_GSRB_WIDE=0: never use the 8-boxes-per-CTA half-sweep (gsrb_one_wave)
+  int small_ctas = 148;  // launches of at most this many CTAs take the latency-optimised kernel variants (AFMG_SMALL_CTAS)
   bool cs_fused = true;  // single-CTA coarse solve for small separable coarse grids (AFMG_CS_FUSED=0: off)
   std::map<std::string, ProfEntry> prof;
   std::vector<std::tuple<std::string, cudaEvent_t, cudaEvent_t>> prof_pending;
@@ -439,6 +442,7 @@ inline int mega_items(const afmg_handle* h, int kind) {
     case MK_EC: return big ? MegaCfg<16>::EC_PER : MegaCfg<8>::EC_PER;
     case MK_RESTRICT:
     case MK_RESID: return big ? MegaCfg<16>::RES_PER : MegaCfg<8>::RES_PER;
+    case MK_CORRECT: return big ? Correct3Cfg<16>::BPC : Correct3Cfg<8>::BPC;
     default: return 1;
   }
 }
@@ -614,6 +618,45 @@ void set_max_smem(K kernel, size_t smem) {
 
 inline int nspec(const afmg_handle* h, int l) { return h->have_stencils ? h->spec_off[l + 1] - h->spec_off[l] : 0; }
 
+// k_gsrb2s exists for 8^3 and 16^3 boxes; blocks < 0: only opt in to its shared memory size (configure_kernels)
+template <int NC>
+bool gsrb_small(afmg_handle* h, int blocks, int threads, size_t smem, int s0, int n, int C, int l) {
+  if constexpr (NC == 8 || NC == 16) {
+    using G = Gsrb2Cfg<NC>;
+    if (blocks < 0) {
+      set_max_smem(k_gsrb2s<NC, G::BPC, G::KS>, smem);
+      return true;
+    }
+    if (blocks <= h->small_ctas) {
+      launch_k(h, k_gsrb2s<NC, G::BPC, G::KS>, blocks, threads, smem, h->cx, s0, n, C, l);
+      return true;
+    }
+  }
+  return false;
+}
+
+// 8^3 boxes: k_gsrb2<8, 4, 2> keeps 6 CTAs of 4 boxes per SM = 3552 boxes in flight on 148 SMs.  A level slightly
+// larger than that (the finest level of a streamer tree: 3904 boxes) takes a second, nearly empty wave at full
+// latency.  k_gsrb2<8, 8, 1> (32 threads per box, 8 boxes per CTA, 5 CTAs per SM by shared memory = 5920 boxes) does
+// such a level in one wave.
+template <int NC>
+bool gsrb_one_wave(afmg_handle* h, int blocks, int s0, int n, int C, int l) {
+  if constexpr (NC == 8) {
+    constexpr int BPC = 8, KS = 1, MINB = 5;
+    const size_t smem = (size_t)BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double);
+    if (blocks < 0) {
+      set_max_smem(k_gsrb2<NC, BPC, KS, MINB>, smem);
+      return true;
+    }
+    const int cap = h->n_sm * Gsrb2Cfg<NC>::MINB;
+    if (h->gsrb_wide && blocks > cap && (n + BPC - 1) / BPC <= h->n_sm * MINB) {
+      launch_k(h, k_gsrb2<NC, BPC, KS, MINB>, (n + BPC - 1) / BPC, BPC * KS * NC * NC / 2, smem, h->cx, s0, n, C, l);
+      return true;
+    }
+  }
+  return false;
+}
+
 // Every enq_* below works on the slots of a level this rank owns and ends with a cross-GPU barrier
 // when its results are read, or its inputs overwritten, by kernels of other ranks.
 void enq_gsrb(afmg_handle* h, int l, int redblack) {
@@ -643,8 +686,14 @@ void enq_gsrb(afmg_handle* h, int l, int redblack) {
       using G = Gsrb2Cfg<NC>;
       constexpr int threads = G::BPC * G::KS * NC * NC / 2;
       const size_t smem = (size_t)G::BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double);
-      auto kern = k_gsrb2<NC, G::BPC, G::KS, G::MINB>;
-      launch_k(h, kern, (r.n + G::BPC - 1) / G::BPC, threads, smem, h->cx, r.s0, r.n, redblack & 1, l);
+      const int blocks = (r.n + G::BPC - 1) / G::BPC;
+      // latency-bound launch: the variant with plain loads / stores (k_gsrb2s); a launch just above one wave of
+      // resident CTAs: half as many CTAs with twice the boxes each (one wave instead of two)
+      if (!gsrb_small<NC>(h, blocks, threads, smem, r.s0, r.n, redblack & 1, l) &&
+          !gsrb_one_wave<NC>(h, blocks, r.s0, r.n, redblack & 1, l)) {
+        auto kern = k_gsrb2<NC, G::BPC, G::KS, G::MINB>;
+        launch_k(h, kern, blocks, threads, smem, h->cx, r.s0, r.n, redblack & 1, l);
+      }
     });
   }
   if (const int ns = nspec(h, l)) {  // boxes with an explicit stencil (skipped by the kernel above)
@@ -778,9 +827,9 @@ void enq_correct(afmg_handle* h, int lp, bool store_corr, bool push) {
   } else if (rc.n > 0) {
     Launch L_(h, "correct", lp);
     DISPATCH_NC(h, NC, {
-      constexpr int W = NC / 2 + 2;
-      const size_t smem = (size_t)(2 * Lay3<NC>::NI + W * W * W) * sizeof(double);
-      launch_k(h, k_correct3<NC>, rc.n, 256, smem, h->cx, rc.s0, rc.n, push ? 1 : 0);
+      using CC = Correct3Cfg<NC>;
+      const size_t smem = (size_t)CC::BPC * CC::SB * sizeof(double);
+      launch_k(h, k_correct3<NC>, (rc.n + CC::BPC - 1) / CC::BPC, 256, smem, h->cx, rc.s0, rc.n, push ? 1 : 0);
     });
   }
   enq_barrier(h, multi);  // all children have read the old tmp of their parents
@@ -861,10 +910,12 @@ void configure_kernels(afmg_handle* h) {
     using G = Gsrb2Cfg<NC>;
     set_max_smem(k_gsrb2<NC, G::BPC, G::KS, G::MINB>, (size_t)G::BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double));
     set_max_smem(k_gsrb2g<NC, G::BPC, G::KS>, (size_t)G::BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double));
+    gsrb_small<NC>(h, -1, 0, (size_t)G::BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double), 0, 0, 0, 0);
+    gsrb_one_wave<NC>(h, -1, 0, 0, 0, 0);
     set_max_smem(k_resid3<NC, OpCfg<NC>::KS, 0, OpCfg<NC>::RES_MINB>, OpCfg<NC>::TILE);
     set_max_smem(k_resid3<NC, OpCfg<NC>::KS, 1, OpCfg<NC>::RES_MINB>, OpCfg<NC>::TILE);
     set_max_smem(k_gc2<NC>, OpCfg<NC>::TILE);
-    set_max_smem(k_correct3<NC>, (size_t)(2 * Lay3<NC>::NI + (NC / 2 + 2) * (NC / 2 + 2) * (NC / 2 + 2)) * sizeof(double));
+    set_max_smem(k_correct3<NC>, (size_t)Correct3Cfg<NC>::BPC * Correct3Cfg<NC>::SB * sizeof(double));
   });
   // persistent kernel: grid = what is co-resident on this device (cooperative launch)
   h->mega_grid = 0;
@@ -2262,6 +2313,9 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
   h->peers.p[0] = h->d_comm;
   if (const char* env = getenv("AFMG_PDL")) h->pdl = atoi(env) != 0;
   if (const char* env = getenv("AFMG_CS_FUSED")) h->cs_fused = atoi(env) != 0;
+  if (const char* env = getenv("AFMG_SMALL_CTAS")) h->small_ctas = atoi(env);
+  if (const char* env = getenv("AFMG_GSRB_WIDE")) h->gsrb_wide = atoi(env) != 0;
+  cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device);
   if (const char* env = getenv("AFMG_GSRB_FUSED_GEN")) h->gsrb_fused_gen = atoi(env) != 0;
   if (const char* env = getenv("AFMG_MIN_SPLIT_BOXES")) h->min_split_boxes = atoi(env);
   if (const char* env = getenv("AFMG_MEGA")) h->mega_enabled = atoi(env) != 0;

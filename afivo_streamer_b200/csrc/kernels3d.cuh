@@ -390,6 +390,148 @@ __device__ __forceinline__ void gsrb2_vblock(const DevCtx& cx, int slot0, int nb
   }
 }
 
+// k_gsrb2s: the same half-sweep for SMALL launches (levels of a few hundred boxes, where a kernel is a chain of
+// dependent latencies and not a bandwidth problem; a dependent graph node costs ~1 us on this part,
+// profiles/r02q_graphnode.txt, so the rest of a ~6 us node is the kernel's own critical path).  Differences to k_gsrb2,
+// none of them in the arithmetic: the box data arrives by plain 16-byte loads issued by all threads at once instead
+// of TMA bulk copies behind an mbarrier (lower latency for a few KB), the boundary values of the rule faces (rule_B)
+// are fetched into registers while the box data is in flight instead of after the sweep, and results leave by plain
+// stores (no bulk-group wait at the end).  Used when the launch has at most SMALL_CTAS blocks.
+template <int NC, int BPC, int KS>
+__global__ void __launch_bounds__(BPC* KS* NC* NC / 2, 2) k_gsrb2s(DevCtx cx, int slot0, int nbox, int C, int lvl) {
+  pdl_wait();
+  using L = Lay3<NC>;
+  constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL, BOX = L::BOX;
+  constexpr int TPB = H * NC * KS, KL = NC / KS, SBOX = COL + NI;
+  static_assert(L::NC2 == TPB, "one rule-face cell per thread");
+  extern __shared__ __align__(128) double smem[];
+  const int tid = threadIdx.x;
+  const int box0 = blockIdx.x * BPC;
+  const int nhere = min(BPC, nbox - box0);
+  const int b = tid / TPB, t = tid % TPB;
+  const int slot = slot0 + box0 + (b < nhere ? b : 0);
+  const bool active = b < nhere && !(cx.opk && cx.opk[slot]);
+  double* const S = smem + b * SBOX;
+  double* const R = S + COL;
+  double* const gphi = cx.cc[V_PHI] + (size_t)slot * BOX;
+  // ---- everything this block needs from global memory, issued back to back
+  if (active) {
+    const double2* src = reinterpret_cast<const double2*>(gphi + (1 - C) * COL);
+    double2* dst = reinterpret_cast<double2*>(S);
+#pragma unroll
+    for (int q = t; q < COL / 2; q += TPB) dst[q] = src[q];
+    const double2* rsrc = reinterpret_cast<const double2*>(cx.cc[V_RHS] + (size_t)slot * BOX + C * COL);
+    double2* rdst = reinterpret_cast<double2*>(R);
+#pragma unroll
+    for (int q = t; q < NI / 2; q += TPB) rdst[q] = rsrc[q];
+  }
+  const double* cf = cx.coef + 8 * lvl;
+  const double c2 = cf[1], c3 = cf[2], c4 = cf[3], c5 = cf[4], c6 = cf[5], c7 = cf[6], inv = cf[7];
+  int nbf[6], rowf[6];
+  double Bpre[6], rc0[6], rc1[6], rc2[6];
+#pragma unroll
+  for (int f = 0; f < 6; ++f) {
+    nbf[f] = active ? cx.nbr[slot * 6 + f] : 0;
+    rowf[f] = active ? cx.aux[slot * 6 + f] : 0;
+  }
+#pragma unroll
+  for (int f = 0; f < 6; ++f) {
+    Bpre[f] = rc0[f] = rc1[f] = rc2[f] = 0.0;
+    if (active && nbf[f] < 0) {
+      Bpre[f] = cx.rule_B[(size_t)rowf[f] * L::NC2 + t];
+      rc0[f] = cx.rule_c[3 * rowf[f]];
+      rc1[f] = cx.rule_c[3 * rowf[f] + 1];
+      rc2[f] = cx.rule_c[3 * rowf[f] + 2];
+    }
+  }
+  __syncthreads();
+  if (active) {
+    const int m = t % H, j = (t / H) % NC + 1, ks = t / (H * NC);
+    const int k0 = ks * KL + 1;
+    double s_km1 = (k0 == 1) ? S[NI + 4 * NF + (j - 1) * H + m] : S[L::iidx(m, j, k0 - 1)];
+    double s_k = S[L::iidx(m, j, k0)];
+#pragma unroll
+    for (int kk = 0; kk < KL; ++kk) {
+      const int k = k0 + kk;
+      const int idx = L::iidx(m, j, k);
+      const int pi = (C + j + k) & 1;
+      const double s_kp1 = (k < NC) ? S[idx + NC * H] : S[NI + 5 * NF + (j - 1) * H + m];
+      const double ym = (j > 1) ? S[idx - H] : S[NI + 2 * NF + (k - 1) * H + m];
+      const double yp = (j < NC) ? S[idx + H] : S[NI + 3 * NF + (k - 1) * H + m];
+      const int fx = (k - 1) * H + ((j - 1) >> 1);
+      double xm, xp;
+      if (pi) {
+        xm = (m > 0) ? S[idx - 1] : S[NI + 0 * NF + fx];
+        xp = s_k;
+      } else {
+        xm = s_k;
+        xp = (m < H - 1) ? S[idx + 1] : S[NI + 1 * NF + fx];
+      }
+      double acc = R[idx];
+      acc = acc - c2 * xm;
+      acc = acc - c3 * xp;
+      acc = acc - c4 * ym;
+      acc = acc - c5 * yp;
+      acc = acc - c6 * s_km1;
+      acc = acc - c7 * s_kp1;
+      R[idx] = acc * inv;
+      s_km1 = s_k;
+      s_k = s_kp1;
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  // ---- new colour-C values out: own interior, neighbours' ghost faces, own rule faces
+  {
+    const double2* src = reinterpret_cast<const double2*>(R);
+    double2* dst = reinterpret_cast<double2*>(gphi + C * COL);
+#pragma unroll
+    for (int q = t; q < NI / 2; q += TPB) dst[q] = src[q];
+  }
+  const double* I0 = C ? S : R;
+  const double* I1 = C ? R : S;
+  const double* Ic = R;
+#pragma unroll
+  for (int f = 0; f < 6; ++f) {
+    const int nb = nbf[f];
+    if (nb < 0) continue;
+    double* dstf = cx.at<BOX>(V_PHI, nb) + C * COL + NI + (f ^ 1) * NF;
+    for (int fi = t; fi < NF; fi += TPB) {
+      int src;
+      if (f >= 4) {
+        src = (f == 4 ? 0 : (NC - 1) * NC * H) + fi;
+      } else {
+        const int k = fi / H + 1, ah = fi % H;
+        if (f >= 2) {
+          src = L::iidx(ah, (f & 1) ? NC : 1, k);
+        } else {
+          const int i = (f & 1) ? NC : 1;
+          const int j = 2 * ah + 2 - ((C + i + k) & 1);
+          src = L::iidx((i - 1) >> 1, j, k);
+        }
+      }
+      dstf[fi] = Ic[src];
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < 6; ++f) {
+    if (nbf[f] >= 0) continue;
+    const int d = f >> 1, hi = f & 1;
+    const bool diag = cx.rule_flag && cx.rule_flag[rowf[f]];
+    const int n = t;
+    const int a = n % NC + 1, bb = n / NC + 1;
+    const int l1 = hi ? NC : 1, l2 = hi ? NC - 1 : 2;
+    const int a2 = diag ? a - 1 + 2 * (a & 1) : a, b2 = diag ? bb - 1 + 2 * (bb & 1) : bb;
+    const int px1 = (d == 0) ? l1 : a, py1 = (d == 0) ? a : (d == 1 ? l1 : bb), pz1 = (d == 2) ? l1 : bb;
+    const int px2 = (d == 0) ? l2 : a2, py2 = (d == 0) ? a2 : (d == 1 ? l2 : b2), pz2 = (d == 2) ? l2 : b2;
+    const int col1 = (px1 + py1 + pz1) & 1;
+    const int i1 = L::iidx((px1 - 1) >> 1, py1, pz1), i2 = L::iidx((px2 - 1) >> 1, py2, pz2);
+    const double x1 = (col1 ? I1 : I0)[i1];
+    const double x2 = (col1 ? I0 : I1)[i2];
+    gphi[(1 - col1) * COL + L::fidx(f, a, bb)] = (rc0[f] * Bpre[f] + rc1[f] * x1) + rc2[f] * x2;
+  }
+}
+
 template <int NC, int BPC, int KS, int MINB>
 __global__ void __launch_bounds__(BPC* KS* NC* NC / 2, MINB) k_gsrb2(DevCtx cx, int slot0, int nbox, int C, int lvl) {
   pdl_wait();
@@ -868,36 +1010,53 @@ __global__ void __launch_bounds__(256) k_resid_gen(DevCtx cx, const int* list, i
 // follows correct_children in the cycle (m_af_multigrid.f90:222, :171): boundary layers of both
 // colours are pushed to the neighbours, rule faces are recomputed (epilogue_faces); edges / corners
 // are done by k_edges_corners afterwards.
+// TPB threads work on one child box and a CTA of 256 threads holds 256 / TPB of them (16^3 boxes: one, with the
+// register-sliding prolongation below; 8^3 boxes: four groups of 64 threads, which also take the sliding path --
+// with 256 threads per 8^3 box they had fallen to the generic one and needed 6.6 waves of CTAs on the finest level of
+// a streamer tree).  cslot0 = first child of the block, nhere = how many of them exist.
+template <int NC>
+struct Correct3Cfg {
+  static constexpr int TPB = (NC == 16) ? 256 : 64;
+  static constexpr int BPC = 256 / TPB;
+  static constexpr int W = NC / 2 + 2;
+  static constexpr int SB = 2 * Lay3<NC>::NI + W * W * W;  // smem doubles per box: I0[NI], I1[NI], sub[W^3]
+};
+
 template <int NC, bool LDG>
-__device__ __forceinline__ void correct3_box(const DevCtx& cx, int cslot, int push, double* smem, uint64_t* bar,
+__device__ __forceinline__ void correct3_box(const DevCtx& cx, int cslot0, int nhere, int push, double* smem, uint64_t* bar,
                                              uint32_t& par) {
   using L = Lay3<NC>;
   constexpr int H = L::H, W = H + 2, NI = L::NI, COL = L::COL, BOX = L::BOX;
-  // smem: I0[NI], I1[NI], sub[W^3]
-  double* I0 = smem;
-  double* I1 = smem + NI;
-  double* sub = smem + 2 * NI;
+  constexpr int TPB = Correct3Cfg<NC>::TPB, BPC = Correct3Cfg<NC>::BPC, SB = Correct3Cfg<NC>::SB;
+  const int g = threadIdx.x / TPB, t = threadIdx.x % TPB;
+  const bool active = g < nhere;
+  const int cslot = cslot0 + (active ? g : 0);
+  double* I0 = smem + (size_t)g * SB;
+  double* I1 = I0 + NI;
+  double* sub = I0 + 2 * NI;
   // cslot: child box (this rank's); its parent may live on a peer GPU
   const int slot = cx.parent[cslot], ch = cx.coff[cslot];
-  const int t = threadIdx.x;
   double* cphi = cx.cc[V_PHI] + (size_t)cslot * BOX;
-  if (t == 0) {
-    mbar_expect_tx(bar, 2 * NI * 8);
-    bulk_g2s(I0, cphi, NI * 8, bar);
-    bulk_g2s(I1, cphi + COL, NI * 8, bar);
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, (uint32_t)(nhere * 2 * NI * 8));
+    for (int q = 0; q < nhere; ++q) {
+      double* cq = cx.cc[V_PHI] + (size_t)(cslot0 + q) * BOX;
+      bulk_g2s(smem + (size_t)q * SB, cq, NI * 8, bar);
+      bulk_g2s(smem + (size_t)q * SB + NI, cq + COL, NI * 8, bar);
+    }
   }
   const double* phi = cx.at<BOX>(V_PHI, slot);
   const double* tmp = cx.at<BOX>(V_TMP, slot);
   const int ox = (ch & 1) * H, oy = ((ch >> 1) & 1) * H, oz = ((ch >> 2) & 1) * H;
-  __shared__ FaceMeta fmeta;
-  if (push && t < 6) prefetch_face_meta(cx, cslot, &fmeta, t);
-  {
+  __shared__ FaceMeta fmeta[BPC];
+  if (push && active && t < 6) prefetch_face_meta(cx, cslot, &fmeta[g], t);
+  if (active) {
     // all loads of the window are issued before the first use (one round trip instead of NW)
-    constexpr int NW = (W * W * W + 255) / 256;
+    constexpr int NW = (W * W * W + TPB - 1) / TPB;
     double pv[NW], tv[NW];
 #pragma unroll
     for (int u = 0; u < NW; ++u) {
-      const int n = t + u * 256;
+      const int n = t + u * TPB;
       if (n < W * W * W) {
         const int a = n % W, b = (n / W) % W, c = n / (W * W);
         const int q = L::cell(ox + a, oy + b, oz + c);
@@ -907,7 +1066,7 @@ __device__ __forceinline__ void correct3_box(const DevCtx& cx, int cslot, int pu
     }
 #pragma unroll
     for (int u = 0; u < NW; ++u) {
-      const int n = t + u * 256;
+      const int n = t + u * TPB;
       if (n < W * W * W) sub[n] = pv[u] - tv[u];
     }
   }
@@ -923,9 +1082,9 @@ __device__ __forceinline__ void correct3_box(const DevCtx& cx, int cslot, int pu
   for (int q = 0; q < 8; ++q) pc[q] = (pkind == 3 || (pkind == 2 && q >= 4)) ? 0.0 : pv[q];
   const int pshape = (pkind == 0) ? cx.pshape : (pkind == 1 ? 8 : 4);
   constexpr int TPBX = H * NC;  // threads per k-range
-  constexpr int KSX = (256 / TPBX < NC) ? 256 / TPBX : NC;
+  constexpr int KSX = (TPB / TPBX < NC) ? TPB / TPBX : NC;
   constexpr int KLX = NC / KSX;
-  if (t < TPBX * KSX && pkind == 0 && pshape == 8 && (KLX % 2) == 0) {
+  if (active && t < TPBX * KSX && pkind == 0 && pshape == 8 && (KLX % 2) == 0) {
     // Default stencil_prolong_248 (m_af_stencil.f90:766-813), the common case.  A thread owns the cell pair
     // i = 2m+1, 2m+2 of row j and walks k: the 3 x 2 x 3 coarse values it needs per fine k-pair stay in
     // registers and slide along k (6 LDS per k-pair instead of 32); the coefficients are the literals of
@@ -980,7 +1139,7 @@ __device__ __forceinline__ void correct3_box(const DevCtx& cx, int cslot, int pu
           B[r][x] = C[r][x];
         }
     }
-  } else if (t < TPBX * KSX) {
+  } else if (active && t < TPBX * KSX) {
     const int m = t % H, j = (t / H) % NC + 1, ks = t / TPBX;
     const int j1 = (j + 1) >> 1, j2 = j1 + 1 - 2 * (j & 1);
 #pragma unroll
@@ -1024,12 +1183,12 @@ __device__ __forceinline__ void correct3_box(const DevCtx& cx, int cslot, int pu
   }
   fence_async_smem();
   __syncthreads();
-  if (t == 0) {
+  if (active && t == 0) {
     bulk_s2g(cphi, I0, NI * 8);
     bulk_s2g(cphi + COL, I1, NI * 8);
   }
-  if (push) epilogue_faces<NC, 256>(cx, cslot, I0, I1, 3, t, &fmeta);
-  if (t == 0) {
+  if (push && active) epilogue_faces<NC, TPB>(cx, cslot, I0, I1, 3, t, &fmeta[g]);
+  if (active && t == 0) {
     bulk_commit();
     bulk_wait_read0();
   }
@@ -1043,7 +1202,9 @@ __global__ void __launch_bounds__(256, 4) k_correct3(DevCtx cx, int slot0, int n
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
   uint32_t par = 0;
-  correct3_box<NC, true>(cx, slot0 + blockIdx.x, push, smem, &bar, par);
+  constexpr int BPC = Correct3Cfg<NC>::BPC;
+  const int b0 = blockIdx.x * BPC;
+  correct3_box<NC, true>(cx, slot0 + b0, min(BPC, nbox - b0), push, smem, &bar, par);
 }
 
 template <int NC>

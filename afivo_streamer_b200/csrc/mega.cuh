@@ -82,7 +82,7 @@ struct MegaCfg {
   static constexpr size_t smem_bytes(int coarse_cells) {
     size_t a = (size_t)GS_BPC * (Lay3<NC>::COL + Lay3<NC>::NI);
     const size_t b = (size_t)RES_PER * 2 * Lay3<NC>::COL;
-    const size_t c = (size_t)2 * Lay3<NC>::NI + W * W * W;
+    const size_t c = (size_t)Correct3Cfg<NC>::BPC * Correct3Cfg<NC>::SB;
     const size_t d = (size_t)2 * coarse_cells;
     a = a > b ? a : b;
     a = a > c ? a : c;
@@ -201,7 +201,10 @@ __device__ __forceinline__ void mega_run_op(const DevCtx& cx, const CoarseCtx& c
       cs_scatter_cell<NC>(cx, cs, op.n, op.a3 ? cs.v1 : cs.v0, v * M::THREADS + tid);
       break;
     case MK_CORRECT:
-      correct3_box<NC, false>(cx, op.s0 + v, op.a0, smem, bar, par);
+    {
+      constexpr int CB = Correct3Cfg<NC>::BPC;
+      correct3_box<NC, false>(cx, op.s0 + v * CB, min(CB, op.n - v * CB), op.a0, smem, bar, par);
+    }
       break;
     case MK_STORE_CORR: {
       const int slot = op.s0 + v;
