@@ -213,6 +213,7 @@ struct afmg_handle {
   bool mega_enabled = false;     // opt-in (AFMG_MEGA=1 / afmg_set_mega): measured slower than the graph of launches, see mega.cuh
   int mega_max_boxes = 0;        // levels with at most this many boxes run inside k_mega (0: default per n_cell)
   int mega_grid = 0;             // co-resident CTAs of k_mega on this device
+  int mega_cluster = 0;          // > 0: k_mega runs as ONE thread-block cluster of this many CTAs (hardware barrier)
   size_t mega_smem = 0;
   int mega_mode = 0;             // 0 off, 1 plan (record phases, launch nothing), 2 exec (launch recorded programs)
   bool mega_open = false;        // a segment is being recorded / waiting to be launched
@@ -529,29 +530,41 @@ void mega_flush(afmg_handle* h) {
     h->stamps_used += pr.nphase + 1;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(std::min(h->mega_grid, max_nvb));
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = h->mega_smem;
   cfg.stream = h->stream;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident, or the launch waits: the grid barrier cannot deadlock
-  attr[0].val.cooperative = 1;
+  const int cluster = h->mega_cluster;
+  if (cluster > 0) {  // the grid is one cluster: co-scheduled by construction, hardware barrier between the phases
+    int g = 1;
+    while (g < cluster && g < max_nvb) g *= 2;
+    cfg.gridDim = dim3(g);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = g;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+  } else {
+    cfg.gridDim = dim3(std::min(h->mega_grid, max_nvb));
+    attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident, or the launch waits: the grid barrier cannot deadlock
+    attr[0].val.cooperative = 1;
+  }
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   h->mega_launched = true;
   if (h->o.n_cell == 16)
     cudaLaunchKernelEx(&cfg, k_mega<16>, h->cx, h->cs, (const MegaPhase*)pr.d_phases, (const MegaOp*)pr.d_ops, pr.nphase,
-                       h->d_msync, h->d_scal, h->mega_timeout_ns, stamps);
+                       h->d_msync, h->d_scal, h->mega_timeout_ns, stamps, cluster > 0 ? 1 : 0);
   else
     cudaLaunchKernelEx(&cfg, k_mega<8>, h->cx, h->cs, (const MegaPhase*)pr.d_phases, (const MegaOp*)pr.d_ops, pr.nphase,
-                       h->d_msync, h->d_scal, h->mega_timeout_ns, stamps);
+                       h->d_msync, h->d_scal, h->mega_timeout_ns, stamps, cluster > 0 ? 1 : 0);
 }
 
 // true: the operation (on a level of `nboxes` boxes) belongs to the persistent-kernel segment -- the caller records it
 // (plan pass) or skips it (exec pass); false: it takes the launch path, after the open segment has been closed
 inline bool mega_route(afmg_handle* h, int nboxes, bool ok = true) {
   if (h->mega_mode == 0) return false;
-  const int lim = h->mega_max_boxes > 0 ? h->mega_max_boxes : (h->o.n_cell == 16 ? 1024 : 8192);
+  int lim = h->mega_max_boxes > 0 ? h->mega_max_boxes : (h->o.n_cell == 16 ? 1024 : 8192);
+  if (h->mega_cluster > 0 && h->mega_max_boxes <= 0) lim = h->mega_cluster * mega_items(h, MK_GSRB);  // one pass per phase
   if (ok && nboxes <= lim) {
     h->mega_open = true;
     return true;
@@ -936,6 +949,11 @@ void configure_kernels(afmg_handle* h) {
   if (const char* env = getenv("AFMG_MEGA_GRID")) {
     const int g = atoi(env);
     if (g > 0 && g < h->mega_grid) h->mega_grid = g;
+  }
+  if (h->mega_cluster > 8) {  // more than 8 CTAs per cluster is opt-in on the function
+    cudaError_t e = (h->o.n_cell == 16) ? cudaFuncSetAttribute(k_mega<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)
+                                        : cudaFuncSetAttribute(k_mega<8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) h->mega_cluster = 8;
   }
   cudaGetLastError();
 }
@@ -2320,6 +2338,7 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
   if (const char* env = getenv("AFMG_MIN_SPLIT_BOXES")) h->min_split_boxes = atoi(env);
   if (const char* env = getenv("AFMG_MEGA")) h->mega_enabled = atoi(env) != 0;
   if (const char* env = getenv("AFMG_MEGA_MAX_BOXES")) h->mega_max_boxes = atoi(env);
+  if (const char* env = getenv("AFMG_MEGA_CLUSTER")) h->mega_cluster = std::max(0, std::min(16, atoi(env)));
   if (const char* env = getenv("AFMG_MEGA_TIMEOUT_S")) {
     const double sec = atof(env);
     if (sec > 0) h->mega_timeout_ns = (unsigned long long)(sec * 1e9);

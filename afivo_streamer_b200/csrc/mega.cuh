@@ -140,6 +140,17 @@ __device__ __forceinline__ void mega_grid_barrier(MegaSync* sync, unsigned long 
   __syncthreads();
 }
 
+// The same phase boundary when the whole grid is ONE thread-block cluster (<= 16 CTAs: the levels of at most a few
+// dozen boxes at the bottom of a cycle): the hardware cluster barrier with release / acquire semantics, executed by
+// every thread -- no atomics, no polling, no __syncthreads pair around it.  Cluster scope covers the global-memory
+// writes of the CTAs of the cluster; the bulk stores have been waited for by their issuing threads as above.
+__device__ __forceinline__ void mega_cluster_barrier() {
+  asm volatile(
+      "barrier.cluster.arrive.release.aligned;\n"
+      "barrier.cluster.wait.acquire.aligned;\n" ::
+          : "memory");
+}
+
 template <int NC>
 __device__ __forceinline__ void mega_run_op(const DevCtx& cx, const CoarseCtx& cs, const MegaOp& op, int v, double* smem,
                                             uint64_t* bar, uint32_t& par, unsigned long long* scal) {
@@ -255,7 +266,8 @@ constexpr int MEGA_MAX_OPS = 4;  // operations per phase (the host never records
 template <int NC>
 __global__ void __launch_bounds__(MegaCfg<NC>::THREADS, MegaCfg<NC>::MINB)
     k_mega(DevCtx cx, CoarseCtx cs, const MegaPhase* __restrict__ phases, const MegaOp* __restrict__ ops, int nphase,
-           MegaSync* sync, unsigned long long* scal, unsigned long long timeout_ns, unsigned long long* stamps) {
+           MegaSync* sync, unsigned long long* scal, unsigned long long timeout_ns, unsigned long long* stamps,
+           int cluster) {
   extern __shared__ __align__(128) double smem[];
   __shared__ uint64_t bar;
   __shared__ unsigned long long s_base;
@@ -274,7 +286,7 @@ __global__ void __launch_bounds__(MegaCfg<NC>::THREADS, MegaCfg<NC>::MINB)
   };
   if (tid == 0) {
     mbar_init(&bar, 1);
-    s_base = ld_acquire_gpu(&sync->base);
+    s_base = cluster ? 0ull : ld_acquire_gpu(&sync->base);
     if (stamps && blockIdx.x == 0) stamps[0] = globaltimer_ns();
   }
   fetch(0);
@@ -299,11 +311,12 @@ __global__ void __launch_bounds__(MegaCfg<NC>::THREADS, MegaCfg<NC>::MINB)
       __syncthreads();
     }
     target += gridDim.x;
-    mega_grid_barrier(sync, target, timeout_ns);
+    if (cluster) mega_cluster_barrier();
+    else mega_grid_barrier(sync, target, timeout_ns);
     if (stamps && blockIdx.x == 0 && tid == 0) stamps[p + 1] = globaltimer_ns();
   }
   // every CTA has read `base` before it arrived at the first barrier, and the last barrier above is complete
-  if (blockIdx.x == 0 && tid == 0 && nphase > 0) sync->base = target;
+  if (!cluster && blockIdx.x == 0 && tid == 0 && nphase > 0) sync->base = target;
 }
 
 }  // namespace afmg

@@ -40,17 +40,21 @@ def pytest_collection_modifyitems(config, items):
 
 # ---- the two execution paths of the 3D cycles (csrc/mega.cuh): the persistent kernel with grid barriers ("mega": every
 # level inside it), the launch path ("launch": one kernel per operation, as in round 1) and their mixture ("hybrid":
-# only levels of at most 8 boxes inside the persistent kernel, so segments open and close within a cycle).  The
-# bit-exact suites run under all three; the handle reads the environment at afmg_create.
+# only levels of at most 8 boxes inside the persistent kernel, so segments open and close within a cycle) and the
+# cluster variant ("cluster": the bottom levels in one thread-block cluster with the hardware cluster barrier; once with
+# the default level limit, once with every level inside so that CTAs loop over several blocks per phase).  The
+# bit-exact suites run under all of them; the handle reads the environment at afmg_create.
 PATH_MODULES = {"test_gpu_kernels", "test_gpu_cycles", "test_golden"}
 PATH_ENV = {"mega": {"AFMG_MEGA": "1", "AFMG_MEGA_MAX_BOXES": "1000000"},
             "launch": {"AFMG_MEGA": "0"},
-            "hybrid": {"AFMG_MEGA": "1", "AFMG_MEGA_MAX_BOXES": "8"}}
+            "hybrid": {"AFMG_MEGA": "1", "AFMG_MEGA_MAX_BOXES": "8"},
+            "cluster": {"AFMG_MEGA": "1", "AFMG_MEGA_CLUSTER": "16"},
+            "cluster_all": {"AFMG_MEGA": "1", "AFMG_MEGA_CLUSTER": "8", "AFMG_MEGA_MAX_BOXES": "1000000"}}
 
 
 @pytest.fixture
 def afmg_path(request):
-    old = {k: os.environ.get(k) for k in ("AFMG_MEGA", "AFMG_MEGA_MAX_BOXES")}
+    old = {k: os.environ.get(k) for k in ("AFMG_MEGA", "AFMG_MEGA_MAX_BOXES", "AFMG_MEGA_CLUSTER")}
     for k in old:
         os.environ.pop(k, None)
     os.environ.update(PATH_ENV[request.param])
