@@ -151,6 +151,7 @@ struct afmg_handle {
   cudaStream_t side_stream = nullptr;  // the generic-stencil kernels of a level run beside the fast ones (fork / join)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t launch_stream = nullptr;  // where launch_k puts the next kernel (the solver stream unless forked)
+  int side_priority = 0;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   int* d_stage_slots = nullptr;
   size_t stage_slots_n = 0;
@@ -191,6 +192,7 @@ struct afmg_handle {
   std::vector<unsigned char> h_owner;
   std::vector<char> lvl_multi;   // [L+2] 1: boxes of the level are owned by more than one rank
   bool unsynced = false;         // operations ran since the last cross-GPU barrier (all of them on rank 0's levels)
+  int barrier_lean = 1;          // AFMG_BARRIER_LEAN=0: the round-1 barrier with explicit system fences around the release
   int min_split_boxes = -1;      // levels with fewer boxes stay on rank 0 (-1: 4 Mi cells worth of boxes)
   unsigned char* d_owner = nullptr;
   CommBlock* d_comm = nullptr;
@@ -387,11 +389,20 @@ void launch_k(afmg_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = h->launch_stream ? h->launch_stream : h->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (h->pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (h->launch_stream) {  // side-stream kernels keep their priority as nodes of a captured graph
+    attr[na].id = cudaLaunchAttributePriority;
+    attr[na].val.priority = h->side_priority;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = h->pdl ? 1 : 0;
+  cfg.numAttrs = na;
   cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
 
@@ -608,7 +619,7 @@ void enq_barrier(afmg_handle* h, bool multi = true) {
     return;
   }
   Launch L_(h, "barrier");
-  launch_k(h, k_barrier, 1, 32, 0, h->d_comm, h->peers, h->nranks, h->me, h->barrier_timeout_ns);
+  launch_k(h, k_barrier, 1, 32, 0, h->d_comm, h->peers, h->nranks, h->me, h->barrier_timeout_ns, h->barrier_lean);
   h->unsynced = false;
 }
 inline void pre_sync(afmg_handle* h, bool multi = true) {
@@ -670,6 +681,22 @@ bool gsrb_one_wave(afmg_handle* h, int blocks, int s0, int n, int C, int l) {
   return false;
 }
 
+// the fast half-sweep kernel for `n` slots from `s0` on level l (boxes with explicit stencils are skipped by it)
+void launch_gsrb_range(afmg_handle* h, int l, int s0, int n, int C) {
+  DISPATCH_NC(h, NC, {
+    using G = Gsrb2Cfg<NC>;
+    constexpr int threads = G::BPC * G::KS * NC * NC / 2;
+    const size_t smem = (size_t)G::BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double);
+    const int blocks = (n + G::BPC - 1) / G::BPC;
+    // latency-bound launch: the variant with plain loads / stores (k_gsrb2s); a launch just above one wave of
+    // resident CTAs: half as many CTAs with twice the boxes each (one wave instead of two)
+    if (!gsrb_small<NC>(h, blocks, threads, smem, s0, n, C, l) && !gsrb_one_wave<NC>(h, blocks, s0, n, C, l)) {
+      auto kern = k_gsrb2<NC, G::BPC, G::KS, G::MINB>;
+      launch_k(h, kern, blocks, threads, smem, h->cx, s0, n, C, l);
+    }
+  });
+}
+
 // Every enq_* below works on the slots of a level this rank owns and ends with a cross-GPU barrier
 // when its results are read, or its inputs overwritten, by kernels of other ranks.
 void enq_gsrb(afmg_handle* h, int l, int redblack) {
@@ -695,19 +722,7 @@ void enq_gsrb(afmg_handle* h, int l, int redblack) {
   SideLaunch side(h, r.n > 0 && nspec(h, l) > 0);
   if (r.n > 0) {
     Launch L_(h, "gsrb", l);
-    DISPATCH_NC(h, NC, {
-      using G = Gsrb2Cfg<NC>;
-      constexpr int threads = G::BPC * G::KS * NC * NC / 2;
-      const size_t smem = (size_t)G::BPC * (Lay3<NC>::COL + Lay3<NC>::NI) * sizeof(double);
-      const int blocks = (r.n + G::BPC - 1) / G::BPC;
-      // latency-bound launch: the variant with plain loads / stores (k_gsrb2s); a launch just above one wave of
-      // resident CTAs: half as many CTAs with twice the boxes each (one wave instead of two)
-      if (!gsrb_small<NC>(h, blocks, threads, smem, r.s0, r.n, redblack & 1, l) &&
-          !gsrb_one_wave<NC>(h, blocks, r.s0, r.n, redblack & 1, l)) {
-        auto kern = k_gsrb2<NC, G::BPC, G::KS, G::MINB>;
-        launch_k(h, kern, blocks, threads, smem, h->cx, r.s0, r.n, redblack & 1, l);
-      }
-    });
+    launch_gsrb_range(h, l, r.s0, r.n, redblack & 1);
   }
   if (const int ns = nspec(h, l)) {  // boxes with an explicit stencil (skipped by the kernel above)
     side.begin();
@@ -2311,7 +2326,14 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) {
+    // highest priority: a kernel of the side stream (a cross-GPU barrier next to a long half-sweep) must get its CTA
+    // before the thousands of pending CTAs of the kernel it runs beside
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    h->side_priority = greatest;
+    e = cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, greatest);
+  }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
@@ -2336,6 +2358,7 @@ int afmg_create(afmg_handle** out, const afmg_opts* opts) {
   cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device);
   if (const char* env = getenv("AFMG_GSRB_FUSED_GEN")) h->gsrb_fused_gen = atoi(env) != 0;
   if (const char* env = getenv("AFMG_MIN_SPLIT_BOXES")) h->min_split_boxes = atoi(env);
+  if (const char* env = getenv("AFMG_BARRIER_LEAN")) h->barrier_lean = atoi(env);
   if (const char* env = getenv("AFMG_MEGA")) h->mega_enabled = atoi(env) != 0;
   if (const char* env = getenv("AFMG_MEGA_MAX_BOXES")) h->mega_max_boxes = atoi(env);
   if (const char* env = getenv("AFMG_MEGA_CLUSTER")) h->mega_cluster = std::max(0, std::min(16, atoi(env)));
@@ -2459,6 +2482,14 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
   h->lvl_off[1] = 0;
   h->id2slot.assign(N + 1, -1);
   h->slot2id.assign(total, 0);
+  // ownership: contiguous Morton ranges per level, cut at sibling groups (afmg_partition); depends on the box
+  // counts only
+  std::vector<int> rel((size_t)L * (h->nranks + 1));
+  {
+    int min_split = h->min_split_boxes;
+    if (min_split < 0) min_split = (4 << 20) / (h->o.n_cell * h->o.n_cell * h->o.n_cell);  // 4 Mi cells
+    afmg_partition_min(h->nranks, L, t->lvl_counts, min_split, rel.data());
+  }
   // slots: level 1 in list order, finer levels in Morton order of ix-1
   {
     int p = 0;
@@ -2598,10 +2629,6 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
 
   // ownership: contiguous Morton ranges per level, cut at sibling groups (afmg_partition)
   {
-    std::vector<int> rel((size_t)L * (h->nranks + 1));
-    int min_split = h->min_split_boxes;
-    if (min_split < 0) min_split = (4 << 20) / (h->o.n_cell * h->o.n_cell * h->o.n_cell);  // 4 Mi cells
-    afmg_partition_min(h->nranks, L, t->lvl_counts, min_split, rel.data());
     h->cut.assign((size_t)(L + 2) * (h->nranks + 1), 0);
     h->rb_cut.assign((size_t)(L + 2) * (h->nranks + 1), 0);
     h->h_owner.assign(total, 0);

@@ -154,7 +154,10 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-__global__ void k_barrier(CommBlock* mine, CommPeers peers, int nranks, int me, unsigned long long timeout_ns) {
+// lean (the default): the release store IS the system-scope fence (it is cumulative over the writes of the preceding
+// kernels, which happen before this one in stream order), and the acquire polls order the peers' writes before the
+// kernels that follow; the explicit fences of the first version (lean = 0) cost several microseconds per barrier.
+__global__ void k_barrier(CommBlock* mine, CommPeers peers, int nranks, int me, unsigned long long timeout_ns, int lean) {
   pdl_wait();
   __shared__ unsigned long long ep;
   const int t = threadIdx.x;
@@ -165,19 +168,23 @@ __global__ void k_barrier(CommBlock* mine, CommPeers peers, int nranks, int me, 
   __syncthreads();
   const unsigned long long e = ep;
   if (t < nranks && t != me) {
-    __threadfence_system();
+    if (!lean) __threadfence_system();
     st_release_sys(&peers.p[t]->flags[me], e);
-    if (ld_acquire_sys(&mine->err) == 0) {
-      const unsigned long long t0 = globaltimer_ns();
+    if (lean ? (mine->err == 0) : (ld_acquire_sys(&mine->err) == 0)) {
+      unsigned long long t0 = 0;
+      unsigned spins = 0;
       while (ld_acquire_sys(&mine->flags[t]) < e) {
-        if (globaltimer_ns() - t0 > timeout_ns) {
+        if (lean && (++spins & 63u)) continue;
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > timeout_ns) {
           mine->err = 1;
           break;
         }
       }
     }
   }
-  __threadfence_system();
+  if (!lean) __threadfence_system();
 }
 
 // scal[4 + idx] = max over ranks of scal[idx] (after a barrier); non-negative doubles order like uint64
