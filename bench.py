@@ -364,6 +364,10 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
+    # page-locked buffers next to the GPU: bind this process to the GPU's NUMA node before anything is allocated
+    # (no-op on a single-node host such as the B200 boxes of this pool, profiles/r02r_pcie_probe_n8.txt)
+    from afivo_streamer_b200 import numa
+    numa_node = numa.bind_to_gpu_node(local)
     comm = None
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
@@ -731,6 +735,7 @@ def run_gpu(args):
             "barrier": barrier_stat,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                     "steps": e2e_steps, "ms_per_step": 1e3 * wall_max / e2e_steps, "phases_max_over_ranks": e2e_parts,
+                    "host_numa_node_bound": numa_node,
                     "what": "upload rhs (interior, leaves) -> V-cycle -> residual max-norm -> download phi (interior, "
                             "leaves); pinned host buffers, blocking C-ABI calls"},
             "shim_sequence": shim,
