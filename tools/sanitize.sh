@@ -16,3 +16,8 @@ timeout 900 $CS --tool memcheck --error-exitcode 86 --print-limit 20 python -m p
   > gpurun_out/sanitizer_memcheck_stencils.log 2>&1
 echo "memcheck (stencils) exit code $?" >> gpurun_out/sanitizer_memcheck_stencils.log
 grep -E "ERROR SUMMARY|passed|failed|exit code" gpurun_out/sanitizer_memcheck_stencils.log | tail -3
+# the kernels the large nc = 8 levels take (one-wave half-sweep, four boxes per CTA in the prolongation) on S2 at full size
+timeout 900 $CS --tool memcheck --error-exitcode 86 --print-limit 20 python -m pytest tests/test_gpu_fullsize.py -k "s2" -m gpu -q -x -p no:cacheprovider \
+  > gpurun_out/sanitizer_memcheck_s2.log 2>&1
+echo "memcheck (S2) exit code $?" >> gpurun_out/sanitizer_memcheck_s2.log
+grep -E "ERROR SUMMARY|passed|failed|exit code" gpurun_out/sanitizer_memcheck_s2.log | tail -3
