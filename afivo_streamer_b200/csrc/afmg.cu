@@ -152,6 +152,8 @@ struct afmg_handle {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t launch_stream = nullptr;  // where launch_k puts the next kernel (the solver stream unless forked)
   int side_priority = 0;
+  int grad_grid = 0;             // CTAs of the persistent gradient kernel k_grad3p (field.cuh); 0: not available
+  bool grad_simple = false;      // AFMG_GRAD_SIMPLE=1: one box per CTA (k_grad3) for every box
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   int* d_stage_slots = nullptr;
   size_t stage_slots_n = 0;

@@ -42,13 +42,14 @@ struct Fc3 {
 // (rows of nc+1 / nc consecutive doubles).  Boundary faces of variable-eps boxes (:1938-1997) read eps from
 // global memory (few boxes).
 template <int NC>
-__global__ void __launch_bounds__(256) k_grad3(DevCtx cx, FieldCtx fx, int slot0, int nbox, int with_norm) {
+__global__ void __launch_bounds__(256) k_grad3(DevCtx cx, FieldCtx fx, int slot0, int nbox, int with_norm, int only_veps) {
   using L = Lay3<NC>;
   using F = Fc3<NC>;
   constexpr int BOX = L::BOX, N1 = NC + 1, N2 = NC + 2;
   extern __shared__ __align__(16) double P[];  // N2^3, natural order (i fastest); edges / corners unused
   const int slot = slot0 + blockIdx.x;
   const int t = threadIdx.x;
+  if (only_veps && !(fx.veps && fx.veps[slot])) return;  // the other boxes have been done by k_grad3p
   const double* phi = cx.cc[V_PHI] + (size_t)slot * BOX;
   for (int n = t; n < NC * NC * NC; n += 256) {
     const int i = n % NC + 1, j = (n / NC) % NC + 1, k = n / (NC * NC) + 1;
@@ -131,6 +132,130 @@ __global__ void __launch_bounds__(256) k_grad3(DevCtx cx, FieldCtx fx, int slot0
     zm = c;
     c = zp;
     Pc += N2 * N2;
+  }
+}
+
+// k_grad3p: the same operation as k_grad3 for the boxes WITHOUT eps-weighted boundary faces (all boxes of a tree
+// without dielectrics), organised for bandwidth: this kernel moves 45 B per cell (8 (nc+2)^3 / nc^3 read, 3 fc
+// components and the norm written) and is the second-largest consumer of a time step after the multigrid cycles.
+//   * persistent CTAs (as many as are resident), boxes taken grid-stride;
+//   * the record's two colour blocks arrive by ONE TMA bulk copy (2 COL doubles), and the copy of the NEXT box is
+//     issued as soon as the current one has been unpacked into the natural-order array P, so loads overlap the
+//     arithmetic and the stores of the current box;
+//   * the fc record is written in its own linear order, consecutive threads -> consecutive doubles over the whole
+//     component (entries outside a component's range are the zeros af_init_box left there, m_af_core.f90:555), and
+//     the norm in the linear order of its colour blocks: every store instruction covers whole 32-byte sectors.
+// Same expressions as k_grad3 (face value = inv_dr * (hi - lo); norm = 0.5 sqrt(a^2 + b^2 + c^2)): identical bits.
+template <int NC>
+struct Grad3Cfg {
+  static constexpr int THREADS = (NC == 16) ? 512 : 128;
+  static constexpr size_t SMEM = ((size_t)2 * Lay3<NC>::COL + (size_t)(NC + 2) * (NC + 2) * (NC + 2)) * sizeof(double);
+};
+
+template <int NC>
+__global__ void __launch_bounds__(Grad3Cfg<NC>::THREADS) k_grad3p(DevCtx cx, FieldCtx fx, int slot0, int nbox, int with_norm) {
+  using L = Lay3<NC>;
+  using F = Fc3<NC>;
+  constexpr int THREADS = Grad3Cfg<NC>::THREADS;
+  constexpr int BOX = L::BOX, COL = L::COL, NI = L::NI, NF = L::NF, H = L::H, N1 = NC + 1, N2 = NC + 2, PER = F::PER;
+  constexpr int NIT = (PER + THREADS - 1) / THREADS;  // fc entries of one component per thread
+  constexpr int CIT = NI / THREADS;                   // interior cells of one colour per thread
+  constexpr int KSTEP = THREADS / (H * NC);           // k advances by this much from one of them to the next
+  static_assert(NI % THREADS == 0 && THREADS % (H * NC) == 0 && KSTEP % 2 == 0, "cell <-> thread map of the interior");
+  extern __shared__ __align__(128) double smem[];
+  double* const raw = smem;          // the record's colour blocks as they lie in global memory
+  double* const P = smem + 2 * COL;  // N2^3, natural order (i fastest); edges / corners unused
+  __shared__ uint64_t bar;
+  const int t = threadIdx.x;
+  if (t == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  // ---- index maps, the same for every box: computed once, kept in registers (the loops below are fully unrolled).
+  // fc entry n = t + it * THREADS of a component <-> cell (i, j, k) of the (nc+1)^3 record: offset of P(i, j, k) and,
+  // per component, whether the entry exists (bit it + 10 d)
+  int cidx[NIT];
+  unsigned vmask = 0;
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int n = t + it * THREADS;
+    const int i = n % N1 + 1, r = n / N1, j = r % N1 + 1, k = r / N1 + 1;
+    cidx[it] = (k * N2 + j) * N2 + i;
+    if (n < PER) {
+      if (j <= NC && k <= NC) vmask |= 1u << it;
+      if (i <= NC && k <= NC) vmask |= 1u << (it + 10);
+      if (i <= NC && j <= NC) vmask |= 1u << (it + 20);
+    }
+  }
+  static_assert(NIT <= 10, "validity bits");
+  // interior cell r = t + it * THREADS of colour block c: (m, j) fixed, k = k0 + KSTEP * it, and since KSTEP is even
+  // the x index depends on the colour only
+  const int cm = t % H, cj = (t / H) % NC + 1, ck0 = t / (H * NC) + 1;
+  const int pbase0 = (ck0 * N2 + cj) * N2 + 2 * cm + 2 - ((0 + cj + ck0) & 1);
+  const int pbase1 = (ck0 * N2 + cj) * N2 + 2 * cm + 2 - ((1 + cj + ck0) & 1);
+  const double* const phi = cx.cc[V_PHI];
+  int b = blockIdx.x;
+  if (t == 0 && b < nbox) {
+    mbar_expect_tx(&bar, (uint32_t)(2 * COL * 8));
+    bulk_g2s(raw, phi + (size_t)(slot0 + b) * BOX, 2 * COL * 8, &bar);
+  }
+  uint32_t par = 0;
+  for (; b < nbox; b += gridDim.x) {
+    const int slot = slot0 + b;
+    const bool veps = fx.veps && fx.veps[slot];
+    const int lv = cx.lvl[slot];
+    const double idr0 = fx.inv_dr[lv][0], idr1 = fx.inv_dr[lv][1], idr2 = fx.inv_dr[lv][2];
+    mbar_wait(&bar, par);
+    par ^= 1u;
+    // ---- unpack: interior of both colours, then the six ghost faces of both colours
+#pragma unroll
+    for (int it = 0; it < CIT; ++it) {
+      P[pbase0 + it * KSTEP * N2 * N2] = raw[t + it * THREADS];
+      P[pbase1 + it * KSTEP * N2 * N2] = raw[COL + t + it * THREADS];
+    }
+    for (int n = t; n < 12 * NF; n += THREADS) {
+      const int c = n / (6 * NF), r = n - c * 6 * NF;
+      int i, j, k;
+      L::uncell(c * COL + NI + r, i, j, k);
+      P[(k * N2 + j) * N2 + i] = raw[c * COL + NI + r];
+    }
+    __syncthreads();
+    const int nb = b + gridDim.x;
+    if (t == 0 && nb < nbox) {  // raw is free: fetch the next record while this one is worked on
+      fence_async_smem();
+      mbar_expect_tx(&bar, (uint32_t)(2 * COL * 8));
+      bulk_g2s(raw, phi + (size_t)(slot0 + nb) * BOX, 2 * COL * 8, &bar);
+    }
+    if (!veps) {
+      double* const fcb = fx.fc + (size_t)slot * F::LEN + t;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double idr = (d == 0) ? idr0 : (d == 1 ? idr1 : idr2);
+        const int st = (d == 0) ? 1 : (d == 1 ? N2 : N2 * N2);
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          if (it * THREADS + t >= PER) break;  // only the last iteration can be partial
+          double v = 0.0;
+          if ((vmask >> (it + 10 * d)) & 1u) v = idr * (P[cidx[it]] - P[cidx[it] - st]);
+          fcb[d * PER + it * THREADS] = v;
+        }
+      }
+      if (with_norm) {
+        double* const out = fx.fld + (size_t)slot * BOX + t;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int it = 0; it < CIT; ++it) {
+            const double* Pc = P + (c ? pbase1 : pbase0) + it * KSTEP * N2 * N2;
+            const double ctr = Pc[0];
+            const double fxl = idr0 * (ctr - Pc[-1]), fxh = idr0 * (Pc[1] - ctr);
+            const double fyl = idr1 * (ctr - Pc[-N2]), fyh = idr1 * (Pc[N2] - ctr);
+            const double fzl = idr2 * (ctr - Pc[-N2 * N2]), fzh = idr2 * (Pc[N2 * N2] - ctr);
+            const double a = fxl + fxh, bb = fyl + fyh, cc = fzl + fzh;
+            out[c * COL + it * THREADS] = 0.5 * sqrt(a * a + bb * bb + cc * cc);
+          }
+        }
+      }
+    }
+    __syncthreads();  // P is rewritten by the next box
   }
 }
 
