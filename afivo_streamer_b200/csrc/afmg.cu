@@ -1278,7 +1278,9 @@ void close_peers(afmg_handle* h) {
 
 void mega_resolve_stamps(afmg_handle* h);
 
+void fs_drop_graph(afmg_handle* h);  // afmg_field.inc
 void drop_graphs(afmg_handle* h) {
+  fs_drop_graph(h);
   for (auto& kv : h->graphs) {
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     free_programs(kv.second.progs);
