@@ -323,43 +323,25 @@ __global__ void __launch_bounds__(256) k_lsf_fix3(DevCtx cx, FieldCtx fx, const 
 template <int NC>
 __global__ void __launch_bounds__(256) k_gc_fld3(DevCtx cx, FieldCtx fx, int slot0, int nbox, int corners) {
   using L = Lay3<NC>;
-  constexpr int H = L::H, NI = L::NI, NF = L::NF, COL = L::COL;
+  constexpr int H = L::H;
   const int slot = slot0 + blockIdx.x;
   double* box = cx.cc[V_FLD] + (size_t)slot * L::BOX;
   const double third = 1 / 3.0, sixth = 1 / 6.0;
-  for (int f = 0; f < 6; ++f) {
+  for (int n = threadIdx.x; n < 6 * L::NC2; n += blockDim.x) {
+    const int f = n / L::NC2, rr = n % L::NC2;
+    const int a = rr % NC + 1, b = rr / NC + 1;
     const int d = f >> 1, hi = f & 1;
-    const int nb = cx.nbr[slot * 6 + f];
-    if (nb >= 0) {
-      // copy_from_nb: the neighbour's boundary layer has the colours and the (b, a/2) order of the ghost face, so
-      // both colour segments of the face are filled by index arithmetic only (z faces: two contiguous copies)
-      const double* src = cx.at<L::BOX>(V_FLD, nb);
-      const int layer = hi ? 1 : NC;
-      for (int n = threadIdx.x; n < 2 * NF; n += blockDim.x) {
-        const int c = n / NF, r = n - c * NF;
-        const int ah = r % H, b = r / H + 1;
-        int idx;
-        if (d == 0) {
-          const int g = hi ? NC + 1 : 0;
-          const int a = 2 * ah + 2 - ((c + g + b) & 1);
-          idx = ((b - 1) * NC + (a - 1)) * H + ((layer - 1) >> 1);
-        } else if (d == 1) {
-          idx = ((b - 1) * NC + (layer - 1)) * H + ah;
-        } else {
-          idx = ((layer - 1) * NC + (b - 1)) * H + ah;
-        }
-        box[c * COL + NI + f * NF + r] = src[c * COL + idx];
-      }
-      continue;
-    }
     const int ta = (d == 0) ? 1 : 0, tb = (d == 2) ? 1 : 2;
-    const int row = cx.aux[slot * 6 + f];
-    for (int rr = threadIdx.x; rr < L::NC2; rr += blockDim.x) {
-      const int a = rr % NC + 1, b = rr / NC + 1;
-      int q[3];
-      q[ta] = a;
-      q[tb] = b;
-      double v;
+    int q[3];
+    q[ta] = a;
+    q[tb] = b;
+    const int nb = cx.nbr[slot * 6 + f];
+    double v;
+    if (nb >= 0) {
+      q[d] = hi ? 1 : NC;
+      v = ldcell<NC>(cx.at<L::BOX>(V_FLD, nb), q[0], q[1], q[2]);
+    } else {
+      const int row = cx.aux[slot * 6 + f];
       if (row < cx.rb_row0) {  // physical boundary: bc_to_gc
         const double* rc = fx.bc_c + 3 * row;
         const double B = fx.bc_B[(size_t)row * L::NC2 + rr];
@@ -389,8 +371,8 @@ __global__ void __launch_bounds__(256) k_gc_fld3(DevCtx cx, FieldCtx fx, int slo
         v = (d == 2) ? (third * v11 + sixth * v12 + sixth * v21 + third * vf)
                      : (third * v11 + sixth * v21 + sixth * v12 + third * vf);
       }
-      box[L::face(f, a, b)] = v;
     }
+    box[L::face(f, a, b)] = v;
   }
   if (corners) {
     __syncthreads();
