@@ -143,6 +143,7 @@ struct afmg_handle {
   int *d_nbr = nullptr, *d_aux = nullptr, *d_nmat = nullptr, *d_parent = nullptr, *d_child0 = nullptr,
       *d_coff = nullptr, *d_lvl = nullptr, *d_rb_slot = nullptr, *d_rb_face = nullptr;
   double *d_coef = nullptr, *d_rule_c = nullptr, *d_rule_B = nullptr, *d_pcoef = nullptr;
+  std::vector<double> h_bc_B, h_bc_c;  // host mirrors of the physical-boundary rows of rule_B / rule_c (afmg_set_bc)
   unsigned long long* d_scal = nullptr;  // [0] fused residual max, [1] generic max, [2] mean (double bits)
   double* d_boxsum = nullptr;
   double* d_stage = nullptr;  // two halves: chunk c uses half c & 1 (copy of c + 1 overlaps the kernel of c)
@@ -2622,6 +2623,8 @@ int afmg_set_tree(afmg_handle* h, const afmg_tree* t) {
   if ((rc = dev_upload(h, &h->d_rule_c, rule_c))) return rc;
   std::vector<double> rule_B((size_t)std::max(nrules, 1) * h->nc2, 0.0);
   if ((rc = dev_upload(h, &h->d_rule_B, rule_B))) return rc;
+  h->h_bc_B.assign((size_t)h->nbc * h->nc2, 0.0);  // what the device rows hold now
+  h->h_bc_c.assign((size_t)h->nbc * 3, 0.0);
   // one slab per rank: phi | rhs | tmp | box sums (a single CUDA IPC handle covers all of it)
   close_peers(h);
   slab_free(h);
@@ -2721,20 +2724,27 @@ int afmg_set_bc(afmg_handle* h, int32_t n_faces, const int32_t* box_id, const in
   CK(cudaStreamSynchronize(h->stream));
   if (h->o.ndim == 2) return s2_set_bc(h, n_faces, box_id, nb, bc_type, bc_val);
   const int nc2 = h->nc2;
-  std::vector<double> rc3((size_t)3);
   bool types_changed = false;
-  // stage into host mirrors then upload row by row (rows are few: physical faces only)
-  std::vector<double> rows((size_t)n_faces * nc2), coefs((size_t)n_faces * 3);
-  std::vector<int> rowidx(n_faces);
-  for (int q = 0; q < n_faces; ++q) {
+  // The rows go into the host mirrors of the physical-boundary part of rule_B / rule_c, and the touched range of
+  // rows goes up in ONE copy each: the call precedes every solve (the applied voltage changes with time,
+  // src/m_field.f90:590-610), and a copy per face -- the faces arrive in the caller's order, not in row order -- cost
+  // 3 ms on a streamer-like tree, five V-cycles' worth.
+  for (int q = 0; q < n_faces; ++q) {  // all arguments are checked before anything changes
     const int id = box_id[q], f = nb[q] - 1;
     if (id < 1 || id > h->highest_id || h->id2slot[id] < 0) return h->fail(AFMG_ERR_ARG, "afmg_set_bc: unknown box %d", id);
     if (f < 0 || f > 5) return h->fail(AFMG_ERR_ARG, "afmg_set_bc: invalid neighbour direction %d", nb[q]);
     const int s = h->id2slot[id];
     if (h->h_nbr[(size_t)s * 6 + f] != -1 || h->h_aux[(size_t)s * 6 + f] >= h->nbc)
       return h->fail(AFMG_ERR_ARG, "afmg_set_bc: box %d face %d is not a physical boundary", id, nb[q]);
+    if (bc_type[q] != AFMG_BC_DIRICHLET && bc_type[q] != AFMG_BC_NEUMANN && bc_type[q] != AFMG_BC_CONTINUOUS &&
+        bc_type[q] != AFMG_BC_DIRICHLET_COPY)
+      return h->fail(AFMG_ERR_ARG, "afmg_set_bc: unknown boundary condition %d", bc_type[q]);
+  }
+  int rmin = h->nbc, rmax = -1;
+  for (int q = 0; q < n_faces; ++q) {
+    const int f = nb[q] - 1, s = h->id2slot[box_id[q]];
     const int r = h->h_aux[(size_t)s * 6 + f];
-    double c0, c1, c2;
+    double c0 = 0, c1 = 0, c2 = 0;
     switch (bc_type[q]) {  // bc_to_gc (m_af_ghostcell.f90:192-214)
       case AFMG_BC_DIRICHLET: c0 = 2; c1 = -1; c2 = 0; break;
       case AFMG_BC_NEUMANN:
@@ -2743,28 +2753,22 @@ int afmg_set_bc(afmg_handle* h, int32_t n_faces, const int32_t* box_id, const in
         c2 = 0;
         break;
       case AFMG_BC_CONTINUOUS: c0 = 0; c1 = 2; c2 = -1; break;
-      case AFMG_BC_DIRICHLET_COPY: c0 = 1; c1 = 0; c2 = 0; break;
-      default: return h->fail(AFMG_ERR_ARG, "afmg_set_bc: unknown boundary condition %d", bc_type[q]);
+      default: c0 = 1; c1 = 0; c2 = 0; break;  // AFMG_BC_DIRICHLET_COPY
     }
     if (!h->bc_set[r] || h->h_bc_type[r] != bc_type[q]) types_changed = true;
     h->bc_set[r] = 1;
     h->h_bc_type[r] = bc_type[q];
-    rowidx[q] = r;
-    coefs[(size_t)q * 3 + 0] = c0;
-    coefs[(size_t)q * 3 + 1] = c1;
-    coefs[(size_t)q * 3 + 2] = c2;
-    std::memcpy(&rows[(size_t)q * nc2], bc_val + (size_t)q * nc2, nc2 * sizeof(double));
+    h->h_bc_c[(size_t)r * 3 + 0] = c0;
+    h->h_bc_c[(size_t)r * 3 + 1] = c1;
+    h->h_bc_c[(size_t)r * 3 + 2] = c2;
+    std::memcpy(&h->h_bc_B[(size_t)r * nc2], bc_val + (size_t)q * nc2, nc2 * sizeof(double));
+    rmin = std::min(rmin, r);
+    rmax = std::max(rmax, r);
   }
-  // coalesce contiguous runs of rows into few memcpys
-  int q = 0;
-  while (q < n_faces) {
-    int e = q + 1;
-    while (e < n_faces && rowidx[e] == rowidx[e - 1] + 1) ++e;
-    CK(cudaMemcpy(h->d_rule_B + (size_t)rowidx[q] * nc2, &rows[(size_t)q * nc2], (size_t)(e - q) * nc2 * sizeof(double),
-                  cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_rule_c + (size_t)rowidx[q] * 3, &coefs[(size_t)q * 3], (size_t)(e - q) * 3 * sizeof(double),
-                  cudaMemcpyHostToDevice));
-    q = e;
+  if (rmax >= rmin) {
+    const size_t nr = (size_t)(rmax - rmin + 1);
+    CK(cudaMemcpy(h->d_rule_B + (size_t)rmin * nc2, &h->h_bc_B[(size_t)rmin * nc2], nr * nc2 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_rule_c + (size_t)rmin * 3, &h->h_bc_c[(size_t)rmin * 3], nr * 3 * sizeof(double), cudaMemcpyHostToDevice));
   }
   if (types_changed) h->cs_ready = false;
   return AFMG_OK;
