@@ -13,6 +13,7 @@
 #include <functional>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "afmg.h"
@@ -104,6 +105,7 @@ struct mg_t {
   sides_bc_t sides_bc;
   sides_bc_coords_t sides_bc_coords;  // takes precedence over sides_bc when set
   int device = -1;
+  int n_gpus = 0;  // > 1: this many GPUs of the node from ONE process (afmg_opts.n_gpus; 3D)
   bool initialized = false;
   afmg_handle* h = nullptr;
 
@@ -131,6 +133,18 @@ struct mg_t {
   void get_cc(int var, const std::vector<int32_t>& ids, double* packed) {
     need_init();
     check(afmg_download(h, var, (int32_t)ids.size(), ids.data(), packed), "afmg_download");
+  }
+  // interior cells only, nc^ndim doubles per box (what a caller that fills ghost cells itself needs)
+  void get_cc_interior(int var, const std::vector<int32_t>& ids, double* packed) {
+    need_init();
+    check(afmg_download_interior(h, var, (int32_t)ids.size(), ids.data(), packed), "afmg_download_interior");
+  }
+  // wrapping sum / xor of the bit patterns of a variable over all boxes: equal for bit-identical solves
+  std::pair<uint64_t, uint64_t> checksum(int var) {
+    need_init();
+    uint64_t a = 0, b = 0;
+    check(afmg_checksum(h, var, &a, &b), "afmg_checksum");
+    return {a, b};
   }
   // per-face boundary rows: ids, nb (1..2*ndim), types, values (nc^(ndim-1) each)
   void set_bc(const std::vector<int32_t>& ids, const std::vector<int32_t>& nb, const std::vector<int32_t>& types,
@@ -200,6 +214,7 @@ inline void mg_init(const af_t& tree, mg_t& mg) {
   o.prolongation_type = mg.prolongation_type;
   o.operator_mask = mg.operator_mask;
   o.device = mg.device;
+  o.n_gpus = mg.n_gpus;
   o.helmholtz_lambda = mg.helmholtz_lambda;
   o.lsf_boundary_value = mg.lsf_boundary_value;
   for (int d = 0; d < 3; ++d) {
@@ -404,6 +419,27 @@ inline stencil_set_t mg_set_operators_tree(const af_t& tree, mg_t& mg, const dou
 }
 
 // af_tree_maxabs_cc (m_af_utils.f90:773-785): max |cc| over the interior of the leaves
+// field_set_rhs (src/m_field.f90:406-444) on the device: cc(:, i_rhs) = sum_n charges[n] * densities[n] on the listed
+// leaves, in the reference's order.  densities[n] = packed records ((nc+2)^ndim doubles per box, list order) in host
+// memory, or in device memory with on_device.
+inline void field_set_rhs(const af_t&, mg_t& mg, const std::vector<int32_t>& leaf_ids, const std::vector<double>& charges,
+                          const std::vector<const double*>& densities, bool on_device = false) {
+  mg.need_init();
+  if (charges.size() != densities.size()) throw error(AFMG_ERR_ARG, "field_set_rhs: one density array per charge");
+  mg.check(afmg_field_set_rhs(mg.h, (int32_t)leaf_ids.size(), leaf_ids.data(), (int32_t)charges.size(), charges.data(),
+                              densities.data(), on_device ? 1 : 0),
+           "afmg_field_set_rhs");
+}
+
+// mg_set_operators_tree with the stencils built ON THE DEVICE from the resident permittivity (AFMG_EPS, if the caller
+// uploaded one) and a built-in electrode shape: nothing but the topology travels after a refinement.  Single-GPU
+// handles, 3D.
+inline void mg_set_operators_tree_device(const af_t&, mg_t& mg, const afmg_electrode* electrode = nullptr,
+                                         const afmg_lsf_opts* lsf_opts = nullptr) {
+  mg.need_init();
+  mg.check(afmg_build_stencils_device(mg.h, electrode, lsf_opts), "afmg_build_stencils_device");
+}
+
 inline double af_tree_maxabs_cc(const af_t&, mg_t& mg, int var) {
   mg.need_init();
   double v = 0.0;
